@@ -1,0 +1,283 @@
+/*
+ * mimpy_b200 -- C-ABI of the B200-native MFD hot path (libmimpy_b200.so).
+ *
+ * Drop-in boundary: these entry points replace, one for one, the reference's native operator
+ * boundary (its three Cython modules) and the Python hot loops of mimpy.mfd.MFD /
+ * mimpy.models.TwoPhase that sit directly above it.  File:line citations are relative to the
+ * reference tree (ohinai/mimpy).  INTEGRATION.md shows the ctypes stubs a mimpy maintainer
+ * would add at the cited call sites.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (MIMPY_E_*); the message for the last
+ *     error on the calling thread is returned by mimpy_b200_last_error().
+ *   - all array arguments are DEVICE pointers unless the name ends in _host; the caller owns
+ *     every buffer, nothing is retained beyond the call (the reference natives have the same
+ *     contract: caller-owned, in-place, mfd_cython.pyx:6-10, mesh_cython.pyx:5-17).
+ *   - work is enqueued on the context's stream; functions that return sizes synchronise.
+ *   - indices are int32 (reference: array('i') / np.dtype('i'), mfd.py:557-558), values are
+ *     FP64, orientations are int8 (+1/-1).
+ *   - one host thread per context.
+ */
+#ifndef MIMPY_B200_H
+#define MIMPY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIMPY_OK 0
+#define MIMPY_E_INVALID (-1) /* bad argument                               */
+#define MIMPY_E_CUDA (-2)    /* a CUDA runtime call failed                 */
+#define MIMPY_E_UNSUPPORTED (-3)
+#define MIMPY_E_NOCONV (-4)  /* solver hit maxit before reaching tolerance */
+#define MIMPY_E_NCCL (-5)
+
+#define MIMPY_MAX_CELL_FACES 32 /* one warp lane per face of a cell */
+
+typedef struct mimpy_ctx mimpy_ctx;
+
+int mimpy_b200_version(void);
+const char* mimpy_b200_last_error(void);
+/* stream: a cudaStream_t (may be NULL = legacy default stream). */
+int mimpy_b200_create(int device, void* stream, mimpy_ctx** out);
+int mimpy_b200_destroy(mimpy_ctx* ctx);
+int mimpy_b200_set_stream(mimpy_ctx* ctx, void* stream);
+int mimpy_b200_sync(mimpy_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------
+ * SoA mesh view (device).  face_geom is the packed per-face record
+ *   [area, n_x, n_y, n_z, x_f, y_f, z_f, 0]   (8 doubles = 64 B = two 32-B sectors)
+ * gathered once per (cell, face) by the M_E kernels.  cell_* arrays keep the reference's own
+ * layouts (mesh.py:246-255: cell_volume[nc], cell_real_centroid[nc,3], cell_k[nc,9]).
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t nc;
+  int32_t nf;
+  int32_t max_faces;          /* max faces per cell (<= MIMPY_MAX_CELL_FACES)             */
+  int32_t uniform_faces;      /* >0: every cell has exactly this many faces (hex: 6)      */
+  const int32_t* cell_ptr;    /* nc+1 offsets into cell_faces / cell_sigma                */
+  const int32_t* cell_faces;  /* global face ids, reference order (mesh.py:1034-1042)     */
+  const int8_t* cell_sigma;   /* cell_normal_orientation (mesh.py:1044-1056)              */
+  const double* face_geom;    /* nf*8                                                     */
+  const double* cell_k;       /* nc*9 row-major (mesh.py:1163-1173)                       */
+  const double* cell_centroid;/* nc*3 (real, or shifted when the mesh uses shifted ones)  */
+  const double* cell_volume;  /* nc                                                       */
+} mimpy_mesh_view;
+
+/* -- (0) G2: structured hex topology ----------------------------------------------------------
+ * replaces the Python loops of HexMesh.build_mesh / _build_faces (hexmesh.py:161-234, 269-350):
+ * points (i dx, j dy, k dz), the interleaved z/y/x face numbering, face point lists, cells
+ * [z-,y-,x-,x+,y+,z+] with orientations [-1,-1,-1,1,1,1].  Any output may be NULL.
+ * Sizes: points 3*(cx+1)(cy+1)(cz+1); face_points 4*nf; cell_faces/cell_sigma 6*cx*cy*cz. */
+int mimpy_b200_hex_topology(mimpy_ctx* ctx, int32_t cx, int32_t cy, int32_t cz, double dx, double dy,
+                            double dz, double* points, int32_t* face_points, int32_t* cell_faces,
+                            int8_t* cell_sigma);
+
+/* -- (1) G3-G5: quad face geometry ----------------------------------------------------------
+ * replaces hexmesh_cython.all_face_areas (hexmesh_cython.pyx:30-89), all_face_normals
+ * (hexmesh_cython.pyx:91-118) and HexMesh._populate_face_centroids (hexmesh.py:68-74).
+ * Any of the four outputs may be NULL. */
+int mimpy_b200_geom_hex_faces(mimpy_ctx* ctx, int32_t nf, const int32_t* face_points /*nf*4*/,
+                              const double* points /*np*3*/, double* face_areas /*nf*/,
+                              double* face_normals /*nf*3*/, double* face_centroids /*nf*3*/,
+                              double* face_geom /*nf*8*/);
+
+/* pack separately stored face arrays (any polygonal mesh) into face_geom */
+int mimpy_b200_face_pack(mimpy_ctx* ctx, int32_t nf, const double* face_areas,
+                         const double* face_normals, const double* face_centroids,
+                         double* face_geom);
+
+/* -- (2) G6: Mirtich cell volumes and centroids ---------------------------------------------
+ * replaces mesh_cython.all_cell_volumes_centroids (mesh_cython.pyx:5-207), caller
+ * Mesh.find_volume_centroid_all (mesh.py:1758-1781).  Gather form: one lane per (cell, face),
+ * no scatter, outputs need not be pre-zeroed.  face_ptr: nf+1 offsets into face_points. */
+int mimpy_b200_geom_cells(mimpy_ctx* ctx, int32_t nc, int32_t max_faces, const int32_t* cell_ptr,
+                          const int32_t* cell_faces, const int8_t* cell_sigma,
+                          const int32_t* face_ptr, const int32_t* face_points,
+                          const double* points, const double* face_normals /*nf*3*/,
+                          double* cell_volume /*nc*/, double* cell_centroid /*nc*3*/);
+
+/* -- (3) L1-L4: batched local inner-product matrices ------------------------------------------
+ * replaces MFD.build_r_e / build_n_e / build_c_e / build_m_e (mfd.py:248-483), methods 0..7
+ * (MFD.set_m_e_construction_method, mfd.py:131-139).  m_ptr[c] = offset of the row-major
+ * n_E x n_E block of cell c in m_e (m_ptr[nc] = sum n_E^2).
+ * flags: bit0 k_unity (mfd.py:300-304, 367-369).
+ * face_real_centroids / cell_real_centroids: only read by methods 2 and 6 when the mesh view
+ * carries SHIFTED centroids (mfd.py:398-399, 451-452 always use the real ones); may be NULL.
+ * diagonality (nc, nullable): ||M_E - diag||_F / ||M_E||_F          (mfd.py:476-478)
+ * consistency (nc, nullable): ||M_E N_E - R_E||_F                    (mfd.py:472-474)      */
+int mimpy_b200_mfd_local_matrices(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int32_t method,
+                                  int32_t flags, const int32_t* m_ptr, double* m_e,
+                                  double* diagonality, double* consistency);
+
+/* -- (4) A1-A5: symbolic assembly ------------------------------------------------------------
+ * Everything index-valued that MFD.renumber_for_neumann (mfd.py:141-159), build_m (545-599),
+ * build_div (203-246), build_bottom_right (745-774) and coo_matrix(...).tocsr() (906-908)
+ * decide, computed once per (mesh, Neumann set):
+ *
+ *   face_to_flux[nf+1] g(f) = f - #Neumann faces before f, -1 on Neumann faces; [nf] = flux_dof
+ *   face_cell[nf*2]    the <=2 cells that list face f, lower cell index first, -1 = none
+ *                      (derived from the cell lists; Mesh.face_to_cell is not reliable after
+ *                      divide_cell_by_plane, mesh.py:2405-2410)
+ *   indptr/indices     sorted CSR pattern of the saddle matrix [M -DIV^T; DIV C],
+ *                      size (flux_dof+nc)^2; M keeps its full STRUCTURAL pattern (the
+ *                      reference's 1e-20 value filter, mfd.py:582, only removes exact zeros)
+ *   m_indptr/m_indices CSR pattern of the M block alone (= pattern of the hybridised system)
+ *   m_ptr[nc+1]        offsets of the per-cell n_E^2 blocks
+ *   pos_m[sum n_E^2]   uint8: offset of entry (i,j) of cell c inside row g(f_i) (0xFF = dropped:
+ *                      i or j Neumann); same offset in the saddle CSR and in the M-only CSR
+ *   pos_dt[sum n_E]    uint8: offset of the -DIV^T entry (g(f_i), flux_dof+c) inside its row
+ *   pos_d[sum n_E]     uint8: offset of the DIV entry (flux_dof+c, g(f_i)) inside its row
+ *   diag_pos[nf]       uint8: offset of the diagonal entry inside flux row g (first flux_dof used)
+ *
+ * Two calls because sizes are data dependent: _sizes fills face_to_flux, face_cell, m_ptr,
+ * indptr, m_indptr and returns flux_dof / nnz / nnz_m (synchronises); the caller allocates
+ * indices, m_indices; _fill writes them and the pos_* maps.                               */
+typedef struct {
+  int32_t flux_dof;
+  int64_t nnz;      /* saddle matrix                */
+  int64_t nnz_m;    /* M block / hybridised system  */
+  int64_t n_blocks; /* sum n_E^2                    */
+  int32_t* face_to_flux;
+  int32_t* face_cell;
+  int32_t* indptr;    /* nf+nc+1 allocated, flux_dof+nc+1 used */
+  int32_t* indices;   /* nnz                                   */
+  int32_t* m_indptr;  /* nf+1 allocated, flux_dof+1 used       */
+  int32_t* m_indices; /* nnz_m                                 */
+  int32_t* m_ptr;     /* nc+1                                  */
+  uint8_t* pos_m;     /* n_blocks                              */
+  uint8_t* pos_dt;    /* cell_ptr[nc]                          */
+  uint8_t* pos_d;     /* cell_ptr[nc]                          */
+  uint8_t* diag_pos;  /* nf                                    */
+} mimpy_symbolic;
+
+int mimpy_b200_mfd_symbolic_sizes(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,
+                                  const uint8_t* neumann_mask /*nf, 1 = Neumann*/,
+                                  mimpy_symbolic* sym);
+int mimpy_b200_mfd_symbolic_fill(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, mimpy_symbolic* sym);
+
+/* -- (5) A2-A5 + A8: numeric assembly (fused with the M_E construction) ------------------------
+ * vals[nnz] of the saddle CSR in one pass over the cells: per cell the n_E^2 block is built
+ * in registers/shared memory and scattered straight into its CSR slots
+ *   M[g(i),g(j)] += s_i s_j mult[c] M_E[i,j]      (mfd.py:575-588; mult: update_m,
+ *                                                  mfd.py:729-743 / mfd_cython.pyx:6-22)
+ *   A[F+c, g(i)] = s_i a_i ; A[g(i), F+c] = -s_i a_i            (mfd.py:232-243)
+ *   A[F+c, F+c]  = c_diag ? c_diag[c] : alpha * vol(c)          (mfd.py:766-772, twophase.py:783)
+ * Every slot has <= 2 contributors (the two cells of a face), so the sum is order-free and
+ * bit-reproducible.  multipliers / c_diag / m_e_out may be NULL.  m_e_out receives the
+ * UNSCALED blocks (what the reference keeps in m_data_for_update, mfd.py:593-595).       */
+int mimpy_b200_mfd_numeric(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
+                           int32_t method, int32_t flags, const double* multipliers, double alpha,
+                           const double* c_diag, double* vals, double* m_e_out);
+
+/* same scatter from already built blocks (m_e, layout of (3)); used when M_E comes from the
+ * caller (e.g. mesh-dependent user construction) */
+int mimpy_b200_mfd_numeric_from_blocks(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,
+                                       const mimpy_symbolic* sym, const double* m_e,
+                                       const double* multipliers, double alpha,
+                                       const double* c_diag, double* vals);
+
+/* COO view of the M block in the reference's own order (cell-major, row-major inside the cell,
+ * Neumann rows/cols skipped; mfd.py:575-588): coo_ptr[nc+1] = m_e_locations (mfd.py:590-595),
+ * and optionally rows/cols/vals of each triple.  Any output may be NULL. */
+int mimpy_b200_mfd_coo(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
+                       const double* m_e, int64_t* coo_ptr, int32_t* rows, int32_t* cols,
+                       double* vals);
+
+/* -- (6) A6: right-hand side -------------------------------------------------------------------
+ * replaces MFD.build_rhs (mfd.py:991-1041, 1209-1215): rhs = 0; Neumann rhs[g(f)] = value with
+ * g = -1, i.e. rhs[last] = value of the LAST Neumann face in insertion order (reference quirk,
+ * mfd.py:1041 with mfd.py:153); Dirichlet rhs[g(f)] = -value; forcing rhs[F+c] += F_c.     */
+int mimpy_b200_mfd_rhs(mimpy_ctx* ctx, int32_t nc, int32_t flux_dof, const int32_t* face_to_flux,
+                       int32_t n_dirichlet, const int32_t* dirichlet_faces,
+                       const double* dirichlet_values, int32_t has_neumann,
+                       double last_neumann_value, const double* forcing /*nc, nullable*/,
+                       double* rhs /*flux_dof+nc*/);
+
+/* -- (7) S1: linear solve -----------------------------------------------------------------------
+ * replaces MFD.solve('spsolve') (mfd.py:1349-1358) for the saddle system
+ *     M v - DIV^T p = b_v ,  DIV v + C p = b_p
+ * by exact algebraic hybridisation (face multipliers lambda, one per flux DOF) followed by
+ * Jacobi-preconditioned CG on the SPD face system  A lambda = h  (pattern = m_indptr/m_indices)
+ * and cell-local recovery of [v ; p] in the reference's DOF order.
+ *
+ * hybrid_setup : per cell W_E = (masked, scaled M_E)^-1, A_E = a W a - r c^T / S scattered into
+ *                a_vals[nnz_m]; boundary (single-cell) flux DOFs become identity rows/cols;
+ *                w_e (n_blocks) keeps W_E for rhs/recovery; a_diag_inv[flux_dof] = 1/diag(A).
+ * hybrid_rhs   : h[flux_dof] for given saddle rhs (b = [b_v ; b_p]); boundary rows carry the
+ *                prescribed multiplier.
+ * pcg          : solves A x = h; x holds the initial guess on entry.
+ * hybrid_recover: solution[flux_dof+nc] = [v ; p] from lambda.                              */
+int mimpy_b200_hybrid_setup(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
+                            const double* m_e, const double* multipliers, double alpha,
+                            const double* c_diag, double* w_e, double* a_vals, double* a_diag_inv);
+int mimpy_b200_hybrid_rhs(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
+                          const double* w_e, double alpha, const double* c_diag,
+                          const double* rhs /*flux_dof+nc*/, double* cell_tmp /*cell_ptr[nc]*/,
+                          double* h /*flux_dof*/);
+int mimpy_b200_hybrid_recover(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,
+                              const mimpy_symbolic* sym, const double* w_e, double alpha,
+                              const double* c_diag, const double* rhs, const double* lambda,
+                              double* solution /*flux_dof+nc*/);
+
+typedef struct {
+  double rtol;          /* stop when ||r||_2 <= rtol * ||h||_2                        */
+  double atol;          /* ... or ||r||_2 <= atol                                      */
+  int32_t maxit;
+  int32_t check_every;  /* host looks at the residual every this many iterations       */
+  int32_t use_graph;    /* 1: replay each block of check_every iterations as a graph   */
+  /* outputs */
+  int32_t iterations;
+  double residual;      /* final ||r||_2 (recurrence)                                  */
+  double rhs_norm;
+  float ms_total;       /* device time of the whole solve (CUDA events)               */
+} mimpy_pcg_info;
+
+/* work: 4*n doubles (r, p, Ap, spare) */
+int mimpy_b200_pcg(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, const int32_t* indices,
+                   const double* vals, const double* diag_inv, const double* b, double* x,
+                   double* work, mimpy_pcg_info* info);
+
+/* y = A x for a CSR matrix with int32 indices (the solver's SpMV, exposed for tests/bench) */
+int mimpy_b200_spmv(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, const int32_t* indices,
+                    const double* vals, const double* x, double* y);
+
+/* -- (8)(9) T2, T4, T5: two-phase saturation transport -----------------------------------------
+ * upwind: upwind_cell[g] = the cell c with sigma_{c,f} * u_t[g(f)] > 0, -1 if none, INCLUDING
+ * the reference quirk that Neumann faces test u_t[-1] and may overwrite the entry of the last
+ * flux DOF (twophase.py:928-958).
+ * saturation_step: f_w (persistent, twophase.py:957, 968-971) refreshed on the upwinded DOFs,
+ * boundary inflow DOFs set from bnd_fw where sigma_b*u_t < 0 (twophase.py:974-994), then
+ *   s_w <- (1+c_w p_prev)/(1+c_w p) s_w - dt div(f_w u_t)/(phi rho_w (1+c_w p) vol) + wells
+ * (twophase.py:996-1092).  Corey relperm with clipping (twophase.py:268-344).              */
+typedef struct {
+  double mu_w, mu_o, rho_w, rho_o, c_w, c_o, s_wr, s_or, n_w, n_o, k_rw_o;
+} mimpy_fluid;
+
+int mimpy_b200_twophase_mobility(mimpy_ctx* ctx, int32_t nc, const mimpy_fluid* fluid_host,
+                                 const double* s_w, const double* p, double* inv_total_mobility,
+                                 double* water_mob, double* oil_mob);
+int mimpy_b200_twophase_upwind(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,
+                               const mimpy_symbolic* sym, const double* u_t,
+                               int32_t* upwind_cell /*flux_dof*/);
+int mimpy_b200_twophase_saturation_step(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,
+                                        const mimpy_symbolic* sym, const mimpy_fluid* fluid_host,
+                                        double dt, const int32_t* upwind_cell, const double* u_t,
+                                        const double* p, const double* p_prev,
+                                        const double* porosity, int32_t n_bnd,
+                                        const int32_t* bnd_faces, const int8_t* bnd_sigma,
+                                        const double* bnd_fw, int32_t n_rate_wells,
+                                        const int32_t* well_cells, const double* well_rate_water,
+                                        double* f_w /*flux_dof, in/out*/, double* s_w /*nc, in/out*/);
+
+/* -- (10) multi-GPU: slab partition helpers (see mimpy_b200/partition.py) ------------------------
+ * attaches an NCCL communicator (ncclComm_t created by the caller from an id broadcast with
+ * torch.distributed) used by pcg for the dot-product all-reduce and the halo exchange. */
+int mimpy_b200_set_comm(mimpy_ctx* ctx, void* nccl_comm, int32_t rank, int32_t world);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIMPY_B200_H */

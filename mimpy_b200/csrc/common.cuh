@@ -1,0 +1,106 @@
+// Shared helpers for libmimpy_b200 (sm_100a). FP64 CUDA-core math only: the path works on
+// 3xn / nxn blocks with n = faces per cell (6 for hexes), far too small for tcgen05 tiles.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "mimpy_b200.h"
+
+struct mimpy_ctx {
+  int device;
+  cudaStream_t stream;
+  int sm_count;
+  void* scratch;         // ctx-owned temporary storage (CUB temp, reduction partials)
+  size_t scratch_bytes;
+  double* partials;      // reduction partials (device)
+  unsigned int* counters;  // last-block counters (device)
+  double* scalars;       // device scalars for PCG (alpha, beta, rz, ...)
+  double* host_scalars;  // pinned
+  void* nccl_comm;
+  int rank, world;
+  cudaEvent_t ev0, ev1;
+};
+
+void mimpy_set_error(const char* fmt, ...);
+int mimpy_scratch(mimpy_ctx* ctx, size_t bytes, void** out);
+
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      mimpy_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,                 \
+                      cudaGetErrorString(_e));                                           \
+      return MIMPY_E_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define KERNEL_CHECK() CUDA_TRY(cudaGetLastError())
+
+#define REQUIRE(cond, msg)                                   \
+  do {                                                       \
+    if (!(cond)) {                                           \
+      mimpy_set_error("%s: %s", __func__, msg);              \
+      return MIMPY_E_INVALID;                                \
+    }                                                        \
+  } while (0)
+
+static inline int mimpy_group_size(int max_faces) {
+  if (max_faces <= 8) return 8;
+  if (max_faces <= 16) return 16;
+  return 32;
+}
+
+// ---- small dense helpers (device) -------------------------------------------------------
+__device__ __forceinline__ void inv3(const double a[9], double out[9]) {
+  const double c00 = a[4] * a[8] - a[5] * a[7];
+  const double c01 = a[3] * a[8] - a[5] * a[6];
+  const double c02 = a[3] * a[7] - a[4] * a[6];
+  const double det = a[0] * c00 - a[1] * c01 + a[2] * c02;
+  const double id = 1.0 / det;
+  out[0] = c00 * id;
+  out[1] = (a[2] * a[7] - a[1] * a[8]) * id;
+  out[2] = (a[1] * a[5] - a[2] * a[4]) * id;
+  out[3] = -c01 * id;
+  out[4] = (a[0] * a[8] - a[2] * a[6]) * id;
+  out[5] = (a[2] * a[3] - a[0] * a[5]) * id;
+  out[6] = c02 * id;
+  out[7] = (a[1] * a[6] - a[0] * a[7]) * id;
+  out[8] = (a[0] * a[4] - a[1] * a[3]) * id;
+}
+
+// Cholesky of a symmetric 3x3 given as (g00,g10,g11,g20,g21,g22); returns the inverse
+// diagonal (i0,i1,i2) and the strict lower part (l10,l20,l21) of L.
+struct Chol3 {
+  double i0, i1, i2, l10, l20, l21;
+};
+__device__ __forceinline__ Chol3 chol3(double g00, double g10, double g11, double g20, double g21,
+                                       double g22) {
+  Chol3 c;
+  const double l00 = sqrt(g00);
+  c.i0 = 1.0 / l00;
+  c.l10 = g10 * c.i0;
+  c.l20 = g20 * c.i0;
+  const double l11 = sqrt(g11 - c.l10 * c.l10);
+  c.i1 = 1.0 / l11;
+  c.l21 = (g21 - c.l20 * c.l10) * c.i1;
+  const double l22 = sqrt(g22 - c.l20 * c.l20 - c.l21 * c.l21);
+  c.i2 = 1.0 / l22;
+  return c;
+}
+// solve L q = b in place
+__device__ __forceinline__ void chol3_fwd(const Chol3& c, double& b0, double& b1, double& b2) {
+  b0 = b0 * c.i0;
+  b1 = (b1 - c.l10 * b0) * c.i1;
+  b2 = (b2 - c.l20 * b0 - c.l21 * b1) * c.i2;
+}
+
+// sum over the G lanes of a lane group (G a power of two, groups aligned inside the warp)
+template <int G>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ double ldg_f64(const double* p) { return __ldg(p); }

@@ -1,0 +1,314 @@
+// Exact algebraic hybridisation of the saddle-point system of MFD.build_lhs (mfd.py:851-914)
+//
+//     M v - DIV^T p = b_v ,   DIV v + C p = b_p            (solved by SuperLU in mfd.py:1349-1358)
+//
+// Every flux DOF g(f) gets a multiplier lambda_f.  With u_E = sigma o v|_E (outward fluxes of cell
+// E), a = face areas, W_E = (mult_E M_E restricted to non-Neumann faces)^-1:
+//     u_E = W_E (a p_E - a o lambda_E + sigma o beta_E),   a^T u_E + C_E p_E = b_p[E]
+// (beta carries b_v of interior faces, given to the lower-index cell).  Eliminating u_E, p_E
+// cell by cell leaves the SPD face system  A lambda = h,
+//     A = sum_E P_E^T (a W_E a - r_E c_E^T / S_E) P_E ,  r = (aWa) 1, c = (aWa)^T 1, S = 1^T(aWa)1 + C_E
+// whose pattern is the pattern of M (m_indptr / m_indices).  Boundary flux DOFs (one cell) have
+// lambda prescribed: lambda_f = -sigma b_v / a_f (= the Dirichlet pressure), identity rows in A.
+// The recovered [v ; p] is the solution of the original system (up to the CG tolerance).
+#include "common.cuh"
+
+struct HybArgs {
+  const int* face_to_flux;
+  const int* face_cell;
+  const int* m_indptr;
+  const int* m_ptr;
+  const uint8_t* pos_m;
+  int flux_dof;
+  double alpha;
+  const double* c_diag;
+};
+
+// in-place Gauss-Jordan inverse of the n x n matrix A (shared memory, leading dim G+1), performed
+// by the G lanes of a group, lane j owning column j.  No pivoting: the blocks are SPD.
+template <int G>
+__device__ __forceinline__ void group_invert(double (*A)[G + 1], int n, int j, int nw) {
+  for (int k = 0; k < nw; ++k) {
+    double pinv = 0., akj = 0.;
+    const bool act = (k < n) && (j < n);
+    if (act) {
+      pinv = 1.0 / A[k][k];
+      akj = A[k][j] * pinv;
+    }
+    __syncwarp();
+    if (act && j != k) {
+      for (int i = 0; i < n; ++i) {
+        if (i == k) continue;
+        A[i][j] -= A[i][k] * akj;
+      }
+      A[k][j] = akj;
+    }
+    __syncwarp();
+    if (act && j == k) {
+      for (int i = 0; i < n; ++i) {
+        if (i == k) continue;
+        A[i][k] = -A[i][k] * pinv;
+      }
+      A[k][k] = pinv;
+    }
+    __syncwarp();
+  }
+}
+
+template <int G>
+__device__ __forceinline__ int warp_max_n(int n) {
+  int nw = n;
+#pragma unroll
+  for (int o = 16; o >= G; o >>= 1) nw = max(nw, __shfl_xor_sync(0xffffffffu, nw, o));
+  return nw;
+}
+
+template <int G>
+__global__ void __launch_bounds__(128)
+k_hybrid_setup(mimpy_mesh_view m, HybArgs h, const double* __restrict__ m_e,
+               const double* __restrict__ multipliers, double* __restrict__ w_e,
+               double* __restrict__ a_vals) {
+  constexpr int CPB = 128 / G;
+  __shared__ double As[CPB][G][G + 1];
+  __shared__ double s_a[CPB][G];
+  __shared__ double s_r[CPB][G];
+  __shared__ int s_row[CPB][G];
+  __shared__ int s_flag[CPB][G];  // bit0: dropped (Neumann), bit1: boundary (single cell)
+  const int slot = threadIdx.x / G;
+  const int j = threadIdx.x % G;
+  const int cell = blockIdx.x * CPB + slot;
+  const bool cell_ok = cell < m.nc;
+  const int base = cell_ok ? m.cell_ptr[cell] : 0;
+  const int n = cell_ok ? m.cell_ptr[cell + 1] - base : 0;
+  const bool valid = j < n;
+  const int nw = warp_max_n<G>(n);
+  int gj = -1, flag = 1;
+  double area = 0.;
+  if (valid) {
+    const int f = m.cell_faces[base + j];
+    area = __ldg(m.face_geom + 8 * (size_t)f);
+    gj = h.face_to_flux[f];
+    flag = (gj < 0 ? 1 : 0) | (h.face_cell[2 * (size_t)f + 1] < 0 ? 2 : 0);
+  }
+  s_a[slot][j] = area;
+  s_flag[slot][j] = flag;
+  s_row[slot][j] = gj >= 0 ? h.m_indptr[gj] : -1;
+  __syncwarp();
+  const double mult = (multipliers && cell_ok) ? __ldg(multipliers + cell) : 1.;
+  const int boff = cell_ok ? h.m_ptr[cell] : 0;
+  for (int i = 0; i < n; ++i) {
+    if (valid) {
+      const bool drop = (s_flag[slot][i] & 1) || (flag & 1);
+      As[slot][i][j] = drop ? (i == j ? 1. : 0.) : mult * m_e[boff + (size_t)i * n + j];
+    }
+  }
+  __syncwarp();
+  group_invert<G>(As[slot], n, j, nw);
+  // masked inverse, W stored for rhs / recovery; scaled block aWa in place
+  for (int i = 0; i < n; ++i) {
+    if (valid) {
+      const bool drop = (s_flag[slot][i] & 1) || (flag & 1);
+      const double w = drop ? 0. : As[slot][i][j];
+      w_e[boff + (size_t)i * n + j] = w;
+      As[slot][i][j] = s_a[slot][i] * w * area;
+    }
+  }
+  __syncwarp();
+  double rj = 0., cj = 0.;  // row sum of row j, column sum of column j
+  if (valid) {
+    for (int k = 0; k < n; ++k) {
+      rj += As[slot][j][k];
+      cj += As[slot][k][j];
+    }
+  }
+  s_r[slot][j] = rj;
+  const double cd = cell_ok ? (h.c_diag ? __ldg(h.c_diag + cell) : h.alpha * __ldg(m.cell_volume + cell)) : 0.;
+  const double S = group_sum<G>(cj) + cd;
+  __syncwarp();
+  for (int i = 0; i < n; ++i) {
+    const int rs = s_row[slot][i];
+    if (valid && rs >= 0 && gj >= 0) {
+      const bool bnd = (s_flag[slot][i] & 2) || (flag & 2);
+      double v = As[slot][i][j] - s_r[slot][i] * cj / S;
+      if (bnd) v = (i == j) ? 1. : 0.;
+      const unsigned pos = h.pos_m[boff + (size_t)i * n + j];
+      if (i == j)
+        atomicAdd(a_vals + rs + pos, v);
+      else
+        a_vals[rs + pos] = v;
+    }
+  }
+}
+
+__global__ void k_diag_inv(int F, const int* __restrict__ m_indptr,
+                           const uint8_t* __restrict__ diag_pos, const double* __restrict__ a_vals,
+                           double* __restrict__ dinv) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= F) return;
+  dinv[g] = 1.0 / a_vals[m_indptr[g] + diag_pos[g]];
+}
+
+__global__ void k_zero_diag_m(int F, const int* __restrict__ m_indptr,
+                              const uint8_t* __restrict__ diag_pos, double* __restrict__ vals) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= F) return;
+  vals[m_indptr[g] + diag_pos[g]] = 0.;
+}
+
+// MODE 0: h (face-system right-hand side) ; MODE 1: recover [v ; p] from lambda
+template <int G, int MODE>
+__global__ void __launch_bounds__(128)
+k_hybrid_local(mimpy_mesh_view m, HybArgs h, const double* __restrict__ w_e,
+               const double* __restrict__ rhs, const double* __restrict__ lambda,
+               double* __restrict__ out) {
+  constexpr int CPB = 128 / G;
+  __shared__ double Ws[CPB][G][G + 1];
+  __shared__ double s_a[CPB][G];
+  __shared__ double s_t[CPB][G];
+  const int slot = threadIdx.x / G;
+  const int j = threadIdx.x % G;
+  const int cell = blockIdx.x * CPB + slot;
+  const bool cell_ok = cell < m.nc;
+  const int base = cell_ok ? m.cell_ptr[cell] : 0;
+  const int n = cell_ok ? m.cell_ptr[cell + 1] - base : 0;
+  const bool valid = j < n;
+  const int F = h.flux_dof;
+  int gj = -1;
+  double area = 0., sg = 0., t = 0., lam = 0.;
+  bool bnd = false, owner = false;
+  if (valid) {
+    const int f = m.cell_faces[base + j];
+    sg = (double)m.cell_sigma[base + j];
+    area = __ldg(m.face_geom + 8 * (size_t)f);
+    gj = h.face_to_flux[f];
+    bnd = h.face_cell[2 * (size_t)f + 1] < 0;
+    owner = h.face_cell[2 * (size_t)f] == cell;
+    if (gj >= 0) {
+      const double bv = rhs[gj];
+      double beta = 0.;
+      if (bnd)
+        lam = -sg * bv / area;
+      else {
+        if (MODE == 1) lam = lambda[gj];
+        if (owner) beta = bv;
+      }
+      t = -area * lam + sg * beta;
+    }
+  }
+  s_a[slot][j] = area;
+  s_t[slot][j] = t;
+  const int boff = cell_ok ? h.m_ptr[cell] : 0;
+  for (int i = 0; i < n; ++i)
+    if (valid) Ws[slot][i][j] = w_e[boff + (size_t)i * n + j];
+  __syncwarp();
+  double wa = 0., wt = 0.;
+  if (valid) {
+    for (int k = 0; k < n; ++k) {
+      const double w = Ws[slot][j][k];
+      wa += w * s_a[slot][k];
+      wt += w * s_t[slot][k];
+    }
+  }
+  const double cd = cell_ok ? (h.c_diag ? __ldg(h.c_diag + cell) : h.alpha * __ldg(m.cell_volume + cell)) : 0.;
+  const double S = group_sum<G>(area * wa) + cd;
+  const double awt = group_sum<G>(area * wt);
+  const double bp = cell_ok ? rhs[F + cell] : 0.;
+  const double p = (bp - awt) / S;
+  const double u = p * wa + wt;
+  if (MODE == 0) {
+    if (valid && gj >= 0) {
+      if (bnd)
+        out[gj] = lam;
+      else
+        atomicAdd(out + gj, area * u);  // two cells on a zeroed slot: order-free
+    }
+  } else {
+    if (j == 0 && cell_ok) out[F + cell] = p;
+    if (valid && gj >= 0 && owner) out[gj] = sg * u;
+  }
+}
+
+static HybArgs make_hyb(const mimpy_symbolic* sym, double alpha, const double* c_diag) {
+  HybArgs h;
+  h.face_to_flux = sym->face_to_flux;
+  h.face_cell = sym->face_cell;
+  h.m_indptr = sym->m_indptr;
+  h.m_ptr = sym->m_ptr;
+  h.pos_m = sym->pos_m;
+  h.flux_dof = sym->flux_dof;
+  h.alpha = alpha;
+  h.c_diag = c_diag;
+  return h;
+}
+
+#define DISPATCH_G(G, CALL8, CALL16, CALL32) \
+  do {                                       \
+    if ((G) == 8) { CALL8; }                 \
+    else if ((G) == 16) { CALL16; }          \
+    else { CALL32; }                         \
+  } while (0)
+
+extern "C" {
+
+int mimpy_b200_hybrid_setup(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
+                            const double* m_e, const double* multipliers, double alpha,
+                            const double* c_diag, double* w_e, double* a_vals, double* a_diag_inv) {
+  REQUIRE(ctx && mesh && sym && m_e && w_e && a_vals && a_diag_inv, "NULL argument");
+  REQUIRE(mesh->max_faces >= 1 && mesh->max_faces <= MIMPY_MAX_CELL_FACES, "max_faces out of range");
+  if (mesh->nc <= 0) return MIMPY_OK;
+  const int F = sym->flux_dof;
+  cudaStream_t st = ctx->stream;
+  if (F > 0) {
+    k_zero_diag_m<<<(F + 255) / 256, 256, 0, st>>>(F, sym->m_indptr, sym->diag_pos, a_vals);
+    KERNEL_CHECK();
+  }
+  const int G = mimpy_group_size(mesh->max_faces);
+  const int blocks = (mesh->nc + 128 / G - 1) / (128 / G);
+  HybArgs h = make_hyb(sym, alpha, c_diag);
+  DISPATCH_G(G, (k_hybrid_setup<8><<<blocks, 128, 0, st>>>(*mesh, h, m_e, multipliers, w_e, a_vals)),
+             (k_hybrid_setup<16><<<blocks, 128, 0, st>>>(*mesh, h, m_e, multipliers, w_e, a_vals)),
+             (k_hybrid_setup<32><<<blocks, 128, 0, st>>>(*mesh, h, m_e, multipliers, w_e, a_vals)));
+  KERNEL_CHECK();
+  if (F > 0) {
+    k_diag_inv<<<(F + 255) / 256, 256, 0, st>>>(F, sym->m_indptr, sym->diag_pos, a_vals, a_diag_inv);
+    KERNEL_CHECK();
+  }
+  return MIMPY_OK;
+}
+
+int mimpy_b200_hybrid_rhs(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
+                          const double* w_e, double alpha, const double* c_diag, const double* rhs,
+                          double* cell_tmp, double* hvec) {
+  (void)cell_tmp;
+  REQUIRE(ctx && mesh && sym && w_e && rhs && hvec, "NULL argument");
+  if (mesh->nc <= 0) return MIMPY_OK;
+  cudaStream_t st = ctx->stream;
+  CUDA_TRY(cudaMemsetAsync(hvec, 0, sizeof(double) * (size_t)sym->flux_dof, st));
+  const int G = mimpy_group_size(mesh->max_faces);
+  const int blocks = (mesh->nc + 128 / G - 1) / (128 / G);
+  HybArgs h = make_hyb(sym, alpha, c_diag);
+  DISPATCH_G(G, (k_hybrid_local<8, 0><<<blocks, 128, 0, st>>>(*mesh, h, w_e, rhs, nullptr, hvec)),
+             (k_hybrid_local<16, 0><<<blocks, 128, 0, st>>>(*mesh, h, w_e, rhs, nullptr, hvec)),
+             (k_hybrid_local<32, 0><<<blocks, 128, 0, st>>>(*mesh, h, w_e, rhs, nullptr, hvec)));
+  KERNEL_CHECK();
+  return MIMPY_OK;
+}
+
+int mimpy_b200_hybrid_recover(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,
+                              const mimpy_symbolic* sym, const double* w_e, double alpha,
+                              const double* c_diag, const double* rhs, const double* lambda,
+                              double* solution) {
+  REQUIRE(ctx && mesh && sym && w_e && rhs && lambda && solution, "NULL argument");
+  if (mesh->nc <= 0) return MIMPY_OK;
+  cudaStream_t st = ctx->stream;
+  const int G = mimpy_group_size(mesh->max_faces);
+  const int blocks = (mesh->nc + 128 / G - 1) / (128 / G);
+  HybArgs h = make_hyb(sym, alpha, c_diag);
+  DISPATCH_G(G, (k_hybrid_local<8, 1><<<blocks, 128, 0, st>>>(*mesh, h, w_e, rhs, lambda, solution)),
+             (k_hybrid_local<16, 1><<<blocks, 128, 0, st>>>(*mesh, h, w_e, rhs, lambda, solution)),
+             (k_hybrid_local<32, 1><<<blocks, 128, 0, st>>>(*mesh, h, w_e, rhs, lambda, solution)));
+  KERNEL_CHECK();
+  return MIMPY_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,315 @@
+// Jacobi-preconditioned conjugate gradients on the SPD face system (replaces the SuperLU call of
+// MFD.solve, mfd.py:1349-1358; the reference's own Schur-complement CG, mfd.py:1370-1428 and
+// twophase.py:31-86, is the design precedent).
+//
+// One iteration = three kernels, all scalars stay on the device:
+//   K1  Ap = A p                   + partial sums of p.Ap      -> S_PAP
+//   K2  x += a p ; r -= a Ap       + partial sums of r.D^-1 r, r.r -> S_RZNEW, S_RR   (a = S_RZ/S_PAP)
+//   K3  p = D^-1 r + b p           (b = S_RZNEW/S_RZ) ; then S_RZ <- S_RZNEW
+// Reductions are two-stage and ordered (per-block partials, last block sums them in index order),
+// so a solve is bit-reproducible for a fixed grid.  With more than one rank the three scalars are
+// all-reduced over NCCL between the kernels.  check_every iterations are replayed as one CUDA
+// graph; the host reads ||r||^2 only at those points.
+//
+// Algorithmic bytes per iteration (n rows, nnz non-zeros): SpMV 12 nnz + 4(n+1) + 16 n,
+// K2 48 n + 8 n (D^-1), K3 8 n (r) + 8 n (D^-1) + 16 n (p)  ->  12 nnz + 108 n  (SURVEY 8d).
+#include "common.cuh"
+
+#ifdef MIMPY_WITH_NCCL
+#include <nccl.h>
+#endif
+
+enum { S_RZ = 0, S_PAP = 1, S_RZNEW = 2, S_RR = 3, S_BNORM = 4, S_TMP = 8 };
+
+#define RED_THREADS 256
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double t = 0.;
+  if (w == 0) {
+    t = (l < (blockDim.x >> 5)) ? sh[l] : 0.;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  __syncthreads();
+  return t;  // valid in warp 0
+}
+
+// last block to arrive sums the per-block partials (NV values each) in index order
+template <int NV>
+__device__ __forceinline__ void finish_reduction(const double (&v)[NV], double* partials,
+                                                 unsigned int* counter, double* dst0, double* sh) {
+  __shared__ bool is_last;
+  double tot[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) tot[k] = block_sum(v[k], sh);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) partials[(size_t)k * gridDim.x + blockIdx.x] = tot[k];
+    __threadfence();
+    const unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double a = 0.;
+      for (int b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+        a += __ldcg(partials + (size_t)k * gridDim.x + b);
+      a = block_sum(a, sh);
+      if (threadIdx.x == 0) dst0[k] = a;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+  }
+}
+
+// ---- SpMV: LPR lanes per row (rows of the face system have ~11 entries) --------------------
+template <int LPR, bool DOT>
+__global__ void __launch_bounds__(RED_THREADS)
+k_spmv(int n, const int* __restrict__ indptr, const int* __restrict__ indices,
+       const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+       double* partials, unsigned int* counter, double* scal) {
+  __shared__ double sh[32];
+  const int lane = threadIdx.x % LPR;
+  const int rows_per_block = RED_THREADS / LPR;
+  double acc_dot = 0.;
+  for (long long row0 = (long long)blockIdx.x * rows_per_block; row0 < n;
+       row0 += (long long)gridDim.x * rows_per_block) {
+    const int row = (int)row0 + threadIdx.x / LPR;
+    double s = 0.;
+    if (row < n) {
+      const int b = __ldg(indptr + row), e = __ldg(indptr + row + 1);
+      for (int k = b + lane; k < e; k += LPR) s += __ldg(vals + k) * __ldg(x + __ldg(indices + k));
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (row < n && lane == 0) {
+      y[row] = s;
+      if (DOT) acc_dot += s * __ldg(x + row);
+    }
+  }
+  if (DOT) {
+    const double v[1] = {acc_dot};
+    finish_reduction<1>(v, partials, counter, scal + S_PAP, sh);
+  }
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+k_update_xr(int n, const double* __restrict__ p, const double* __restrict__ ap,
+            const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
+            double* partials, unsigned int* counter, double* scal) {
+  __shared__ double sh[32];
+  const double pap = scal[S_PAP];
+  const double alpha = (pap != 0.) ? scal[S_RZ] / pap : 0.;
+  double rz = 0., rr = 0.;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    x[i] += alpha * p[i];
+    const double ri = r[i] - alpha * ap[i];
+    r[i] = ri;
+    rz += ri * (__ldg(dinv + i) * ri);
+    rr += ri * ri;
+  }
+  const double v[2] = {rz, rr};
+  finish_reduction<2>(v, partials, counter, scal + S_RZNEW, sh);
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+k_update_p(int n, const double* __restrict__ r, const double* __restrict__ dinv,
+           double* __restrict__ p, unsigned int* counter, double* scal) {
+  const double rz = scal[S_RZ];
+  const double beta = (rz != 0.) ? scal[S_RZNEW] / rz : 0.;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    p[i] = __ldg(dinv + i) * r[i] + beta * p[i];
+  // the last block to finish rotates the scalar (every block has read S_RZ by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(counter, 1u);
+    if (t == gridDim.x - 1) {
+      scal[S_RZ] = scal[S_RZNEW];
+      *counter = 0u;
+    }
+  }
+}
+
+// r = b - A x (given Ax in ap), p = D^-1 r, S_RZ = r.D^-1 r, S_RR = r.r, S_BNORM = b.b
+__global__ void __launch_bounds__(RED_THREADS)
+k_init(int n, const double* __restrict__ b, const double* __restrict__ ax,
+       const double* __restrict__ dinv, double* __restrict__ r, double* __restrict__ p,
+       double* partials, unsigned int* counter, double* scal) {
+  __shared__ double sh[32];
+  double rz = 0., rr = 0., bb = 0.;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double bi = b[i];
+    const double ri = bi - ax[i];
+    const double zi = __ldg(dinv + i) * ri;
+    r[i] = ri;
+    p[i] = zi;
+    rz += ri * zi;
+    rr += ri * ri;
+    bb += bi * bi;
+  }
+  const double v[3] = {rz, rr, bb};
+  finish_reduction<3>(v, partials, counter, scal + S_TMP, sh);
+}
+
+__global__ void k_init_scalars(double* scal) {
+  scal[S_RZ] = scal[S_TMP];
+  scal[S_RR] = scal[S_TMP + 1];
+  scal[S_BNORM] = scal[S_TMP + 2];
+  scal[S_RZNEW] = scal[S_TMP];
+}
+
+static int allreduce(mimpy_ctx* ctx, double* buf, int count) {
+#ifdef MIMPY_WITH_NCCL
+  if (ctx->world > 1) {
+    ncclResult_t r = ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm,
+                                   ctx->stream);
+    if (r != ncclSuccess) {
+      mimpy_set_error("ncclAllReduce failed: %s", ncclGetErrorString(r));
+      return MIMPY_E_NCCL;
+    }
+  }
+#else
+  if (ctx->world > 1) {
+    mimpy_set_error("built without NCCL");
+    return MIMPY_E_NCCL;
+  }
+#endif
+  (void)buf;
+  (void)count;
+  return MIMPY_OK;
+}
+
+static int launch_iteration(mimpy_ctx* ctx, int grid, int n, const int* indptr, const int* indices,
+                            const double* vals, const double* dinv, double* x, double* r, double* p,
+                            double* ap) {
+  cudaStream_t st = ctx->stream;
+  k_spmv<8, true><<<grid, RED_THREADS, 0, st>>>(n, indptr, indices, vals, p, ap, ctx->partials,
+                                                ctx->counters + 0, ctx->scalars);
+  int rc = allreduce(ctx, ctx->scalars + S_PAP, 1);
+  if (rc) return rc;
+  k_update_xr<<<grid, RED_THREADS, 0, st>>>(n, p, ap, dinv, x, r, ctx->partials, ctx->counters + 1,
+                                            ctx->scalars);
+  rc = allreduce(ctx, ctx->scalars + S_RZNEW, 2);
+  if (rc) return rc;
+  k_update_p<<<grid, RED_THREADS, 0, st>>>(n, r, dinv, p, ctx->counters + 2, ctx->scalars);
+  return MIMPY_OK;
+}
+
+extern "C" {
+
+int mimpy_b200_spmv(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, const int32_t* indices,
+                    const double* vals, const double* x, double* y) {
+  REQUIRE(ctx && indptr && indices && vals && x && y, "NULL argument");
+  if (n <= 0) return MIMPY_OK;
+  const int rpb = RED_THREADS / 8;
+  long long want = ((long long)n + rpb - 1) / rpb;
+  const int grid = (int)(want < (long long)ctx->sm_count * 8 ? want : (long long)ctx->sm_count * 8);
+  k_spmv<8, false><<<grid, RED_THREADS, 0, ctx->stream>>>(n, indptr, indices, vals, x, y, nullptr,
+                                                          nullptr, nullptr);
+  KERNEL_CHECK();
+  return MIMPY_OK;
+}
+
+int mimpy_b200_pcg(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, const int32_t* indices,
+                   const double* vals, const double* diag_inv, const double* b, double* x,
+                   double* work, mimpy_pcg_info* info) {
+  REQUIRE(ctx && indptr && indices && vals && diag_inv && b && x && work && info, "NULL argument");
+  REQUIRE(n > 0, "empty system");
+  REQUIRE(info->maxit > 0, "maxit must be positive");
+  cudaStream_t st = ctx->stream;
+  double* r = work;
+  double* p = work + (size_t)n;
+  double* ap = work + 2 * (size_t)n;
+  const int grid = ctx->sm_count * 8;  // persistent-style: 8 resident CTAs of 256 threads per SM
+  const int check = info->check_every > 0 ? info->check_every : 25;
+
+  CUDA_TRY(cudaEventRecord(ctx->ev0, st));
+  // r0 = b - A x0
+  k_spmv<8, false><<<grid, RED_THREADS, 0, st>>>(n, indptr, indices, vals, x, ap, nullptr, nullptr,
+                                                 nullptr);
+  k_init<<<grid, RED_THREADS, 0, st>>>(n, b, ap, diag_inv, r, p, ctx->partials, ctx->counters + 3,
+                                       ctx->scalars);
+  int rc = allreduce(ctx, ctx->scalars + S_TMP, 3);
+  if (rc) return rc;
+  k_init_scalars<<<1, 1, 0, st>>>(ctx->scalars);
+  KERNEL_CHECK();
+  CUDA_TRY(cudaMemcpyAsync(ctx->host_scalars, ctx->scalars, sizeof(double) * 8,
+                           cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const double bnorm = sqrt(ctx->host_scalars[S_BNORM]);
+  double rnorm = sqrt(ctx->host_scalars[S_RR]);
+  const double target = fmax(info->rtol * bnorm, info->atol);
+  info->rhs_norm = bnorm;
+  int it = 0;
+
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  bool use_graph = info->use_graph && st != nullptr && st != cudaStreamLegacy &&
+                   st != cudaStreamPerThread;
+  if (use_graph && rnorm > target) {
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      int crc = MIMPY_OK;
+      for (int k = 0; k < check && crc == MIMPY_OK; ++k)
+        crc = launch_iteration(ctx, grid, n, indptr, indices, vals, diag_inv, x, r, p, ap);
+      cudaError_t e = cudaStreamEndCapture(st, &graph);
+      if (crc != MIMPY_OK || e != cudaSuccess || graph == nullptr ||
+          cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        graph = nullptr;
+        gexec = nullptr;
+        use_graph = false;
+        cudaGetLastError();
+      }
+    } else {
+      use_graph = false;
+      cudaGetLastError();
+    }
+  }
+
+  while (rnorm > target && it < info->maxit) {
+    if (use_graph && gexec) {
+      CUDA_TRY(cudaGraphLaunch(gexec, st));
+    } else {
+      for (int k = 0; k < check; ++k) {
+        rc = launch_iteration(ctx, grid, n, indptr, indices, vals, diag_inv, x, r, p, ap);
+        if (rc) return rc;
+      }
+      KERNEL_CHECK();
+    }
+    it += check;
+    CUDA_TRY(cudaMemcpyAsync(ctx->host_scalars, ctx->scalars, sizeof(double) * 8,
+                             cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    rnorm = sqrt(ctx->host_scalars[S_RR]);
+    if (!(rnorm == rnorm)) break;  // NaN: matrix not SPD
+  }
+  CUDA_TRY(cudaEventRecord(ctx->ev1, st));
+  CUDA_TRY(cudaEventSynchronize(ctx->ev1));
+  CUDA_TRY(cudaEventElapsedTime(&info->ms_total, ctx->ev0, ctx->ev1));
+  if (gexec) cudaGraphExecDestroy(gexec);
+  if (graph) cudaGraphDestroy(graph);
+  info->iterations = it;
+  info->residual = rnorm;
+  if (!(rnorm == rnorm)) {
+    mimpy_set_error("pcg: residual became NaN (face system not SPD?)");
+    return MIMPY_E_NOCONV;
+  }
+  if (rnorm > target) {
+    mimpy_set_error("pcg: %d iterations, residual %.3e > target %.3e", it, rnorm, target);
+    return MIMPY_E_NOCONV;
+  }
+  return MIMPY_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+// Two-phase (IMPES) transport kernels: Corey mobilities (twophase.py:268-344), upwind direction
+// (twophase.py:928-958) and the explicit saturation update (twophase.py:960-1092).
+#include "common.cuh"
+
+__device__ __forceinline__ double powd(double x, double e) {
+  if (e == 2.) return x * x;
+  if (e == 1.) return x;
+  if (e == 3.) return x * x * x;
+  return pow(x, e);
+}
+
+__device__ __forceinline__ void mobilities(const mimpy_fluid& fl, double sw, double p, double& mw,
+                                           double& mo) {
+  // sefromsw (twophase.py:317-324), krw/kro with clipping (275-289), mobility (326-344)
+  double se = sw - fl.s_wr;
+  se /= 1. - fl.s_wr - fl.s_or;
+  se = se < 0. ? 0. : (se > 1. ? 1. : se);
+  const double krw = fl.k_rw_o * powd(se, fl.n_w);
+  const double kro = powd(1.0 - se, fl.n_o);
+  mw = krw / fl.mu_w * fl.rho_w * (1. + fl.c_w * p);
+  mo = kro / fl.mu_o * fl.rho_o * (1. + fl.c_o * p);
+}
+
+__global__ void k_mobility(int nc, mimpy_fluid fl, const double* __restrict__ sw,
+                           const double* __restrict__ p, double* __restrict__ inv_tot,
+                           double* __restrict__ wm, double* __restrict__ om) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  double mw, mo;
+  mobilities(fl, sw[c], p[c], mw, mo);
+  if (inv_tot) inv_tot[c] = 1. / (mw + mo);
+  if (wm) wm[c] = mw;
+  if (om) om[c] = mo;
+}
+
+__global__ void k_fill_i32(int n, int* a, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+
+// (flux_index, cell) pairs with sigma*u_t[flux_index] > 0, flux_index = -1 on Neumann faces reads
+// u_t[-1] = the LAST flux DOF and later overwrites its f_w: the last pair in (cell, local face)
+// order wins (twophase.py:933-943, 968-971).
+__global__ void k_upwind(int nc, int F, const int* __restrict__ cell_ptr,
+                         const int* __restrict__ cell_faces, const int8_t* __restrict__ sigma,
+                         const int* __restrict__ f2f, const double* __restrict__ u_t,
+                         int* __restrict__ upwind, long long* __restrict__ last_key) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int base = cell_ptr[c];
+  const int n = cell_ptr[c + 1] - base;
+  for (int j = 0; j < n; ++j) {
+    int g = f2f[cell_faces[base + j]];
+    if (g < 0) g = F - 1;
+    const double dir = (double)sigma[base + j] * u_t[g];
+    if (dir > 0) {
+      if (g == F - 1)
+        atomicMax(last_key, (long long)c * 64 + j);
+      else
+        upwind[g] = c;
+    }
+  }
+}
+
+__global__ void k_upwind_last(int F, const long long* __restrict__ last_key, int* __restrict__ upwind) {
+  if (*last_key >= 0) upwind[F - 1] = (int)(*last_key >> 6);
+}
+
+__global__ void k_frac_flow(int F, mimpy_fluid fl, const int* __restrict__ upwind,
+                            const double* __restrict__ sw, const double* __restrict__ p,
+                            double* __restrict__ f_w) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= F) return;
+  const int c = upwind[g];
+  if (c < 0) return;
+  double mw, mo;
+  mobilities(fl, sw[c], p[c], mw, mo);
+  f_w[g] = mw / (mw + mo);
+}
+
+__global__ void k_bnd_inflow(int n_bnd, const int* __restrict__ faces, const int8_t* __restrict__ sg,
+                             const double* __restrict__ bnd_fw, const int* __restrict__ f2f,
+                             const double* __restrict__ u_t, double* __restrict__ f_w) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_bnd) return;
+  const int g = f2f[faces[k]];
+  if (g < 0) return;
+  if ((double)sg[k] * u_t[g] < 0) f_w[g] = bnd_fw[k];
+}
+
+__global__ void k_saturation(int nc, mimpy_fluid fl, double dt, const int* __restrict__ cell_ptr,
+                             const int* __restrict__ cell_faces, const int8_t* __restrict__ sigma,
+                             const double* __restrict__ face_geom, const int* __restrict__ f2f,
+                             const double* __restrict__ u_t, const double* __restrict__ f_w,
+                             const double* __restrict__ p, const double* __restrict__ p_prev,
+                             const double* __restrict__ porosity, const double* __restrict__ vol,
+                             double* __restrict__ s_w) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int base = cell_ptr[c];
+  const int n = cell_ptr[c + 1] - base;
+  double div = 0.;
+  for (int j = 0; j < n; ++j) {
+    const int f = cell_faces[base + j];
+    const int g = f2f[f];
+    if (g < 0) continue;
+    const double e = (double)sigma[base + j] * face_geom[8 * (size_t)f];
+    div += e * (f_w[g] * u_t[g]);
+  }
+  // twophase.py:1007-1022
+  double a = p_prev[c] * fl.c_w + 1.;
+  a *= fl.rho_w;
+  a *= s_w[c];
+  a /= fl.rho_w;
+  a /= 1. + fl.c_w * p[c];
+  double b = 1. / porosity[c];
+  b /= fl.rho_w;
+  b /= (1. + fl.c_w * p[c]);
+  b /= vol[c];
+  b *= div;
+  b *= -dt;
+  s_w[c] = a + b;
+}
+
+__global__ void k_rate_wells(int nw, mimpy_fluid fl, double dt, const int* __restrict__ cells,
+                             const double* __restrict__ rate_w, const double* __restrict__ p,
+                             const double* __restrict__ porosity, const double* __restrict__ vol,
+                             double* __restrict__ s_w) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  const int c = cells[w];
+  // twophase.py:1024-1035
+  double v = dt;
+  v /= porosity[c];
+  v /= 1. + fl.c_w * p[c];
+  v /= fl.rho_w;
+  v *= rate_w[w];
+  v /= vol[c];
+  atomicAdd(s_w + c, v);
+}
+
+extern "C" {
+
+int mimpy_b200_twophase_mobility(mimpy_ctx* ctx, int32_t nc, const mimpy_fluid* fluid_host,
+                                 const double* s_w, const double* p, double* inv_total_mobility,
+                                 double* water_mob, double* oil_mob) {
+  REQUIRE(ctx && fluid_host && s_w && p, "NULL argument");
+  if (nc <= 0) return MIMPY_OK;
+  k_mobility<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(nc, *fluid_host, s_w, p, inv_total_mobility,
+                                                        water_mob, oil_mob);
+  KERNEL_CHECK();
+  return MIMPY_OK;
+}
+
+int mimpy_b200_twophase_upwind(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,
+                               const mimpy_symbolic* sym, const double* u_t, int32_t* upwind_cell) {
+  REQUIRE(ctx && mesh && sym && u_t && upwind_cell, "NULL argument");
+  const int F = sym->flux_dof, nc = mesh->nc;
+  if (F <= 0 || nc <= 0) return MIMPY_OK;
+  cudaStream_t st = ctx->stream;
+  long long* key = reinterpret_cast<long long*>(ctx->scalars + 32);
+  CUDA_TRY(cudaMemsetAsync(key, 0xFF, sizeof(long long), st));  // -1
+  k_fill_i32<<<(F + 255) / 256, 256, 0, st>>>(F, upwind_cell, -1);
+  k_upwind<<<(nc + 255) / 256, 256, 0, st>>>(nc, F, mesh->cell_ptr, mesh->cell_faces,
+                                             mesh->cell_sigma, sym->face_to_flux, u_t, upwind_cell, key);
+  k_upwind_last<<<1, 1, 0, st>>>(F, key, upwind_cell);
+  KERNEL_CHECK();
+  return MIMPY_OK;
+}
+
+int mimpy_b200_twophase_saturation_step(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,
+                                        const mimpy_symbolic* sym, const mimpy_fluid* fluid_host,
+                                        double dt, const int32_t* upwind_cell, const double* u_t,
+                                        const double* p, const double* p_prev,
+                                        const double* porosity, int32_t n_bnd,
+                                        const int32_t* bnd_faces, const int8_t* bnd_sigma,
+                                        const double* bnd_fw, int32_t n_rate_wells,
+                                        const int32_t* well_cells, const double* well_rate_water,
+                                        double* f_w, double* s_w) {
+  REQUIRE(ctx && mesh && sym && fluid_host && upwind_cell && u_t && p && p_prev && porosity && f_w && s_w,
+          "NULL argument");
+  const int F = sym->flux_dof, nc = mesh->nc;
+  if (nc <= 0) return MIMPY_OK;
+  cudaStream_t st = ctx->stream;
+  const mimpy_fluid fl = *fluid_host;
+  if (F > 0) k_frac_flow<<<(F + 255) / 256, 256, 0, st>>>(F, fl, upwind_cell, s_w, p, f_w);
+  if (n_bnd > 0) {
+    REQUIRE(bnd_faces && bnd_sigma && bnd_fw, "boundary inflow arrays are NULL");
+    k_bnd_inflow<<<(n_bnd + 255) / 256, 256, 0, st>>>(n_bnd, bnd_faces, bnd_sigma, bnd_fw,
+                                                      sym->face_to_flux, u_t, f_w);
+  }
+  k_saturation<<<(nc + 255) / 256, 256, 0, st>>>(nc, fl, dt, mesh->cell_ptr, mesh->cell_faces,
+                                                 mesh->cell_sigma, mesh->face_geom,
+                                                 sym->face_to_flux, u_t, f_w, p, p_prev, porosity,
+                                                 mesh->cell_volume, s_w);
+  if (n_rate_wells > 0) {
+    REQUIRE(well_cells && well_rate_water, "well arrays are NULL");
+    k_rate_wells<<<(n_rate_wells + 255) / 256, 256, 0, st>>>(n_rate_wells, fl, dt, well_cells,
+                                                             well_rate_water, p, porosity,
+                                                             mesh->cell_volume, s_w);
+  }
+  KERNEL_CHECK();
+  return MIMPY_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,405 @@
+"""Device-side data model and thin wrappers over the C-ABI (include/mimpy_b200.h).
+
+DeviceMesh is the SoA snapshot of a mimpy Mesh in HBM; SymbolicPlan is the index plan of the
+saddle system.  Every function enqueues work on the context's stream and returns torch tensors
+that live on the device (PyTorch only owns the buffers).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MeshView, Symbolic, PcgInfo, Fluid, ptr
+
+
+def _group(max_faces):
+    return 8 if max_faces <= 8 else (16 if max_faces <= 16 else 32)
+
+
+class DeviceMesh(object):
+    """SoA mesh in HBM (SURVEY 8a G1-G6 outputs, laid out for the M_E kernels).
+
+    cell_ptr/cell_faces/cell_sigma : ragged cells (int32 / int32 / int8)
+    face_geom[nf,8]                : packed [area, n, x_f, 0] record (64 B)
+    cell_k[nc,9], cell_centroid[nc,3], cell_volume[nc] : the reference's own cell arrays
+    """
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.nc = 0
+        self.nf = 0
+        self.max_faces = 0
+        self.uniform_faces = 0
+        self.cell_ptr = None
+        self.cell_faces = None
+        self.cell_sigma = None
+        self.face_geom = None
+        self.cell_k = None
+        self.cell_centroid = None
+        self.cell_volume = None
+        # optional (geometry inputs / outputs kept for the host API)
+        self.points = None
+        self.face_ptr = None
+        self.face_points = None
+        self.face_areas = None
+        self.face_normals = None
+        self.face_centroids = None
+
+    def view(self):
+        v = MeshView()
+        v.nc, v.nf = self.nc, self.nf
+        v.max_faces, v.uniform_faces = self.max_faces, self.uniform_faces
+        v.cell_ptr = self.cell_ptr.data_ptr()
+        v.cell_faces = self.cell_faces.data_ptr()
+        v.cell_sigma = self.cell_sigma.data_ptr()
+        v.face_geom = self.face_geom.data_ptr()
+        v.cell_k = self.cell_k.data_ptr() if self.cell_k is not None else None
+        v.cell_centroid = self.cell_centroid.data_ptr()
+        v.cell_volume = self.cell_volume.data_ptr()
+        return v
+
+    # ---- builders ---------------------------------------------------------------------
+    @classmethod
+    def hex(cls, ctx, cx, cy, cz, dim_x, dim_y, dim_z, cell_k=None, points=None):
+        """Structured hex mesh built on the device (hexmesh.py:269-350): topology in closed form,
+        quad face geometry, Mirtich cell volumes/centroids.  cell_k: (nc,9)/(nc,3,3) array or None."""
+        dev = ctx.device
+        with ctx.on_stream():
+            m = cls(ctx)
+            nc = cx * cy * cz
+            L = cx * cy + cx * (cy + 1) + (cx + 1) * cy
+            nf = cz * L + cx * cy
+            npnt = (cx + 1) * (cy + 1) * (cz + 1)
+            m.nc, m.nf, m.max_faces, m.uniform_faces = nc, nf, 6, 6
+            # hexmesh.py:295-297
+            dx = dim_x / float(cx + 1 - 1.)
+            dy = dim_y / float(cy + 1 - 1.)
+            dz = dim_z / float(cz + 1 - 1.)
+            m.face_points = torch.empty((nf, 4), dtype=torch.int32, device=dev)
+            m.cell_faces = torch.empty(nc * 6, dtype=torch.int32, device=dev)
+            m.cell_sigma = torch.empty(nc * 6, dtype=torch.int8, device=dev)
+            own_points = points is None
+            m.points = torch.empty((npnt, 3), dtype=torch.float64, device=dev) if own_points \
+                else torch.as_tensor(points, dtype=torch.float64).reshape(npnt, 3).to(dev).contiguous()
+            ctx.call("mimpy_b200_hex_topology", cx, cy, cz, dx, dy, dz,
+                     ptr(m.points) if own_points else None, ptr(m.face_points), ptr(m.cell_faces),
+                     ptr(m.cell_sigma))
+            m.cell_ptr = torch.arange(0, 6 * nc + 1, 6, dtype=torch.int32, device=dev)
+            m.face_ptr = torch.arange(0, 4 * nf + 1, 4, dtype=torch.int32, device=dev)
+            m.compute_hex_face_geometry()
+            m.compute_cell_geometry()
+            m.set_cell_k(cell_k)
+        return m
+
+    def set_cell_k(self, cell_k):
+        dev = self.ctx.device
+        with self.ctx.on_stream():
+            if cell_k is None:
+                eye = torch.tensor([1., 0., 0., 0., 1., 0., 0., 0., 1.], dtype=torch.float64, device=dev)
+                self.cell_k = eye.repeat(self.nc, 1).contiguous()
+            else:
+                k = torch.as_tensor(cell_k, dtype=torch.float64)
+                self.cell_k = k.reshape(self.nc, 9).to(dev).contiguous()
+
+    def compute_hex_face_geometry(self):
+        """G3-G5 on the device (hexmesh_cython.pyx:30-118, hexmesh.py:68-74)."""
+        dev = self.ctx.device
+        with self.ctx.on_stream():
+            nf = self.nf
+            self.face_areas = torch.empty(nf, dtype=torch.float64, device=dev)
+            self.face_normals = torch.empty((nf, 3), dtype=torch.float64, device=dev)
+            self.face_centroids = torch.empty((nf, 3), dtype=torch.float64, device=dev)
+            self.face_geom = torch.empty((nf, 8), dtype=torch.float64, device=dev)
+            self.ctx.call("mimpy_b200_geom_hex_faces", nf, ptr(self.face_points), ptr(self.points),
+                          ptr(self.face_areas), ptr(self.face_normals), ptr(self.face_centroids),
+                          ptr(self.face_geom))
+
+    def compute_cell_geometry(self):
+        """G6 on the device (mesh_cython.pyx:5-207)."""
+        dev = self.ctx.device
+        with self.ctx.on_stream():
+            self.cell_volume = torch.empty(self.nc, dtype=torch.float64, device=dev)
+            self.cell_centroid = torch.empty((self.nc, 3), dtype=torch.float64, device=dev)
+            self.ctx.call("mimpy_b200_geom_cells", self.nc, self.max_faces, ptr(self.cell_ptr),
+                          ptr(self.cell_faces), ptr(self.cell_sigma), ptr(self.face_ptr),
+                          ptr(self.face_points), ptr(self.points), ptr(self.face_normals),
+                          ptr(self.cell_volume), ptr(self.cell_centroid))
+
+    @classmethod
+    def from_arrays(cls, ctx, cell_ptr, cell_faces, cell_sigma, face_areas, face_normals,
+                    face_centroids, cell_k, cell_centroid, cell_volume, points=None, face_ptr=None,
+                    face_points=None):
+        """Generic exporter: host (numpy) arrays of any polyhedral mesh -> HBM."""
+        dev = ctx.device
+        with ctx.on_stream():
+            m = cls(ctx)
+            cp = np.asarray(cell_ptr, dtype=np.int64)
+            m.nc = len(cp) - 1
+            m.nf = len(face_areas)
+            counts = np.diff(cp)
+            m.max_faces = int(counts.max()) if m.nc else 0
+            if m.max_faces > 32:
+                raise ValueError("cells with more than 32 faces are not supported")
+            m.uniform_faces = int(counts[0]) if m.nc and (counts == counts[0]).all() else 0
+            m.cell_ptr = torch.as_tensor(cp.astype(np.int32), device=dev)
+            m.cell_faces = torch.as_tensor(np.ascontiguousarray(cell_faces, dtype=np.int32), device=dev)
+            m.cell_sigma = torch.as_tensor(np.ascontiguousarray(cell_sigma, dtype=np.int8), device=dev)
+            m.face_areas = torch.as_tensor(np.ascontiguousarray(face_areas, dtype=np.float64), device=dev)
+            m.face_normals = torch.as_tensor(np.ascontiguousarray(face_normals, dtype=np.float64), device=dev)
+            m.face_centroids = torch.as_tensor(np.ascontiguousarray(face_centroids, dtype=np.float64), device=dev)
+            m.face_geom = torch.empty((m.nf, 8), dtype=torch.float64, device=dev)
+            ctx.call("mimpy_b200_face_pack", m.nf, ptr(m.face_areas), ptr(m.face_normals),
+                     ptr(m.face_centroids), ptr(m.face_geom))
+            m.cell_k = torch.as_tensor(np.ascontiguousarray(cell_k, dtype=np.float64).reshape(m.nc, 9), device=dev)
+            m.cell_centroid = torch.as_tensor(np.ascontiguousarray(cell_centroid, dtype=np.float64), device=dev)
+            m.cell_volume = torch.as_tensor(np.ascontiguousarray(cell_volume, dtype=np.float64), device=dev)
+            if points is not None:
+                m.points = torch.as_tensor(np.ascontiguousarray(points, dtype=np.float64), device=dev)
+                m.face_ptr = torch.as_tensor(np.asarray(face_ptr).astype(np.int32), device=dev)
+                m.face_points = torch.as_tensor(np.ascontiguousarray(face_points, dtype=np.int32), device=dev)
+        return m
+
+    @classmethod
+    def from_oracle_mesh(cls, ctx, o):
+        """From an oracle-style flat container (tests)."""
+        return cls.from_arrays(ctx, o.cell_ptr, o.cell_faces, o.cell_sigma, o.face_areas,
+                               o.face_normals, o.face_centroids, o.cell_k, o.cell_centroid,
+                               o.cell_volume, o.points, o.face_ptr, o.face_points)
+
+
+class SymbolicPlan(object):
+    """Index plan of the saddle system (C struct mimpy_symbolic + the tensors behind it)."""
+
+    def __init__(self):
+        self.s = Symbolic()
+        self.t = {}
+
+    @property
+    def flux_dof(self):
+        return int(self.s.flux_dof)
+
+    @property
+    def nnz(self):
+        return int(self.s.nnz)
+
+    @property
+    def nnz_m(self):
+        return int(self.s.nnz_m)
+
+    @property
+    def n_blocks(self):
+        return int(self.s.n_blocks)
+
+    def __getattr__(self, name):
+        t = self.__dict__.get("t", {})
+        if name in t:
+            return t[name]
+        raise AttributeError(name)
+
+
+def symbolic(dmesh, neumann_mask):
+    """A1-A5 index work (mimpy_b200_mfd_symbolic_sizes/_fill). neumann_mask: uint8[nf] (host or device)."""
+    ctx = dmesh.ctx
+    dev = ctx.device
+    with ctx.on_stream():
+        mask = torch.as_tensor(neumann_mask, dtype=torch.uint8).to(dev).contiguous()
+        nf, nc = dmesh.nf, dmesh.nc
+        total = int(6 * nc) if dmesh.uniform_faces == 6 else int(dmesh.cell_ptr[-1].item())
+        plan = SymbolicPlan()
+        t = plan.t
+        t["face_to_flux"] = torch.empty(nf + 1, dtype=torch.int32, device=dev)
+        t["face_cell"] = torch.empty((nf, 2), dtype=torch.int32, device=dev)
+        t["indptr"] = torch.empty(nf + nc + 1, dtype=torch.int32, device=dev)
+        t["m_indptr"] = torch.empty(nf + 1, dtype=torch.int32, device=dev)
+        t["m_ptr"] = torch.empty(nc + 1, dtype=torch.int32, device=dev)
+        s = plan.s
+        s.face_to_flux = t["face_to_flux"].data_ptr()
+        s.face_cell = t["face_cell"].data_ptr()
+        s.indptr = t["indptr"].data_ptr()
+        s.m_indptr = t["m_indptr"].data_ptr()
+        s.m_ptr = t["m_ptr"].data_ptr()
+        mv = dmesh.view()
+        ctx.call("mimpy_b200_mfd_symbolic_sizes", C.byref(mv), ptr(mask), C.byref(s))
+        t["indices"] = torch.empty(max(plan.nnz, 1), dtype=torch.int32, device=dev)
+        t["m_indices"] = torch.empty(max(plan.nnz_m, 1), dtype=torch.int32, device=dev)
+        t["pos_m"] = torch.empty(max(plan.n_blocks, 1), dtype=torch.uint8, device=dev)
+        t["pos_dt"] = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+        t["pos_d"] = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+        t["diag_pos"] = torch.zeros(nf, dtype=torch.uint8, device=dev)
+        s.indices = t["indices"].data_ptr()
+        s.m_indices = t["m_indices"].data_ptr()
+        s.pos_m = t["pos_m"].data_ptr()
+        s.pos_dt = t["pos_dt"].data_ptr()
+        s.pos_d = t["pos_d"].data_ptr()
+        s.diag_pos = t["diag_pos"].data_ptr()
+        ctx.call("mimpy_b200_mfd_symbolic_fill", C.byref(mv), C.byref(s))
+        plan.mask = mask
+        plan.ndof = plan.flux_dof + nc
+        plan.total_cell_faces = total
+    return plan
+
+
+def local_matrices(dmesh, plan_or_mptr, method, k_unity=False, want_diagonality=False,
+                   want_consistency=False):
+    """L1-L4: all M_E blocks (mimpy_b200_mfd_local_matrices). Returns (m_e, diagonality, consistency)."""
+    ctx = dmesh.ctx
+    dev = ctx.device
+    with ctx.on_stream():
+        if isinstance(plan_or_mptr, SymbolicPlan):
+            m_ptr, nb = plan_or_mptr.m_ptr, plan_or_mptr.n_blocks
+        else:
+            m_ptr = plan_or_mptr
+            nb = int(m_ptr[-1].item())
+        m_e = torch.empty(max(nb, 1), dtype=torch.float64, device=dev)
+        diag = torch.empty(dmesh.nc, dtype=torch.float64, device=dev) if want_diagonality else None
+        cons = torch.empty(dmesh.nc, dtype=torch.float64, device=dev) if want_consistency else None
+        mv = dmesh.view()
+        ctx.call("mimpy_b200_mfd_local_matrices", C.byref(mv), int(method), 1 if k_unity else 0,
+                 ptr(m_ptr), ptr(m_e), ptr(diag), ptr(cons))
+    return m_e[:nb], diag, cons
+
+
+def block_offsets(dmesh):
+    """m_ptr without a symbolic plan (offsets of the n_E^2 blocks)."""
+    with dmesh.ctx.on_stream():
+        n = (dmesh.cell_ptr[1:] - dmesh.cell_ptr[:-1]).to(torch.int64)
+        out = torch.zeros(dmesh.nc + 1, dtype=torch.int64, device=dmesh.ctx.device)
+        out[1:] = torch.cumsum(n * n, 0)
+        return out.to(torch.int32)
+
+
+def numeric(dmesh, plan, method, k_unity=False, multipliers=None, alpha=0., c_diag=None, vals=None,
+            m_e_out=None):
+    """A2-A5+A8: fused M_E construction + CSR scatter (mimpy_b200_mfd_numeric)."""
+    ctx = dmesh.ctx
+    with ctx.on_stream():
+        if vals is None:
+            vals = torch.empty(max(plan.nnz, 1), dtype=torch.float64, device=ctx.device)
+        mv = dmesh.view()
+        ctx.call("mimpy_b200_mfd_numeric", C.byref(mv), C.byref(plan.s), int(method),
+                 1 if k_unity else 0, ptr(multipliers), float(alpha), ptr(c_diag), ptr(vals),
+                 ptr(m_e_out))
+    return vals
+
+
+def numeric_from_blocks(dmesh, plan, m_e, multipliers=None, alpha=0., c_diag=None, vals=None):
+    ctx = dmesh.ctx
+    with ctx.on_stream():
+        if vals is None:
+            vals = torch.empty(max(plan.nnz, 1), dtype=torch.float64, device=ctx.device)
+        mv = dmesh.view()
+        ctx.call("mimpy_b200_mfd_numeric_from_blocks", C.byref(mv), C.byref(plan.s), ptr(m_e),
+                 ptr(multipliers), float(alpha), ptr(c_diag), ptr(vals))
+    return vals
+
+
+def coo_view(dmesh, plan, m_e=None, want_triples=True):
+    """Reference-ordered COO of the M block: (m_e_locations, rows, cols, vals)."""
+    ctx = dmesh.ctx
+    dev = ctx.device
+    with ctx.on_stream():
+        coo_ptr = torch.empty(dmesh.nc + 1, dtype=torch.int64, device=dev)
+        mv = dmesh.view()
+        ctx.call("mimpy_b200_mfd_coo", C.byref(mv), C.byref(plan.s), None, ptr(coo_ptr), None, None, None)
+        if not want_triples:
+            return coo_ptr, None, None, None
+        n = int(coo_ptr[-1].item())
+        rows = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        cols = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        vals = torch.empty(max(n, 1), dtype=torch.float64, device=dev) if m_e is not None else None
+        ctx.call("mimpy_b200_mfd_coo", C.byref(mv), C.byref(plan.s), ptr(m_e), ptr(coo_ptr), ptr(rows),
+                 ptr(cols), ptr(vals))
+    return coo_ptr, rows[:n], cols[:n], (vals[:n] if vals is not None else None)
+
+
+def build_rhs(dmesh, plan, dirichlet_faces, dirichlet_values, has_neumann, last_neumann_value, forcing):
+    """A6 (mimpy_b200_mfd_rhs)."""
+    ctx = dmesh.ctx
+    dev = ctx.device
+    with ctx.on_stream():
+        nd = len(dirichlet_faces)
+        df = torch.as_tensor(np.asarray(dirichlet_faces, dtype=np.int32), device=dev) if nd else None
+        dv = torch.as_tensor(np.asarray(dirichlet_values, dtype=np.float64), device=dev) if nd else None
+        fo = None
+        if forcing is not None:
+            fo = torch.as_tensor(forcing, dtype=torch.float64).to(dev).contiguous()
+        rhs = torch.empty(plan.ndof, dtype=torch.float64, device=dev)
+        ctx.call("mimpy_b200_mfd_rhs", dmesh.nc, plan.flux_dof, ptr(plan.face_to_flux), nd, ptr(df),
+                 ptr(dv), 1 if has_neumann else 0, float(last_neumann_value), ptr(fo), ptr(rhs))
+    return rhs
+
+
+class HybridSystem(object):
+    """The SPD face system A lambda = h of the hybridised saddle problem, in HBM."""
+
+    def __init__(self, dmesh, plan, m_e, multipliers=None, alpha=0., c_diag=None):
+        self.dmesh, self.plan = dmesh, plan
+        self.alpha, self.c_diag = float(alpha), c_diag
+        ctx = dmesh.ctx
+        dev = ctx.device
+        with ctx.on_stream():
+            self.w_e = torch.empty(max(plan.n_blocks, 1), dtype=torch.float64, device=dev)
+            self.a_vals = torch.zeros(max(plan.nnz_m, 1), dtype=torch.float64, device=dev)
+            self.a_diag_inv = torch.empty(max(plan.flux_dof, 1), dtype=torch.float64, device=dev)
+            self.work = None
+            self.setup(m_e, multipliers, c_diag)
+
+    def setup(self, m_e, multipliers=None, c_diag=None):
+        ctx = self.dmesh.ctx
+        self.c_diag = c_diag
+        with ctx.on_stream():
+            mv = self.dmesh.view()
+            ctx.call("mimpy_b200_hybrid_setup", C.byref(mv), C.byref(self.plan.s), ptr(m_e),
+                     ptr(multipliers), self.alpha, ptr(c_diag), ptr(self.w_e), ptr(self.a_vals),
+                     ptr(self.a_diag_inv))
+
+    def solve(self, rhs, rtol=1e-10, atol=0., maxit=20000, check_every=50, use_graph=True, x0=None,
+              raise_on_noconv=True):
+        """Returns (solution [v;p], info). rhs: device tensor of length flux_dof+nc."""
+        ctx = self.dmesh.ctx
+        dev = ctx.device
+        plan = self.plan
+        F = plan.flux_dof
+        with ctx.on_stream():
+            mv = self.dmesh.view()
+            h = torch.empty(F, dtype=torch.float64, device=dev)
+            ctx.call("mimpy_b200_hybrid_rhs", C.byref(mv), C.byref(plan.s), ptr(self.w_e), self.alpha,
+                     ptr(self.c_diag), ptr(rhs), None, ptr(h))
+            lam = torch.zeros(F, dtype=torch.float64, device=dev) if x0 is None else x0.clone()
+            if self.work is None or self.work.numel() < 4 * F:
+                self.work = torch.empty(4 * F, dtype=torch.float64, device=dev)
+            info = PcgInfo()
+            info.rtol, info.atol, info.maxit = rtol, atol, maxit
+            info.check_every, info.use_graph = check_every, 1 if use_graph else 0
+            allow = () if raise_on_noconv else (_lib.MIMPY_E_NOCONV,)
+            ctx.call("mimpy_b200_pcg", F, ptr(plan.m_indptr), ptr(plan.m_indices), ptr(self.a_vals),
+                     ptr(self.a_diag_inv), ptr(h), ptr(lam), ptr(self.work), C.byref(info), allow=allow)
+            sol = torch.empty(plan.ndof, dtype=torch.float64, device=dev)
+            ctx.call("mimpy_b200_hybrid_recover", C.byref(mv), C.byref(plan.s), ptr(self.w_e),
+                     self.alpha, ptr(self.c_diag), ptr(rhs), ptr(lam), ptr(sol))
+            self.last_lambda = lam
+        return sol, info
+
+
+def spmv(ctx, indptr, indices, vals, x, n=None):
+    with ctx.on_stream():
+        n = int(indptr.numel() - 1) if n is None else n
+        y = torch.empty(n, dtype=torch.float64, device=ctx.device)
+        ctx.call("mimpy_b200_spmv", n, ptr(indptr), ptr(indices), ptr(vals), ptr(x), ptr(y))
+    return y
+
+
+def make_fluid(mu_w, mu_o, rho_w, rho_o, c_w, c_o, s_wr, s_or, n_w, n_o, k_rw_o=1.):
+    f = Fluid()
+    f.mu_w, f.mu_o, f.rho_w, f.rho_o = mu_w, mu_o, rho_w, rho_o
+    f.c_w, f.c_o, f.s_wr, f.s_or = c_w, c_o, s_wr, s_or
+    f.n_w, f.n_o, f.k_rw_o = n_w, n_o, k_rw_o
+    return f
+
+
+def to_host(ctx, t):
+    """Device tensor -> numpy, ordered after the context stream."""
+    with ctx.on_stream():
+        out = t.detach().cpu()
+    return out.numpy()

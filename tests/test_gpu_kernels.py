@@ -1,0 +1,415 @@
+"""GPU parity of the CUDA kernels (through the C-ABI) against the CPU oracle and the golden
+vectors of the reference.  Run on the B200 box:  pytest -m gpu"""
+import numpy as np
+import pytest
+from scipy import sparse
+
+from oracle import mimpy_oracle as orc
+from oracle import ref_shim
+
+pytestmark = pytest.mark.gpu
+
+zero_flux = lambda p: np.array([0., 0., 0.])
+lin = lambda p: 1. + 2. * p[0] - p[1] + .5 * p[2]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+    from mimpy_b200 import _lib
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return _lib.default_context()
+
+
+def H(ctx, t):
+    from mimpy_b200 import device
+
+    return device.to_host(ctx, t)
+
+
+def neumann_mask(o, markers):
+    m = np.zeros(o.nf, dtype=np.uint8)
+    for b in markers:
+        for f, _ in o.boundary_faces[b]:
+            m[f] = 1
+    return m
+
+
+def blocks_of(o, flat):
+    out, pos = [], 0
+    for c in range(o.nc):
+        n = int(o.cell_ptr[c + 1] - o.cell_ptr[c])
+        out.append(flat[pos:pos + n * n].reshape(n, n))
+        pos += n * n
+    return out
+
+
+# ---- geometry ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(5, 5, 5, 1., 1., 1.), (4, 3, 2, 2., 1.5, 1.), (7, 2, 9, 3., .5, 2.)])
+def test_hex_build_bit_exact(ctx, shape):
+    """Topology identical, geometry bit-identical to the oracle (and through it to the reference)."""
+    from mimpy_b200.device import DeviceMesh
+
+    cx, cy, cz, dx, dy, dz = shape
+    o = orc.hex_mesh(cx, cy, cz, dx, dy, dz)
+    d = DeviceMesh.hex(ctx, cx, cy, cz, dx, dy, dz)
+    assert (d.nc, d.nf) == (o.nc, o.nf)
+    assert np.array_equal(H(ctx, d.face_points).ravel(), o.face_points)
+    assert np.array_equal(H(ctx, d.cell_faces), o.cell_faces)
+    assert np.array_equal(H(ctx, d.cell_sigma), o.cell_sigma)
+    assert np.array_equal(H(ctx, d.points), o.points)
+    assert np.array_equal(H(ctx, d.face_areas), o.face_areas)
+    assert np.array_equal(H(ctx, d.face_normals), o.face_normals)
+    assert np.array_equal(H(ctx, d.face_centroids), o.face_centroids)
+    assert np.allclose(H(ctx, d.cell_volume), o.cell_volume, rtol=1e-14, atol=0)
+    assert np.allclose(H(ctx, d.cell_centroid), o.cell_centroid, rtol=1e-13, atol=1e-16)
+    g = H(ctx, d.face_geom)
+    assert np.array_equal(g[:, 0], o.face_areas) and np.array_equal(g[:, 1:4], o.face_normals)
+    assert np.array_equal(g[:, 4:7], o.face_centroids)
+
+
+def test_geometry_against_reference_natives(ctx, golden):
+    """Distorted hexes: CUDA geometry vs the reference's own Cython natives (oracle/_ref)."""
+    if not ref_shim.natives_available():
+        pytest.skip("oracle/_ref not built")
+    import torch
+    from mimpy_b200.device import DeviceMesh
+
+    g = golden("hex_distorted_333")
+    o = orc.omesh_from_dict(g)
+    hx = ref_shim.load_native("hexmesh_cython")
+    mc = ref_shim.load_native("mesh_cython")
+    nf, nc = o.nf, o.nc
+    fptr = np.stack([np.arange(nf) * 4, np.full(nf, 4)], 1).astype(np.int32)
+    cptr = np.stack([np.arange(nc) * 6, np.full(nc, 6)], 1).astype(np.int32)
+    areas = np.zeros(nf)
+    normals = np.zeros((nf, 3))
+    hx.all_face_areas(fptr, nf, o.face_points.astype(np.int32), o.points, areas)
+    hx.all_face_normals(fptr, nf, o.face_points.astype(np.int32), o.points, normals)
+    vol = np.zeros(nc)
+    cen = np.zeros((nc, 3))
+    mc.all_cell_volumes_centroids(cptr, nc, o.cell_faces.astype(np.int32), o.cell_sigma.astype(np.int32),
+                                  o.points, vol, cen, fptr, nf, o.face_points.astype(np.int32), normals,
+                                  o.face_to_cell.astype(np.int32))
+    d = DeviceMesh.hex(ctx, 3, 3, 3, 1., 1., 1., points=o.points)
+    assert np.array_equal(H(ctx, d.face_areas), areas)
+    assert np.array_equal(H(ctx, d.face_normals), normals)
+    assert np.array_equal(H(ctx, d.cell_volume), vol)
+    assert np.array_equal(H(ctx, d.cell_centroid), cen)
+
+
+def test_mirtich_cut_cells(ctx, golden):
+    import torch
+    from mimpy_b200.device import DeviceMesh
+
+    g = golden("cut_checker_4")
+    o = orc.omesh_from_dict(g)
+    d = DeviceMesh.from_oracle_mesh(ctx, o)
+    d.compute_cell_geometry()
+    assert np.allclose(H(ctx, d.cell_volume), o.cell_volume, rtol=1e-12, atol=0)
+    assert np.allclose(H(ctx, d.cell_centroid), o.cell_centroid, rtol=1e-11, atol=1e-14)
+
+
+# ---- local matrices ----------------------------------------------------------------------------
+@pytest.mark.parametrize("name,methods", [("hex_aniso_432", (0, 1, 2, 3, 5, 6, 7)),
+                                          ("hex_distorted_333", (0, 1, 6)),
+                                          ("cut_checker_4", (0, 1))])
+def test_local_matrices_vs_reference(ctx, golden, name, methods):
+    """M_E within 1e-12 (Frobenius, relative) of the blocks the reference itself built."""
+    from mimpy_b200 import device
+
+    g = golden(name)
+    o = orc.omesh_from_dict(g)
+    d = device.DeviceMesh.from_oracle_mesh(ctx, o)
+    mptr = device.block_offsets(d)
+    for method in methods:
+        m_e, diag, cons = device.local_matrices(d, mptr, method, want_diagonality=True, want_consistency=True)
+        ours = blocks_of(o, H(ctx, m_e))
+        ref = blocks_of(o, g["m%d_m_e_flat" % method])
+        worst = max(np.linalg.norm(a - b) / np.linalg.norm(b) for a, b in zip(ours, ref))
+        assert worst < 1e-12, (method, worst)
+        dref = np.array([np.linalg.norm(b - np.diag(np.diag(b))) / np.linalg.norm(b) for b in ref])
+        assert np.allclose(H(ctx, diag), dref, atol=1e-11)
+        if method not in (5, 7):  # diagonal variants do not satisfy M N = R
+            scale = np.array([np.linalg.norm(orc.build_r_e(o, c)) for c in range(o.nc)])
+            assert (H(ctx, cons) < 1e-11 * scale).all()
+
+
+def test_local_matrices_large_random_vs_batched_oracle(ctx):
+    """32^3 heterogeneous anisotropic K (C3 shape): every block within 1e-12 of the oracle."""
+    from mimpy_b200 import device
+
+    n = 32
+    rng = np.random.default_rng(256)
+    kd = np.exp(rng.standard_normal((n ** 3, 3)))
+    ktab = np.zeros((n ** 3, 9))
+    ktab[:, 0], ktab[:, 4], ktab[:, 8] = kd[:, 0], kd[:, 1], kd[:, 2]
+    d = device.DeviceMesh.hex(ctx, n, n, n, 1., 1., 1., cell_k=ktab)
+    o = orc.OMesh()
+    o.cell_ptr = np.arange(n ** 3 + 1) * 6
+    o.cell_faces = H(ctx, d.cell_faces)
+    o.cell_sigma = H(ctx, d.cell_sigma).astype(np.int32)
+    o.face_areas, o.face_normals = H(ctx, d.face_areas), H(ctx, d.face_normals)
+    o.face_centroids = H(ctx, d.face_centroids)
+    o.cell_centroid, o.cell_volume, o.cell_k = H(ctx, d.cell_centroid), H(ctx, d.cell_volume), ktab
+    mptr = device.block_offsets(d)
+    for method in (0, 1, 6):
+        ref = orc.build_m_e_batched(o, method)
+        ours = H(ctx, device.local_matrices(d, mptr, method)[0]).reshape(-1, 6, 6)
+        err = np.linalg.norm((ours - ref).reshape(len(ref), -1), axis=1) / np.linalg.norm(ref.reshape(len(ref), -1), axis=1)
+        assert err.max() < 1e-12, (method, err.max())
+
+
+# ---- symbolic + numeric assembly -----------------------------------------------------------------
+def _oracle_system(o, method, bc, forcing):
+    f = orc.OracleMFD(o, method)
+    for kind, marker, fn in bc:
+        (f.apply_dirichlet_from_function if kind == "d" else f.apply_neumann_from_function)(marker, fn)
+    if forcing is not None:
+        f.apply_forcing_from_function(forcing)
+    return f
+
+
+def _check_assembly(ctx, o, method, bc, forcing, g=None, prefix=""):
+    from mimpy_b200 import device
+
+    f = _oracle_system(o, method, bc, forcing)
+    f.build_lhs()
+    f.build_rhs()
+    d = device.DeviceMesh.from_oracle_mesh(ctx, o)
+    mask = np.zeros(o.nf, dtype=np.uint8)
+    for face in f.neumann_boundary_values:
+        mask[face] = 1
+    plan = device.symbolic(d, mask)
+    # DOF numbering: bit exact
+    assert plan.flux_dof == f.flux_dof
+    assert np.array_equal(H(ctx, plan.face_to_flux)[:o.nf], f.face_to_flux[:, 0])
+    vals = device.numeric(d, plan, method)
+    n = plan.ndof
+    ours = sparse.csr_matrix((H(ctx, vals)[:plan.nnz], H(ctx, plan.indices)[:plan.nnz], H(ctx, plan.indptr)[:n + 1]), shape=(n, n))
+    assert ours.has_sorted_indices
+    ref = f.lhs.tocsr()
+    ref.sort_indices()
+    scale = abs(ref).max()
+    # entries: 1e-12 relative
+    assert abs(ours - ref).max() <= 1e-12 * scale
+    # pattern: the reference's (value-filtered) pattern is a subset of ours, the surplus is roundoff
+    pat_o = sparse.csr_matrix((np.ones(ours.nnz), ours.indices, ours.indptr), shape=ours.shape)
+    pat_r = sparse.csr_matrix((np.ones(ref.nnz), ref.indices, ref.indptr), shape=ref.shape)
+    assert (pat_r - pat_r.multiply(pat_o)).nnz == 0
+    # the DIV / DIV^T / C blocks: pattern AND values bit exact
+    F = plan.flux_dof
+    for blk in (lambda a: a[F:, :], lambda a: a[:F, F:]):
+        a, b = blk(ours).tocsr(), blk(ref).tocsr()
+        a.sort_indices(); b.sort_indices()
+        assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+        assert np.array_equal(a.data, b.data)
+    # after thresholding both at 1e-12 the M patterns agree exactly
+    def thr(a):
+        a = a[:F, :F].tocsr().copy()
+        a.data[abs(a.data) < 1e-12 * scale] = 0
+        a.eliminate_zeros()
+        a.sort_indices()
+        return a
+    a, b = thr(ours), thr(ref)
+    assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+    if g is not None:
+        gref = sparse.csr_matrix((g[prefix + "csr_data"], g[prefix + "csr_indices"], g[prefix + "csr_indptr"]), shape=(n, n))
+        assert abs(ours - gref).max() <= 1e-12 * scale
+    # rhs
+    dfaces = list(f.dirichlet_boundary_values.keys())
+    dvals = [f.dirichlet_boundary_values[k] for k in dfaces]
+    nvals = list(f.neumann_boundary_values.values())
+    rhs = device.build_rhs(d, plan, dfaces, dvals, len(nvals) > 0, nvals[-1] if nvals else 0., f.cell_forcing_function)
+    assert np.array_equal(H(ctx, rhs), f.rhs)
+    return d, plan, f, vals, rhs
+
+
+BC_MIXED = [("d", 0, lambda p: 1. + 0.3 * p[1]), ("d", 1, lambda p: 0.2 * p[2])] + [("n", b, zero_flux) for b in (2, 3, 4, 5)]
+FORCING = lambda x: np.sin(3. * x[0]) + x[1] * x[2]
+
+
+@pytest.mark.parametrize("method", [0, 1, 2, 3, 6])
+def test_assembly_aniso_mixed_bc(ctx, golden, method):
+    g = golden("hex_aniso_432")
+    _check_assembly(ctx, orc.omesh_from_dict(g), method, BC_MIXED, FORCING, g, "m%d_" % method)
+
+
+def test_assembly_config1(ctx, golden):
+    g = golden("hex_c1_n5")
+    u = lambda p: p[0] ** 2 + p[1] ** 2 + p[2] ** 2
+    _check_assembly(ctx, orc.omesh_from_dict(g), 0, [("d", b, u) for b in range(6)], lambda x: -6., g, "")
+
+
+def test_assembly_cut_polyhedral(ctx, golden):
+    g = golden("cut_checker_4")
+    o = orc.omesh_from_dict(g)
+    _check_assembly(ctx, o, 1, [("d", b, lin) for b in range(6)], None, g, "m1_")
+    bc = [("d", 0, lambda p: 1.), ("d", 1, lambda p: 0.)] + [("n", b, zero_flux) for b in (2, 3, 4, 5)]
+    _check_assembly(ctx, o, 1, bc, None, g, "m1n_")
+
+
+def test_update_m_multipliers_and_coo_view(ctx, golden):
+    """A8: per-cell multipliers (mfd_cython.update_m_fast) and the reference-ordered COO view."""
+    from mimpy_b200 import device
+    import torch
+
+    g = golden("twophase_633_wells")
+    o = orc.omesh_from_dict(g)
+    f = _oracle_system(o, 6, [("n", b, zero_flux) for b in (0, 2, 3, 4, 5)] + [("d", 1, lambda p: 0.)], None)
+    m = f.build_m(save_update_info=True)
+    d = device.DeviceMesh.from_oracle_mesh(ctx, o)
+    mask = np.zeros(o.nf, dtype=np.uint8)
+    mask[list(f.neumann_boundary_values.keys())] = 1
+    plan = device.symbolic(d, mask)
+    m_e, _, _ = device.local_matrices(d, plan, 6)
+    loc, rows, cols, vals = device.coo_view(d, plan, m_e)
+    # m_e_locations: ours is structural ((#non-Neumann faces)^2 per cell); the reference's is
+    # value-filtered (mfd.py:582 drops exact zeros, keeps 1e-17 noise), hence <= ours per cell
+    g2f = f.face_to_flux[:, 0]
+    kept = np.array([(g2f[o.cell(c)] >= 0).sum() ** 2 for c in range(o.nc)])
+    assert np.array_equal(H(ctx, loc), np.concatenate(([0], np.cumsum(kept))))
+    assert (np.diff(g["m_e_locations"]) <= kept).all()
+    # same matrix: our COO triples and the reference's (m[0..2] from the oracle) sum to the same M
+    F0 = f.flux_dof
+    ours_m = sparse.coo_matrix((H(ctx, vals), (H(ctx, rows), H(ctx, cols))), shape=(F0, F0)).tocsr()
+    ref_m = sparse.coo_matrix((m[0], (m[1], m[2])), shape=(F0, F0)).tocsr()
+    assert abs(ours_m - ref_m).max() <= 1e-12 * abs(ref_m).max()
+    # cell-major / row-major order of the triples (mfd.py:575-588)
+    r_exp = np.concatenate([np.repeat(g2f[o.cell(c)][g2f[o.cell(c)] >= 0], (g2f[o.cell(c)] >= 0).sum()) for c in range(o.nc)])
+    assert np.array_equal(H(ctx, rows), r_exp)
+    # multipliers: numeric(mult) == mult[cell] * numeric(1) on the M block, DIV untouched
+    rng = np.random.default_rng(1)
+    mult = rng.uniform(.5, 2., o.nc)
+    v1 = H(ctx, device.numeric(d, plan, 6))
+    tm = torch.as_tensor(mult, device=ctx.device)
+    v2 = H(ctx, device.numeric(d, plan, 6, multipliers=tm))
+    n = plan.ndof
+    a1 = sparse.csr_matrix((v1[:plan.nnz], H(ctx, plan.indices)[:plan.nnz], H(ctx, plan.indptr)[:n + 1]), shape=(n, n))
+    a2 = sparse.csr_matrix((v2[:plan.nnz], H(ctx, plan.indices)[:plan.nnz], H(ctx, plan.indptr)[:n + 1]), shape=(n, n))
+    # oracle: scale the COO list per cell and re-assemble
+    data = np.array(m[0])
+    f.update_m(data, mult)
+    ref = sparse.coo_matrix((data, (m[1], m[2])), shape=(f.flux_dof, f.flux_dof)).tocsr()
+    F = plan.flux_dof
+    assert abs(a2[:F, :F] - ref).max() <= 1e-12 * abs(ref).max()
+    assert abs(a2[F:, :] - a1[F:, :]).max() == 0
+
+
+# ---- solve ------------------------------------------------------------------------------------------
+def _solve_and_compare(ctx, o, method, bc, forcing, ref_solution, tol=1e-8):
+    from mimpy_b200 import device
+
+    d, plan, f, vals, rhs = _check_assembly(ctx, o, method, bc, forcing)
+    m_e, _, _ = device.local_matrices(d, plan, method)
+    hyb = device.HybridSystem(d, plan, m_e)
+    sol, info = hyb.solve(rhs, rtol=1e-13, maxit=5000, check_every=20)
+    sol = H(ctx, sol)
+    err = np.linalg.norm(sol - ref_solution) / np.linalg.norm(ref_solution)
+    assert err < tol, (err, info.iterations)
+    # the recovered vector solves the ORIGINAL saddle system
+    a = f.lhs.tocsr()
+    assert np.linalg.norm(a @ sol - f.rhs) <= 1e-9 * max(np.linalg.norm(f.rhs), 1e-30)
+    return info
+
+
+def test_solve_config1_vs_spsolve(ctx, golden):
+    g = golden("hex_c1_n5")
+    u = lambda p: p[0] ** 2 + p[1] ** 2 + p[2] ** 2
+    _solve_and_compare(ctx, orc.omesh_from_dict(g), 0, [("d", b, u) for b in range(6)], lambda x: -6., g["solution"])
+
+
+@pytest.mark.parametrize("method", [0, 1, 3])
+def test_solve_aniso_mixed_bc_vs_spsolve(ctx, golden, method):
+    g = golden("hex_aniso_432")
+    _solve_and_compare(ctx, orc.omesh_from_dict(g), method, BC_MIXED, FORCING, g["m%d_solution" % method])
+
+
+def test_solve_cut_polyhedral_vs_spsolve(ctx, golden):
+    g = golden("cut_checker_4")
+    o = orc.omesh_from_dict(g)
+    _solve_and_compare(ctx, o, 1, [("d", b, lin) for b in range(6)], None, g["m1_solution"])
+    bc = [("d", 0, lambda p: 1.), ("d", 1, lambda p: 0.)] + [("n", b, zero_flux) for b in (2, 3, 4, 5)]
+    _solve_and_compare(ctx, o, 1, bc, None, g["m1n_solution"])
+
+
+def test_solve_flow1d_known_answer(ctx, golden):
+    g = golden("flow1d_322")
+    o = orc.omesh_from_dict(g)
+    bc = [("d", 0, lambda p: 1.), ("d", 1, lambda p: 0.)] + [("n", b, zero_flux) for b in (2, 3, 4, 5)]
+    _solve_and_compare(ctx, o, 1, bc, None, g["solution"])
+
+
+def test_solve_24cubed_heterogeneous_vs_spsolve(ctx):
+    """C3 shape at n=16: log-normal diagonal K, method 1, Dirichlet x-/x+, no-flow elsewhere."""
+    n = 16
+    rng = np.random.default_rng(256)
+    kd = np.exp(rng.standard_normal((n ** 3, 3)))
+    ktab = np.zeros((n ** 3, 9))
+    ktab[:, 0], ktab[:, 4], ktab[:, 8] = kd[:, 0], kd[:, 1], kd[:, 2]
+    o = orc.hex_mesh(n, n, n, 1., 1., 1., k_array=ktab)
+    bc = [("d", 0, lambda p: 1.), ("d", 1, lambda p: 0.)] + [("n", b, zero_flux) for b in (2, 3, 4, 5)]
+    f = _oracle_system(o, 1, bc, None)
+    f.build_lhs(m_e_list=list(orc.build_m_e_batched(o, 1)))
+    f.build_rhs()
+    ref = f.solve()
+    info = _solve_and_compare(ctx, o, 1, bc, None, ref)
+    assert info.iterations < 5000
+
+
+# ---- two-phase kernels ---------------------------------------------------------------------------------
+def test_twophase_kernels_vs_reference_history(ctx, golden):
+    """Upwind flags + saturation step reproduce the reference's s_w to 1e-10 per step when driven
+    by the reference's own p/u_t history (isolates T2/T4/T5 from the linear solver)."""
+    import ctypes as C
+    import torch
+    from mimpy_b200 import device
+    from mimpy_b200._lib import ptr
+
+    for variant in ("wells", "inflow"):
+        g = golden("twophase_633_" + variant)
+        o = orc.omesh_from_dict(g)
+        d = device.DeviceMesh.from_oracle_mesh(ctx, o)
+        neu = (0, 2, 3, 4, 5) if variant == "wells" else (2, 3, 4, 5)
+        plan = device.symbolic(d, neumann_mask(o, neu))
+        F, nc = plan.flux_dof, o.nc
+        assert np.array_equal(H(ctx, plan.face_to_flux)[:o.nf], g["face_to_flux"])
+        fl = device.make_fluid(8.9e-4, 1.78e-3, 1000., 1000., 0., 0., 0., .2, 2., 2.)
+        dev = ctx.device
+        dt = float(g["delta_t"])
+        with ctx.on_stream():
+            s_w = torch.zeros(nc, dtype=torch.float64, device=dev)
+            f_w = torch.zeros(F, dtype=torch.float64, device=dev)
+            poro = torch.full((nc,), .2, dtype=torch.float64, device=dev)
+            upw = torch.empty(F, dtype=torch.int32, device=dev)
+            if variant == "wells":
+                wc = np.array([c for c in range(nc) if c % 6 == 0], dtype=np.int32)
+                wr = np.full(len(wc), 10. / 9)
+                bf = bs = bw = None
+                nb = 0
+            else:
+                wc = np.zeros(0, dtype=np.int32)
+                wr = np.zeros(0)
+                faces = [f for f, _ in o.boundary_faces[0]]
+                bf = torch.as_tensor(np.array(faces, dtype=np.int32), device=dev)
+                bs = torch.as_tensor(np.array([s for _, s in o.boundary_faces[0]], dtype=np.int8), device=dev)
+                # boundary saturation 1 -> se clipped to 1 -> kro = 0 -> f_w = 1
+                bw = torch.ones(len(faces), dtype=torch.float64, device=dev)
+                nb = len(faces)
+            twc = torch.as_tensor(wc, device=dev) if len(wc) else None
+            twr = torch.as_tensor(wr, device=dev) if len(wc) else None
+            mv = d.view()
+            p_prev = torch.zeros(nc, dtype=torch.float64, device=dev)
+            for step in range(1, int(g["steps"]) + 1):
+                p = torch.as_tensor(g["p_o"][step - 1], device=dev)
+                u = torch.as_tensor(g["u_t"][step - 1], device=dev)
+                if step == 1 or step % 10 == 0:
+                    ctx.call("mimpy_b200_twophase_upwind", C.byref(mv), C.byref(plan.s), ptr(u), ptr(upw))
+                    f_w.zero_()
+                ctx.call("mimpy_b200_twophase_saturation_step", C.byref(mv), C.byref(plan.s), C.byref(fl), dt,
+                         ptr(upw), ptr(u), ptr(p), ptr(p_prev), ptr(poro), nb, ptr(bf), ptr(bs), ptr(bw),
+                         len(wc), ptr(twc), ptr(twr), ptr(f_w), ptr(s_w))
+                got = s_w.cpu().numpy()
+                assert abs(got - g["s_w"][step - 1]).max() < 1e-10, (variant, step)
+                p_prev = p
