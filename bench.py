@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Benchmark of the MFD hot path on B200 (BASELINE.json metric):
+
+    MFD assembly Mcells/s + PCG s/iter & solve time, 256^3 hex, 1/2/4/8 B200
+
+    python bench.py --gpus N --steps K --warmup W          # our arm (CUDA)
+    python bench.py --impl reference --steps K --warmup W  # the reference algorithm on host cores
+
+Workload (BASELINE.json configs[2], SURVEY.md 8d "C3"): n^3 unit-cube hex mesh (n = 256),
+K = diag(exp g1, exp g2, exp g3) iid per cell (seed 256), M_E method 1, Dirichlet p=1 on x-,
+p=0 on x+, no-flow elsewhere, f = 0.  One step = numeric assembly of the saddle-point CSR
+(fused M_E construction + scatter) followed by the full solve (hybrid set-up, PCG to rtol,
+recovery of [v;p]).  `value` is the assembly throughput; PCG s/iter and time-to-solution ride in
+the same JSON line.  Inputs are resident in HBM for `value`; `e2e` goes through host buffers.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mfd_assembly_mcells_per_s"
+UNIT = "Mcells/s"
+ASM_BYTES_PER_CELL = 700.0     # 332 B read + 368 B written per hex cell
+PCG_BYTES_PER_ROW = lambda nnz_per_row: 12.0 * nnz_per_row + 108.0
+SPMV_BYTES_PER_ROW = lambda nnz_per_row: 12.0 * nnz_per_row + 20.0
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(parts[0]))
+                self.max_mhz = float(parts[1])
+                for nme, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nme)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def lognormal_k(nc, seed, sigma=1.0):
+    rng = np.random.default_rng(seed)
+    g = rng.standard_normal((nc, 3)) * sigma
+    k = np.zeros((nc, 9))
+    k[:, 0], k[:, 4], k[:, 8] = np.exp(g[:, 0]), np.exp(g[:, 1]), np.exp(g[:, 2])
+    return k
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference algorithm on host cores
+# ------------------------------------------------------------------------------------------
+def cpu_assembly_sample(n, seed=256):
+    """build_lhs + build_rhs of the reference algorithm (oracle port, per-cell Python/NumPy loop
+    exactly like mfd.py:545-599) on an n^3 sample of the workload. Returns (seconds, cells)."""
+    from oracle import mimpy_oracle as orc
+
+    k = lognormal_k(n ** 3, seed)
+    o = orc.hex_mesh(n, n, n, 1., 1., 1., k_array=k)
+    zero = lambda p: np.array([0., 0., 0.])
+    t0 = time.perf_counter()
+    f = orc.OracleMFD(o, 1)
+    f.apply_dirichlet_from_function(0, lambda p: 1.)
+    f.apply_dirichlet_from_function(1, lambda p: 0.)
+    for b in (2, 3, 4, 5):
+        f.apply_neumann_from_function(b, zero)
+    f.build_lhs()
+    f.build_rhs()
+    return time.perf_counter() - t0, n ** 3, f
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = args.ref_n
+    times = []
+    for s in range(args.warmup + args.steps):
+        dt, cells, f = cpu_assembly_sample(n)
+        if s >= args.warmup:
+            times.append(dt)
+    per = float(np.mean(times))
+    value = cells / per / 1e6
+    t0 = time.perf_counter()
+    f.solve()
+    t_solve = time.perf_counter() - t0
+    sample = "%d^3-cell sample (%d cells) of the 256^3 workload; assembly is O(cells)" % (n, cells)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3 hex n^3 log-normal diag K, method 1 (sampled at n=%d)" % n,
+                   "n": n, "cells": cells},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores_available": os.cpu_count(),
+                         "spsolve_s": t_solve, "spsolve_dof": int(f.flux_dof + f.o.nc)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    from mimpy_b200 import _lib, device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = _lib.Context(local_rank)
+    dev = ctx.device
+    n = args.n
+    peak, peak_src = measured_peak()
+
+    if world > 1:
+        from mimpy_b200 import partition
+        return partition.bench_multi_gpu(args, ctx, rank, world, peak, peak_src, ClockSampler)
+
+    # ---- problem set-up (untimed; inputs end up resident in HBM) ---------------------------
+    nc = n ** 3
+    k_host = lognormal_k(nc, 256)
+    t_setup = time.perf_counter()
+    dm = device.DeviceMesh.hex(ctx, n, n, n, 1., 1., 1., cell_k=k_host)
+    L = n * n + n * (n + 1) + (n + 1) * n
+    nf = dm.nf
+    with ctx.on_stream():
+        fp = dm.face_points  # boundary markers from the closed form: x- faces / x+ faces etc.
+        mask = torch.zeros(nf, dtype=torch.uint8, device=dev)
+        pts = dm.points
+        fc = dm.face_centroids
+        eps = 1e-9
+        on_y = (fc[:, 1] < eps) | (fc[:, 1] > 1. - eps)
+        on_z = (fc[:, 2] < eps) | (fc[:, 2] > 1. - eps)
+        mask[on_y | on_z] = 1
+        dir_faces = torch.nonzero(fc[:, 0] < eps).flatten().to(torch.int32)
+        # value = p(x_f) a_f sigma_bdry, p = 1 on x- (sigma -1), p = 0 on x+   (mfd.py:1157-1162)
+        dir_vals = -dm.face_areas[dir_faces.long()]
+        dir0_faces = torch.nonzero(fc[:, 0] > 1. - eps).flatten().to(torch.int32)
+        all_dir_faces = torch.cat([dir_faces, dir0_faces])
+        all_dir_vals = torch.cat([dir_vals, torch.zeros(dir0_faces.numel(), dtype=torch.float64, device=dev)])
+    plan = device.symbolic(dm, mask)
+    rhs = device.build_rhs(dm, plan, all_dir_faces.cpu().numpy(), all_dir_vals.cpu().numpy(), True, 0., None)
+    ctx.sync()
+    t_setup = time.perf_counter() - t_setup
+    F = plan.flux_dof
+    with ctx.on_stream():
+        vals = torch.empty(plan.nnz, dtype=torch.float64, device=dev)
+        del fc, on_y, on_z
+    method = 1
+
+    def step(collect):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        with ctx.on_stream():
+            evs[0].record(ctx.stream)
+            device.numeric(dm, plan, method, vals=vals)
+            evs[1].record(ctx.stream)
+            m_e, _, _ = device.local_matrices(dm, plan, method)
+            hyb = device.HybridSystem(dm, plan, m_e)
+            del m_e
+            evs[2].record(ctx.stream)
+            sol, info = hyb.solve(rhs, rtol=args.rtol, maxit=args.maxit, check_every=args.check_every,
+                                  raise_on_noconv=False)
+            evs[3].record(ctx.stream)
+        ctx.sync()
+        torch.cuda.synchronize()
+        out = {"asm_ms": evs[0].elapsed_time(evs[1]), "setup_ms": evs[1].elapsed_time(evs[2]),
+               "solve_ms": evs[2].elapsed_time(evs[3]), "pcg_ms": float(info.ms_total),
+               "iters": int(info.iterations), "residual": float(info.residual),
+               "rhs_norm": float(info.rhs_norm), "step_ms": evs[0].elapsed_time(evs[3])}
+        if collect:
+            out["sol"] = sol
+        del hyb
+        return out
+
+    for _ in range(args.warmup):
+        step(False)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    torch.cuda.synchronize()
+    res = []
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        res.append(step(s == args.steps - 1))
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    asm_ms = float(np.mean([r["asm_ms"] for r in res]))
+    step_ms = float(np.mean([r["step_ms"] for r in res]))
+    iters = res[-1]["iters"]
+    pcg_ms = float(np.mean([r["pcg_ms"] for r in res]))
+    s_per_iter = pcg_ms / 1e3 / max(iters, 1)
+    value = nc / (asm_ms / 1e3) / 1e6
+    nnz_row = plan.nnz_m / float(F)
+    asm_gbs = ASM_BYTES_PER_CELL * nc / (asm_ms / 1e3) / 1e9
+    pcg_gbs = PCG_BYTES_PER_ROW(nnz_row) * F / s_per_iter / 1e9
+
+    # residual of the ORIGINAL saddle system for the recovered [v;p] (correctness of the timed work)
+    sol = res[-1]["sol"]
+    with ctx.on_stream():
+        ax = device.spmv(ctx, plan.indptr, plan.indices, vals, sol, n=plan.ndof)
+        saddle_res = float(torch.linalg.norm(ax - rhs) / torch.linalg.norm(rhs))
+        p_mean = float(sol[F:].mean())
+
+    # ---- e2e: host buffers in, host buffers out (H2D of K, D2H of CSR values + solution) ----
+    e2e = None
+    if not args.no_e2e:
+        k_pin = torch.from_numpy(k_host).pin_memory()
+        vals_host = torch.empty(plan.nnz, dtype=torch.float64).pin_memory()
+        sol_host = torch.empty(plan.ndof, dtype=torch.float64).pin_memory()
+        e2e_times = []
+        for s in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            with ctx.on_stream():
+                dm.cell_k.copy_(k_pin.reshape(nc, 9), non_blocking=True)
+                device.numeric(dm, plan, method, vals=vals)
+                vals_host.copy_(vals, non_blocking=True)
+            ctx.sync()
+            torch.cuda.synchronize()
+            e2e_times.append(time.perf_counter() - t0)
+        e2e_s = min(e2e_times)
+        e2e = {"value": nc / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(k_pin.numel() * 8),
+               "d2h_bytes_per_step": int(vals_host.numel() * 8),
+               "what": "cell_k from pinned host -> numeric assembly -> CSR values to pinned host"}
+        del k_pin, vals_host, sol_host
+
+    # ---- cpu baseline: the reference algorithm on this box's host cores, bounded sample -----
+    cpu = None
+    if not args.no_cpu:
+        dt, cells, f = cpu_assembly_sample(args.cpu_n)
+        cpu = {"value": cells / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+               "host_cores_available": os.cpu_count(),
+               "sample": "%d^3 cells of the same workload (build_lhs+build_rhs, %.1f s); O(cells)" % (args.cpu_n, dt)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3: %d^3 hex, log-normal diag K (seed 256), method 1, Dirichlet x-/x+, no-flow else" % n,
+                   "cells": nc, "faces": nf, "flux_dof": F, "saddle_nnz": plan.nnz, "face_system_nnz": plan.nnz_m,
+                   "l2": "inputs larger than L2 (>= %.1f GB touched per step)" % (ASM_BYTES_PER_CELL * nc / 1e9),
+                   "pcg": {"preconditioner": "jacobi", "rtol": args.rtol, "check_every": args.check_every}},
+        "assembly_ms": asm_ms, "hybrid_setup_ms": float(np.mean([r["setup_ms"] for r in res])),
+        "pcg_iters": iters, "pcg_s_per_iter": s_per_iter, "solve_time_s": float(np.mean([r["solve_ms"] for r in res])) / 1e3,
+        "pcg_rel_residual": res[-1]["residual"] / max(res[-1]["rhs_norm"], 1e-300),
+        "saddle_rel_residual": saddle_res, "mean_pressure": p_mean,
+        "roofline": {"bound": "hbm", "achieved": asm_gbs, "peak": peak, "unit": "GB/s", "frac": asm_gbs / peak,
+                     "traffic": None, "kernel": "k_local_matrices<8,true> (fused M_E + CSR scatter)",
+                     "peak_source": peak_src, "frac_of_8TBs_spec": asm_gbs / 8000.,
+                     "algorithmic_bytes_per_cell": ASM_BYTES_PER_CELL},
+        "roofline_pcg": {"bound": "hbm", "achieved": pcg_gbs, "peak": peak, "unit": "GB/s", "frac": pcg_gbs / peak,
+                         "algorithmic_bytes_per_row": PCG_BYTES_PER_ROW(nnz_row), "rows": F},
+        "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": int(args.steps * (2 + 1 + 4 + 2 + 3 * iters + 4)),
+        "clocks": sampler.summary(), "setup_s": t_setup, "wall_s_timed": wall,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--rtol", type=float, default=1e-8)
+    ap.add_argument("--maxit", type=int, default=20000)
+    ap.add_argument("--check-every", type=int, default=50)
+    ap.add_argument("--cpu-n", type=int, default=40)
+    ap.add_argument("--ref-n", type=int, default=32)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_cuda(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

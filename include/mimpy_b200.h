@@ -36,6 +36,10 @@ extern "C" {
 
 #define MIMPY_MAX_CELL_FACES 32 /* one warp lane per face of a cell */
 
+/* flags of mfd_local_matrices / mfd_numeric */
+#define MIMPY_FLAG_K_UNITY 1        /* N_E = s n (mfd.py:300-304)                          */
+#define MIMPY_FLAG_GENERIC_KERNEL 2 /* force the generic warp-group kernel (tests, polyhedra) */
+
 typedef struct mimpy_ctx mimpy_ctx;
 
 int mimpy_b200_version(void);
@@ -151,6 +155,10 @@ typedef struct {
   uint8_t* pos_dt;    /* cell_ptr[nc]                          */
   uint8_t* pos_d;     /* cell_ptr[nc]                          */
   uint8_t* diag_pos;  /* nf                                    */
+  uint8_t* role;      /* cell_ptr[nc]: 0 = the face has this cell only, 1 = this is the lower-index
+                         cell of a shared face, 2 = the higher-index one (finishes the diagonal)   */
+  int32_t* cell_rowstart; /* cell_ptr[nc]: indptr[g(f_i)] per (cell, face), -1 on Neumann faces --
+                         saves the numeric kernel the dependent gathers f -> g(f) -> indptr[g]    */
 } mimpy_symbolic;
 
 int mimpy_b200_mfd_symbolic_sizes(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,

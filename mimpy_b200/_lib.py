@@ -27,7 +27,8 @@ class Symbolic(C.Structure):
     _fields_ = [("flux_dof", _i32), ("nnz", _i64), ("nnz_m", _i64), ("n_blocks", _i64),
                 ("face_to_flux", _vp), ("face_cell", _vp), ("indptr", _vp), ("indices", _vp),
                 ("m_indptr", _vp), ("m_indices", _vp), ("m_ptr", _vp), ("pos_m", _vp),
-                ("pos_dt", _vp), ("pos_d", _vp), ("diag_pos", _vp)]
+                ("pos_dt", _vp), ("pos_d", _vp), ("diag_pos", _vp), ("role", _vp),
+                ("cell_rowstart", _vp)]
 
 
 class PcgInfo(C.Structure):

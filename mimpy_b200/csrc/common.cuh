@@ -23,6 +23,10 @@ struct mimpy_ctx {
 };
 
 void mimpy_set_error(const char* fmt, ...);
+// uniform-face-count fast path of the numeric assembly (assemble_uniform.cu)
+int mimpy_numeric_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
+                          int method, int flags, const double* multipliers, double alpha,
+                          const double* c_diag, double* vals);
 int mimpy_scratch(mimpy_ctx* ctx, size_t bytes, void** out);
 
 #define CUDA_TRY(expr)                                                                   \

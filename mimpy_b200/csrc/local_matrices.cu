@@ -434,6 +434,11 @@ int mimpy_b200_mfd_numeric(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mi
   REQUIRE(method >= 0 && method <= 7 && method != 4, "unsupported M_E construction method");
   REQUIRE((flags & 1) || mesh->cell_k, "cell_k is NULL");
   if (mesh->nc <= 0) return MIMPY_OK;
+  if (!m_e_out && !(flags & MIMPY_FLAG_GENERIC_KERNEL)) {
+    // uniform-face-count fast path (hexes); same arithmetic, thread-per-cell mapping
+    rc = mimpy_numeric_uniform(ctx, mesh, sym, method, flags, multipliers, alpha, c_diag, vals);
+    if (rc != MIMPY_E_UNSUPPORTED) return rc;
+  }
   const int F = sym->flux_dof;
   if (F > 0) {
     k_zero_diag<<<(F + 255) / 256, 256, 0, ctx->stream>>>(F, sym->indptr, sym->diag_pos, vals);

@@ -138,7 +138,8 @@ __global__ void k_fill_cells(int nc, int F, const int* __restrict__ cell_ptr,
                              int* __restrict__ indices, const int* __restrict__ m_indptr,
                              const int* __restrict__ m_indices, const int* __restrict__ m_ptr,
                              uint8_t* __restrict__ pos_m, uint8_t* __restrict__ pos_dt,
-                             uint8_t* __restrict__ pos_d) {
+                             uint8_t* __restrict__ pos_d, uint8_t* __restrict__ role,
+                             int* __restrict__ cell_rowstart) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= cell_ptr[nc]) return;
   // find the cell of entry t: binary search in cell_ptr
@@ -157,6 +158,11 @@ __global__ void k_fill_cells(int nc, int F, const int* __restrict__ cell_ptr,
   const int fi = cell_faces[base + i];
   const int gi = f2f[fi];
   uint8_t* pm = pos_m + m_ptr[c] + (size_t)i * n;
+  if (role) {
+    const int c_lo = face_cell[2 * (size_t)fi], c_hi = face_cell[2 * (size_t)fi + 1];
+    role[base + i] = (c_hi < 0) ? 0 : (c == c_lo ? 1 : 2);
+  }
+  if (cell_rowstart) cell_rowstart[base + i] = (gi >= 0) ? indptr[gi] : -1;
   if (gi < 0) {
     for (int j = 0; j < n; ++j) pm[j] = 0xFF;
     pos_dt[base + i] = 0xFF;
@@ -278,7 +284,8 @@ int mimpy_b200_mfd_symbolic_fill(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, mi
     k_fill_cells<<<(unsigned)blocks, T, 0, st>>>(nc, F, mesh->cell_ptr, mesh->cell_faces,
                                                  sym->face_to_flux, sym->face_cell, sym->indptr,
                                                  sym->indices, sym->m_indptr, sym->m_indices,
-                                                 sym->m_ptr, sym->pos_m, sym->pos_dt, sym->pos_d);
+                                                 sym->m_ptr, sym->pos_m, sym->pos_dt, sym->pos_d,
+                                                 sym->role, sym->cell_rowstart);
     KERNEL_CHECK();
   }
   return MIMPY_OK;

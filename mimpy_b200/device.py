@@ -232,6 +232,10 @@ def symbolic(dmesh, neumann_mask):
         s.pos_m = t["pos_m"].data_ptr()
         s.pos_dt = t["pos_dt"].data_ptr()
         s.pos_d = t["pos_d"].data_ptr()
+        t["role"] = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+        s.role = t["role"].data_ptr()
+        t["cell_rowstart"] = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        s.cell_rowstart = t["cell_rowstart"].data_ptr()
         s.diag_pos = t["diag_pos"].data_ptr()
         ctx.call("mimpy_b200_mfd_symbolic_fill", C.byref(mv), C.byref(s))
         plan.mask = mask
@@ -270,15 +274,17 @@ def block_offsets(dmesh):
 
 
 def numeric(dmesh, plan, method, k_unity=False, multipliers=None, alpha=0., c_diag=None, vals=None,
-            m_e_out=None):
-    """A2-A5+A8: fused M_E construction + CSR scatter (mimpy_b200_mfd_numeric)."""
+            m_e_out=None, generic_kernel=False, debug_flags=0):
+    """A2-A5+A8: fused M_E construction + CSR scatter (mimpy_b200_mfd_numeric).
+    generic_kernel=True forces the warp-group kernel even on uniform (hex) meshes."""
     ctx = dmesh.ctx
     with ctx.on_stream():
         if vals is None:
             vals = torch.empty(max(plan.nnz, 1), dtype=torch.float64, device=ctx.device)
         mv = dmesh.view()
+        flags = (1 if k_unity else 0) | (2 if generic_kernel else 0) | int(debug_flags)
         ctx.call("mimpy_b200_mfd_numeric", C.byref(mv), C.byref(plan.s), int(method),
-                 1 if k_unity else 0, ptr(multipliers), float(alpha), ptr(c_diag), ptr(vals),
+                 flags, ptr(multipliers), float(alpha), ptr(c_diag), ptr(vals),
                  ptr(m_e_out))
     return vals
 
