@@ -267,6 +267,13 @@ typedef struct {
 int mimpy_b200_twophase_mobility(mimpy_ctx* ctx, int32_t nc, const mimpy_fluid* fluid_host,
                                  const double* s_w, const double* p, double* inv_total_mobility,
                                  double* water_mob, double* oil_mob);
+/* Newton set-up of TwoPhase.update_pressure (twophase.py:764-816): c_diag[c] = accumulation
+ * diagonal (rho_w s c_w + rho_o c_o (1-s)) phi |E| / dt, and rhs[flux_dof+c] += f1 + f2 - f3 (the
+ * phase masses at time n minus their linearisation at pressure p_n).  rhs / c_diag may be NULL. */
+int mimpy_b200_twophase_newton_terms(mimpy_ctx* ctx, int32_t nc, int32_t flux_dof,
+                                     const mimpy_fluid* fluid_host, double dt, const double* s_w,
+                                     const double* p_n, const double* porosity,
+                                     const double* cell_volume, double* rhs, double* c_diag);
 int mimpy_b200_twophase_upwind(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,
                                const mimpy_symbolic* sym, const double* u_t,
                                int32_t* upwind_cell /*flux_dof*/);

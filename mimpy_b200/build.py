@@ -18,10 +18,10 @@ LIB = os.path.join(HERE, "libmimpy_b200.so")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 
 SOURCES = ["context.cu", "geometry.cu", "symbolic.cu", "local_matrices.cu", "assemble_uniform.cu", "hybrid.cu", "pcg.cu",
-           "twophase.cu", "rhs.cu", "partition.cu"]
+           "twophase.cu", "rhs.cu", "comm.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC,
-          "-DMIMPY_WITH_NCCL"]
+          "-I", "/usr/include"]
 PER_FILE = {"geometry.cu": ["-fmad=false"]}
 
 
@@ -69,7 +69,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc compilation failed")
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-lnccl"]
+        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
         if verbose:
             print(" ".join(cmd))
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

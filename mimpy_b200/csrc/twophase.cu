@@ -204,3 +204,57 @@ int mimpy_b200_twophase_saturation_step(mimpy_ctx* ctx, const mimpy_mesh_view* m
 }
 
 }  // extern "C"
+
+// Newton set-up of TwoPhase.update_pressure (twophase.py:764-816): the accumulation diagonal
+//   C_c = (rho_w s c_w + rho_o c_o (1-s)) phi |E| / dt
+// and the cell part of the residual  rhs[F+c] += f1 + f2 - f3  (mass of both phases at time n
+// minus its linearisation), evaluated with the pressure of time level n.
+__global__ void k_newton_cell_terms(int nc, int F, mimpy_fluid fl, double dt,
+                                    const double* __restrict__ s_w, const double* __restrict__ p_n,
+                                    const double* __restrict__ porosity, const double* __restrict__ vol,
+                                    double* __restrict__ rhs, double* __restrict__ c_diag) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const double s = s_w[c], phi = porosity[c], v = vol[c], p = p_n[c];
+  if (c_diag) {
+    double cm = fl.rho_w * s;
+    cm *= fl.c_w;
+    cm += fl.rho_o * (fl.c_o * (1. - s));
+    cm *= phi;
+    cm *= v;
+    cm /= dt;
+    c_diag[c] = cm;
+  }
+  if (rhs) {
+    double f1 = 1. * (fl.rho_w * s);
+    f1 *= phi / dt;
+    f1 *= v;
+    double f2 = 1. * fl.rho_o;
+    f2 *= 1. - s;
+    f2 *= phi / dt;
+    f2 *= v;
+    double f3 = 0. + fl.rho_w * (1. + fl.c_w * p);
+    f3 *= s;
+    f3 += fl.rho_o * (1 + fl.c_o * p) * (1. - s);
+    f3 *= phi / dt;
+    f3 *= v;
+    double r = rhs[F + c];
+    r += f1;
+    r += f2;
+    r -= f3;
+    rhs[F + c] = r;
+  }
+}
+
+extern "C" int mimpy_b200_twophase_newton_terms(mimpy_ctx* ctx, int32_t nc, int32_t flux_dof,
+                                                const mimpy_fluid* fluid_host, double dt,
+                                                const double* s_w, const double* p_n,
+                                                const double* porosity, const double* cell_volume,
+                                                double* rhs, double* c_diag) {
+  REQUIRE(ctx && fluid_host && s_w && p_n && porosity && cell_volume, "NULL argument");
+  if (nc <= 0) return MIMPY_OK;
+  k_newton_cell_terms<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(nc, flux_dof, *fluid_host, dt, s_w, p_n,
+                                                                 porosity, cell_volume, rhs, c_diag);
+  KERNEL_CHECK();
+  return MIMPY_OK;
+}

@@ -1,0 +1,184 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol the header declares, the
+ctypes structures match the C layouts, and the host-side mesh logic (ragged arrays, plane cutting,
+planar polygon geometry) reproduces the reference.  No compute call is made without a GPU."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import mimpy_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "mimpy_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from mimpy_b200 import build
+
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    hdr = open(HEADER).read()
+    names = sorted(set(re.findall(r"\b(mimpy_b200_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 25
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.mimpy_b200_version() >= 100
+
+
+def test_ctypes_signatures_cover_the_header(lib_path):
+    from mimpy_b200 import _lib
+
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    names = set(re.findall(r"\b(mimpy_b200_[a-z0-9_]+)\s*\(", hdr)) - {"mimpy_b200_last_error"}
+    undeclared = [n for n in sorted(names) if n not in _lib.SIGNATURES]
+    assert not undeclared, undeclared
+    # argument counts agree with the prototypes
+    for name in names:
+        m = re.search(r"int\s+" + name + r"\s*\(([^;]*?)\)\s*;", hdr, re.S)
+        assert m, name
+        args = [a for a in m.group(1).split(",") if a.strip() and a.strip() != "void"]
+        assert len(args) == len(_lib.SIGNATURES[name]), name
+
+
+def test_struct_layouts_match_c(lib_path):
+    """sizeof/offsetof of every struct that crosses the boundary, from a C program built with gcc."""
+    from mimpy_b200 import _lib
+
+    structs = {"mimpy_mesh_view": _lib.MeshView, "mimpy_symbolic": _lib.Symbolic,
+               "mimpy_pcg_info": _lib.PcgInfo, "mimpy_fluid": _lib.Fluid}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "mimpy_b200.h"', 'int main(void){']
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines.append('return 0;}')
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, "layout.c")
+        open(src, "w").write("\n".join(lines))
+        exe = os.path.join(tmp, "layout")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    got = dict(l.split() for l in out.strip().splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_product_has_no_cpu_fallback_and_never_imports_the_oracle():
+    """The product path must fail loudly without CUDA and must not route through oracle/."""
+    import torch
+    from mimpy_b200 import _lib
+
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            _lib.Context()
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "mimpy_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), f
+                assert "scipy.sparse.linalg" not in text and "spsolve" not in text.replace("'spsolve'", "").replace("('spsolve')", "").replace("solve('spsolve')", ""), f
+
+
+# ---- host mesh logic -----------------------------------------------------------------------------
+def test_variable_array_semantics():
+    from mimpy_b200.mesh.mesh import variable_array
+
+    a = variable_array(dtype=np.dtype('i'))
+    idx = [a.add_entry(list(range(k, k + 3 + k % 4))) for k in range(2500)]
+    assert idx == list(range(2500)) and len(a) == 2500
+    assert list(a[7]) == list(range(7, 7 + 3 + 3))
+    a[7] = [1, 2]                      # shorter: in place
+    assert list(a[7]) == [1, 2]
+    a[8] = list(range(40))             # longer: re-appended
+    assert list(a[8]) == list(range(40)) and list(a[9]) == list(range(9, 9 + 3 + 1))
+    ptr, data = a.compact()
+    assert ptr[-1] == len(data) and list(data[ptr[8]:ptr[9]]) == list(range(40))
+    with pytest.raises(IndexError):
+        a[2500]
+
+
+def mesh_from_omesh(o):
+    """Host-only construction through the public Mesh API (no GPU)."""
+    from mimpy_b200.mesh.mesh import Mesh
+
+    m = Mesh()
+    for p in o.points:
+        m.add_point(p)
+    for f in range(o.nf):
+        m.add_face(list(o.face(f)))
+        m.set_face_area(f, o.face_areas[f])
+        m.set_face_normal(f, o.face_normals[f])
+        m.set_face_real_centroid(f, o.face_centroids[f])
+    m.set_boundary_markers(sorted(o.boundary_faces), ["b%d" % b for b in sorted(o.boundary_faces)])
+    for b, lst in o.boundary_faces.items():
+        for f, s in lst:
+            m.add_boundary_face(b, f, s)
+    for c in range(o.nc):
+        m.add_cell(list(o.cell(c)), list(o.sigma(c)))
+        m.set_cell_volume(c, o.cell_volume[c])
+        m.set_cell_real_centroid(c, o.cell_centroid[c])
+        m.set_cell_k(c, o.cell_k[c].reshape(3, 3))
+    return m
+
+
+def test_mesh_roundtrip_and_cutting_reproduce_reference(golden):
+    g = golden("cut_checker_4")
+    ref = orc.omesh_from_dict(g)
+    rng = np.random.default_rng(5)
+    n = 4
+    ktab = np.zeros((n ** 3, 3, 3))
+    for c in range(n ** 3):  # same generator as tests/golden/gen_golden.py:spd_tensors(64, 5)
+        gg = rng.standard_normal(3)
+        q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+        ktab[c] = q @ np.diag(np.exp(gg)) @ q.T
+    m = mesh_from_omesh(orc.hex_mesh(n, n, n, 1., 1., 1., k_array=ktab))
+    assert m.get_number_of_cells() == 64 and m.get_number_of_faces() == 240
+    nrm = np.array([1.2, .2, 1.3])
+    nrm /= np.linalg.norm(nrm)
+    for c in range(n ** 3):
+        i, j, k = c % n, (c // n) % n, c // (n * n)
+        if (i + j + k) % 2 == 0:
+            m.divide_cell_by_plane(c, np.array(m.get_cell_real_centroid(c)), nrm)
+    o = orc.OMesh.from_mesh(m)
+    for key in ("face_ptr", "face_points", "cell_ptr", "cell_faces", "cell_sigma"):
+        assert np.array_equal(getattr(o, key), getattr(ref, key)), key
+    assert {b: [(int(a), int(s)) for a, s in v] for b, v in o.boundary_faces.items()} == ref.boundary_faces
+    assert np.allclose(o.points, ref.points, rtol=1e-14, atol=1e-16)
+    assert np.allclose(o.face_areas, ref.face_areas, rtol=1e-12, atol=0)
+    assert np.allclose(o.face_centroids, ref.face_centroids, rtol=1e-12, atol=1e-15)
+    assert np.allclose(o.face_normals, ref.face_normals, rtol=1e-12, atol=1e-15)
+    assert np.allclose(o.cell_volume, ref.cell_volume, rtol=1e-12, atol=0)
+    assert np.allclose(o.cell_centroid, ref.cell_centroid, rtol=1e-11, atol=1e-14)
+    assert np.array_equal(o.cell_k, ref.cell_k)
+    # unlike the reference (mesh.py:2405-2410) the cut face keeps BOTH of its cells
+    assert np.array_equal(m.face_to_cell[:o.nf], orc.rebuild_face_to_cell(o))
+
+
+def test_hexmesh_closed_form_tables_match_reference(golden):
+    """HexMesh's closed-form face numbering / boundary lists (host part, no GPU needed)."""
+    from mimpy_b200.mesh.hexmesh import HexMesh
+
+    for name, dims in (("hex_c1_n5", (5, 5, 5)), ("hex_aniso_432", (4, 3, 2)), ("flow1d_322", (3, 2, 2))):
+        ref = orc.omesh_from_dict(golden(name))
+        h = HexMesh()
+        h.ni, h.nj, h.nk = dims[0] + 1, dims[1] + 1, dims[2] + 1
+        got = {m: [(f, s) for f, s in v] for m, v in h._boundary_lists().items()}
+        assert got == ref.boundary_faces
+        zf, yf, xf = h._face_tables()
+        cx, cy, cz = dims
+        c = np.arange(cx * cy * cz)
+        i, j, k = c % cx, (c // cx) % cy, c // (cx * cy)
+        cells = np.stack([zf(i, j, k), yf(i, j, k), xf(i, j, k), xf(i + 1, j, k), yf(i, j + 1, k), zf(i, j, k + 1)], 1)
+        assert np.array_equal(cells.ravel(), ref.cell_faces)
+        assert h.ijk_to_cell_index(1, 1, 1) == 1 + cx + cx * cy

@@ -1,0 +1,232 @@
+"""Drop-in API parity on the GPU: the scripts a mimpy user writes (HexMesh / MFD / TwoPhase)
+produce what the reference produced (golden vectors) -- run with pytest -m gpu."""
+import numpy as np
+import pytest
+from scipy import sparse
+
+from oracle import mimpy_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+zero_flux = lambda p: np.array([0., 0., 0.])
+lin = lambda p: 1. + 2. * p[0] - p[1] + .5 * p[2]
+
+
+def spd_tensors(nc, seed, full=True):
+    rng = np.random.default_rng(seed)
+    out = np.zeros((nc, 3, 3))
+    for c in range(nc):
+        g = rng.standard_normal(3)
+        if full:
+            q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+            out[c] = q @ np.diag(np.exp(g)) @ q.T
+        else:
+            out[c] = np.diag(np.exp(g))
+    return out
+
+
+def assert_mesh_equals_reference(mesh, ref, geometry_exact=True):
+    o = orc.OMesh.from_mesh(mesh)
+    for k in ("face_ptr", "face_points", "cell_ptr", "cell_faces", "cell_sigma"):
+        assert np.array_equal(getattr(o, k), getattr(ref, k)), k
+    assert {m: [(int(a), int(b)) for a, b in v] for m, v in o.boundary_faces.items()} == ref.boundary_faces
+    cmp = np.array_equal if geometry_exact else (lambda a, b: np.allclose(a, b, rtol=1e-12, atol=1e-14))
+    for k in ("points", "face_areas", "face_normals", "face_centroids"):
+        assert cmp(getattr(o, k), getattr(ref, k)), k
+    assert np.allclose(o.cell_volume, ref.cell_volume, rtol=1e-12, atol=0)
+    assert np.allclose(o.cell_centroid, ref.cell_centroid, rtol=1e-11, atol=1e-14)
+    assert np.array_equal(o.cell_k, ref.cell_k)
+    return o
+
+
+def test_example1_script_matches_reference(golden):
+    """hexmesh_example_1.py (BASELINE config 1) with only the imports changed."""
+    import mimpy_b200.mesh.hexmesh as hexmesh
+    import mimpy_b200.mfd.mfd as mfd
+
+    g = golden("hex_c1_n5")
+    res_mfd = mfd.MFD()
+    res_mfd.set_compute_diagonality(True)
+    res_mfd.set_m_e_construction_method(0)
+    K = lambda p, i, j, k: np.eye(3)
+    u = lambda p: p[0] ** 2 + p[1] ** 2 + p[2] ** 2
+    res_mesh = hexmesh.HexMesh()
+    res_mesh.build_mesh(5, 5, 5, 1., 1., 1., K, lambda p, i, j, k: p)
+    ref = orc.omesh_from_dict(g)
+    assert_mesh_equals_reference(res_mesh, ref)
+    assert np.array_equal(res_mesh.face_to_cell[:ref.nf], ref.face_to_cell)
+    res_mfd.set_mesh(res_mesh)
+    for b in range(6):
+        res_mfd.apply_dirichlet_from_function(b, lambda p: u(p))
+    res_mfd.apply_forcing_from_function(lambda x: -6.)
+    lhs = res_mfd.build_lhs()
+    rhs = res_mfd.build_rhs()
+    assert np.array_equal(res_mfd.face_to_flux[:, 0], g["face_to_flux"])
+    assert res_mfd.flux_dof == int(g["flux_dof"])
+    n = lhs.shape[0]
+    gref = sparse.csr_matrix((g["csr_data"], g["csr_indices"], g["csr_indptr"]), shape=(n, n))
+    assert abs(lhs - gref).max() <= 1e-12 * abs(gref).max()
+    assert np.array_equal(rhs, g["rhs"])
+    sol = res_mfd.solve()
+    assert np.linalg.norm(sol - g["solution"]) <= 1e-8 * np.linalg.norm(g["solution"])
+    p = res_mfd.get_pressure_solution()
+    exact = np.array(res_mfd.get_analytical_pressure_solution(u))
+    assert abs(abs(p - exact).max() - (1. / 5) ** 2 / 4) < 1e-9   # h^2/4 (SURVEY 8c ii)
+    assert res_mfd.get_diagonality().max() < 1e-8                    # iso K, method 0: diagonal M_E
+    assert abs(res_mfd.compute_l2_error_pressure(u) - np.sqrt(np.sum(ref.cell_volume * (p - exact) ** 2))) < 1e-14
+
+
+def test_build_m_div_bottom_right_like_reference(golden):
+    import mimpy_b200.mesh.hexmesh as hexmesh
+    import mimpy_b200.mfd.mfd as mfd
+
+    g = golden("hex_aniso_432")
+    ref = orc.omesh_from_dict(g)
+    mesh = hexmesh.HexMesh()
+    mesh.build_mesh(4, 3, 2, 2., 1.5, 1., ref.cell_k.reshape(-1, 3, 3))
+    assert_mesh_equals_reference(mesh, ref)
+    f = mfd.MFD()
+    f.set_m_e_construction_method(1)
+    f.set_mesh(mesh)
+    f.apply_dirichlet_from_function(0, lambda p: 1. + 0.3 * p[1])
+    f.apply_dirichlet_from_function(1, lambda p: 0.2 * p[2])
+    for b in (2, 3, 4, 5):
+        f.apply_neumann_from_function(b, zero_flux)
+    f.apply_forcing_from_function(lambda x: np.sin(3. * x[0]) + x[1] * x[2])
+    data, row, col = f.build_m(save_update_info=True)
+    (dd, dr, dc), (td, tr, tc) = f.build_div()
+    cd, cr, cc = f.build_bottom_right()
+    # full-tensor K + method 1: the reference keeps every structural entry -> identical COO stream
+    nm = len(data)
+    assert np.array_equal(row, g["m1_coo_row"][:nm]) and np.array_equal(col, g["m1_coo_col"][:nm])
+    assert np.allclose(data, g["m1_coo_data"][:nm], rtol=0, atol=1e-12 * abs(g["m1_coo_data"]).max())
+    nd = len(dd)
+    assert np.array_equal(np.concatenate([dd, td, cd]), g["m1_coo_data"][nm:])
+    assert np.array_equal(np.concatenate([dr, tr, cr]), g["m1_coo_row"][nm:])
+    assert np.array_equal(np.concatenate([dc, tc, cc]), g["m1_coo_col"][nm:])
+    assert f.m_e_locations[-1] == nm
+    # per-cell block through the API
+    blk = f.build_m_e(7)
+    ref_blk = g["m1_m_e_flat"][7 * 36:8 * 36].reshape(6, 6)
+    assert np.linalg.norm(blk - ref_blk) <= 1e-12 * np.linalg.norm(ref_blk)
+    f.build_lhs()
+    f.build_rhs()
+    sol = f.solve()
+    assert np.linalg.norm(sol - g["m1_solution"]) <= 1e-8 * np.linalg.norm(g["m1_solution"])
+
+
+def test_reference_unit_tests_divide_cell_by_plane():
+    """The reference's own tests (tests/test_divide_cell_by_plane.py:12-58) against our Mesh."""
+    import mimpy_b200.mesh.hexmesh as hexmesh
+
+    K = lambda x, i, j, k: np.eye(3)
+    for normal in [np.array([1., 0., 0.]), np.array([0., 1., 0.]), np.array([0., 0., 1.]),
+                   -np.array([1., 0., 0.]), -np.array([0., 1., 0.]), -np.array([0., 0., 1.])]:
+        m = hexmesh.HexMesh()
+        m.build_mesh(1, 1, 1, 1., 1., 1., K)
+        m.divide_cell_by_plane(0, np.array([.5, .5, .5]), normal)
+        assert m.get_number_of_cells() == 2
+        assert abs(m.get_cell_volume(0) - .5) < 1.e-12
+        assert abs(m.get_cell_volume(1) - .5) < 1.e-12
+    for normal in [np.array([1.2, .8, 0.]), np.array([1.2, .2, 1.3]), -np.array([1.2, .8, 0.]), -np.array([1.2, .2, 1.3])]:
+        m = hexmesh.HexMesh()
+        m.build_mesh(1, 1, 1, 1., 1., 1., K)
+        m.divide_cell_by_plane(0, np.array([.5, .5, .5]), normal)
+        assert m.get_number_of_cells() == 2
+        m = hexmesh.HexMesh()
+        m.build_mesh(3, 3, 3, 1., 1., 1., K)
+        c = m.find_cell_near_point(np.array([.5, .5, .5]))
+        m.divide_cell_by_plane(c, np.array([.5, .5, .5]), normal)
+        assert m.get_number_of_cells() == 28
+        assert abs(m.cell_volume[:28].sum() - 1.) < 1e-13
+
+
+def test_cut_mesh_generator_and_solve_match_reference(golden):
+    """BASELINE config 5 shape: checkerboard of plane-cut cells built with OUR divide_cell_by_plane
+    equals the reference's mesh, and the GPU solve equals the reference's spsolve."""
+    import mimpy_b200.mesh.hexmesh as hexmesh
+    import mimpy_b200.mfd.mfd as mfd
+
+    g = golden("cut_checker_4")
+    ref = orc.omesh_from_dict(g)
+    n = 4
+    ktab = spd_tensors(n ** 3, 5, full=True)
+    mesh = hexmesh.HexMesh()
+    mesh.build_mesh(n, n, n, 1., 1., 1., ktab)
+    nrm = np.array([1.2, .2, 1.3])
+    nrm /= np.linalg.norm(nrm)
+    for c in range(n ** 3):
+        i, j, k = mesh.cell_to_ijk[c]
+        if (i + j + k) % 2 == 0:
+            mesh.divide_cell_by_plane(c, np.array(mesh.get_cell_real_centroid(c)), nrm)
+    assert_mesh_equals_reference(mesh, ref, geometry_exact=False)
+    # all volumes again on the GPU (Mirtich kernel, general polyhedra)
+    vol_cut = mesh.cell_volume[:ref.nc].copy()
+    mesh.find_volume_centroid_all()
+    assert np.allclose(mesh.cell_volume[:ref.nc], vol_cut, rtol=1e-12, atol=0)
+    f = mfd.MFD()
+    f.set_m_e_construction_method(1)
+    f.set_mesh(mesh)
+    for b in range(6):
+        f.apply_dirichlet_from_function(b, lin)
+    f.build_lhs()
+    f.build_rhs()
+    sol = f.solve()
+    assert np.linalg.norm(sol - g["m1_solution"]) <= 1e-8 * np.linalg.norm(g["m1_solution"])
+
+
+@pytest.mark.parametrize("variant", ["wells", "inflow"])
+def test_twophase_model_matches_reference_history(golden, variant):
+    """BASELINE config 4 shape at 6x3x3: 12 IMPES steps; s_w within 1e-10 per step, p/u within 1e-8."""
+    import mimpy_b200.mesh.hexmesh as hexmesh
+    import mimpy_b200.models.twophase as twophase
+
+    g = golden("twophase_633_" + variant)
+    ref = orc.omesh_from_dict(g)
+    nx, ny, nz = 6, 3, 3
+    mesh = hexmesh.HexMesh()
+    mesh.build_mesh(nx, ny, nz, 6., 3., 3., ref.cell_k.reshape(-1, 3, 3))
+    tp = twophase.TwoPhase()
+    tp.set_mesh(mesh)
+    nc = mesh.get_number_of_cells()
+    if variant == "wells":
+        for b in (0, 2, 3, 4, 5):
+            tp.apply_flux_boundary_from_function(b, zero_flux)
+        tp.apply_pressure_boundary_from_function(1, lambda p: 0.)
+    else:
+        for b in (2, 3, 4, 5):
+            tp.apply_flux_boundary_from_function(b, zero_flux)
+        tp.apply_pressure_boundary_from_function(0, lambda p: 2.e5)
+        tp.apply_pressure_boundary_from_function(1, lambda p: 0.)
+        tp.set_saturation_boundaries(0, lambda p: 1.)
+    tp.set_initial_p_o(np.zeros(nc))
+    tp.set_initial_s_w(np.zeros(nc))
+    tp.set_porosities(np.array([.2] * nc))
+    tp.set_viscosity_water(8.9e-4)
+    tp.set_viscosity_oil(1.78e-3)
+    tp.set_compressibility_water(0.)
+    tp.set_compressibility_oil(0.)
+    tp.set_ref_density_water(1000.)
+    tp.set_ref_density_oil(1000.)
+    tp.set_ref_pressure_oil(0.)
+    tp.set_ref_pressure_water(0.)
+    tp.set_residual_saturation_water(0.)
+    tp.set_residual_saturation_oil(.2)
+    tp.set_corey_relperm(2., 2.)
+    tp.set_time_step_size(float(g["delta_t"]))
+    if variant == "wells":
+        for c in range(nc):
+            if mesh.cell_to_ijk[c][0] == 0:
+                tp.add_rate_well(10. / (ny * nz), 0., c, "w%d" % c)
+    tp.initialize_system()
+    # c_start counts M's COO triples: ours is structural, the reference's is value-filtered
+    assert tp.c_start >= int(g["c_start"]) and tp.c_end - tp.c_start == nc
+    for step in range(1, int(g["steps"]) + 1):
+        tp.update_pressure(step)
+        if step == 1 or step % 10 == 0:
+            tp.find_upwinding_direction()
+        tp.update_saturation(step)
+        tp._sync_host()
+        assert abs(tp.current_s_w - g["s_w"][step - 1]).max() < 1e-10, step
+        assert np.linalg.norm(tp.current_p_o - g["p_o"][step - 1]) <= 1e-8 * np.linalg.norm(g["p_o"][step - 1]), step
+        assert np.linalg.norm(tp.current_u_t - g["u_t"][step - 1]) <= 1e-8 * np.linalg.norm(g["u_t"][step - 1]), step
