@@ -3,15 +3,17 @@
 
     MFD assembly Mcells/s + PCG s/iter & solve time, 256^3 hex, 1/2/4/8 B200
 
-    python bench.py --gpus N --steps K --warmup W          # our arm (CUDA)
+    python bench.py --gpus N --steps K --warmup W          # our arm (CUDA); N>1 under torchrun
     python bench.py --impl reference --steps K --warmup W  # the reference algorithm on host cores
 
 Workload (BASELINE.json configs[2], SURVEY.md 8d "C3"): n^3 unit-cube hex mesh (n = 256),
 K = diag(exp g1, exp g2, exp g3) iid per cell (seed 256), M_E method 1, Dirichlet p=1 on x-,
 p=0 on x+, no-flow elsewhere, f = 0.  One step = numeric assembly of the saddle-point CSR
 (fused M_E construction + scatter) followed by the full solve (hybrid set-up, PCG to rtol,
-recovery of [v;p]).  `value` is the assembly throughput; PCG s/iter and time-to-solution ride in
-the same JSON line.  Inputs are resident in HBM for `value`; `e2e` goes through host buffers.
+recovery of [v;p]).  `value` is the assembly throughput (cells of all ranks / slowest rank's
+time); PCG s/iter and time-to-solution ride in the same JSON line.  Inputs are resident in HBM
+for `value`; `e2e` goes through pinned host buffers.  With N > 1 the cell set is split into
+z-slabs (strong scaling: the 256^3 problem is fixed), see mimpy_b200/partition.py.
 """
 import argparse
 import json
@@ -29,8 +31,10 @@ sys.path.insert(0, ROOT)
 METRIC = "mfd_assembly_mcells_per_s"
 UNIT = "Mcells/s"
 ASM_BYTES_PER_CELL = 700.0     # 332 B read + 368 B written per hex cell
-PCG_BYTES_PER_ROW = lambda nnz_per_row: 12.0 * nnz_per_row + 108.0
-SPMV_BYTES_PER_ROW = lambda nnz_per_row: 12.0 * nnz_per_row + 20.0
+
+
+def pcg_bytes_per_row(nnz_per_row):
+    return 12.0 * nnz_per_row + 108.0
 
 
 def measured_peak():
@@ -93,7 +97,7 @@ def lognormal_k(nc, seed, sigma=1.0):
 # ------------------------------------------------------------------------------------------
 def cpu_assembly_sample(n, seed=256):
     """build_lhs + build_rhs of the reference algorithm (oracle port, per-cell Python/NumPy loop
-    exactly like mfd.py:545-599) on an n^3 sample of the workload. Returns (seconds, cells)."""
+    exactly like mfd.py:545-599) on an n^3 sample of the workload. Returns (seconds, cells, mfd)."""
     from oracle import mimpy_oracle as orc
 
     k = lognormal_k(n ** 3, seed)
@@ -134,6 +138,7 @@ def run_reference(args):
                    "n": n, "cells": cells},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                          "host_cores_available": os.cpu_count(),
+                         "note": "the reference is single-threaded Python (per-cell NumPy/LAPACK calls); 1 core is all it can use",
                          "spsolve_s": t_solve, "spsolve_dof": int(f.flux_dof + f.o.nc)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -145,10 +150,33 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+def build_problem(ctx, n, rank, world):
+    """This rank's slab of the C3 problem, resident in HBM."""
+    import torch
+    from mimpy_b200 import device, partition
+
+    slab = partition.SlabPlan(n, n, n, rank, world)
+    k_full = lognormal_k(n ** 3, 256)
+    k_host = np.ascontiguousarray(k_full[slab.k0 * n * n:slab.k1 * n * n])
+    del k_full
+    dm = device.DeviceMesh.hex(ctx, n, n, slab.nzl, 1., 1., float(slab.nzl) / n, cell_k=k_host)
+    plan = device.symbolic(dm, slab.neumann_mask(), face_flag=slab.face_flag() if world > 1 else None)
+    xm, xp = slab.dirichlet_faces()
+    areas = device.to_host(ctx, dm.face_areas)
+    faces = np.concatenate([xm, xp])
+    # value = p(x_f) a_f sigma_bdry with p = 1 on x- (sigma -1), p = 0 on x+   (mfd.py:1157-1162)
+    vals = np.concatenate([-areas[xm], np.zeros(len(xp))])
+    rhs = device.build_rhs(dm, plan, faces, vals, True, 0., None)
+    n_owned = plan.flux_dof
+    if world > 1:
+        n_owned = partition.attach_halo(ctx, slab, plan)
+    return {"slab": slab, "dm": dm, "plan": plan, "rhs": rhs, "k_host": k_host, "n_owned": n_owned}
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
-    from mimpy_b200 import _lib, device
+    from mimpy_b200 import _lib, device, partition
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -158,47 +186,31 @@ def run_cuda(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = _lib.Context(local_rank)
     dev = ctx.device
+    if world > 1:
+        partition.init_nccl(ctx, rank, world)
     n = args.n
     peak, peak_src = measured_peak()
 
-    if world > 1:
-        from mimpy_b200 import partition
-        return partition.bench_multi_gpu(args, ctx, rank, world, peak, peak_src, ClockSampler)
-
-    # ---- problem set-up (untimed; inputs end up resident in HBM) ---------------------------
-    nc = n ** 3
-    k_host = lognormal_k(nc, 256)
     t_setup = time.perf_counter()
-    dm = device.DeviceMesh.hex(ctx, n, n, n, 1., 1., 1., cell_k=k_host)
-    L = n * n + n * (n + 1) + (n + 1) * n
-    nf = dm.nf
-    with ctx.on_stream():
-        fp = dm.face_points  # boundary markers from the closed form: x- faces / x+ faces etc.
-        mask = torch.zeros(nf, dtype=torch.uint8, device=dev)
-        pts = dm.points
-        fc = dm.face_centroids
-        eps = 1e-9
-        on_y = (fc[:, 1] < eps) | (fc[:, 1] > 1. - eps)
-        on_z = (fc[:, 2] < eps) | (fc[:, 2] > 1. - eps)
-        mask[on_y | on_z] = 1
-        dir_faces = torch.nonzero(fc[:, 0] < eps).flatten().to(torch.int32)
-        # value = p(x_f) a_f sigma_bdry, p = 1 on x- (sigma -1), p = 0 on x+   (mfd.py:1157-1162)
-        dir_vals = -dm.face_areas[dir_faces.long()]
-        dir0_faces = torch.nonzero(fc[:, 0] > 1. - eps).flatten().to(torch.int32)
-        all_dir_faces = torch.cat([dir_faces, dir0_faces])
-        all_dir_vals = torch.cat([dir_vals, torch.zeros(dir0_faces.numel(), dtype=torch.float64, device=dev)])
-    plan = device.symbolic(dm, mask)
-    rhs = device.build_rhs(dm, plan, all_dir_faces.cpu().numpy(), all_dir_vals.cpu().numpy(), True, 0., None)
+    pb = build_problem(ctx, n, rank, world)
     ctx.sync()
     t_setup = time.perf_counter() - t_setup
+    dm, plan, rhs = pb["dm"], pb["plan"], pb["rhs"]
     F = plan.flux_dof
+    nc_total = n ** 3
     with ctx.on_stream():
         vals = torch.empty(plan.nnz, dtype=torch.float64, device=dev)
-        del fc, on_y, on_z
     method = 1
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     def step(collect):
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        barrier()
         with ctx.on_stream():
             evs[0].record(ctx.stream)
             device.numeric(dm, plan, method, vals=vals)
@@ -211,11 +223,14 @@ def run_cuda(args):
                                   raise_on_noconv=False)
             evs[3].record(ctx.stream)
         ctx.sync()
-        torch.cuda.synchronize()
-        out = {"asm_ms": evs[0].elapsed_time(evs[1]), "setup_ms": evs[1].elapsed_time(evs[2]),
-               "solve_ms": evs[2].elapsed_time(evs[3]), "pcg_ms": float(info.ms_total),
-               "iters": int(info.iterations), "residual": float(info.residual),
-               "rhs_norm": float(info.rhs_norm), "step_ms": evs[0].elapsed_time(evs[3])}
+        barrier()
+        t = torch.tensor([evs[0].elapsed_time(evs[1]), evs[1].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3]),
+                          float(info.ms_total), evs[0].elapsed_time(evs[3])], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # device times, max over ranks
+        t = t.tolist()
+        out = {"asm_ms": t[0], "setup_ms": t[1], "solve_ms": t[2], "pcg_ms": t[3], "step_ms": t[4],
+               "iters": int(info.iterations), "residual": float(info.residual), "rhs_norm": float(info.rhs_norm)}
         if collect:
             out["sol"] = sol
         del hyb
@@ -225,12 +240,12 @@ def run_cuda(args):
         step(False)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    torch.cuda.synchronize()
+    barrier()
     res = []
     t0 = time.perf_counter()
     for s in range(args.steps):
         res.append(step(s == args.steps - 1))
-    torch.cuda.synchronize()
+    barrier()
     wall = time.perf_counter() - t0
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -240,72 +255,88 @@ def run_cuda(args):
     iters = res[-1]["iters"]
     pcg_ms = float(np.mean([r["pcg_ms"] for r in res]))
     s_per_iter = pcg_ms / 1e3 / max(iters, 1)
-    value = nc / (asm_ms / 1e3) / 1e6
-    nnz_row = plan.nnz_m / float(F)
-    asm_gbs = ASM_BYTES_PER_CELL * nc / (asm_ms / 1e3) / 1e9
-    pcg_gbs = PCG_BYTES_PER_ROW(nnz_row) * F / s_per_iter / 1e9
+    value = nc_total / (asm_ms / 1e3) / 1e6
+    rows = torch.tensor([float(pb["n_owned"]), float(plan.nnz_m)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(rows)
+    rows_total, nnz_total = rows.tolist()
+    nnz_row = nnz_total / rows_total
+    # per-GPU achieved bandwidth of the dominant kernels (algorithmic bytes of the local slab)
+    asm_gbs = ASM_BYTES_PER_CELL * (nc_total / world) / (asm_ms / 1e3) / 1e9
+    pcg_gbs = pcg_bytes_per_row(nnz_row) * (rows_total / world) / s_per_iter / 1e9
 
-    # residual of the ORIGINAL saddle system for the recovered [v;p] (correctness of the timed work)
     sol = res[-1]["sol"]
     with ctx.on_stream():
-        ax = device.spmv(ctx, plan.indptr, plan.indices, vals, sol, n=plan.ndof)
-        saddle_res = float(torch.linalg.norm(ax - rhs) / torch.linalg.norm(rhs))
-        p_mean = float(sol[F:].mean())
+        psum = sol[F:].sum().reshape(1).clone()
+        if world > 1:
+            dist.all_reduce(psum)
+        p_mean = float(psum) / nc_total
+        saddle_res = None
+        if world == 1:
+            ax = device.spmv(ctx, plan.indptr, plan.indices, vals, sol, n=plan.ndof)
+            saddle_res = float(torch.linalg.norm(ax - rhs) / torch.linalg.norm(rhs))
 
-    # ---- e2e: host buffers in, host buffers out (H2D of K, D2H of CSR values + solution) ----
+    # ---- e2e: pinned host buffers in and out (H2D of K, D2H of the CSR values), every rank its slab ----
     e2e = None
     if not args.no_e2e:
-        k_pin = torch.from_numpy(k_host).pin_memory()
+        nc_loc = dm.nc
+        k_pin = torch.from_numpy(pb["k_host"]).pin_memory()
         vals_host = torch.empty(plan.nnz, dtype=torch.float64).pin_memory()
-        sol_host = torch.empty(plan.ndof, dtype=torch.float64).pin_memory()
-        e2e_times = []
-        for s in range(2):
-            torch.cuda.synchronize()
+        times = []
+        for s in range(3):
+            barrier()
             t0 = time.perf_counter()
             with ctx.on_stream():
-                dm.cell_k.copy_(k_pin.reshape(nc, 9), non_blocking=True)
+                dm.cell_k.copy_(k_pin.reshape(nc_loc, 9), non_blocking=True)
                 device.numeric(dm, plan, method, vals=vals)
                 vals_host.copy_(vals, non_blocking=True)
             ctx.sync()
-            torch.cuda.synchronize()
-            e2e_times.append(time.perf_counter() - t0)
-        e2e_s = min(e2e_times)
-        e2e = {"value": nc / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(k_pin.numel() * 8),
-               "d2h_bytes_per_step": int(vals_host.numel() * 8),
-               "what": "cell_k from pinned host -> numeric assembly -> CSR values to pinned host"}
-        del k_pin, vals_host, sol_host
+            barrier()
+            times.append(time.perf_counter() - t0)
+        tt = torch.tensor([min(times[1:])], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": nc_total / float(tt) / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": int(k_pin.numel() * 8 * world), "d2h_bytes_per_step": int(vals_host.numel() * 8 * world),
+               "what": "per rank: cell_k from pinned host -> numeric assembly -> CSR values to pinned host (wall clock, max over ranks)"}
+        del k_pin, vals_host
 
-    # ---- cpu baseline: the reference algorithm on this box's host cores, bounded sample -----
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and rank == 0 and world == 1:
         dt, cells, f = cpu_assembly_sample(args.cpu_n)
         cpu = {"value": cells / dt / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
                "host_cores_available": os.cpu_count(),
                "sample": "%d^3 cells of the same workload (build_lhs+build_rhs, %.1f s); O(cells)" % (args.cpu_n, dt)}
 
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C3: %d^3 hex, log-normal diag K (seed 256), method 1, Dirichlet x-/x+, no-flow else" % n,
-                   "cells": nc, "faces": nf, "flux_dof": F, "saddle_nnz": plan.nnz, "face_system_nnz": plan.nnz_m,
-                   "l2": "inputs larger than L2 (>= %.1f GB touched per step)" % (ASM_BYTES_PER_CELL * nc / 1e9),
-                   "pcg": {"preconditioner": "jacobi", "rtol": args.rtol, "check_every": args.check_every}},
-        "assembly_ms": asm_ms, "hybrid_setup_ms": float(np.mean([r["setup_ms"] for r in res])),
-        "pcg_iters": iters, "pcg_s_per_iter": s_per_iter, "solve_time_s": float(np.mean([r["solve_ms"] for r in res])) / 1e3,
-        "pcg_rel_residual": res[-1]["residual"] / max(res[-1]["rhs_norm"], 1e-300),
-        "saddle_rel_residual": saddle_res, "mean_pressure": p_mean,
-        "roofline": {"bound": "hbm", "achieved": asm_gbs, "peak": peak, "unit": "GB/s", "frac": asm_gbs / peak,
-                     "traffic": None, "kernel": "k_local_matrices<8,true> (fused M_E + CSR scatter)",
-                     "peak_source": peak_src, "frac_of_8TBs_spec": asm_gbs / 8000.,
-                     "algorithmic_bytes_per_cell": ASM_BYTES_PER_CELL},
-        "roofline_pcg": {"bound": "hbm", "achieved": pcg_gbs, "peak": peak, "unit": "GB/s", "frac": pcg_gbs / peak,
-                         "algorithmic_bytes_per_row": PCG_BYTES_PER_ROW(nnz_row), "rows": F},
-        "cpu_baseline": cpu, "e2e": e2e,
-        "gpu_launches": int(args.steps * (2 + 1 + 4 + 2 + 3 * iters + 4)),
-        "clocks": sampler.summary(), "setup_s": t_setup, "wall_s_timed": wall,
-    }
-    print(json.dumps(line))
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C3: %d^3 hex, log-normal diag K (seed 256), method 1, Dirichlet x-/x+, no-flow else" % n,
+                       "cells": nc_total, "face_rows": int(rows_total), "face_system_nnz": int(nnz_total),
+                       "partition": "z-slabs x%d" % world,
+                       "l2": "inputs larger than L2 (>= %.1f GB touched per step per GPU)" % (ASM_BYTES_PER_CELL * nc_total / world / 1e9),
+                       "pcg": {"preconditioner": "jacobi", "rtol": args.rtol, "check_every": args.check_every}},
+            "assembly_ms": asm_ms, "hybrid_setup_ms": float(np.mean([r["setup_ms"] for r in res])),
+            "pcg_iters": iters, "pcg_s_per_iter": s_per_iter,
+            "solve_time_s": float(np.mean([r["solve_ms"] for r in res])) / 1e3,
+            "pcg_rel_residual": res[-1]["residual"] / max(res[-1]["rhs_norm"], 1e-300),
+            "saddle_rel_residual": saddle_res, "mean_pressure": p_mean,
+            "roofline": {"bound": "hbm", "achieved": asm_gbs, "peak": peak, "unit": "GB/s", "frac": asm_gbs / peak,
+                         "traffic": None, "kernel": "k_numeric_direct<6,1> (fused M_E + CSR scatter), per GPU",
+                         "peak_source": peak_src, "frac_of_8TBs_spec": asm_gbs / 8000.,
+                         "algorithmic_bytes_per_cell": ASM_BYTES_PER_CELL},
+            "roofline_pcg": {"bound": "hbm", "achieved": pcg_gbs, "peak": peak, "unit": "GB/s", "frac": pcg_gbs / peak,
+                             "algorithmic_bytes_per_row": pcg_bytes_per_row(nnz_row), "rows": int(rows_total)},
+            "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(args.steps * (3 + 1 + 5 + 2 + 3 * iters + 4)),
+            "clocks": sampler.summary(), "setup_s": t_setup, "wall_s_timed": wall,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 

@@ -159,6 +159,11 @@ typedef struct {
                          cell of a shared face, 2 = the higher-index one (finishes the diagonal)   */
   int32_t* cell_rowstart; /* cell_ptr[nc]: indptr[g(f_i)] per (cell, face), -1 on Neumann faces --
                          saves the numeric kernel the dependent gathers f -> g(f) -> indptr[g]    */
+  const uint8_t* face_flag; /* nf or NULL (input, set by the caller on a slab-partitioned mesh):
+                         1 = interface face whose other cell lives on the upper neighbour rank
+                         (this rank holds the lower-index cell), 2 = ... on the lower neighbour
+                         rank.  Interface faces are interior faces of the global problem, not
+                         boundary faces, for the hybridised solve.                                */
 } mimpy_symbolic;
 
 int mimpy_b200_mfd_symbolic_sizes(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,
@@ -287,10 +292,28 @@ int mimpy_b200_twophase_saturation_step(mimpy_ctx* ctx, const mimpy_mesh_view* m
                                         const int32_t* well_cells, const double* well_rate_water,
                                         double* f_w /*flux_dof, in/out*/, double* s_w /*nc, in/out*/);
 
-/* -- (10) multi-GPU: slab partition helpers (see mimpy_b200/partition.py) ------------------------
- * attaches an NCCL communicator (ncclComm_t created by the caller from an id broadcast with
- * torch.distributed) used by pcg for the dot-product all-reduce and the halo exchange. */
+/* -- (10) multi-GPU: z-slab partition of the cell set (host side in
+ * mimpy_b200/partition.py) ----------------------------------------------------------------------
+ * Each rank assembles and solves on its own slab (a standalone local mesh); the face system is
+ * SUB-ASSEMBLED: interface rows hold this rank's half until hybrid_setup / hybrid_rhs / every SpMV
+ * of pcg exchange-add the two halves with the neighbour (ncclSend/ncclRecv in one group), and the
+ * dot products are all-reduced (ncclAllReduce, FP64 sum).  No other collective is used.
+ *
+ * NCCL is resolved at run time from the library already resident in the process (PyTorch's), see
+ * comm.cu.  nccl_unique_id: rank 0 creates the 128-byte id, the caller broadcasts it (e.g. with
+ * torch.distributed) and every rank calls nccl_init.
+ * set_halo: n_owned = number of leading face-system rows counted in dot products (ghost copies of
+ * the upper interface layer come last in the local numbering); idx_lo / idx_hi = positions of the
+ * rows shared with the lower / upper neighbour; buf = 2*(n_lo+n_hi) doubles. */
 int mimpy_b200_set_comm(mimpy_ctx* ctx, void* nccl_comm, int32_t rank, int32_t world);
+int mimpy_b200_nccl_load(const char* path_host);
+int mimpy_b200_nccl_unique_id(void* out128_host);
+int mimpy_b200_nccl_init(mimpy_ctx* ctx, const void* id128_host, int32_t rank, int32_t world);
+int mimpy_b200_set_halo(mimpy_ctx* ctx, int32_t n_owned, int32_t n_lo, const int32_t* idx_lo,
+                        int32_t rank_lo, int32_t n_hi, const int32_t* idx_hi, int32_t rank_hi,
+                        double* buf);
+int mimpy_b200_halo_exchange_add(mimpy_ctx* ctx, double* v);
+int mimpy_b200_allreduce_sum(mimpy_ctx* ctx, double* buf, int32_t count);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,7 @@ class Symbolic(C.Structure):
                 ("face_to_flux", _vp), ("face_cell", _vp), ("indptr", _vp), ("indices", _vp),
                 ("m_indptr", _vp), ("m_indices", _vp), ("m_ptr", _vp), ("pos_m", _vp),
                 ("pos_dt", _vp), ("pos_d", _vp), ("diag_pos", _vp), ("role", _vp),
-                ("cell_rowstart", _vp)]
+                ("cell_rowstart", _vp), ("face_flag", _vp)]
 
 
 class PcgInfo(C.Structure):
@@ -75,9 +75,12 @@ SIGNATURES = {
     "mimpy_b200_twophase_saturation_step": [_vp, _PM, _PS, C.POINTER(Fluid), _f64, _vp, _vp, _vp,
                                             _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
     "mimpy_b200_set_comm": [_vp, _vp, _i32, _i32],
+    "mimpy_b200_nccl_load": [C.c_char_p],
     "mimpy_b200_nccl_unique_id": [_vp],
     "mimpy_b200_nccl_init": [_vp, _vp, _i32, _i32],
-    "mimpy_b200_halo_exchange": [_vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _i32],
+    "mimpy_b200_set_halo": [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp],
+    "mimpy_b200_halo_exchange_add": [_vp, _vp],
+    "mimpy_b200_allreduce_sum": [_vp, _vp, _i32],
 }
 
 _lib = None

@@ -7,7 +7,19 @@
 
 #include "mimpy_b200.h"
 
+// interface layers of a z-slab partition: positions (in the local face-system
+// numbering) of the faces shared with the lower / upper neighbour rank
+struct mimpy_halo {
+  int n_owned;          // rows [0, n_owned) are counted in dot products (the rest are ghost copies)
+  int n_lo, n_hi;
+  const int* idx_lo;
+  const int* idx_hi;
+  int rank_lo, rank_hi;
+  double* buf;          // 2*(n_lo + n_hi) doubles
+};
+
 struct mimpy_ctx {
+  mimpy_halo halo;
   int device;
   cudaStream_t stream;
   int sm_count;
@@ -28,6 +40,9 @@ int mimpy_numeric_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mim
                           int method, int flags, const double* multipliers, double alpha,
                           const double* c_diag, double* vals);
 int mimpy_scratch(mimpy_ctx* ctx, size_t bytes, void** out);
+// comm.cu
+int mimpy_allreduce_f64(mimpy_ctx* ctx, double* buf, int count);
+int mimpy_halo_exchange_add(mimpy_ctx* ctx, double* v);
 
 #define CUDA_TRY(expr)                                                                   \
   do {                                                                                   \

@@ -16,6 +16,7 @@
 struct HybArgs {
   const int* face_to_flux;
   const int* face_cell;
+  const uint8_t* face_flag;  // nullable; bit0/bit1: interface face of a slab partition (see header)
   const int* m_indptr;
   const int* m_ptr;
   const uint8_t* pos_m;
@@ -88,7 +89,8 @@ k_hybrid_setup(mimpy_mesh_view m, HybArgs h, const double* __restrict__ m_e,
     const int f = m.cell_faces[base + j];
     area = __ldg(m.face_geom + 8 * (size_t)f);
     gj = h.face_to_flux[f];
-    flag = (gj < 0 ? 1 : 0) | (h.face_cell[2 * (size_t)f + 1] < 0 ? 2 : 0);
+    const bool iface = h.face_flag && (h.face_flag[f] & 3);  // the other cell lives on another rank
+    flag = (gj < 0 ? 1 : 0) | ((h.face_cell[2 * (size_t)f + 1] < 0 && !iface) ? 2 : 0);
   }
   s_a[slot][j] = area;
   s_flag[slot][j] = flag;
@@ -145,7 +147,12 @@ __global__ void k_diag_inv(int F, const int* __restrict__ m_indptr,
                            double* __restrict__ dinv) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= F) return;
-  dinv[g] = 1.0 / a_vals[m_indptr[g] + diag_pos[g]];
+  dinv[g] = a_vals[m_indptr[g] + diag_pos[g]];  // inverted after the interface exchange
+}
+
+__global__ void k_invert(int F, double* __restrict__ d) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < F) d[g] = 1.0 / d[g];
 }
 
 __global__ void k_zero_diag_m(int F, const int* __restrict__ m_indptr,
@@ -175,14 +182,16 @@ k_hybrid_local(mimpy_mesh_view m, HybArgs h, const double* __restrict__ w_e,
   const int F = h.flux_dof;
   int gj = -1;
   double area = 0., sg = 0., t = 0., lam = 0.;
-  bool bnd = false, owner = false;
+  bool bnd = false, owner = false, iface = false;
   if (valid) {
     const int f = m.cell_faces[base + j];
     sg = (double)m.cell_sigma[base + j];
     area = __ldg(m.face_geom + 8 * (size_t)f);
     gj = h.face_to_flux[f];
-    bnd = h.face_cell[2 * (size_t)f + 1] < 0;
-    owner = h.face_cell[2 * (size_t)f] == cell;
+    const unsigned ff = h.face_flag ? (h.face_flag[f] & 3) : 0;
+    bnd = h.face_cell[2 * (size_t)f + 1] < 0 && !ff;
+    owner = ff ? (ff & 1) : (h.face_cell[2 * (size_t)f] == cell);
+    iface = ff != 0;
     if (gj >= 0) {
       const double bv = rhs[gj];
       double beta = 0.;
@@ -224,7 +233,8 @@ k_hybrid_local(mimpy_mesh_view m, HybArgs h, const double* __restrict__ w_e,
     }
   } else {
     if (j == 0 && cell_ok) out[F + cell] = p;
-    if (valid && gj >= 0 && owner) out[gj] = sg * u;
+    // the lower-index cell reports the face flux; on a slab interface the only local cell does
+    if (valid && gj >= 0 && (owner || iface)) out[gj] = sg * u;
   }
 }
 
@@ -232,6 +242,7 @@ static HybArgs make_hyb(const mimpy_symbolic* sym, double alpha, const double* c
   HybArgs h;
   h.face_to_flux = sym->face_to_flux;
   h.face_cell = sym->face_cell;
+  h.face_flag = sym->face_flag;
   h.m_indptr = sym->m_indptr;
   h.m_ptr = sym->m_ptr;
   h.pos_m = sym->pos_m;
@@ -272,6 +283,11 @@ int mimpy_b200_hybrid_setup(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
   if (F > 0) {
     k_diag_inv<<<(F + 255) / 256, 256, 0, st>>>(F, sym->m_indptr, sym->diag_pos, a_vals, a_diag_inv);
     KERNEL_CHECK();
+    // slab partition: the diagonal of an interface row is the sum of both ranks' halves
+    int rc = mimpy_halo_exchange_add(ctx, a_diag_inv);
+    if (rc) return rc;
+    k_invert<<<(F + 255) / 256, 256, 0, st>>>(F, a_diag_inv);
+    KERNEL_CHECK();
   }
   return MIMPY_OK;
 }
@@ -291,7 +307,7 @@ int mimpy_b200_hybrid_rhs(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mim
              (k_hybrid_local<16, 0><<<blocks, 128, 0, st>>>(*mesh, h, w_e, rhs, nullptr, hvec)),
              (k_hybrid_local<32, 0><<<blocks, 128, 0, st>>>(*mesh, h, w_e, rhs, nullptr, hvec)));
   KERNEL_CHECK();
-  return MIMPY_OK;
+  return mimpy_halo_exchange_add(ctx, hvec);  // interface rows: own + neighbour (no-op on one rank)
 }
 
 int mimpy_b200_hybrid_recover(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,

@@ -15,9 +15,6 @@
 // K2 48 n + 8 n (D^-1), K3 8 n (r) + 8 n (D^-1) + 16 n (p)  ->  12 nnz + 108 n  (SURVEY 8d).
 #include "common.cuh"
 
-#ifdef MIMPY_WITH_NCCL
-#include <nccl.h>
-#endif
 
 enum { S_RZ = 0, S_PAP = 1, S_RZNEW = 2, S_RR = 3, S_BNORM = 4, S_TMP = 8 };
 
@@ -101,7 +98,7 @@ k_spmv(int n, const int* __restrict__ indptr, const int* __restrict__ indices,
 }
 
 __global__ void __launch_bounds__(RED_THREADS)
-k_update_xr(int n, const double* __restrict__ p, const double* __restrict__ ap,
+k_update_xr(int n, int n_owned, const double* __restrict__ p, const double* __restrict__ ap,
             const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
             double* partials, unsigned int* counter, double* scal) {
   __shared__ double sh[32];
@@ -113,8 +110,10 @@ k_update_xr(int n, const double* __restrict__ p, const double* __restrict__ ap,
     x[i] += alpha * p[i];
     const double ri = r[i] - alpha * ap[i];
     r[i] = ri;
-    rz += ri * (__ldg(dinv + i) * ri);
-    rr += ri * ri;
+    if (i < n_owned) {  // ghost copies of interface rows are counted by their owner rank
+      rz += ri * (__ldg(dinv + i) * ri);
+      rr += ri * ri;
+    }
   }
   const double v[2] = {rz, rr};
   finish_reduction<2>(v, partials, counter, scal + S_RZNEW, sh);
@@ -142,7 +141,7 @@ k_update_p(int n, const double* __restrict__ r, const double* __restrict__ dinv,
 
 // r = b - A x (given Ax in ap), p = D^-1 r, S_RZ = r.D^-1 r, S_RR = r.r, S_BNORM = b.b
 __global__ void __launch_bounds__(RED_THREADS)
-k_init(int n, const double* __restrict__ b, const double* __restrict__ ax,
+k_init(int n, int n_owned, const double* __restrict__ b, const double* __restrict__ ax,
        const double* __restrict__ dinv, double* __restrict__ r, double* __restrict__ p,
        double* partials, unsigned int* counter, double* scal) {
   __shared__ double sh[32];
@@ -154,9 +153,11 @@ k_init(int n, const double* __restrict__ b, const double* __restrict__ ax,
     const double zi = __ldg(dinv + i) * ri;
     r[i] = ri;
     p[i] = zi;
-    rz += ri * zi;
-    rr += ri * ri;
-    bb += bi * bi;
+    if (i < n_owned) {
+      rz += ri * zi;
+      rr += ri * ri;
+      bb += bi * bi;
+    }
   }
   const double v[3] = {rz, rr, bb};
   finish_reduction<3>(v, partials, counter, scal + S_TMP, sh);
@@ -169,26 +170,7 @@ __global__ void k_init_scalars(double* scal) {
   scal[S_RZNEW] = scal[S_TMP];
 }
 
-static int allreduce(mimpy_ctx* ctx, double* buf, int count) {
-#ifdef MIMPY_WITH_NCCL
-  if (ctx->world > 1) {
-    ncclResult_t r = ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm,
-                                   ctx->stream);
-    if (r != ncclSuccess) {
-      mimpy_set_error("ncclAllReduce failed: %s", ncclGetErrorString(r));
-      return MIMPY_E_NCCL;
-    }
-  }
-#else
-  if (ctx->world > 1) {
-    mimpy_set_error("built without NCCL");
-    return MIMPY_E_NCCL;
-  }
-#endif
-  (void)buf;
-  (void)count;
-  return MIMPY_OK;
-}
+static int allreduce(mimpy_ctx* ctx, double* buf, int count) { return mimpy_allreduce_f64(ctx, buf, count); }
 
 static int launch_iteration(mimpy_ctx* ctx, int grid, int n, const int* indptr, const int* indices,
                             const double* vals, const double* dinv, double* x, double* r, double* p,
@@ -196,9 +178,14 @@ static int launch_iteration(mimpy_ctx* ctx, int grid, int n, const int* indptr, 
   cudaStream_t st = ctx->stream;
   k_spmv<8, true><<<grid, RED_THREADS, 0, st>>>(n, indptr, indices, vals, p, ap, ctx->partials,
                                                 ctx->counters + 0, ctx->scalars);
+  // p.Ap = sum over ranks of p_loc.(A_loc p_loc): the fused dot over ALL local rows of the
+  // still-partial interface values is already this rank's exact share (sub-assembled operator)
   int rc = allreduce(ctx, ctx->scalars + S_PAP, 1);
   if (rc) return rc;
-  k_update_xr<<<grid, RED_THREADS, 0, st>>>(n, p, ap, dinv, x, r, ctx->partials, ctx->counters + 1,
+  rc = mimpy_halo_exchange_add(ctx, ap);  // interface rows of Ap: own + neighbour
+  if (rc) return rc;
+  const int n_owned = (ctx->world > 1 && ctx->halo.n_owned > 0) ? ctx->halo.n_owned : n;
+  k_update_xr<<<grid, RED_THREADS, 0, st>>>(n, n_owned, p, ap, dinv, x, r, ctx->partials, ctx->counters + 1,
                                             ctx->scalars);
   rc = allreduce(ctx, ctx->scalars + S_RZNEW, 2);
   if (rc) return rc;
@@ -238,9 +225,12 @@ int mimpy_b200_pcg(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, const int32
   // r0 = b - A x0
   k_spmv<8, false><<<grid, RED_THREADS, 0, st>>>(n, indptr, indices, vals, x, ap, nullptr, nullptr,
                                                  nullptr);
-  k_init<<<grid, RED_THREADS, 0, st>>>(n, b, ap, diag_inv, r, p, ctx->partials, ctx->counters + 3,
+  int rc = mimpy_halo_exchange_add(ctx, ap);
+  if (rc) return rc;
+  const int n_owned = (ctx->world > 1 && ctx->halo.n_owned > 0) ? ctx->halo.n_owned : n;
+  k_init<<<grid, RED_THREADS, 0, st>>>(n, n_owned, b, ap, diag_inv, r, p, ctx->partials, ctx->counters + 3,
                                        ctx->scalars);
-  int rc = allreduce(ctx, ctx->scalars + S_TMP, 3);
+  rc = allreduce(ctx, ctx->scalars + S_TMP, 3);
   if (rc) return rc;
   k_init_scalars<<<1, 1, 0, st>>>(ctx->scalars);
   KERNEL_CHECK();

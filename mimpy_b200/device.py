@@ -198,8 +198,9 @@ class SymbolicPlan(object):
         raise AttributeError(name)
 
 
-def symbolic(dmesh, neumann_mask):
-    """A1-A5 index work (mimpy_b200_mfd_symbolic_sizes/_fill). neumann_mask: uint8[nf] (host or device)."""
+def symbolic(dmesh, neumann_mask, face_flag=None):
+    """A1-A5 index work (mimpy_b200_mfd_symbolic_sizes/_fill). neumann_mask: uint8[nf] (host or device).
+    face_flag: uint8[nf] interface flags of a slab-partitioned mesh (partition.SlabPlan.face_flag)."""
     ctx = dmesh.ctx
     dev = ctx.device
     with ctx.on_stream():
@@ -208,6 +209,9 @@ def symbolic(dmesh, neumann_mask):
         total = int(6 * nc) if dmesh.uniform_faces == 6 else int(dmesh.cell_ptr[-1].item())
         plan = SymbolicPlan()
         t = plan.t
+        if face_flag is not None:
+            t["face_flag"] = torch.as_tensor(face_flag, dtype=torch.uint8).to(dev).contiguous()
+            plan.s.face_flag = t["face_flag"].data_ptr()
         t["face_to_flux"] = torch.empty(nf + 1, dtype=torch.int32, device=dev)
         t["face_cell"] = torch.empty((nf, 2), dtype=torch.int32, device=dev)
         t["indptr"] = torch.empty(nf + nc + 1, dtype=torch.int32, device=dev)
