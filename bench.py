@@ -346,7 +346,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--size", dest="n", type=int, default=256, help="cells per axis (256 = BASELINE config)")
     ap.add_argument("--rtol", type=float, default=1e-8)
     ap.add_argument("--maxit", type=int, default=20000)
     ap.add_argument("--check-every", type=int, default=50)
