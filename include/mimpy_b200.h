@@ -225,7 +225,9 @@ int mimpy_b200_mfd_rhs(mimpy_ctx* ctx, int32_t nc, int32_t flux_dof, const int32
  * hybrid_recover: solution[flux_dof+nc] = [v ; p] from lambda.                              */
 int mimpy_b200_hybrid_setup(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
                             const double* m_e, const double* multipliers, double alpha,
-                            const double* c_diag, double* w_e, double* a_vals, double* a_diag_inv);
+                            const double* c_diag, double* w_e, double* a_vals, double* a_diag_inv,
+                            const int32_t* sell_ptr /* NULL: a_vals in CSR order (m_indptr);
+                            else a_vals in the SELL-32 layout of mimpy_b200_sell_sizes/_fill */);
 int mimpy_b200_hybrid_rhs(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
                           const double* w_e, double alpha, const double* c_diag,
                           const double* rhs /*flux_dof+nc*/, double* cell_tmp /*cell_ptr[nc]*/,
@@ -254,6 +256,20 @@ int mimpy_b200_pcg(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, const int32
                    double* work, mimpy_pcg_info* info);
 
 /* y = A x for a CSR matrix with int32 indices (the solver's SpMV, exposed for tests/bench) */
+/* SELL-32 layout of a CSR pattern (the solver's preferred layout for the face system): 32-row
+ * slices stored column-major, padded to the longest row of the slice; entry k of row g lives at
+ * sell_ptr[g>>5] + 32*k + (g&31); padding = value 0, column g.  sell_ptr: (n+31)/32+1 ints.
+ * sell_sizes returns the padded entry count (synchronises); sell_fill writes the columns.
+ * pcg_sell / spmv_sell are pcg / spmv on that layout. */
+int mimpy_b200_sell_sizes(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, int32_t* sell_ptr,
+                          int64_t* total_host);
+int mimpy_b200_sell_fill(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, const int32_t* indices,
+                         const int32_t* sell_ptr, int32_t* sell_cols);
+int mimpy_b200_pcg_sell(mimpy_ctx* ctx, int32_t n, const int32_t* sell_ptr, const int32_t* sell_cols,
+                        const double* sell_vals, const double* diag_inv, const double* b, double* x,
+                        double* work, mimpy_pcg_info* info);
+int mimpy_b200_spmv_sell(mimpy_ctx* ctx, int32_t n, const int32_t* sell_ptr, const int32_t* sell_cols,
+                         const double* sell_vals, const double* x, double* y);
 int mimpy_b200_spmv(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, const int32_t* indices,
                     const double* vals, const double* x, double* y);
 

@@ -18,6 +18,13 @@ struct HybArgs {
   const int* face_cell;
   const uint8_t* face_flag;  // nullable; bit0/bit1: interface face of a slab partition (see header)
   const int* m_indptr;
+  const int* sell_ptr;  // non-NULL: the face-system values are laid out in SELL-32 (sell.cu)
+
+  // address of entry k of row g, and the distance between consecutive entries of a row
+  __device__ __forceinline__ int row_base(int g) const {
+    return sell_ptr ? sell_ptr[g >> 5] + (g & 31) : m_indptr[g];
+  }
+  __device__ __forceinline__ int row_stride() const { return sell_ptr ? 32 : 1; }
   const int* m_ptr;
   const uint8_t* pos_m;
   int flux_dof;
@@ -94,7 +101,8 @@ k_hybrid_setup(mimpy_mesh_view m, HybArgs h, const double* __restrict__ m_e,
   }
   s_a[slot][j] = area;
   s_flag[slot][j] = flag;
-  s_row[slot][j] = gj >= 0 ? h.m_indptr[gj] : -1;
+  s_row[slot][j] = gj >= 0 ? h.row_base(gj) : -1;
+  const int stride = h.row_stride();
   __syncwarp();
   const double mult = (multipliers && cell_ok) ? __ldg(multipliers + cell) : 1.;
   const int boff = cell_ok ? h.m_ptr[cell] : 0;
@@ -135,19 +143,18 @@ k_hybrid_setup(mimpy_mesh_view m, HybArgs h, const double* __restrict__ m_e,
       if (bnd) v = (i == j) ? 1. : 0.;
       const unsigned pos = h.pos_m[boff + (size_t)i * n + j];
       if (i == j)
-        atomicAdd(a_vals + rs + pos, v);
+        atomicAdd(a_vals + rs + (int)pos * stride, v);
       else
-        a_vals[rs + pos] = v;
+        a_vals[rs + (int)pos * stride] = v;
     }
   }
 }
 
-__global__ void k_diag_inv(int F, const int* __restrict__ m_indptr,
-                           const uint8_t* __restrict__ diag_pos, const double* __restrict__ a_vals,
-                           double* __restrict__ dinv) {
+__global__ void k_diag_inv(int F, HybArgs h, const uint8_t* __restrict__ diag_pos,
+                           const double* __restrict__ a_vals, double* __restrict__ dinv) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= F) return;
-  dinv[g] = a_vals[m_indptr[g] + diag_pos[g]];  // inverted after the interface exchange
+  dinv[g] = a_vals[h.row_base(g) + (int)diag_pos[g] * h.row_stride()];  // inverted after the interface exchange
 }
 
 __global__ void k_invert(int F, double* __restrict__ d) {
@@ -155,11 +162,11 @@ __global__ void k_invert(int F, double* __restrict__ d) {
   if (g < F) d[g] = 1.0 / d[g];
 }
 
-__global__ void k_zero_diag_m(int F, const int* __restrict__ m_indptr,
-                              const uint8_t* __restrict__ diag_pos, double* __restrict__ vals) {
+__global__ void k_zero_diag_m(int F, HybArgs h, const uint8_t* __restrict__ diag_pos,
+                              double* __restrict__ vals) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= F) return;
-  vals[m_indptr[g] + diag_pos[g]] = 0.;
+  vals[h.row_base(g) + (int)diag_pos[g] * h.row_stride()] = 0.;
 }
 
 // MODE 0: h (face-system right-hand side) ; MODE 1: recover [v ; p] from lambda
@@ -244,6 +251,7 @@ static HybArgs make_hyb(const mimpy_symbolic* sym, double alpha, const double* c
   h.face_cell = sym->face_cell;
   h.face_flag = sym->face_flag;
   h.m_indptr = sym->m_indptr;
+  h.sell_ptr = nullptr;
   h.m_ptr = sym->m_ptr;
   h.pos_m = sym->pos_m;
   h.flux_dof = sym->flux_dof;
@@ -263,25 +271,27 @@ extern "C" {
 
 int mimpy_b200_hybrid_setup(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
                             const double* m_e, const double* multipliers, double alpha,
-                            const double* c_diag, double* w_e, double* a_vals, double* a_diag_inv) {
+                            const double* c_diag, double* w_e, double* a_vals, double* a_diag_inv,
+                            const int32_t* sell_ptr) {
   REQUIRE(ctx && mesh && sym && m_e && w_e && a_vals && a_diag_inv, "NULL argument");
   REQUIRE(mesh->max_faces >= 1 && mesh->max_faces <= MIMPY_MAX_CELL_FACES, "max_faces out of range");
   if (mesh->nc <= 0) return MIMPY_OK;
   const int F = sym->flux_dof;
   cudaStream_t st = ctx->stream;
+  HybArgs h = make_hyb(sym, alpha, c_diag);
+  h.sell_ptr = sell_ptr;
   if (F > 0) {
-    k_zero_diag_m<<<(F + 255) / 256, 256, 0, st>>>(F, sym->m_indptr, sym->diag_pos, a_vals);
+    k_zero_diag_m<<<(F + 255) / 256, 256, 0, st>>>(F, h, sym->diag_pos, a_vals);
     KERNEL_CHECK();
   }
   const int G = mimpy_group_size(mesh->max_faces);
   const int blocks = (mesh->nc + 128 / G - 1) / (128 / G);
-  HybArgs h = make_hyb(sym, alpha, c_diag);
   DISPATCH_G(G, (k_hybrid_setup<8><<<blocks, 128, 0, st>>>(*mesh, h, m_e, multipliers, w_e, a_vals)),
              (k_hybrid_setup<16><<<blocks, 128, 0, st>>>(*mesh, h, m_e, multipliers, w_e, a_vals)),
              (k_hybrid_setup<32><<<blocks, 128, 0, st>>>(*mesh, h, m_e, multipliers, w_e, a_vals)));
   KERNEL_CHECK();
   if (F > 0) {
-    k_diag_inv<<<(F + 255) / 256, 256, 0, st>>>(F, sym->m_indptr, sym->diag_pos, a_vals, a_diag_inv);
+    k_diag_inv<<<(F + 255) / 256, 256, 0, st>>>(F, h, sym->diag_pos, a_vals, a_diag_inv);
     KERNEL_CHECK();
     // slab partition: the diagonal of an interface row is the sum of both ranks' halves
     int rc = mimpy_halo_exchange_add(ctx, a_diag_inv);

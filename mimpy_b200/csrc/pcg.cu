@@ -170,14 +170,80 @@ __global__ void k_init_scalars(double* scal) {
   scal[S_RZNEW] = scal[S_TMP];
 }
 
+// ---- SpMV, SELL-32 layout (sell.cu): lane r of a warp owns row r of a 32-row slice; every load of
+// the warp is one contiguous line (256 B of values, 128 B of columns), no cross-lane reduction ----
+template <bool DOT>
+__global__ void __launch_bounds__(RED_THREADS)
+k_spmv_sell(int n, const int* __restrict__ sell_ptr, const int* __restrict__ cols,
+            const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+            double* partials, unsigned int* counter, double* scal) {
+  __shared__ double sh[32];
+  const long long n_pad = ((long long)n + 31) & ~31LL;
+  double acc_dot = 0.;
+  for (long long row = (long long)blockIdx.x * RED_THREADS + threadIdx.x; row < n_pad;
+       row += (long long)gridDim.x * RED_THREADS) {
+    const int s = (int)(row >> 5);
+    const int base = __ldg(sell_ptr + s);
+    const int w = (__ldg(sell_ptr + s + 1) - base) >> 5;
+    const double* v = vals + base + (row & 31);
+    const int* c = cols + base + (row & 31);
+    double a0 = 0., a1 = 0.;
+    int k = 0;
+    for (; k + 3 < w; k += 4) {  // 4 independent value/column/x chains in flight
+      const int c0 = __ldg(c + 32 * k), c1 = __ldg(c + 32 * (k + 1));
+      const int c2 = __ldg(c + 32 * (k + 2)), c3 = __ldg(c + 32 * (k + 3));
+      const double v0 = __ldg(v + 32 * k), v1 = __ldg(v + 32 * (k + 1));
+      const double v2 = __ldg(v + 32 * (k + 2)), v3 = __ldg(v + 32 * (k + 3));
+      a0 += v0 * __ldg(x + c0);
+      a1 += v1 * __ldg(x + c1);
+      a0 += v2 * __ldg(x + c2);
+      a1 += v3 * __ldg(x + c3);
+    }
+    for (; k < w; ++k) a0 += __ldg(v + 32 * k) * __ldg(x + __ldg(c + 32 * k));
+    const double acc = a0 + a1;
+    if (row < n) {
+      y[row] = acc;
+      if (DOT) acc_dot += acc * __ldg(x + row);
+    }
+  }
+  if (DOT) {
+    const double vv[1] = {acc_dot};
+    finish_reduction<1>(vv, partials, counter, scal + S_PAP, sh);
+  }
+}
+
+// the face system in either layout
+struct SpmvMat {
+  int sell;          // 0: CSR (ptr = indptr), 1: SELL-32 (ptr = sell_ptr)
+  const int* ptr;
+  const int* idx;
+  const double* vals;
+};
+
+static void launch_spmv(mimpy_ctx* ctx, int grid, int n, const SpmvMat& A, const double* x, double* y,
+                        bool dot) {
+  cudaStream_t st = ctx->stream;
+  if (A.sell) {
+    if (dot)
+      k_spmv_sell<true><<<grid, RED_THREADS, 0, st>>>(n, A.ptr, A.idx, A.vals, x, y, ctx->partials,
+                                                      ctx->counters + 0, ctx->scalars);
+    else
+      k_spmv_sell<false><<<grid, RED_THREADS, 0, st>>>(n, A.ptr, A.idx, A.vals, x, y, nullptr, nullptr, nullptr);
+  } else {
+    if (dot)
+      k_spmv<8, true><<<grid, RED_THREADS, 0, st>>>(n, A.ptr, A.idx, A.vals, x, y, ctx->partials,
+                                                    ctx->counters + 0, ctx->scalars);
+    else
+      k_spmv<8, false><<<grid, RED_THREADS, 0, st>>>(n, A.ptr, A.idx, A.vals, x, y, nullptr, nullptr, nullptr);
+  }
+}
+
 static int allreduce(mimpy_ctx* ctx, double* buf, int count) { return mimpy_allreduce_f64(ctx, buf, count); }
 
-static int launch_iteration(mimpy_ctx* ctx, int grid, int n, const int* indptr, const int* indices,
-                            const double* vals, const double* dinv, double* x, double* r, double* p,
-                            double* ap) {
+static int launch_iteration(mimpy_ctx* ctx, int grid, int n, const SpmvMat& A, const double* dinv,
+                            double* x, double* r, double* p, double* ap) {
   cudaStream_t st = ctx->stream;
-  k_spmv<8, true><<<grid, RED_THREADS, 0, st>>>(n, indptr, indices, vals, p, ap, ctx->partials,
-                                                ctx->counters + 0, ctx->scalars);
+  launch_spmv(ctx, grid, n, A, p, ap, true);
   // p.Ap = sum over ranks of p_loc.(A_loc p_loc): the fused dot over ALL local rows of the
   // still-partial interface values is already this rank's exact share (sub-assembled operator)
   int rc = allreduce(ctx, ctx->scalars + S_PAP, 1);
@@ -208,10 +274,23 @@ int mimpy_b200_spmv(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, const int3
   return MIMPY_OK;
 }
 
-int mimpy_b200_pcg(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, const int32_t* indices,
-                   const double* vals, const double* diag_inv, const double* b, double* x,
-                   double* work, mimpy_pcg_info* info) {
-  REQUIRE(ctx && indptr && indices && vals && diag_inv && b && x && work && info, "NULL argument");
+int mimpy_b200_spmv_sell(mimpy_ctx* ctx, int32_t n, const int32_t* sell_ptr, const int32_t* sell_cols,
+                         const double* sell_vals, const double* x, double* y) {
+  REQUIRE(ctx && sell_ptr && sell_cols && sell_vals && x && y, "NULL argument");
+  if (n <= 0) return MIMPY_OK;
+  long long want = ((long long)n + RED_THREADS - 1) / RED_THREADS;
+  const int grid = (int)(want < (long long)ctx->sm_count * 8 ? want : (long long)ctx->sm_count * 8);
+  SpmvMat A = {1, sell_ptr, sell_cols, sell_vals};
+  launch_spmv(ctx, grid, n, A, x, y, false);
+  KERNEL_CHECK();
+  return MIMPY_OK;
+}
+
+}  // extern "C"
+
+static int pcg_core(mimpy_ctx* ctx, int32_t n, const SpmvMat& A, const double* diag_inv,
+                    const double* b, double* x, double* work, mimpy_pcg_info* info) {
+  REQUIRE(ctx && A.ptr && A.idx && A.vals && diag_inv && b && x && work && info, "NULL argument");
   REQUIRE(n > 0, "empty system");
   REQUIRE(info->maxit > 0, "maxit must be positive");
   cudaStream_t st = ctx->stream;
@@ -223,8 +302,7 @@ int mimpy_b200_pcg(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, const int32
 
   CUDA_TRY(cudaEventRecord(ctx->ev0, st));
   // r0 = b - A x0
-  k_spmv<8, false><<<grid, RED_THREADS, 0, st>>>(n, indptr, indices, vals, x, ap, nullptr, nullptr,
-                                                 nullptr);
+  launch_spmv(ctx, grid, n, A, x, ap, false);
   int rc = mimpy_halo_exchange_add(ctx, ap);
   if (rc) return rc;
   const int n_owned = (ctx->world > 1 && ctx->halo.n_owned > 0) ? ctx->halo.n_owned : n;
@@ -251,7 +329,7 @@ int mimpy_b200_pcg(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, const int32
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
       int crc = MIMPY_OK;
       for (int k = 0; k < check && crc == MIMPY_OK; ++k)
-        crc = launch_iteration(ctx, grid, n, indptr, indices, vals, diag_inv, x, r, p, ap);
+        crc = launch_iteration(ctx, grid, n, A, diag_inv, x, r, p, ap);
       cudaError_t e = cudaStreamEndCapture(st, &graph);
       if (crc != MIMPY_OK || e != cudaSuccess || graph == nullptr ||
           cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) {
@@ -272,7 +350,7 @@ int mimpy_b200_pcg(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, const int32
       CUDA_TRY(cudaGraphLaunch(gexec, st));
     } else {
       for (int k = 0; k < check; ++k) {
-        rc = launch_iteration(ctx, grid, n, indptr, indices, vals, diag_inv, x, r, p, ap);
+        rc = launch_iteration(ctx, grid, n, A, diag_inv, x, r, p, ap);
         if (rc) return rc;
       }
       KERNEL_CHECK();
@@ -300,6 +378,22 @@ int mimpy_b200_pcg(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, const int32
     return MIMPY_E_NOCONV;
   }
   return MIMPY_OK;
+}
+
+extern "C" {
+
+int mimpy_b200_pcg(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, const int32_t* indices,
+                   const double* vals, const double* diag_inv, const double* b, double* x,
+                   double* work, mimpy_pcg_info* info) {
+  SpmvMat A = {0, indptr, indices, vals};
+  return pcg_core(ctx, n, A, diag_inv, b, x, work, info);
+}
+
+int mimpy_b200_pcg_sell(mimpy_ctx* ctx, int32_t n, const int32_t* sell_ptr, const int32_t* sell_cols,
+                        const double* sell_vals, const double* diag_inv, const double* b, double* x,
+                        double* work, mimpy_pcg_info* info) {
+  SpmvMat A = {1, sell_ptr, sell_cols, sell_vals};
+  return pcg_core(ctx, n, A, diag_inv, b, x, work, info);
 }
 
 }  // extern "C"

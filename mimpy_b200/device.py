@@ -343,16 +343,32 @@ def build_rhs(dmesh, plan, dirichlet_faces, dirichlet_values, has_neumann, last_
 class HybridSystem(object):
     """The SPD face system A lambda = h of the hybridised saddle problem, in HBM."""
 
-    def __init__(self, dmesh, plan, m_e, multipliers=None, alpha=0., c_diag=None):
+    def __init__(self, dmesh, plan, m_e, multipliers=None, alpha=0., c_diag=None, layout="sell"):
+        """layout: "sell" (SELL-32, the solver's native layout) or "csr" (m_indptr/m_indices order)."""
         self.dmesh, self.plan = dmesh, plan
         self.alpha, self.c_diag = float(alpha), c_diag
+        self.layout = layout
         ctx = dmesh.ctx
         dev = ctx.device
+        F = plan.flux_dof
         with ctx.on_stream():
             self.w_e = torch.empty(max(plan.n_blocks, 1), dtype=torch.float64, device=dev)
-            self.a_vals = torch.zeros(max(plan.nnz_m, 1), dtype=torch.float64, device=dev)
-            self.a_diag_inv = torch.empty(max(plan.flux_dof, 1), dtype=torch.float64, device=dev)
+            self.a_diag_inv = torch.empty(max(F, 1), dtype=torch.float64, device=dev)
             self.work = None
+            if layout == "sell":
+                if "sell_ptr" not in plan.t:  # pattern-only: built once per symbolic plan
+                    sp = torch.empty((F + 31) // 32 + 1, dtype=torch.int32, device=dev)
+                    total = C.c_int64(0)
+                    ctx.call("mimpy_b200_sell_sizes", F, ptr(plan.m_indptr), ptr(sp), C.byref(total))
+                    sc = torch.empty(max(int(total.value), 1), dtype=torch.int32, device=dev)
+                    ctx.call("mimpy_b200_sell_fill", F, ptr(plan.m_indptr), ptr(plan.m_indices), ptr(sp), ptr(sc))
+                    plan.t["sell_ptr"], plan.t["sell_cols"] = sp, sc
+                    plan.sell_total = int(total.value)
+                self.sell_ptr, self.sell_cols = plan.t["sell_ptr"], plan.t["sell_cols"]
+                self.a_vals = torch.zeros(max(plan.sell_total, 1), dtype=torch.float64, device=dev)  # padding stays 0
+            else:
+                self.sell_ptr = self.sell_cols = None
+                self.a_vals = torch.zeros(max(plan.nnz_m, 1), dtype=torch.float64, device=dev)
             self.setup(m_e, multipliers, c_diag)
 
     def setup(self, m_e, multipliers=None, c_diag=None):
@@ -362,7 +378,7 @@ class HybridSystem(object):
             mv = self.dmesh.view()
             ctx.call("mimpy_b200_hybrid_setup", C.byref(mv), C.byref(self.plan.s), ptr(m_e),
                      ptr(multipliers), self.alpha, ptr(c_diag), ptr(self.w_e), ptr(self.a_vals),
-                     ptr(self.a_diag_inv))
+                     ptr(self.a_diag_inv), ptr(self.sell_ptr))
 
     def solve(self, rhs, rtol=1e-10, atol=0., maxit=20000, check_every=50, use_graph=True, x0=None,
               raise_on_noconv=True):
@@ -383,8 +399,12 @@ class HybridSystem(object):
             info.rtol, info.atol, info.maxit = rtol, atol, maxit
             info.check_every, info.use_graph = check_every, 1 if use_graph else 0
             allow = () if raise_on_noconv else (_lib.MIMPY_E_NOCONV,)
-            ctx.call("mimpy_b200_pcg", F, ptr(plan.m_indptr), ptr(plan.m_indices), ptr(self.a_vals),
-                     ptr(self.a_diag_inv), ptr(h), ptr(lam), ptr(self.work), C.byref(info), allow=allow)
+            if self.layout == "sell":
+                ctx.call("mimpy_b200_pcg_sell", F, ptr(self.sell_ptr), ptr(self.sell_cols), ptr(self.a_vals),
+                         ptr(self.a_diag_inv), ptr(h), ptr(lam), ptr(self.work), C.byref(info), allow=allow)
+            else:
+                ctx.call("mimpy_b200_pcg", F, ptr(plan.m_indptr), ptr(plan.m_indices), ptr(self.a_vals),
+                         ptr(self.a_diag_inv), ptr(h), ptr(lam), ptr(self.work), C.byref(info), allow=allow)
             sol = torch.empty(plan.ndof, dtype=torch.float64, device=dev)
             ctx.call("mimpy_b200_hybrid_recover", C.byref(mv), C.byref(plan.s), ptr(self.w_e),
                      self.alpha, ptr(self.c_diag), ptr(rhs), ptr(lam), ptr(sol))
