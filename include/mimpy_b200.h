@@ -209,6 +209,16 @@ int mimpy_b200_mfd_rhs(mimpy_ctx* ctx, int32_t nc, int32_t flux_dof, const int32
                        double last_neumann_value, const double* forcing /*nc, nullable*/,
                        double* rhs /*flux_dof+nc*/);
 
+/* P1: per-step terms of SinglePhase.start_solving (singlephase.py:263-281):
+ * multipliers[c] = mu / (((p - p_ref) c_f + 1) rho_ref)   (update_m factor, inverse of rho/mu)
+ * c_diag[c]      = c_f phi / dt |E|                        (accumulation diagonal)
+ * rhs[flux_dof+c] += c_diag[c] * p[c] */
+int mimpy_b200_singlephase_terms(mimpy_ctx* ctx, int32_t nc, int32_t flux_dof, double ref_pressure,
+                                 double compressibility, double ref_density, double viscosity,
+                                 double dt, const double* pressure, const double* porosity,
+                                 const double* cell_volume, double* rhs, double* multipliers,
+                                 double* c_diag);
+
 /* -- (7) S1: linear solve -----------------------------------------------------------------------
  * replaces MFD.solve('spsolve') (mfd.py:1349-1358) for the saddle system
  *     M v - DIV^T p = b_v ,  DIV v + C p = b_p

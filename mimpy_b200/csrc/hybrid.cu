@@ -32,45 +32,6 @@ struct HybArgs {
   const double* c_diag;
 };
 
-// in-place Gauss-Jordan inverse of the n x n matrix A (shared memory, leading dim G+1), performed
-// by the G lanes of a group, lane j owning column j.  No pivoting: the blocks are SPD.
-template <int G>
-__device__ __forceinline__ void group_invert(double (*A)[G + 1], int n, int j, int nw) {
-  for (int k = 0; k < nw; ++k) {
-    double pinv = 0., akj = 0.;
-    const bool act = (k < n) && (j < n);
-    if (act) {
-      pinv = 1.0 / A[k][k];
-      akj = A[k][j] * pinv;
-    }
-    __syncwarp();
-    if (act && j != k) {
-      for (int i = 0; i < n; ++i) {
-        if (i == k) continue;
-        A[i][j] -= A[i][k] * akj;
-      }
-      A[k][j] = akj;
-    }
-    __syncwarp();
-    if (act && j == k) {
-      for (int i = 0; i < n; ++i) {
-        if (i == k) continue;
-        A[i][k] = -A[i][k] * pinv;
-      }
-      A[k][k] = pinv;
-    }
-    __syncwarp();
-  }
-}
-
-template <int G>
-__device__ __forceinline__ int warp_max_n(int n) {
-  int nw = n;
-#pragma unroll
-  for (int o = 16; o >= G; o >>= 1) nw = max(nw, __shfl_xor_sync(0xffffffffu, nw, o));
-  return nw;
-}
-
 template <int G>
 __global__ void __launch_bounds__(128)
 k_hybrid_setup(mimpy_mesh_view m, HybArgs h, const double* __restrict__ m_e,

@@ -24,6 +24,7 @@ struct CellSmem {
   double d[G];      // per-row coefficient (method 6) / scratch
   double sg[G];     // orientation as double
   int row[G];       // CSR row start of flux row g(f_i), -1 when dropped
+  double w[G][G + 1];  // method 4: W_E, inverted in place
 };
 
 struct ScatterArgs {
@@ -103,6 +104,7 @@ k_local_matrices(mimpy_mesh_view m, int method, int flags, const int* __restrict
   double T[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   double g00 = 0, g10 = 0, g11 = 0, g20 = 0, g21 = 0, g22 = 0;
   double rr0[3] = {0, 0, 0};  // first row of R^T R (method 0)
+  double rr11 = 0, rr21 = 0, rr22 = 0;  // rest of R^T R (method 4)
   for (int i = 0; i < n; ++i) {
     const double ri0 = s.r[i][0], ri1 = s.r[i][1], ri2 = s.r[i][2];
     const double ni0 = s.n[i][0], ni1 = s.n[i][1], ni2 = s.n[i][2];
@@ -112,6 +114,7 @@ k_local_matrices(mimpy_mesh_view m, int method, int flags, const int* __restrict
     g00 += ni0 * ni0; g10 += ni1 * ni0; g11 += ni1 * ni1;
     g20 += ni2 * ni0; g21 += ni2 * ni1; g22 += ni2 * ni2;
     rr0[0] += ri0 * ri0; rr0[1] += ri0 * ri1; rr0[2] += ri0 * ri2;
+    rr11 += ri1 * ri1; rr21 += ri2 * ri1; rr22 += ri2 * ri2;
   }
   double Ti[9];
   if (n > 0) {
@@ -126,9 +129,14 @@ k_local_matrices(mimpy_mesh_view m, int method, int flags, const int* __restrict
   for (int t = 0; t < 3; ++t) y[t] = Ti[3 * t] * r[0] + Ti[3 * t + 1] * r[1] + Ti[3 * t + 2] * r[2];
 
   // ---- projector: CholeskyQR2 of N (n x 3) ------------------------------------------------
-  double q[3] = {nn[0], nn[1], nn[2]};
-  const bool need_p = (method <= 3) || (method == 6);
+  // method 4 (mfd.py:338-355, 420-421) needs D D^T = I - Q_R Q_R^T with Q_R = orth(R) instead
+  const bool q_from_r = (method == 4);
+  double q[3] = {q_from_r ? r[0] : nn[0], q_from_r ? r[1] : nn[1], q_from_r ? r[2] : nn[2]};
+  const bool need_p = (method <= 4) || (method == 6);
   if (need_p) {
+    if (q_from_r) {
+      g00 = rr0[0]; g10 = rr0[1]; g11 = rr11; g20 = rr0[2]; g21 = rr21; g22 = rr22;
+    }
     if (n > 0) {
       Chol3 c1 = chol3(g00, g10, g11, g20, g21, g22);
       chol3_fwd(c1, q[0], q[1], q[2]);
@@ -214,10 +222,28 @@ k_local_matrices(mimpy_mesh_view m, int method, int flags, const int* __restrict
   int nw = n;
 #pragma unroll
   for (int o = 16; o >= G; o >>= 1) nw = max(nw, __shfl_xor_sync(0xffffffffu, nw, o));
+  if (method == 4) {
+    // W_E = (N (N^T R)^-1 N^T + D D^T) tr(K)/|E| ;  M_E = W_E^-1          mfd.py:349-353, 421
+    double z[3];  // (N^T R)^-1 N_j = T^-T N_j
+#pragma unroll
+    for (int t = 0; t < 3; ++t) z[t] = Ti[t] * nn[0] + Ti[3 + t] * nn[1] + Ti[6 + t] * nn[2];
+    const double scale = (K[0] + K[4] + K[8]) / vol;
+    for (int i = 0; i < n; ++i) {
+      if (valid) {
+        const double w1 = s.n[i][0] * z[0] + s.n[i][1] * z[1] + s.n[i][2] * z[2];
+        const double ddt = ((i == j) ? 1. : 0.) - (s.q[i][0] * q[0] + s.q[i][1] * q[1] + s.q[i][2] * q[2]);
+        s.w[i][j] = (w1 + ddt) * scale;
+      }
+    }
+    __syncwarp();
+    group_invert<G>(s.w, n, j, nw);
+  }
   for (int i = 0; i < nw; ++i) {
     const bool row_ok = i < n;
     double v;
-    if (method == 5 || method == 7) {
+    if (method == 4) {
+      v = (row_ok && valid) ? s.w[i][j] : 0.;
+    } else if (method == 5 || method == 7) {
       v = (i == j) ? s.d[i] : 0.;
     } else {
       const double m0 = s.r[i][0] * y[0] + s.r[i][1] * y[1] + s.r[i][2] * y[2];
@@ -406,7 +432,6 @@ int mimpy_b200_mfd_local_matrices(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, i
   int rc = check_mesh(mesh);
   if (rc) return rc;
   REQUIRE(method >= 0 && method <= 7, "unknown M_E construction method");
-  REQUIRE(method != 4, "method 4 (inverse of W_E) is not available in this build");
   REQUIRE((flags & 1) || mesh->cell_k, "cell_k is NULL");
   REQUIRE(m_ptr && (m_e || diagonality || consistency), "no output requested");
   if (mesh->nc <= 0) return MIMPY_OK;
@@ -431,7 +456,7 @@ int mimpy_b200_mfd_numeric(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mi
   REQUIRE(ctx && sym && vals, "NULL argument");
   int rc = check_mesh(mesh);
   if (rc) return rc;
-  REQUIRE(method >= 0 && method <= 7 && method != 4, "unsupported M_E construction method");
+  REQUIRE(method >= 0 && method <= 7, "unsupported M_E construction method");
   REQUIRE((flags & 1) || mesh->cell_k, "cell_k is NULL");
   if (mesh->nc <= 0) return MIMPY_OK;
   if (!m_e_out && !(flags & MIMPY_FLAG_GENERIC_KERNEL)) {

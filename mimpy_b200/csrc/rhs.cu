@@ -1,5 +1,6 @@
 // Right-hand side of the saddle system: MFD.build_rhs (mfd.py:991-999) with its three parts
-// build_rhs_neumann (1035-1041), build_rhs_dirichlet (1209-1215), build_rhs_forcing (1027-1033).
+// build_rhs_neumann (1035-1041), build_rhs_dirichlet (1209-1215), build_rhs_forcing (1027-1033);
+// and the per-step terms of SinglePhase.start_solving (singlephase.py:256-287).
 #include "common.cuh"
 
 __global__ void k_rhs_dirichlet(int n, const int* __restrict__ faces, const double* __restrict__ values,
@@ -19,11 +20,35 @@ __global__ void k_rhs_forcing(int nc, int F, const double* __restrict__ forcing,
 
 __global__ void k_set_one(double* p, double v) { *p = v; }
 
-extern "C" int mimpy_b200_mfd_rhs(mimpy_ctx* ctx, int32_t nc, int32_t flux_dof,
-                                  const int32_t* face_to_flux, int32_t n_dirichlet,
-                                  const int32_t* dirichlet_faces, const double* dirichlet_values,
-                                  int32_t has_neumann, double last_neumann_value,
-                                  const double* forcing, double* rhs) {
+// singlephase.py:263-281: density = ((p - p_ref) c + 1) rho_ref ; multiplier = mu / density ;
+// c_entry = c phi / dt |E| ; rhs[F+c] += c_entry p
+__global__ void k_singlephase_terms(int nc, int F, double ref_p, double compressibility, double ref_rho,
+                                    double mu, double dt, const double* __restrict__ p,
+                                    const double* __restrict__ porosity, const double* __restrict__ vol,
+                                    double* __restrict__ rhs, double* __restrict__ mult,
+                                    double* __restrict__ c_diag) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  double density = -ref_p;
+  density += p[c];
+  density *= compressibility;
+  density += 1.;
+  density *= ref_rho;
+  mult[c] = mu / density;
+  double ce = compressibility;
+  ce *= porosity[c];
+  ce /= dt;
+  ce *= vol[c];
+  rhs[F + c] += ce * p[c];
+  c_diag[c] = ce;
+}
+
+extern "C" {
+
+int mimpy_b200_mfd_rhs(mimpy_ctx* ctx, int32_t nc, int32_t flux_dof, const int32_t* face_to_flux,
+                       int32_t n_dirichlet, const int32_t* dirichlet_faces,
+                       const double* dirichlet_values, int32_t has_neumann, double last_neumann_value,
+                       const double* forcing, double* rhs) {
   REQUIRE(ctx && face_to_flux && rhs, "NULL argument");
   const int ndof = flux_dof + nc;
   if (ndof <= 0) return MIMPY_OK;
@@ -41,3 +66,19 @@ extern "C" int mimpy_b200_mfd_rhs(mimpy_ctx* ctx, int32_t nc, int32_t flux_dof,
   KERNEL_CHECK();
   return MIMPY_OK;
 }
+
+int mimpy_b200_singlephase_terms(mimpy_ctx* ctx, int32_t nc, int32_t flux_dof, double ref_pressure,
+                                 double compressibility, double ref_density, double viscosity,
+                                 double dt, const double* pressure, const double* porosity,
+                                 const double* cell_volume, double* rhs, double* multipliers,
+                                 double* c_diag) {
+  REQUIRE(ctx && pressure && porosity && cell_volume && rhs && multipliers && c_diag, "NULL argument");
+  if (nc <= 0) return MIMPY_OK;
+  k_singlephase_terms<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(nc, flux_dof, ref_pressure, compressibility,
+                                                                 ref_density, viscosity, dt, pressure, porosity,
+                                                                 cell_volume, rhs, multipliers, c_diag);
+  KERNEL_CHECK();
+  return MIMPY_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+"""Time-dependent slightly compressible single-phase flow with the API of
+mimpy.models.singlephase.SinglePhase (reference singlephase.py:16-299).
+
+Each implicit time step (singlephase.py:252-291) re-scales M by mu/rho(p) per cell (update_m),
+sets the accumulation diagonal c phi |E| / dt, adds it times the old pressure (and the point
+sources) to the right-hand side and solves the saddle system.  Here: mimpy_b200_singlephase_terms,
+the fused numeric assembly is not even needed (only the hybridised face system is rebuilt), the
+solve is the hybridised PCG.  No VTK output; start_solving_newton
+(singlephase.py:301-376, a fixed 100-sweep Picard loop) is not provided.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib, device
+from ..mfd import mfd as _mfd
+
+
+class SinglePhase(object):
+    def __init__(self):
+        self.mesh = None
+        self.mfd = None
+        self.initial_pressure = None
+        self.current_pressure = None
+        self.current_velocity = None
+        self.porosities = None
+        self.viscosity = None
+        self.ref_pressure = None
+        self.ref_density = None
+        self.compressibility = None
+        self.m_x_coo_length = None
+        self.c_start = None
+        self.rhs_mfd = None
+        self.delta_t = 1.
+        self.number_of_time_steps = 1
+        self.output_frequency = 1
+        self.rate_wells = []
+        self.rate_wells_rate = []
+        self.rate_wells_name = []
+        self.model_name = "model"
+        self.pcg_rtol = 1.e-12
+
+    def set_model_name(self, name):
+        self.model_name = name
+
+    def set_output_frequency(self, frequency):
+        self.output_frequency = frequency
+
+    def set_mesh(self, mesh, ctx=None):
+        """singlephase.py:88-96: method 1, consistency check of M_E switched on."""
+        self.mesh = mesh
+        self.mfd = _mfd.MFD()
+        self.mfd.set_mesh(mesh, ctx)
+        self.mfd.set_m_e_construction_method(1)
+        self.mfd.check_m_e = True
+        self.ctx = self.mfd.ctx
+
+    def set_compressibility(self, compressibility):
+        self.compressibility = compressibility
+
+    def set_ref_density(self, ref_density):
+        self.ref_density = ref_density
+
+    def set_ref_pressure(self, ref_pressure):
+        self.ref_pressure = ref_pressure
+
+    def set_viscosity(self, viscosity):
+        self.viscosity = viscosity
+
+    def set_initial_pressure(self, pressures):
+        self.initial_pressure = pressures
+        self.current_pressure = pressures
+        self.current_velocity = np.zeros(self.mfd.flux_dof)
+
+    def set_porosities(self, porosities):
+        self.porosities = porosities
+
+    def set_porosity_by_cell(self, cell_index, porosity):
+        self.porosities[cell_index] = porosity
+
+    def add_rate_well(self, injection_rate, cell_index, well_name):
+        raise NameError("add_rate_well not yet implemented")  # singlephase.py:137-142
+
+    def add_point_rate_well(self, injection_rate, cell_index, well_name):
+        self.rate_wells.append(cell_index)
+        self.rate_wells_rate.append(injection_rate)
+        self.rate_wells_name.append(well_name)
+        return len(self.rate_wells) - 1
+
+    def set_time_step_size(self, delta_t):
+        self.delta_t = delta_t
+
+    def set_number_of_time_steps(self, number_of_time_steps):
+        self.number_of_time_steps = number_of_time_steps
+
+    def apply_pressure_boundary_from_function(self, boundary_marker, p_function):
+        self.mfd.apply_dirichlet_from_function(boundary_marker, p_function)
+
+    def apply_flux_boundary_from_function(self, boundary_marker, f_function):
+        self.mfd.apply_neumann_from_function(boundary_marker, f_function)
+
+    def initialize_system(self):
+        """singlephase.py:182-237: blocks, numbering, static right-hand side."""
+        import torch
+
+        mfd = self.mfd
+        dm, plan = mfd._ensure_plan()
+        self._dm, self._plan = dm, plan
+        self._m_e = mfd._blocks()
+        self.m_x_coo_length = int(device.coo_view(dm, plan, None, want_triples=False)[0][-1].item())
+        n_div = int((mfd.face_to_flux[:, 0][self.mesh.cells.compact()[1]] >= 0).sum())
+        self.c_start = self.m_x_coo_length + 2 * n_div
+        self.c_end = dm.nc
+        self.rhs_mfd = mfd.build_rhs()
+        self._d_rhs_mfd = mfd.device_rhs
+        ctx = self.ctx
+        with ctx.on_stream():
+            self._d_mult = torch.empty(dm.nc, dtype=torch.float64, device=ctx.device)
+            self._d_cdiag = torch.empty(dm.nc, dtype=torch.float64, device=ctx.device)
+        self._hyb = None
+
+    def time_step_output(self, current_time, time_step):
+        pass
+
+    def start_solving(self):
+        """Implicit time stepping (singlephase.py:244-299)."""
+        import torch
+
+        ctx, dm, plan = self.ctx, self._dm, self._plan
+        nc, F = dm.nc, plan.flux_dof
+        self.time_step_output(0., 0)
+        with ctx.on_stream():
+            d_p = torch.as_tensor(np.asarray(self.current_pressure, dtype=float).copy(), device=ctx.device)
+            d_phi = torch.as_tensor(np.asarray(self.porosities, dtype=float), device=ctx.device)
+            wells = None
+            if self.rate_wells:
+                w = np.zeros(nc)
+                for idx, cell in enumerate(self.rate_wells):
+                    w[cell] += self.rate_wells_rate[idx]
+                wells = torch.as_tensor(w, device=ctx.device)
+            for time_step in range(1, self.number_of_time_steps + 1):
+                rhs = self._d_rhs_mfd.clone()
+                ctx.call("mimpy_b200_singlephase_terms", nc, F, float(self.ref_pressure), float(self.compressibility),
+                         float(self.ref_density), float(self.viscosity), float(self.delta_t), _lib.ptr(d_p),
+                         _lib.ptr(d_phi), _lib.ptr(dm.cell_volume), _lib.ptr(rhs), _lib.ptr(self._d_mult),
+                         _lib.ptr(self._d_cdiag))
+                if wells is not None:
+                    rhs[F:] += wells
+                if self._hyb is None:
+                    self._hyb = device.HybridSystem(dm, plan, self._m_e, multipliers=self._d_mult, c_diag=self._d_cdiag)
+                else:
+                    self._hyb.setup(self._m_e, self._d_mult, self._d_cdiag)
+                sol, info = self._hyb.solve(rhs, rtol=self.pcg_rtol, maxit=50000)
+                self.last_solver_info = info
+                d_p = sol[F:].clone()
+                self.current_pressure = device.to_host(ctx, d_p)
+                self.current_velocity = device.to_host(ctx, sol[:F])
+                if time_step % self.output_frequency == 0:
+                    self.time_step_output(time_step * self.delta_t, time_step)

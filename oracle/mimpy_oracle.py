@@ -848,6 +848,58 @@ class OracleTwoPhase(object):
 
 
 # --------------------------------------------------------------------------------------
+# P1: single-phase slightly compressible flow (singlephase.py:88-96, 182-299)
+# --------------------------------------------------------------------------------------
+class OracleSinglePhase(object):
+    """Restatement of SinglePhase.initialize_system / start_solving (implicit time stepping)."""
+
+    def __init__(self, o):
+        self.o = o
+        self.mfd = OracleMFD(o, method=1)  # singlephase.py:95
+        self.rate_wells = []
+        self.rate_wells_rate = []
+        self.delta_t = 1.
+
+    def add_point_rate_well(self, rate, cell):
+        self.rate_wells.append(cell)
+        self.rate_wells_rate.append(rate)
+
+    def initialize_system(self):
+        """singlephase.py:182-237"""
+        mfd = self.mfd
+        mfd.renumber_for_neumann()
+        dv, dvt = mfd.build_div()
+        m = mfd.build_m(save_update_info=True)
+        self.m_x_coo_length = len(m[0])
+        c = mfd.build_bottom_right()
+        data = np.concatenate([m[0], dv[0], dvt[0]])
+        self.c_start = len(data)
+        data = np.concatenate([data, c[0]])
+        row = np.concatenate([m[1], dv[1], dvt[1], c[1]])
+        col = np.concatenate([m[2], dv[2], dvt[2], c[2]])
+        self.lhs_coo = sparse.coo_matrix((data, (row, col)))
+        self.rhs_mfd = mfd.build_rhs()
+
+    def step(self):
+        """One pass of the loop body of start_solving (singlephase.py:256-291)."""
+        o, mfd = self.o, self.mfd
+        rhs = np.zeros(o.nc + mfd.flux_dof)
+        rhs += self.rhs_mfd
+        density = (-self.ref_pressure + self.current_pressure) * self.compressibility
+        density = (density + 1.) * self.ref_density
+        mult = self.viscosity / density
+        c_entry = self.compressibility * self.porosities / self.delta_t * o.cell_volume
+        rhs[mfd.flux_dof:] += c_entry * self.current_pressure
+        self.lhs_coo.data[self.c_start:self.c_start + o.nc] = c_entry
+        for w, cell in enumerate(self.rate_wells):
+            rhs[mfd.flux_dof + cell] += self.rate_wells_rate[w]
+        mfd.update_m(self.lhs_coo.data[:self.m_x_coo_length], mult)
+        sol = spla.spsolve(self.lhs_coo.tocsr().tocsc(), rhs)
+        self.current_pressure = sol[mfd.flux_dof:]
+        self.current_velocity = sol[:mfd.flux_dof]
+
+
+# --------------------------------------------------------------------------------------
 # (de)serialisation of OMesh for the golden fixtures
 # --------------------------------------------------------------------------------------
 _OMESH_ARRAYS = ("points", "face_ptr", "face_points", "cell_ptr", "cell_faces", "cell_sigma",

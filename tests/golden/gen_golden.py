@@ -84,6 +84,9 @@ def dump_system(ref, mesh, method, bc, forcing, with_blocks=True, solve=True):
 
 
 def save(name, d):
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
+    if only and name not in only:  # python gen_golden.py singlephase_543  -> rewrite only that fixture
+        return
     path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **d)
     print("wrote %-28s %7.1f KiB" % (name + ".npz", os.path.getsize(path) / 1024.))
@@ -240,6 +243,38 @@ def main():
         d["c_start"] = np.int64(tp.c_start)
         d["c_end"] = np.int64(tp.c_end)
         save("twophase_633_" + variant, d)
+
+    # ---- 7. single-phase slightly compressible flow (singlephase.py:244-299), 5x4x3, 6 steps --------
+    nx, ny, nz = 5, 4, 3
+    ktab = spd_tensors(nx * ny * nz, 11, full=False)
+    mesh = ref_hex(ref, nx, ny, nz, (5., 4., 3.), ktab)
+    sp = ref.singlephase.SinglePhase()
+    sp.set_mesh(mesh)
+    nc = mesh.get_number_of_cells()
+    for b in (2, 3, 4, 5):
+        sp.apply_flux_boundary_from_function(b, zero_flux)
+    sp.apply_pressure_boundary_from_function(0, lambda p: 2.)
+    sp.apply_pressure_boundary_from_function(1, lambda p: 1.)
+    sp.set_compressibility(1.e-2)
+    sp.set_ref_density(1.3)
+    sp.set_ref_pressure(1.)
+    sp.set_viscosity(0.7)
+    sp.set_porosities(np.linspace(.1, .3, nc))
+    sp.set_time_step_size(0.5)
+    sp.set_number_of_time_steps(1)
+    sp.add_point_rate_well(0.4, 27, "w")
+    quiet(sp.initialize_system)
+    sp.set_initial_pressure(np.full(nc, 1.5))
+    p_hist, v_hist = [], []
+    for step in range(6):
+        quiet(sp.start_solving)          # one time step per call (number_of_time_steps = 1)
+        p_hist.append(np.array(sp.current_pressure))
+        v_hist.append(np.array(sp.current_velocity))
+    d = orc.omesh_to_dict(orc.OMesh.from_mesh(mesh))
+    d["p"] = np.array(p_hist)
+    d["v"] = np.array(v_hist)
+    d["porosities"] = np.linspace(.1, .3, nc)
+    save("singlephase_543", d)
 
 
 if __name__ == "__main__":

@@ -230,3 +230,35 @@ def test_twophase_model_matches_reference_history(golden, variant):
         assert abs(tp.current_s_w - g["s_w"][step - 1]).max() < 1e-10, step
         assert np.linalg.norm(tp.current_p_o - g["p_o"][step - 1]) <= 1e-8 * np.linalg.norm(g["p_o"][step - 1]), step
         assert np.linalg.norm(tp.current_u_t - g["u_t"][step - 1]) <= 1e-8 * np.linalg.norm(g["u_t"][step - 1]), step
+
+
+def test_singlephase_model_matches_reference_history(golden):
+    """SinglePhase (implicit compressible stepping, singlephase.py:244-299): 6 steps vs the reference."""
+    import mimpy_b200.mesh.hexmesh as hexmesh
+    import mimpy_b200.models.singlephase as singlephase
+
+    g = golden("singlephase_543")
+    ref = orc.omesh_from_dict(g)
+    mesh = hexmesh.HexMesh()
+    mesh.build_mesh(5, 4, 3, 5., 4., 3., ref.cell_k.reshape(-1, 3, 3))
+    sp = singlephase.SinglePhase()
+    sp.set_mesh(mesh)
+    nc = mesh.get_number_of_cells()
+    for b in (2, 3, 4, 5):
+        sp.apply_flux_boundary_from_function(b, zero_flux)
+    sp.apply_pressure_boundary_from_function(0, lambda p: 2.)
+    sp.apply_pressure_boundary_from_function(1, lambda p: 1.)
+    sp.set_compressibility(1.e-2)
+    sp.set_ref_density(1.3)
+    sp.set_ref_pressure(1.)
+    sp.set_viscosity(0.7)
+    sp.set_porosities(np.linspace(.1, .3, nc))
+    sp.set_time_step_size(0.5)
+    sp.set_number_of_time_steps(1)
+    sp.add_point_rate_well(0.4, 27, "w")
+    sp.initialize_system()
+    sp.set_initial_pressure(np.full(nc, 1.5))
+    for step in range(len(g["p"])):
+        sp.start_solving()
+        assert np.linalg.norm(sp.current_pressure - g["p"][step]) <= 1e-8 * np.linalg.norm(g["p"][step]), step
+        assert np.linalg.norm(sp.current_velocity - g["v"][step]) <= 1e-8 * np.linalg.norm(g["v"][step]), step

@@ -267,3 +267,23 @@ def test_twophase_history(golden, variant):
         un = np.linalg.norm(g["u_t"][step - 1])
         assert np.linalg.norm(tp.current_u_t - g["u_t"][step - 1]) <= 1e-8 * un
     assert nup == list(g["n_upwind_pairs"])
+
+
+def test_singlephase_history(golden):
+    g = golden("singlephase_543")
+    o = orc.omesh_from_dict(g)
+    sp = orc.OracleSinglePhase(o)
+    for b in (2, 3, 4, 5):
+        sp.mfd.apply_neumann_from_function(b, zero_flux)
+    sp.mfd.apply_dirichlet_from_function(0, lambda p: 2.)
+    sp.mfd.apply_dirichlet_from_function(1, lambda p: 1.)
+    sp.compressibility, sp.ref_density, sp.ref_pressure, sp.viscosity = 1.e-2, 1.3, 1., 0.7
+    sp.porosities = g["porosities"]
+    sp.delta_t = 0.5
+    sp.add_point_rate_well(0.4, 27)
+    sp.initialize_system()
+    sp.current_pressure = np.full(o.nc, 1.5)
+    for step in range(len(g["p"])):
+        sp.step()
+        assert np.linalg.norm(sp.current_pressure - g["p"][step]) <= 1e-10 * np.linalg.norm(g["p"][step])
+        assert np.linalg.norm(sp.current_velocity - g["v"][step]) <= 1e-9 * np.linalg.norm(g["v"][step])
