@@ -39,6 +39,7 @@ extern "C" {
 /* flags of mfd_local_matrices / mfd_numeric */
 #define MIMPY_FLAG_K_UNITY 1        /* N_E = s n (mfd.py:300-304)                          */
 #define MIMPY_FLAG_GENERIC_KERNEL 2 /* force the generic warp-group kernel (tests, polyhedra) */
+#define MIMPY_FLAG_DIRECT_KERNEL 4  /* hex meshes: thread-per-cell direct stores instead of bricks */
 
 typedef struct mimpy_ctx mimpy_ctx;
 
@@ -61,6 +62,10 @@ typedef struct {
   int32_t nf;
   int32_t max_faces;          /* max faces per cell (<= MIMPY_MAX_CELL_FACES)             */
   int32_t uniform_faces;      /* >0: every cell has exactly this many faces (hex: 6)      */
+  int32_t hex_nx, hex_ny, hex_nz; /* >0: structured hex mesh with HexMesh's cell/face numbering
+                                 (hexmesh.py:172-243) and that many cells per axis; enables the
+                                 brick-tiled assembly kernel.  0 for any other mesh.           */
+  int32_t reserved0;
   const int32_t* cell_ptr;    /* nc+1 offsets into cell_faces / cell_sigma                */
   const int32_t* cell_faces;  /* global face ids, reference order (mesh.py:1034-1042)     */
   const int8_t* cell_sigma;   /* cell_normal_orientation (mesh.py:1044-1056)              */

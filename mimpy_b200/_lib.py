@@ -19,6 +19,7 @@ _f64 = C.c_double
 
 class MeshView(C.Structure):
     _fields_ = [("nc", _i32), ("nf", _i32), ("max_faces", _i32), ("uniform_faces", _i32),
+                ("hex_nx", _i32), ("hex_ny", _i32), ("hex_nz", _i32), ("reserved0", _i32),
                 ("cell_ptr", _vp), ("cell_faces", _vp), ("cell_sigma", _vp), ("face_geom", _vp),
                 ("cell_k", _vp), ("cell_centroid", _vp), ("cell_volume", _vp)]
 

@@ -1,36 +1,38 @@
-// Fused numeric assembly for meshes whose cells all have NF faces (hexes: NF = 6) -- the
-// headline kernel (700 algorithmic bytes per hex cell).
+// Fused numeric assembly for hexahedral meshes (every cell has 6 faces) -- the headline kernel
+// (700 algorithmic bytes per hex cell).  Two kernels share one thread-per-cell core:
 //
-// One CTA of 128 threads owns 128 consecutive cells and runs three stages:
-//
-//  S  staging: every contiguous input of the CTA (K, centroids, volumes, face ids, orientations,
-//     the pos_* byte maps, the cell-row starts) is fetched with coalesced, fully unrolled loads
-//     into shared memory -- ~40 independent loads in flight per thread, one DRAM latency.
-//  A  thread-per-cell: the whole 3xNF / 3x3 pipeline of MFD.build_m_e (mfd.py:357-483, methods 0,
-//     1, 6) in registers -- no redundant work across lanes (the 3x3 inverse, the two Cholesky
-//     factorisations and their divisions/rsqrts are done once per cell, not once per face).
+//  cell_entries<NF, METHOD>: the whole 3xNF / 3x3 pipeline of MFD.build_m_e (mfd.py:357-483,
+//     methods 0, 1, 6) in registers -- no redundant work across lanes (the 3x3 inverse, the two
+//     Cholesky factorisations and their divisions/rsqrts are done once per cell, not once per face).
 //     Orientations are folded into the operands:  R~_i = s_i a_i (x_f - x_E),  KN_i = K n_f, so
 //     that  s_i s_j M_E[i,j] = R~_i . (T^-1 R~_j) + coef_i (d_ij - Q~_i . Q~_j)  directly
 //     (T = R~^T KN, Q~ = orth(KN) by CholeskyQR2; mfd.py:575-588 applies s_i s_j afterwards).
-//     The NF^2 signed, scaled entries go to shared memory.
-//  B  entry-per-thread: the CTA streams its 128*NF^2 entries out of shared memory; consecutive
-//     lanes hold consecutive (i,j) of one cell, i.e. contiguous pieces of CSR row g(f_i).  No
-//     global loads are left in this stage (positions and row starts come from shared memory).
 //
-// Diagonal entries M[g,g] have two contributors (the two cells of face f).  Instead of atomics on
-// a pre-zeroed array, the lower-index cell PUBLISHES its contribution in diag_pub[f] and the
-// higher-index cell adds it and writes the slot -- a + b in a fixed order, bit-reproducible.  CTAs
-// take their cell range from an atomic ticket, so a CTA only ever waits for CTAs that started
-// earlier and are resident (the ordering argument of decoupled look-back scans): no deadlock.
+//  k_numeric_direct  (any uniform-6 mesh): each thread stores its 36+13 entries straight from
+//     registers to their CSR slots.  Simple, but every 8-byte store is its own L2 sector write
+//     (48 write sectors per cell measured; the L2 is the busiest unit at 65 %).
+//
+//  k_numeric_brick   (structured hex meshes in HexMesh numbering): a CTA owns a brick of 8x4x4
+//     cells.  The 464 face rows of the brick are ASSEMBLED IN SHARED MEMORY (row buffer of 13
+//     slots per row): for the 2/3 of the rows whose two cells both live in the brick the CTA then
+//     writes the complete row -- M entries of both cells, summed diagonal, both -DIV^T entries -- as
+//     one contiguous 88-104 byte burst (3-4 sectors instead of 13 partial ones).  Rows on the brick
+//     surface are written as the brick's half (the slots the other brick owns stay untouched).
+//
+// Diagonal entries M[g,g] have two contributors (the two cells of face f).  Inside a brick they are
+// added in shared memory in a fixed order (lower cell first).  Across CTAs the lower-index cell
+// PUBLISHES its half in diag_pub[f] and the higher-index cell adds it and writes the slot -- a + b
+// in a fixed order, bit-reproducible, no atomics on the matrix.  CTAs take their cell range / brick
+// from an atomic ticket and bricks are ordered lexicographically (k slowest), so a CTA only ever
+// waits for CTAs that started earlier and are resident (the ordering argument of decoupled
+// look-back scans): no deadlock; the wait is bounded and raises an error flag instead of hanging.
 #include <stdlib.h>
 
 #include "common.cuh"
 
-#define AU_CELLS 128
 #define AU_SENTINEL 0xFFFFFFFFFFFFFFFFull  // memset(0xFF): a NaN no arithmetic produces
 
 struct UniArgs {
-  const int* face_to_flux;
   const int* indptr;
   const uint8_t* pos_m;
   const uint8_t* pos_dt;
@@ -60,365 +62,12 @@ __device__ __forceinline__ Chol3 chol3r(double g00, double g10, double g11, doub
   return c;
 }
 
-template <int NF>
-struct UniSmem {
-  // phase-A inputs (dead once every thread has read its cell) alias the entry buffer
-  union {
-    struct {
-      double k[AU_CELLS * 9];
-      double xc[AU_CELLS * 3];
-      double vol[AU_CELLS];
-    } in;
-    double entries[AU_CELLS * (NF * NF + 1)];  // odd per-cell stride: conflict-free 64-bit stores
-  } u;
-  int ids[AU_CELLS * NF];       // global face ids
-  int rowstart[AU_CELLS * NF];  // indptr[g(f_i)] or -1 (cell_rowstart of the symbolic plan)
-  int cellrow[AU_CELLS + 1];    // indptr[F + c]
-  unsigned int ticket;
-  alignas(16) uint8_t pos_m[AU_CELLS * NF * NF];
-  alignas(16) uint8_t pos_dt[AU_CELLS * NF];
-  alignas(16) uint8_t pos_d[AU_CELLS * NF];
-  alignas(16) uint8_t role[AU_CELLS * NF];
-  alignas(16) int8_t sg[AU_CELLS * NF];
-};
-
-// COUNT elements (multiple of 128 per pass) from src[first ...] into shared memory: all loads are
-// issued before the first store (PER independent requests in flight per thread)
-template <typename T, int COUNT>
-__device__ __forceinline__ void stage(T* dst, const T* __restrict__ src, long long first, long long limit) {
-  constexpr int PER = (COUNT + AU_CELLS - 1) / AU_CELLS;
-  T tmp[PER];
-#pragma unroll
-  for (int k = 0; k < PER; ++k) {
-    const int o = k * AU_CELLS + threadIdx.x;
-    const long long g = first + o;
-    tmp[k] = (o < COUNT && g < limit) ? src[g] : T(0);
-  }
-#pragma unroll
-  for (int k = 0; k < PER; ++k) {
-    const int o = k * AU_CELLS + threadIdx.x;
-    if (o < COUNT) dst[o] = tmp[k];
-  }
-}
-
-// byte maps as 32-bit words (the CTA's slice starts at a multiple of 128*NF bytes)
-template <int BYTES>
-__device__ __forceinline__ void stage_bytes(uint8_t* dst, const uint8_t* __restrict__ src, long long first,
-                                            long long limit) {
-  static_assert(BYTES % 4 == 0, "slice must be a whole number of words");
-  if (first + BYTES <= limit && ((reinterpret_cast<uintptr_t>(src) + first) & 3) == 0) {
-    stage<unsigned int, BYTES / 4>(reinterpret_cast<unsigned int*>(dst),
-                                   reinterpret_cast<const unsigned int*>(src + first), 0, BYTES / 4);
-  } else {
-    stage<uint8_t, BYTES>(dst, src, first, limit);
-  }
-}
-
-template <int NF, int METHOD>
-__global__ void __launch_bounds__(AU_CELLS, 4)
-k_numeric_uniform(mimpy_mesh_view m, int flags, UniArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  UniSmem<NF>& s = *reinterpret_cast<UniSmem<NF>*>(smem_raw);
-  const int t = threadIdx.x;
-  if (t == 0) s.ticket = atomicAdd(a.ticket, 1u);
-  __syncthreads();
-  const long long c0 = (long long)s.ticket * AU_CELLS;
-  const int nc = m.nc;
-  const int F = a.flux_dof;
-  const bool k_unity = flags & 1;
-  constexpr int NN = NF * NF;
-  constexpr int ES = NN + 1;
-  const long long cell = c0 + t;
-  const bool ok = cell < nc;
-
-  // ---- S0: face ids first, so that the record gathers can start as early as possible ---------
-  stage<int, AU_CELLS * NF>(s.ids, m.cell_faces, c0 * NF, (long long)nc * NF);
-  __syncthreads();
-  int fid[NF];
-  double2 rec[NF][4];
-#pragma unroll
-  for (int i = 0; i < NF; ++i) fid[i] = s.ids[t * NF + i];
-#pragma unroll
-  for (int i = 0; i < NF; ++i) {
-    const double2* p = reinterpret_cast<const double2*>(m.face_geom + 8 * (size_t)(ok ? fid[i] : 0));
-#pragma unroll
-    for (int q = 0; q < 4; ++q) rec[i][q] = __ldg(p + q);
-  }
-  // ---- S1: the CTA's contiguous inputs, in flight together with the gathers ---------------------
-  if (!k_unity) stage<double, AU_CELLS * 9>(s.u.in.k, m.cell_k, c0 * 9, (long long)nc * 9);
-  stage<double, AU_CELLS * 3>(s.u.in.xc, m.cell_centroid, c0 * 3, (long long)nc * 3);
-  stage<double, AU_CELLS>(s.u.in.vol, m.cell_volume, c0, nc);
-  stage<int, AU_CELLS * NF>(s.rowstart, a.cell_rowstart, c0 * NF, (long long)nc * NF);
-  stage_bytes<AU_CELLS * NF>(reinterpret_cast<uint8_t*>(s.sg), reinterpret_cast<const uint8_t*>(m.cell_sigma),
-                             c0 * NF, (long long)nc * NF);
-  stage_bytes<AU_CELLS * NN>(s.pos_m, a.pos_m, c0 * NN, (long long)nc * NN);
-  stage_bytes<AU_CELLS * NF>(s.pos_dt, a.pos_dt, c0 * NF, (long long)nc * NF);
-  stage_bytes<AU_CELLS * NF>(s.pos_d, a.pos_d, c0 * NF, (long long)nc * NF);
-  stage_bytes<AU_CELLS * NF>(s.role, a.role, c0 * NF, (long long)nc * NF);
-  for (int k = t; k <= AU_CELLS; k += AU_CELLS) {
-    const long long c = c0 + k;
-    s.cellrow[k] = (c <= nc) ? a.indptr[F + c] : 0;
-  }
-  const double mult = (a.multipliers && ok) ? __ldg(a.multipliers + cell) : 1.;
-  const double cdiag = (a.c_diag && ok) ? __ldg(a.c_diag + cell) : 0.;
-  __syncthreads();
-
-  double K[9], xc[3], vol;
-  double sg[NF];
-  if (k_unity) {
-#pragma unroll
-    for (int q = 0; q < 9; ++q) K[q] = (q % 4 == 0) ? 1. : 0.;
-  } else {
-#pragma unroll
-    for (int q = 0; q < 9; ++q) K[q] = s.u.in.k[t * 9 + q];
-  }
-#pragma unroll
-  for (int q = 0; q < 3; ++q) xc[q] = s.u.in.xc[t * 3 + q];
-  vol = s.u.in.vol[t];
-#pragma unroll
-  for (int i = 0; i < NF; ++i) sg[i] = (double)s.sg[t * NF + i];
-  __syncthreads();  // inputs consumed: the entry buffer may now be overwritten
-
-  if (ok) {
-    double rt[NF][3], kn[NF][3];
-    double dcoef[NF];  // method 6
-    double Ki[9];
-    if (METHOD == 6) inv3(K, Ki);
-    const int crow = s.cellrow[t];
-#pragma unroll
-    for (int i = 0; i < NF; ++i) {
-      const double area = rec[i][0].x;
-      const double nx = rec[i][0].y, ny = rec[i][1].x, nz = rec[i][1].y;
-      const double dx = rec[i][2].x - xc[0], dy = rec[i][2].y - xc[1], dz = rec[i][3].x - xc[2];
-      const double sa = sg[i] * area;
-      const int rs = s.rowstart[t * NF + i];
-      if (rs >= 0) {  // DIV / -DIV^T                                    mfd.py:232-243
-        a.vals[rs + s.pos_dt[t * NF + i]] = -sa;
-        a.vals[crow + s.pos_d[t * NF + i]] = sa;
-      }
-      rt[i][0] = sa * dx;
-      rt[i][1] = sa * dy;
-      rt[i][2] = sa * dz;
-      kn[i][0] = K[0] * nx + K[1] * ny + K[2] * nz;
-      kn[i][1] = K[3] * nx + K[4] * ny + K[5] * nz;
-      kn[i][2] = K[6] * nx + K[7] * ny + K[8] * nz;
-      if (METHOD == 6) {  // d_f = n^T K^-1 n a_f |x_f - x_E|            mfd.py:446-453
-        const double e = nx * (Ki[0] * nx + Ki[1] * ny + Ki[2] * nz) +
-                         ny * (Ki[3] * nx + Ki[4] * ny + Ki[5] * nz) +
-                         nz * (Ki[6] * nx + Ki[7] * ny + Ki[8] * nz);
-        dcoef[i] = e * area * sqrt(dx * dx + dy * dy + dz * dz);
-      }
-    }
-    // C diagonal                                                        mfd.py:766-772
-    a.vals[s.cellrow[t + 1] - 1] = a.c_diag ? cdiag : a.alpha * vol;
-    // ---- T = R~^T KN, G = KN^T KN ------------------------------------------------------------------
-    double T[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    double g00 = 0, g10 = 0, g11 = 0, g20 = 0, g21 = 0, g22 = 0;
-    double rr0 = 0, rr1 = 0, rr2 = 0;
-#pragma unroll
-    for (int i = 0; i < NF; ++i) {
-      T[0] += rt[i][0] * kn[i][0]; T[1] += rt[i][0] * kn[i][1]; T[2] += rt[i][0] * kn[i][2];
-      T[3] += rt[i][1] * kn[i][0]; T[4] += rt[i][1] * kn[i][1]; T[5] += rt[i][1] * kn[i][2];
-      T[6] += rt[i][2] * kn[i][0]; T[7] += rt[i][2] * kn[i][1]; T[8] += rt[i][2] * kn[i][2];
-      g00 += kn[i][0] * kn[i][0]; g10 += kn[i][1] * kn[i][0]; g11 += kn[i][1] * kn[i][1];
-      g20 += kn[i][2] * kn[i][0]; g21 += kn[i][2] * kn[i][1]; g22 += kn[i][2] * kn[i][2];
-      if (METHOD == 0) {
-        rr0 += rt[i][0] * rt[i][0]; rr1 += rt[i][0] * rt[i][1]; rr2 += rt[i][0] * rt[i][2];
-      }
-    }
-    double Ti[9];
-    inv3(T, Ti);
-    double u = 0.;
-    if (METHOD == 0) u = rr0 * Ti[0] + rr1 * Ti[3] + rr2 * Ti[6];      // mfd.py:380-382
-    if (METHOD == 1) u = vol / (K[0] + K[4] + K[8]);                    // mfd.py:387
-    u *= mult;
-    // ---- Q~ = orth(KN): CholeskyQR2 -------------------------------------------------------------------
-    {
-      const Chol3 c1 = chol3r(g00, g10, g11, g20, g21, g22);
-      double h00 = 0, h10 = 0, h11 = 0, h20 = 0, h21 = 0, h22 = 0;
-#pragma unroll
-      for (int i = 0; i < NF; ++i) {
-        chol3_fwd(c1, kn[i][0], kn[i][1], kn[i][2]);
-        h00 += kn[i][0] * kn[i][0]; h10 += kn[i][1] * kn[i][0]; h11 += kn[i][1] * kn[i][1];
-        h20 += kn[i][2] * kn[i][0]; h21 += kn[i][2] * kn[i][1]; h22 += kn[i][2] * kn[i][2];
-      }
-      const Chol3 c2 = chol3r(h00, h10, h11, h20, h21, h22);
-#pragma unroll
-      for (int i = 0; i < NF; ++i) chol3_fwd(c2, kn[i][0], kn[i][1], kn[i][2]);
-    }
-    // ---- entries: row i uses R~_i, Q~_i ; column j uses Y~_j = mult T^-1 R~_j, Q~_j ---------------
-    double* ent = s.u.entries + t * ES;
-#pragma unroll
-    for (int j = 0; j < NF; ++j) {
-      double y[3];
-#pragma unroll
-      for (int q = 0; q < 3; ++q)
-        y[q] = mult * (Ti[3 * q] * rt[j][0] + Ti[3 * q + 1] * rt[j][1] + Ti[3 * q + 2] * rt[j][2]);
-#pragma unroll
-      for (int i = 0; i < NF; ++i) {
-        const double coef = (METHOD == 6) ? mult * dcoef[i] : u;
-        const double m0 = rt[i][0] * y[0] + rt[i][1] * y[1] + rt[i][2] * y[2];
-        const double qq = kn[i][0] * kn[j][0] + kn[i][1] * kn[j][1] + kn[i][2] * kn[j][2];
-        const double v = m0 + coef * (((i == j) ? 1. : 0.) - qq);
-        ent[i * NF + j] = v;
-        // lower-index cell of a shared face publishes its diagonal contribution right away
-        if (i == j && s.role[t * NF + i] == 1 && s.rowstart[t * NF + i] >= 0) a.diag_pub[fid[i]] = v;
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- B: stream the off-diagonal M entries (no global loads) -------------------------------------
-  const long long elimit = (long long)nc * NN - c0 * NN;
-#pragma unroll 6
-  for (int k = 0; k < NN; ++k) {
-    const int e = k * AU_CELLS + t;
-    if (e >= elimit) break;
-    const int cl = e / NN;
-    const int ij = e - cl * NN;
-    const int i = ij / NF;
-    const int j = ij - i * NF;
-    const unsigned pos = s.pos_m[e];
-    const int rs = s.rowstart[cl * NF + i];
-    if (i != j && pos != 0xFFu && rs >= 0) a.vals[rs + pos] = s.u.entries[cl * ES + ij];
-  }
-  // ---- diagonals: the finishing cell adds the half published by the lower-index cell ---------------
-  // first an optimistic, non-blocking read of all NF candidates (independent loads), then spin on
-  // the few that were not there yet
-  unsigned long long pub[NF];
-#pragma unroll
-  for (int k = 0; k < NF; ++k) {
-    const int e = k * AU_CELLS + t;
-    pub[k] = 0ull;
-    if (c0 + e / NF < nc && s.role[e] == 2 && s.rowstart[e] >= 0) {
-      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(a.diag_pub + s.ids[e]);
-      asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(pub[k]) : "l"(src));
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < NF; ++k) {
-    const int e = k * AU_CELLS + t;
-    const int cl = e / NF;
-    const int i = e - cl * NF;
-    if (c0 + cl >= nc) break;
-    const int rs = s.rowstart[e];
-    const unsigned role = s.role[e];
-    if (rs < 0 || role == 1) continue;  // Neumann, or the other cell finishes this diagonal
-    double d = s.u.entries[cl * ES + i * NF + i];
-    if (role == 2) {
-      unsigned long long bits = pub[k];
-      if (bits == AU_SENTINEL) {
-        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(a.diag_pub + s.ids[e]);
-        unsigned int spins = 0;
-        do {
-          __nanosleep(64);
-          asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(bits) : "l"(src));
-        } while (bits == AU_SENTINEL && ++spins < (1u << 22));
-        if (bits == AU_SENTINEL) atomicExch(a.error_flag, 1u);
-      }
-      d = __longlong_as_double((long long)bits) + d;  // lower cell first: fixed order
-    }
-    a.vals[rs + s.pos_m[cl * NN + i * NF + i]] = d;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Variant "direct": thread-per-cell end to end.  No shared-memory staging or transposition: every
-// input address is a function of the cell index alone, so all loads of a thread are issued up
-// front (two dependent levels: face ids -> face records), and each entry is stored straight from
-// registers to its CSR slot.  Far fewer instructions and barriers, higher occupancy; costs ~30 %
-// more L2 write-sector slots than the row-cooperative stores of the staged variant.
-// ---------------------------------------------------------------------------------------------
-#define AD_THREADS 128
-
-template <int NF, int METHOD>
-#ifndef AD_MINB
-#define AD_MINB 2  /* measured on B200: 2 -> 7.0 ms, 3 -> 7.5 ms, 4 -> 9.5 ms at 256^3 (spills) */
-#endif
-__global__ void __launch_bounds__(AD_THREADS, AD_MINB)
-k_numeric_direct(mimpy_mesh_view m, int flags, UniArgs a) {
-  __shared__ unsigned int s_ticket;
-  const int t = threadIdx.x;
-  if (t == 0) s_ticket = atomicAdd(a.ticket, 1u);
-  __syncthreads();
-  const long long cell = (long long)s_ticket * AD_THREADS + t;
-  if (cell >= m.nc) return;
-  const int F = a.flux_dof;
-  const bool k_unity = flags & 1;
-  const bool dbg_no_mstore = flags & 256, dbg_no_gather = flags & 512, dbg_no_wait = flags & 1024;
-  constexpr int NN = NF * NF;
-
-  // ---- level-1 loads (addresses depend on the cell index only) ---------------------------------
-  int fid[NF], rs[NF];
-  {
-    const int2* p = reinterpret_cast<const int2*>(m.cell_faces + cell * NF);
-    const int2* q = reinterpret_cast<const int2*>(a.cell_rowstart + cell * NF);
-#pragma unroll
-    for (int i = 0; i < NF / 2; ++i) {
-      const int2 v = __ldg(p + i);
-      fid[2 * i] = v.x;
-      fid[2 * i + 1] = v.y;
-      const int2 w = __ldg(q + i);
-      rs[2 * i] = w.x;
-      rs[2 * i + 1] = w.y;
-    }
-  }
-  double K[9];
-  if (k_unity) {
-#pragma unroll
-    for (int q = 0; q < 9; ++q) K[q] = (q % 4 == 0) ? 1. : 0.;
-  } else {
-#pragma unroll
-    for (int q = 0; q < 9; ++q) K[q] = __ldg(m.cell_k + cell * 9 + q);
-  }
-  double xc[3];
-#pragma unroll
-  for (int q = 0; q < 3; ++q) xc[q] = __ldg(m.cell_centroid + cell * 3 + q);
-  const double vol = __ldg(m.cell_volume + cell);
-  const double mult = a.multipliers ? __ldg(a.multipliers + cell) : 1.;
-  const int crow = __ldg(a.indptr + F + cell);
-  const int crow_end = __ldg(a.indptr + F + cell + 1);
-  unsigned int pm[NN / 4];
-  {
-    const unsigned int* p = reinterpret_cast<const unsigned int*>(a.pos_m + cell * NN);
-#pragma unroll
-    for (int q = 0; q < NN / 4; ++q) pm[q] = __ldg(p + q);
-  }
-  // 6-byte maps: three 16-bit words each (cell*6 is even)
-  unsigned short w_sg[NF / 2], w_dt[NF / 2], w_d[NF / 2], w_role[NF / 2];
-  {
-    const unsigned short* p0 = reinterpret_cast<const unsigned short*>(m.cell_sigma + cell * NF);
-    const unsigned short* p1 = reinterpret_cast<const unsigned short*>(a.pos_dt + cell * NF);
-    const unsigned short* p2 = reinterpret_cast<const unsigned short*>(a.pos_d + cell * NF);
-    const unsigned short* p3 = reinterpret_cast<const unsigned short*>(a.role + cell * NF);
-#pragma unroll
-    for (int q = 0; q < NF / 2; ++q) {
-      w_sg[q] = __ldg(p0 + q);
-      w_dt[q] = __ldg(p1 + q);
-      w_d[q] = __ldg(p2 + q);
-      w_role[q] = __ldg(p3 + q);
-    }
-  }
-  // ---- level-2 loads: face records; optimistic read of the published diagonal halves ------------
-  double2 rec[NF][4];
-#pragma unroll
-  for (int i = 0; i < NF; ++i) {
-    const double2* p = reinterpret_cast<const double2*>(m.face_geom + 8 * (size_t)(dbg_no_gather ? (cell % 1024) * 3 + i : fid[i]));
-#pragma unroll
-    for (int q = 0; q < 4; ++q) rec[i][q] = __ldg(p + q);
-  }
-  auto byte_of = [](const unsigned short* w, int i) -> unsigned { return (w[i >> 1] >> ((i & 1) * 8)) & 0xFFu; };
-  unsigned long long pub[NF];
-#pragma unroll
-  for (int i = 0; i < NF; ++i) {
-    pub[i] = 0ull;
-    if (byte_of(w_role, i) == 2 && rs[i] >= 0 && !dbg_no_wait) {
-      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(a.diag_pub + fid[i]);
-      asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(pub[i]) : "l"(src));
-    }
-  }
-
-  // ---- geometry -> R~, KN ; DIV / -DIV^T / C stores -------------------------------------------------
+// rec[i] = the packed face record [a, n, x_f, 0]; sgn[i] = orientation.  Calls sink(i, j, v) with
+// v = mult * s_i s_j M_E[i,j] for all NF^2 entries, row by row.
+template <int NF, int METHOD, class Sink>
+__device__ __forceinline__ void cell_entries(const double (&K)[9], const double (&xc)[3], double vol,
+                                             double mult, const double2 (&rec)[NF][4],
+                                             const double (&sgn)[NF], Sink&& sink) {
   double rt[NF][3], kn[NF][3];
   double dcoef[NF];
   double Ki[9];
@@ -428,27 +77,20 @@ k_numeric_direct(mimpy_mesh_view m, int flags, UniArgs a) {
     const double area = rec[i][0].x;
     const double nx = rec[i][0].y, ny = rec[i][1].x, nz = rec[i][1].y;
     const double dx = rec[i][2].x - xc[0], dy = rec[i][2].y - xc[1], dz = rec[i][3].x - xc[2];
-    const double sgn = (double)(signed char)byte_of(w_sg, i);
-    const double sa = sgn * area;
-    if (rs[i] >= 0) {  // mfd.py:232-243
-      a.vals[rs[i] + byte_of(w_dt, i)] = -sa;
-      a.vals[crow + byte_of(w_d, i)] = sa;
-    }
+    const double sa = sgn[i] * area;
     rt[i][0] = sa * dx;
     rt[i][1] = sa * dy;
     rt[i][2] = sa * dz;
     kn[i][0] = K[0] * nx + K[1] * ny + K[2] * nz;
     kn[i][1] = K[3] * nx + K[4] * ny + K[5] * nz;
     kn[i][2] = K[6] * nx + K[7] * ny + K[8] * nz;
-    if (METHOD == 6) {
+    if (METHOD == 6) {  // d_f = n^T K^-1 n a_f |x_f - x_E|            mfd.py:446-453
       const double e = nx * (Ki[0] * nx + Ki[1] * ny + Ki[2] * nz) +
                        ny * (Ki[3] * nx + Ki[4] * ny + Ki[5] * nz) +
                        nz * (Ki[6] * nx + Ki[7] * ny + Ki[8] * nz);
       dcoef[i] = e * area * sqrt(dx * dx + dy * dy + dz * dz);
     }
   }
-  a.vals[crow_end - 1] = a.c_diag ? __ldg(a.c_diag + cell) : a.alpha * vol;  // mfd.py:766-772
-
   double T[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   double g00 = 0, g10 = 0, g11 = 0, g20 = 0, g21 = 0, g22 = 0;
   double rr0 = 0, rr1 = 0, rr2 = 0;
@@ -466,8 +108,8 @@ k_numeric_direct(mimpy_mesh_view m, int flags, UniArgs a) {
   double Ti[9];
   inv3(T, Ti);
   double u = 0.;
-  if (METHOD == 0) u = rr0 * Ti[0] + rr1 * Ti[3] + rr2 * Ti[6];
-  if (METHOD == 1) u = vol / (K[0] + K[4] + K[8]);
+  if (METHOD == 0) u = rr0 * Ti[0] + rr1 * Ti[3] + rr2 * Ti[6];      // mfd.py:380-382
+  if (METHOD == 1) u = vol / (K[0] + K[4] + K[8]);                    // mfd.py:387
   u *= mult;
   {
     const Chol3 c1 = chol3r(g00, g10, g11, g20, g21, g22);
@@ -482,11 +124,9 @@ k_numeric_direct(mimpy_mesh_view m, int flags, UniArgs a) {
 #pragma unroll
     for (int i = 0; i < NF; ++i) chol3_fwd(c2, kn[i][0], kn[i][1], kn[i][2]);
   }
-  // ---- entries, row by row, stored from registers ----------------------------------------------------
-  double diag[NF];
 #pragma unroll
   for (int i = 0; i < NF; ++i) {
-    // row i: R~_i^T (mult T^-1) R~_j  -> z_i = mult T^-T R~_i, then z_i . R~_j
+    // row i: R~_i^T (mult T^-1) R~_j  ->  z_i = mult T^-T R~_i, then z_i . R~_j
     double z[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q)
@@ -496,67 +136,314 @@ k_numeric_direct(mimpy_mesh_view m, int flags, UniArgs a) {
     for (int j = 0; j < NF; ++j) {
       const double m0 = z[0] * rt[j][0] + z[1] * rt[j][1] + z[2] * rt[j][2];
       const double qq = kn[i][0] * kn[j][0] + kn[i][1] * kn[j][1] + kn[i][2] * kn[j][2];
-      const double v = m0 + coef * (((i == j) ? 1. : 0.) - qq);
-      if (i == j) {
-        diag[i] = v;
-      } else {
-        const unsigned pos = (pm[(i * NF + j) >> 2] >> (((i * NF + j) & 3) * 8)) & 0xFFu;
-        if (rs[i] >= 0 && pos != 0xFFu && !dbg_no_mstore) a.vals[rs[i] + pos] = v;
-      }
+      sink(i, j, m0 + coef * (((i == j) ? 1. : 0.) - qq));
     }
-    // the lower-index cell of a shared face publishes its diagonal half as soon as it exists
-    if (rs[i] >= 0 && byte_of(w_role, i) == 1) a.diag_pub[fid[i]] = diag[i];
-  }
-  // ---- diagonals ---------------------------------------------------------------------------------------
-#pragma unroll
-  for (int i = 0; i < NF; ++i) {
-    const unsigned role = byte_of(w_role, i);
-    if (rs[i] < 0 || role == 1) continue;
-    double d = diag[i];
-    if (role == 2 && !dbg_no_wait) {
-      unsigned long long bits = pub[i];
-      if (bits == AU_SENTINEL) {
-        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(a.diag_pub + fid[i]);
-        unsigned int spins = 0;
-        do {
-          __nanosleep(64);
-          asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(bits) : "l"(src));
-        } while (bits == AU_SENTINEL && ++spins < (1u << 22));
-        if (bits == AU_SENTINEL) atomicExch(a.error_flag, 1u);
-      }
-      d = __longlong_as_double((long long)bits) + d;
-    }
-    const unsigned pos = (pm[(i * NF + i) >> 2] >> (((i * NF + i) & 3) * 8)) & 0xFFu;
-    a.vals[rs[i] + pos] = d;
   }
 }
 
+__device__ __forceinline__ unsigned byte_of(const unsigned short* w, int i) {
+  return (w[i >> 1] >> ((i & 1) * 8)) & 0xFFu;
+}
+
+// bounded wait for the half published by the lower-index cell
+__device__ __forceinline__ double wait_published(const double* slot, unsigned long long first,
+                                                 unsigned int* error_flag) {
+  unsigned long long bits = first;
+  if (bits == AU_SENTINEL) {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(slot);
+    unsigned int spins = 0;
+    do {
+      __nanosleep(64);
+      asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(bits) : "l"(src));
+    } while (bits == AU_SENTINEL && ++spins < (1u << 22));
+    if (bits == AU_SENTINEL) atomicExch(error_flag, 1u);
+  }
+  return __longlong_as_double((long long)bits);
+}
+
+// per-cell inputs whose addresses depend on the cell index only
+template <int NF>
+struct CellIn {
+  int fid[NF], rs[NF];
+  double K[9], xc[3], vol, mult, sgn[NF];
+  int crow, crow_end;
+  unsigned int pm[NF * NF / 4];
+  unsigned short w_dt[NF / 2], w_d[NF / 2], w_role[NF / 2];
+};
+
+template <int NF>
+__device__ __forceinline__ void load_cell(const mimpy_mesh_view& m, const UniArgs& a, long long cell,
+                                          bool k_unity, CellIn<NF>& in) {
+  const int2* p = reinterpret_cast<const int2*>(m.cell_faces + cell * NF);
+  const int2* q = reinterpret_cast<const int2*>(a.cell_rowstart + cell * NF);
+#pragma unroll
+  for (int i = 0; i < NF / 2; ++i) {
+    const int2 v = __ldg(p + i);
+    in.fid[2 * i] = v.x;
+    in.fid[2 * i + 1] = v.y;
+    const int2 w = __ldg(q + i);
+    in.rs[2 * i] = w.x;
+    in.rs[2 * i + 1] = w.y;
+  }
+  if (k_unity) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) in.K[t] = (t % 4 == 0) ? 1. : 0.;
+  } else {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) in.K[t] = __ldg(m.cell_k + cell * 9 + t);
+  }
+#pragma unroll
+  for (int t = 0; t < 3; ++t) in.xc[t] = __ldg(m.cell_centroid + cell * 3 + t);
+  in.vol = __ldg(m.cell_volume + cell);
+  in.mult = a.multipliers ? __ldg(a.multipliers + cell) : 1.;
+  in.crow = __ldg(a.indptr + a.flux_dof + cell);
+  in.crow_end = __ldg(a.indptr + a.flux_dof + cell + 1);
+  const unsigned int* pp = reinterpret_cast<const unsigned int*>(a.pos_m + cell * (NF * NF));
+#pragma unroll
+  for (int t = 0; t < NF * NF / 4; ++t) in.pm[t] = __ldg(pp + t);
+  const unsigned short* p0 = reinterpret_cast<const unsigned short*>(m.cell_sigma + cell * NF);
+  const unsigned short* p1 = reinterpret_cast<const unsigned short*>(a.pos_dt + cell * NF);
+  const unsigned short* p2 = reinterpret_cast<const unsigned short*>(a.pos_d + cell * NF);
+  const unsigned short* p3 = reinterpret_cast<const unsigned short*>(a.role + cell * NF);
+  unsigned short w_sg[NF / 2];
+#pragma unroll
+  for (int t = 0; t < NF / 2; ++t) {
+    w_sg[t] = __ldg(p0 + t);
+    in.w_dt[t] = __ldg(p1 + t);
+    in.w_d[t] = __ldg(p2 + t);
+    in.w_role[t] = __ldg(p3 + t);
+  }
+#pragma unroll
+  for (int i = 0; i < NF; ++i) in.sgn[i] = (double)(signed char)byte_of(w_sg, i);
+}
+
+template <int NF>
+__device__ __forceinline__ void load_records(const mimpy_mesh_view& m, const int (&fid)[NF],
+                                             double2 (&rec)[NF][4]) {
+#pragma unroll
+  for (int i = 0; i < NF; ++i) {
+    const double2* p = reinterpret_cast<const double2*>(m.face_geom + 8 * (size_t)fid[i]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) rec[i][q] = __ldg(p + q);
+  }
+}
+
+#define PM_POS(pm, e) (((pm)[(e) >> 2] >> (((e) & 3) * 8)) & 0xFFu)
+
+// ---------------------------------------------------------------------------------------------
+// direct: thread-per-cell, stores from registers
+// ---------------------------------------------------------------------------------------------
+#define AD_THREADS 128
+#ifndef AD_MINB
+#define AD_MINB 2  /* measured on B200: 2 -> 7.0 ms, 3 -> 7.5 ms, 4 -> 9.5 ms at 256^3 (spills) */
+#endif
+
+template <int NF, int METHOD>
+__global__ void __launch_bounds__(AD_THREADS, AD_MINB)
+k_numeric_direct(mimpy_mesh_view m, int flags, UniArgs a) {
+  __shared__ unsigned int s_ticket;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1u);
+  __syncthreads();
+  const long long cell = (long long)s_ticket * AD_THREADS + threadIdx.x;
+  if (cell >= m.nc) return;
+  CellIn<NF> in;
+  load_cell<NF>(m, a, cell, flags & 1, in);
+  double2 rec[NF][4];
+  load_records<NF>(m, in.fid, rec);
+  unsigned long long pub[NF];
+#pragma unroll
+  for (int i = 0; i < NF; ++i) {  // optimistic, non-blocking read of the published halves
+    pub[i] = 0ull;
+    if (byte_of(in.w_role, i) == 2 && in.rs[i] >= 0) {
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(a.diag_pub + in.fid[i]);
+      asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(pub[i]) : "l"(src));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NF; ++i) {  // DIV / -DIV^T                       mfd.py:232-243
+    const double sa = in.sgn[i] * rec[i][0].x;
+    if (in.rs[i] >= 0) {
+      a.vals[in.rs[i] + byte_of(in.w_dt, i)] = -sa;
+      a.vals[in.crow + byte_of(in.w_d, i)] = sa;
+    }
+  }
+  a.vals[in.crow_end - 1] = a.c_diag ? __ldg(a.c_diag + cell) : a.alpha * in.vol;  // mfd.py:766-772
+  double diag[NF];
+  cell_entries<NF, METHOD>(in.K, in.xc, in.vol, in.mult, rec, in.sgn, [&](int i, int j, double v) {
+    if (i == j) {
+      diag[i] = v;
+      // the lower-index cell of a shared face publishes its diagonal half as soon as it exists
+      if (in.rs[i] >= 0 && byte_of(in.w_role, i) == 1) a.diag_pub[in.fid[i]] = v;
+    } else {
+      const unsigned pos = PM_POS(in.pm, i * NF + j);
+      if (in.rs[i] >= 0 && pos != 0xFFu) a.vals[in.rs[i] + pos] = v;
+    }
+  });
+#pragma unroll
+  for (int i = 0; i < NF; ++i) {
+    const unsigned role = byte_of(in.w_role, i);
+    if (in.rs[i] < 0 || role == 1) continue;
+    double d = diag[i];
+    if (role == 2) d = wait_published(a.diag_pub + in.fid[i], pub[i], a.error_flag) + d;  // lower first
+    a.vals[in.rs[i] + PM_POS(in.pm, i * NF + i)] = d;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// brick: 8x4x4 cells per CTA, face rows assembled in shared memory, whole-row bursts
+// ---------------------------------------------------------------------------------------------
+#define BX 8
+#define BY 4
+#define BZ 4
+#define BR_THREADS (BX * BY * BZ)
+#define BR_NZF (BX * BY * (BZ + 1))
+#define BR_NYF (BX * (BY + 1) * BZ)
+#define BR_NXF ((BX + 1) * BY * BZ)
+#define BR_NFACE (BR_NZF + BR_NYF + BR_NXF)
+#define BR_RW 13  // 11 M entries of an interior row + 2 (-DIV^T); longer rows cannot occur on a hex mesh
+
+struct BrickSmem {
+  double row[BR_NFACE * BR_RW];
+  int rowstart[BR_NFACE];
+  unsigned int ticket;
+};
+
+template <int METHOD>
+__global__ void __launch_bounds__(BR_THREADS, 2)
+k_numeric_brick(mimpy_mesh_view m, int flags, UniArgs a) {
+  constexpr int NF = 6;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BrickSmem& s = *reinterpret_cast<BrickSmem*>(smem_raw);
+  const int t = threadIdx.x;
+  if (t == 0) s.ticket = atomicAdd(a.ticket, 1u);
+  // sentinel-fill the row buffer: a slot nobody in this brick writes is not stored
+  unsigned long long* rowbits = reinterpret_cast<unsigned long long*>(s.row);
+  for (int e = t; e < BR_NFACE * BR_RW; e += BR_THREADS) rowbits[e] = AU_SENTINEL;
+  for (int e = t; e < BR_NFACE; e += BR_THREADS) s.rowstart[e] = -1;
+  __syncthreads();
+  const int nbx = (m.hex_nx + BX - 1) / BX, nby = (m.hex_ny + BY - 1) / BY;
+  const int brick = (int)s.ticket;  // lexicographic: x fastest, z slowest
+  const int bi = brick % nbx, bj = (brick / nbx) % nby, bk = brick / (nbx * nby);
+  const int li = t % BX, lj = (t / BX) % BY, lk = t / (BX * BY);
+  const int ci = bi * BX + li, cj = bj * BY + lj, ck = bk * BZ + lk;
+  const bool ok = ci < m.hex_nx && cj < m.hex_ny && ck < m.hex_nz;
+  const long long cell = ci + (long long)m.hex_nx * (cj + (long long)m.hex_ny * ck);
+
+  // local face ids of the cell's faces [z-, y-, x-, x+, y+, z+]
+  int lf[NF];
+  lf[0] = (lk * BY + lj) * BX + li;
+  lf[5] = ((lk + 1) * BY + lj) * BX + li;
+  lf[1] = BR_NZF + (lk * (BY + 1) + lj) * BX + li;
+  lf[4] = BR_NZF + (lk * (BY + 1) + lj + 1) * BX + li;
+  lf[2] = BR_NZF + BR_NYF + (lk * BY + lj) * (BX + 1) + li;
+  lf[3] = BR_NZF + BR_NYF + (lk * BY + lj) * (BX + 1) + li + 1;
+  // is the other cell of face i inside this brick?  (it exists iff role != 0)
+  const bool in_brick[NF] = {lk > 0, lj > 0, li > 0, li < BX - 1, lj < BY - 1, lk < BZ - 1};
+
+  CellIn<NF> in;
+  double diag[NF];
+  if (ok) {
+    load_cell<NF>(m, a, cell, flags & 1, in);
+    double2 rec[NF][4];
+    load_records<NF>(m, in.fid, rec);
+    unsigned long long pub[NF];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {  // halves published by lower cells of OTHER bricks
+      pub[i] = 0ull;
+      if (byte_of(in.w_role, i) == 2 && in.rs[i] >= 0 && !in_brick[i]) {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(a.diag_pub + in.fid[i]);
+        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(pub[i]) : "l"(src));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+      const double sa = in.sgn[i] * rec[i][0].x;
+      if (in.rs[i] >= 0) {
+        s.rowstart[lf[i]] = in.rs[i];                             // both cells write the same value
+        s.row[lf[i] * BR_RW + byte_of(in.w_dt, i)] = -sa;         // -DIV^T   mfd.py:240-243
+        a.vals[in.crow + byte_of(in.w_d, i)] = sa;                // DIV      mfd.py:232-238
+      }
+    }
+    a.vals[in.crow_end - 1] = a.c_diag ? __ldg(a.c_diag + cell) : a.alpha * in.vol;
+    cell_entries<NF, METHOD>(in.K, in.xc, in.vol, in.mult, rec, in.sgn, [&](int i, int j, double v) {
+      if (i == j) {
+        diag[i] = v;
+      } else {
+        const unsigned pos = PM_POS(in.pm, i * NF + j);
+        if (in.rs[i] >= 0 && pos != 0xFFu) s.row[lf[i] * BR_RW + pos] = v;
+      }
+    });
+    // diagonals, step 1: single-cell faces and the LOWER cell of shared faces.  Publish first
+    // (faces x+, y+, z+), wait afterwards (faces z-, y-, x-): a brick never delays its successors
+    // by its own waiting.
+#pragma unroll
+    for (int ii = 0; ii < NF; ++ii) {
+      const int i = (ii + 3) % NF;  // 3, 4, 5, 0, 1, 2
+      if (in.rs[i] < 0) continue;
+      const unsigned role = byte_of(in.w_role, i);
+      const int slot = lf[i] * BR_RW + PM_POS(in.pm, i * NF + i);
+      if (role == 0) s.row[slot] = diag[i];
+      if (role == 1) {
+        if (in_brick[i]) s.row[slot] = diag[i];           // finished in shared memory by the upper cell
+        else a.diag_pub[in.fid[i]] = diag[i];              // the upper cell lives in a later brick
+      }
+      if (role == 2 && !in_brick[i])                       // lower cell lives in an earlier brick
+        s.row[slot] = wait_published(a.diag_pub + in.fid[i], pub[i < 3 ? i : 0], a.error_flag) + diag[i];
+    }
+  }
+  __syncthreads();
+  // diagonals, step 2: the UPPER cell adds its half (lower + upper, fixed order)
+  if (ok) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (in.rs[i] >= 0 && byte_of(in.w_role, i) == 2 && in_brick[i]) {
+        const int slot = lf[i] * BR_RW + PM_POS(in.pm, i * NF + i);
+        s.row[slot] = s.row[slot] + diag[i];
+      }
+    }
+  }
+  __syncthreads();
+  // stream the rows out: 8 rows x 13 slots per pass (104 of the 128 threads), thread = fixed slot
+  // of a fixed row-in-pass, so that no index arithmetic is left in the loop; consecutive lanes hold
+  // consecutive slots of a row
+  if (t < 8 * BR_RW) {
+    const int r0 = t / BR_RW, pos = t - r0 * BR_RW;
+#pragma unroll 8
+    for (int r = r0; r < BR_NFACE; r += 8) {
+      const unsigned long long bits = rowbits[r * BR_RW + pos];
+      if (bits != AU_SENTINEL) a.vals[s.rowstart[r] + pos] = __longlong_as_double((long long)bits);
+    }
+  }
+}
+
+// 0 direct, 1 brick (default where the mesh is a structured hex mesh)
 static int asm_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MIMPY_B200_ASM_VARIANT");
-    v = (e && e[0] == 's') ? 1 : 0;  // "staged" selects the shared-memory variant, default direct
+    v = (e && e[0] == 'd') ? 0 : 1;
   }
   return v;
 }
 
-template <int NF, int METHOD>
+template <int METHOD>
 static int launch_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int flags, const UniArgs& a) {
-  if (asm_variant() == 0) {
+  const bool structured = mesh->hex_nx > 0 && mesh->hex_ny > 0 && mesh->hex_nz > 0 &&
+                          (long long)mesh->hex_nx * mesh->hex_ny * mesh->hex_nz == mesh->nc;
+  if (structured && asm_variant() == 1 && !(flags & MIMPY_FLAG_DIRECT_KERNEL)) {
+    const size_t smem = sizeof(BrickSmem);
+    static bool configured = false;
+    if (!configured) {
+      CUDA_TRY(cudaFuncSetAttribute(k_numeric_brick<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    const long long bricks = (long long)((mesh->hex_nx + BX - 1) / BX) * ((mesh->hex_ny + BY - 1) / BY) *
+                             ((mesh->hex_nz + BZ - 1) / BZ);
+    k_numeric_brick<METHOD><<<(unsigned)bricks, BR_THREADS, smem, ctx->stream>>>(*mesh, flags, a);
+  } else {
     const int blocks = (mesh->nc + AD_THREADS - 1) / AD_THREADS;
-    k_numeric_direct<NF, METHOD><<<blocks, AD_THREADS, 0, ctx->stream>>>(*mesh, flags, a);
-    KERNEL_CHECK();
-    return MIMPY_OK;
+    k_numeric_direct<6, METHOD><<<blocks, AD_THREADS, 0, ctx->stream>>>(*mesh, flags, a);
   }
-  const size_t smem = sizeof(UniSmem<NF>);
-  static bool configured = false;
-  if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(k_numeric_uniform<NF, METHOD>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
-  const int blocks = (mesh->nc + AU_CELLS - 1) / AU_CELLS;
-  k_numeric_uniform<NF, METHOD><<<blocks, AU_CELLS, smem, ctx->stream>>>(*mesh, flags, a);
   KERNEL_CHECK();
   return MIMPY_OK;
 }
@@ -574,7 +461,6 @@ int mimpy_numeric_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mim
   CUDA_TRY(cudaMemsetAsync(scratch, 0xFF, sizeof(double) * (size_t)mesh->nf, ctx->stream));
   CUDA_TRY(cudaMemsetAsync(ctx->counters + 8, 0, 2 * sizeof(unsigned int), ctx->stream));
   UniArgs a;
-  a.face_to_flux = sym->face_to_flux;
   a.indptr = sym->indptr;
   a.pos_m = sym->pos_m;
   a.pos_dt = sym->pos_dt;
@@ -589,7 +475,7 @@ int mimpy_numeric_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mim
   a.ticket = ctx->counters + 8;
   a.error_flag = ctx->counters + 9;
   a.flux_dof = sym->flux_dof;
-  if (method == 0) return launch_uniform<6, 0>(ctx, mesh, flags, a);
-  if (method == 1) return launch_uniform<6, 1>(ctx, mesh, flags, a);
-  return launch_uniform<6, 6>(ctx, mesh, flags, a);
+  if (method == 0) return launch_uniform<0>(ctx, mesh, flags, a);
+  if (method == 1) return launch_uniform<1>(ctx, mesh, flags, a);
+  return launch_uniform<6>(ctx, mesh, flags, a);
 }

@@ -24,8 +24,11 @@ struct CellSmem {
   double d[G];      // per-row coefficient (method 6) / scratch
   double sg[G];     // orientation as double
   int row[G];       // CSR row start of flux row g(f_i), -1 when dropped
-  double w[G][G + 1];  // method 4: W_E, inverted in place
 };
+
+// method 4 only: W_E per cell (G x (G+1) doubles), inverted in place -- dynamic shared memory so
+// that the other methods keep their occupancy
+extern __shared__ __align__(16) unsigned char lm_dyn_smem[];
 
 struct ScatterArgs {
   const int* face_to_flux;
@@ -222,6 +225,7 @@ k_local_matrices(mimpy_mesh_view m, int method, int flags, const int* __restrict
   int nw = n;
 #pragma unroll
   for (int o = 16; o >= G; o >>= 1) nw = max(nw, __shfl_xor_sync(0xffffffffu, nw, o));
+  double (*wbuf)[G + 1] = reinterpret_cast<double (*)[G + 1]>(lm_dyn_smem) + (size_t)slot * G;
   if (method == 4) {
     // W_E = (N (N^T R)^-1 N^T + D D^T) tr(K)/|E| ;  M_E = W_E^-1          mfd.py:349-353, 421
     double z[3];  // (N^T R)^-1 N_j = T^-T N_j
@@ -232,17 +236,17 @@ k_local_matrices(mimpy_mesh_view m, int method, int flags, const int* __restrict
       if (valid) {
         const double w1 = s.n[i][0] * z[0] + s.n[i][1] * z[1] + s.n[i][2] * z[2];
         const double ddt = ((i == j) ? 1. : 0.) - (s.q[i][0] * q[0] + s.q[i][1] * q[1] + s.q[i][2] * q[2]);
-        s.w[i][j] = (w1 + ddt) * scale;
+        wbuf[i][j] = (w1 + ddt) * scale;
       }
     }
     __syncwarp();
-    group_invert<G>(s.w, n, j, nw);
+    group_invert<G>(wbuf, n, j, nw);
   }
   for (int i = 0; i < nw; ++i) {
     const bool row_ok = i < n;
     double v;
     if (method == 4) {
-      v = (row_ok && valid) ? s.w[i][j] : 0.;
+      v = (row_ok && valid) ? wbuf[i][j] : 0.;
     } else if (method == 5 || method == 7) {
       v = (i == j) ? s.d[i] : 0.;
     } else {
@@ -439,9 +443,10 @@ int mimpy_b200_mfd_local_matrices(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, i
   const int cpb = 128 / G;
   const int blocks = (mesh->nc + cpb - 1) / cpb;
   ScatterArgs sc = {};
+  const size_t dyn = (method == 4) ? sizeof(double) * (size_t)cpb * G * (G + 1) : 0;
 #define LAUNCH(GG)                                                                     \
-  k_local_matrices<GG, false><<<blocks, 128, 0, ctx->stream>>>(*mesh, method, flags, m_ptr, m_e, \
-                                                               diagonality, consistency, sc)
+  k_local_matrices<GG, false><<<blocks, 128, dyn, ctx->stream>>>(*mesh, method, flags, m_ptr, m_e, \
+                                                                 diagonality, consistency, sc)
   if (G == 8) LAUNCH(8);
   else if (G == 16) LAUNCH(16);
   else LAUNCH(32);
@@ -473,9 +478,10 @@ int mimpy_b200_mfd_numeric(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mi
   const int cpb = 128 / G;
   const int blocks = (mesh->nc + cpb - 1) / cpb;
   ScatterArgs sc = make_scatter(sym, multipliers, alpha, c_diag, vals);
-#define LAUNCH(GG)                                                                              \
-  k_local_matrices<GG, true><<<blocks, 128, 0, ctx->stream>>>(*mesh, method, flags, sym->m_ptr, \
-                                                              m_e_out, nullptr, nullptr, sc)
+  const size_t dyn = (method == 4) ? sizeof(double) * (size_t)cpb * G * (G + 1) : 0;
+#define LAUNCH(GG)                                                                                \
+  k_local_matrices<GG, true><<<blocks, 128, dyn, ctx->stream>>>(*mesh, method, flags, sym->m_ptr, \
+                                                                m_e_out, nullptr, nullptr, sc)
   if (G == 8) LAUNCH(8);
   else if (G == 16) LAUNCH(16);
   else LAUNCH(32);

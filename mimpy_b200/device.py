@@ -50,6 +50,7 @@ class DeviceMesh(object):
         v = MeshView()
         v.nc, v.nf = self.nc, self.nf
         v.max_faces, v.uniform_faces = self.max_faces, self.uniform_faces
+        v.hex_nx, v.hex_ny, v.hex_nz = getattr(self, "hex_dims", (0, 0, 0))
         v.cell_ptr = self.cell_ptr.data_ptr()
         v.cell_faces = self.cell_faces.data_ptr()
         v.cell_sigma = self.cell_sigma.data_ptr()
@@ -72,6 +73,7 @@ class DeviceMesh(object):
             nf = cz * L + cx * cy
             npnt = (cx + 1) * (cy + 1) * (cz + 1)
             m.nc, m.nf, m.max_faces, m.uniform_faces = nc, nf, 6, 6
+            m.hex_dims = (cx, cy, cz)
             # hexmesh.py:295-297
             dx = dim_x / float(cx + 1 - 1.)
             dy = dim_y / float(cy + 1 - 1.)

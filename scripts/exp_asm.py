@@ -22,10 +22,6 @@ def timeit(label, **kw):
             e0.record(ctx.stream); device.numeric(dm, plan, 1, vals=vals, **kw); e1.record(ctx.stream)
         ctx.sync(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     print("%-40s %.3f ms  (%.0f Mcells/s, %.1f%% of 6546.6 GB/s algorithmic)" % (label, min(ts), nc / min(ts) / 1e3, 700. * nc / min(ts) / 1e6 / 6546.6 * 100))
-timeit("full")
-timeit("no M stores", debug_flags=256)
-timeit("no gathers (records from L1/L2)", debug_flags=512)
-timeit("no diag wait", debug_flags=1024)
-timeit("no M stores + no gathers", debug_flags=256 | 512)
-timeit("no M stores + no gathers + no wait", debug_flags=256 | 512 | 1024)
+timeit("brick (default)")
+timeit("direct", debug_flags=4)
 timeit("generic warp-group kernel", generic_kernel=True)

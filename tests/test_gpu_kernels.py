@@ -323,6 +323,9 @@ def test_uniform_fast_path_equals_generic_kernel(ctx, method):
     a = H(ctx, device.numeric(d, plan, method, multipliers=mult, c_diag=cd))
     a2 = H(ctx, device.numeric(d, plan, method, multipliers=mult, c_diag=cd))
     b = H(ctx, device.numeric(d, plan, method, multipliers=mult, c_diag=cd, generic_kernel=True))
+    # brick-tiled (default on structured hexes) and direct-store kernels: same core arithmetic
+    a3 = H(ctx, device.numeric(d, plan, method, multipliers=mult, c_diag=cd, debug_flags=4))
+    assert np.array_equal(a, a3)
     assert np.array_equal(a, a2)
     assert not np.isnan(a).any()
     scale = abs(b).max()
