@@ -46,7 +46,7 @@ struct ScatterArgs {
 };
 
 template <int G, bool SCATTER>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)  // <= 128 registers: 4 CTAs per SM
 k_local_matrices(mimpy_mesh_view m, int method, int flags, const int* __restrict__ m_ptr,
                  double* __restrict__ m_e, double* __restrict__ diagonality,
                  double* __restrict__ consistency, ScatterArgs sc) {
