@@ -186,9 +186,14 @@ def run_cuda(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = _lib.Context(local_rank)
     dev = ctx.device
+    n = args.n
+    comm = "single"
     if world > 1:
         partition.init_nccl(ctx, rank, world)
-    n = args.n
+        comm = "nccl"
+        if os.environ.get("MIMPY_B200_COMM", "peer") != "nccl":
+            partition.init_peer(ctx, rank, world, n * n)  # NVLink peer-memory halo + all-reduce
+            comm = "nvlink-peer"
     peak, peak_src = measured_peak()
 
     t_setup = time.perf_counter()
@@ -315,7 +320,7 @@ def run_cuda(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C3: %d^3 hex, log-normal diag K (seed 256), method 1, Dirichlet x-/x+, no-flow else" % n,
                        "cells": nc_total, "face_rows": int(rows_total), "face_system_nnz": int(nnz_total),
-                       "partition": "z-slabs x%d" % world,
+                       "partition": "z-slabs x%d" % world, "pcg_collectives": comm,
                        "l2": "inputs larger than L2 (>= %.1f GB touched per step per GPU)" % (ASM_BYTES_PER_CELL * nc_total / world / 1e9),
                        "pcg": {"preconditioner": "jacobi", "rtol": args.rtol, "check_every": args.check_every}},
             "assembly_ms": asm_ms, "hybrid_setup_ms": float(np.mean([r["setup_ms"] for r in res])),

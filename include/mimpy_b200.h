@@ -344,6 +344,15 @@ int mimpy_b200_set_halo(mimpy_ctx* ctx, int32_t n_owned, int32_t n_lo, const int
                         int32_t rank_lo, int32_t n_hi, const int32_t* idx_hi, int32_t rank_hi,
                         double* buf);
 int mimpy_b200_halo_exchange_add(mimpy_ctx* ctx, double* v);
+/* NVLink peer-memory path for the same two collectives (latency, not bandwidth, is what they
+ * cost): peer_alloc creates this rank's symmetric buffer (halo_cap_doubles >= nx*ny) and returns
+ * its 64-byte cudaIpc handle; the caller all-gathers the handles of the `world` (<= 8) ranks of
+ * the node and calls peer_attach.  From then on halo_exchange_add / allreduce_sum / pcg push their
+ * data straight into the peers' buffers (st.global over NVLink + system fence + epoch flag)
+ * instead of calling NCCL.  peer_disable switches back to NCCL. */
+int mimpy_b200_peer_alloc(mimpy_ctx* ctx, int64_t halo_cap_doubles, void* handle64_host);
+int mimpy_b200_peer_attach(mimpy_ctx* ctx, int32_t rank, int32_t world, const void* handles_host);
+int mimpy_b200_peer_disable(mimpy_ctx* ctx);
 int mimpy_b200_allreduce_sum(mimpy_ctx* ctx, double* buf, int32_t count);
 
 #ifdef __cplusplus

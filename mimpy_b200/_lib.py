@@ -86,6 +86,9 @@ SIGNATURES = {
     "mimpy_b200_nccl_init": [_vp, _vp, _i32, _i32],
     "mimpy_b200_set_halo": [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp],
     "mimpy_b200_halo_exchange_add": [_vp, _vp],
+    "mimpy_b200_peer_alloc": [_vp, _i64, _vp],
+    "mimpy_b200_peer_attach": [_vp, _i32, _i32, _vp],
+    "mimpy_b200_peer_disable": [_vp],
     "mimpy_b200_allreduce_sum": [_vp, _vp, _i32],
 }
 

@@ -65,9 +65,143 @@ static int nccl_load(const char* path) {
     }                                                                               \
   } while (0)
 
+// ---------------------------------------------------------------------------------------------
+// NVLink peer-memory path.  The two collectives of a PCG iteration move a few bytes (3 doubles)
+// and 512 KiB (one face layer): what they cost is LATENCY.  Every rank owns one symmetric buffer
+// (cudaMalloc + cudaIpc handles); a rank PUSHES its contribution straight into its peers' buffers
+// over NVLink (st.global on the mapped peer pointer), fences (system scope) and raises an epoch
+// flag there; the receiver spins on its LOCAL copy of the flag.  Buffers are double-buffered by
+// epoch parity: a rank can run at most one exchange ahead of its partner (it needs the partner's
+// push to finish the current one), so parity e&1 is never overwritten while still being read.
+// All waits are bounded and raise ctx error flag 1 instead of hanging.
+//   layout of the symmetric buffer:  [0, 1024)    reduce slots  [parity][rank] x 32 B (3 doubles + epoch)
+//                                    [1024, 2048) halo flags    [dir][parity] x u64
+//                                    [4096, ...)  halo data     [dir][parity][cap] doubles
+// dir 0 = data arriving from the LOWER neighbour, dir 1 = from the UPPER neighbour.
+// ---------------------------------------------------------------------------------------------
+#define PEER_RED_OFF 0
+#define PEER_FLAG_OFF 1024
+#define PEER_DATA_OFF 4096
+#define PEER_SPIN_MAX (1u << 24)
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// one warp; lane r talks to rank r.  Sum in rank order => identical bits on every rank.
+__global__ void k_peer_allreduce(mimpy_peer pr, double* buf, int count, unsigned int* error_flag) {
+  const int r = threadIdx.x;
+  const unsigned long long e = pr.epoch[0] + 1;
+  const int par = (int)(e & 1);
+  double mine[3] = {0., 0., 0.};
+  for (int k = 0; k < count; ++k) mine[k] = buf[k];
+  double got[3] = {0., 0., 0.};
+  if (r < pr.world) {
+    char* dst = pr.peers[r] + PEER_RED_OFF + ((par * 8 + pr.rank) * 32);
+    for (int k = 0; k < count; ++k)
+      st_volatile_u64(reinterpret_cast<unsigned long long*>(dst) + k, (unsigned long long)__double_as_longlong(mine[k]));
+    __threadfence_system();
+    st_volatile_u64(reinterpret_cast<unsigned long long*>(dst) + 3, e);
+    const char* src = pr.local + PEER_RED_OFF + ((par * 8 + r) * 32);
+    unsigned int spins = 0;
+    while (ld_volatile_u64(reinterpret_cast<const unsigned long long*>(src) + 3) != e && ++spins < PEER_SPIN_MAX) {
+    }
+    if (spins >= PEER_SPIN_MAX) atomicExch(error_flag, 1u);
+    __threadfence_system();
+    for (int k = 0; k < count; ++k)
+      got[k] = __longlong_as_double((long long)ld_volatile_u64(reinterpret_cast<const unsigned long long*>(src) + k));
+  }
+  for (int k = 0; k < count; ++k) {
+    double tot = 0.;
+    for (int q = 0; q < pr.world; ++q) tot += __shfl_sync(0xffffffffu, got[k], q);
+    if (r == 0) buf[k] = tot;
+  }
+  if (r == 0) pr.epoch[0] = e;
+}
+
+// pack the two interface layers and push them into the neighbours' buffers
+__global__ void k_peer_halo_push(mimpy_peer pr, mimpy_halo h, const double* __restrict__ v, unsigned int* counter) {
+  const unsigned long long e = pr.epoch[1] + 1;
+  const int par = (int)(e & 1);
+  const size_t cap = pr.halo_cap;
+  const int total = h.n_lo + h.n_hi;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    if (i < h.n_lo) {  // to the lower neighbour: arrives there as "from the UPPER neighbour" (dir 1)
+      double* dst = reinterpret_cast<double*>(pr.peers[h.rank_lo] + PEER_DATA_OFF) + (size_t)(1 * 2 + par) * cap;
+      dst[i] = v[h.idx_lo[i]];
+    } else {           // to the upper neighbour: dir 0 there
+      const int k = i - h.n_lo;
+      double* dst = reinterpret_cast<double*>(pr.peers[h.rank_hi] + PEER_DATA_OFF) + (size_t)(0 * 2 + par) * cap;
+      dst[k] = v[h.idx_hi[k]];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(counter, 1u);
+    if (done == gridDim.x - 1) {  // every block's stores are fenced: raise the flags
+      __threadfence_system();
+      if (h.n_lo)
+        st_volatile_u64(reinterpret_cast<unsigned long long*>(pr.peers[h.rank_lo] + PEER_FLAG_OFF) + (1 * 2 + par), e);
+      if (h.n_hi)
+        st_volatile_u64(reinterpret_cast<unsigned long long*>(pr.peers[h.rank_hi] + PEER_FLAG_OFF) + (0 * 2 + par), e);
+      *counter = 0u;
+    }
+  }
+}
+
+__global__ void k_peer_halo_add(mimpy_peer pr, mimpy_halo h, double* __restrict__ v, unsigned int* counter,
+                                unsigned int* error_flag) {
+  const unsigned long long e = pr.epoch[1] + 1;
+  const int par = (int)(e & 1);
+  const size_t cap = pr.halo_cap;
+  if (threadIdx.x == 0) {
+    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(pr.local + PEER_FLAG_OFF);
+    unsigned int spins = 0;
+    if (h.n_lo)
+      while (ld_volatile_u64(flags + (0 * 2 + par)) != e && ++spins < PEER_SPIN_MAX) {
+      }
+    if (h.n_hi)
+      while (ld_volatile_u64(flags + (1 * 2 + par)) != e && ++spins < PEER_SPIN_MAX) {
+      }
+    if (spins >= PEER_SPIN_MAX) atomicExch(error_flag, 1u);
+    __threadfence_system();
+  }
+  __syncthreads();
+  const double* from_lo = reinterpret_cast<const double*>(pr.local + PEER_DATA_OFF) + (size_t)(0 * 2 + par) * cap;
+  const double* from_hi = reinterpret_cast<const double*>(pr.local + PEER_DATA_OFF) + (size_t)(1 * 2 + par) * cap;
+  const int total = h.n_lo + h.n_hi;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    if (i < h.n_lo) {
+      v[h.idx_lo[i]] += __longlong_as_double((long long)ld_volatile_u64(reinterpret_cast<const unsigned long long*>(from_lo) + i));
+    } else {
+      const int k = i - h.n_lo;
+      v[h.idx_hi[k]] += __longlong_as_double((long long)ld_volatile_u64(reinterpret_cast<const unsigned long long*>(from_hi) + k));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(counter, 1u);
+    if (done == gridDim.x - 1) {
+      pr.epoch[1] = e;
+      *counter = 0u;
+    }
+  }
+}
+
 // in-stream sum of `count` doubles over all ranks (no-op for a single rank)
 int mimpy_allreduce_f64(mimpy_ctx* ctx, double* buf, int count) {
   if (ctx->world <= 1) return MIMPY_OK;
+  if (ctx->peer.enabled && count <= 3) {
+    k_peer_allreduce<<<1, 32, 0, ctx->stream>>>(ctx->peer, buf, count, ctx->counters + 9);
+    KERNEL_CHECK();
+    return MIMPY_OK;
+  }
   if (!ctx->nccl_comm || !g_nccl.handle) {
     mimpy_set_error("world size %d but no NCCL communicator attached", ctx->world);
     return MIMPY_E_NCCL;
@@ -93,6 +227,14 @@ int mimpy_halo_exchange_add(mimpy_ctx* ctx, double* v) {
   const mimpy_halo& h = ctx->halo;
   if (ctx->world <= 1 || (h.n_lo == 0 && h.n_hi == 0)) return MIMPY_OK;
   cudaStream_t st = ctx->stream;
+  if (ctx->peer.enabled && (size_t)h.n_lo <= ctx->peer.halo_cap && (size_t)h.n_hi <= ctx->peer.halo_cap) {
+    const int total = h.n_lo + h.n_hi;
+    const int blocks = min((total + 255) / 256, 2 * ctx->sm_count);
+    k_peer_halo_push<<<blocks, 256, 0, st>>>(ctx->peer, h, v, ctx->counters + 10);
+    k_peer_halo_add<<<blocks, 256, 0, st>>>(ctx->peer, h, v, ctx->counters + 11, ctx->counters + 9);
+    KERNEL_CHECK();
+    return MIMPY_OK;
+  }
   double* send_lo = h.buf;
   double* recv_lo = h.buf + h.n_lo;
   double* send_hi = h.buf + 2 * (size_t)h.n_lo;
@@ -161,6 +303,62 @@ int mimpy_b200_set_halo(mimpy_ctx* ctx, int32_t n_owned, int32_t n_lo, const int
   ctx->halo.idx_hi = idx_hi;
   ctx->halo.rank_hi = rank_hi;
   ctx->halo.buf = buf;
+  return MIMPY_OK;
+}
+
+// NVLink peer-memory set-up: every rank allocates its symmetric buffer and exports a cudaIpc
+// handle (64 bytes); the caller all-gathers the handles (e.g. torch.distributed) and attaches.
+int mimpy_b200_peer_alloc(mimpy_ctx* ctx, int64_t halo_cap_doubles, void* handle64_host) {
+  REQUIRE(ctx && handle64_host && halo_cap_doubles >= 0, "bad argument");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const size_t bytes = PEER_DATA_OFF + sizeof(double) * 4 * (size_t)halo_cap_doubles;
+  char* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, bytes));
+  CUDA_TRY(cudaMemset(p, 0, bytes));
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, p));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64_host, &h, 64);
+  ctx->peer.local = p;
+  ctx->peer.halo_cap = (size_t)halo_cap_doubles;
+  return MIMPY_OK;
+}
+
+int mimpy_b200_peer_attach(mimpy_ctx* ctx, int32_t rank, int32_t world, const void* handles_host) {
+  REQUIRE(ctx && handles_host && ctx->peer.local, "peer_alloc must be called first");
+  REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "peer path supports up to 8 ranks of one node");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  char* ptrs[8] = {nullptr};
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      ptrs[r] = ctx->peer.local;
+    } else {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const char*)handles_host + 64 * r, 64);
+      void* q = nullptr;
+      CUDA_TRY(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+      ptrs[r] = (char*)q;
+    }
+  }
+  char** dev_ptrs = nullptr;
+  CUDA_TRY(cudaMalloc(&dev_ptrs, sizeof(char*) * 8));
+  CUDA_TRY(cudaMemcpy(dev_ptrs, ptrs, sizeof(char*) * 8, cudaMemcpyHostToDevice));
+  unsigned long long* epoch = nullptr;
+  CUDA_TRY(cudaMalloc(&epoch, sizeof(unsigned long long) * 2));
+  CUDA_TRY(cudaMemset(epoch, 0, sizeof(unsigned long long) * 2));
+  ctx->peer.peers = dev_ptrs;
+  ctx->peer.epoch = epoch;
+  ctx->peer.rank = rank;
+  ctx->peer.world = world;
+  ctx->peer.enabled = 1;
+  ctx->rank = rank;
+  ctx->world = world;
+  return MIMPY_OK;
+}
+
+int mimpy_b200_peer_disable(mimpy_ctx* ctx) {
+  REQUIRE(ctx, "ctx is NULL");
+  ctx->peer.enabled = 0;
   return MIMPY_OK;
 }
 

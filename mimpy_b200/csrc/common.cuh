@@ -18,8 +18,18 @@ struct mimpy_halo {
   double* buf;          // 2*(n_lo + n_hi) doubles
 };
 
+// NVLink peer-memory state (comm.cu): this rank's symmetric buffer and its peers' mapped copies
+struct mimpy_peer {
+  int enabled, rank, world;
+  char* local;
+  char** peers;                 // device array of `world` pointers (peers[rank] == local)
+  unsigned long long* epoch;    // device: [0] all-reduce epoch, [1] halo epoch
+  size_t halo_cap;              // doubles per halo buffer
+};
+
 struct mimpy_ctx {
   mimpy_halo halo;
+  mimpy_peer peer;
   int device;
   cudaStream_t stream;
   int sm_count;

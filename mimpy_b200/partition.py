@@ -130,6 +130,27 @@ def init_nccl(ctx, rank, world):
     ctx.rank, ctx.world = rank, world
 
 
+def init_peer(ctx, rank, world, halo_cap):
+    """NVLink peer-memory path for the halo exchange and the scalar all-reduces (comm.cu): every
+    rank allocates a symmetric buffer, the 64-byte cudaIpc handles are all-gathered over
+    torch.distributed, every rank maps its peers' buffers.  halo_cap: doubles per interface layer."""
+    import torch
+    import torch.distributed as dist
+
+    handle = (C.c_uint8 * 64)()
+    ctx.call("mimpy_b200_peer_alloc", int(halo_cap), C.cast(handle, C.c_void_p))
+    mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8)
+    on_dev = dist.get_backend() == "nccl"
+    if on_dev:
+        mine = mine.to(ctx.device)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    flat = torch.cat(parts).cpu().tolist()
+    buf = (C.c_uint8 * (64 * world))(*flat)
+    ctx.call("mimpy_b200_peer_attach", rank, world, C.cast(buf, C.c_void_p))
+    dist.barrier()
+
+
 def attach_halo(ctx, slab, plan):
     """Uploads the exchange lists of `slab` for the symbolic plan `plan` and registers them."""
     import torch

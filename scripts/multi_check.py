@@ -15,6 +15,9 @@ torch.cuda.set_device(local_rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 ctx = _lib.Context(local_rank)
 partition.init_nccl(ctx, rank, world)
+comm = os.environ.get("MIMPY_B200_COMM", "peer")
+if comm != "nccl":
+    partition.init_peer(ctx, rank, world, n * n)
 pb = bench.build_problem(ctx, n, rank, world)
 dm, plan, rhs = pb["dm"], pb["plan"], pb["rhs"]
 m_e, _, _ = device.local_matrices(dm, plan, 1)
@@ -39,7 +42,7 @@ if rank == 0:
     s1, i1 = device.HybridSystem(pb1["dm"], pb1["plan"], m1).solve(pb1["rhs"], rtol=1e-13, maxit=20000, check_every=25)
     p1 = device.to_host(ctx1, s1[pb1["plan"].flux_dof:])
     err = np.linalg.norm(p_multi - p1) / np.linalg.norm(p1)
-    print("MULTI_CHECK world=%d n=%d iters multi=%d single=%d rel_l2=%.3e" % (world, n, info.iterations, i1.iterations, err))
+    print("MULTI_CHECK comm=%s world=%d n=%d iters multi=%d single=%d rel_l2=%.3e" % (comm, world, n, info.iterations, i1.iterations, err))
     ok = err < 1e-8
 dist.barrier()
 dist.destroy_process_group()
