@@ -62,14 +62,17 @@ __device__ __forceinline__ Chol3 chol3r(double g00, double g10, double g11, doub
   return c;
 }
 
-// rec[i] = the packed face record [a, n, x_f, 0]; sgn[i] = orientation.  Calls sink(i, j, v) with
-// v = mult * s_i s_j M_E[i,j] for all NF^2 entries, row by row.
-template <int NF, int METHOD, class Sink>
-__device__ __forceinline__ void cell_entries(const double (&K)[9], const double (&xc)[3], double vol,
-                                             double mult, const double2 (&rec)[NF][4],
-                                             const double (&sgn)[NF], Sink&& sink) {
-  double rt[NF][3], kn[NF][3];
-  double dcoef[NF];
+// Per-cell operands: R~_i = s_i a_i (x_f - x_E), KN_i = K n_f, d_f of method 6.
+template <int NF>
+struct CellOps {
+  double rt[NF][3], kn[NF][3], dcoef[NF];
+};
+
+// rec[i] = the packed face record [a, n, x_f, 0]; sgn[i] = orientation.
+template <int NF, int METHOD>
+__device__ __forceinline__ void cell_prep(const double (&K)[9], const double (&xc)[3],
+                                          const double2 (&rec)[NF][4], const double (&sgn)[NF],
+                                          CellOps<NF>& o) {
   double Ki[9];
   if (METHOD == 6) inv3(K, Ki);
 #pragma unroll
@@ -78,19 +81,28 @@ __device__ __forceinline__ void cell_entries(const double (&K)[9], const double 
     const double nx = rec[i][0].y, ny = rec[i][1].x, nz = rec[i][1].y;
     const double dx = rec[i][2].x - xc[0], dy = rec[i][2].y - xc[1], dz = rec[i][3].x - xc[2];
     const double sa = sgn[i] * area;
-    rt[i][0] = sa * dx;
-    rt[i][1] = sa * dy;
-    rt[i][2] = sa * dz;
-    kn[i][0] = K[0] * nx + K[1] * ny + K[2] * nz;
-    kn[i][1] = K[3] * nx + K[4] * ny + K[5] * nz;
-    kn[i][2] = K[6] * nx + K[7] * ny + K[8] * nz;
+    o.rt[i][0] = sa * dx;
+    o.rt[i][1] = sa * dy;
+    o.rt[i][2] = sa * dz;
+    o.kn[i][0] = K[0] * nx + K[1] * ny + K[2] * nz;
+    o.kn[i][1] = K[3] * nx + K[4] * ny + K[5] * nz;
+    o.kn[i][2] = K[6] * nx + K[7] * ny + K[8] * nz;
     if (METHOD == 6) {  // d_f = n^T K^-1 n a_f |x_f - x_E|            mfd.py:446-453
       const double e = nx * (Ki[0] * nx + Ki[1] * ny + Ki[2] * nz) +
                        ny * (Ki[3] * nx + Ki[4] * ny + Ki[5] * nz) +
                        nz * (Ki[6] * nx + Ki[7] * ny + Ki[8] * nz);
-      dcoef[i] = e * area * sqrt(dx * dx + dy * dy + dz * dz);
+      o.dcoef[i] = e * area * sqrt(dx * dx + dy * dy + dz * dz);
     }
   }
+}
+
+// Calls sink(i, j, v) with v = mult * s_i s_j M_E[i,j] for all NF^2 entries, row by row.
+// trk = trace(K) (method 1 only).
+template <int NF, int METHOD, class Sink>
+__device__ __forceinline__ void cell_core(CellOps<NF>& o, double trk, double vol, double mult,
+                                          Sink&& sink) {
+  double (&rt)[NF][3] = o.rt;
+  double (&kn)[NF][3] = o.kn;
   double T[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   double g00 = 0, g10 = 0, g11 = 0, g20 = 0, g21 = 0, g22 = 0;
   double rr0 = 0, rr1 = 0, rr2 = 0;
@@ -109,7 +121,7 @@ __device__ __forceinline__ void cell_entries(const double (&K)[9], const double 
   inv3(T, Ti);
   double u = 0.;
   if (METHOD == 0) u = rr0 * Ti[0] + rr1 * Ti[3] + rr2 * Ti[6];      // mfd.py:380-382
-  if (METHOD == 1) u = vol / (K[0] + K[4] + K[8]);                    // mfd.py:387
+  if (METHOD == 1) u = vol / trk;                                     // mfd.py:387
   u *= mult;
   {
     const Chol3 c1 = chol3r(g00, g10, g11, g20, g21, g22);
@@ -131,7 +143,7 @@ __device__ __forceinline__ void cell_entries(const double (&K)[9], const double 
 #pragma unroll
     for (int q = 0; q < 3; ++q)
       z[q] = mult * (Ti[q] * rt[i][0] + Ti[3 + q] * rt[i][1] + Ti[6 + q] * rt[i][2]);
-    const double coef = (METHOD == 6) ? mult * dcoef[i] : u;
+    const double coef = (METHOD == 6) ? mult * o.dcoef[i] : u;
 #pragma unroll
     for (int j = 0; j < NF; ++j) {
       const double m0 = z[0] * rt[j][0] + z[1] * rt[j][1] + z[2] * rt[j][2];
@@ -139,6 +151,15 @@ __device__ __forceinline__ void cell_entries(const double (&K)[9], const double 
       sink(i, j, m0 + coef * (((i == j) ? 1. : 0.) - qq));
     }
   }
+}
+
+template <int NF, int METHOD, class Sink>
+__device__ __forceinline__ void cell_entries(const double (&K)[9], const double (&xc)[3], double vol,
+                                             double mult, const double2 (&rec)[NF][4],
+                                             const double (&sgn)[NF], Sink&& sink) {
+  CellOps<NF> o;
+  cell_prep<NF, METHOD>(K, xc, rec, sgn, o);
+  cell_core<NF, METHOD>(o, K[0] + K[4] + K[8], vol, mult, sink);
 }
 
 __device__ __forceinline__ unsigned byte_of(const unsigned short* w, int i) {
@@ -158,6 +179,20 @@ __device__ __forceinline__ double wait_published(const double* slot, unsigned lo
     } while (bits == AU_SENTINEL && ++spins < (1u << 22));
     if (bits == AU_SENTINEL) atomicExch(error_flag, 1u);
   }
+  return __longlong_as_double((long long)bits);
+}
+
+// same, without an earlier optimistic read: load first, sleep only when the half is missing
+__device__ __forceinline__ double read_published(const double* slot, unsigned int* error_flag) {
+  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(slot);
+  unsigned long long bits;
+  unsigned int spins = 0;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(bits) : "l"(src));
+  while (bits == AU_SENTINEL && ++spins < (1u << 22)) {
+    __nanosleep(64);
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(bits) : "l"(src));
+  }
+  if (bits == AU_SENTINEL) atomicExch(error_flag, 1u);
   return __longlong_as_double((long long)bits);
 }
 
@@ -419,12 +454,306 @@ k_numeric_brick(mimpy_mesh_view m, int flags, UniArgs a) {
   }
 }
 
-// 0 direct, 1 brick (default where the mesh is a structured hex mesh)
+// ---------------------------------------------------------------------------------------------
+// staged brick: same brick, same row buffer, but every input is brought into shared memory by
+// coalesced asynchronous copies (cp.async) instead of per-thread strided loads.  The per-thread
+// loads of the kernel above touch one 32-byte sector per lane and instruction (53 sectors per
+// cell measured, the L1 data pipe was the busiest unit); here
+//   * the 464 face records of the brick are fetched once (not once per adjacent cell), 4 lanes
+//     per 64-byte record, into a 16-byte-chunk XOR swizzle that makes the later per-cell
+//     128-bit reads conflict free;
+//   * K, centroid, volume and the symbolic byte/int maps of the 16 x-runs of 8 cells are copied
+//     as contiguous runs;
+//   * face ids come from the closed form of the HexMesh numbering (hexmesh.py:161-234), so no
+//     load depends on another load.
+// The staging area for records/K/centroid/volume ALIASES the row buffer: operands are pulled into
+// registers (R~, KN), then the buffer is sentinel-filled and used as above.
+// Needs hex_nx even (16-byte alignment of the cell runs).
+// ---------------------------------------------------------------------------------------------
+#define B2_OFF_REC 0
+#define B2_OFF_K (BR_NFACE * 64)
+#define B2_OFF_XC (B2_OFF_K + BR_THREADS * 72)
+#define B2_OFF_VOL (B2_OFF_XC + BR_THREADS * 24)
+#define B2_OFF_ROWSTART (BR_NFACE * BR_RW * 8)
+#define B2_OFF_CRS (B2_OFF_ROWSTART + BR_NFACE * 4)
+#define B2_OFF_PM (B2_OFF_CRS + BR_THREADS * 24)
+#define B2_OFF_SG (B2_OFF_PM + BR_THREADS * 36)
+#define B2_OFF_DT (B2_OFF_SG + BR_THREADS * 6)
+#define B2_OFF_D (B2_OFF_DT + BR_THREADS * 6)
+#define B2_OFF_ROLE (B2_OFF_D + BR_THREADS * 6)
+#define B2_OFF_TICKET (B2_OFF_ROLE + BR_THREADS * 6)
+#define B2_SMEM (B2_OFF_TICKET + 16)
+static_assert(B2_OFF_VOL + BR_THREADS * 8 <= B2_OFF_ROWSTART, "staging area must fit in the row buffer");
+static_assert(B2_OFF_ROWSTART % 16 == 0 && B2_OFF_CRS % 16 == 0 && B2_OFF_PM % 16 == 0, "alignment");
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(unsigned dst, const void* src) {
+  if (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  else if (BYTES == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// 8 lanes copy one x-run (nbytes, a multiple of 4; of 16 when vec16) of a per-cell array
+template <int MAXBYTES>
+__device__ __forceinline__ void stage_run(unsigned dst, const void* src_, int lane8, int nbytes, bool vec16) {
+  const char* src = reinterpret_cast<const char*>(src_);
+  if (vec16) {
+#pragma unroll
+    for (int off0 = 0; off0 < MAXBYTES; off0 += 128) {
+      const int off = off0 + lane8 * 16;
+      if (off < nbytes) cp_async<16>(dst + off, src + off);
+    }
+  } else {
+#pragma unroll
+    for (int off0 = 0; off0 < MAXBYTES; off0 += 32) {
+      const int off = off0 + lane8 * 4;
+      if (off < nbytes) cp_async<4>(dst + off, src + off);
+    }
+  }
+}
+
+__device__ __forceinline__ void stage_record(unsigned sbase, const double* face_geom, int lf, int c, int fid) {
+  cp_async<16>(sbase + B2_OFF_REC + lf * 64 + (((c ^ (lf >> 1)) & 3) << 4), face_geom + 8 * (size_t)fid + 2 * c);
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(BR_THREADS, BR_MINB)
+k_numeric_brick2(mimpy_mesh_view m, int flags, UniArgs a) {
+  constexpr int NF = 6;
+  extern __shared__ __align__(128) unsigned char sm[];
+  double* row = reinterpret_cast<double*>(sm);
+  int* s_rowstart = reinterpret_cast<int*>(sm + B2_OFF_ROWSTART);
+  unsigned int* s_ticket = reinterpret_cast<unsigned int*>(sm + B2_OFF_TICKET);
+  const int t = threadIdx.x;
+  if (t == 0) *s_ticket = atomicAdd(a.ticket, 1u);
+  for (int e = t; e < BR_NFACE; e += BR_THREADS) s_rowstart[e] = -1;
+  __syncthreads();
+  const int nx = m.hex_nx, ny = m.hex_ny, nz = m.hex_nz;
+  const int nbx = (nx + BX - 1) / BX, nby = (ny + BY - 1) / BY;
+  const int brick = (int)*s_ticket;  // lexicographic: x fastest, z slowest
+  const int bi = brick % nbx, bj = (brick / nbx) % nby, bk = brick / (nbx * nby);
+  const int ci0 = bi * BX, cj0 = bj * BY, ck0 = bk * BZ;
+  const int runlen = min(BX, nx - ci0);
+  const int li = t % BX, lj = (t / BX) % BY, lk = t / (BX * BY);
+  const int ci = ci0 + li, cj = cj0 + lj, ck = ck0 + lk;
+  const bool run_ok = cj < ny && ck < nz;          // the x-run (lj, lk) this thread belongs to
+  const bool ok = run_ok && ci < nx;
+  const int cell0 = ci0 + nx * (cj + ny * ck);     // first cell of the run
+  const int cell = cell0 + li;
+  const int L = nx * ny + nx * (ny + 1) + (nx + 1) * ny;  // nf < 2^31 (checked by hex_topology)
+  const int xrow = 3 * nx + 1;
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm);
+  const bool k_unity = flags & 1;
+
+  // ---- stage: face records, 4 lanes per 64-byte record (HexMesh numbering, hexmesh.py:161-234) ----
+  {
+    const int c = t & 3, i = (t >> 2) & 7, w = t >> 5;
+    const int gi = ci0 + i;
+    if (gi < nx) {
+      {  // z faces: lj = w, lk = 0..BZ
+        const int gj = cj0 + w;
+        int fid = ck0 * L + gj * xrow + 3 * gi;
+#pragma unroll
+        for (int q = 0; q <= BZ; ++q, fid += L) {
+          const int gk = ck0 + q;
+          if (gj < ny && gk <= nz)
+            stage_record(sbase, m.face_geom, (q * BY + w) * BX + i, c, gk < nz ? fid : nz * L + gj * nx + gi);
+        }
+      }
+      {  // y faces: lk = w, lj = 0..BY
+        const int gk = ck0 + w;
+        int fid = gk * L + cj0 * xrow + 3 * gi + 1;
+#pragma unroll
+        for (int q = 0; q <= BY; ++q, fid += xrow) {
+          const int gj = cj0 + q;
+          if (gk < nz && gj <= ny)
+            stage_record(sbase, m.face_geom, BR_NZF + (w * (BY + 1) + q) * BX + i, c,
+                         gj < ny ? fid : gk * L + ny * xrow + gi);
+        }
+      }
+    }
+    if (run_ok) {  // x faces of this thread's run: 9 records = 36 chunks over 8 lanes
+      const int base = ck * L + cj * xrow;
+#pragma unroll
+      for (int q0 = 0; q0 < 4 * (BX + 1); q0 += 8) {
+        const int cc = q0 + (t & 7);
+        const int q = cc >> 2, gx = ci0 + q;
+        if (cc < 4 * (BX + 1) && gx <= nx)
+          stage_record(sbase, m.face_geom, BR_NZF + BR_NYF + (t >> 3) * (BX + 1) + q, cc & 3,
+                       base + (gx < nx ? 3 * gx + 2 : 3 * nx));
+      }
+    }
+  }
+  // ---- stage: per-cell arrays of this thread's x-run (8 lanes per run) ----
+  if (run_ok) {
+    const int r = t >> 3, l8 = t & 7;
+    const bool v16_pm = (nx & 3) == 0 && (runlen & 3) == 0;
+    const bool v16_b6 = (nx & 7) == 0 && runlen == BX;
+    const size_t c0 = (size_t)cell0;
+    if (!k_unity) stage_run<BX * 72>(sbase + B2_OFF_K + r * (BX * 72), m.cell_k + c0 * 9, l8, runlen * 72, true);
+    stage_run<BX * 24>(sbase + B2_OFF_XC + r * (BX * 24), m.cell_centroid + c0 * 3, l8, runlen * 24, true);
+    stage_run<BX * 8>(sbase + B2_OFF_VOL + r * (BX * 8), m.cell_volume + c0, l8, runlen * 8, true);
+    stage_run<BX * 24>(sbase + B2_OFF_CRS + r * (BX * 24), a.cell_rowstart + c0 * 6, l8, runlen * 24, true);
+    stage_run<BX * 36>(sbase + B2_OFF_PM + r * (BX * 36), a.pos_m + c0 * 36, l8, runlen * 36, v16_pm);
+    stage_run<BX * 6>(sbase + B2_OFF_SG + r * (BX * 6), m.cell_sigma + c0 * 6, l8, runlen * 6, v16_b6);
+    stage_run<BX * 6>(sbase + B2_OFF_DT + r * (BX * 6), a.pos_dt + c0 * 6, l8, runlen * 6, v16_b6);
+    stage_run<BX * 6>(sbase + B2_OFF_D + r * (BX * 6), a.pos_d + c0 * 6, l8, runlen * 6, v16_b6);
+    stage_run<BX * 6>(sbase + B2_OFF_ROLE + r * (BX * 6), a.role + c0 * 6, l8, runlen * 6, v16_b6);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  // local face ids of the cell's faces [z-, y-, x-, x+, y+, z+]
+  int lf[NF];
+  lf[0] = (lk * BY + lj) * BX + li;
+  lf[5] = ((lk + 1) * BY + lj) * BX + li;
+  lf[1] = BR_NZF + (lk * (BY + 1) + lj) * BX + li;
+  lf[4] = BR_NZF + (lk * (BY + 1) + lj + 1) * BX + li;
+  lf[2] = BR_NZF + BR_NYF + (lk * BY + lj) * (BX + 1) + li;
+  lf[3] = BR_NZF + BR_NYF + (lk * BY + lj) * (BX + 1) + li + 1;
+  const bool in_brick[NF] = {lk > 0, lj > 0, li > 0, li < BX - 1, lj < BY - 1, lk < BZ - 1};
+  const int cbase = ck * L + cj * xrow + 3 * ci;  // global ids of faces z-, y-, x- are cbase + 0, 1, 2
+
+  int crow = 0, crow_end = 0;
+  double mult = 1., cdiag = 0.;
+  if (ok) {
+    crow = __ldg(a.indptr + a.flux_dof + cell);
+    crow_end = __ldg(a.indptr + a.flux_dof + cell + 1);
+    if (a.multipliers) mult = __ldg(a.multipliers + cell);
+    if (a.c_diag) cdiag = __ldg(a.c_diag + cell);
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // ---- pull: operands into registers ----
+  CellOps<NF> o;
+  int rs[NF];
+  unsigned int pm[NF * NF / 4];
+  unsigned short w_dt[NF / 2], w_d[NF / 2], w_role[NF / 2];
+  double sa[NF], vol = 0., trk = 1.;
+  if (ok) {
+    double K[9], xc[3], sgn[NF];
+    double2 rec[NF][4];
+#pragma unroll
+    for (int i = 0; i < NF; ++i)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        rec[i][q] = *reinterpret_cast<const double2*>(sm + B2_OFF_REC + lf[i] * 64 + (((q ^ (lf[i] >> 1)) & 3) << 4));
+    if (k_unity) {
+#pragma unroll
+      for (int q = 0; q < 9; ++q) K[q] = (q % 4 == 0) ? 1. : 0.;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 9; ++q) K[q] = *reinterpret_cast<const double*>(sm + B2_OFF_K + t * 72 + q * 8);
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) xc[q] = *reinterpret_cast<const double*>(sm + B2_OFF_XC + t * 24 + q * 8);
+    vol = *reinterpret_cast<const double*>(sm + B2_OFF_VOL + t * 8);
+    unsigned short w_sg[NF / 2];
+#pragma unroll
+    for (int q = 0; q < NF / 2; ++q) {
+      const int2 v = *reinterpret_cast<const int2*>(sm + B2_OFF_CRS + t * 24 + q * 8);
+      rs[2 * q] = v.x;
+      rs[2 * q + 1] = v.y;
+      w_sg[q] = *reinterpret_cast<const unsigned short*>(sm + B2_OFF_SG + t * 6 + q * 2);
+      w_dt[q] = *reinterpret_cast<const unsigned short*>(sm + B2_OFF_DT + t * 6 + q * 2);
+      w_d[q] = *reinterpret_cast<const unsigned short*>(sm + B2_OFF_D + t * 6 + q * 2);
+      w_role[q] = *reinterpret_cast<const unsigned short*>(sm + B2_OFF_ROLE + t * 6 + q * 2);
+    }
+#pragma unroll
+    for (int q = 0; q < NF * NF / 4; ++q) pm[q] = *reinterpret_cast<const unsigned int*>(sm + B2_OFF_PM + t * 36 + q * 4);
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+      sgn[i] = (double)(signed char)byte_of(w_sg, i);
+      sa[i] = sgn[i] * rec[i][0].x;
+    }
+    trk = K[0] + K[4] + K[8];
+    cell_prep<NF, METHOD>(K, xc, rec, sgn, o);
+  }
+  __syncthreads();
+  // sentinel-fill the row buffer: a slot nobody in this brick writes is not stored
+  {
+    const ulonglong2 s2 = make_ulonglong2(AU_SENTINEL, AU_SENTINEL);
+    ulonglong2* r2 = reinterpret_cast<ulonglong2*>(sm);
+    static_assert((BR_NFACE * BR_RW) % 2 == 0, "row buffer is a whole number of 16-byte words");
+    for (int e = t; e < BR_NFACE * BR_RW / 2; e += BR_THREADS) r2[e] = s2;
+  }
+  __syncthreads();
+
+  double diag[NF];
+  if (ok) {
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+      if (rs[i] >= 0) {
+        s_rowstart[lf[i]] = rs[i];                              // both cells write the same value
+        row[lf[i] * BR_RW + byte_of(w_dt, i)] = -sa[i];         // -DIV^T   mfd.py:240-243
+        a.vals[crow + byte_of(w_d, i)] = sa[i];                 // DIV      mfd.py:232-238
+      }
+    }
+    a.vals[crow_end - 1] = a.c_diag ? cdiag : a.alpha * vol;    // mfd.py:766-772
+    cell_core<NF, METHOD>(o, trk, vol, mult, [&](int i, int j, double v) {
+      if (i == j) {
+        diag[i] = v;
+      } else {
+        const unsigned pos = PM_POS(pm, i * NF + j);
+        if (rs[i] >= 0 && pos != 0xFFu) row[lf[i] * BR_RW + pos] = v;
+      }
+    });
+    // diagonals, step 1: single-cell faces and the LOWER cell of shared faces; halves whose upper
+    // cell lives in a later brick are published right away
+    const int fid_up[3] = {ci + 1 < nx ? cbase + 5 : ck * L + cj * xrow + 3 * nx,
+                           cj + 1 < ny ? cbase + xrow + 1 : ck * L + ny * xrow + ci,
+                           ck + 1 < nz ? cbase + L : nz * L + cj * nx + ci};
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+      if (rs[i] < 0) continue;
+      const unsigned role = byte_of(w_role, i);
+      const int slot = lf[i] * BR_RW + PM_POS(pm, i * NF + i);
+      if (role == 0 || (role == 1 && in_brick[i])) row[slot] = diag[i];
+      if (role == 1 && !in_brick[i]) a.diag_pub[i >= 3 ? fid_up[i >= 3 ? i - 3 : 0] : cbase + i] = diag[i];
+    }
+  }
+  __syncthreads();
+  if (ok) {  // diagonals, step 2: the UPPER cell adds its half (lower + upper, fixed order)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (rs[i] >= 0 && byte_of(w_role, i) == 2 && in_brick[i]) {
+        const int slot = lf[i] * BR_RW + PM_POS(pm, i * NF + i);
+        row[slot] = row[slot] + diag[i];
+      }
+    }
+  }
+  __syncthreads();
+  // stream the rows out: 8 rows x 13 slots per pass (104 of the 128 threads), thread = fixed slot
+  // of a fixed row-in-pass; a sentinel has an all-ones high word, which no finite value has
+  if (t < 8 * BR_RW) {
+    const int r0 = t / BR_RW, pos = t - r0 * BR_RW;
+#pragma unroll 8
+    for (int r = r0; r < BR_NFACE; r += 8) {
+      const double v = row[r * BR_RW + pos];
+      if (__double2hiint(v) != -1) a.vals[s_rowstart[r] + pos] = v;
+    }
+  }
+  // diagonals, step 3: faces whose lower cell lives in an EARLIER brick.  Their slot was left as
+  // sentinel above; waiting this late means the half is practically always there already.
+  if (ok) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (rs[i] >= 0 && byte_of(w_role, i) == 2 && !in_brick[i])
+        a.vals[rs[i] + PM_POS(pm, i * NF + i)] =
+            read_published(a.diag_pub + (cbase + i), a.error_flag) + diag[i];
+    }
+  }
+}
+
+// 0 direct, 1 brick, 2 staged brick (default where the mesh is a structured hex mesh with even nx)
 static int asm_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MIMPY_B200_ASM_VARIANT");
-    v = (e && e[0] == 'd') ? 0 : 1;
+    v = (e && e[0] == 'd') ? 0 : (e && e[0] == 'b') ? 1 : 2;
   }
   return v;
 }
@@ -433,7 +762,16 @@ template <int METHOD>
 static int launch_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int flags, const UniArgs& a) {
   const bool structured = mesh->hex_nx > 0 && mesh->hex_ny > 0 && mesh->hex_nz > 0 &&
                           (long long)mesh->hex_nx * mesh->hex_ny * mesh->hex_nz == mesh->nc;
-  if (structured && asm_variant() == 1 && !(flags & MIMPY_FLAG_DIRECT_KERNEL)) {
+  const long long n_bricks = (long long)((mesh->hex_nx + BX - 1) / BX) * ((mesh->hex_ny + BY - 1) / BY) *
+                             ((mesh->hex_nz + BZ - 1) / BZ);
+  if (structured && asm_variant() == 2 && mesh->hex_nx % 2 == 0 && !(flags & MIMPY_FLAG_DIRECT_KERNEL)) {
+    static bool configured2 = false;
+    if (!configured2) {
+      CUDA_TRY(cudaFuncSetAttribute(k_numeric_brick2<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2_SMEM));
+      configured2 = true;
+    }
+    k_numeric_brick2<METHOD><<<(unsigned)n_bricks, BR_THREADS, B2_SMEM, ctx->stream>>>(*mesh, flags, a);
+  } else if (structured && asm_variant() >= 1 && !(flags & MIMPY_FLAG_DIRECT_KERNEL)) {
     const size_t smem = sizeof(BrickSmem);
     static bool configured = false;
     if (!configured) {

@@ -1,4 +1,4 @@
-"""Bottleneck experiments for the numeric assembly kernel (debug flag bits 256/512/1024)."""
+"""Timing of the numeric assembly kernel variants: exp_asm.py [n] [all]."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -22,6 +22,7 @@ def timeit(label, **kw):
             e0.record(ctx.stream); device.numeric(dm, plan, 1, vals=vals, **kw); e1.record(ctx.stream)
         ctx.sync(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     print("%-40s %.3f ms  (%.0f Mcells/s, %.1f%% of 6546.6 GB/s algorithmic)" % (label, min(ts), nc / min(ts) / 1e3, 700. * nc / min(ts) / 1e6 / 6546.6 * 100))
-timeit("brick (default)")
-timeit("direct", debug_flags=4)
-timeit("generic warp-group kernel", generic_kernel=True)
+timeit("structured-hex kernel, MIMPY_B200_ASM_VARIANT=%s" % os.environ.get("MIMPY_B200_ASM_VARIANT", "(default: staged brick)"))
+if len(sys.argv) > 2:
+    timeit("direct", debug_flags=4)
+    timeit("generic warp-group kernel", generic_kernel=True)

@@ -299,15 +299,17 @@ def test_update_m_multipliers_and_coo_view(ctx, golden):
     assert abs(a2[F:, :] - a1[F:, :]).max() == 0
 
 
+@pytest.mark.parametrize("n", [(37, 20, 23), (38, 21, 23), (8, 4, 4), (2, 1, 1)])
 @pytest.mark.parametrize("method", [0, 1, 6])
-def test_uniform_fast_path_equals_generic_kernel(ctx, method):
+def test_uniform_fast_path_equals_generic_kernel(ctx, method, n):
     """The thread-per-cell hex kernel and the generic warp-group kernel fill the same CSR:
     identical slots, values within 1e-13 (different but equivalent operation order), and the
     fast path is bit-reproducible run to run (the diagonal has a fixed summation order)."""
     import torch
     from mimpy_b200 import device
 
-    n = (37, 20, 23)
+    # odd nx -> brick kernel with per-thread loads; even nx -> cp.async-staged brick kernel
+    # (38x21x23 has partial bricks on all three axes)
     nc = n[0] * n[1] * n[2]
     rng = np.random.default_rng(3)
     k = np.zeros((nc, 3, 3))
