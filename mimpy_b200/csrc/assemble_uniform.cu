@@ -526,14 +526,11 @@ k_numeric_brick2(mimpy_mesh_view m, int flags, UniArgs a) {
   extern __shared__ __align__(128) unsigned char sm[];
   double* row = reinterpret_cast<double*>(sm);
   int* s_rowstart = reinterpret_cast<int*>(sm + B2_OFF_ROWSTART);
-  unsigned int* s_ticket = reinterpret_cast<unsigned int*>(sm + B2_OFF_TICKET);
   const int t = threadIdx.x;
-  if (t == 0) *s_ticket = atomicAdd(a.ticket, 1u);
-  for (int e = t; e < BR_NFACE; e += BR_THREADS) s_rowstart[e] = -1;
-  __syncthreads();
+  for (int e = t; e < BR_NFACE; e += BR_THREADS) s_rowstart[e] = -1;  // (barriers follow before use)
   const int nx = m.hex_nx, ny = m.hex_ny, nz = m.hex_nz;
   const int nbx = (nx + BX - 1) / BX, nby = (ny + BY - 1) / BY;
-  const int brick = (int)*s_ticket;  // lexicographic: x fastest, z slowest
+  const int brick = (int)blockIdx.x;  // x fastest, z slowest; bricks are independent of each other
   const int bi = brick % nbx, bj = (brick / nbx) % nby, bk = brick / (nbx * nby);
   const int ci0 = bi * BX, cj0 = bj * BY, ck0 = bk * BZ;
   const int runlen = min(BX, nx - ci0);
@@ -683,6 +680,7 @@ k_numeric_brick2(mimpy_mesh_view m, int flags, UniArgs a) {
   __syncthreads();
 
   double diag[NF];
+  unsigned long long other[NF];
   if (ok) {
 #pragma unroll
     for (int i = 0; i < NF; ++i) {
@@ -701,18 +699,23 @@ k_numeric_brick2(mimpy_mesh_view m, int flags, UniArgs a) {
         if (rs[i] >= 0 && pos != 0xFFu) row[lf[i] * BR_RW + pos] = v;
       }
     });
-    // diagonals, step 1: single-cell faces and the LOWER cell of shared faces; halves whose upper
-    // cell lives in a later brick are published right away
+    // diagonals, step 1: single-cell faces and the LOWER cell of faces inside the brick go to the
+    // row buffer.  A face shared with ANOTHER brick: both cells swap their half into diag_pub[f]
+    // (pre-set to the sentinel); whoever finds the other's half there -- the second to arrive --
+    // writes half + half to the CSR slot (step 3).  IEEE addition commutes, so the result does not
+    // depend on the arrival order: bit-reproducible, and nobody ever waits.
     const int fid_up[3] = {ci + 1 < nx ? cbase + 5 : ck * L + cj * xrow + 3 * nx,
                            cj + 1 < ny ? cbase + xrow + 1 : ck * L + ny * xrow + ci,
                            ck + 1 < nz ? cbase + L : nz * L + cj * nx + ci};
 #pragma unroll
     for (int i = 0; i < NF; ++i) {
+      other[i] = AU_SENTINEL;
       if (rs[i] < 0) continue;
       const unsigned role = byte_of(w_role, i);
-      const int slot = lf[i] * BR_RW + PM_POS(pm, i * NF + i);
-      if (role == 0 || (role == 1 && in_brick[i])) row[slot] = diag[i];
-      if (role == 1 && !in_brick[i]) a.diag_pub[i >= 3 ? fid_up[i >= 3 ? i - 3 : 0] : cbase + i] = diag[i];
+      if (role == 0 || (role == 1 && in_brick[i])) row[lf[i] * BR_RW + PM_POS(pm, i * NF + i)] = diag[i];
+      if (role != 0 && !in_brick[i])
+        other[i] = atomicExch(reinterpret_cast<unsigned long long*>(a.diag_pub + (i >= 3 ? fid_up[i >= 3 ? i - 3 : 0] : cbase + i)),
+                              (unsigned long long)__double_as_longlong(diag[i]));
     }
   }
   __syncthreads();
@@ -736,14 +739,12 @@ k_numeric_brick2(mimpy_mesh_view m, int flags, UniArgs a) {
       if (__double2hiint(v) != -1) a.vals[s_rowstart[r] + pos] = v;
     }
   }
-  // diagonals, step 3: faces whose lower cell lives in an EARLIER brick.  Their slot was left as
-  // sentinel above; waiting this late means the half is practically always there already.
+  // diagonals, step 3: second arrivals at a face shared with another brick finish the slot
   if (ok) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      if (rs[i] >= 0 && byte_of(w_role, i) == 2 && !in_brick[i])
-        a.vals[rs[i] + PM_POS(pm, i * NF + i)] =
-            read_published(a.diag_pub + (cbase + i), a.error_flag) + diag[i];
+    for (int i = 0; i < NF; ++i) {
+      if (other[i] != AU_SENTINEL)
+        a.vals[rs[i] + PM_POS(pm, i * NF + i)] = __longlong_as_double((long long)other[i]) + diag[i];
     }
   }
 }
