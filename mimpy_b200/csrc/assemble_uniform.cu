@@ -529,9 +529,15 @@ k_numeric_brick2(mimpy_mesh_view m, int flags, UniArgs a) {
   const int t = threadIdx.x;
   for (int e = t; e < BR_NFACE; e += BR_THREADS) s_rowstart[e] = -1;  // (barriers follow before use)
   const int nx = m.hex_nx, ny = m.hex_ny, nz = m.hex_nz;
-  const int nbx = (nx + BX - 1) / BX, nby = (ny + BY - 1) / BY;
-  const int brick = (int)blockIdx.x;  // x fastest, z slowest; bricks are independent of each other
-  const int bi = brick % nbx, bj = (brick / nbx) % nby, bk = brick / (nbx * nby);
+  // Bricks are independent of each other; blockIdx walks them in super-tiles of 4x4x4 bricks so
+  // that the two bricks sharing a surface row (and its face record) run close together in time
+  // and their half rows merge in L2 instead of each making a partial-sector round trip to HBM.
+  const int nbx = (nx + BX - 1) / BX, nby = (ny + BY - 1) / BY, nbz = (nz + BZ - 1) / BZ;
+  const int nsx = (nbx + 3) >> 2, nsy = (nby + 3) >> 2;
+  const int sb = (int)(blockIdx.x >> 6), wi = (int)(blockIdx.x & 63);
+  const int bi = (sb % nsx) * 4 + (wi & 3), bj = ((sb / nsx) % nsy) * 4 + ((wi >> 2) & 3),
+            bk = (sb / (nsx * nsy)) * 4 + (wi >> 4);
+  if (bi >= nbx || bj >= nby || bk >= nbz) return;
   const int ci0 = bi * BX, cj0 = bj * BY, ck0 = bk * BZ;
   const int runlen = min(BX, nx - ci0);
   const int li = t % BX, lj = (t / BX) % BY, lk = t / (BX * BY);
@@ -771,7 +777,9 @@ static int launch_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int flags
       CUDA_TRY(cudaFuncSetAttribute(k_numeric_brick2<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2_SMEM));
       configured2 = true;
     }
-    k_numeric_brick2<METHOD><<<(unsigned)n_bricks, BR_THREADS, B2_SMEM, ctx->stream>>>(*mesh, flags, a);
+    const long long super_tiles = (long long)(((mesh->hex_nx + BX - 1) / BX + 3) / 4) * (((mesh->hex_ny + BY - 1) / BY + 3) / 4) *
+                                  (((mesh->hex_nz + BZ - 1) / BZ + 3) / 4);
+    k_numeric_brick2<METHOD><<<(unsigned)(super_tiles * 64), BR_THREADS, B2_SMEM, ctx->stream>>>(*mesh, flags, a);
   } else if (structured && asm_variant() >= 1 && !(flags & MIMPY_FLAG_DIRECT_KERNEL)) {
     const size_t smem = sizeof(BrickSmem);
     static bool configured = false;
