@@ -474,15 +474,28 @@ k_numeric_brick(mimpy_mesh_view m, int flags, UniArgs a) {
 #define B2_OFF_K (BR_NFACE * 64)
 #define B2_OFF_XC (B2_OFF_K + BR_THREADS * 72)
 #define B2_OFF_VOL (B2_OFF_XC + BR_THREADS * 24)
-#define B2_OFF_ROWSTART (BR_NFACE * BR_RW * 8)
-#define B2_OFF_CRS (B2_OFF_ROWSTART + BR_NFACE * 4)
+// output image in shared memory, laid out like the CSR value array itself:
+//   16 x-runs x 312 slots : the 24 face rows (z-, y-, x- of 8 cells) of a run are CONSECUTIVE CSR rows,
+//                           so a run is one contiguous piece of `vals` (<= 24 * 13 values)
+//   80 extra rows x 13    : x+ faces of the last cell column, y+ of the last row, z+ of the top layer
+//   16 x-runs x 56 slots  : the cell rows (DIV + C diagonal, <= 7 values per cell) of a run
+#define B2_RUNS (BY * BZ)
+#define B2_RUN_SLOTS (3 * BX * BR_RW)
+#define B2_EXTRA_ROWS (BY * BZ + BX * BZ + BX * BY)
+#define B2_EXTRA0 (B2_RUNS * B2_RUN_SLOTS)
+#define B2_CELL0 (B2_EXTRA0 + B2_EXTRA_ROWS * BR_RW)
+#define B2_CELL_SLOTS (BX * 7)
+#define B2_OUT_SLOTS (B2_CELL0 + B2_RUNS * B2_CELL_SLOTS)
+#define B2_OFF_ROWSTART (B2_OUT_SLOTS * 8)   /* int run_base[16], cell_base[16], extra_rowstart[80] */
+#define B2_OFF_CRS (B2_OFF_ROWSTART + (2 * B2_RUNS + B2_EXTRA_ROWS) * 4)
 #define B2_OFF_PM (B2_OFF_CRS + BR_THREADS * 24)
 #define B2_OFF_SG (B2_OFF_PM + BR_THREADS * 36)
 #define B2_OFF_DT (B2_OFF_SG + BR_THREADS * 6)
 #define B2_OFF_D (B2_OFF_DT + BR_THREADS * 6)
 #define B2_OFF_ROLE (B2_OFF_D + BR_THREADS * 6)
-#define B2_OFF_TICKET (B2_OFF_ROLE + BR_THREADS * 6)
-#define B2_SMEM (B2_OFF_TICKET + 16)
+#define B2_SMEM (B2_OFF_ROLE + BR_THREADS * 6)
+static_assert(B2_EXTRA0 + B2_EXTRA_ROWS * BR_RW == BR_NFACE * BR_RW, "row image holds every face row of the brick");
+static_assert(B2_OUT_SLOTS % 2 == 0, "output image is a whole number of 16-byte words");
 static_assert(B2_OFF_VOL + BR_THREADS * 8 <= B2_OFF_ROWSTART, "staging area must fit in the row buffer");
 static_assert(B2_OFF_ROWSTART % 16 == 0 && B2_OFF_CRS % 16 == 0 && B2_OFF_PM % 16 == 0, "alignment");
 
@@ -525,18 +538,20 @@ k_numeric_brick2(mimpy_mesh_view m, int flags, UniArgs a) {
   constexpr int NF = 6;
   extern __shared__ __align__(128) unsigned char sm[];
   double* row = reinterpret_cast<double*>(sm);
-  int* s_rowstart = reinterpret_cast<int*>(sm + B2_OFF_ROWSTART);
+  int* s_runbase = reinterpret_cast<int*>(sm + B2_OFF_ROWSTART);
+  int* s_cellbase = s_runbase + B2_RUNS;
+  int* s_extra_rs = s_cellbase + B2_RUNS;
   const int t = threadIdx.x;
-  for (int e = t; e < BR_NFACE; e += BR_THREADS) s_rowstart[e] = -1;  // (barriers follow before use)
+  if (t < B2_EXTRA_ROWS) s_extra_rs[t] = 0;  // (barriers follow before use)
   const int nx = m.hex_nx, ny = m.hex_ny, nz = m.hex_nz;
   // Bricks are independent of each other; blockIdx walks them in super-tiles of 4x4x4 bricks so
   // that the two bricks sharing a surface row (and its face record) run close together in time
   // and their half rows merge in L2 instead of each making a partial-sector round trip to HBM.
   const int nbx = (nx + BX - 1) / BX, nby = (ny + BY - 1) / BY, nbz = (nz + BZ - 1) / BZ;
   const int nsx = (nbx + 3) >> 2, nsy = (nby + 3) >> 2;
-  const int sb = (int)(blockIdx.x >> 6), wi = (int)(blockIdx.x & 63);
-  const int bi = (sb % nsx) * 4 + (wi & 3), bj = ((sb / nsx) % nsy) * 4 + ((wi >> 2) & 3),
-            bk = (sb / (nsx * nsy)) * 4 + (wi >> 4);
+  const int st = (int)(blockIdx.x >> 6), wi = (int)(blockIdx.x & 63);
+  const int bi = (st % nsx) * 4 + (wi & 3), bj = ((st / nsx) % nsy) * 4 + ((wi >> 2) & 3),
+            bk = (st / (nsx * nsy)) * 4 + (wi >> 4);
   if (bi >= nbx || bj >= nby || bk >= nbz) return;
   const int ci0 = bi * BX, cj0 = bj * BY, ck0 = bk * BZ;
   const int runlen = min(BX, nx - ci0);
@@ -675,34 +690,67 @@ k_numeric_brick2(mimpy_mesh_view m, int flags, UniArgs a) {
     trk = K[0] + K[4] + K[8];
     cell_prep<NF, METHOD>(K, xc, rec, sgn, o);
   }
+  const int run = t >> 3;
+  {  // CSR offset of the run's first face row (rows z-, y-, x- of a cell ascend) and first cell row
+    int first = 0x7fffffff;
+    if (ok) first = rs[0] >= 0 ? rs[0] : rs[1] >= 0 ? rs[1] : rs[2] >= 0 ? rs[2] : 0x7fffffff;
+#pragma unroll
+    for (int d = 4; d > 0; d >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, d));
+    if (li == 0) {
+      s_runbase[run] = first;
+      s_cellbase[run] = crow;
+    }
+  }
   __syncthreads();
-  // sentinel-fill the row buffer: a slot nobody in this brick writes is not stored
+  // sentinel-fill the output image: a slot nobody in this brick writes is not stored
   {
     const ulonglong2 s2 = make_ulonglong2(AU_SENTINEL, AU_SENTINEL);
     ulonglong2* r2 = reinterpret_cast<ulonglong2*>(sm);
-    static_assert((BR_NFACE * BR_RW) % 2 == 0, "row buffer is a whole number of 16-byte words");
-    for (int e = t; e < BR_NFACE * BR_RW / 2; e += BR_THREADS) r2[e] = s2;
+    for (int e = t; e < B2_OUT_SLOTS / 2; e += BR_THREADS) r2[e] = s2;
   }
   __syncthreads();
 
   double diag[NF];
   unsigned long long other[NF];
+  int sb[NF];  // where slot 0 of the face's row lives in the output image
   if (ok) {
+    const int rb = s_runbase[run];
+    sb[0] = run * B2_RUN_SLOTS + rs[0] - rb;
+    sb[1] = run * B2_RUN_SLOTS + rs[1] - rb;
+    sb[2] = run * B2_RUN_SLOTS + rs[2] - rb;
+    if (li < BX - 1 && ci + 1 < nx) {
+      sb[3] = run * B2_RUN_SLOTS + rs[3] - rb;
+    } else {
+      sb[3] = B2_EXTRA0 + run * BR_RW;
+      s_extra_rs[run] = rs[3];
+    }
+    if (lj < BY - 1 && cj + 1 < ny) {
+      sb[4] = (run + 1) * B2_RUN_SLOTS + rs[4] - s_runbase[run + 1];
+    } else {
+      sb[4] = B2_EXTRA0 + (B2_RUNS + lk * BX + li) * BR_RW;
+      s_extra_rs[B2_RUNS + lk * BX + li] = rs[4];
+    }
+    if (lk < BZ - 1 && ck + 1 < nz) {
+      sb[5] = (run + BY) * B2_RUN_SLOTS + rs[5] - s_runbase[run + BY];
+    } else {
+      sb[5] = B2_EXTRA0 + (B2_RUNS + BX * BZ + lj * BX + li) * BR_RW;
+      s_extra_rs[B2_RUNS + BX * BZ + lj * BX + li] = rs[5];
+    }
+    const int cb = B2_CELL0 + run * B2_CELL_SLOTS + (crow - s_cellbase[run]);
 #pragma unroll
     for (int i = 0; i < NF; ++i) {
       if (rs[i] >= 0) {
-        s_rowstart[lf[i]] = rs[i];                              // both cells write the same value
-        row[lf[i] * BR_RW + byte_of(w_dt, i)] = -sa[i];         // -DIV^T   mfd.py:240-243
-        a.vals[crow + byte_of(w_d, i)] = sa[i];                 // DIV      mfd.py:232-238
+        row[sb[i] + byte_of(w_dt, i)] = -sa[i];                 // -DIV^T   mfd.py:240-243
+        row[cb + byte_of(w_d, i)] = sa[i];                      // DIV      mfd.py:232-238
       }
     }
-    a.vals[crow_end - 1] = a.c_diag ? cdiag : a.alpha * vol;    // mfd.py:766-772
+    row[cb + (crow_end - 1 - crow)] = a.c_diag ? cdiag : a.alpha * vol;    // mfd.py:766-772
     cell_core<NF, METHOD>(o, trk, vol, mult, [&](int i, int j, double v) {
       if (i == j) {
         diag[i] = v;
       } else {
         const unsigned pos = PM_POS(pm, i * NF + j);
-        if (rs[i] >= 0 && pos != 0xFFu) row[lf[i] * BR_RW + pos] = v;
+        if (rs[i] >= 0 && pos != 0xFFu) row[sb[i] + pos] = v;
       }
     });
     // diagonals, step 1: single-cell faces and the LOWER cell of faces inside the brick go to the
@@ -718,7 +766,7 @@ k_numeric_brick2(mimpy_mesh_view m, int flags, UniArgs a) {
       other[i] = AU_SENTINEL;
       if (rs[i] < 0) continue;
       const unsigned role = byte_of(w_role, i);
-      if (role == 0 || (role == 1 && in_brick[i])) row[lf[i] * BR_RW + PM_POS(pm, i * NF + i)] = diag[i];
+      if (role == 0 || (role == 1 && in_brick[i])) row[sb[i] + PM_POS(pm, i * NF + i)] = diag[i];
       if (role != 0 && !in_brick[i])
         other[i] = atomicExch(reinterpret_cast<unsigned long long*>(a.diag_pub + (i >= 3 ? fid_up[i >= 3 ? i - 3 : 0] : cbase + i)),
                               (unsigned long long)__double_as_longlong(diag[i]));
@@ -729,20 +777,46 @@ k_numeric_brick2(mimpy_mesh_view m, int flags, UniArgs a) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       if (rs[i] >= 0 && byte_of(w_role, i) == 2 && in_brick[i]) {
-        const int slot = lf[i] * BR_RW + PM_POS(pm, i * NF + i);
+        const int slot = sb[i] + PM_POS(pm, i * NF + i);
         row[slot] = row[slot] + diag[i];
       }
     }
   }
   __syncthreads();
-  // stream the rows out: 8 rows x 13 slots per pass (104 of the 128 threads), thread = fixed slot
-  // of a fixed row-in-pass; a sentinel has an all-ones high word, which no finite value has
-  if (t < 8 * BR_RW) {
+  // stream the image out; consecutive lanes write consecutive CSR values.  A sentinel has an
+  // all-ones high word, which no finite value has.
+  {  // face rows of the runs: 312 slots = 128 + 128 + 56 per run, addresses fixed per thread
+    static_assert(B2_RUN_SLOTS > 2 * BR_THREADS && B2_RUN_SLOTS <= 3 * BR_THREADS, "three passes per run");
+    const double* q = row + t;
+    double* out = a.vals + t;
+#pragma unroll 4
+    for (int r = 0; r < B2_RUNS; ++r, q += B2_RUN_SLOTS) {
+      const int base = s_runbase[r];
+      if (base == 0x7fffffff) continue;
+      const double v0 = q[0], v1 = q[BR_THREADS];
+      const double v2 = t < B2_RUN_SLOTS - 2 * BR_THREADS ? q[2 * BR_THREADS] : __longlong_as_double(-1ll);
+      double* o = out + base;
+      if (__double2hiint(v0) != -1) o[0] = v0;
+      if (__double2hiint(v1) != -1) o[BR_THREADS] = v1;
+      if (__double2hiint(v2) != -1) o[2 * BR_THREADS] = v2;
+    }
+  }
+  {  // cell rows: two runs per pass, 56 of 64 lanes each
+    const int half = t >> 6, l = t & 63;
+    if (l < B2_CELL_SLOTS) {
+#pragma unroll
+      for (int r = half; r < B2_RUNS; r += 2) {
+        const double v = row[B2_CELL0 + r * B2_CELL_SLOTS + l];
+        if (__double2hiint(v) != -1) a.vals[s_cellbase[r] + l] = v;
+      }
+    }
+  }
+  if (t < 8 * BR_RW) {  // rows on the brick's upper surfaces: 8 rows x 13 slots per pass
     const int r0 = t / BR_RW, pos = t - r0 * BR_RW;
-#pragma unroll 8
-    for (int r = r0; r < BR_NFACE; r += 8) {
-      const double v = row[r * BR_RW + pos];
-      if (__double2hiint(v) != -1) a.vals[s_rowstart[r] + pos] = v;
+#pragma unroll
+    for (int e = r0; e < B2_EXTRA_ROWS; e += 8) {
+      const double v = row[B2_EXTRA0 + e * BR_RW + pos];
+      if (__double2hiint(v) != -1) a.vals[s_extra_rs[e] + pos] = v;
     }
   }
   // diagonals, step 3: second arrivals at a face shared with another brick finish the slot
