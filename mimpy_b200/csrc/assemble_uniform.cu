@@ -713,6 +713,10 @@ k_numeric_brick2(mimpy_mesh_view m, int flags, UniArgs a) {
   double diag[NF];
   unsigned long long other[NF];
   int sb[NF];  // where slot 0 of the face's row lives in the output image
+  const int fid[NF] = {cbase, cbase + 1, cbase + 2,
+                       ci + 1 < nx ? cbase + 5 : ck * L + cj * xrow + 3 * nx,
+                       cj + 1 < ny ? cbase + xrow + 1 : ck * L + ny * xrow + ci,
+                       ck + 1 < nz ? cbase + L : nz * L + cj * nx + ci};
   if (ok) {
     const int rb = s_runbase[run];
     sb[0] = run * B2_RUN_SLOTS + rs[0] - rb;
@@ -755,12 +759,9 @@ k_numeric_brick2(mimpy_mesh_view m, int flags, UniArgs a) {
     });
     // diagonals, step 1: single-cell faces and the LOWER cell of faces inside the brick go to the
     // row buffer.  A face shared with ANOTHER brick: both cells swap their half into diag_pub[f]
-    // (pre-set to the sentinel); whoever finds the other's half there -- the second to arrive --
-    // writes half + half to the CSR slot (step 3).  IEEE addition commutes, so the result does not
+    // (all-sentinel between launches); whoever finds the other's half there -- the second to arrive --
+    // writes half + half to the CSR slot and restores the sentinel (step 3).  IEEE addition commutes, so the result does not
     // depend on the arrival order: bit-reproducible, and nobody ever waits.
-    const int fid_up[3] = {ci + 1 < nx ? cbase + 5 : ck * L + cj * xrow + 3 * nx,
-                           cj + 1 < ny ? cbase + xrow + 1 : ck * L + ny * xrow + ci,
-                           ck + 1 < nz ? cbase + L : nz * L + cj * nx + ci};
 #pragma unroll
     for (int i = 0; i < NF; ++i) {
       other[i] = AU_SENTINEL;
@@ -768,7 +769,7 @@ k_numeric_brick2(mimpy_mesh_view m, int flags, UniArgs a) {
       const unsigned role = byte_of(w_role, i);
       if (role == 0 || (role == 1 && in_brick[i])) row[sb[i] + PM_POS(pm, i * NF + i)] = diag[i];
       if (role != 0 && !in_brick[i])
-        other[i] = atomicExch(reinterpret_cast<unsigned long long*>(a.diag_pub + (i >= 3 ? fid_up[i >= 3 ? i - 3 : 0] : cbase + i)),
+        other[i] = atomicExch(reinterpret_cast<unsigned long long*>(a.diag_pub) + fid[i],
                               (unsigned long long)__double_as_longlong(diag[i]));
     }
   }
@@ -823,8 +824,10 @@ k_numeric_brick2(mimpy_mesh_view m, int flags, UniArgs a) {
   if (ok) {
 #pragma unroll
     for (int i = 0; i < NF; ++i) {
-      if (other[i] != AU_SENTINEL)
+      if (other[i] != AU_SENTINEL) {
         a.vals[rs[i] + PM_POS(pm, i * NF + i)] = __longlong_as_double((long long)other[i]) + diag[i];
+        reinterpret_cast<unsigned long long*>(a.diag_pub)[fid[i]] = AU_SENTINEL;  // leave the slot clean
+      }
     }
   }
 }
@@ -843,8 +846,6 @@ template <int METHOD>
 static int launch_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int flags, const UniArgs& a) {
   const bool structured = mesh->hex_nx > 0 && mesh->hex_ny > 0 && mesh->hex_nz > 0 &&
                           (long long)mesh->hex_nx * mesh->hex_ny * mesh->hex_nz == mesh->nc;
-  const long long n_bricks = (long long)((mesh->hex_nx + BX - 1) / BX) * ((mesh->hex_ny + BY - 1) / BY) *
-                             ((mesh->hex_nz + BZ - 1) / BZ);
   if (structured && asm_variant() == 2 && mesh->hex_nx % 2 == 0 && !(flags & MIMPY_FLAG_DIRECT_KERNEL)) {
     static bool configured2 = false;
     if (!configured2) {
@@ -879,11 +880,32 @@ int mimpy_numeric_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mim
                           const double* c_diag, double* vals) {
   if (mesh->uniform_faces != 6 || !sym->role || !sym->cell_rowstart) return MIMPY_E_UNSUPPORTED;
   if (method != 0 && method != 1 && method != 6) return MIMPY_E_UNSUPPORTED;
-  void* scratch = nullptr;
-  int rc = mimpy_scratch(ctx, sizeof(double) * (size_t)mesh->nf, &scratch);
-  if (rc) return rc;
-  CUDA_TRY(cudaMemsetAsync(scratch, 0xFF, sizeof(double) * (size_t)mesh->nf, ctx->stream));
-  CUDA_TRY(cudaMemsetAsync(ctx->counters + 8, 0, 2 * sizeof(unsigned int), ctx->stream));
+  const bool staged = mesh->hex_nx > 0 && mesh->hex_ny > 0 && mesh->hex_nz > 0 &&
+                      (long long)mesh->hex_nx * mesh->hex_ny * mesh->hex_nz == mesh->nc && asm_variant() == 2 &&
+                      mesh->hex_nx % 2 == 0 && !(flags & MIMPY_FLAG_DIRECT_KERNEL);
+  double* exchange = nullptr;
+  if (staged) {
+    // persistent exchange slots: set to the sentinel once, kept clean by the kernel itself
+    if (ctx->diag_swap_len < (size_t)mesh->nf) {
+      if (ctx->diag_swap) {
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaFree(ctx->diag_swap));
+      }
+      ctx->diag_swap = nullptr;
+      ctx->diag_swap_len = 0;
+      CUDA_TRY(cudaMalloc(&ctx->diag_swap, sizeof(double) * (size_t)mesh->nf));
+      ctx->diag_swap_len = (size_t)mesh->nf;
+      CUDA_TRY(cudaMemsetAsync(ctx->diag_swap, 0xFF, sizeof(double) * (size_t)mesh->nf, ctx->stream));
+    }
+    exchange = ctx->diag_swap;
+  } else {
+    void* scratch = nullptr;
+    int rc = mimpy_scratch(ctx, sizeof(double) * (size_t)mesh->nf, &scratch);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(scratch, 0xFF, sizeof(double) * (size_t)mesh->nf, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->counters + 8, 0, 2 * sizeof(unsigned int), ctx->stream));
+    exchange = (double*)scratch;
+  }
   UniArgs a;
   a.indptr = sym->indptr;
   a.pos_m = sym->pos_m;
@@ -895,7 +917,7 @@ int mimpy_numeric_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mim
   a.c_diag = c_diag;
   a.alpha = alpha;
   a.vals = vals;
-  a.diag_pub = (double*)scratch;
+  a.diag_pub = exchange;
   a.ticket = ctx->counters + 8;
   a.error_flag = ctx->counters + 9;
   a.flux_dof = sym->flux_dof;

@@ -35,6 +35,8 @@ struct mimpy_ctx {
   int sm_count;
   void* scratch;         // ctx-owned temporary storage (CUB temp, reduction partials)
   size_t scratch_bytes;
+  double* diag_swap;     // per-face exchange slots of the staged brick assembly kernel; all-sentinel
+  size_t diag_swap_len;  //   between launches (the kernel restores every slot it used)
   double* partials;      // reduction partials (device)
   unsigned int* counters;  // last-block counters (device)
   double* scalars;       // device scalars for PCG (alpha, beta, rz, ...)

@@ -68,6 +68,7 @@ int mimpy_b200_destroy(mimpy_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->diag_swap) cudaFree(ctx->diag_swap);
   cudaFree(ctx->partials);
   cudaFree(ctx->counters);
   cudaFree(ctx->scalars);
