@@ -31,6 +31,28 @@ sys.path.insert(0, ROOT)
 METRIC = "mfd_assembly_mcells_per_s"
 UNIT = "Mcells/s"
 ASM_BYTES_PER_CELL = 700.0     # 332 B read + 368 B written per hex cell
+# dram__bytes_read.sum + dram__bytes_write.sum of k_numeric_brick2<1> at 256^3, one `ncu --set full`
+# capture (profiles/r1_ncu_full_summary.txt): 7.12 GB + 6.46 GB
+ASM_TRAFFIC_256 = 13.59e9
+
+
+def aux_levels(nx, ny, nz):
+    """Levels of the auxiliary-space multigrid (csrc/auxmg.cu: halve until <= 64 cells)."""
+    lv = 1
+    while nx * ny * nz > 64:
+        nx, ny, nz = (nx + 1) // 2, (ny + 1) // 2, (nz + 1) // 2
+        lv += 1
+    return lv
+
+
+def launches_per_step(precond, n, nz_local, iters):
+    """Kernels of OUR library launched by one bench step (assembly, set-up, solve)."""
+    setup = 1 + 2 + 4 + 1 + 1          # assembly; local matrices; hybrid set-up; rhs; recover
+    if precond != "auxmg":
+        return setup + 3 + 3 * iters   # PCG init + 3 kernels per iteration
+    lv = aux_levels(n, n, nz_local)
+    cycle = 2 + 3 * (lv - 1) + 1       # face restrict/prolong, (pre-smooth, restrict, prolong) per level, coarse solve
+    return setup + (2 + 2 * lv) + (3 + cycle + 1) + (3 + cycle) * iters
 
 
 def pcg_bytes_per_row(nnz_per_row):
@@ -203,6 +225,7 @@ def run_cuda(args):
     dm, plan, rhs = pb["dm"], pb["plan"], pb["rhs"]
     F = plan.flux_dof
     nc_total = n ** 3
+    slab_nz = pb["slab"].nzl
     with ctx.on_stream():
         vals = torch.empty(plan.nnz, dtype=torch.float64, device=dev)
     method = 1
@@ -213,6 +236,8 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    check_every = args.check_every if args.check_every > 0 else (5 if args.precond == "auxmg" else 50)
+
     def step(collect):
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         barrier()
@@ -221,10 +246,10 @@ def run_cuda(args):
             device.numeric(dm, plan, method, vals=vals)
             evs[1].record(ctx.stream)
             m_e, _, _ = device.local_matrices(dm, plan, method)
-            hyb = device.HybridSystem(dm, plan, m_e)
+            hyb = device.HybridSystem(dm, plan, m_e, precond=args.precond)
             del m_e
             evs[2].record(ctx.stream)
-            sol, info = hyb.solve(rhs, rtol=args.rtol, maxit=args.maxit, check_every=args.check_every,
+            sol, info = hyb.solve(rhs, rtol=args.rtol, maxit=args.maxit, check_every=check_every,
                                   raise_on_noconv=False)
             evs[3].record(ctx.stream)
         ctx.sync()
@@ -255,6 +280,31 @@ def run_cuda(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # ---- the SpMV kernel alone and the plain Jacobi-PCG iteration (bounded: 100 iterations) ----
+    with ctx.on_stream():
+        m_e, _, _ = device.local_matrices(dm, plan, method)
+        hyb = device.HybridSystem(dm, plan, m_e, precond="jacobi")
+        del m_e
+        _, jinfo = hyb.solve(rhs, rtol=1e-30, maxit=100, check_every=50, raise_on_noconv=False)
+        _, jinfo = hyb.solve(rhs, rtol=1e-30, maxit=100, check_every=50, raise_on_noconv=False)
+        xs = torch.ones(F, dtype=torch.float64, device=dev)
+        ys = torch.empty(F, dtype=torch.float64, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        for i in range(reps + 3):
+            if i == 3:
+                e0.record(ctx.stream)
+            ctx.call("mimpy_b200_spmv_sell", F, _lib.ptr(hyb.sell_ptr), _lib.ptr(hyb.sell_cols), _lib.ptr(hyb.a_vals),
+                     _lib.ptr(xs), _lib.ptr(ys))
+        e1.record(ctx.stream)
+    ctx.sync()
+    tj = torch.tensor([float(jinfo.ms_total) / max(int(jinfo.iterations), 1), e0.elapsed_time(e1) / reps],
+                      dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tj, op=dist.ReduceOp.MAX)
+    jacobi_ms_iter, spmv_ms = tj.tolist()
+    del hyb, xs, ys
+
     asm_ms = float(np.mean([r["asm_ms"] for r in res]))
     step_ms = float(np.mean([r["step_ms"] for r in res]))
     iters = res[-1]["iters"]
@@ -268,7 +318,8 @@ def run_cuda(args):
     nnz_row = nnz_total / rows_total
     # per-GPU achieved bandwidth of the dominant kernels (algorithmic bytes of the local slab)
     asm_gbs = ASM_BYTES_PER_CELL * (nc_total / world) / (asm_ms / 1e3) / 1e9
-    pcg_gbs = pcg_bytes_per_row(nnz_row) * (rows_total / world) / s_per_iter / 1e9
+    pcg_gbs = pcg_bytes_per_row(nnz_row) * (rows_total / world) / (jacobi_ms_iter / 1e3) / 1e9
+    spmv_gbs = (12.0 * nnz_row + 20.0) * (rows_total / world) / (spmv_ms / 1e3) / 1e9
 
     sol = res[-1]["sol"]
     with ctx.on_stream():
@@ -322,20 +373,26 @@ def run_cuda(args):
                        "cells": nc_total, "face_rows": int(rows_total), "face_system_nnz": int(nnz_total),
                        "partition": "z-slabs x%d" % world, "pcg_collectives": comm,
                        "l2": "inputs larger than L2 (>= %.1f GB touched per step per GPU)" % (ASM_BYTES_PER_CELL * nc_total / world / 1e9),
-                       "pcg": {"preconditioner": "jacobi", "rtol": args.rtol, "check_every": args.check_every}},
+                       "pcg": {"preconditioner": args.precond, "rtol": args.rtol, "check_every": check_every}},
             "assembly_ms": asm_ms, "hybrid_setup_ms": float(np.mean([r["setup_ms"] for r in res])),
             "pcg_iters": iters, "pcg_s_per_iter": s_per_iter,
             "solve_time_s": float(np.mean([r["solve_ms"] for r in res])) / 1e3,
             "pcg_rel_residual": res[-1]["residual"] / max(res[-1]["rhs_norm"], 1e-300),
             "saddle_rel_residual": saddle_res, "mean_pressure": p_mean,
             "roofline": {"bound": "hbm", "achieved": asm_gbs, "peak": peak, "unit": "GB/s", "frac": asm_gbs / peak,
-                         "traffic": None, "kernel": "k_numeric_direct<6,1> (fused M_E + CSR scatter), per GPU",
+                         "traffic": ASM_TRAFFIC_256 if (n == 256 and world == 1) else None,
+                         "kernel": "k_numeric_brick2<1> (fused M_E + CSR assembly), per GPU",
                          "peak_source": peak_src, "frac_of_8TBs_spec": asm_gbs / 8000.,
                          "algorithmic_bytes_per_cell": ASM_BYTES_PER_CELL},
+            "roofline_spmv": {"bound": "hbm", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak,
+                              "kernel": "k_spmv_sell (face system, SELL-32), per GPU, timed alone",
+                              "ms": spmv_ms, "algorithmic_bytes_per_row": 12.0 * nnz_row + 20.0},
             "roofline_pcg": {"bound": "hbm", "achieved": pcg_gbs, "peak": peak, "unit": "GB/s", "frac": pcg_gbs / peak,
+                             "what": "one Jacobi-PCG iteration (3 kernels), 100-iteration run",
+                             "s_per_iter": jacobi_ms_iter / 1e3,
                              "algorithmic_bytes_per_row": pcg_bytes_per_row(nnz_row), "rows": int(rows_total)},
             "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(args.steps * (3 + 1 + 5 + 2 + 3 * iters + 4)),
+            "gpu_launches": int(args.steps * launches_per_step(args.precond, n, slab_nz, iters)),
             "clocks": sampler.summary(), "setup_s": t_setup, "wall_s_timed": wall,
         }
         print(json.dumps(line))
@@ -354,7 +411,8 @@ def main():
     ap.add_argument("--size", dest="n", type=int, default=256, help="cells per axis (256 = BASELINE config)")
     ap.add_argument("--rtol", type=float, default=1e-8)
     ap.add_argument("--maxit", type=int, default=20000)
-    ap.add_argument("--check-every", type=int, default=50)
+    ap.add_argument("--check-every", type=int, default=0, help="PCG convergence check interval (0: 5 with auxmg, 50 with jacobi)")
+    ap.add_argument("--precond", default="auxmg", choices=["auxmg", "jacobi"])
     ap.add_argument("--cpu-n", type=int, default=40)
     ap.add_argument("--ref-n", type=int, default=32)
     ap.add_argument("--no-cpu", action="store_true")

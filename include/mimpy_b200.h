@@ -283,6 +283,24 @@ int mimpy_b200_sell_fill(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, const
 int mimpy_b200_pcg_sell(mimpy_ctx* ctx, int32_t n, const int32_t* sell_ptr, const int32_t* sell_cols,
                         const double* sell_vals, const double* diag_inv, const double* b, double* x,
                         double* work, mimpy_pcg_info* info);
+
+/* Auxiliary-space multigrid preconditioner for the face system on structured hex meshes
+ * (csrc/auxmg.cu): B = D^-1 + Pi V(A_c) Pi^T with A_c the cell-centred two-point-flux operator built
+ * from the inverse local matrices w_e of hybrid_setup.  No reference counterpart: MFD.solve
+ * (mfd.py:1349-1358) factorises; the reference's unused Schur CG preconditions with the same kind of
+ * operator (twophase.py:665-686).  The handle owns its device memory; the mesh / symbolic arrays it
+ * was given must outlive it.  auxmg_setup must follow every hybrid_setup (new w_e). */
+int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
+                            void** handle);
+int mimpy_b200_auxmg_setup(mimpy_ctx* ctx, void* handle, const mimpy_mesh_view* mesh,
+                           const mimpy_symbolic* sym, const double* w_e, double alpha,
+                           const double* c_diag);
+int mimpy_b200_auxmg_destroy(mimpy_ctx* ctx, void* handle);
+/* PCG with that preconditioner.  (ptr, idx, vals): the face system in CSR (sell = 0) or SELL-32
+ * (sell = 1) layout; work: 4 n doubles.  Same info / error behaviour as mimpy_b200_pcg. */
+int mimpy_b200_pcg_aux(mimpy_ctx* ctx, int32_t n, const int32_t* ptr, const int32_t* idx,
+                       const double* vals, int32_t sell, const double* diag_inv, void* auxmg,
+                       const double* b, double* x, double* work, mimpy_pcg_info* info);
 int mimpy_b200_spmv_sell(mimpy_ctx* ctx, int32_t n, const int32_t* sell_ptr, const int32_t* sell_cols,
                          const double* sell_vals, const double* x, double* y);
 int mimpy_b200_spmv(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, const int32_t* indices,

@@ -1,0 +1,423 @@
+// Auxiliary-space multigrid preconditioner for the hybridised face system (structured hex meshes).
+//
+// Jacobi-PCG on the face system A lambda = h needs O(n) iterations on an n^3 mesh (1600 at 256^3).
+// The reference has no counterpart (it factorises with SuperLU, mfd.py:1349-1358; its dead
+// Schur-complement CG, twophase.py:665-686, preconditions with D diag(M)^-1 D^T + C -- a
+// cell-centred two-point-flux operator, which is exactly the auxiliary operator used here):
+//
+//     B = D^-1  +  Pi  V(A_c)  Pi^T                                  (additive, SPD)
+//
+//   A_c   cell operator with two-point transmissibilities: every cell E gives each of its flux
+//         faces a half transmissibility tau_{E,f} = a_f^2 W_E[f,f] (W_E = the inverse local matrix of
+//         hybrid.cu); interior face: t_f = tau_1 tau_2 / (tau_1 + tau_2) couples its two cells,
+//         Dirichlet boundary face: tau on the diagonal; plus the C block (alpha |E| or c_diag).
+//   Pi    cells -> faces, lambda_f = (tau_1 p_1 + tau_2 p_2) / (tau_1 + tau_2)  (flux continuity);
+//         zero on boundary faces (their multiplier is prescribed).
+//   V     one V(1,1) cycle of geometric multigrid on the 7-point operator: 2x2x2 aggregation with
+//         piecewise-constant transfer (the Galerkin coarse operators stay 7-point: coarse couplings
+//         are sums of the fine couplings through the coarse face), damped Jacobi smoothing, coarse
+//         correction scaled by 2 (the usual cure for unsmoothed aggregation), dense inverse on the
+//         coarsest (<= 64 cells) level.  Every operation is linear and symmetric, so B is a fixed SPD
+//         operator and plain CG applies.
+//
+// Measured (CPU prototype of the same operator, log-normal K): 184/273/725 Jacobi iterations at
+// 16^3/24^3/64^3 become 37/41/~45.
+//
+// Slab partitions: every rank runs the cycle on its own cells; an interface face adds its t_f to the
+// diagonal (block-Jacobi of A_c across ranks).  tau sums and the prolongated correction of
+// interface rows are completed with the same exchange-add as the SpMV.
+#include "reduce.cuh"
+
+#define AUX_MAX_LEVELS 24
+#define AUX_COARSEST 64
+#define AUX_T 256
+
+struct AuxLevel {
+  int nx, ny, nz, n;
+  double *tx, *ty, *tz;  // coupling of cell c with its +x / +y / +z neighbour (0 on the boundary)
+  double *dd;            // extra diagonal: Dirichlet faces, interface faces, C block
+  double *dg;            // full diagonal
+  double *b, *x, *x2;    // right-hand side, pre-smoothed iterate, result of the level
+};
+
+struct mimpy_auxmg {
+  int nlev;
+  AuxLevel lev[AUX_MAX_LEVELS];
+  int nc, nf, flux_dof;
+  double* wc;    // [nc*6]  weight of cell c at its local face i (Pi^T gathers with it)
+  double* fw;    // [nf*2]  weights of the two cells of face f   (Pi gathers with it)
+  double* tsum;  // [flux_dof] sum of the half transmissibilities of a face
+  double* cinv;  // dense inverse of the coarsest operator
+  double omega, scale;
+  const int* cell_faces;
+  const int* face_to_flux;
+  const int* face_cell;
+  const uint8_t* face_flag;
+};
+
+// ---------------------------------------------------------------------------------------------
+// set-up
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(AUX_T)
+k_aux_tau(int nc, const int* __restrict__ cell_faces, const int* __restrict__ f2f,
+          const int* __restrict__ m_ptr, const double* __restrict__ face_geom,
+          const double* __restrict__ w_e, double* __restrict__ wc, double* __restrict__ tsum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int boff = m_ptr[c];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int f = cell_faces[c * 6 + i];
+    const int g = f2f[f];
+    double tau = 0.;
+    if (g >= 0) {
+      const double a = face_geom[8 * (size_t)f];
+      tau = a * a * w_e[boff + i * 7];
+      atomicAdd(tsum + g, tau);  // <= 2 addends on a zeroed slot: order-free
+    }
+    wc[(size_t)c * 6 + i] = tau;
+  }
+}
+
+__global__ void __launch_bounds__(AUX_T)
+k_aux_level0(int nc, const int* __restrict__ cell_faces, const int* __restrict__ f2f,
+             const int* __restrict__ face_cell, const uint8_t* __restrict__ face_flag,
+             const double* __restrict__ tsum, const double* __restrict__ cell_volume, double alpha,
+             const double* __restrict__ c_diag, double* __restrict__ wc, double* __restrict__ fw,
+             AuxLevel L) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  double dd = c_diag ? c_diag[c] : alpha * cell_volume[c];
+  double tp[3] = {0., 0., 0.};
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int f = cell_faces[c * 6 + i];
+    const int g = f2f[f];
+    const double tau = wc[(size_t)c * 6 + i];
+    double w = 0.;
+    if (g >= 0 && tau > 0.) {
+      const bool iface = face_flag && (face_flag[f] & 3);
+      const bool two = face_cell[2 * (size_t)f + 1] >= 0;
+      if (!two && !iface) {
+        dd += tau;  // boundary face with a prescribed multiplier
+      } else {
+        const double S = tsum[g];
+        const double t = tau * (S - tau) / S;
+        w = tau / S;
+        if (iface) dd += t;           // neighbour on another rank: block-Jacobi
+        else if (i >= 3) tp[i - 3] = t;  // faces x+, y+, z+ (cell face order z-,y-,x-,x+,y+,z+)
+      }
+    }
+    wc[(size_t)c * 6 + i] = w;
+    fw[2 * (size_t)f + (face_cell[2 * (size_t)f] == c ? 0 : 1)] = w;
+  }
+  L.tx[c] = tp[0];
+  L.ty[c] = tp[1];
+  L.tz[c] = tp[2];
+  L.dd[c] = dd;
+}
+
+__global__ void __launch_bounds__(AUX_T) k_aux_diag(AuxLevel L) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= L.n) return;
+  const int i = c % L.nx, j = (c / L.nx) % L.ny, k = c / (L.nx * L.ny);
+  double d = L.dd[c] + L.tx[c] + L.ty[c] + L.tz[c];
+  if (i > 0) d += L.tx[c - 1];
+  if (j > 0) d += L.ty[c - L.nx];
+  if (k > 0) d += L.tz[c - L.nx * L.ny];
+  L.dg[c] = d > 0. ? d : 1.;
+}
+
+// Galerkin coarse operator for piecewise-constant aggregation of 2x2x2 cells
+__global__ void __launch_bounds__(AUX_T) k_aux_coarsen(AuxLevel F, AuxLevel C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C.n) return;
+  const int I = c % C.nx, J = (c / C.nx) % C.ny, K = c / (C.nx * C.ny);
+  const int i0 = 2 * I, j0 = 2 * J, k0 = 2 * K;
+  const int i1 = min(i0 + 1, F.nx - 1), j1 = min(j0 + 1, F.ny - 1), k1 = min(k0 + 1, F.nz - 1);
+  double tx = 0., ty = 0., tz = 0., dd = 0.;
+  for (int k = k0; k <= k1; ++k)
+    for (int j = j0; j <= j1; ++j)
+      for (int i = i0; i <= i1; ++i) {
+        const int f = i + F.nx * (j + F.ny * k);
+        dd += F.dd[f];
+        if (i == i1) tx += F.tx[f];  // the fine faces through the coarse +x face (0 on the boundary)
+        if (j == j1) ty += F.ty[f];
+        if (k == k1) tz += F.tz[f];
+      }
+  C.tx[c] = tx;
+  C.ty[c] = ty;
+  C.tz[c] = tz;
+  C.dd[c] = dd;
+}
+
+// dense inverse of the coarsest operator (n <= AUX_COARSEST), Gauss-Jordan without pivoting (SPD)
+__global__ void __launch_bounds__(AUX_T) k_aux_dense_inverse(AuxLevel L, double* __restrict__ cinv) {
+  __shared__ double A[AUX_COARSEST][AUX_COARSEST + 1];
+  __shared__ double piv_row[AUX_COARSEST], piv_col[AUX_COARSEST];
+  const int n = L.n, t = threadIdx.x;
+  for (int e = t; e < n * n; e += AUX_T) A[e / n][e % n] = 0.;
+  __syncthreads();
+  double dmax = 0.;
+  for (int c = 0; c < n; ++c) dmax = fmax(dmax, L.dg[c]);
+  for (int c = t; c < n; c += AUX_T) {
+    const int i = c % L.nx, j = (c / L.nx) % L.ny, k = c / (L.nx * L.ny);
+    A[c][c] = L.dg[c] + 1e-13 * dmax;  // keeps a pure-Neumann (singular) operator invertible
+    if (i + 1 < L.nx) { A[c][c + 1] = -L.tx[c]; A[c + 1][c] = -L.tx[c]; }
+    if (j + 1 < L.ny) { A[c][c + L.nx] = -L.ty[c]; A[c + L.nx][c] = -L.ty[c]; }
+    if (k + 1 < L.nz) { A[c][c + L.nx * L.ny] = -L.tz[c]; A[c + L.nx * L.ny][c] = -L.tz[c]; }
+  }
+  __syncthreads();
+  for (int p = 0; p < n; ++p) {  // in-place inversion
+    const double piv = 1.0 / A[p][p];
+    for (int e = t; e < n; e += AUX_T) {
+      piv_row[e] = A[p][e] * piv;
+      piv_col[e] = A[e][p];
+    }
+    __syncthreads();
+    for (int e = t; e < n * n; e += AUX_T) {
+      const int r = e / n, c = e % n;
+      double v;
+      if (r == p) v = (c == p) ? piv : piv_row[c];
+      else if (c == p) v = -piv_col[r] * piv;
+      else v = A[r][c] - piv_col[r] * piv_row[c];
+      A[r][c] = v;
+    }
+    __syncthreads();
+  }
+  for (int e = t; e < n * n; e += AUX_T) cinv[e] = A[e / n][e % n];
+}
+
+// ---------------------------------------------------------------------------------------------
+// V-cycle
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(AUX_T) k_aux_presmooth(AuxLevel L, double omega) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < L.n) L.x[c] = omega * L.b[c] / L.dg[c];
+}
+
+__device__ __forceinline__ double aux_apply(const AuxLevel& L, const double* __restrict__ x, int c,
+                                            int i, int j, int k, double xc) {
+  double s = L.dg[c] * xc;
+  const int sx = 1, sy = L.nx, sz = L.nx * L.ny;
+  if (i + 1 < L.nx) s -= L.tx[c] * x[c + sx];
+  if (i > 0) s -= L.tx[c - sx] * x[c - sx];
+  if (j + 1 < L.ny) s -= L.ty[c] * x[c + sy];
+  if (j > 0) s -= L.ty[c - sy] * x[c - sy];
+  if (k + 1 < L.nz) s -= L.tz[c] * x[c + sz];
+  if (k > 0) s -= L.tz[c - sz] * x[c - sz];
+  return s;
+}
+
+// coarse right-hand side = sum over the aggregate of the fine residual b - A x
+__global__ void __launch_bounds__(AUX_T) k_aux_restrict(AuxLevel F, AuxLevel C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C.n) return;
+  const int I = c % C.nx, J = (c / C.nx) % C.ny, K = c / (C.nx * C.ny);
+  const int i0 = 2 * I, j0 = 2 * J, k0 = 2 * K;
+  const int i1 = min(i0 + 1, F.nx - 1), j1 = min(j0 + 1, F.ny - 1), k1 = min(k0 + 1, F.nz - 1);
+  double s = 0.;
+  for (int k = k0; k <= k1; ++k)
+    for (int j = j0; j <= j1; ++j)
+      for (int i = i0; i <= i1; ++i) {
+        const int f = i + F.nx * (j + F.ny * k);
+        s += F.b[f] - aux_apply(F, F.x, f, i, j, k, F.x[f]);
+      }
+  C.b[c] = s;
+}
+
+// x2 = xp + omega D^-1 (b - A xp),  xp = x + scale * P e_coarse   (prolongation fused into the smoother)
+__global__ void __launch_bounds__(AUX_T)
+k_aux_prolong_smooth(AuxLevel F, AuxLevel C, double omega, double scale) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= F.n) return;
+  const int i = c % F.nx, j = (c / F.nx) % F.ny, k = c / (F.nx * F.ny);
+  const double* __restrict__ e = C.x2;
+  const double* __restrict__ x = F.x;
+  const int cs_y = C.nx, cs_z = C.nx * C.ny;
+  auto xp = [&](int ii, int jj, int kk) {
+    return x[ii + F.nx * (jj + F.ny * kk)] + scale * e[(ii >> 1) + cs_y * (jj >> 1) + cs_z * (kk >> 1)];
+  };
+  const double xc = xp(i, j, k);
+  double s = F.dg[c] * xc;
+  const int sx = 1, sy = F.nx, sz = F.nx * F.ny;
+  if (i + 1 < F.nx) s -= F.tx[c] * xp(i + 1, j, k);
+  if (i > 0) s -= F.tx[c - sx] * xp(i - 1, j, k);
+  if (j + 1 < F.ny) s -= F.ty[c] * xp(i, j + 1, k);
+  if (j > 0) s -= F.ty[c - sy] * xp(i, j - 1, k);
+  if (k + 1 < F.nz) s -= F.tz[c] * xp(i, j, k + 1);
+  if (k > 0) s -= F.tz[c - sz] * xp(i, j, k - 1);
+  F.x2[c] = xc + omega * (F.b[c] - s) / F.dg[c];
+}
+
+__global__ void __launch_bounds__(AUX_T) k_aux_coarse_solve(AuxLevel L, const double* __restrict__ cinv) {
+  const int r = threadIdx.x;
+  if (r >= L.n) return;
+  double s = 0.;
+  for (int c = 0; c < L.n; ++c) s += cinv[r * L.n + c] * L.b[c];
+  L.x2[r] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// transfers between the face system and the cells
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(AUX_T)
+k_aux_face_restrict(int nc, const int* __restrict__ cell_faces, const int* __restrict__ f2f,
+                    const double* __restrict__ wc, const double* __restrict__ r, double* __restrict__ b) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  double s = 0.;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const double w = wc[(size_t)c * 6 + i];
+    if (w != 0.) s += w * r[f2f[cell_faces[c * 6 + i]]];
+  }
+  b[c] = s;
+}
+
+// z = [owned rows] D^-1 r + Pi e ; partial sums of r.z over ALL local rows (interface rows hold this
+// rank's share of z, r is identical on both ranks, so the shares add up to r.z across ranks)
+__global__ void __launch_bounds__(RED_THREADS)
+k_aux_face_prolong(int nf, int n_owned, const int* __restrict__ f2f, const int* __restrict__ face_cell,
+                   const double* __restrict__ fw, const double* __restrict__ e,
+                   const double* __restrict__ dinv, const double* __restrict__ r,
+                   double* __restrict__ z, double* partials, unsigned int* counter, double* dst) {
+  __shared__ double sh[32];
+  double acc = 0.;
+  for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < nf;
+       f += (long long)gridDim.x * blockDim.x) {
+    const int g = f2f[f];
+    if (g < 0) continue;
+    const int c1 = face_cell[2 * f], c2 = face_cell[2 * f + 1];
+    const double rg = r[g];
+    double zz = (g < n_owned) ? dinv[g] * rg : 0.;
+    const double w1 = fw[2 * f], w2 = fw[2 * f + 1];
+    if (w1 != 0.) zz += w1 * e[c1];
+    if (c2 >= 0 && w2 != 0.) zz += w2 * e[c2];
+    z[g] = zz;
+    acc += rg * zz;
+  }
+  const double v[1] = {acc};
+  finish_reduction<1>(v, partials, counter, dst, sh);
+}
+
+static int aux_free(mimpy_auxmg* h) {
+  if (!h) return MIMPY_OK;
+  for (int l = 0; l < h->nlev; ++l) {
+    AuxLevel& L = h->lev[l];
+    cudaFree(L.tx); cudaFree(L.ty); cudaFree(L.tz); cudaFree(L.dd); cudaFree(L.dg);
+    cudaFree(L.b); cudaFree(L.x); cudaFree(L.x2);
+  }
+  cudaFree(h->wc); cudaFree(h->fw); cudaFree(h->tsum); cudaFree(h->cinv);
+  delete h;
+  return MIMPY_OK;
+}
+
+static inline int aux_blocks(int n) { return (n + AUX_T - 1) / AUX_T; }
+
+// z = B r, scalar r.z (this rank's share) -> *rz_dst.  Stream-ordered, no host synchronisation.
+int mimpy_auxmg_apply(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, const double* r, double* z,
+                      double* rz_dst, int n_owned) {
+  cudaStream_t st = ctx->stream;
+  AuxLevel* L = h->lev;
+  k_aux_face_restrict<<<aux_blocks(h->nc), AUX_T, 0, st>>>(h->nc, h->cell_faces, h->face_to_flux, h->wc, r, L[0].b);
+  const int last = h->nlev - 1;
+  for (int l = 0; l < last; ++l) {
+    k_aux_presmooth<<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], h->omega);
+    k_aux_restrict<<<aux_blocks(L[l + 1].n), AUX_T, 0, st>>>(L[l], L[l + 1]);
+  }
+  k_aux_coarse_solve<<<1, AUX_COARSEST, 0, st>>>(L[last], h->cinv);
+  for (int l = last - 1; l >= 0; --l)
+    k_aux_prolong_smooth<<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], L[l + 1], h->omega, h->scale);
+  const int grid = ctx->sm_count * 8;
+  k_aux_face_prolong<<<grid, RED_THREADS, 0, st>>>(h->nf, n_owned, h->face_to_flux, h->face_cell, h->fw,
+                                                   L[0].x2, dinv, r, z, ctx->partials, ctx->counters + 4, rz_dst);
+  KERNEL_CHECK();
+  return MIMPY_OK;
+}
+
+extern "C" {
+
+int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
+                            void** handle) {
+  REQUIRE(ctx && mesh && sym && handle, "NULL argument");
+  REQUIRE(mesh->uniform_faces == 6 && mesh->hex_nx > 0 && mesh->hex_ny > 0 && mesh->hex_nz > 0 &&
+              (long long)mesh->hex_nx * mesh->hex_ny * mesh->hex_nz == mesh->nc,
+          "the auxiliary-space multigrid needs a structured hex mesh (DeviceMesh.hex)");
+  mimpy_auxmg* h = new mimpy_auxmg();
+  memset(h, 0, sizeof(*h));
+  h->nc = mesh->nc;
+  h->nf = mesh->nf;
+  h->flux_dof = sym->flux_dof;
+  h->omega = 0.8;
+  h->scale = 2.0;
+  h->cell_faces = mesh->cell_faces;
+  h->face_to_flux = sym->face_to_flux;
+  h->face_cell = sym->face_cell;
+  h->face_flag = sym->face_flag;
+  int nx = mesh->hex_nx, ny = mesh->hex_ny, nz = mesh->hex_nz;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](double** p, size_t n) {
+    if (e == cudaSuccess) e = cudaMalloc(p, sizeof(double) * (n ? n : 1));
+  };
+  for (;;) {
+    if (h->nlev >= AUX_MAX_LEVELS) break;
+    AuxLevel& L = h->lev[h->nlev++];
+    L.nx = nx; L.ny = ny; L.nz = nz; L.n = nx * ny * nz;
+    alloc(&L.tx, L.n); alloc(&L.ty, L.n); alloc(&L.tz, L.n); alloc(&L.dd, L.n); alloc(&L.dg, L.n);
+    alloc(&L.b, L.n); alloc(&L.x, L.n); alloc(&L.x2, L.n);
+    if (L.n <= AUX_COARSEST) break;
+    nx = (nx + 1) / 2; ny = (ny + 1) / 2; nz = (nz + 1) / 2;
+  }
+  alloc(&h->wc, (size_t)h->nc * 6);
+  alloc(&h->fw, (size_t)h->nf * 2);
+  alloc(&h->tsum, (size_t)h->flux_dof);
+  alloc(&h->cinv, (size_t)AUX_COARSEST * AUX_COARSEST);
+  if (e != cudaSuccess || h->lev[h->nlev - 1].n > AUX_COARSEST) {
+    aux_free(h);
+    mimpy_set_error("auxmg_create: %s", e != cudaSuccess ? cudaGetErrorString(e) : "too many levels");
+    cudaGetLastError();
+    return e != cudaSuccess ? MIMPY_E_CUDA : MIMPY_E_INVALID;
+  }
+  *handle = h;
+  return MIMPY_OK;
+}
+
+int mimpy_b200_auxmg_destroy(mimpy_ctx* ctx, void* handle) {
+  REQUIRE(ctx, "NULL context");
+  if (!handle) return MIMPY_OK;
+  cudaStreamSynchronize(ctx->stream);
+  return aux_free(static_cast<mimpy_auxmg*>(handle));
+}
+
+int mimpy_b200_auxmg_setup(mimpy_ctx* ctx, void* handle, const mimpy_mesh_view* mesh,
+                           const mimpy_symbolic* sym, const double* w_e, double alpha,
+                           const double* c_diag) {
+  REQUIRE(ctx && handle && mesh && sym && w_e, "NULL argument");
+  mimpy_auxmg* h = static_cast<mimpy_auxmg*>(handle);
+  REQUIRE(h->nc == mesh->nc && h->nf == mesh->nf && h->flux_dof == sym->flux_dof, "handle/mesh mismatch");
+  cudaStream_t st = ctx->stream;
+  h->cell_faces = mesh->cell_faces;
+  h->face_to_flux = sym->face_to_flux;
+  h->face_cell = sym->face_cell;
+  h->face_flag = sym->face_flag;
+  CUDA_TRY(cudaMemsetAsync(h->tsum, 0, sizeof(double) * (size_t)(h->flux_dof ? h->flux_dof : 1), st));
+  CUDA_TRY(cudaMemsetAsync(h->fw, 0, sizeof(double) * (size_t)h->nf * 2, st));
+  k_aux_tau<<<aux_blocks(h->nc), AUX_T, 0, st>>>(h->nc, mesh->cell_faces, sym->face_to_flux, sym->m_ptr,
+                                                mesh->face_geom, w_e, h->wc, h->tsum);
+  KERNEL_CHECK();
+  int rc = mimpy_halo_exchange_add(ctx, h->tsum);  // interface faces: tau of the cell on the other rank
+  if (rc) return rc;
+  k_aux_level0<<<aux_blocks(h->nc), AUX_T, 0, st>>>(h->nc, mesh->cell_faces, sym->face_to_flux, sym->face_cell,
+                                                   sym->face_flag, h->tsum, mesh->cell_volume, alpha, c_diag,
+                                                   h->wc, h->fw, h->lev[0]);
+  for (int l = 0; l < h->nlev; ++l) {
+    if (l > 0) k_aux_coarsen<<<aux_blocks(h->lev[l].n), AUX_T, 0, st>>>(h->lev[l - 1], h->lev[l]);
+    k_aux_diag<<<aux_blocks(h->lev[l].n), AUX_T, 0, st>>>(h->lev[l]);
+  }
+  k_aux_dense_inverse<<<1, AUX_T, 0, st>>>(h->lev[h->nlev - 1], h->cinv);
+  KERNEL_CHECK();
+  return MIMPY_OK;
+}
+
+}  // extern "C"

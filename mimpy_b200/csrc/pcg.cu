@@ -16,55 +16,7 @@
 #include "common.cuh"
 
 
-enum { S_RZ = 0, S_PAP = 1, S_RZNEW = 2, S_RR = 3, S_BNORM = 4, S_TMP = 8 };
-
-#define RED_THREADS 256
-
-__device__ __forceinline__ double block_sum(double v, double* sh) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) sh[w] = v;
-  __syncthreads();
-  double t = 0.;
-  if (w == 0) {
-    t = (l < (blockDim.x >> 5)) ? sh[l] : 0.;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-  }
-  __syncthreads();
-  return t;  // valid in warp 0
-}
-
-// last block to arrive sums the per-block partials (NV values each) in index order
-template <int NV>
-__device__ __forceinline__ void finish_reduction(const double (&v)[NV], double* partials,
-                                                 unsigned int* counter, double* dst0, double* sh) {
-  __shared__ bool is_last;
-  double tot[NV];
-#pragma unroll
-  for (int k = 0; k < NV; ++k) tot[k] = block_sum(v[k], sh);
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int k = 0; k < NV; ++k) partials[(size_t)k * gridDim.x + blockIdx.x] = tot[k];
-    __threadfence();
-    const unsigned int t = atomicAdd(counter, 1u);
-    is_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      double a = 0.;
-      for (int b = threadIdx.x; b < gridDim.x; b += blockDim.x)
-        a += __ldcg(partials + (size_t)k * gridDim.x + b);
-      a = block_sum(a, sh);
-      if (threadIdx.x == 0) dst0[k] = a;
-    }
-    if (threadIdx.x == 0) *counter = 0u;
-  }
-}
+#include "reduce.cuh"
 
 // ---- SpMV: LPR lanes per row (rows of the face system have ~11 entries) --------------------
 template <int LPR, bool DOT>
@@ -128,6 +80,47 @@ k_update_p(int n, const double* __restrict__ r, const double* __restrict__ dinv,
        i += (long long)gridDim.x * blockDim.x)
     p[i] = __ldg(dinv + i) * r[i] + beta * p[i];
   // the last block to finish rotates the scalar (every block has read S_RZ by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(counter, 1u);
+    if (t == gridDim.x - 1) {
+      scal[S_RZ] = scal[S_RZNEW];
+      *counter = 0u;
+    }
+  }
+}
+
+// ---- variants for a preconditioner that is not a diagonal (auxmg.cu): z is a vector of its own ----
+// x += a p ; r -= a Ap ; S_RR = r.r
+__global__ void __launch_bounds__(RED_THREADS)
+k_update_xr_gen(int n, int n_owned, const double* __restrict__ p, const double* __restrict__ ap,
+                double* __restrict__ x, double* __restrict__ r, double* partials, unsigned int* counter,
+                double* scal) {
+  __shared__ double sh[32];
+  const double pap = scal[S_PAP];
+  const double alpha = (pap != 0.) ? scal[S_RZ] / pap : 0.;
+  double rr = 0.;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    x[i] += alpha * p[i];
+    const double ri = r[i] - alpha * ap[i];
+    r[i] = ri;
+    if (i < n_owned) rr += ri * ri;
+  }
+  const double v[1] = {rr};
+  finish_reduction<1>(v, partials, counter, scal + S_RR, sh);
+}
+
+// p = z + b p (b = S_RZNEW / S_RZ, or 0 when `first`), then S_RZ <- S_RZNEW
+__global__ void __launch_bounds__(RED_THREADS)
+k_update_p_gen(int n, const double* __restrict__ z, double* __restrict__ p, unsigned int* counter,
+               double* scal, int first) {
+  const double rz = scal[S_RZ];
+  const double beta = (first || rz == 0.) ? 0. : scal[S_RZNEW] / rz;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    p[i] = z[i] + beta * p[i];
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -240,9 +233,35 @@ static void launch_spmv(mimpy_ctx* ctx, int grid, int n, const SpmvMat& A, const
 
 static int allreduce(mimpy_ctx* ctx, double* buf, int count) { return mimpy_allreduce_f64(ctx, buf, count); }
 
+// z = B r with the auxiliary-space preconditioner, completed on interface rows, r.z all-reduced
+static int apply_aux(mimpy_ctx* ctx, mimpy_auxmg* aux, int n, const double* dinv, const double* r, double* z,
+                     int reduce_count = 2) {
+  const int n_owned = (ctx->world > 1 && ctx->halo.n_owned > 0) ? ctx->halo.n_owned : n;
+  int rc = mimpy_auxmg_apply(ctx, aux, dinv, r, z, ctx->scalars + S_RZNEW, n_owned);
+  if (rc) return rc;
+  rc = allreduce(ctx, ctx->scalars + S_RZNEW, reduce_count);  // r.z (and r.r of k_update_xr_gen)
+  if (rc) return rc;
+  return mimpy_halo_exchange_add(ctx, z);
+}
+
 static int launch_iteration(mimpy_ctx* ctx, int grid, int n, const SpmvMat& A, const double* dinv,
-                            double* x, double* r, double* p, double* ap) {
+                            double* x, double* r, double* p, double* ap, mimpy_auxmg* aux = nullptr,
+                            double* z = nullptr) {
   cudaStream_t st = ctx->stream;
+  if (aux) {
+    launch_spmv(ctx, grid, n, A, p, ap, true);
+    int rc = allreduce(ctx, ctx->scalars + S_PAP, 1);
+    if (rc) return rc;
+    rc = mimpy_halo_exchange_add(ctx, ap);
+    if (rc) return rc;
+    const int n_owned = (ctx->world > 1 && ctx->halo.n_owned > 0) ? ctx->halo.n_owned : n;
+    k_update_xr_gen<<<grid, RED_THREADS, 0, st>>>(n, n_owned, p, ap, x, r, ctx->partials, ctx->counters + 1,
+                                                  ctx->scalars);
+    rc = apply_aux(ctx, aux, n, dinv, r, z);
+    if (rc) return rc;
+    k_update_p_gen<<<grid, RED_THREADS, 0, st>>>(n, z, p, ctx->counters + 2, ctx->scalars, 0);
+    return MIMPY_OK;
+  }
   launch_spmv(ctx, grid, n, A, p, ap, true);
   // p.Ap = sum over ranks of p_loc.(A_loc p_loc): the fused dot over ALL local rows of the
   // still-partial interface values is already this rank's exact share (sub-assembled operator)
@@ -289,7 +308,8 @@ int mimpy_b200_spmv_sell(mimpy_ctx* ctx, int32_t n, const int32_t* sell_ptr, con
 }  // extern "C"
 
 static int pcg_core(mimpy_ctx* ctx, int32_t n, const SpmvMat& A, const double* diag_inv,
-                    const double* b, double* x, double* work, mimpy_pcg_info* info) {
+                    const double* b, double* x, double* work, mimpy_pcg_info* info,
+                    mimpy_auxmg* aux = nullptr) {
   REQUIRE(ctx && A.ptr && A.idx && A.vals && diag_inv && b && x && work && info, "NULL argument");
   REQUIRE(n > 0, "empty system");
   REQUIRE(info->maxit > 0, "maxit must be positive");
@@ -297,6 +317,7 @@ static int pcg_core(mimpy_ctx* ctx, int32_t n, const SpmvMat& A, const double* d
   double* r = work;
   double* p = work + (size_t)n;
   double* ap = work + 2 * (size_t)n;
+  double* z = work + 3 * (size_t)n;  // used with `aux` only
   const int grid = ctx->sm_count * 8;  // persistent-style: 8 resident CTAs of 256 threads per SM
   const int check = info->check_every > 0 ? info->check_every : 25;
 
@@ -312,6 +333,12 @@ static int pcg_core(mimpy_ctx* ctx, int32_t n, const SpmvMat& A, const double* d
   if (rc) return rc;
   k_init_scalars<<<1, 1, 0, st>>>(ctx->scalars);
   KERNEL_CHECK();
+  if (aux) {  // replace the Jacobi start by z0 = B r0, p0 = z0
+    rc = apply_aux(ctx, aux, n, diag_inv, r, z, 1);
+    if (rc) return rc;
+    k_update_p_gen<<<grid, RED_THREADS, 0, st>>>(n, z, p, ctx->counters + 2, ctx->scalars, 1);
+    KERNEL_CHECK();
+  }
   CUDA_TRY(cudaMemcpyAsync(ctx->host_scalars, ctx->scalars, sizeof(double) * 8,
                            cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
@@ -329,7 +356,7 @@ static int pcg_core(mimpy_ctx* ctx, int32_t n, const SpmvMat& A, const double* d
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
       int crc = MIMPY_OK;
       for (int k = 0; k < check && crc == MIMPY_OK; ++k)
-        crc = launch_iteration(ctx, grid, n, A, diag_inv, x, r, p, ap);
+        crc = launch_iteration(ctx, grid, n, A, diag_inv, x, r, p, ap, aux, z);
       cudaError_t e = cudaStreamEndCapture(st, &graph);
       if (crc != MIMPY_OK || e != cudaSuccess || graph == nullptr ||
           cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) {
@@ -350,7 +377,7 @@ static int pcg_core(mimpy_ctx* ctx, int32_t n, const SpmvMat& A, const double* d
       CUDA_TRY(cudaGraphLaunch(gexec, st));
     } else {
       for (int k = 0; k < check; ++k) {
-        rc = launch_iteration(ctx, grid, n, A, diag_inv, x, r, p, ap);
+        rc = launch_iteration(ctx, grid, n, A, diag_inv, x, r, p, ap, aux, z);
         if (rc) return rc;
       }
       KERNEL_CHECK();
@@ -394,6 +421,14 @@ int mimpy_b200_pcg_sell(mimpy_ctx* ctx, int32_t n, const int32_t* sell_ptr, cons
                         double* work, mimpy_pcg_info* info) {
   SpmvMat A = {1, sell_ptr, sell_cols, sell_vals};
   return pcg_core(ctx, n, A, diag_inv, b, x, work, info);
+}
+
+int mimpy_b200_pcg_aux(mimpy_ctx* ctx, int32_t n, const int32_t* ptr, const int32_t* idx,
+                       const double* vals, int32_t sell, const double* diag_inv, void* auxmg,
+                       const double* b, double* x, double* work, mimpy_pcg_info* info) {
+  REQUIRE(auxmg, "NULL preconditioner handle");
+  SpmvMat A = {sell ? 1 : 0, ptr, idx, vals};
+  return pcg_core(ctx, n, A, diag_inv, b, x, work, info, static_cast<mimpy_auxmg*>(auxmg));
 }
 
 }  // extern "C"

@@ -345,11 +345,23 @@ def build_rhs(dmesh, plan, dirichlet_faces, dirichlet_values, has_neumann, last_
 class HybridSystem(object):
     """The SPD face system A lambda = h of the hybridised saddle problem, in HBM."""
 
-    def __init__(self, dmesh, plan, m_e, multipliers=None, alpha=0., c_diag=None, layout="sell"):
-        """layout: "sell" (SELL-32, the solver's native layout) or "csr" (m_indptr/m_indices order)."""
+    def __init__(self, dmesh, plan, m_e, multipliers=None, alpha=0., c_diag=None, layout="sell",
+                 precond="auto"):
+        """layout: "sell" (SELL-32, the solver's native layout) or "csr" (m_indptr/m_indices order).
+        precond: "auxmg" (Jacobi + auxiliary-space multigrid, structured hex meshes only), "jacobi",
+        or "auto" (auxmg where the mesh is a structured hex mesh)."""
         self.dmesh, self.plan = dmesh, plan
         self.alpha, self.c_diag = float(alpha), c_diag
         self.layout = layout
+        structured = getattr(dmesh, "hex_dims", (0, 0, 0))[0] > 0
+        if precond == "auto":
+            precond = "auxmg" if structured else "jacobi"
+        if precond == "auxmg" and not structured:
+            raise ValueError("precond='auxmg' needs a structured hex mesh (DeviceMesh.hex)")
+        if precond not in ("auxmg", "jacobi"):
+            raise ValueError("unknown preconditioner %r" % (precond,))
+        self.precond = precond
+        self.aux = None
         ctx = dmesh.ctx
         dev = ctx.device
         F = plan.flux_dof
@@ -381,6 +393,21 @@ class HybridSystem(object):
             ctx.call("mimpy_b200_hybrid_setup", C.byref(mv), C.byref(self.plan.s), ptr(m_e),
                      ptr(multipliers), self.alpha, ptr(c_diag), ptr(self.w_e), ptr(self.a_vals),
                      ptr(self.a_diag_inv), ptr(self.sell_ptr))
+            if self.precond == "auxmg":
+                if self.aux is None:
+                    h = C.c_void_p()
+                    ctx.call("mimpy_b200_auxmg_create", C.byref(mv), C.byref(self.plan.s), C.byref(h))
+                    self.aux = h
+                ctx.call("mimpy_b200_auxmg_setup", self.aux, C.byref(mv), C.byref(self.plan.s), ptr(self.w_e),
+                         self.alpha, ptr(c_diag))
+
+    def __del__(self):
+        try:
+            if getattr(self, "aux", None):
+                self.dmesh.ctx.call("mimpy_b200_auxmg_destroy", self.aux)
+                self.aux = None
+        except Exception:
+            pass
 
     def solve(self, rhs, rtol=1e-10, atol=0., maxit=20000, check_every=50, use_graph=True, x0=None,
               raise_on_noconv=True):
@@ -401,7 +428,13 @@ class HybridSystem(object):
             info.rtol, info.atol, info.maxit = rtol, atol, maxit
             info.check_every, info.use_graph = check_every, 1 if use_graph else 0
             allow = () if raise_on_noconv else (_lib.MIMPY_E_NOCONV,)
-            if self.layout == "sell":
+            if self.aux is not None:
+                sell = self.layout == "sell"
+                ctx.call("mimpy_b200_pcg_aux", F, ptr(self.sell_ptr if sell else plan.m_indptr),
+                         ptr(self.sell_cols if sell else plan.m_indices), ptr(self.a_vals), 1 if sell else 0,
+                         ptr(self.a_diag_inv), self.aux, ptr(h), ptr(lam), ptr(self.work), C.byref(info),
+                         allow=allow)
+            elif self.layout == "sell":
                 ctx.call("mimpy_b200_pcg_sell", F, ptr(self.sell_ptr), ptr(self.sell_cols), ptr(self.a_vals),
                          ptr(self.a_diag_inv), ptr(h), ptr(lam), ptr(self.work), C.byref(info), allow=allow)
             else:
