@@ -20,8 +20,9 @@
 //         coarsest (<= 64 cells) level.  Every operation is linear and symmetric, so B is a fixed SPD
 //         operator and plain CG applies.
 //
-// Measured (CPU prototype of the same operator, log-normal K): 184/273/725 Jacobi iterations at
-// 16^3/24^3/64^3 become 37/41/~45.
+// Measured on B200 (log-normal K, rtol 1e-8, scripts/exp_precond.py): 200/600/1050/1600 Jacobi
+// iterations at 16^3/64^3/128^3/256^3 become 35/40/45/45; with an exact solve of A_c instead of the
+// V-cycle a CPU prototype needs 37-42, so the cycle is as good as the auxiliary space allows.
 //
 // Slab partitions: every rank runs the cycle on its own cells; an interface face adds its t_f to the
 // diagonal (block-Jacobi of A_c across ranks).  tau sums and the prolongated correction of
@@ -48,6 +49,7 @@ struct mimpy_auxmg {
   double* fw;    // [nf*2]  weights of the two cells of face f   (Pi gathers with it)
   double* tsum;  // [flux_dof] sum of the half transmissibilities of a face
   double* cinv;  // dense inverse of the coarsest operator
+  double* slab;  // the one stream-ordered allocation all arrays above are carved from
   double omega, scale;
   const int* cell_faces;
   const int* face_to_flux;
@@ -301,14 +303,9 @@ k_aux_face_prolong(int nf, int n_owned, const int* __restrict__ f2f, const int* 
   finish_reduction<1>(v, partials, counter, dst, sh);
 }
 
-static int aux_free(mimpy_auxmg* h) {
+static int aux_free(mimpy_ctx* ctx, mimpy_auxmg* h) {
   if (!h) return MIMPY_OK;
-  for (int l = 0; l < h->nlev; ++l) {
-    AuxLevel& L = h->lev[l];
-    cudaFree(L.tx); cudaFree(L.ty); cudaFree(L.tz); cudaFree(L.dd); cudaFree(L.dg);
-    cudaFree(L.b); cudaFree(L.x); cudaFree(L.x2);
-  }
-  cudaFree(h->wc); cudaFree(h->fw); cudaFree(h->tsum); cudaFree(h->cinv);
+  if (h->slab) cudaFreeAsync(h->slab, ctx->stream);  // stream-ordered: no device synchronisation
   delete h;
   return MIMPY_OK;
 }
@@ -356,29 +353,51 @@ int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
   h->face_cell = sym->face_cell;
   h->face_flag = sym->face_flag;
   int nx = mesh->hex_nx, ny = mesh->hex_ny, nz = mesh->hex_nz;
-  cudaError_t e = cudaSuccess;
-  auto alloc = [&](double** p, size_t n) {
-    if (e == cudaSuccess) e = cudaMalloc(p, sizeof(double) * (n ? n : 1));
-  };
+  size_t total = 0;
+  auto pad = [](size_t n) { return (n + 31) & ~(size_t)31; };  // keep every array 256-byte aligned
   for (;;) {
     if (h->nlev >= AUX_MAX_LEVELS) break;
     AuxLevel& L = h->lev[h->nlev++];
     L.nx = nx; L.ny = ny; L.nz = nz; L.n = nx * ny * nz;
-    alloc(&L.tx, L.n); alloc(&L.ty, L.n); alloc(&L.tz, L.n); alloc(&L.dd, L.n); alloc(&L.dg, L.n);
-    alloc(&L.b, L.n); alloc(&L.x, L.n); alloc(&L.x2, L.n);
+    total += 8 * pad((size_t)L.n);
     if (L.n <= AUX_COARSEST) break;
     nx = (nx + 1) / 2; ny = (ny + 1) / 2; nz = (nz + 1) / 2;
   }
-  alloc(&h->wc, (size_t)h->nc * 6);
-  alloc(&h->fw, (size_t)h->nf * 2);
-  alloc(&h->tsum, (size_t)h->flux_dof);
-  alloc(&h->cinv, (size_t)AUX_COARSEST * AUX_COARSEST);
-  if (e != cudaSuccess || h->lev[h->nlev - 1].n > AUX_COARSEST) {
-    aux_free(h);
-    mimpy_set_error("auxmg_create: %s", e != cudaSuccess ? cudaGetErrorString(e) : "too many levels");
-    cudaGetLastError();
-    return e != cudaSuccess ? MIMPY_E_CUDA : MIMPY_E_INVALID;
+  if (h->lev[h->nlev - 1].n > AUX_COARSEST) {
+    delete h;
+    mimpy_set_error("auxmg_create: too many levels");
+    return MIMPY_E_INVALID;
   }
+  total += pad((size_t)h->nc * 6) + pad((size_t)h->nf * 2) + pad((size_t)h->flux_dof) +
+           pad((size_t)AUX_COARSEST * AUX_COARSEST);
+  static bool pool_configured = false;
+  if (!pool_configured) {  // keep freed blocks in the pool: set-up is repeated every Newton step
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    pool_configured = true;
+  }
+  cudaError_t e = cudaMallocAsync(&h->slab, sizeof(double) * total, ctx->stream);
+  if (e != cudaSuccess) {
+    delete h;
+    mimpy_set_error("auxmg_create: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return MIMPY_E_CUDA;
+  }
+  double* cur = h->slab;
+  auto take = [&](size_t n) { double* p = cur; cur += pad(n); return p; };
+  for (int l = 0; l < h->nlev; ++l) {
+    AuxLevel& L = h->lev[l];
+    L.tx = take(L.n); L.ty = take(L.n); L.tz = take(L.n); L.dd = take(L.n); L.dg = take(L.n);
+    L.b = take(L.n); L.x = take(L.n); L.x2 = take(L.n);
+  }
+  h->wc = take((size_t)h->nc * 6);
+  h->fw = take((size_t)h->nf * 2);
+  h->tsum = take((size_t)h->flux_dof);
+  h->cinv = take((size_t)AUX_COARSEST * AUX_COARSEST);
   *handle = h;
   return MIMPY_OK;
 }
@@ -386,8 +405,7 @@ int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
 int mimpy_b200_auxmg_destroy(mimpy_ctx* ctx, void* handle) {
   REQUIRE(ctx, "NULL context");
   if (!handle) return MIMPY_OK;
-  cudaStreamSynchronize(ctx->stream);
-  return aux_free(static_cast<mimpy_auxmg*>(handle));
+  return aux_free(ctx, static_cast<mimpy_auxmg*>(handle));
 }
 
 int mimpy_b200_auxmg_setup(mimpy_ctx* ctx, void* handle, const mimpy_mesh_view* mesh,
