@@ -148,6 +148,9 @@ def run_reference(args):
             times.append(dt)
     per = float(np.mean(times))
     value = cells / per / 1e6
+    # the reference's solve (SuperLU spsolve, mfd.py:1349-1358) on a smaller sample: 356 s at 30^3
+    # (SURVEY 6), super-linear, so n = ref_solve_n keeps the whole arm within a few minutes
+    _, _, f = cpu_assembly_sample(args.ref_solve_n)
     t0 = time.perf_counter()
     f.solve()
     t_solve = time.perf_counter() - t0
@@ -161,7 +164,8 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                          "host_cores_available": os.cpu_count(),
                          "note": "the reference is single-threaded Python (per-cell NumPy/LAPACK calls); 1 core is all it can use",
-                         "spsolve_s": t_solve, "spsolve_dof": int(f.flux_dof + f.o.nc)},
+                         "spsolve_s": t_solve, "spsolve_dof": int(f.flux_dof + f.o.nc),
+                         "spsolve_sample": "%d^3 cells" % args.ref_solve_n},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -415,6 +419,7 @@ def main():
     ap.add_argument("--precond", default="auxmg", choices=["auxmg", "jacobi"])
     ap.add_argument("--cpu-n", type=int, default=40)
     ap.add_argument("--ref-n", type=int, default=32)
+    ap.add_argument("--ref-solve-n", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
