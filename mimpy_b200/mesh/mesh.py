@@ -756,6 +756,23 @@ class Mesh(object):
         return new_cell
 
     # ---- SoA export ---------------------------------------------------------------------------------
+    # ---- on-disk formats (mesh.py:584-949, 1985-2087) -> meshio.py --------------------------------
+    def load_mesh(self, input_file):
+        from . import meshio
+        meshio.load_mesh(self, input_file)
+
+    def save_mesh(self, output_file):
+        from . import meshio
+        meshio.save_mesh(self, output_file)
+
+    def output_vtk_mesh(self, file_name, cell_values=[], cell_value_labels=[]):
+        from . import meshio
+        meshio.output_vtk_mesh(self, file_name, cell_values, cell_value_labels)
+
+    def output_vtk_faces(self, file_name, face_indices, face_values=[], face_value_labels=[]):
+        from . import meshio
+        meshio.output_vtk_faces(self, file_name, face_indices, face_values, face_value_labels)
+
     def to_device(self, ctx=None):
         """Gathers the mesh into SoA device arrays (cached until the mesh is modified)."""
         from .. import _lib, device

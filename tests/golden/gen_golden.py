@@ -276,6 +276,30 @@ def main():
     d["porosities"] = np.linspace(.1, .3, nc)
     save("singlephase_543", d)
 
+    # ---- 8. `.mms` file written by the reference's Mesh.save_mesh (mesh.py:811-949) ---------
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
+    if not only or "mms_cut_232" in only:
+        ktab = spd_tensors(12, 9, full=True)
+        mesh = ref_hex(ref, 2, 3, 2, (1., 1.5, 1.), ktab)
+        for va in (mesh.faces, mesh.cells, mesh.cell_normal_orientation):
+            va.set_data_capacity(40 * len(va.data) + 1000)
+            va.set_pointer_capacity(8 * len(va.pointers) + 1000)
+        mesh.divide_cell_by_plane(4, np.array(mesh.get_cell_real_centroid(4)), nrm)
+        mesh.add_internal_no_flow(int(mesh.get_cell(0)[3]), 1)
+        mesh.set_forcing_pointer(2, [int(mesh.get_cell(7)[0])], [1])
+        path = os.path.join(OUT, "ref_mms_cut_232.mms")
+        mesh.save_mesh(open(path, "wb"))
+        import gzip
+        import shutil
+        with open(path, "rb") as src, gzip.GzipFile(path + ".gz", "wb", mtime=0) as dst:
+            shutil.copyfileobj(src, dst)  # the pre-sized ragged arrays are written in full: mostly zeros
+        os.remove(path)
+        path += ".gz"
+        print("wrote %-28s %7.1f KiB" % (os.path.basename(path), os.path.getsize(path) / 1024.))
+        d = orc.omesh_to_dict(orc.OMesh.from_mesh(mesh))
+        d["n_points"] = np.int64(mesh.get_number_of_points())
+        save("mms_cut_232", d)
+
 
 if __name__ == "__main__":
     main()

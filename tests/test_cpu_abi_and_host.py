@@ -182,3 +182,101 @@ def test_hexmesh_closed_form_tables_match_reference(golden):
         cells = np.stack([zf(i, j, k), yf(i, j, k), xf(i, j, k), xf(i + 1, j, k), yf(i, j + 1, k), zf(i, j, k + 1)], 1)
         assert np.array_equal(cells.ravel(), ref.cell_faces)
         assert h.ijk_to_cell_index(1, 1, 1) == 1 + cx + cx * cy
+
+
+# ---- on-disk formats -------------------------------------------------------------
+def _assert_same_mesh(o, ref, exact=True):
+    for key in ("face_ptr", "face_points", "cell_ptr", "cell_faces", "cell_sigma"):
+        assert np.array_equal(getattr(o, key), getattr(ref, key)), key
+    assert {b: [(int(a), int(s)) for a, s in v] for b, v in o.boundary_faces.items()} == \
+        {b: [(int(a), int(s)) for a, s in v] for b, v in ref.boundary_faces.items()}
+    assert [tuple(map(int, x)) for x in o.internal_no_flow] == [tuple(map(int, x)) for x in ref.internal_no_flow]
+    for key in ("points", "face_areas", "face_centroids", "face_normals", "cell_volume", "cell_centroid", "cell_k"):
+        a, b = getattr(o, key), getattr(ref, key)
+        assert np.array_equal(a, b) if exact else np.allclose(a, b, rtol=1e-15, atol=0), key
+
+
+def test_mms_file_written_by_the_reference_loads(golden):
+    """Mesh.load_mesh reads a `.mms` file produced by the UNMODIFIED reference's save_mesh
+    (tests/golden/ref_mms_cut_232.mms.gz: a 2x3x2 hex mesh with one cell cut by a plane, an internal
+    no-flow face and a forcing pointer) into exactly the arrays the reference held."""
+    import gzip
+    from mimpy_b200.mesh.mesh import Mesh
+
+    g = golden("mms_cut_232")
+    ref = orc.omesh_from_dict(g)
+    m = Mesh()
+    with gzip.open(os.path.join(os.path.dirname(__file__), "golden", "ref_mms_cut_232.mms.gz"), "rt") as fh:
+        m.load_mesh(fh)
+    assert m.get_number_of_cells() == ref.nc == 13 and m.get_number_of_faces() == ref.nf
+    # the reference writes its whole over-allocated point table (mesh.py:826-828) and sizes the mesh
+    # from that count on load (mesh.py:601-603); the live points come first
+    assert m.get_number_of_points() >= int(g["n_points"])
+    m.number_of_points = int(g["n_points"])
+    _assert_same_mesh(orc.OMesh.from_mesh(m), ref, exact=False)   # text round trip: %.18e is exact, str(area) too
+    assert m.get_forcing_pointers_for_cell(2) == [(int(m.get_cell(7)[0]), 1)] or \
+        [tuple(x) for x in m.get_forcing_pointers_for_cell(2)] == [(int(m.get_cell(7)[0]), 1)]
+
+
+@pytest.mark.parametrize("mode", ["wb", "w"])
+def test_mms_save_load_round_trip(golden, mode, tmp_path):
+    """save_mesh -> load_mesh is the identity on a cut polyhedral mesh (binary handle like the
+    reference's own test, tests/test_read_write.py:18-26, or a text handle), counts included."""
+    from mimpy_b200.mesh.mesh import Mesh
+
+    ref = orc.omesh_from_dict(golden("cut_checker_4"))
+    m = mesh_from_omesh(ref)
+    m.add_internal_no_flow(int(m.get_cell(3)[2]), -1)
+    m.set_dirichlet_face_pointer(5, 1, 2)
+    path = str(tmp_path / "mesh.mms")
+    m.save_mesh(open(path, mode))
+    m2 = Mesh()
+    m2.load_mesh(open(path))
+    assert m2.get_number_of_faces() == m.get_number_of_faces()      # the reference's own assertions
+    assert m2.get_number_of_cells() == m.get_number_of_cells()
+    assert m2.get_number_of_points() == m.get_number_of_points()
+    _assert_same_mesh(orc.OMesh.from_mesh(m2), orc.OMesh.from_mesh(m), exact=True)
+    assert m2.get_dirichlet_pointer(5) == m.get_dirichlet_pointer(5)
+    assert np.array_equal(m2.face_to_cell[:m.get_number_of_faces()], m.face_to_cell[:m.get_number_of_faces()])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/mimpy"), reason="needs the reference tree (build container only)")
+def test_mms_file_written_here_loads_in_the_reference(golden, tmp_path):
+    from oracle import ref_shim
+
+    ref = ref_shim.load_reference()
+    o = orc.omesh_from_dict(golden("cut_checker_4"))
+    m = mesh_from_omesh(o)
+    path = str(tmp_path / "ours.mms")
+    m.save_mesh(open(path, "wb"))
+    r = ref.mesh.Mesh()
+    r.load_mesh(open(path))
+    assert r.get_number_of_cells() == o.nc and r.get_number_of_faces() == o.nf
+    _assert_same_mesh(orc.OMesh.from_mesh(r), o, exact=True)
+
+
+def test_vtk_writers(golden, tmp_path):
+    """Legacy-VTK output (mesh.py:1985-2087): polyhedral cells (type 42) and face polygons (type 7),
+    connectivity counts consistent, scalars attached."""
+    o = orc.omesh_from_dict(golden("cut_checker_4"))
+    m = mesh_from_omesh(o)
+    base = str(tmp_path / "out")
+    p = np.arange(o.nc, dtype=float)
+    m.output_vtk_mesh(base, [p, 2 * p], ["pressure", "twice"])
+    txt = open(base + ".vtk").read().split("\n")
+    assert txt[0] == "# vtk DataFile Version 2.0" and txt[3] == "DATASET UNSTRUCTURED_GRID"
+    i = next(k for k, l in enumerate(txt) if l.startswith("CELLS "))
+    ncell, total = map(int, txt[i].split()[1:])
+    rows = [list(map(int, l.split())) for l in txt[i + 1:i + 1 + ncell]]
+    assert ncell == o.nc and sum(len(r) for r in rows) == total and all(r[0] == len(r) - 1 for r in rows)
+    assert all(r[1] == o.cell_ptr[c + 1] - o.cell_ptr[c] for c, r in enumerate(rows))
+    assert txt[i + 1 + ncell] == "CELL_TYPES %d" % o.nc and txt[i + 2 + ncell] == "42"
+    j = txt.index("SCALARS twice double 1")
+    assert [float(x) for x in txt[j + 2:j + 2 + o.nc]] == list(2 * p)
+    faces = [0, 5, 17]
+    m.output_vtk_faces(base + "_f", faces, [np.array([1., 2., 3.])], ["v"])
+    t2 = open(base + "_f.vtk").read().split("\n")
+    i = next(k for k, l in enumerate(t2) if l.startswith("CELLS "))
+    assert t2[i] == "CELLS 3 %d" % sum(len(o.face(f)) + 1 for f in faces)
+    assert t2[i + 1].split() == [str(len(o.face(0)))] + [str(int(q)) for q in o.face(0)]
+    assert t2[i + 4:i + 8] == ["CELL_TYPES 3", "7", "7", "7"]
