@@ -224,6 +224,17 @@ int mimpy_b200_singlephase_terms(mimpy_ctx* ctx, int32_t nc, int32_t flux_dof, d
                                  const double* cell_volume, double* rhs, double* multipliers,
                                  double* c_diag);
 
+/* Transport.update_concentration + find_upwinding_direction (transport.py:303-361): explicit upwind
+ * step of a concentration carried by the flux field `velocity` (flux-DOF indexed, as returned by the
+ * solve).  boundary_conc: NULL or one value per FACE, NaN = none (transport.py:308-317 applies it on
+ * inflow faces of the markers given to set_concentration_boundaries).  conc_new must not alias
+ * conc_old.  The result is not divided by the cell volume (transport.py:344 is commented out). */
+int mimpy_b200_transport_step(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
+                              const double* velocity, const double* conc_old,
+                              const double* boundary_conc, const double* p_prev, const double* p_cur,
+                              const double* porosity, double ref_pressure, double compressibility,
+                              double ref_density, double dt, double* conc_new);
+
 /* -- (7) S1: linear solve -----------------------------------------------------------------------
  * replaces MFD.solve('spsolve') (mfd.py:1349-1358) for the saddle system
  *     M v - DIV^T p = b_v ,  DIV v + C p = b_p

@@ -66,6 +66,7 @@ SIGNATURES = {
     "mimpy_b200_mfd_coo": [_vp, _PM, _PS, _vp, _vp, _vp, _vp, _vp],
     "mimpy_b200_mfd_rhs": [_vp, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _f64, _vp, _vp],
     "mimpy_b200_singlephase_terms": [_vp, _i32, _i32, _f64, _f64, _f64, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mimpy_b200_transport_step": [_vp, _PM, _PS, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _f64, _f64, _vp],
     "mimpy_b200_hybrid_setup": [_vp, _PM, _PS, _vp, _vp, _f64, _vp, _vp, _vp, _vp, _vp],
     "mimpy_b200_sell_sizes": [_vp, _i32, _vp, _vp, C.POINTER(_i64)],
     "mimpy_b200_sell_fill": [_vp, _i32, _vp, _vp, _vp, _vp],

@@ -899,6 +899,56 @@ class OracleSinglePhase(object):
         self.current_velocity = sol[:mfd.flux_dof]
 
 
+class OracleTransport(OracleSinglePhase):
+    """Restatement of Transport (transport.py:186-391): the pressure step is SinglePhase's
+    (transport.py:261-301 == singlephase.py:256-291), followed by an explicit upwind update of a
+    concentration.  Like the reference it only makes sense without Neumann faces (transport.py:205-209
+    and 276-277 index the system with the number of faces, not flux_dof)."""
+
+    def __init__(self, o):
+        OracleSinglePhase.__init__(self, o)
+        self.concentration_boundaries = {}
+
+    def step(self):
+        self.prev_pressure = self.current_pressure
+        OracleSinglePhase.step(self)
+        self.find_upwinding_direction()
+        self.update_concentration()
+
+    def find_upwinding_direction(self):
+        """transport.py:346-361 (no Dirichlet pointers)"""
+        o = self.o
+        self.upwinded_face_cell = []
+        for c in range(o.nc):
+            for f, s in zip(o.cell(c), o.sigma(c)):
+                if s * self.current_velocity[f] > 0:
+                    self.upwinded_face_cell.append((f, c))
+
+    def update_concentration(self):
+        """transport.py:303-344; the result is NOT divided by the cell volume (the line is commented
+        out in the reference, transport.py:344)."""
+        o = self.o
+        c_uw = np.zeros(o.nf)
+        for f, c in self.upwinded_face_cell:
+            c_uw[f] = self.current_concentration[c]
+        for marker, fn in self.concentration_boundaries.items():
+            for f, s in o.boundary_faces[marker]:
+                if s * self.current_velocity[f] < 0:
+                    c_uw[f] = fn(o.face_centroids[f])
+        c_uw *= self.current_velocity
+        div_c = np.zeros(o.nc)
+        for c in range(o.nc):
+            for f, s in zip(o.cell(c), o.sigma(c)):
+                div_c[c] += s * o.face_areas[f] * c_uw[f]          # DIV of mfd.py:203-246
+        prev_density = ((self.prev_pressure - self.ref_pressure) * self.compressibility + 1.) * self.ref_density
+        cur_density = ((self.current_pressure - self.ref_pressure) * self.compressibility + 1.) * self.ref_density
+        conc = self.current_concentration * (prev_density * self.porosities)
+        conc = conc / self.delta_t
+        conc = conc - div_c
+        conc = conc * (self.delta_t / self.porosities)
+        self.current_concentration = conc / cur_density
+
+
 # --------------------------------------------------------------------------------------
 # (de)serialisation of OMesh for the golden fixtures
 # --------------------------------------------------------------------------------------

@@ -93,6 +93,7 @@ def load_reference():
     mfd = importlib.import_module("mimpy.mfd.mfd")
     twophase = importlib.import_module("mimpy.models.twophase")
     singlephase = importlib.import_module("mimpy.models.singlephase")
+    transport = importlib.import_module("mimpy.models.transport")
 
     # shim 2: integer sizes
     def new_size(self, size, minimum=1000):
@@ -119,6 +120,6 @@ def load_reference():
     mesh.Mesh.output_vtk_mesh = lambda self, *a, **k: None
 
     ns = types.SimpleNamespace(mesh=mesh, hexmesh=hexmesh, mfd=mfd, twophase=twophase,
-                               singlephase=singlephase, root=root)
+                               singlephase=singlephase, transport=transport, root=root)
     _loaded = ns
     return ns

@@ -276,6 +276,44 @@ def main():
     d["porosities"] = np.linspace(.1, .3, nc)
     save("singlephase_543", d)
 
+    # ---- 9. Transport (transport.py): SinglePhase pressure step + explicit upwind concentration ----
+    nx, ny, nz = 5, 4, 3
+    rng = np.random.default_rng(3)
+    kiso = np.exp(rng.standard_normal(nx * ny * nz))
+    mesh = ref_hex(ref, nx, ny, nz, (2.5, 2., 1.8), kiso[:, None, None] * np.eye(3)[None])
+    tr = ref.transport.Transport()
+    f = ref.mfd.MFD()
+    f.set_m_e_construction_method(1)
+    tr.set_mesh_mfd(mesh, f)
+    nc = mesh.get_number_of_cells()
+    tr.apply_pressure_boundary_from_function(0, lambda p: 2.)
+    tr.apply_pressure_boundary_from_function(1, lambda p: 1.)
+    for b in (2, 3, 4, 5):          # Transport indexes with the number of faces: no Neumann faces
+        tr.apply_pressure_boundary_from_function(b, lambda p: 2. - p[0] / 2.5)
+    tr.set_concentration_boundaries(0, lambda p: 1. + 0.5 * p[1])
+    tr.set_compressibility(1.e-2)
+    tr.set_ref_density(1.3)
+    tr.set_ref_pressure(1.)
+    tr.set_viscosity(0.7)
+    tr.set_porosities(np.linspace(.1, .3, nc))
+    tr.set_time_step_size(0.004)
+    tr.set_number_of_time_steps(1)
+    tr.add_point_rate_well(0.4, 27, "w")
+    tr.set_initial_pressure(np.full(nc, 1.5))
+    tr.set_initial_concentration(np.linspace(0., .2, nc))
+    quiet(tr.initialize_system)
+    p_hist, v_hist, c_hist = [], [], []
+    for step in range(6):
+        quiet(tr.start_solving)
+        p_hist.append(np.array(tr.current_pressure))
+        v_hist.append(np.array(tr.current_velocity))
+        c_hist.append(np.array(tr.current_concentration))
+    d = orc.omesh_to_dict(orc.OMesh.from_mesh(mesh))
+    d["p"], d["v"], d["c"] = np.array(p_hist), np.array(v_hist), np.array(c_hist)
+    d["porosities"] = np.linspace(.1, .3, nc)
+    d["c0"] = np.linspace(0., .2, nc)
+    save("transport_543", d)
+
     # ---- 8. `.mms` file written by the reference's Mesh.save_mesh (mesh.py:811-949) ---------
     only = [a for a in sys.argv[1:] if not a.startswith("-")]
     if not only or "mms_cut_232" in only:

@@ -262,3 +262,49 @@ def test_singlephase_model_matches_reference_history(golden):
         sp.start_solving()
         assert np.linalg.norm(sp.current_pressure - g["p"][step]) <= 1e-8 * np.linalg.norm(g["p"][step]), step
         assert np.linalg.norm(sp.current_velocity - g["v"][step]) <= 1e-8 * np.linalg.norm(g["v"][step]), step
+
+
+def test_transport_model_matches_reference_history(golden):
+    """Transport (transport.py:363-391): SinglePhase pressure step + explicit upwind concentration;
+    6 steps against the unmodified reference (c within 1e-10 per step, p/v within 1e-8)."""
+    import mimpy_b200.mesh.hexmesh as hexmesh
+    import mimpy_b200.mfd.mfd as mfd
+    import mimpy_b200.models.transport as transport
+
+    g = golden("transport_543")
+    ref = orc.omesh_from_dict(g)
+    mesh = hexmesh.HexMesh()
+    mesh.build_mesh(5, 4, 3, 2.5, 2., 1.8, ref.cell_k.reshape(-1, 3, 3))
+    tr = transport.Transport()
+    f = mfd.MFD()
+    f.set_m_e_construction_method(1)
+    tr.set_mesh_mfd(mesh, f)
+    nc = mesh.get_number_of_cells()
+    tr.apply_pressure_boundary_from_function(0, lambda p: 2.)
+    tr.apply_pressure_boundary_from_function(1, lambda p: 1.)
+    for b in (2, 3, 4, 5):
+        tr.apply_pressure_boundary_from_function(b, lambda p: 2. - p[0] / 2.5)
+    tr.set_concentration_boundaries(0, lambda p: 1. + 0.5 * p[1])
+    tr.set_compressibility(1.e-2)
+    tr.set_ref_density(1.3)
+    tr.set_ref_pressure(1.)
+    tr.set_viscosity(0.7)
+    tr.set_porosities(np.linspace(.1, .3, nc))
+    tr.set_time_step_size(0.004)
+    tr.set_number_of_time_steps(1)
+    tr.add_point_rate_well(0.4, 27, "w")
+    tr.set_initial_pressure(np.full(nc, 1.5))
+    tr.set_initial_concentration(np.array(g["c0"]))
+    tr.initialize_system()
+    for step in range(len(g["p"])):
+        tr.start_solving()
+        assert np.linalg.norm(tr.current_pressure - g["p"][step]) <= 1e-8 * np.linalg.norm(g["p"][step]), step
+        assert np.linalg.norm(tr.current_velocity - g["v"][step]) <= 1e-8 * np.linalg.norm(g["v"][step]), step
+        assert abs(tr.current_concentration - g["c"][step]).max() <= 1e-10, step
+    assert len(tr.get_upwinded_face_cell()) > 0
+    # Neumann boundaries are rejected (the reference would index out of range, transport.py:205-209)
+    tr2 = transport.Transport()
+    tr2.set_mesh(mesh)
+    tr2.apply_flux_boundary_from_function(2, zero_flux)
+    with pytest.raises(ValueError):
+        tr2.initialize_system()

@@ -287,3 +287,34 @@ def test_singlephase_history(golden):
         sp.step()
         assert np.linalg.norm(sp.current_pressure - g["p"][step]) <= 1e-10 * np.linalg.norm(g["p"][step])
         assert np.linalg.norm(sp.current_velocity - g["v"][step]) <= 1e-9 * np.linalg.norm(g["v"][step])
+
+
+def _setup_transport(t, g, dirichlet, concentration_boundary):
+    """The configuration of tests/golden/gen_golden.py section 9, applied through `dirichlet(marker, fn)`."""
+    dirichlet(0, lambda p: 2.)
+    dirichlet(1, lambda p: 1.)
+    for b in (2, 3, 4, 5):
+        dirichlet(b, lambda p: 2. - p[0] / 2.5)
+    concentration_boundary(0, lambda p: 1. + 0.5 * p[1])
+    t.compressibility, t.ref_density, t.ref_pressure, t.viscosity = 1.e-2, 1.3, 1., 0.7
+    t.porosities = g["porosities"]
+    t.delta_t = 0.004
+
+
+def test_transport_history(golden):
+    """OracleTransport (transport.py:261-361) against the unmodified reference: 6 steps of pressure,
+    velocity and concentration, including the missing division by the cell volume (cells of 0.15)."""
+    g = golden("transport_543")
+    o = orc.omesh_from_dict(g)
+    t = orc.OracleTransport(o)
+    _setup_transport(t, g, t.mfd.apply_dirichlet_from_function,
+                     lambda m, fn: t.concentration_boundaries.__setitem__(m, fn))
+    t.add_point_rate_well(0.4, 27)
+    t.initialize_system()
+    t.current_pressure = np.full(o.nc, 1.5)
+    t.current_concentration = np.array(g["c0"])
+    for step in range(len(g["p"])):
+        t.step()
+        assert np.linalg.norm(t.current_pressure - g["p"][step]) <= 1e-10 * np.linalg.norm(g["p"][step])
+        assert np.linalg.norm(t.current_velocity - g["v"][step]) <= 1e-9 * np.linalg.norm(g["v"][step])
+        assert abs(t.current_concentration - g["c"][step]).max() <= 1e-12, step
