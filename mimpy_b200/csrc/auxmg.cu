@@ -25,12 +25,19 @@
 // V-cycle a CPU prototype needs 37-42, so the cycle is as good as the auxiliary space allows.
 //
 // Slab partitions: every rank runs the cycle on its own cells; an interface face adds its t_f to the
-// diagonal (block-Jacobi of A_c across ranks).  tau sums and the prolongated correction of
-// interface rows are completed with the same exchange-add as the SpMV.
+// diagonal (block-Jacobi of A_c across ranks) -- except on the COARSEST level, which is shared: the
+// ranks keep coarsening until world x (cells per rank) <= 128, all-gather their coarse right-hand
+// sides (one small all-reduce per iteration) and every rank applies the dense inverse of the global
+// coarse operator, in which the interface couplings (Galerkin sums of the interface t_f) are real
+// off-diagonal entries.  That restores the global low-frequency coupling block-Jacobi lacks.
+// tau sums and the prolongated correction of interface rows are completed with the same
+// exchange-add as the SpMV.
 #include "reduce.cuh"
 
 #define AUX_MAX_LEVELS 24
 #define AUX_COARSEST 64
+#define AUX_GLOBAL_MAX 128   /* rows of the shared coarsest operator (world x cells per rank) */
+#define AUX_SLOT (5 * AUX_COARSEST)  /* per-rank record of the shared level: tx, ty, tz, dg, tzi */
 #define AUX_T 256
 
 struct AuxLevel {
@@ -38,7 +45,10 @@ struct AuxLevel {
   double *tx, *ty, *tz;  // coupling of cell c with its +x / +y / +z neighbour (0 on the boundary)
   double *dd;            // extra diagonal: Dirichlet faces, interface faces, C block
   double *dg;            // full diagonal
-  double *b, *x, *x2;    // right-hand side, pre-smoothed iterate, result of the level
+  double *b, *x, *x2;    // right-hand side, pre-smoothed iterate, result of the level; x and x2 carry two
+                         // ghost layers behind the n cells: [n, n+nx*ny) from the rank below, then from above
+  double *tzi, *bzi;     // [nx*ny] coupling of the top / bottom layer cells with the rank above / below
+  int has_lo, has_hi;    // 1: the ghost layer is live (slab partition with the levels shared across ranks)
 };
 
 struct mimpy_auxmg {
@@ -50,6 +60,11 @@ struct mimpy_auxmg {
   double* tsum;  // [flux_dof] sum of the half transmissibilities of a face
   double* cinv;  // dense inverse of the coarsest operator
   double* slab;  // the one stream-ordered allocation all arrays above are carved from
+  int global;    // 1: the coarsest level is shared between the ranks
+  int gn;        // rows of the shared operator = world * cells of the coarsest level
+  double* gset;  // [world * AUX_SLOT] gathered coarsest stencils
+  double* gbuf;  // [gn] gathered coarse right-hand side
+  double* ginv;  // [gn * gn] dense inverse of the shared operator
   double omega, scale;
   const int* cell_faces;
   const int* face_to_flux;
@@ -91,6 +106,7 @@ k_aux_level0(int nc, const int* __restrict__ cell_faces, const int* __restrict__
   if (c >= nc) return;
   double dd = c_diag ? c_diag[c] : alpha * cell_volume[c];
   double tp[3] = {0., 0., 0.};
+  double t_up = 0., t_dn = 0.;  // couplings through the top / bottom interface of a slab partition
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     const int f = cell_faces[c * 6 + i];
@@ -106,8 +122,13 @@ k_aux_level0(int nc, const int* __restrict__ cell_faces, const int* __restrict__
         const double S = tsum[g];
         const double t = tau * (S - tau) / S;
         w = tau / S;
-        if (iface) dd += t;           // neighbour on another rank: block-Jacobi
-        else if (i >= 3) tp[i - 3] = t;  // faces x+, y+, z+ (cell face order z-,y-,x-,x+,y+,z+)
+        if (iface) {
+          dd += t;  // neighbour on another rank: block-Jacobi (the shared coarsest level couples them)
+          if (face_flag[f] & 1) t_up = t;
+          else t_dn = t;
+        } else if (i >= 3) {
+          tp[i - 3] = t;  // faces x+, y+, z+ (cell face order z-,y-,x-,x+,y+,z+)
+        }
       }
     }
     wc[(size_t)c * 6 + i] = w;
@@ -117,6 +138,9 @@ k_aux_level0(int nc, const int* __restrict__ cell_faces, const int* __restrict__
   L.ty[c] = tp[1];
   L.tz[c] = tp[2];
   L.dd[c] = dd;
+  const int layer = L.nx * L.ny;
+  if (c >= L.n - layer) L.tzi[c - (L.n - layer)] = t_up;
+  if (c < layer) L.bzi[c] = t_dn;
 }
 
 __global__ void __launch_bounds__(AUX_T) k_aux_diag(AuxLevel L) {
@@ -151,6 +175,106 @@ __global__ void __launch_bounds__(AUX_T) k_aux_coarsen(AuxLevel F, AuxLevel C) {
   C.ty[c] = ty;
   C.tz[c] = tz;
   C.dd[c] = dd;
+  if (K == C.nz - 1) {
+    double tu = 0.;
+    for (int j = j0; j <= j1; ++j)
+      for (int i = i0; i <= i1; ++i) tu += F.tzi[i + F.nx * j];
+    C.tzi[I + C.nx * J] = tu;
+  }
+  if (K == 0) {
+    double td = 0.;
+    for (int j = j0; j <= j1; ++j)
+      for (int i = i0; i <= i1; ++i) td += F.bzi[i + F.nx * j];
+    C.bzi[I + C.nx * J] = td;
+  }
+}
+
+// ---- shared coarsest level of a slab partition ----------------------------------------------
+// own record into slot `rank` of the (zeroed) gather buffer; an all-reduce completes the gather
+__global__ void k_aux_global_pack(AuxLevel L, int rank, double* __restrict__ gset) {
+  double* slot = gset + (size_t)rank * AUX_SLOT;
+  for (int c = threadIdx.x; c < L.n; c += blockDim.x) {
+    slot[c] = L.tx[c];
+    slot[AUX_COARSEST + c] = L.ty[c];
+    slot[2 * AUX_COARSEST + c] = L.tz[c];
+    slot[3 * AUX_COARSEST + c] = L.dg[c];
+    if (c < L.nx * L.ny) slot[4 * AUX_COARSEST + c] = L.tzi[c];
+  }
+}
+
+// dense inverse of the global coarsest operator: rank r's cells are rows r*n .. r*n+n-1, stacked in z
+__global__ void __launch_bounds__(1024)
+k_aux_global_inverse(int world, int nx, int ny, int nz, const double* __restrict__ gset,
+                     double* __restrict__ ginv) {
+  extern __shared__ double A[];  // N x (N + 1)
+  __shared__ double piv_row[AUX_GLOBAL_MAX], piv_col[AUX_GLOBAL_MAX];
+  const int n = nx * ny * nz, N = world * n, ld = N + 1, t = threadIdx.x, T = blockDim.x;
+  for (int e = t; e < N * ld; e += T) A[e] = 0.;
+  __syncthreads();
+  double dmax = 0.;
+  for (int g = 0; g < N; ++g) dmax = fmax(dmax, gset[(size_t)(g / n) * AUX_SLOT + 3 * AUX_COARSEST + g % n]);
+  for (int g = t; g < N; g += T) {
+    const int r = g / n, c = g % n;
+    const double* slot = gset + (size_t)r * AUX_SLOT;
+    const int i = c % nx, j = (c / nx) % ny, k = c / (nx * ny);
+    A[g * ld + g] = slot[3 * AUX_COARSEST + c] + 1e-13 * dmax;
+    if (i + 1 < nx) { A[g * ld + g + 1] = -slot[c]; A[(g + 1) * ld + g] = -slot[c]; }
+    if (j + 1 < ny) { A[g * ld + g + nx] = -slot[AUX_COARSEST + c]; A[(g + nx) * ld + g] = -slot[AUX_COARSEST + c]; }
+    if (k + 1 < nz) {
+      A[g * ld + g + nx * ny] = -slot[2 * AUX_COARSEST + c];
+      A[(g + nx * ny) * ld + g] = -slot[2 * AUX_COARSEST + c];
+    } else if (r + 1 < world) {  // top layer: the cell above is the bottom-layer cell (i, j) of rank r + 1
+      const int g2 = (r + 1) * n + i + nx * j;
+      const double tu = slot[4 * AUX_COARSEST + i + nx * j];
+      A[g * ld + g2] = -tu;
+      A[g2 * ld + g] = -tu;
+    }
+  }
+  __syncthreads();
+  for (int p = 0; p < N; ++p) {  // in-place Gauss-Jordan, no pivoting (SPD)
+    const double piv = 1.0 / A[p * ld + p];
+    for (int e = t; e < N; e += T) {
+      piv_row[e] = A[p * ld + e] * piv;
+      piv_col[e] = A[e * ld + p];
+    }
+    __syncthreads();
+    for (int e = t; e < N * N; e += T) {
+      const int r = e / N, c = e - r * N;
+      double v;
+      if (r == p) v = (c == p) ? piv : piv_row[c];
+      else if (c == p) v = -piv_col[r] * piv;
+      else v = A[r * ld + c] - piv_col[r] * piv_row[c];
+      A[r * ld + c] = v;
+    }
+    __syncthreads();
+  }
+  for (int e = t; e < N * N; e += T) ginv[e] = A[(e / N) * ld + e % N];
+}
+
+__global__ void k_aux_global_gather(int N, int n, int rank, const double* __restrict__ b, double* __restrict__ gbuf) {
+  const int g = threadIdx.x;
+  if (g < N) gbuf[g] = (g / n == rank) ? b[g - rank * n] : 0.;
+}
+
+// x2 = rows of ginv times the gathered right-hand side: the rank's own n cells, then its two ghost
+// layers (top layer of the rank below, bottom layer of the rank above); one warp per row
+__global__ void __launch_bounds__(256)
+k_aux_global_solve(int N, int n, int nxy, int rank, int world, const double* __restrict__ ginv,
+                   const double* __restrict__ gbuf, double* __restrict__ x2) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  for (int r = w; r < n + 2 * nxy; r += 8) {
+    int g;
+    if (r < n) g = rank * n + r;
+    else if (r < n + nxy) g = rank > 0 ? (rank - 1) * n + (n - nxy) + (r - n) : -1;
+    else g = rank + 1 < world ? (rank + 1) * n + (r - n - nxy) : -1;
+    if (g < 0) continue;
+    const double* row = ginv + (size_t)g * N;
+    double s = 0.;
+    for (int c = l; c < N; c += 32) s += row[c] * gbuf[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (l == 0) x2[r] = s;
+  }
 }
 
 // dense inverse of the coarsest operator (n <= AUX_COARSEST), Gauss-Jordan without pivoting (SPD)
@@ -207,7 +331,9 @@ __device__ __forceinline__ double aux_apply(const AuxLevel& L, const double* __r
   if (j + 1 < L.ny) s -= L.ty[c] * x[c + sy];
   if (j > 0) s -= L.ty[c - sy] * x[c - sy];
   if (k + 1 < L.nz) s -= L.tz[c] * x[c + sz];
+  else if (L.has_hi) s -= L.tzi[i + sy * j] * x[L.n + sz + i + sy * j];  // cell of the rank above
   if (k > 0) s -= L.tz[c - sz] * x[c - sz];
+  else if (L.has_lo) s -= L.bzi[i + sy * j] * x[L.n + i + sy * j];       // cell of the rank below
   return s;
 }
 
@@ -247,8 +373,11 @@ k_aux_prolong_smooth(AuxLevel F, AuxLevel C, double omega, double scale) {
   if (i > 0) s -= F.tx[c - sx] * xp(i - 1, j, k);
   if (j + 1 < F.ny) s -= F.ty[c] * xp(i, j + 1, k);
   if (j > 0) s -= F.ty[c - sy] * xp(i, j - 1, k);
+  const int ij = i + sy * j, cij = (i >> 1) + cs_y * (j >> 1);
   if (k + 1 < F.nz) s -= F.tz[c] * xp(i, j, k + 1);
+  else if (F.has_hi) s -= F.tzi[ij] * (x[F.n + sz + ij] + scale * e[C.n + C.nx * C.ny + cij]);
   if (k > 0) s -= F.tz[c - sz] * xp(i, j, k - 1);
+  else if (F.has_lo) s -= F.bzi[ij] * (x[F.n + ij] + scale * e[C.n + cij]);
   F.x2[c] = xc + omega * (F.b[c] - s) / F.dg[c];
 }
 
@@ -319,13 +448,34 @@ int mimpy_auxmg_apply(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, const 
   AuxLevel* L = h->lev;
   k_aux_face_restrict<<<aux_blocks(h->nc), AUX_T, 0, st>>>(h->nc, h->cell_faces, h->face_to_flux, h->wc, r, L[0].b);
   const int last = h->nlev - 1;
+  auto ghosts = [&](double* v, const AuxLevel& lv) {  // both ghost layers of a level vector
+    mimpy_xchg x;
+    x.n = lv.nx * lv.ny;
+    x.send_lo = 0;
+    x.send_hi = (size_t)lv.n - x.n;
+    x.recv_lo = (size_t)lv.n;
+    x.recv_hi = (size_t)lv.n + x.n;
+    return mimpy_layer_exchange(ctx, v, x);
+  };
+  int rc;
   for (int l = 0; l < last; ++l) {
     k_aux_presmooth<<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], h->omega);
+    if (h->global && (rc = ghosts(L[l].x, L[l]))) return rc;
     k_aux_restrict<<<aux_blocks(L[l + 1].n), AUX_T, 0, st>>>(L[l], L[l + 1]);
   }
-  k_aux_coarse_solve<<<1, AUX_COARSEST, 0, st>>>(L[last], h->cinv);
-  for (int l = last - 1; l >= 0; --l)
+  if (h->global) {
+    k_aux_global_gather<<<1, AUX_GLOBAL_MAX, 0, st>>>(h->gn, L[last].n, ctx->rank, L[last].b, h->gbuf);
+    rc = mimpy_allreduce_f64(ctx, h->gbuf, h->gn);  // zero-padded sum == all-gather
+    if (rc) return rc;
+    k_aux_global_solve<<<1, 256, 0, st>>>(h->gn, L[last].n, L[last].nx * L[last].ny, ctx->rank, ctx->world, h->ginv,
+                                          h->gbuf, L[last].x2);
+  } else {
+    k_aux_coarse_solve<<<1, AUX_COARSEST, 0, st>>>(L[last], h->cinv);
+  }
+  for (int l = last - 1; l >= 0; --l) {
     k_aux_prolong_smooth<<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], L[l + 1], h->omega, h->scale);
+    if (h->global && l > 0 && (rc = ghosts(L[l].x2, L[l]))) return rc;
+  }
   const int grid = ctx->sm_count * 8;
   k_aux_face_prolong<<<grid, RED_THREADS, 0, st>>>(h->nf, n_owned, h->face_to_flux, h->face_cell, h->fw,
                                                    L[0].x2, dinv, r, z, ctx->partials, ctx->counters + 4, rz_dst);
@@ -355,14 +505,43 @@ int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
   int nx = mesh->hex_nx, ny = mesh->hex_ny, nz = mesh->hex_nz;
   size_t total = 0;
   auto pad = [](size_t n) { return (n + 31) & ~(size_t)31; };  // keep every array 256-byte aligned
+  // slab partition with identical slabs on every rank: share the coarsest level (see the header)
+  int coarsest = AUX_COARSEST;
+  h->global = 0;
+  if (ctx->world > 1 && ctx->world <= 16 && ctx->nccl_comm != nullptr) {
+    const char* env = getenv("MIMPY_B200_AUX_GLOBAL");
+    if (!(env && env[0] == '0')) {
+      double* d = ctx->scalars + 16;  // world * 3 doubles of scratch (64 scalars are allocated)
+      double mine[48];
+      for (int q = 0; q < ctx->world * 3; ++q) mine[q] = 0.;
+      mine[ctx->rank * 3] = nx; mine[ctx->rank * 3 + 1] = ny; mine[ctx->rank * 3 + 2] = nz;
+      CUDA_TRY(cudaMemcpyAsync(d, mine, sizeof(double) * ctx->world * 3, cudaMemcpyHostToDevice, ctx->stream));
+      int rc = mimpy_allreduce_f64(ctx, d, ctx->world * 3);
+      if (rc) { delete h; return rc; }
+      CUDA_TRY(cudaMemcpyAsync(mine, d, sizeof(double) * ctx->world * 3, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      bool same = true;
+      for (int r = 0; r < ctx->world; ++r)
+        same = same && mine[r * 3] == nx && mine[r * 3 + 1] == ny && mine[r * 3 + 2] == nz;
+      if (same) {
+        h->global = 1;
+        coarsest = AUX_GLOBAL_MAX / ctx->world;
+        if (coarsest > AUX_COARSEST) coarsest = AUX_COARSEST;
+        if (coarsest < 1) coarsest = 1;
+      }
+    }
+  }
   for (;;) {
     if (h->nlev >= AUX_MAX_LEVELS) break;
     AuxLevel& L = h->lev[h->nlev++];
     L.nx = nx; L.ny = ny; L.nz = nz; L.n = nx * ny * nz;
-    total += 8 * pad((size_t)L.n);
-    if (L.n <= AUX_COARSEST) break;
+    total += 6 * pad((size_t)L.n) + 2 * pad((size_t)L.n + 2 * (size_t)nx * ny) + 2 * pad((size_t)nx * ny);
+    if (L.n <= coarsest) break;
     nx = (nx + 1) / 2; ny = (ny + 1) / 2; nz = (nz + 1) / 2;
   }
+  h->gn = h->global ? ctx->world * h->lev[h->nlev - 1].n : 0;
+  if (h->global && (h->lev[h->nlev - 1].n > coarsest || h->nlev < 2)) h->global = 0;
+  total += pad((size_t)AUX_GLOBAL_MAX * AUX_SLOT) + pad(AUX_GLOBAL_MAX) + pad((size_t)AUX_GLOBAL_MAX * AUX_GLOBAL_MAX);
   if (h->lev[h->nlev - 1].n > AUX_COARSEST) {
     delete h;
     mimpy_set_error("auxmg_create: too many levels");
@@ -392,8 +571,17 @@ int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
   for (int l = 0; l < h->nlev; ++l) {
     AuxLevel& L = h->lev[l];
     L.tx = take(L.n); L.ty = take(L.n); L.tz = take(L.n); L.dd = take(L.n); L.dg = take(L.n);
-    L.b = take(L.n); L.x = take(L.n); L.x2 = take(L.n);
+    L.b = take(L.n);
+    L.x = take((size_t)L.n + 2 * (size_t)L.nx * L.ny);
+    L.x2 = take((size_t)L.n + 2 * (size_t)L.nx * L.ny);
+    L.tzi = take((size_t)L.nx * L.ny);
+    L.bzi = take((size_t)L.nx * L.ny);
+    L.has_lo = (h->global && ctx->rank > 0) ? 1 : 0;
+    L.has_hi = (h->global && ctx->rank < ctx->world - 1) ? 1 : 0;
   }
+  h->gset = take((size_t)AUX_GLOBAL_MAX * AUX_SLOT);
+  h->gbuf = take(AUX_GLOBAL_MAX);
+  h->ginv = take((size_t)AUX_GLOBAL_MAX * AUX_GLOBAL_MAX);
   h->wc = take((size_t)h->nc * 6);
   h->fw = take((size_t)h->nf * 2);
   h->tsum = take((size_t)h->flux_dof);
@@ -433,7 +621,23 @@ int mimpy_b200_auxmg_setup(mimpy_ctx* ctx, void* handle, const mimpy_mesh_view* 
     if (l > 0) k_aux_coarsen<<<aux_blocks(h->lev[l].n), AUX_T, 0, st>>>(h->lev[l - 1], h->lev[l]);
     k_aux_diag<<<aux_blocks(h->lev[l].n), AUX_T, 0, st>>>(h->lev[l]);
   }
-  k_aux_dense_inverse<<<1, AUX_T, 0, st>>>(h->lev[h->nlev - 1], h->cinv);
+  const AuxLevel& last = h->lev[h->nlev - 1];
+  if (h->global) {
+    CUDA_TRY(cudaMemsetAsync(h->gset, 0, sizeof(double) * (size_t)ctx->world * AUX_SLOT, st));
+    k_aux_global_pack<<<1, AUX_COARSEST, 0, st>>>(last, ctx->rank, h->gset);
+    rc = mimpy_allreduce_f64(ctx, h->gset, ctx->world * AUX_SLOT);
+    if (rc) return rc;
+    const size_t smem = sizeof(double) * (size_t)h->gn * (h->gn + 1);
+    static bool configured = false;
+    if (!configured) {
+      CUDA_TRY(cudaFuncSetAttribute(k_aux_global_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(sizeof(double) * AUX_GLOBAL_MAX * (AUX_GLOBAL_MAX + 1))));
+      configured = true;
+    }
+    k_aux_global_inverse<<<1, 1024, smem, st>>>(ctx->world, last.nx, last.ny, last.nz, h->gset, h->ginv);
+  } else {
+    k_aux_dense_inverse<<<1, AUX_T, 0, st>>>(last, h->cinv);
+  }
   KERNEL_CHECK();
   return MIMPY_OK;
 }

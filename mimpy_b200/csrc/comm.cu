@@ -258,6 +258,110 @@ int mimpy_halo_exchange_add(mimpy_ctx* ctx, double* v) {
   return MIMPY_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Ghost-layer exchange of a z-slab partition (auxmg.cu): n doubles starting at v + send_lo go to
+// the lower neighbour (rank - 1) and arrive there at v + recv_hi; n doubles at v + send_hi go to the
+// upper neighbour (rank + 1) and arrive at its v + recv_lo.  Plain copies (no sum).  Same buffers,
+// flags and epoch as the halo exchange-add: exchanges on one stream are strictly sequential.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_peer_layer_push(mimpy_peer pr, const double* __restrict__ v, mimpy_xchg x, int has_lo, int has_hi,
+                                  unsigned int* counter) {
+  const unsigned long long e = pr.epoch[1] + 1;
+  const int par = (int)(e & 1);
+  const size_t cap = pr.halo_cap;
+  const int n_lo = has_lo ? x.n : 0, total = n_lo + (has_hi ? x.n : 0);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    if (i < n_lo) {
+      double* dst = reinterpret_cast<double*>(pr.peers[pr.rank - 1] + PEER_DATA_OFF) + (size_t)(1 * 2 + par) * cap;
+      dst[i] = v[x.send_lo + i];
+    } else {
+      const int k = i - n_lo;
+      double* dst = reinterpret_cast<double*>(pr.peers[pr.rank + 1] + PEER_DATA_OFF) + (size_t)(0 * 2 + par) * cap;
+      dst[k] = v[x.send_hi + k];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(counter, 1u);
+    if (done == gridDim.x - 1) {
+      __threadfence_system();
+      if (has_lo)
+        st_volatile_u64(reinterpret_cast<unsigned long long*>(pr.peers[pr.rank - 1] + PEER_FLAG_OFF) + (1 * 2 + par), e);
+      if (has_hi)
+        st_volatile_u64(reinterpret_cast<unsigned long long*>(pr.peers[pr.rank + 1] + PEER_FLAG_OFF) + (0 * 2 + par), e);
+      *counter = 0u;
+    }
+  }
+}
+
+__global__ void k_peer_layer_pull(mimpy_peer pr, double* __restrict__ v, mimpy_xchg x, int has_lo, int has_hi,
+                                  unsigned int* counter, unsigned int* error_flag) {
+  const unsigned long long e = pr.epoch[1] + 1;
+  const int par = (int)(e & 1);
+  const size_t cap = pr.halo_cap;
+  if (threadIdx.x == 0) {
+    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(pr.local + PEER_FLAG_OFF);
+    unsigned int spins = 0;
+    if (has_lo)
+      while (ld_volatile_u64(flags + (0 * 2 + par)) != e && ++spins < PEER_SPIN_MAX) {
+      }
+    if (has_hi)
+      while (ld_volatile_u64(flags + (1 * 2 + par)) != e && ++spins < PEER_SPIN_MAX) {
+      }
+    if (spins >= PEER_SPIN_MAX) atomicExch(error_flag, 1u);
+    __threadfence_system();
+  }
+  __syncthreads();
+  const unsigned long long* from_lo =
+      reinterpret_cast<const unsigned long long*>(reinterpret_cast<const double*>(pr.local + PEER_DATA_OFF) + (size_t)(0 * 2 + par) * cap);
+  const unsigned long long* from_hi =
+      reinterpret_cast<const unsigned long long*>(reinterpret_cast<const double*>(pr.local + PEER_DATA_OFF) + (size_t)(1 * 2 + par) * cap);
+  const int n_lo = has_lo ? x.n : 0, total = n_lo + (has_hi ? x.n : 0);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    if (i < n_lo) v[x.recv_lo + i] = __longlong_as_double((long long)ld_volatile_u64(from_lo + i));
+    else v[x.recv_hi + (i - n_lo)] = __longlong_as_double((long long)ld_volatile_u64(from_hi + (i - n_lo)));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(counter, 1u);
+    if (done == gridDim.x - 1) {
+      pr.epoch[1] = e;
+      *counter = 0u;
+    }
+  }
+}
+
+int mimpy_layer_exchange(mimpy_ctx* ctx, double* v, const mimpy_xchg& x) {
+  if (ctx->world <= 1 || x.n <= 0) return MIMPY_OK;
+  const int has_lo = ctx->rank > 0, has_hi = ctx->rank < ctx->world - 1;
+  cudaStream_t st = ctx->stream;
+  if (ctx->peer.enabled && (size_t)x.n <= ctx->peer.halo_cap) {
+    const int total = x.n * (has_lo + has_hi);
+    const int blocks = max(1, min((total + 255) / 256, 2 * ctx->sm_count));
+    k_peer_layer_push<<<blocks, 256, 0, st>>>(ctx->peer, v, x, has_lo, has_hi, ctx->counters + 10);
+    k_peer_layer_pull<<<blocks, 256, 0, st>>>(ctx->peer, v, x, has_lo, has_hi, ctx->counters + 11, ctx->counters + 9);
+    KERNEL_CHECK();
+    return MIMPY_OK;
+  }
+  if (!ctx->nccl_comm || !g_nccl.handle) {
+    mimpy_set_error("world size %d but no NCCL communicator attached", ctx->world);
+    return MIMPY_E_NCCL;
+  }
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  NCCL_TRY(g_nccl.GroupStart());
+  if (has_lo) {
+    NCCL_TRY(g_nccl.Send(v + x.send_lo, x.n, ncclDouble, ctx->rank - 1, comm, st));
+    NCCL_TRY(g_nccl.Recv(v + x.recv_lo, x.n, ncclDouble, ctx->rank - 1, comm, st));
+  }
+  if (has_hi) {
+    NCCL_TRY(g_nccl.Send(v + x.send_hi, x.n, ncclDouble, ctx->rank + 1, comm, st));
+    NCCL_TRY(g_nccl.Recv(v + x.recv_hi, x.n, ncclDouble, ctx->rank + 1, comm, st));
+  }
+  NCCL_TRY(g_nccl.GroupEnd());
+  return MIMPY_OK;
+}
+
 extern "C" {
 
 int mimpy_b200_nccl_load(const char* path) { return nccl_load(path); }

@@ -59,6 +59,13 @@ int mimpy_auxmg_apply(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, const 
 // comm.cu
 int mimpy_allreduce_f64(mimpy_ctx* ctx, double* buf, int count);
 int mimpy_halo_exchange_add(mimpy_ctx* ctx, double* v);
+// ghost layers of a z-slab partition: v[send_lo .. +n) -> rank-1 (lands at its recv_hi), v[send_hi .. +n)
+// -> rank+1 (lands at its recv_lo); plain copies
+struct mimpy_xchg {
+  int n;
+  size_t send_lo, send_hi, recv_lo, recv_hi;
+};
+int mimpy_layer_exchange(mimpy_ctx* ctx, double* v, const mimpy_xchg& x);
 
 #define CUDA_TRY(expr)                                                                   \
   do {                                                                                   \
