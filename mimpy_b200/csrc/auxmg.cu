@@ -251,11 +251,6 @@ k_aux_global_inverse(int world, int nx, int ny, int nz, const double* __restrict
   for (int e = t; e < N * N; e += T) ginv[e] = A[(e / N) * ld + e % N];
 }
 
-__global__ void k_aux_global_gather(int N, int n, int rank, const double* __restrict__ b, double* __restrict__ gbuf) {
-  const int g = threadIdx.x;
-  if (g < N) gbuf[g] = (g / n == rank) ? b[g - rank * n] : 0.;
-}
-
 // x2 = rows of ginv times the gathered right-hand side: the rank's own n cells, then its two ghost
 // layers (top layer of the rank below, bottom layer of the rank above); one warp per row
 __global__ void __launch_bounds__(256)
@@ -464,8 +459,7 @@ int mimpy_auxmg_apply(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, const 
     k_aux_restrict<<<aux_blocks(L[l + 1].n), AUX_T, 0, st>>>(L[l], L[l + 1]);
   }
   if (h->global) {
-    k_aux_global_gather<<<1, AUX_GLOBAL_MAX, 0, st>>>(h->gn, L[last].n, ctx->rank, L[last].b, h->gbuf);
-    rc = mimpy_allreduce_f64(ctx, h->gbuf, h->gn);  // zero-padded sum == all-gather
+    rc = mimpy_allgather_f64(ctx, L[last].b, L[last].n, h->gbuf);
     if (rc) return rc;
     k_aux_global_solve<<<1, 256, 0, st>>>(h->gn, L[last].n, L[last].nx * L[last].ny, ctx->rank, ctx->world, h->ginv,
                                           h->gbuf, L[last].x2);

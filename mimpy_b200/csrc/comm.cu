@@ -76,12 +76,16 @@ static int nccl_load(const char* path) {
 // All waits are bounded and raise ctx error flag 1 instead of hanging.
 //   layout of the symmetric buffer:  [0, 1024)    reduce slots  [parity][rank] x 32 B (3 doubles + epoch)
 //                                    [1024, 2048) halo flags    [dir][parity] x u64
-//                                    [4096, ...)  halo data     [dir][parity][cap] doubles
+//                                    [4096, 16384) gather slots [parity][rank] x 528 B (64 doubles + epoch)
+//                                    [16384, ...) halo data     [dir][parity][cap] doubles
 // dir 0 = data arriving from the LOWER neighbour, dir 1 = from the UPPER neighbour.
 // ---------------------------------------------------------------------------------------------
 #define PEER_RED_OFF 0
 #define PEER_FLAG_OFF 1024
-#define PEER_DATA_OFF 4096
+#define PEER_GATHER_OFF 4096
+#define PEER_GATHER_SLOT 528
+#define PEER_GATHER_MAX 64   /* doubles per rank */
+#define PEER_DATA_OFF 16384
 #define PEER_SPIN_MAX (1u << 24)
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
@@ -256,6 +260,61 @@ int mimpy_halo_exchange_add(mimpy_ctx* ctx, double* v) {
   if (h.n_hi) k_unpack_add<<<(h.n_hi + 255) / 256, 256, 0, st>>>(h.n_hi, h.idx_hi, recv_hi, v);
   KERNEL_CHECK();
   return MIMPY_OK;
+}
+
+// all-gather of n <= 64 doubles per rank (coarsest level of auxmg.cu): thread (r, i) stores value i of
+// this rank into rank r's slot [parity][this rank]; out[r * n + i] = value i of rank r
+__global__ void __launch_bounds__(512)
+k_peer_allgather(mimpy_peer pr, const double* __restrict__ mine, int n, double* __restrict__ out,
+                 unsigned int* error_flag) {
+  const unsigned long long e = pr.epoch[2] + 1;
+  const int par = (int)(e & 1), t = threadIdx.x;
+  const int r = t / n, i = t - r * n;
+  if (r < pr.world) {
+    char* dst = pr.peers[r] + PEER_GATHER_OFF + (size_t)(par * 8 + pr.rank) * PEER_GATHER_SLOT;
+    st_volatile_u64(reinterpret_cast<unsigned long long*>(dst) + i, (unsigned long long)__double_as_longlong(mine[i]));
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < pr.world) {
+    char* dst = pr.peers[t] + PEER_GATHER_OFF + (size_t)(par * 8 + pr.rank) * PEER_GATHER_SLOT;
+    st_volatile_u64(reinterpret_cast<unsigned long long*>(dst) + PEER_GATHER_MAX, e);
+    const char* src = pr.local + PEER_GATHER_OFF + (size_t)(par * 8 + t) * PEER_GATHER_SLOT;
+    unsigned int spins = 0;
+    while (ld_volatile_u64(reinterpret_cast<const unsigned long long*>(src) + PEER_GATHER_MAX) != e && ++spins < PEER_SPIN_MAX) {
+    }
+    if (spins >= PEER_SPIN_MAX) atomicExch(error_flag, 1u);
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (r < pr.world) {
+    const char* src = pr.local + PEER_GATHER_OFF + (size_t)(par * 8 + r) * PEER_GATHER_SLOT;
+    out[t] = __longlong_as_double((long long)ld_volatile_u64(reinterpret_cast<const unsigned long long*>(src) + i));
+  }
+  if (t == 0) pr.epoch[2] = e;
+}
+
+__global__ void k_gather_pad(int N, int n, int rank, const double* __restrict__ mine, double* __restrict__ out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < N) out[g] = (g / n == rank) ? mine[g - rank * n] : 0.;
+}
+
+// out[r * n + i] = mine[i] of rank r.  Peer memory for small n, otherwise a zero-padded all-reduce.
+int mimpy_allgather_f64(mimpy_ctx* ctx, const double* mine, int n, double* out) {
+  if (n <= 0) return MIMPY_OK;
+  if (ctx->world <= 1) {
+    CUDA_TRY(cudaMemcpyAsync(out, mine, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    return MIMPY_OK;
+  }
+  if (ctx->peer.enabled && n <= PEER_GATHER_MAX && ctx->world * n <= 512) {
+    k_peer_allgather<<<1, 512, 0, ctx->stream>>>(ctx->peer, mine, n, out, ctx->counters + 9);
+    KERNEL_CHECK();
+    return MIMPY_OK;
+  }
+  const int N = ctx->world * n;
+  k_gather_pad<<<(N + 255) / 256, 256, 0, ctx->stream>>>(N, n, ctx->rank, mine, out);
+  KERNEL_CHECK();
+  return mimpy_allreduce_f64(ctx, out, N);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -448,8 +507,8 @@ int mimpy_b200_peer_attach(mimpy_ctx* ctx, int32_t rank, int32_t world, const vo
   CUDA_TRY(cudaMalloc(&dev_ptrs, sizeof(char*) * 8));
   CUDA_TRY(cudaMemcpy(dev_ptrs, ptrs, sizeof(char*) * 8, cudaMemcpyHostToDevice));
   unsigned long long* epoch = nullptr;
-  CUDA_TRY(cudaMalloc(&epoch, sizeof(unsigned long long) * 2));
-  CUDA_TRY(cudaMemset(epoch, 0, sizeof(unsigned long long) * 2));
+  CUDA_TRY(cudaMalloc(&epoch, sizeof(unsigned long long) * 4));
+  CUDA_TRY(cudaMemset(epoch, 0, sizeof(unsigned long long) * 4));
   ctx->peer.peers = dev_ptrs;
   ctx->peer.epoch = epoch;
   ctx->peer.rank = rank;

@@ -59,6 +59,7 @@ int mimpy_auxmg_apply(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, const 
 // comm.cu
 int mimpy_allreduce_f64(mimpy_ctx* ctx, double* buf, int count);
 int mimpy_halo_exchange_add(mimpy_ctx* ctx, double* v);
+int mimpy_allgather_f64(mimpy_ctx* ctx, const double* mine, int n, double* out);  // out[r*n+i] = mine[i] of rank r
 // ghost layers of a z-slab partition: v[send_lo .. +n) -> rank-1 (lands at its recv_hi), v[send_hi .. +n)
 // -> rank+1 (lands at its recv_lo); plain copies
 struct mimpy_xchg {
