@@ -24,14 +24,15 @@
 // iterations at 16^3/64^3/128^3/256^3 become 35/40/45/45; with an exact solve of A_c instead of the
 // V-cycle a CPU prototype needs 37-42, so the cycle is as good as the auxiliary space allows.
 //
-// Slab partitions: every rank runs the cycle on its own cells; an interface face adds its t_f to the
-// diagonal (block-Jacobi of A_c across ranks) -- except on the COARSEST level, which is shared: the
-// ranks keep coarsening until world x (cells per rank) <= 128, all-gather their coarse right-hand
-// sides (one small all-reduce per iteration) and every rank applies the dense inverse of the global
-// coarse operator, in which the interface couplings (Galerkin sums of the interface t_f) are real
-// off-diagonal entries.  That restores the global low-frequency coupling block-Jacobi lacks.
-// tau sums and the prolongated correction of interface rows are completed with the same
-// exchange-add as the SpMV.
+// Slab partitions (identical slabs): the hierarchy is shared between the ranks.  Aggregates never
+// straddle a rank; every level exchanges one ghost layer of x (before the residual) and of the coarse
+// correction (before the prolongation) with its z-neighbours (mimpy_layer_exchange, comm.cu); the
+// couplings through the interfaces (tzi / bzi, Galerkin sums of the interface t_f) are applied to
+// the ghost values; the ranks keep coarsening until world x (cells per rank) <= 128, all-gather the
+// coarse right-hand sides and every rank applies the dense inverse of the GLOBAL coarsest operator.
+// The cycle is then the single-GPU cycle (45 iterations at 256^3 on 1, 2 and 8 GPUs; a rank-local
+// block-Jacobi version needed 85 / 145).  tau sums and the prolongated correction of interface rows
+// are completed with the same exchange-add as the SpMV.  Uneven slabs: rank-local cycle.
 #include "reduce.cuh"
 
 #define AUX_MAX_LEVELS 24
