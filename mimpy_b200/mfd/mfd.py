@@ -337,8 +337,9 @@ class MFD(object):
     # ---- solve -------------------------------------------------------------------------------------------
     def solve(self, initial_guess=0., solver='spsolve', rtol=None, maxit=None):
         """Solves the saddle system for [v ; p] (mfd.py:1349-1368).  Every `solver` value runs the
-        same GPU path: exact hybridisation to the SPD face system + Jacobi-PCG + local recovery;
-        there is no sparse direct factorisation on the device."""
+        same GPU path: exact hybridisation to the SPD face system + PCG (auxiliary-space multigrid
+        on structured hex meshes, Jacobi otherwise) + local recovery; there is no sparse direct
+        factorisation on the device."""
         import torch
 
         dm, plan = self._ensure_plan()
