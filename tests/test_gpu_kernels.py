@@ -299,7 +299,7 @@ def test_update_m_multipliers_and_coo_view(ctx, golden):
     assert abs(a2[F:, :] - a1[F:, :]).max() == 0
 
 
-@pytest.mark.parametrize("n", [(37, 20, 23), (38, 21, 23), (8, 4, 4), (2, 1, 1)])
+@pytest.mark.parametrize("n", [(37, 20, 23), (38, 21, 23), (8, 4, 4), (2, 1, 1), (-10, 9, 6)])
 @pytest.mark.parametrize("method", [0, 1, 6])
 def test_uniform_fast_path_equals_generic_kernel(ctx, method, n):
     """The thread-per-cell hex kernel and the generic warp-group kernel fill the same CSR:
@@ -310,15 +310,27 @@ def test_uniform_fast_path_equals_generic_kernel(ctx, method, n):
 
     # odd nx -> brick kernel with per-thread loads; even nx -> cp.async-staged brick kernel
     # (38x21x23 has partial bricks on all three axes)
+    # a negative nx marks the DISTORTED variant: grid points shifted like HexMesh's modification_function
+    # does (non-planar faces, non-orthogonal cells), same structured numbering
+    distorted = n[0] < 0
+    n = (abs(n[0]), n[1], n[2])
     nc = n[0] * n[1] * n[2]
     rng = np.random.default_rng(3)
     k = np.zeros((nc, 3, 3))
     g = np.exp(rng.standard_normal((nc, 3)))
     k[:, 0, 0], k[:, 1, 1], k[:, 2, 2] = g[:, 0], g[:, 1], g[:, 2]
     k[:, 0, 1] = k[:, 1, 0] = 0.2 * np.sqrt(g[:, 0] * g[:, 1]) * rng.uniform(-1, 1, nc)
-    d = device.DeviceMesh.hex(ctx, n[0], n[1], n[2], 2., 1., 1.5, cell_k=k.reshape(nc, 9))
-    fc = H(ctx, d.face_centroids)
-    mask = ((fc[:, 1] < 1e-9) | (fc[:, 2] > 1.5 - 1e-9)).astype(np.uint8)
+    points = None
+    if distorted:
+        kk, jj, ii = np.meshgrid(np.arange(n[2] + 1), np.arange(n[1] + 1), np.arange(n[0] + 1), indexing="ij")
+        p0 = np.stack([ii.ravel() * 2. / n[0], jj.ravel() * 1. / n[1], kk.ravel() * 1.5 / n[2]], axis=1)
+        points = p0 + 0.02 * np.stack([np.sin(5. * p0[:, 1] + p0[:, 2]), np.cos(4. * p0[:, 0] * p0[:, 2]),
+                                       np.sin(3. * p0[:, 0] + 2. * p0[:, 1])], axis=1)
+    d = device.DeviceMesh.hex(ctx, n[0], n[1], n[2], 2., 1., 1.5, cell_k=k.reshape(nc, 9), points=points)
+    hx = HexIndexHost(*n)
+    mask = np.zeros(d.nf, dtype=np.uint8)
+    mask[hx.boundary(2)] = 1      # y-  (by index: the distorted boundary is not a coordinate plane)
+    mask[hx.boundary(5)] = 1      # z+
     plan = device.symbolic(d, mask)
     mult = torch.as_tensor(rng.uniform(.5, 2., nc), device=ctx.device)
     cd = torch.as_tensor(rng.uniform(.0, 1., nc), device=ctx.device)
@@ -336,6 +348,26 @@ def test_uniform_fast_path_equals_generic_kernel(ctx, method, n):
     ip = H(ctx, plan.indptr)
     # DIV / DIV^T / C slots are bit-identical
     assert np.array_equal(a[ip[F]:], b[ip[F]:])
+
+
+class HexIndexHost(object):
+    """Closed-form HexMesh face numbering (hexmesh.py:161-234) for picking boundary faces by index."""
+
+    def __init__(self, cx, cy, cz):
+        self.c = (cx, cy, cz)
+        self.L = cx * cy + cx * (cy + 1) + (cx + 1) * cy
+
+    def boundary(self, marker):
+        cx, cy, cz = self.c
+        L, s = self.L, 3 * cx + 1
+        if marker in (4, 5):
+            j, i = np.meshgrid(np.arange(cy), np.arange(cx), indexing="ij")
+            return (j * s + 3 * i if marker == 4 else cz * L + j * cx + i).ravel()
+        if marker in (2, 3):
+            k, i = np.meshgrid(np.arange(cz), np.arange(cx), indexing="ij")
+            return (k * L + 3 * i + 1 if marker == 2 else k * L + cy * s + i).ravel()
+        k, j = np.meshgrid(np.arange(cz), np.arange(cy), indexing="ij")
+        return (k * L + j * s + 2 if marker == 0 else k * L + j * s + 3 * cx).ravel()
 
 
 # ---- solve ------------------------------------------------------------------------------------------
