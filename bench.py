@@ -47,7 +47,7 @@ def aux_levels(nx, ny, nz):
 
 def launches_per_step(precond, n, nz_local, iters):
     """Kernels of OUR library launched by one bench step (assembly, set-up, solve)."""
-    setup = 1 + 2 + 4 + 1 + 1          # assembly; local matrices; hybrid set-up; rhs; recover
+    setup = 1 + 4 + 1 + 1              # assembly; fused hybrid set-up (zero, set-up, diag, invert); rhs; recover
     if precond != "auxmg":
         return setup + 3 + 3 * iters   # PCG init + 3 kernels per iteration
     lv = aux_levels(n, n, nz_local)
@@ -249,9 +249,7 @@ def run_cuda(args):
             evs[0].record(ctx.stream)
             device.numeric(dm, plan, method, vals=vals)
             evs[1].record(ctx.stream)
-            m_e, _, _ = device.local_matrices(dm, plan, method)
-            hyb = device.HybridSystem(dm, plan, m_e, precond=args.precond)
-            del m_e
+            hyb = device.HybridSystem(dm, plan, None, precond=args.precond, method=method)  # fused M_E + set-up
             evs[2].record(ctx.stream)
             sol, info = hyb.solve(rhs, rtol=args.rtol, maxit=args.maxit, check_every=check_every,
                                   raise_on_noconv=False)
@@ -286,9 +284,7 @@ def run_cuda(args):
 
     # ---- the SpMV kernel alone and the plain Jacobi-PCG iteration (bounded: 100 iterations) ----
     with ctx.on_stream():
-        m_e, _, _ = device.local_matrices(dm, plan, method)
-        hyb = device.HybridSystem(dm, plan, m_e, precond="jacobi")
-        del m_e
+        hyb = device.HybridSystem(dm, plan, None, precond="jacobi", method=method)
         _, jinfo = hyb.solve(rhs, rtol=1e-30, maxit=100, check_every=50, raise_on_noconv=False)
         _, jinfo = hyb.solve(rhs, rtol=1e-30, maxit=100, check_every=50, raise_on_noconv=False)
         xs = torch.ones(F, dtype=torch.float64, device=dev)

@@ -254,6 +254,14 @@ int mimpy_b200_hybrid_setup(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
                             const double* c_diag, double* w_e, double* a_vals, double* a_diag_inv,
                             const int32_t* sell_ptr /* NULL: a_vals in CSR order (m_indptr);
                             else a_vals in the SELL-32 layout of mimpy_b200_sell_sizes/_fill */);
+/* Same as mimpy_b200_mfd_local_matrices + mimpy_b200_hybrid_setup in one pass for hexahedral cells
+ * (uniform_faces == 6, methods 0/1/6): M_E is built and inverted per cell without ever being stored
+ * (mfd.py:357-483 feeding the elimination above).  Returns MIMPY_E_UNSUPPORTED otherwise -- callers
+ * then use the two-step path.  flags: MIMPY_FLAG_K_UNITY. */
+int mimpy_b200_hybrid_setup_fused(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
+                                  int32_t method, int32_t flags, const double* multipliers, double alpha,
+                                  const double* c_diag, double* w_e, double* a_vals, double* a_diag_inv,
+                                  const int32_t* sell_ptr);
 int mimpy_b200_hybrid_rhs(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
                           const double* w_e, double alpha, const double* c_diag,
                           const double* rhs /*flux_dof+nc*/, double* cell_tmp /*cell_ptr[nc]*/,

@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmimpy_b200.so")
 
 MIMPY_E_NOCONV = -4
+MIMPY_E_UNSUPPORTED = -3
 
 _vp = C.c_void_p
 _i32 = C.c_int32
@@ -68,6 +69,7 @@ SIGNATURES = {
     "mimpy_b200_singlephase_terms": [_vp, _i32, _i32, _f64, _f64, _f64, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp],
     "mimpy_b200_transport_step": [_vp, _PM, _PS, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _f64, _f64, _vp],
     "mimpy_b200_hybrid_setup": [_vp, _PM, _PS, _vp, _vp, _f64, _vp, _vp, _vp, _vp, _vp],
+    "mimpy_b200_hybrid_setup_fused": [_vp, _PM, _PS, _i32, _i32, _vp, _f64, _vp, _vp, _vp, _vp, _vp],
     "mimpy_b200_sell_sizes": [_vp, _i32, _vp, _vp, C.POINTER(_i64)],
     "mimpy_b200_sell_fill": [_vp, _i32, _vp, _vp, _vp, _vp],
     "mimpy_b200_pcg_sell": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(PcgInfo)],

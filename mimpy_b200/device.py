@@ -346,8 +346,11 @@ class HybridSystem(object):
     """The SPD face system A lambda = h of the hybridised saddle problem, in HBM."""
 
     def __init__(self, dmesh, plan, m_e, multipliers=None, alpha=0., c_diag=None, layout="sell",
-                 precond="auto"):
-        """layout: "sell" (SELL-32, the solver's native layout) or "csr" (m_indptr/m_indices order).
+                 precond="auto", method=None, k_unity=False):
+        """m_e: the M_E blocks of `local_matrices`, or None with `method` given: the blocks are then built
+        inside the set-up kernel (hexahedral cells, methods 0/1/6; other meshes fall back to
+        `local_matrices` transparently) and never stored.
+        layout: "sell" (SELL-32, the solver's native layout) or "csr" (m_indptr/m_indices order).
         precond: "auxmg" (Jacobi + auxiliary-space multigrid, structured hex meshes only), "jacobi",
         or "auto" (auxmg where the mesh is a structured hex mesh)."""
         self.dmesh, self.plan = dmesh, plan
@@ -362,6 +365,9 @@ class HybridSystem(object):
             raise ValueError("unknown preconditioner %r" % (precond,))
         self.precond = precond
         self.aux = None
+        if m_e is None and method is None:
+            raise ValueError("HybridSystem needs the M_E blocks or the construction method")
+        self.method, self.k_unity = method, bool(k_unity)
         ctx = dmesh.ctx
         dev = ctx.device
         F = plan.flux_dof
@@ -390,9 +396,18 @@ class HybridSystem(object):
         self.c_diag = c_diag
         with ctx.on_stream():
             mv = self.dmesh.view()
-            ctx.call("mimpy_b200_hybrid_setup", C.byref(mv), C.byref(self.plan.s), ptr(m_e),
-                     ptr(multipliers), self.alpha, ptr(c_diag), ptr(self.w_e), ptr(self.a_vals),
-                     ptr(self.a_diag_inv), ptr(self.sell_ptr))
+            fused = False
+            if m_e is None:
+                rc = ctx.call("mimpy_b200_hybrid_setup_fused", C.byref(mv), C.byref(self.plan.s), int(self.method),
+                              1 if self.k_unity else 0, ptr(multipliers), self.alpha, ptr(c_diag), ptr(self.w_e),
+                              ptr(self.a_vals), ptr(self.a_diag_inv), ptr(self.sell_ptr), allow=(_lib.MIMPY_E_UNSUPPORTED,))
+                fused = rc == 0
+                if not fused:
+                    m_e = local_matrices(self.dmesh, self.plan, self.method, k_unity=self.k_unity)[0]
+            if not fused:
+                ctx.call("mimpy_b200_hybrid_setup", C.byref(mv), C.byref(self.plan.s), ptr(m_e),
+                         ptr(multipliers), self.alpha, ptr(c_diag), ptr(self.w_e), ptr(self.a_vals),
+                         ptr(self.a_diag_inv), ptr(self.sell_ptr))
             if self.precond == "auxmg":
                 if self.aux is None:
                     h = C.c_void_p()

@@ -101,7 +101,9 @@ class Transport(SinglePhase):
                 self._hyb = device.HybridSystem(dm, plan, self._m_e, multipliers=self._d_mult, c_diag=self._d_cdiag)
             else:
                 self._hyb.setup(self._m_e, self._d_mult, self._d_cdiag)
-            sol, info = self._hyb.solve(rhs, rtol=self.pcg_rtol, maxit=50000)
+            # warm start: the face multipliers of the previous time step
+            sol, info = self._hyb.solve(rhs, rtol=self.pcg_rtol, maxit=50000,
+                                        x0=getattr(self._hyb, "last_lambda", None))
             self.last_solver_info = info
             self._d_p_prev = self._d_p
             self._d_p = sol[F:].clone()

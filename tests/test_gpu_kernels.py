@@ -513,6 +513,49 @@ def test_auxmg_preconditioner_vs_spsolve_and_jacobi(ctx, dims, alpha):
         assert ia.iterations < ij.iterations
 
 
+@pytest.mark.parametrize("method", [0, 1, 6])
+@pytest.mark.parametrize("layout", ["sell", "csr"])
+def test_fused_hex_setup_equals_two_step_setup(ctx, method, layout):
+    """mimpy_b200_hybrid_setup_fused (M_E built and inverted inside the kernel) gives the same face
+    system, W_E blocks and Jacobi diagonal as local_matrices + hybrid_setup: Neumann faces, per-cell
+    multipliers, an accumulation diagonal and k_unity included; other meshes fall back."""
+    import torch
+    from mimpy_b200 import device
+
+    nx, ny, nz = 11, 7, 5
+    nc = nx * ny * nz
+    rng = np.random.default_rng(21)
+    k = np.zeros((nc, 3, 3))
+    g = np.exp(rng.standard_normal((nc, 3)))
+    k[:, 0, 0], k[:, 1, 1], k[:, 2, 2] = g[:, 0], g[:, 1], g[:, 2]
+    k[:, 0, 2] = k[:, 2, 0] = 0.3 * np.sqrt(g[:, 0] * g[:, 2]) * rng.uniform(-1, 1, nc)
+    d = device.DeviceMesh.hex(ctx, nx, ny, nz, 1., 2., .5, cell_k=k.reshape(nc, 9))
+    hx = HexIndexHost(nx, ny, nz)
+    mask = np.zeros(d.nf, dtype=np.uint8)
+    mask[hx.boundary(3)] = 1
+    mask[hx.boundary(4)] = 1
+    plan = device.symbolic(d, mask)
+    mult = torch.as_tensor(rng.uniform(.5, 2., nc), device=ctx.device)
+    cd = torch.as_tensor(rng.uniform(0., 1., nc), device=ctx.device)
+    for k_unity in (False, True):
+        m_e, _, _ = device.local_matrices(d, plan, method, k_unity=k_unity)
+        two = device.HybridSystem(d, plan, m_e, multipliers=mult, c_diag=cd, layout=layout, precond="jacobi")
+        one = device.HybridSystem(d, plan, None, multipliers=mult, c_diag=cd, layout=layout, precond="jacobi",
+                                  method=method, k_unity=k_unity)
+        for name in ("a_vals", "w_e", "a_diag_inv"):
+            a, b = H(ctx, getattr(one, name)), H(ctx, getattr(two, name))
+            assert abs(a - b).max() <= 1e-12 * abs(b).max(), (name, k_unity)
+    # generic meshes: the same call falls back to the two-step path
+    o = orc.hex_mesh(3, 3, 2, 1., 1., 1.)
+    dg = device.DeviceMesh.from_oracle_mesh(ctx, o)
+    dg.uniform_faces = 0          # pretend the cells are ragged
+    pg = device.symbolic(dg, np.zeros(o.nf, dtype=np.uint8))
+    mg, _, _ = device.local_matrices(dg, pg, 1)
+    a = device.HybridSystem(dg, pg, None, method=1, precond="jacobi")
+    b = device.HybridSystem(dg, pg, mg, precond="jacobi")
+    assert np.array_equal(H(ctx, a.a_vals), H(ctx, b.a_vals))
+
+
 def test_auxmg_rejected_on_unstructured_mesh(ctx, golden):
     from mimpy_b200 import device
 
