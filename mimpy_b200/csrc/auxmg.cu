@@ -56,8 +56,9 @@ struct mimpy_auxmg {
   int nlev;
   AuxLevel lev[AUX_MAX_LEVELS];
   int nc, nf, flux_dof;
-  double* wc;    // [nc*6]  weight of cell c at its local face i (Pi^T gathers with it)
-  double* fw;    // [nf*2]  weights of the two cells of face f   (Pi gathers with it)
+  double* wc;    // [nc*6]  set-up scratch: half transmissibility of cell c at its local face i
+  double* fw;    // [nf]    transfer weight of the FIRST cell of face f (face_cell[2f]); the second cell
+                 //         of an interior face has 1 - fw (the two weights of Pi sum to one)
   double* tsum;  // [flux_dof] sum of the half transmissibilities of a face
   double* cinv;  // dense inverse of the coarsest operator
   double* slab;  // the one stream-ordered allocation all arrays above are carved from
@@ -132,8 +133,7 @@ k_aux_level0(int nc, const int* __restrict__ cell_faces, const int* __restrict__
         }
       }
     }
-    wc[(size_t)c * 6 + i] = w;
-    fw[2 * (size_t)f + (face_cell[2 * (size_t)f] == c ? 0 : 1)] = w;
+    if (face_cell[2 * (size_t)f] == c) fw[f] = w;
   }
   L.tx[c] = tp[0];
   L.ty[c] = tp[1];
@@ -388,41 +388,73 @@ __global__ void __launch_bounds__(AUX_T) k_aux_coarse_solve(AuxLevel L, const do
 // ---------------------------------------------------------------------------------------------
 // transfers between the face system and the cells
 // ---------------------------------------------------------------------------------------------
+// HexMesh numbering in closed form (hexmesh.py:161-234): faces of cell (i, j, k)
+struct AuxHex {
+  int nx, ny, nz, L, xrow;
+  __device__ __forceinline__ int cbase(int i, int j, int k) const { return k * L + j * xrow + 3 * i; }  // z-, y-, x- = +0, +1, +2
+  __device__ __forceinline__ int xp(int i, int j, int k) const { return i + 1 < nx ? cbase(i, j, k) + 5 : k * L + j * xrow + 3 * nx; }
+  __device__ __forceinline__ int yp(int i, int j, int k) const { return j + 1 < ny ? cbase(i, j, k) + xrow + 1 : k * L + ny * xrow + i; }
+  __device__ __forceinline__ int zp(int i, int j, int k) const { return k + 1 < nz ? cbase(i, j, k) + L : nz * L + j * nx + i; }
+};
+
+// b = Pi^T r on the cells.  A cell is the SECOND cell of its z-/y-/x- face when that neighbour exists
+// (weight 1 - fw), the first cell of every other face (weight fw); no index array is read.
 __global__ void __launch_bounds__(AUX_T)
-k_aux_face_restrict(int nc, const int* __restrict__ cell_faces, const int* __restrict__ f2f,
-                    const double* __restrict__ wc, const double* __restrict__ r, double* __restrict__ b) {
+k_aux_face_restrict(AuxHex hx, const int* __restrict__ f2f, const double* __restrict__ fw,
+                    const double* __restrict__ r, double* __restrict__ b) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= nc) return;
+  if (c >= hx.nx * hx.ny * hx.nz) return;
+  const int i = c % hx.nx, j = (c / hx.nx) % hx.ny, k = c / (hx.nx * hx.ny);
+  const int cb = hx.cbase(i, j, k);
+  const int f[6] = {cb, cb + 1, cb + 2, hx.xp(i, j, k), hx.yp(i, j, k), hx.zp(i, j, k)};
+  const bool second[6] = {k > 0, j > 0, i > 0, false, false, false};
   double s = 0.;
 #pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    const double w = wc[(size_t)c * 6 + i];
-    if (w != 0.) s += w * r[f2f[cell_faces[c * 6 + i]]];
+  for (int q = 0; q < 6; ++q) {
+    const int g = f2f[f[q]];
+    if (g < 0) continue;
+    const double w1 = fw[f[q]];
+    const double w = second[q] ? (w1 > 0. ? 1. - w1 : 0.) : w1;
+    if (w != 0.) s += w * r[g];
   }
   b[c] = s;
 }
 
 // z = [owned rows] D^-1 r + Pi e ; partial sums of r.z over ALL local rows (interface rows hold this
-// rank's share of z, r is identical on both ranks, so the shares add up to r.z across ranks)
+// rank's share of z, r is identical on both ranks, so the shares add up to r.z across ranks).  Every
+// face is written by exactly one cell: its second cell (the cell whose z-/y-/x- face it is), or its
+// only cell -- three consecutive rows per cell.
 __global__ void __launch_bounds__(RED_THREADS)
-k_aux_face_prolong(int nf, int n_owned, const int* __restrict__ f2f, const int* __restrict__ face_cell,
-                   const double* __restrict__ fw, const double* __restrict__ e,
-                   const double* __restrict__ dinv, const double* __restrict__ r,
-                   double* __restrict__ z, double* partials, unsigned int* counter, double* dst) {
+k_aux_face_prolong(AuxHex hx, int n_owned, const int* __restrict__ f2f, const double* __restrict__ fw,
+                   const double* __restrict__ e, const double* __restrict__ dinv,
+                   const double* __restrict__ r, double* __restrict__ z, double* partials,
+                   unsigned int* counter, double* dst) {
   __shared__ double sh[32];
+  const int nc = hx.nx * hx.ny * hx.nz, sy = hx.nx, sz = hx.nx * hx.ny;
   double acc = 0.;
-  for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < nf;
-       f += (long long)gridDim.x * blockDim.x) {
-    const int g = f2f[f];
-    if (g < 0) continue;
-    const int c1 = face_cell[2 * f], c2 = face_cell[2 * f + 1];
-    const double rg = r[g];
-    double zz = (g < n_owned) ? dinv[g] * rg : 0.;
-    const double w1 = fw[2 * f], w2 = fw[2 * f + 1];
-    if (w1 != 0.) zz += w1 * e[c1];
-    if (c2 >= 0 && w2 != 0.) zz += w2 * e[c2];
-    z[g] = zz;
-    acc += rg * zz;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+    const int i = c % hx.nx, j = (c / hx.nx) % hx.ny, k = c / sz;
+    const int cb = hx.cbase(i, j, k);
+    const double ec = e[c];
+    auto face = [&](int f, int other) {  // other: the first cell of the face, or -1 when this cell is
+      const int g = f2f[f];
+      if (g < 0) return;
+      const double rg = r[g], w1 = fw[f];
+      double zz = (g < n_owned) ? dinv[g] * rg : 0.;
+      if (other >= 0) {
+        if (w1 > 0.) zz += w1 * e[other] + (1. - w1) * ec;
+      } else {
+        zz += w1 * ec;
+      }
+      z[g] = zz;
+      acc += rg * zz;
+    };
+    face(cb, k > 0 ? c - sz : -1);
+    face(cb + 1, j > 0 ? c - sy : -1);
+    face(cb + 2, i > 0 ? c - 1 : -1);
+    if (i + 1 == hx.nx) face(hx.xp(i, j, k), -1);
+    if (j + 1 == hx.ny) face(hx.yp(i, j, k), -1);
+    if (k + 1 == hx.nz) face(hx.zp(i, j, k), -1);
   }
   const double v[1] = {acc};
   finish_reduction<1>(v, partials, counter, dst, sh);
@@ -442,7 +474,11 @@ int mimpy_auxmg_apply(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, const 
                       double* rz_dst, int n_owned) {
   cudaStream_t st = ctx->stream;
   AuxLevel* L = h->lev;
-  k_aux_face_restrict<<<aux_blocks(h->nc), AUX_T, 0, st>>>(h->nc, h->cell_faces, h->face_to_flux, h->wc, r, L[0].b);
+  AuxHex hx;
+  hx.nx = L[0].nx; hx.ny = L[0].ny; hx.nz = L[0].nz;
+  hx.L = hx.nx * hx.ny + hx.nx * (hx.ny + 1) + (hx.nx + 1) * hx.ny;
+  hx.xrow = 3 * hx.nx + 1;
+  k_aux_face_restrict<<<aux_blocks(h->nc), AUX_T, 0, st>>>(hx, h->face_to_flux, h->fw, r, L[0].b);
   const int last = h->nlev - 1;
   auto ghosts = [&](double* v, const AuxLevel& lv) {  // both ghost layers of a level vector
     mimpy_xchg x;
@@ -472,8 +508,8 @@ int mimpy_auxmg_apply(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, const 
     if (h->global && l > 0 && (rc = ghosts(L[l].x2, L[l]))) return rc;
   }
   const int grid = ctx->sm_count * 8;
-  k_aux_face_prolong<<<grid, RED_THREADS, 0, st>>>(h->nf, n_owned, h->face_to_flux, h->face_cell, h->fw,
-                                                   L[0].x2, dinv, r, z, ctx->partials, ctx->counters + 4, rz_dst);
+  k_aux_face_prolong<<<grid, RED_THREADS, 0, st>>>(hx, n_owned, h->face_to_flux, h->fw, L[0].x2, dinv, r, z,
+                                                   ctx->partials, ctx->counters + 4, rz_dst);
   KERNEL_CHECK();
   return MIMPY_OK;
 }
@@ -542,7 +578,7 @@ int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
     mimpy_set_error("auxmg_create: too many levels");
     return MIMPY_E_INVALID;
   }
-  total += pad((size_t)h->nc * 6) + pad((size_t)h->nf * 2) + pad((size_t)h->flux_dof) +
+  total += pad((size_t)h->nc * 6) + pad((size_t)h->nf) + pad((size_t)h->flux_dof) +
            pad((size_t)AUX_COARSEST * AUX_COARSEST);
   static bool pool_configured = false;
   if (!pool_configured) {  // keep freed blocks in the pool: set-up is repeated every Newton step
@@ -578,7 +614,7 @@ int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
   h->gbuf = take(AUX_GLOBAL_MAX);
   h->ginv = take((size_t)AUX_GLOBAL_MAX * AUX_GLOBAL_MAX);
   h->wc = take((size_t)h->nc * 6);
-  h->fw = take((size_t)h->nf * 2);
+  h->fw = take((size_t)h->nf);
   h->tsum = take((size_t)h->flux_dof);
   h->cinv = take((size_t)AUX_COARSEST * AUX_COARSEST);
   *handle = h;
@@ -603,7 +639,7 @@ int mimpy_b200_auxmg_setup(mimpy_ctx* ctx, void* handle, const mimpy_mesh_view* 
   h->face_cell = sym->face_cell;
   h->face_flag = sym->face_flag;
   CUDA_TRY(cudaMemsetAsync(h->tsum, 0, sizeof(double) * (size_t)(h->flux_dof ? h->flux_dof : 1), st));
-  CUDA_TRY(cudaMemsetAsync(h->fw, 0, sizeof(double) * (size_t)h->nf * 2, st));
+  CUDA_TRY(cudaMemsetAsync(h->fw, 0, sizeof(double) * (size_t)h->nf, st));
   k_aux_tau<<<aux_blocks(h->nc), AUX_T, 0, st>>>(h->nc, mesh->cell_faces, sym->face_to_flux, sym->m_ptr,
                                                 mesh->face_geom, w_e, h->wc, h->tsum);
   KERNEL_CHECK();
