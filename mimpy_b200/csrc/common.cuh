@@ -52,6 +52,7 @@ int mimpy_numeric_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mim
                           int method, int flags, const double* multipliers, double alpha,
                           const double* c_diag, double* vals);
 int mimpy_scratch(mimpy_ctx* ctx, size_t bytes, void** out);
+int mimpy_check_device_flag(mimpy_ctx* ctx);  // stream sync + error if a bounded device wait ran out
 // auxmg.cu: z = B r (auxiliary-space multigrid + Jacobi), this rank's share of r.z -> *rz_dst
 struct mimpy_auxmg;
 int mimpy_auxmg_apply(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, const double* r, double* z,

@@ -28,6 +28,21 @@ int mimpy_scratch(mimpy_ctx* ctx, size_t bytes, void** out) {
   return MIMPY_OK;
 }
 
+// Synchronises the stream and reads the device error flag (counters[9]) that the bounded waits of
+// the kernels raise instead of hanging: a wait that ran out is an ERROR, never a silent wrong result.
+int mimpy_check_device_flag(mimpy_ctx* ctx) {
+  unsigned int* host = reinterpret_cast<unsigned int*>(ctx->host_scalars + 32);
+  CUDA_TRY(cudaMemcpyAsync(host, ctx->counters + 9, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (*host != 0u) {
+    CUDA_TRY(cudaMemsetAsync(ctx->counters + 9, 0, sizeof(unsigned int), ctx->stream));
+    mimpy_set_error("a bounded device-side wait timed out (peer-memory exchange with rank neighbours, or the "
+                    "cross-CTA hand-over of the assembly kernel): results are invalid");
+    return MIMPY_E_CUDA;
+  }
+  return MIMPY_OK;
+}
+
 extern "C" {
 
 int mimpy_b200_version(void) { return 100; }
@@ -87,8 +102,7 @@ int mimpy_b200_set_stream(mimpy_ctx* ctx, void* stream) {
 
 int mimpy_b200_sync(mimpy_ctx* ctx) {
   REQUIRE(ctx != nullptr, "ctx is NULL");
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  return MIMPY_OK;
+  return mimpy_check_device_flag(ctx);
 }
 
 int mimpy_b200_set_comm(mimpy_ctx* ctx, void* nccl_comm, int32_t rank, int32_t world) {

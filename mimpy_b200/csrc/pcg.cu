@@ -392,6 +392,14 @@ static int pcg_core(mimpy_ctx* ctx, int32_t n, const SpmvMat& A, const double* d
   CUDA_TRY(cudaEventRecord(ctx->ev1, st));
   CUDA_TRY(cudaEventSynchronize(ctx->ev1));
   CUDA_TRY(cudaEventElapsedTime(&info->ms_total, ctx->ev0, ctx->ev1));
+  if (ctx->world > 1) {  // a peer-memory wait that ran out must not pass as a result
+    rc = mimpy_check_device_flag(ctx);
+    if (rc) {
+      if (gexec) cudaGraphExecDestroy(gexec);
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+  }
   if (gexec) cudaGraphExecDestroy(gexec);
   if (graph) cudaGraphDestroy(graph);
   info->iterations = it;
