@@ -1,31 +1,23 @@
 // Fused numeric assembly for hexahedral meshes (every cell has 6 faces) -- the headline kernel
-// (700 algorithmic bytes per hex cell).  Two kernels share one thread-per-cell core:
+// (700 algorithmic bytes per hex cell).  Three kernels share one thread-per-cell core
+// (cell_core.cuh):
 //
-//  cell_entries<NF, METHOD>: the whole 3xNF / 3x3 pipeline of MFD.build_m_e (mfd.py:357-483,
-//     methods 0, 1, 6) in registers -- no redundant work across lanes (the 3x3 inverse, the two
-//     Cholesky factorisations and their divisions/rsqrts are done once per cell, not once per face).
-//     Orientations are folded into the operands:  R~_i = s_i a_i (x_f - x_E),  KN_i = K n_f, so
-//     that  s_i s_j M_E[i,j] = R~_i . (T^-1 R~_j) + coef_i (d_ij - Q~_i . Q~_j)  directly
-//     (T = R~^T KN, Q~ = orth(KN) by CholeskyQR2; mfd.py:575-588 applies s_i s_j afterwards).
+//  k_numeric_brick2  (structured hex meshes in HexMesh numbering, even nx; the default): a CTA owns a
+//     brick of 8x4x4 cells; inputs staged by cp.async, output image in shared memory laid out like
+//     the CSR value array, cross-brick diagonals by a wait-free swap -- see the comment above it.
+//
+//  k_numeric_brick   (the same bricks for odd nx): per-thread loads; the 464 face rows of the brick
+//     are assembled in a shared-memory row buffer of 13 slots per row and written as whole rows.
 //
 //  k_numeric_direct  (any uniform-6 mesh): each thread stores its 36+13 entries straight from
-//     registers to their CSR slots.  Simple, but every 8-byte store is its own L2 sector write
-//     (48 write sectors per cell measured; the L2 is the busiest unit at 65 %).
-//
-//  k_numeric_brick   (structured hex meshes in HexMesh numbering): a CTA owns a brick of 8x4x4
-//     cells.  The 464 face rows of the brick are ASSEMBLED IN SHARED MEMORY (row buffer of 13
-//     slots per row): for the 2/3 of the rows whose two cells both live in the brick the CTA then
-//     writes the complete row -- M entries of both cells, summed diagonal, both -DIV^T entries -- as
-//     one contiguous 88-104 byte burst (3-4 sectors instead of 13 partial ones).  Rows on the brick
-//     surface are written as the brick's half (the slots the other brick owns stay untouched).
+//     registers to their CSR slots (48 write sectors per cell: the L2 is the busiest unit).
 //
 // Diagonal entries M[g,g] have two contributors (the two cells of face f).  Inside a brick they are
-// added in shared memory in a fixed order (lower cell first).  Across CTAs the lower-index cell
-// PUBLISHES its half in diag_pub[f] and the higher-index cell adds it and writes the slot -- a + b
-// in a fixed order, bit-reproducible, no atomics on the matrix.  CTAs take their cell range / brick
-// from an atomic ticket and bricks are ordered lexicographically (k slowest), so a CTA only ever
-// waits for CTAs that started earlier and are resident (the ordering argument of decoupled
-// look-back scans): no deadlock; the wait is bounded and raises an error flag instead of hanging.
+// added in shared memory in a fixed order.  Across CTAs the two older kernels let the lower-index
+// cell PUBLISH its half in diag_pub[f] and the higher-index cell add it (CTAs take their work from
+// an atomic ticket, bricks ordered lexicographically, so a CTA only ever waits for CTAs that started
+// earlier and are resident; the wait is bounded and raises an error flag instead of hanging).
+// k_numeric_brick2 replaces the wait by an atomic swap of the halves.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -63,20 +55,6 @@ __device__ __forceinline__ double wait_published(const double* slot, unsigned lo
     } while (bits == AU_SENTINEL && ++spins < (1u << 22));
     if (bits == AU_SENTINEL) atomicExch(error_flag, 1u);
   }
-  return __longlong_as_double((long long)bits);
-}
-
-// same, without an earlier optimistic read: load first, sleep only when the half is missing
-__device__ __forceinline__ double read_published(const double* slot, unsigned int* error_flag) {
-  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(slot);
-  unsigned long long bits;
-  unsigned int spins = 0;
-  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(bits) : "l"(src));
-  while (bits == AU_SENTINEL && ++spins < (1u << 22)) {
-    __nanosleep(64);
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(bits) : "l"(src));
-  }
-  if (bits == AU_SENTINEL) atomicExch(error_flag, 1u);
   return __longlong_as_double((long long)bits);
 }
 
@@ -339,8 +317,9 @@ k_numeric_brick(mimpy_mesh_view m, int flags, UniArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// staged brick: same brick, same row buffer, but every input is brought into shared memory by
-// coalesced asynchronous copies (cp.async) instead of per-thread strided loads.  The per-thread
+// staged brick: same brick, but every input is brought into shared memory by coalesced
+// asynchronous copies (cp.async) instead of per-thread strided loads, and the output leaves through an
+// image of the CSR value array.  The per-thread
 // loads of the kernel above touch one 32-byte sector per lane and instruction (53 sectors per
 // cell measured, the L1 data pipe was the busiest unit); here
 //   * the 464 face records of the brick are fetched once (not once per adjacent cell), 4 lanes
@@ -350,9 +329,14 @@ k_numeric_brick(mimpy_mesh_view m, int flags, UniArgs a) {
 //     as contiguous runs;
 //   * face ids come from the closed form of the HexMesh numbering (hexmesh.py:161-234), so no
 //     load depends on another load.
-// The staging area for records/K/centroid/volume ALIASES the row buffer: operands are pulled into
-// registers (R~, KN), then the buffer is sentinel-filled and used as above.
-// Needs hex_nx even (16-byte alignment of the cell runs).
+// The staging area for records/K/centroid/volume ALIASES the output image: operands are pulled into
+// registers (R~, KN), then the image is sentinel-filled (a slot nobody in this brick writes is not
+// stored), filled by the cells and streamed out with consecutive lanes writing consecutive values.
+// Bricks are walked in super-tiles of 4x4x4 so that the two bricks of a shared surface row run
+// close in time and their half rows merge in L2.  Diagonals shared with another brick: both cells
+// swap their half into a face-indexed exchange slot; the second to arrive writes half + half and
+// restores the sentinel -- wait-free, and bit-reproducible because IEEE addition commutes.
+// Needs hex_nx even (16-byte alignment of the cell runs).  History and measurements: DESIGN.md 6.
 // ---------------------------------------------------------------------------------------------
 #define B2_OFF_REC 0
 #define B2_OFF_K (BR_NFACE * 64)
