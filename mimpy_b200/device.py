@@ -424,9 +424,13 @@ class HybridSystem(object):
         except Exception:
             pass
 
-    def solve(self, rhs, rtol=1e-10, atol=0., maxit=20000, check_every=50, use_graph=True, x0=None,
+    def solve(self, rhs, rtol=1e-10, atol=0., maxit=20000, check_every=None, use_graph=True, x0=None,
               raise_on_noconv=True):
-        """Returns (solution [v;p], info). rhs: device tensor of length flux_dof+nc."""
+        """Returns (solution [v;p], info). rhs: device tensor of length flux_dof+nc.
+        check_every: iterations between two convergence checks on the host (default: 5 with the
+        multigrid preconditioner, 50 with Jacobi)."""
+        if check_every is None:
+            check_every = 5 if self.aux is not None else 50
         ctx = self.dmesh.ctx
         dev = ctx.device
         plan = self.plan
