@@ -192,6 +192,15 @@ int mimpy_b200_mfd_numeric(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mi
 
 /* same scatter from already built blocks (m_e, layout of (3)); used when M_E comes from the
  * caller (e.g. mesh-dependent user construction) */
+/* mimpy_b200_mfd_numeric restricted to the cell layers [layer_begin, layer_end) of a structured hex
+ * mesh (both multiples of 4, or layer_end == hex_nz), called for increasing ranges that tile the mesh:
+ * after the call for a range, the CSR rows of the faces k*L .. (in HexMesh numbering, L faces per
+ * layer) of those layers and of their cells are final, so a caller can overlap the download of one
+ * slab with the upload of cell_k for the next (bench.py e2e).  MIMPY_E_UNSUPPORTED when the staged
+ * brick kernel does not apply. */
+int mimpy_b200_mfd_numeric_layers(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
+                                  int32_t method, int32_t flags, const double* multipliers, double alpha,
+                                  const double* c_diag, double* vals, int32_t layer_begin, int32_t layer_end);
 int mimpy_b200_mfd_numeric_from_blocks(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,
                                        const mimpy_symbolic* sym, const double* m_e,
                                        const double* multipliers, double alpha,

@@ -63,6 +63,7 @@ SIGNATURES = {
     "mimpy_b200_mfd_symbolic_sizes": [_vp, _PM, _vp, _PS],
     "mimpy_b200_mfd_symbolic_fill": [_vp, _PM, _PS],
     "mimpy_b200_mfd_numeric": [_vp, _PM, _PS, _i32, _i32, _vp, _f64, _vp, _vp, _vp],
+    "mimpy_b200_mfd_numeric_layers": [_vp, _PM, _PS, _i32, _i32, _vp, _f64, _vp, _vp, _i32, _i32],
     "mimpy_b200_mfd_numeric_from_blocks": [_vp, _PM, _PS, _vp, _vp, _f64, _vp, _vp],
     "mimpy_b200_mfd_coo": [_vp, _PM, _PS, _vp, _vp, _vp, _vp, _vp],
     "mimpy_b200_mfd_rhs": [_vp, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _f64, _vp, _vp],

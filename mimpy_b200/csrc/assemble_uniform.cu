@@ -402,7 +402,7 @@ __device__ __forceinline__ void stage_record(unsigned sbase, const double* face_
 
 template <int METHOD>
 __global__ void __launch_bounds__(BR_THREADS, BR_MINB)
-k_numeric_brick2(mimpy_mesh_view m, int flags, UniArgs a) {
+k_numeric_brick2(mimpy_mesh_view m, int flags, UniArgs a, int bk_begin, int bk_end) {
   constexpr int NF = 6;
   extern __shared__ __align__(128) unsigned char sm[];
   double* row = reinterpret_cast<double*>(sm);
@@ -419,8 +419,8 @@ k_numeric_brick2(mimpy_mesh_view m, int flags, UniArgs a) {
   const int nsx = (nbx + 3) >> 2, nsy = (nby + 3) >> 2;
   const int st = (int)(blockIdx.x >> 6), wi = (int)(blockIdx.x & 63);
   const int bi = (st % nsx) * 4 + (wi & 3), bj = ((st / nsx) % nsy) * 4 + ((wi >> 2) & 3),
-            bk = (st / (nsx * nsy)) * 4 + (wi >> 4);
-  if (bi >= nbx || bj >= nby || bk >= nbz) return;
+            bk = bk_begin + (st / (nsx * nsy)) * 4 + (wi >> 4);  // [bk_begin, bk_end): a slab of brick layers
+  if (bi >= nbx || bj >= nby || bk >= min(nbz, bk_end)) return;
   const int ci0 = bi * BX, cj0 = bj * BY, ck0 = bk * BZ;
   const int runlen = min(BX, nx - ci0);
   const int li = t % BX, lj = (t / BX) % BY, lk = t / (BX * BY);
@@ -711,7 +711,8 @@ static int asm_variant() {
 }
 
 template <int METHOD>
-static int launch_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int flags, const UniArgs& a) {
+static int launch_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int flags, const UniArgs& a,
+                          int bk_begin, int bk_end) {
   const bool structured = mesh->hex_nx > 0 && mesh->hex_ny > 0 && mesh->hex_nz > 0 &&
                           (long long)mesh->hex_nx * mesh->hex_ny * mesh->hex_nz == mesh->nc;
   if (structured && asm_variant() == 2 && mesh->hex_nx % 2 == 0 && !(flags & MIMPY_FLAG_DIRECT_KERNEL)) {
@@ -720,9 +721,13 @@ static int launch_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int flags
       CUDA_TRY(cudaFuncSetAttribute(k_numeric_brick2<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2_SMEM));
       configured2 = true;
     }
+    const int nbz = (mesh->hex_nz + BZ - 1) / BZ;
+    if (bk_end > nbz) bk_end = nbz;
     const long long super_tiles = (long long)(((mesh->hex_nx + BX - 1) / BX + 3) / 4) * (((mesh->hex_ny + BY - 1) / BY + 3) / 4) *
-                                  (((mesh->hex_nz + BZ - 1) / BZ + 3) / 4);
-    k_numeric_brick2<METHOD><<<(unsigned)(super_tiles * 64), BR_THREADS, B2_SMEM, ctx->stream>>>(*mesh, flags, a);
+                                  ((bk_end - bk_begin + 3) / 4);
+    if (super_tiles > 0)
+      k_numeric_brick2<METHOD><<<(unsigned)(super_tiles * 64), BR_THREADS, B2_SMEM, ctx->stream>>>(*mesh, flags, a, bk_begin,
+                                                                                                   bk_end);
   } else if (structured && asm_variant() >= 1 && !(flags & MIMPY_FLAG_DIRECT_KERNEL)) {
     const size_t smem = sizeof(BrickSmem);
     static bool configured = false;
@@ -745,12 +750,18 @@ static int launch_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int flags
 // generic warp-group kernel of local_matrices.cu -- same results, CUDA as well)
 int mimpy_numeric_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
                           int method, int flags, const double* multipliers, double alpha,
-                          const double* c_diag, double* vals) {
+                          const double* c_diag, double* vals, int layer_begin, int layer_end) {
   if (mesh->uniform_faces != 6 || !sym->role || !sym->cell_rowstart) return MIMPY_E_UNSUPPORTED;
   if (method != 0 && method != 1 && method != 6) return MIMPY_E_UNSUPPORTED;
   const bool staged = mesh->hex_nx > 0 && mesh->hex_ny > 0 && mesh->hex_nz > 0 &&
                       (long long)mesh->hex_nx * mesh->hex_ny * mesh->hex_nz == mesh->nc && asm_variant() == 2 &&
                       mesh->hex_nx % 2 == 0 && !(flags & MIMPY_FLAG_DIRECT_KERNEL);
+  // a range of cell layers [layer_begin, layer_end) is only served by the staged brick kernel
+  const bool ranged = !(layer_begin == 0 && layer_end < 0);
+  if (ranged && (!staged || layer_begin % BZ != 0 || (layer_end % BZ != 0 && layer_end != mesh->hex_nz)))
+    return MIMPY_E_UNSUPPORTED;
+  const int bk_begin = ranged ? layer_begin / BZ : 0;
+  const int bk_end = ranged ? (layer_end + BZ - 1) / BZ : 0x3fffffff;
   double* exchange = nullptr;
   if (staged) {
     // persistent exchange slots: set to the sentinel once, kept clean by the kernel itself
@@ -789,7 +800,7 @@ int mimpy_numeric_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mim
   a.ticket = ctx->counters + 8;
   a.error_flag = ctx->counters + 9;
   a.flux_dof = sym->flux_dof;
-  if (method == 0) return launch_uniform<0>(ctx, mesh, flags, a);
-  if (method == 1) return launch_uniform<1>(ctx, mesh, flags, a);
-  return launch_uniform<6>(ctx, mesh, flags, a);
+  if (method == 0) return launch_uniform<0>(ctx, mesh, flags, a, bk_begin, bk_end);
+  if (method == 1) return launch_uniform<1>(ctx, mesh, flags, a, bk_begin, bk_end);
+  return launch_uniform<6>(ctx, mesh, flags, a, bk_begin, bk_end);
 }

@@ -50,7 +50,7 @@ void mimpy_set_error(const char* fmt, ...);
 // uniform-face-count fast path of the numeric assembly (assemble_uniform.cu)
 int mimpy_numeric_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
                           int method, int flags, const double* multipliers, double alpha,
-                          const double* c_diag, double* vals);
+                          const double* c_diag, double* vals, int layer_begin = 0, int layer_end = -1);
 int mimpy_scratch(mimpy_ctx* ctx, size_t bytes, void** out);
 int mimpy_check_device_flag(mimpy_ctx* ctx);  // stream sync + error if a bounded device wait ran out
 // auxmg.cu: z = B r (auxiliary-space multigrid + Jacobi), this rank's share of r.z -> *rz_dst

@@ -490,6 +490,17 @@ int mimpy_b200_mfd_numeric(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mi
   return MIMPY_OK;
 }
 
+int mimpy_b200_mfd_numeric_layers(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
+                                  int32_t method, int32_t flags, const double* multipliers, double alpha,
+                                  const double* c_diag, double* vals, int32_t layer_begin, int32_t layer_end) {
+  REQUIRE(ctx && sym && vals, "NULL argument");
+  int rc = check_mesh(mesh);
+  if (rc) return rc;
+  REQUIRE((flags & 1) || mesh->cell_k, "cell_k is NULL");
+  REQUIRE(layer_begin >= 0 && layer_end > layer_begin && layer_end <= mesh->hex_nz, "bad layer range");
+  return mimpy_numeric_uniform(ctx, mesh, sym, method, flags, multipliers, alpha, c_diag, vals, layer_begin, layer_end);
+}
+
 int mimpy_b200_mfd_numeric_from_blocks(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,
                                        const mimpy_symbolic* sym, const double* m_e,
                                        const double* multipliers, double alpha,

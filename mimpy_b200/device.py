@@ -295,6 +295,37 @@ def numeric(dmesh, plan, method, k_unity=False, multipliers=None, alpha=0., c_di
     return vals
 
 
+def numeric_layers(dmesh, plan, method, vals, layer_begin, layer_end, k_unity=False, multipliers=None, alpha=0.,
+                   c_diag=None):
+    """`numeric` restricted to the cell layers [layer_begin, layer_end) of a structured hex mesh
+    (mimpy_b200_mfd_numeric_layers); returns False when the staged brick kernel does not apply."""
+    ctx = dmesh.ctx
+    with ctx.on_stream():
+        mv = dmesh.view()
+        rc = ctx.call("mimpy_b200_mfd_numeric_layers", C.byref(mv), C.byref(plan.s), int(method),
+                      1 if k_unity else 0, ptr(multipliers), float(alpha), ptr(c_diag), ptr(vals),
+                      int(layer_begin), int(layer_end), allow=(_lib.MIMPY_E_UNSUPPORTED,))
+    return rc == 0
+
+
+def layer_value_ranges(dmesh, plan, bounds):
+    """For cell-layer boundaries k_0 < k_1 < ... of a structured hex mesh: the half-open ranges of
+    the CSR value array that become final with each slab [k_i, k_{i+1}) -- (face rows, cell rows)."""
+    ctx = dmesh.ctx
+    cx, cy, cz = dmesh.hex_dims
+    L = cx * cy + cx * (cy + 1) + (cx + 1) * cy
+    F, nf = plan.flux_dof, dmesh.nf
+    with ctx.on_stream():
+        live = (plan.face_to_flux[:nf] >= 0).to(torch.int32)
+        before = torch.cumsum(live, 0, dtype=torch.int64)            # flux rows up to and including face f
+        fids = [min(k * L, nf) if k < cz else nf for k in bounds]
+        g = [0 if f == 0 else int(before[f - 1].item()) for f in fids]
+        ip = plan.indptr
+        face_off = [int(ip[x].item()) for x in g]
+        cell_off = [int(ip[F + min(k, cz) * cx * cy].item()) for k in bounds]
+    return [((face_off[i], face_off[i + 1]), (cell_off[i], cell_off[i + 1])) for i in range(len(bounds) - 1)]
+
+
 def numeric_from_blocks(dmesh, plan, m_e, multipliers=None, alpha=0., c_diag=None, vals=None):
     ctx = dmesh.ctx
     with ctx.on_stream():

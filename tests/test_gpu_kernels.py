@@ -350,6 +350,38 @@ def test_uniform_fast_path_equals_generic_kernel(ctx, method, n):
     assert np.array_equal(a[ip[F]:], b[ip[F]:])
 
 
+def test_numeric_by_layer_slabs_equals_full_assembly(ctx):
+    """mimpy_b200_mfd_numeric_layers over slabs that tile the mesh reproduces the full assembly bit for
+    bit, and after each slab exactly the value ranges `layer_value_ranges` names are final."""
+    import torch
+    from mimpy_b200 import device
+
+    nx, ny, nz = 12, 9, 22
+    nc = nx * ny * nz
+    rng = np.random.default_rng(8)
+    g = np.exp(rng.standard_normal((nc, 3)))
+    k = np.zeros((nc, 9))
+    k[:, 0], k[:, 4], k[:, 8] = g[:, 0], g[:, 1], g[:, 2]
+    d = device.DeviceMesh.hex(ctx, nx, ny, nz, 1., 1., 1., cell_k=k)
+    hx = HexIndexHost(nx, ny, nz)
+    mask = np.zeros(d.nf, dtype=np.uint8)
+    mask[hx.boundary(2)] = 1
+    mask[hx.boundary(5)] = 1
+    plan = device.symbolic(d, mask)
+    full = H(ctx, device.numeric(d, plan, 1))
+    bounds = [0, 8, 12, 20, 22]
+    ranges = device.layer_value_ranges(d, plan, bounds)
+    assert ranges[0][0][0] == 0 and ranges[-1][1][1] == plan.nnz and ranges[-1][0][1] == ranges[0][1][0]
+    with ctx.on_stream():
+        vals = torch.full((plan.nnz,), float("nan"), dtype=torch.float64, device=ctx.device)
+    for (k0, k1), ((f0, f1), (c0, c1)) in zip(zip(bounds[:-1], bounds[1:]), ranges):
+        assert device.numeric_layers(d, plan, 1, vals, k0, k1)
+        part = H(ctx, vals)
+        assert np.array_equal(part[f0:f1], full[f0:f1]) and np.array_equal(part[c0:c1], full[c0:c1]), (k0, k1)
+    assert np.array_equal(H(ctx, vals), full)
+    assert not device.numeric_layers(d, plan, 1, vals, 2, 8)     # not a multiple of the brick height
+
+
 class HexIndexHost(object):
     """Closed-form HexMesh face numbering (hexmesh.py:161-234) for picking boundary faces by index."""
 
