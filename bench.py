@@ -242,6 +242,21 @@ def run_cuda(args):
 
     check_every = args.check_every if args.check_every > 0 else (5 if args.precond == "auxmg" else 50)
 
+    def owned_norm(v):
+        """||v||_2 of a saddle-sized vector over all ranks (flux rows counted by their owner)."""
+        with ctx.on_stream():
+            s2 = ((v[:pb["n_owned"]] ** 2).sum() + (v[F:] ** 2).sum()).reshape(1).clone()
+        ctx.sync()
+        if world > 1:
+            dist.all_reduce(s2)
+        return float(s2) ** 0.5
+
+    # The PCG stops on ||h - A lambda||_2 <= rtol * ||b||_2, b = the right-hand side of the ORIGINAL
+    # saddle system: the residual of the condensed face system relative to ||b|| tracks the saddle
+    # residual (scripts/study_rtol.py: within 10 %), and rtol = 1e-8 leaves |x - x_spsolve|/|x| <= 1e-8
+    # at n = 16, 24 (spsolve) and 256 (tests/test_gpu_kernels.py::test_bench_path_*).
+    b_norm = owned_norm(rhs)
+
     def step(collect):
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         barrier()
@@ -252,7 +267,7 @@ def run_cuda(args):
             hyb = device.HybridSystem(dm, plan, None, precond=args.precond, method=method)  # fused M_E + set-up
             evs[2].record(ctx.stream)
             sol, info = hyb.solve(rhs, rtol=args.rtol, maxit=args.maxit, check_every=check_every,
-                                  raise_on_noconv=False)
+                                  raise_on_noconv=False, ref_norm=b_norm)
             evs[3].record(ctx.stream)
         ctx.sync()
         barrier()
@@ -327,10 +342,22 @@ def run_cuda(args):
         if world > 1:
             dist.all_reduce(psum)
         p_mean = float(psum) / nc_total
-        saddle_res = None
-        if world == 1:
-            ax = device.spmv(ctx, plan.indptr, plan.indices, vals, sol, n=plan.ndof)
-            saddle_res = float(torch.linalg.norm(ax - rhs) / torch.linalg.norm(rhs))
+        # residual of the ORIGINAL saddle system [M -DIV^T; DIV C][v;p] = b with the assembled CSR; on a
+        # slab partition the interface flux rows are completed by the exchange-add of the two halves
+        res_vec = device.spmv(ctx, plan.indptr, plan.indices, vals, sol, n=plan.ndof) - rhs
+        if world > 1:
+            ctx.call("mimpy_b200_halo_exchange_add", _lib.ptr(res_vec))
+    saddle_res = owned_norm(res_vec) / b_norm
+    sol_p_l2, sol_v_l2 = None, None
+    with ctx.on_stream():
+        zc = torch.zeros_like(sol)
+        zc[F:] = sol[F:]
+    sol_p_l2 = owned_norm(zc)
+    with ctx.on_stream():
+        zc.zero_()
+        zc[:F] = sol[:F]
+    sol_v_l2 = owned_norm(zc)
+    del zc, res_vec
 
     # ---- e2e: pinned host buffers in and out (H2D of K, D2H of the CSR values), every rank its slab.
     # The assembly runs slab by slab (cell layers), so the download of one slab's finished rows
@@ -404,12 +431,16 @@ def run_cuda(args):
                        "cells": nc_total, "face_rows": int(rows_total), "face_system_nnz": int(nnz_total),
                        "partition": "z-slabs x%d" % world, "pcg_collectives": comm,
                        "l2": "inputs larger than L2 (>= %.1f GB touched per step per GPU)" % (ASM_BYTES_PER_CELL * nc_total / world / 1e9),
-                       "pcg": {"preconditioner": args.precond, "rtol": args.rtol, "check_every": check_every}},
+                       "pcg": {"preconditioner": args.precond, "rtol": args.rtol, "check_every": check_every,
+                               "stop": "||h - A lambda||_2 <= rtol * ||b_saddle||_2 (the tolerance that meets "
+                                       "|x - x_spsolve|/|x| <= 1e-8, tests/test_gpu_kernels.py::test_bench_path_vs_spsolve)"}},
             "assembly_ms": asm_ms, "hybrid_setup_ms": float(np.mean([r["setup_ms"] for r in res])),
             "pcg_iters": iters, "pcg_s_per_iter": s_per_iter,
             "solve_time_s": float(np.mean([r["solve_ms"] for r in res])) / 1e3,
             "pcg_rel_residual": res[-1]["residual"] / max(res[-1]["rhs_norm"], 1e-300),
             "saddle_rel_residual": saddle_res, "mean_pressure": p_mean,
+            "solution_norms": {"p_l2": sol_p_l2, "v_l2": sol_v_l2,
+                               "note": "compare across N: the partitioned solves agree with the 1-GPU solve to the PCG tolerance"},
             "roofline": {"bound": "hbm", "achieved": asm_gbs, "peak": peak, "unit": "GB/s", "frac": asm_gbs / peak,
                          "traffic": ASM_TRAFFIC_256 if (n == 256 and world == 1) else None,
                          "kernel": "k_numeric_brick2<1> (fused M_E + CSR assembly), per GPU",

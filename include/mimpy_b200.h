@@ -53,8 +53,13 @@ int mimpy_b200_sync(mimpy_ctx* ctx);
 
 /* ---------------------------------------------------------------------------------------
  * SoA mesh view (device).  face_geom is the packed per-face record
- *   [area, n_x, n_y, n_z, x_f, y_f, z_f, 0]   (8 doubles = 64 B = two 32-B sectors)
- * gathered once per (cell, face) by the M_E kernels.  cell_* arrays keep the reference's own
+ *   [area, n_x | n_y, n_z | x_f, y_f | z_f, bind]   (8 doubles = 64 B = two 32-B sectors)
+ * gathered once per (cell, face) by the M_E kernels.  Written ONLY by mimpy_b200_geom_hex_faces /
+ * mimpy_b200_face_pack: its four 16-byte chunks are stored in an XOR swizzle keyed by the face id (chunk c
+ * at position c ^ ((f >> 1) & 3), csrc/common.cuh) so that runs of records bulk-copied into shared
+ * memory are read without bank conflicts; `bind` belongs to the library (row offset + flux-DOF flags of
+ * the symbolic plan last used with these records; the array is therefore written by the numeric assembly
+ * of structured hex meshes although the view declares it const).  cell_* arrays keep the reference's own
  * layouts (mesh.py:246-255: cell_volume[nc], cell_real_centroid[nc,3], cell_k[nc,9]).
  * ------------------------------------------------------------------------------------- */
 typedef struct {
@@ -169,6 +174,9 @@ typedef struct {
                          (this rank holds the lower-index cell), 2 = ... on the lower neighbour
                          rank.  Interface faces are interior faces of the global problem, not
                          boundary faces, for the hybridised solve.                                */
+  int64_t serial;     /* output of _fill: process-unique id of this plan (> 0).  The pipelined brick
+                         kernel keeps the plan's row offsets inside the face records ("bind" word below)
+                         and re-binds when a different plan is used with the same records.            */
 } mimpy_symbolic;
 
 int mimpy_b200_mfd_symbolic_sizes(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,
@@ -291,6 +299,15 @@ typedef struct {
   double residual;      /* final ||r||_2 (recurrence)                                  */
   double rhs_norm;
   float ms_total;       /* device time of the whole solve (CUDA events)               */
+  /* inputs (zero-initialised = the behaviour above) */
+  int32_t norm_kind;    /* 0: ||r||_2 against rtol * (ref_norm > 0 ? ref_norm : ||h||_2);
+                           1: preconditioned residual, sqrt(r.Br) <= rtol * sqrt(r0.Br0) (r0 = the
+                              residual of the initial guess) -- an estimate of the energy-norm error
+                              that does not depend on how the rows of h are scaled              */
+  double ref_norm;      /* norm_kind 0: reference norm replacing ||h||_2, e.g. the norm of the saddle
+                           right-hand side the face system was condensed from                   */
+  /* outputs */
+  double rz0, rz;       /* r.Br of the initial guess and at the end                            */
 } mimpy_pcg_info;
 
 /* work: 4*n doubles (r, p, Ap, spare) */

@@ -30,13 +30,14 @@ class Symbolic(C.Structure):
                 ("face_to_flux", _vp), ("face_cell", _vp), ("indptr", _vp), ("indices", _vp),
                 ("m_indptr", _vp), ("m_indices", _vp), ("m_ptr", _vp), ("pos_m", _vp),
                 ("pos_dt", _vp), ("pos_d", _vp), ("diag_pos", _vp), ("role", _vp),
-                ("cell_rowstart", _vp), ("face_flag", _vp)]
+                ("cell_rowstart", _vp), ("face_flag", _vp), ("serial", _i64)]
 
 
 class PcgInfo(C.Structure):
     _fields_ = [("rtol", _f64), ("atol", _f64), ("maxit", _i32), ("check_every", _i32),
                 ("use_graph", _i32), ("iterations", _i32), ("residual", _f64), ("rhs_norm", _f64),
-                ("ms_total", C.c_float)]
+                ("ms_total", C.c_float), ("norm_kind", _i32), ("ref_norm", _f64), ("rz0", _f64),
+                ("rz", _f64)]
 
 
 class Fluid(C.Structure):

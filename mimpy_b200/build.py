@@ -17,7 +17,7 @@ INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(HERE, "libmimpy_b200.so")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 
-SOURCES = ["context.cu", "geometry.cu", "symbolic.cu", "local_matrices.cu", "assemble_uniform.cu", "hybrid.cu", "sell.cu", "pcg.cu", "auxmg.cu", "transport.cu",
+SOURCES = ["context.cu", "geometry.cu", "symbolic.cu", "local_matrices.cu", "assemble_uniform.cu", "assemble_brick3.cu", "hybrid.cu", "sell.cu", "pcg.cu", "auxmg.cu", "transport.cu",
            "twophase.cu", "rhs.cu", "comm.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC,

@@ -1,0 +1,567 @@
+// Pipelined brick assembly for structured hex meshes (HexMesh numbering, even nx) -- the headline kernel.
+// Fuses L1-L4 (MFD.build_m_e, mfd.py:357-483) with A2-A5/A8 (build_m / build_div / build_bottom_right /
+// update_m, mfd.py:545-599, 203-246, 745-774, 729-743) like the other kernels of assemble_uniform.cu,
+// but is built around the Blackwell/Hopper bulk-copy engine instead of per-thread loads:
+//
+//   * PERSISTENT CTAs (2 per SM, 128 threads = one brick of 8x4x4 cells at a time) walk the bricks in
+//     super-tile order.  The inputs of a brick -- per x-run of 8 cells: the 24 CONSECUTIVE face records of
+//     its z-/y-/x- faces plus the x+ record of the last cell (1728 B), K (576 B), centroid (192 B), volume
+//     (64 B); plus, per cell row of the brick's upper y / z surface, the record run that holds its y+ / z+
+//     faces -- arrive by 72 1-D bulk copies (cp.async.bulk -> SASS UBLKCP) issued by a dedicated PRODUCER
+//     warp (the fifth warp of the CTA) and tracked by a full/empty pair of mbarriers (expect_tx).  As soon
+//     as the operands of brick n sit in the registers of the four compute warps, the copies for brick n+1
+//     are issued, so they fly during the whole compute / stream-out of brick n: no compute thread ever
+//     forms a load address, and the staging latency that brick2 exposed (cp.async + wait_group 0) is hidden.
+//   * NO symbolic map is read.  The 82 B/cell of pos_m / pos_dt / pos_d / role / cell_rowstart / sigma
+//     of the older kernels are closed-form on a structured hex mesh once two facts per face are known:
+//     the CSR offset of its row and which faces of its two cells are flux DOFs (non-Neumann).  Both live
+//     in the otherwise unused eighth double of the 64-byte face record (`bind`, common.cuh), written
+//     once per (mesh, plan) by k_bind_plan_hex: they arrive with the record, for free.  The position of
+//     entry (i, j) inside row g(f_i) is a popcount over the merged, id-sorted face list of the two cells.
+//   * The output image in shared memory, the cross-brick diagonal swap and the stream-out are those of
+//     k_numeric_brick2 (assemble_uniform.cu).
+//
+// Algorithmic bytes per cell: 296 read (3 records, K, centroid, volume) + 4 (cell row offset) + 368
+// written = 668 (+32 B of the old count that no longer exist).  DESIGN.md 3 keeps the 700 B/cell of
+// SURVEY 8d as the roofline numerator.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "cell_core.cuh"
+#include "assemble_args.cuh"
+
+// ---- shared memory ------------------------------------------------------------------------------
+#define B3_REC_RUN (27 * 64)                        /* 27 record slots per x-run: 3q+d, x+ of cell q at 3q+5 */
+#define B3_SURF_RUN (22 * 64)                       /* records 1..22 (y+) / 0..21 (z+) of a neighbouring run */
+#define B3_OFF_OUT 0
+#define B3_OFF_IN (B2_OUT_SLOTS * 8)                /* input stage (bulk-copy target)                        */
+#define B3_IN_REC 0
+#define B3_IN_YP (B2_RUNS * B3_REC_RUN)             /* y+ records of the last cell row, one run per lk      */
+#define B3_IN_ZP (B3_IN_YP + BZ * B3_SURF_RUN)      /* z+ records of the top cell layer, one run per lj     */
+#define B3_IN_K (B3_IN_ZP + BY * B3_SURF_RUN)
+#define B3_IN_XC (B3_IN_K + BR_THREADS * 72)
+#define B3_IN_VOL (B3_IN_XC + BR_THREADS * 24)
+#define B3_IN_BYTES (B3_IN_VOL + BR_THREADS * 8)
+#define B3_OFF_SMALL (B3_OFF_IN + B3_IN_BYTES)      /* int run_base[16], cell_base[16], extra_rowstart[80]  */
+#define B3_OFF_BAR (B3_OFF_SMALL + (2 * B2_RUNS + B2_EXTRA_ROWS) * 4)
+#define B3_SMEM (B3_OFF_BAR + 16)                   /* full, empty                                           */
+#define B3_THREADS (2 * BR_THREADS)                 /* compute warpgroup + producer warpgroup (one warp of it works) */
+#define B3_REGS_PRODUCER 40                         /* setmaxnreg: 2 CTAs x (128 x 216 + 128 x 40) = 64 K registers  */
+#define B3_REGS_COMPUTE 216
+static_assert(B3_OFF_IN % 128 == 0 && B3_IN_K % 16 == 0 && B3_IN_XC % 16 == 0 && B3_IN_VOL % 16 == 0, "alignment");
+static_assert(B3_OFF_BAR % 8 == 0, "mbarrier alignment");
+
+// ---- mbarrier / bulk copy (PTX ISA 8.x, sm_90+) ----------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// barrier of the four compute warps only (the producer warp runs ahead on its own)
+__device__ __forceinline__ void sync_compute() { asm volatile("bar.sync 1, %0;" ::"n"(BR_THREADS) : "memory"); }
+// bounded: a transfer that never completes raises the device error flag instead of hanging the GPU
+__device__ __forceinline__ bool mbar_wait(unsigned bar, unsigned parity, unsigned int* error_flag) {
+  unsigned done = 0, spins = 0;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done && ++spins < (1u << 24));
+  if (!done) atomicExch(error_flag, 2u);
+  return done != 0;
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- plan binding of the face records ---------------------------------------------------------------
+// bind = { low word: indptr[g(f)] or -1 ; high word: bits 0-5 "present" (flux DOF) flags of the six faces
+// of the cell that lists f at local index >= 3 (its x+/y+/z+ face), bits 8-13 those of the cell that lists
+// it at local index < 3; 0 where there is no such cell }
+__global__ void __launch_bounds__(256)
+k_bind_plan_hex(int nf, const int* __restrict__ face_cell, const int* __restrict__ cell_faces,
+                const int* __restrict__ f2f, const int* __restrict__ indptr, double* __restrict__ geom) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  unsigned field[2] = {0u, 0u};
+  for (int s = 0; s < 2; ++s) {
+    const int c = face_cell[2 * (size_t)f + s];
+    if (c < 0) continue;
+    unsigned bits = 0;
+    int li = -1;
+    for (int q = 0; q < 6; ++q) {
+      const int fq = cell_faces[6 * (size_t)c + q];
+      if (fq == f) li = q;
+      if (f2f[fq] >= 0) bits |= 1u << q;
+    }
+    field[li >= 3 ? 0 : 1] = bits;
+  }
+  const int g = f2f[f];
+  const unsigned lo = (unsigned)(g >= 0 ? indptr[g] : -1);
+  const unsigned long long w = (unsigned long long)lo | ((unsigned long long)(field[0] | (field[1] << 8)) << 32);
+  double2* chunk = reinterpret_cast<double2*>(geom + 8 * (size_t)f) + rec_pos(f, 3);
+  chunk->y = __longlong_as_double((long long)w);
+}
+
+// position of face j of the cell among the id-sorted union of the faces of the two cells of face i
+// (HexMesh numbering, hexmesh.py:161-234; derivation in DESIGN.md 3): index in the merged list
+__device__ __forceinline__ constexpr int merged_index(int i, int j) {
+  constexpr int Q[6][6] = {{5, 6, 7, 8, 9, 10},   // z- : this cell is the upper one of a z face
+                           {4, 5, 6, 7, 8, 10},   // y-
+                           {3, 4, 5, 6, 8, 10},   // x-
+                           {0, 1, 2, 5, 7, 9},    // x+ : this cell is the lower one of an x face
+                           {0, 1, 2, 3, 5, 9},    // y+
+                           {0, 1, 2, 3, 4, 5}};   // z+
+  return Q[i][j];
+}
+// present flags of the merged list of face i; p1 = flags of the lower cell (0: none), p2 = upper cell
+__device__ __forceinline__ unsigned merged_present(int i, unsigned p1, unsigned p2) {
+  if (i == 0 || i == 5) return (p1 & 0x1Fu) | 0x20u | (((p2 >> 1) & 0x1Fu) << 6);
+  if (i == 1 || i == 4)
+    return (p1 & 0xFu) | ((p2 & 1u) << 4) | 0x20u | (((p2 >> 2) & 7u) << 6) | (((p1 >> 5) & 1u) << 9) | (((p2 >> 5) & 1u) << 10);
+  return (p1 & 7u) | ((p2 & 3u) << 3) | 0x20u | (((p2 >> 3) & 1u) << 6) | (((p1 >> 4) & 1u) << 7) | (((p2 >> 4) & 1u) << 8) |
+         (((p1 >> 5) & 1u) << 9) | (((p2 >> 5) & 1u) << 10);
+}
+
+struct B3Geo {
+  int nx, ny, nz, L, xrow;
+  int nbx, nby, nsx, nsy, bk_begin, bk_end;
+  int total;  // linear brick indices (super-tile order), some of them outside the mesh
+};
+
+__device__ __forceinline__ bool b3_decode(const B3Geo& g, int b, int& bi, int& bj, int& bk) {
+  const int st = b >> 6, wi = b & 63;
+  bi = (st % g.nsx) * 4 + (wi & 3);
+  bj = ((st / g.nsx) % g.nsy) * 4 + ((wi >> 2) & 3);
+  bk = g.bk_begin + (st / (g.nsx * g.nsy)) * 4 + (wi >> 4);
+  return bi < g.nbx && bj < g.nby && bk < g.bk_end;
+}
+
+// the producer warp issues every bulk copy of brick (bi, bj, bk) into the input stage and arms the barrier
+__device__ __forceinline__ void b3_issue(const mimpy_mesh_view& m, const B3Geo& g, bool k_unity, int bi, int bj, int bk,
+                                         unsigned in_base, unsigned bar, int lane) {
+  const int ci0 = bi * BX, cj0 = bj * BY, ck0 = bk * BZ;
+  const int runlen = min(BX, g.nx - ci0);
+  const bool row_end = ci0 + runlen >= g.nx;  // the run ends at the mesh boundary: its last x+ face follows directly
+  unsigned bytes = 0;
+  {  // per x-run: lanes 0-15 the records of the z-/y-/x- faces incl. the x+ face of the last cell, and the
+     // volumes; lanes 16-31 K and the centroids
+    const int r = lane & 15, lj = r & 3, lk = r >> 2;
+    const int cj = cj0 + lj, ck = ck0 + lk;
+    if (cj < g.ny && ck < g.nz) {
+      const int cbase0 = ck * g.L + cj * g.xrow + 3 * ci0;
+      const size_t cell0 = (size_t)ci0 + (size_t)g.nx * ((size_t)cj + (size_t)g.ny * ck);
+      if (lane < 16) {
+        const unsigned nrec = row_end ? 3 * runlen + 1 : 3 * runlen + 3;
+        bulk_g2s(in_base + B3_IN_REC + r * B3_REC_RUN, m.face_geom + 8 * (size_t)cbase0, nrec * 64, bar);
+        bulk_g2s(in_base + B3_IN_VOL + r * (BX * 8), m.cell_volume + cell0, runlen * 8, bar);
+        bytes += nrec * 64 + runlen * 8;
+      } else {
+        if (!k_unity) {
+          bulk_g2s(in_base + B3_IN_K + r * (BX * 72), m.cell_k + 9 * cell0, runlen * 72, bar);
+          bytes += runlen * 72;
+        }
+        bulk_g2s(in_base + B3_IN_XC + r * (BX * 24), m.cell_centroid + 3 * cell0, runlen * 24, bar);
+        bytes += runlen * 24;
+      }
+    }
+  }
+  if (lane < 8) {  // y+ records of the last cell row (lanes 0-3: one per lk), z+ records of the top layer (4-7: per lj)
+    const int l = lane & 3;
+    if (lane < 4) {
+      const int ck = ck0 + l, cjl = min(cj0 + BY - 1, g.ny - 1);
+      if (ck < g.nz) {
+        // inside the mesh they are the y- faces (record 3q+1) of the next cell row; on the boundary a run of their own
+        const bool inner = cjl + 1 < g.ny;
+        const int f0 = inner ? ck * g.L + (cjl + 1) * g.xrow + 3 * ci0 + 1 : ck * g.L + g.ny * g.xrow + ci0;
+        const unsigned nrec = inner ? 3 * runlen - 2 : runlen;
+        bulk_g2s(in_base + B3_IN_YP + l * B3_SURF_RUN, m.face_geom + 8 * (size_t)f0, nrec * 64, bar);
+        bytes += nrec * 64;
+      }
+    } else {
+      const int cj = cj0 + l, ckl = min(ck0 + BZ - 1, g.nz - 1);
+      if (cj < g.ny) {
+        const bool inner = ckl + 1 < g.nz;
+        const int f0 = inner ? (ckl + 1) * g.L + cj * g.xrow + 3 * ci0 : g.nz * g.L + cj * g.nx + ci0;
+        const unsigned nrec = inner ? 3 * runlen - 2 : runlen;
+        bulk_g2s(in_base + B3_IN_ZP + l * B3_SURF_RUN, m.face_geom + 8 * (size_t)f0, nrec * 64, bar);
+        bytes += nrec * 64;
+      }
+    }
+  }
+  bytes = __reduce_add_sync(0xffffffffu, bytes);
+  if (lane == 0) mbar_arrive_expect_tx(bar, bytes);
+}
+
+#ifndef B3_MINB
+#define B3_MINB 2
+#endif
+
+template <int METHOD>
+__global__ void __launch_bounds__(B3_THREADS, B3_MINB)
+k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
+  constexpr int NF = 6;
+  extern __shared__ __align__(128) unsigned char sm[];
+  double* row = reinterpret_cast<double*>(sm + B3_OFF_OUT);
+  const unsigned char* in = sm + B3_OFF_IN;
+  int* s_runbase = reinterpret_cast<int*>(sm + B3_OFF_SMALL);
+  int* s_cellbase = s_runbase + B2_RUNS;
+  int* s_extra_rs = s_cellbase + B2_RUNS;
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm);
+  const unsigned bar_full = sbase + B3_OFF_BAR, bar_empty = bar_full + 8, in_base = sbase + B3_OFF_IN;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int nx = g.nx, ny = g.ny, nz = g.nz, L = g.L, xrow = g.xrow;
+  const bool k_unity = flags & 1;
+
+  int b = blockIdx.x, bi, bj, bk;
+  while (b < g.total && !b3_decode(g, b, bi, bj, bk)) b += gridDim.x;
+  if (t == 0) {
+    mbar_init(bar_full, 1);            // the producer's arrive.expect_tx
+    mbar_init(bar_empty, BR_THREADS / 32);  // one arrival per compute warp
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (b >= g.total) return;
+
+  if (warp >= BR_THREADS / 32) {
+    // ---- producer warpgroup: gives its registers to the compute warpgroup; one warp runs one brick
+    // ahead of the compute warps ----
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B3_REGS_PRODUCER));
+    if (warp != BR_THREADS / 32) return;
+    unsigned it = 0;
+    while (b < g.total) {
+      if (it > 0) {
+        // the operands of the previous brick are in registers
+        if (!mbar_wait(bar_empty, (it - 1) & 1u, a.error_flag)) return;
+        fence_proxy_async();
+      }
+      b3_issue(m, g, k_unity, bi, bj, bk, in_base, bar_full, lane);
+      ++it;
+      b += gridDim.x;
+      while (b < g.total && !b3_decode(g, b, bi, bj, bk)) b += gridDim.x;
+    }
+    return;
+  }
+
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(B3_REGS_COMPUTE));
+  const int li = t % BX, lj = (t / BX) % BY, lk = t / (BX * BY);
+  const int run = t >> 3;
+  // per-cell scalars that no bulk copy brings: offset of the cell's CSR row, multiplier, C diagonal
+  int crow = 0;
+  double mult = 1., cdiag = 0.;
+  auto prefetch = [&](int pbi, int pbj, int pbk, int& pcrow, double& pmult, double& pcdiag) {
+    const int ci = pbi * BX + li, cj = pbj * BY + lj, ck = pbk * BZ + lk;
+    pcrow = 0;
+    pmult = 1.;
+    pcdiag = 0.;
+    if (ci < nx && cj < ny && ck < nz) {
+      const size_t cell = (size_t)ci + (size_t)nx * ((size_t)cj + (size_t)ny * ck);
+      pcrow = __ldg(a.indptr + a.flux_dof + cell);
+      if (a.multipliers) pmult = __ldg(a.multipliers + cell);
+      if (a.c_diag) pcdiag = __ldg(a.c_diag + cell);
+    }
+  };
+  prefetch(bi, bj, bk, crow, mult, cdiag);
+  unsigned phase = 0;
+
+  while (true) {
+    int bn = b + gridDim.x, nbi = 0, nbj = 0, nbk = 0;
+    while (bn < g.total && !b3_decode(g, bn, nbi, nbj, nbk)) bn += gridDim.x;
+
+    // sentinel-fill the output image (free since the barrier that ended the previous brick): a slot
+    // nobody in this brick writes is not stored
+    {
+      const ulonglong2 s2 = make_ulonglong2(AU_SENTINEL, AU_SENTINEL);
+      ulonglong2* r2 = reinterpret_cast<ulonglong2*>(sm + B3_OFF_OUT);
+#pragma unroll 4
+      for (int e = t; e < B2_OUT_SLOTS / 2; e += BR_THREADS) r2[e] = s2;
+      if (t < B2_EXTRA_ROWS) s_extra_rs[t] = 0;
+    }
+    const int ci0 = bi * BX, cj0 = bj * BY, ck0 = bk * BZ;
+    const int ci = ci0 + li, cj = cj0 + lj, ck = ck0 + lk;
+    const bool ok = ci < nx && cj < ny && ck < nz;
+    const int cbase = ck * L + cj * xrow + 3 * ci;  // global ids of faces z-, y-, x- are cbase + 0, 1, 2
+    const int fid[NF] = {cbase, cbase + 1, cbase + 2,
+                         ci + 1 < nx ? cbase + 5 : ck * L + cj * xrow + 3 * nx,
+                         cj + 1 < ny ? cbase + xrow + 1 : ck * L + ny * xrow + ci,
+                         ck + 1 < nz ? cbase + L : nz * L + cj * nx + ci};
+    const bool in_brick[NF] = {lk > 0, lj > 0, li > 0, li < BX - 1, lj < BY - 1, lk < BZ - 1};
+
+    if (!mbar_wait(bar_full, phase, a.error_flag)) return;  // (uniform: every compute thread waits on the same phase)
+    phase ^= 1u;
+
+    // ---- pull: operands into registers ----
+    CellOps<NF> o;
+    int rs[NF];
+    unsigned mp[NF], me = 0, other_mask = 0;  // other_mask bit i: face i has a second cell
+    double sa[NF], vol = 0., trk = 1.;
+    if (ok) {
+      double K[9], xc[3], sgn[NF];
+      double2 rec[NF][4];
+      int off[NF];
+      off[0] = B3_IN_REC + run * B3_REC_RUN + (3 * li) * 64;
+      off[1] = off[0] + 64;
+      off[2] = off[0] + 128;
+      off[3] = off[0] + (ci + 1 < nx ? 5 : 3) * 64;  // the mesh-boundary x+ face follows the run directly
+      off[4] = (lj < BY - 1 && cj + 1 < ny) ? B3_IN_REC + (run + 1) * B3_REC_RUN + (3 * li + 1) * 64
+                                            : B3_IN_YP + lk * B3_SURF_RUN + (cj + 1 < ny ? 3 * li : li) * 64;
+      off[5] = (lk < BZ - 1 && ck + 1 < nz) ? B3_IN_REC + (run + BY) * B3_REC_RUN + (3 * li) * 64
+                                            : B3_IN_ZP + lj * B3_SURF_RUN + (ck + 1 < nz ? 3 * li : li) * 64;
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        const int key = (fid[i] >> 1) & 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rec[i][q] = *reinterpret_cast<const double2*>(in + off[i] + ((q ^ key) << 4));
+      }
+      if (k_unity) {
+#pragma unroll
+        for (int q = 0; q < 9; ++q) K[q] = (q % 4 == 0) ? 1. : 0.;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 9; ++q) K[q] = *reinterpret_cast<const double*>(in + B3_IN_K + t * 72 + q * 8);
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) xc[q] = *reinterpret_cast<const double*>(in + B3_IN_XC + t * 24 + q * 8);
+      vol = *reinterpret_cast<const double*>(in + B3_IN_VOL + t * 8);
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        const unsigned long long w = (unsigned long long)__double_as_longlong(rec[i][3].y);
+        rs[i] = (int)(unsigned)(w & 0xffffffffull);
+        const unsigned hi = (unsigned)(w >> 32);
+        const unsigned p1 = hi & 63u, p2 = (hi >> 8) & 63u;  // lower cell, upper cell of the face
+        mp[i] = merged_present(i, p1, p2);
+        if (i == 0) me = p2;
+        if ((i < 3 ? p1 : p2) != 0u) other_mask |= 1u << i;
+        sgn[i] = i < 3 ? -1. : 1.;  // hexmesh.py:329-342
+        sa[i] = sgn[i] * rec[i][0].x;
+      }
+      trk = K[0] + K[4] + K[8];
+      cell_prep<NF, METHOD>(K, xc, rec, sgn, o);
+    }
+    {  // CSR offset of the run's first face row (rows z-, y-, x- of a cell ascend) and first cell row
+      int first = 0x7fffffff;
+      if (ok) first = rs[0] >= 0 ? rs[0] : rs[1] >= 0 ? rs[1] : rs[2] >= 0 ? rs[2] : 0x7fffffff;
+#pragma unroll
+      for (int d = 4; d > 0; d >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, d));
+      if (li == 0) {
+        s_runbase[run] = first;
+        s_cellbase[run] = crow;
+      }
+    }
+    // the input stage is consumed: hand it back to the producer, whose copies for the next brick fly
+    // during everything below
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty);
+    sync_compute();  // the image is filled, run bases are visible
+
+    int crow_n = 0;
+    double mult_n = 1., cdiag_n = 0.;
+    if (bn < g.total) prefetch(nbi, nbj, nbk, crow_n, mult_n, cdiag_n);
+
+    double diag[NF];
+    unsigned long long other[NF];
+    int sb[NF];  // where slot 0 of the face's row lives in the output image
+    if (ok) {
+      const int rb = s_runbase[run];
+      sb[0] = run * B2_RUN_SLOTS + rs[0] - rb;
+      sb[1] = run * B2_RUN_SLOTS + rs[1] - rb;
+      sb[2] = run * B2_RUN_SLOTS + rs[2] - rb;
+      if (li < BX - 1 && ci + 1 < nx) {
+        sb[3] = run * B2_RUN_SLOTS + rs[3] - rb;
+      } else {
+        sb[3] = B2_EXTRA0 + run * BR_RW;
+        s_extra_rs[run] = rs[3];
+      }
+      if (lj < BY - 1 && cj + 1 < ny) {
+        sb[4] = (run + 1) * B2_RUN_SLOTS + rs[4] - s_runbase[run + 1];
+      } else {
+        sb[4] = B2_EXTRA0 + (B2_RUNS + lk * BX + li) * BR_RW;
+        s_extra_rs[B2_RUNS + lk * BX + li] = rs[4];
+      }
+      if (lk < BZ - 1 && ck + 1 < nz) {
+        sb[5] = (run + BY) * B2_RUN_SLOTS + rs[5] - s_runbase[run + BY];
+      } else {
+        sb[5] = B2_EXTRA0 + (B2_RUNS + BX * BZ + lj * BX + li) * BR_RW;
+        s_extra_rs[B2_RUNS + BX * BZ + lj * BX + li] = rs[5];
+      }
+      const int cb = B2_CELL0 + run * B2_CELL_SLOTS + (crow - s_cellbase[run]);
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        if (rs[i] >= 0) {
+          // -DIV^T: behind the M entries of the row, the lower-index cell first   mfd.py:240-243
+          row[sb[i] + __popc(mp[i]) + ((i < 3 && ((other_mask >> i) & 1u)) ? 1 : 0)] = -sa[i];
+          row[cb + __popc(me & ((1u << i) - 1u))] = sa[i];          // DIV      mfd.py:232-238
+        }
+      }
+      row[cb + __popc(me)] = a.c_diag ? cdiag : a.alpha * vol;      // mfd.py:766-772
+      cell_core<NF, METHOD>(o, trk, vol, mult, [&](int i, int j, double v) {
+        if (i == j) {
+          diag[i] = v;
+        } else if (rs[i] >= 0 && ((me >> j) & 1u)) {
+          row[sb[i] + __popc(mp[i] & ((1u << merged_index(i, j)) - 1u))] = v;
+        }
+      });
+      // diagonals, step 1: single-cell faces and the LOWER cell of faces inside the brick go to the
+      // image.  A face shared with ANOTHER brick: both cells swap their half into diag_pub[f]
+      // (all-sentinel between launches); whoever finds the other's half there -- the second to arrive --
+      // writes half + half to the CSR slot and restores the sentinel (step 3).  IEEE addition commutes,
+      // so the result does not depend on the arrival order: bit-reproducible, and nobody ever waits.
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        other[i] = AU_SENTINEL;
+        if (rs[i] < 0) continue;
+        const bool shared = (other_mask >> i) & 1u;
+        if (!shared || (i >= 3 && in_brick[i])) row[sb[i] + __popc(mp[i] & 0x1Fu)] = diag[i];
+        if (shared && !in_brick[i])
+          other[i] = atomicExch(reinterpret_cast<unsigned long long*>(a.diag_pub) + fid[i],
+                                (unsigned long long)__double_as_longlong(diag[i]));
+      }
+    }
+    sync_compute();
+    if (ok) {  // diagonals, step 2: the UPPER cell adds its half (lower + upper, fixed order)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (rs[i] >= 0 && ((other_mask >> i) & 1u) && in_brick[i]) {
+          const int slot = sb[i] + __popc(mp[i] & 0x1Fu);
+          row[slot] = row[slot] + diag[i];
+        }
+      }
+    }
+    sync_compute();
+    // stream the image out; consecutive lanes write consecutive CSR values.  A sentinel has an
+    // all-ones high word, which no finite value has.
+    {  // face rows of the runs: 312 slots = 128 + 128 + 56 per run, addresses fixed per thread
+      static_assert(B2_RUN_SLOTS > 2 * BR_THREADS && B2_RUN_SLOTS <= 3 * BR_THREADS, "three passes per run");
+      const double* q = row + t;
+      double* out = a.vals + t;
+#pragma unroll 4
+      for (int r = 0; r < B2_RUNS; ++r, q += B2_RUN_SLOTS) {
+        const int base = s_runbase[r];
+        if (base == 0x7fffffff) continue;
+        const double v0 = q[0], v1 = q[BR_THREADS];
+        const double v2 = t < B2_RUN_SLOTS - 2 * BR_THREADS ? q[2 * BR_THREADS] : __longlong_as_double(-1ll);
+        double* op = out + base;
+        if (__double2hiint(v0) != -1) op[0] = v0;
+        if (__double2hiint(v1) != -1) op[BR_THREADS] = v1;
+        if (__double2hiint(v2) != -1) op[2 * BR_THREADS] = v2;
+      }
+    }
+    {  // cell rows: two runs per pass, 56 of 64 lanes each
+      const int half = t >> 6, l = t & 63;
+      if (l < B2_CELL_SLOTS) {
+#pragma unroll
+        for (int r = half; r < B2_RUNS; r += 2) {
+          const double v = row[B2_CELL0 + r * B2_CELL_SLOTS + l];
+          if (__double2hiint(v) != -1) a.vals[s_cellbase[r] + l] = v;
+        }
+      }
+    }
+    if (t < 8 * BR_RW) {  // rows on the brick's upper surfaces: 8 rows x 13 slots per pass
+      const int r0 = t / BR_RW, pos = t - r0 * BR_RW;
+#pragma unroll
+      for (int e = r0; e < B2_EXTRA_ROWS; e += 8) {
+        const double v = row[B2_EXTRA0 + e * BR_RW + pos];
+        if (__double2hiint(v) != -1) a.vals[s_extra_rs[e] + pos] = v;
+      }
+    }
+    // diagonals, step 3: second arrivals at a face shared with another brick finish the slot
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        if (other[i] != AU_SENTINEL) {
+          a.vals[rs[i] + __popc(mp[i] & 0x1Fu)] = __longlong_as_double((long long)other[i]) + diag[i];
+          reinterpret_cast<unsigned long long*>(a.diag_pub)[fid[i]] = AU_SENTINEL;  // leave the slot clean
+        }
+      }
+    }
+    if (bn >= g.total) break;
+    sync_compute();  // every read of the image is done before the next brick refills it
+    b = bn;
+    bi = nbi;
+    bj = nbj;
+    bk = nbk;
+    crow = crow_n;
+    mult = mult_n;
+    cdiag = cdiag_n;
+  }
+}
+
+bool mimpy_brick3_applies(const mimpy_mesh_view* mesh, const mimpy_symbolic* sym, int method, int flags) {
+  const bool structured = mesh->hex_nx > 0 && mesh->hex_ny > 0 && mesh->hex_nz > 0 &&
+                          (long long)mesh->hex_nx * mesh->hex_ny * mesh->hex_nz == mesh->nc;
+  if (!structured || mesh->uniform_faces != 6 || mesh->hex_nx % 2 != 0) return false;
+  if (method != 0 && method != 1 && method != 6) return false;
+  if (flags & (MIMPY_FLAG_DIRECT_KERNEL | MIMPY_FLAG_GENERIC_KERNEL)) return false;
+  if (!sym->face_cell || !sym->face_to_flux || !sym->indptr || sym->serial == 0) return false;
+  // bulk copies need 16-byte aligned sources
+  const uintptr_t al = (uintptr_t)mesh->face_geom | (uintptr_t)mesh->cell_k | (uintptr_t)mesh->cell_centroid |
+                       (uintptr_t)mesh->cell_volume;
+  return (al & 15u) == 0;
+}
+
+// Writes the plan binding into the face records unless `sym` is the plan already bound to them.
+static int bind_plan(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym) {
+  if (ctx->bound_geom == (const void*)mesh->face_geom && ctx->bound_serial == (long long)sym->serial) return MIMPY_OK;
+  const int T = 256;
+  k_bind_plan_hex<<<(mesh->nf + T - 1) / T, T, 0, ctx->stream>>>(mesh->nf, sym->face_cell, mesh->cell_faces, sym->face_to_flux,
+                                                                sym->indptr, const_cast<double*>(mesh->face_geom));
+  KERNEL_CHECK();
+  ctx->bound_geom = mesh->face_geom;
+  ctx->bound_serial = (long long)sym->serial;
+  return MIMPY_OK;
+}
+
+template <int METHOD>
+static int launch_brick3(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int flags, const UniArgs& a, const B3Geo& g) {
+  CUDA_TRY(cudaFuncSetAttribute(k_numeric_brick3<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B3_SMEM));
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    const char* e = getenv("MIMPY_B200_B3_CTAS");
+    per_sm = e ? atoi(e) : B3_MINB;
+    if (per_sm < 1) per_sm = 1;
+  }
+  long long grid = (long long)ctx->sm_count * per_sm;
+  if (grid > g.total) grid = g.total;
+  k_numeric_brick3<METHOD><<<(unsigned)grid, B3_THREADS, B3_SMEM, ctx->stream>>>(*mesh, flags, a, g);
+  KERNEL_CHECK();
+  return MIMPY_OK;
+}
+
+int mimpy_numeric_brick3(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym, int method,
+                         int flags, const UniArgs& a, int bk_begin, int bk_end) {
+  int rc = bind_plan(ctx, mesh, sym);
+  if (rc) return rc;
+  B3Geo g;
+  g.nx = mesh->hex_nx;
+  g.ny = mesh->hex_ny;
+  g.nz = mesh->hex_nz;
+  g.L = g.nx * g.ny + g.nx * (g.ny + 1) + (g.nx + 1) * g.ny;  // nf < 2^31 (checked by hex_topology)
+  g.xrow = 3 * g.nx + 1;
+  g.nbx = (g.nx + BX - 1) / BX;
+  g.nby = (g.ny + BY - 1) / BY;
+  const int nbz = (g.nz + BZ - 1) / BZ;
+  g.nsx = (g.nbx + 3) >> 2;
+  g.nsy = (g.nby + 3) >> 2;
+  g.bk_begin = bk_begin;
+  g.bk_end = bk_end < nbz ? bk_end : nbz;
+  const long long super_tiles = (long long)g.nsx * g.nsy * ((g.bk_end - g.bk_begin + 3) / 4);
+  if (super_tiles <= 0) return MIMPY_OK;
+  if (super_tiles * 64 > 0x7fffffffLL) return MIMPY_E_UNSUPPORTED;
+  g.total = (int)(super_tiles * 64);
+  if (method == 0) return launch_brick3<0>(ctx, mesh, flags, a, g);
+  if (method == 1) return launch_brick3<1>(ctx, mesh, flags, a, g);
+  return launch_brick3<6>(ctx, mesh, flags, a, g);
+}

@@ -22,25 +22,7 @@
 
 #include "common.cuh"
 #include "cell_core.cuh"
-
-#define AU_SENTINEL 0xFFFFFFFFFFFFFFFFull  // memset(0xFF): a NaN no arithmetic produces
-
-struct UniArgs {
-  const int* indptr;
-  const uint8_t* pos_m;
-  const uint8_t* pos_dt;
-  const uint8_t* pos_d;
-  const int* cell_rowstart;
-  const uint8_t* role;  // per (cell, face): 0 sole cell, 1 lower cell (publish), 2 higher (finish)
-  const double* multipliers;
-  const double* c_diag;
-  double alpha;
-  double* vals;
-  double* diag_pub;
-  unsigned int* ticket;
-  unsigned int* error_flag;
-  int flux_dof;
-};
+#include "assemble_args.cuh"
 
 // bounded wait for the half published by the lower-index cell
 __device__ __forceinline__ double wait_published(const double* slot, unsigned long long first,
@@ -119,9 +101,8 @@ __device__ __forceinline__ void load_records(const mimpy_mesh_view& m, const int
                                              double2 (&rec)[NF][4]) {
 #pragma unroll
   for (int i = 0; i < NF; ++i) {
-    const double2* p = reinterpret_cast<const double2*>(m.face_geom + 8 * (size_t)fid[i]);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) rec[i][q] = __ldg(p + q);
+    for (int q = 0; q < 4; ++q) rec[i][q] = __ldg(rec_chunk(m.face_geom, (size_t)fid[i], q));
   }
 }
 
@@ -189,16 +170,6 @@ k_numeric_direct(mimpy_mesh_view m, int flags, UniArgs a) {
 // ---------------------------------------------------------------------------------------------
 // brick: 8x4x4 cells per CTA, face rows assembled in shared memory, whole-row bursts
 // ---------------------------------------------------------------------------------------------
-#define BX 8
-#define BY 4
-#define BZ 4
-#define BR_THREADS (BX * BY * BZ)
-#define BR_NZF (BX * BY * (BZ + 1))
-#define BR_NYF (BX * (BY + 1) * BZ)
-#define BR_NXF ((BX + 1) * BY * BZ)
-#define BR_NFACE (BR_NZF + BR_NYF + BR_NXF)
-#define BR_RW 13  // 11 M entries of an interior row + 2 (-DIV^T); longer rows cannot occur on a hex mesh
-
 struct BrickSmem {
   double row[BR_NFACE * BR_RW];
   int rowstart[BR_NFACE];
@@ -342,18 +313,6 @@ k_numeric_brick(mimpy_mesh_view m, int flags, UniArgs a) {
 #define B2_OFF_K (BR_NFACE * 64)
 #define B2_OFF_XC (B2_OFF_K + BR_THREADS * 72)
 #define B2_OFF_VOL (B2_OFF_XC + BR_THREADS * 24)
-// output image in shared memory, laid out like the CSR value array itself:
-//   16 x-runs x 312 slots : the 24 face rows (z-, y-, x- of 8 cells) of a run are CONSECUTIVE CSR rows,
-//                           so a run is one contiguous piece of `vals` (<= 24 * 13 values)
-//   80 extra rows x 13    : x+ faces of the last cell column, y+ of the last row, z+ of the top layer
-//   16 x-runs x 56 slots  : the cell rows (DIV + C diagonal, <= 7 values per cell) of a run
-#define B2_RUNS (BY * BZ)
-#define B2_RUN_SLOTS (3 * BX * BR_RW)
-#define B2_EXTRA_ROWS (BY * BZ + BX * BZ + BX * BY)
-#define B2_EXTRA0 (B2_RUNS * B2_RUN_SLOTS)
-#define B2_CELL0 (B2_EXTRA0 + B2_EXTRA_ROWS * BR_RW)
-#define B2_CELL_SLOTS (BX * 7)
-#define B2_OUT_SLOTS (B2_CELL0 + B2_RUNS * B2_CELL_SLOTS)
 #define B2_OFF_ROWSTART (B2_OUT_SLOTS * 8)   /* int run_base[16], cell_base[16], extra_rowstart[80] */
 #define B2_OFF_CRS (B2_OFF_ROWSTART + (2 * B2_RUNS + B2_EXTRA_ROWS) * 4)
 #define B2_OFF_PM (B2_OFF_CRS + BR_THREADS * 24)
@@ -362,8 +321,6 @@ k_numeric_brick(mimpy_mesh_view m, int flags, UniArgs a) {
 #define B2_OFF_D (B2_OFF_DT + BR_THREADS * 6)
 #define B2_OFF_ROLE (B2_OFF_D + BR_THREADS * 6)
 #define B2_SMEM (B2_OFF_ROLE + BR_THREADS * 6)
-static_assert(B2_EXTRA0 + B2_EXTRA_ROWS * BR_RW == BR_NFACE * BR_RW, "row image holds every face row of the brick");
-static_assert(B2_OUT_SLOTS % 2 == 0, "output image is a whole number of 16-byte words");
 static_assert(B2_OFF_VOL + BR_THREADS * 8 <= B2_OFF_ROWSTART, "staging area must fit in the row buffer");
 static_assert(B2_OFF_ROWSTART % 16 == 0 && B2_OFF_CRS % 16 == 0 && B2_OFF_PM % 16 == 0, "alignment");
 
@@ -397,7 +354,7 @@ __device__ __forceinline__ void stage_run(unsigned dst, const void* src_, int la
 }
 
 __device__ __forceinline__ void stage_record(unsigned sbase, const double* face_geom, int lf, int c, int fid) {
-  cp_async<16>(sbase + B2_OFF_REC + lf * 64 + (((c ^ (lf >> 1)) & 3) << 4), face_geom + 8 * (size_t)fid + 2 * c);
+  cp_async<16>(sbase + B2_OFF_REC + lf * 64 + (((c ^ (lf >> 1)) & 3) << 4), face_geom + 8 * (size_t)fid + 2 * rec_pos(fid, c));
 }
 
 template <int METHOD>
@@ -700,27 +657,26 @@ k_numeric_brick2(mimpy_mesh_view m, int flags, UniArgs a, int bk_begin, int bk_e
   }
 }
 
-// 0 direct, 1 brick, 2 staged brick (default where the mesh is a structured hex mesh with even nx)
+// 0 direct, 1 brick, 2 staged brick (cp.async), 3 pipelined brick (bulk copies, assemble_brick3.cu; the
+// default where the mesh is a structured hex mesh with even nx)
 static int asm_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MIMPY_B200_ASM_VARIANT");
-    v = (e && e[0] == 'd') ? 0 : (e && e[0] == 'b') ? 1 : 2;
+    v = (e && e[0] == 'd') ? 0 : (e && e[0] == 'b') ? 1 : (e && e[0] == '2') ? 2 : 3;
   }
   return v;
 }
 
 template <int METHOD>
 static int launch_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int flags, const UniArgs& a,
-                          int bk_begin, int bk_end) {
+                          int bk_begin, int bk_end, bool staged) {
   const bool structured = mesh->hex_nx > 0 && mesh->hex_ny > 0 && mesh->hex_nz > 0 &&
                           (long long)mesh->hex_nx * mesh->hex_ny * mesh->hex_nz == mesh->nc;
-  if (structured && asm_variant() == 2 && mesh->hex_nx % 2 == 0 && !(flags & MIMPY_FLAG_DIRECT_KERNEL)) {
-    static bool configured2 = false;
-    if (!configured2) {
-      CUDA_TRY(cudaFuncSetAttribute(k_numeric_brick2<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2_SMEM));
-      configured2 = true;
-    }
+  // cudaFuncSetAttribute is per device and cheap: no process-wide "configured" flag (a second device
+  // in the same process would never get the opt-in)
+  if (staged) {
+    CUDA_TRY(cudaFuncSetAttribute(k_numeric_brick2<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2_SMEM));
     const int nbz = (mesh->hex_nz + BZ - 1) / BZ;
     if (bk_end > nbz) bk_end = nbz;
     const long long super_tiles = (long long)(((mesh->hex_nx + BX - 1) / BX + 3) / 4) * (((mesh->hex_ny + BY - 1) / BY + 3) / 4) *
@@ -730,11 +686,7 @@ static int launch_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int flags
                                                                                                    bk_end);
   } else if (structured && asm_variant() >= 1 && !(flags & MIMPY_FLAG_DIRECT_KERNEL)) {
     const size_t smem = sizeof(BrickSmem);
-    static bool configured = false;
-    if (!configured) {
-      CUDA_TRY(cudaFuncSetAttribute(k_numeric_brick<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = true;
-    }
+    CUDA_TRY(cudaFuncSetAttribute(k_numeric_brick<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long bricks = (long long)((mesh->hex_nx + BX - 1) / BX) * ((mesh->hex_ny + BY - 1) / BY) *
                              ((mesh->hex_nz + BZ - 1) / BZ);
     k_numeric_brick<METHOD><<<(unsigned)bricks, BR_THREADS, smem, ctx->stream>>>(*mesh, flags, a);
@@ -746,36 +698,106 @@ static int launch_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int flags
   return MIMPY_OK;
 }
 
+// Exchange slots of the wait-free diagonal swap: persistent, all-sentinel between FULL assemblies.  A
+// launch over a range of cell layers [b, e) leaves the halves of the z faces of layers b and e in their
+// slots until the neighbouring range is assembled.  Left there they would be taken for the partner's
+// half by a REPEATED or out-of-order launch, so the layers a launch is about to write from the same side
+// again are re-sentinelled first (1 = left by the cells below the layer, 2 = by the cells above).
+static int swap_prepare(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, bool ranged, int layer_begin, int layer_end) {
+  const int nx = mesh->hex_nx, ny = mesh->hex_ny, nz = mesh->hex_nz;
+  const int L = nx * ny + nx * (ny + 1) + (nx + 1) * ny;
+  if (ctx->diag_swap_len < (size_t)mesh->nf) {
+    if (ctx->diag_swap) {
+      CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      CUDA_TRY(cudaFree(ctx->diag_swap));
+    }
+    ctx->diag_swap = nullptr;
+    ctx->diag_swap_len = 0;
+    CUDA_TRY(cudaMalloc(&ctx->diag_swap, sizeof(double) * (size_t)mesh->nf));
+    ctx->diag_swap_len = (size_t)mesh->nf;
+    CUDA_TRY(cudaMemsetAsync(ctx->diag_swap, 0xFF, sizeof(double) * (size_t)mesh->nf, ctx->stream));
+    ctx->swap_dirty_n = 0;
+  }
+  if (ctx->swap_dirty_n > 0 && ctx->swap_L != L) {  // leftovers of another mesh
+    CUDA_TRY(cudaMemsetAsync(ctx->diag_swap, 0xFF, sizeof(double) * ctx->diag_swap_len, ctx->stream));
+    ctx->swap_dirty_n = 0;
+  }
+  ctx->swap_L = L;
+  auto clean_layer = [&](int layer) -> int {
+    const size_t first = (size_t)layer * L;
+    const size_t count = layer < nz ? (size_t)L : (size_t)nx * ny;
+    if (first < ctx->diag_swap_len)
+      CUDA_TRY(cudaMemsetAsync(ctx->diag_swap + first, 0xFF, sizeof(double) * (first + count <= ctx->diag_swap_len ? count : ctx->diag_swap_len - first),
+                               ctx->stream));
+    return MIMPY_OK;
+  };
+  auto find = [&](int layer) {
+    for (int q = 0; q < ctx->swap_dirty_n; ++q)
+      if (ctx->swap_dirty[q][0] == layer) return q;
+    return -1;
+  };
+  auto erase = [&](int q) {
+    ctx->swap_dirty[q][0] = ctx->swap_dirty[ctx->swap_dirty_n - 1][0];
+    ctx->swap_dirty[q][1] = ctx->swap_dirty[ctx->swap_dirty_n - 1][1];
+    --ctx->swap_dirty_n;
+  };
+  if (!ranged) {  // a full assembly completes nothing that is pending: start clean, end clean
+    for (int q = 0; q < ctx->swap_dirty_n; ++q) {
+      int rc = clean_layer(ctx->swap_dirty[q][0]);
+      if (rc) return rc;
+    }
+    ctx->swap_dirty_n = 0;
+    return MIMPY_OK;
+  }
+  // boundary layers this launch touches from one side only
+  const int bnd[2][2] = {{layer_begin, 2}, {layer_end >= nz ? -1 : layer_end, 1}};
+  for (int s = 0; s < 2; ++s) {
+    const int layer = bnd[s][0], side = bnd[s][1];
+    if (layer <= 0) continue;  // the mesh boundary: single-cell faces, no swap
+    const int q = find(layer);
+    if (q >= 0 && ctx->swap_dirty[q][1] != side) {
+      erase(q);  // the halves waiting there are the partners of this launch: completed by it
+    } else {
+      if (q >= 0) {  // same side again: stale halves of an earlier launch of the same range
+        int rc = clean_layer(layer);
+        if (rc) return rc;
+      } else if (ctx->swap_dirty_n < 8) {
+        ctx->swap_dirty[ctx->swap_dirty_n][0] = layer;
+        ctx->swap_dirty[ctx->swap_dirty_n][1] = side;
+        ++ctx->swap_dirty_n;
+      } else {  // more pending layers than we track: clean everything but what this launch completes
+        CUDA_TRY(cudaMemsetAsync(ctx->diag_swap, 0xFF, sizeof(double) * ctx->diag_swap_len, ctx->stream));
+        ctx->swap_dirty_n = 1;
+        ctx->swap_dirty[0][0] = layer;
+        ctx->swap_dirty[0][1] = side;
+      }
+    }
+  }
+  return MIMPY_OK;
+}
+
 // returns MIMPY_E_UNSUPPORTED when the fast path does not apply (caller falls back to the
 // generic warp-group kernel of local_matrices.cu -- same results, CUDA as well)
 int mimpy_numeric_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
                           int method, int flags, const double* multipliers, double alpha,
                           const double* c_diag, double* vals, int layer_begin, int layer_end) {
-  if (mesh->uniform_faces != 6 || !sym->role || !sym->cell_rowstart) return MIMPY_E_UNSUPPORTED;
+  if (mesh->uniform_faces != 6) return MIMPY_E_UNSUPPORTED;
   if (method != 0 && method != 1 && method != 6) return MIMPY_E_UNSUPPORTED;
-  const bool staged = mesh->hex_nx > 0 && mesh->hex_ny > 0 && mesh->hex_nz > 0 &&
-                      (long long)mesh->hex_nx * mesh->hex_ny * mesh->hex_nz == mesh->nc && asm_variant() == 2 &&
+  const bool pipelined = asm_variant() == 3 && mimpy_brick3_applies(mesh, sym, method, flags);
+  if (!pipelined && (!sym->role || !sym->cell_rowstart)) return MIMPY_E_UNSUPPORTED;
+  const bool staged = !pipelined && mesh->hex_nx > 0 && mesh->hex_ny > 0 && mesh->hex_nz > 0 &&
+                      (long long)mesh->hex_nx * mesh->hex_ny * mesh->hex_nz == mesh->nc && asm_variant() >= 2 &&
                       mesh->hex_nx % 2 == 0 && !(flags & MIMPY_FLAG_DIRECT_KERNEL);
-  // a range of cell layers [layer_begin, layer_end) is only served by the staged brick kernel
+  // a range of cell layers [layer_begin, layer_end) is only served by the (staged / pipelined) brick kernels
   const bool ranged = !(layer_begin == 0 && layer_end < 0);
-  if (ranged && (!staged || layer_begin % BZ != 0 || (layer_end % BZ != 0 && layer_end != mesh->hex_nz)))
+  if (ranged && ((!staged && !pipelined) || layer_begin % BZ != 0 || (layer_end % BZ != 0 && layer_end != mesh->hex_nz)))
     return MIMPY_E_UNSUPPORTED;
   const int bk_begin = ranged ? layer_begin / BZ : 0;
   const int bk_end = ranged ? (layer_end + BZ - 1) / BZ : 0x3fffffff;
   double* exchange = nullptr;
-  if (staged) {
-    // persistent exchange slots: set to the sentinel once, kept clean by the kernel itself
-    if (ctx->diag_swap_len < (size_t)mesh->nf) {
-      if (ctx->diag_swap) {
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        CUDA_TRY(cudaFree(ctx->diag_swap));
-      }
-      ctx->diag_swap = nullptr;
-      ctx->diag_swap_len = 0;
-      CUDA_TRY(cudaMalloc(&ctx->diag_swap, sizeof(double) * (size_t)mesh->nf));
-      ctx->diag_swap_len = (size_t)mesh->nf;
-      CUDA_TRY(cudaMemsetAsync(ctx->diag_swap, 0xFF, sizeof(double) * (size_t)mesh->nf, ctx->stream));
-    }
+  if (staged || pipelined) {
+    int rc = swap_prepare(ctx, mesh, ranged && !(layer_begin == 0 && layer_end >= mesh->hex_nz), layer_begin, layer_end);
+    if (rc) return rc;
     exchange = ctx->diag_swap;
   } else {
     void* scratch = nullptr;
@@ -800,7 +822,8 @@ int mimpy_numeric_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mim
   a.ticket = ctx->counters + 8;
   a.error_flag = ctx->counters + 9;
   a.flux_dof = sym->flux_dof;
-  if (method == 0) return launch_uniform<0>(ctx, mesh, flags, a, bk_begin, bk_end);
-  if (method == 1) return launch_uniform<1>(ctx, mesh, flags, a, bk_begin, bk_end);
-  return launch_uniform<6>(ctx, mesh, flags, a, bk_begin, bk_end);
+  if (pipelined) return mimpy_numeric_brick3(ctx, mesh, sym, method, flags, a, bk_begin, bk_end);
+  if (method == 0) return launch_uniform<0>(ctx, mesh, flags, a, bk_begin, bk_end, staged);
+  if (method == 1) return launch_uniform<1>(ctx, mesh, flags, a, bk_begin, bk_end, staged);
+  return launch_uniform<6>(ctx, mesh, flags, a, bk_begin, bk_end, staged);
 }

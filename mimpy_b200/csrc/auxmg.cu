@@ -90,7 +90,7 @@ k_aux_tau(int nc, const int* __restrict__ cell_faces, const int* __restrict__ f2
     const int g = f2f[f];
     double tau = 0.;
     if (g >= 0) {
-      const double a = face_geom[8 * (size_t)f];
+      const double a = rec_area(face_geom, (size_t)f);
       tau = a * a * w_e[boff + i * 7];
       atomicAdd(tsum + g, tau);  // <= 2 addends on a zeroed slot: order-free
     }
@@ -580,15 +580,16 @@ int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
   }
   total += pad((size_t)h->nc * 6) + pad((size_t)h->nf) + pad((size_t)h->flux_dof) +
            pad((size_t)AUX_COARSEST * AUX_COARSEST);
-  static bool pool_configured = false;
-  if (!pool_configured) {  // keep freed blocks in the pool: set-up is repeated every Newton step
+  static bool pool_configured[64] = {false};  // per device
+  bool& pool_done = pool_configured[ctx->device & 63];
+  if (!pool_done) {  // keep freed blocks in the pool: set-up is repeated every Newton step
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
       unsigned long long keep = ~0ull;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     cudaGetLastError();
-    pool_configured = true;
+    pool_done = true;
   }
   cudaError_t e = cudaMallocAsync(&h->slab, sizeof(double) * total, ctx->stream);
   if (e != cudaSuccess) {
@@ -659,12 +660,8 @@ int mimpy_b200_auxmg_setup(mimpy_ctx* ctx, void* handle, const mimpy_mesh_view* 
     rc = mimpy_allreduce_f64(ctx, h->gset, ctx->world * AUX_SLOT);
     if (rc) return rc;
     const size_t smem = sizeof(double) * (size_t)h->gn * (h->gn + 1);
-    static bool configured = false;
-    if (!configured) {
-      CUDA_TRY(cudaFuncSetAttribute(k_aux_global_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(sizeof(double) * AUX_GLOBAL_MAX * (AUX_GLOBAL_MAX + 1))));
-      configured = true;
-    }
+    CUDA_TRY(cudaFuncSetAttribute(k_aux_global_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize,  // per device
+                                  (int)(sizeof(double) * AUX_GLOBAL_MAX * (AUX_GLOBAL_MAX + 1))));
     k_aux_global_inverse<<<1, 1024, smem, st>>>(ctx->world, last.nx, last.ny, last.nz, h->gset, h->ginv);
   } else {
     k_aux_dense_inverse<<<1, AUX_T, 0, st>>>(last, h->cinv);

@@ -37,6 +37,14 @@ struct mimpy_ctx {
   size_t scratch_bytes;
   double* diag_swap;     // per-face exchange slots of the staged brick assembly kernel; all-sentinel
   size_t diag_swap_len;  //   between launches (the kernel restores every slot it used)
+  // a launch over a RANGE of cell layers leaves the halves of its outermost z-face layers in their slots
+  // until the neighbouring range arrives: layer -> 1 (left by the cells below) / 2 (by the cells above)
+  int swap_dirty[8][2];
+  int swap_dirty_n;
+  int swap_L;            // faces per layer of the mesh those entries refer to
+  // plan binding of the face records (assemble_brick3.cu): record array and symbolic serial last bound
+  const void* bound_geom;
+  long long bound_serial;
   double* partials;      // reduction partials (device)
   unsigned int* counters;  // last-block counters (device)
   double* scalars;       // device scalars for PCG (alpha, beta, rz, ...)
@@ -68,6 +76,30 @@ struct mimpy_xchg {
   size_t send_lo, send_hi, recv_lo, recv_hi;
 };
 int mimpy_layer_exchange(mimpy_ctx* ctx, double* v, const mimpy_xchg& x);
+
+// ---- the packed face record -----------------------------------------------------------------
+// face_geom[f] = four 16-byte chunks  c0 = (area, n_x)  c1 = (n_y, n_z)  c2 = (x_f, y_f)  c3 = (z_f, bind)
+// stored in a 2-bit XOR swizzle keyed by the face id: chunk c lives at position c ^ ((f >> 1) & 3).
+// A run of consecutive records that a bulk copy (cp.async.bulk) drops into shared memory unchanged can
+// then be read with one 128-bit load per lane and chunk without bank conflicts: the records of a cell's
+// z-, y-, x- faces are 192 bytes apart (assemble_brick3.cu).  `bind` is the plan binding written by
+// mimpy_bind_plan: low word = CSR offset of the face's row in the saddle matrix (-1: Neumann face, no
+// row), high word = which faces of the two adjacent cells are flux DOFs (bits 0-5: the cell that lists f
+// as one of its x+/y+/z+ faces, bits 8-13: the cell that lists it as x-/y-/z-).
+__device__ __host__ __forceinline__ int rec_pos(long long f, int c) { return c ^ (int)((f >> 1) & 3); }
+__device__ __forceinline__ const double2* rec_chunk(const double* face_geom, size_t f, int c) {
+  return reinterpret_cast<const double2*>(face_geom + 8 * f) + rec_pos((long long)f, c);
+}
+__device__ __forceinline__ double rec_area(const double* face_geom, size_t f) {
+  return __ldg(reinterpret_cast<const double*>(rec_chunk(face_geom, f, 0)));
+}
+__device__ __forceinline__ void rec_store(double* face_geom, size_t f, double area, const double* n, const double* c) {
+  double2* g = reinterpret_cast<double2*>(face_geom + 8 * f);
+  g[rec_pos((long long)f, 0)] = make_double2(area, n[0]);
+  g[rec_pos((long long)f, 1)] = make_double2(n[1], n[2]);
+  g[rec_pos((long long)f, 2)] = make_double2(c[0], c[1]);
+  g[rec_pos((long long)f, 3)] = make_double2(c[2], 0.);
+}
 
 #define CUDA_TRY(expr)                                                                   \
   do {                                                                                   \

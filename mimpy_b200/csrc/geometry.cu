@@ -74,13 +74,7 @@ k_hex_faces(int nf, const int4* __restrict__ face_points, const double* __restri
     centroids[3 * (size_t)f + 1] = c[1];
     centroids[3 * (size_t)f + 2] = c[2];
   }
-  if (geom) {
-    double2* g = reinterpret_cast<double2*>(geom + 8 * (size_t)f);
-    g[0] = make_double2(area, n[0]);
-    g[1] = make_double2(n[1], n[2]);
-    g[2] = make_double2(c[0], c[1]);
-    g[3] = make_double2(c[2], 0.);
-  }
+  if (geom) rec_store(geom, (size_t)f, area, n, c);
 }
 
 __global__ void __launch_bounds__(256)
@@ -88,13 +82,7 @@ k_face_pack(int nf, const double* __restrict__ areas, const double* __restrict__
             const double* __restrict__ centroids, double* __restrict__ geom) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= nf) return;
-  double2* g = reinterpret_cast<double2*>(geom + 8 * (size_t)f);
-  const double* n = normals + 3 * (size_t)f;
-  const double* c = centroids + 3 * (size_t)f;
-  g[0] = make_double2(areas[f], n[0]);
-  g[1] = make_double2(n[1], n[2]);
-  g[2] = make_double2(c[0], c[1]);
-  g[3] = make_double2(c[2], 0.);
+  rec_store(geom, (size_t)f, areas[f], normals + 3 * (size_t)f, centroids + 3 * (size_t)f);
 }
 
 // One lane per (cell, face): the face's projection/face integrals (mesh_cython.pyx:62-150),
@@ -229,6 +217,7 @@ int mimpy_b200_geom_hex_faces(mimpy_ctx* ctx, int32_t nf, const int32_t* face_po
       nf, reinterpret_cast<const int4*>(face_points), points, face_areas, face_normals,
       face_centroids, face_geom);
   KERNEL_CHECK();
+  if (face_geom && ctx->bound_geom == face_geom) ctx->bound_geom = nullptr;  // the bind words were overwritten
   return MIMPY_OK;
 }
 
@@ -241,6 +230,7 @@ int mimpy_b200_face_pack(mimpy_ctx* ctx, int32_t nf, const double* face_areas,
   k_face_pack<<<(nf + threads - 1) / threads, threads, 0, ctx->stream>>>(
       nf, face_areas, face_normals, face_centroids, face_geom);
   KERNEL_CHECK();
+  if (ctx->bound_geom == face_geom) ctx->bound_geom = nullptr;
   return MIMPY_OK;
 }
 

@@ -56,7 +56,7 @@ k_hybrid_setup(mimpy_mesh_view m, HybArgs h, const double* __restrict__ m_e,
   double area = 0.;
   if (valid) {
     const int f = m.cell_faces[base + j];
-    area = __ldg(m.face_geom + 8 * (size_t)f);
+    area = rec_area(m.face_geom, (size_t)f);
     gj = h.face_to_flux[f];
     const bool iface = h.face_flag && (h.face_flag[f] & 3);  // the other cell lives on another rank
     flag = (gj < 0 ? 1 : 0) | ((h.face_cell[2 * (size_t)f + 1] < 0 && !iface) ? 2 : 0);
@@ -145,9 +145,8 @@ k_hybrid_setup_hex(mimpy_mesh_view m, HybArgs h, int k_unity, const double* __re
     for (int i = 0; i < NF; ++i) {
       fid[i] = m.cell_faces[cell * NF + i];
       sgn[i] = (double)m.cell_sigma[cell * NF + i];
-      const double2* p = reinterpret_cast<const double2*>(m.face_geom + 8 * (size_t)fid[i]);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) rec[i][q] = __ldg(p + q);
+      for (int q = 0; q < 4; ++q) rec[i][q] = __ldg(rec_chunk(m.face_geom, (size_t)fid[i], q));
       area[i] = rec[i][0].x;
       gj[i] = h.face_to_flux[fid[i]];
       const bool iface = h.face_flag && (h.face_flag[fid[i]] & 3);
@@ -276,7 +275,7 @@ k_hybrid_local(mimpy_mesh_view m, HybArgs h, const double* __restrict__ w_e,
   if (valid) {
     const int f = m.cell_faces[base + j];
     sg = (double)m.cell_sigma[base + j];
-    area = __ldg(m.face_geom + 8 * (size_t)f);
+    area = rec_area(m.face_geom, (size_t)f);
     gj = h.face_to_flux[f];
     const unsigned ff = h.face_flag ? (h.face_flag[f] & 3) : 0;
     bnd = h.face_cell[2 * (size_t)f + 1] < 0 && !ff;
@@ -405,11 +404,7 @@ int mimpy_b200_hybrid_setup_fused(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, c
   const int ku = flags & MIMPY_FLAG_K_UNITY;
 #define HX_LAUNCH(M)                                                                                     \
   do {                                                                                                   \
-    static bool configured = false;                                                                      \
-    if (!configured) {                                                                                   \
-      CUDA_TRY(cudaFuncSetAttribute(k_hybrid_setup_hex<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      configured = true;                                                                                 \
-    }                                                                                                    \
+    CUDA_TRY(cudaFuncSetAttribute(k_hybrid_setup_hex<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     k_hybrid_setup_hex<M><<<blocks, HX_THREADS, smem, st>>>(*mesh, h, ku, multipliers, w_e, a_vals);       \
   } while (0)
   if (method == 0) HX_LAUNCH(0);

@@ -68,8 +68,8 @@ k_local_matrices(mimpy_mesh_view m, int method, int flags, const int* __restrict
   if (valid) {
     f = m.cell_faces[base + j];
     sg = (double)m.cell_sigma[base + j];
-    const double2* rec = reinterpret_cast<const double2*>(m.face_geom + 8 * (size_t)f);
-    const double2 a0 = __ldg(rec), a1 = __ldg(rec + 1), a2 = __ldg(rec + 2), a3 = __ldg(rec + 3);
+    const double2 a0 = __ldg(rec_chunk(m.face_geom, (size_t)f, 0)), a1 = __ldg(rec_chunk(m.face_geom, (size_t)f, 1));
+    const double2 a2 = __ldg(rec_chunk(m.face_geom, (size_t)f, 2)), a3 = __ldg(rec_chunk(m.face_geom, (size_t)f, 3));
     area = a0.x;
     nrm[0] = a0.y;
     nrm[1] = a1.x;
@@ -322,7 +322,7 @@ k_scatter_blocks(mimpy_mesh_view m, const double* __restrict__ m_e, ScatterArgs 
   if (valid) {
     f = m.cell_faces[base + j];
     sg = (double)m.cell_sigma[base + j];
-    area = __ldg(m.face_geom + 8 * (size_t)f);
+    area = rec_area(m.face_geom, (size_t)f);
     gj = sc.face_to_flux[f];
   }
   s_row[slot][j] = (gj >= 0) ? sc.indptr[gj] : -1;

@@ -344,15 +344,22 @@ static int pcg_core(mimpy_ctx* ctx, int32_t n, const SpmvMat& A, const double* d
   CUDA_TRY(cudaStreamSynchronize(st));
   const double bnorm = sqrt(ctx->host_scalars[S_BNORM]);
   double rnorm = sqrt(ctx->host_scalars[S_RR]);
-  const double target = fmax(info->rtol * bnorm, info->atol);
+  const double rz0 = ctx->host_scalars[S_RZ];
+  double rz = rz0;
+  const bool energy = info->norm_kind == 1;
+  const double target = fmax(info->rtol * (info->ref_norm > 0. ? info->ref_norm : bnorm), info->atol);
+  const double target_rz = info->rtol * info->rtol * rz0;
   info->rhs_norm = bnorm;
+  info->rz0 = rz0;
   int it = 0;
+  // true while the stopping test is not met
+  auto running = [&]() { return energy ? (rz > target_rz && rnorm > info->atol) : (rnorm > target); };
 
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
   bool use_graph = info->use_graph && st != nullptr && st != cudaStreamLegacy &&
                    st != cudaStreamPerThread;
-  if (use_graph && rnorm > target) {
+  if (use_graph && running()) {
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
       int crc = MIMPY_OK;
       for (int k = 0; k < check && crc == MIMPY_OK; ++k)
@@ -372,7 +379,7 @@ static int pcg_core(mimpy_ctx* ctx, int32_t n, const SpmvMat& A, const double* d
     }
   }
 
-  while (rnorm > target && it < info->maxit) {
+  while (running() && it < info->maxit) {
     if (use_graph && gexec) {
       CUDA_TRY(cudaGraphLaunch(gexec, st));
     } else {
@@ -387,6 +394,7 @@ static int pcg_core(mimpy_ctx* ctx, int32_t n, const SpmvMat& A, const double* d
                              cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     rnorm = sqrt(ctx->host_scalars[S_RR]);
+    rz = ctx->host_scalars[S_RZ];
     if (!(rnorm == rnorm)) break;  // NaN: matrix not SPD
   }
   CUDA_TRY(cudaEventRecord(ctx->ev1, st));
@@ -404,12 +412,14 @@ static int pcg_core(mimpy_ctx* ctx, int32_t n, const SpmvMat& A, const double* d
   if (graph) cudaGraphDestroy(graph);
   info->iterations = it;
   info->residual = rnorm;
+  info->rz = rz;
   if (!(rnorm == rnorm)) {
     mimpy_set_error("pcg: residual became NaN (face system not SPD?)");
     return MIMPY_E_NOCONV;
   }
-  if (rnorm > target) {
-    mimpy_set_error("pcg: %d iterations, residual %.3e > target %.3e", it, rnorm, target);
+  if (running()) {
+    mimpy_set_error("pcg: %d iterations, residual %.3e > target %.3e", it, energy ? sqrt(fabs(rz)) : rnorm,
+                    energy ? sqrt(target_rz) : target);
     return MIMPY_E_NOCONV;
   }
   return MIMPY_OK;

@@ -7,7 +7,11 @@
 // sort of the 36*nc COO triples is needed.
 #include <cub/device/device_scan.cuh>
 
+#include <atomic>
+
 #include "common.cuh"
+
+static std::atomic<long long> g_plan_serial{0};
 
 #define MAXC (2 * MIMPY_MAX_CELL_FACES)
 
@@ -271,6 +275,7 @@ int mimpy_b200_mfd_symbolic_fill(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, mi
   const int nf = mesh->nf, nc = mesh->nc, F = sym->flux_dof;
   const int T = 256;
   cudaStream_t st = ctx->stream;
+  sym->serial = ++g_plan_serial;
   k_fill_faces<<<(nf + T - 1) / T, T, 0, st>>>(nf, F, mesh->cell_ptr, mesh->cell_faces,
                                                sym->face_to_flux, sym->face_cell, sym->indptr,
                                                sym->indices, sym->m_indptr, sym->m_indices,

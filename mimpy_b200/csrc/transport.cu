@@ -36,7 +36,7 @@ k_transport_step(mimpy_mesh_view m, const int* __restrict__ f2f, const int* __re
         if (bv == bv) cu = bv;  // NaN marks "no boundary concentration": stays 0 like current_c_uw
       }
     }
-    div_c += s * m.face_geom[8 * (size_t)f] * (cu * vel);  // DIV[c, g(f)] = sigma a_f  (mfd.py:232-238)
+    div_c += s * rec_area(m.face_geom, (size_t)f) * (cu * vel);  // DIV[c, g(f)] = sigma a_f  (mfd.py:232-238)
   }
   // transport.py:323-342 in the reference's operation order (no division by |E|: :344 is commented out)
   const double prev_density = ((p_prev[c] - ref_p) * compressibility + 1.) * ref_rho;

@@ -104,7 +104,7 @@ __global__ void k_saturation(int nc, mimpy_fluid fl, double dt, const int* __res
     const int f = cell_faces[base + j];
     const int g = f2f[f];
     if (g < 0) continue;
-    const double e = (double)sigma[base + j] * face_geom[8 * (size_t)f];
+    const double e = (double)sigma[base + j] * rec_area(face_geom, (size_t)f);
     div += e * (f_w[g] * u_t[g]);
   }
   // twophase.py:1007-1022

@@ -21,7 +21,7 @@ class DeviceMesh(object):
     """SoA mesh in HBM (SURVEY 8a G1-G6 outputs, laid out for the M_E kernels).
 
     cell_ptr/cell_faces/cell_sigma : ragged cells (int32 / int32 / int8)
-    face_geom[nf,8]                : packed [area, n, x_f, 0] record (64 B)
+    face_geom[nf,8]                : packed [area, n, x_f, bind] record (64 B), chunk-swizzled (face_records_host)
     cell_k[nc,9], cell_centroid[nc,3], cell_volume[nc] : the reference's own cell arrays
     """
 
@@ -456,10 +456,15 @@ class HybridSystem(object):
             pass
 
     def solve(self, rhs, rtol=1e-10, atol=0., maxit=20000, check_every=None, use_graph=True, x0=None,
-              raise_on_noconv=True):
+              raise_on_noconv=True, norm="face", ref_norm=None):
         """Returns (solution [v;p], info). rhs: device tensor of length flux_dof+nc.
         check_every: iterations between two convergence checks on the host (default: 5 with the
-        multigrid preconditioner, 50 with Jacobi)."""
+        multigrid preconditioner, 50 with Jacobi).
+        norm: what rtol is measured in -- "face": ||r||_2 / ||h||_2 of the condensed face system (or
+        / ref_norm when given); "saddle": ||r||_2 / ||rhs||_2, i.e. relative to the right-hand side of
+        the ORIGINAL saddle system (the face residual then tracks the saddle residual; on a slab
+        partition pass the global norm as ref_norm); "energy": sqrt(r.Br / r0.Br0), the
+        preconditioned residual, which is independent of the row scaling of h."""
         if check_every is None:
             check_every = 5 if self.aux is not None else 50
         ctx = self.dmesh.ctx
@@ -477,6 +482,12 @@ class HybridSystem(object):
             info = PcgInfo()
             info.rtol, info.atol, info.maxit = rtol, atol, maxit
             info.check_every, info.use_graph = check_every, 1 if use_graph else 0
+            if norm not in ("face", "energy", "saddle"):
+                raise ValueError("norm must be 'face', 'saddle' or 'energy'")
+            info.norm_kind = 1 if norm == "energy" else 0
+            if norm == "saddle" and not ref_norm:
+                ref_norm = float(torch.linalg.norm(rhs))
+            info.ref_norm = float(ref_norm) if ref_norm else 0.
             allow = () if raise_on_noconv else (_lib.MIMPY_E_NOCONV,)
             if self.aux is not None:
                 sell = self.layout == "sell"
@@ -511,6 +522,19 @@ def make_fluid(mu_w, mu_o, rho_w, rho_o, c_w, c_o, s_wr, s_or, n_w, n_o, k_rw_o=
     f.c_w, f.c_o, f.s_wr, f.s_or = c_w, c_o, s_wr, s_or
     f.n_w, f.n_o, f.k_rw_o = n_w, n_o, k_rw_o
     return f
+
+
+def face_records_host(dmesh):
+    """face_geom un-swizzled on the host: (nf, 8) rows [area, n_x, n_y, n_z, x_f, y_f, z_f, bind].  On the
+    device the four 16-byte chunks of record f sit at chunk positions c ^ ((f >> 1) & 3)
+    (csrc/common.cuh); `bind` is library-owned (plan binding of the pipelined brick kernel)."""
+    g = to_host(dmesh.ctx, dmesh.face_geom).reshape(-1, 4, 2)
+    f = np.arange(g.shape[0])
+    key = (f >> 1) & 3
+    out = np.empty_like(g)
+    for c in range(4):
+        out[f, c] = g[f, c ^ key]
+    return out.reshape(-1, 8)
 
 
 def to_host(ctx, t):

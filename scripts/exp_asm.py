@@ -22,7 +22,11 @@ def timeit(label, **kw):
             e0.record(ctx.stream); device.numeric(dm, plan, 1, vals=vals, **kw); e1.record(ctx.stream)
         ctx.sync(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     print("%-40s %.3f ms  (%.0f Mcells/s, %.1f%% of 6546.6 GB/s algorithmic)" % (label, min(ts), nc / min(ts) / 1e3, 700. * nc / min(ts) / 1e6 / 6546.6 * 100))
-timeit("structured-hex kernel, MIMPY_B200_ASM_VARIANT=%s" % os.environ.get("MIMPY_B200_ASM_VARIANT", "(default: staged brick)"))
+ref = device.to_host(ctx, device.numeric(dm, plan, 1, generic_kernel=True)) if n <= 128 else None
+timeit("structured-hex kernel, MIMPY_B200_ASM_VARIANT=%s" % os.environ.get("MIMPY_B200_ASM_VARIANT", "(default: pipelined brick)"))
 if len(sys.argv) > 2:
     timeit("direct", debug_flags=4)
     timeit("generic warp-group kernel", generic_kernel=True)
+if ref is not None:
+    out = device.to_host(ctx, device.numeric(dm, plan, 1, vals=vals))
+    print("max |brick - generic| / max = %.2e" % (abs(out - ref).max() / abs(ref).max()))

@@ -64,7 +64,8 @@ def test_hex_build_bit_exact(ctx, shape):
     assert np.array_equal(H(ctx, d.face_centroids), o.face_centroids)
     assert np.allclose(H(ctx, d.cell_volume), o.cell_volume, rtol=1e-14, atol=0)
     assert np.allclose(H(ctx, d.cell_centroid), o.cell_centroid, rtol=1e-13, atol=1e-16)
-    g = H(ctx, d.face_geom)
+    from mimpy_b200 import device
+    g = device.face_records_host(d)
     assert np.array_equal(g[:, 0], o.face_areas) and np.array_equal(g[:, 1:4], o.face_normals)
     assert np.array_equal(g[:, 4:7], o.face_centroids)
 
@@ -382,6 +383,81 @@ def test_numeric_by_layer_slabs_equals_full_assembly(ctx):
     assert not device.numeric_layers(d, plan, 1, vals, 2, 8)     # not a multiple of the brick height
 
 
+@pytest.mark.parametrize("dims", [(16, 8, 8), (10, 7, 9), (8, 4, 4), (2, 3, 2), (24, 5, 13)])
+def test_pipelined_brick_random_neumann_masks(ctx, dims):
+    """The pipelined brick kernel derives every CSR position from the face records' bind words
+    (closed-form merged face order + popcounts over the flux-DOF flags).  Random Neumann masks over the
+    boundary faces (single faces, whole sides, cells with several Neumann faces) exercise every shifted
+    position; the generic warp-group kernel, which reads the symbolic maps, is the reference."""
+    import torch
+    from mimpy_b200 import device
+
+    nx, ny, nz = dims
+    nc = nx * ny * nz
+    rng = np.random.default_rng(nc)
+    g = np.exp(rng.standard_normal((nc, 3)))
+    k = np.zeros((nc, 9))
+    k[:, 0], k[:, 4], k[:, 8] = g[:, 0], g[:, 1], g[:, 2]
+    k[:, 1] = k[:, 3] = 0.1 * np.sqrt(g[:, 0] * g[:, 1])
+    d = device.DeviceMesh.hex(ctx, nx, ny, nz, 1., 1.3, .7, cell_k=k)
+    hx = HexIndexHost(nx, ny, nz)
+    bnd = np.concatenate([hx.boundary(b) for b in range(6)])
+    for trial, frac in enumerate((0., 0.3, 0.7, 1.0)):
+        mask = np.zeros(d.nf, dtype=np.uint8)
+        mask[bnd[rng.uniform(size=len(bnd)) < frac]] = 1
+        if frac == 1.0:
+            mask[hx.boundary(0)[0]] = 0      # keep one Dirichlet face
+        plan = device.symbolic(d, mask)
+        for method in (1, 6):
+            a = H(ctx, device.numeric(d, plan, method, alpha=0.25))
+            b = H(ctx, device.numeric(d, plan, method, alpha=0.25, generic_kernel=True))
+            assert not np.isnan(a).any()
+            assert abs(a - b).max() <= 1e-13 * abs(b).max(), (dims, frac, method)
+            F = plan.flux_dof
+            ip = H(ctx, plan.indptr)
+            assert np.array_equal(a[ip[F]:], b[ip[F]:])
+    # two plans on the same mesh alternate: the records are re-bound each time the plan changes
+    m1 = np.zeros(d.nf, dtype=np.uint8)
+    m1[hx.boundary(2)] = 1
+    m2 = np.zeros(d.nf, dtype=np.uint8)
+    m2[hx.boundary(5)] = 1
+    p1, p2 = device.symbolic(d, m1), device.symbolic(d, m2)
+    r1 = H(ctx, device.numeric(d, p1, 1, generic_kernel=True))
+    r2 = H(ctx, device.numeric(d, p2, 1, generic_kernel=True))
+    for _ in range(2):
+        assert abs(H(ctx, device.numeric(d, p1, 1)) - r1).max() <= 1e-13 * abs(r1).max()
+        assert abs(H(ctx, device.numeric(d, p2, 1)) - r2).max() <= 1e-13 * abs(r2).max()
+
+
+def test_numeric_layers_repeated_and_out_of_order(ctx):
+    """A repeated or out-of-order mimpy_b200_mfd_numeric_layers call must not pick up the diagonal halves an
+    earlier launch left in the exchange slots of its outermost z-face layers."""
+    import torch
+    from mimpy_b200 import device
+
+    nx, ny, nz = 12, 8, 16
+    nc = nx * ny * nz
+    rng = np.random.default_rng(5)
+    g = np.exp(rng.standard_normal((nc, 3)))
+    k = np.zeros((nc, 9))
+    k[:, 0], k[:, 4], k[:, 8] = g[:, 0], g[:, 1], g[:, 2]
+    d = device.DeviceMesh.hex(ctx, nx, ny, nz, 1., 1., 1., cell_k=k)
+    plan = device.symbolic(d, np.zeros(d.nf, dtype=np.uint8))
+    full = H(ctx, device.numeric(d, plan, 1))
+    with ctx.on_stream():
+        vals = torch.zeros(plan.nnz, dtype=torch.float64, device=ctx.device)
+    # probe (a partial launch), then the same slab again, then the rest out of order
+    for k0, k1 in ((0, 4), (0, 4), (8, 16), (8, 16), (4, 8)):
+        assert device.numeric_layers(d, plan, 1, vals, k0, k1)
+    assert np.array_equal(H(ctx, vals), full)
+    # leftovers of an unfinished sweep do not leak into a full assembly, nor into the next sweep
+    assert device.numeric_layers(d, plan, 1, vals, 4, 12)
+    assert np.array_equal(H(ctx, device.numeric(d, plan, 1)), full)
+    for k0, k1 in ((12, 16), (0, 4), (4, 12)):
+        assert device.numeric_layers(d, plan, 1, vals, k0, k1)
+    assert np.array_equal(H(ctx, vals), full)
+
+
 class HexIndexHost(object):
     """Closed-form HexMesh face numbering (hexmesh.py:161-234) for picking boundary faces by index."""
 
@@ -446,7 +522,7 @@ def test_solve_flow1d_known_answer(ctx, golden):
     _solve_and_compare(ctx, o, 1, bc, None, g["solution"])
 
 
-def test_solve_24cubed_heterogeneous_vs_spsolve(ctx):
+def test_solve_16cubed_heterogeneous_vs_spsolve(ctx):
     """C3 shape at n=16: log-normal diagonal K, method 1, Dirichlet x-/x+, no-flow elsewhere."""
     n = 16
     rng = np.random.default_rng(256)
