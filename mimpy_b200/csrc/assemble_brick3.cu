@@ -33,8 +33,9 @@
 // ---- shared memory ------------------------------------------------------------------------------
 #define B3_REC_RUN (27 * 64)                        /* 27 record slots per x-run: 3q+d, x+ of cell q at 3q+5 */
 #define B3_SURF_RUN (22 * 64)                       /* records 1..22 (y+) / 0..21 (z+) of a neighbouring run */
-#define B3_OFF_OUT 0
-#define B3_OFF_IN (B2_OUT_SLOTS * 8)                /* input stage (bulk-copy target)                        */
+#define B3_OFF_TRASH 0                              /* 16 B nobody reads: target of the stores a cell must not make */
+#define B3_OFF_OUT 16
+#define B3_OFF_IN ((B3_OFF_OUT + B2_OUT_SLOTS * 8 + 127) / 128 * 128) /* input stage (bulk-copy target)   */
 #define B3_IN_REC 0
 #define B3_IN_YP (B2_RUNS * B3_REC_RUN)             /* y+ records of the last cell row, one run per lk      */
 #define B3_IN_ZP (B3_IN_YP + BZ * B3_SURF_RUN)      /* z+ records of the top cell layer, one run per lj     */
@@ -44,7 +45,8 @@
 #define B3_IN_BYTES (B3_IN_VOL + BR_THREADS * 8)
 #define B3_OFF_SMALL (B3_OFF_IN + B3_IN_BYTES)      /* int run_base[16], cell_base[16], extra_rowstart[80]  */
 #define B3_OFF_BAR (B3_OFF_SMALL + (2 * B2_RUNS + B2_EXTRA_ROWS) * 4)
-#define B3_SMEM (B3_OFF_BAR + 16)                   /* full, empty                                           */
+#define B3_OFF_IDS (B3_OFF_BAR + 16)                /* int2 {this brick, next brick} per parity              */
+#define B3_SMEM (B3_OFF_IDS + 16)                   /* full, empty                                           */
 #define B3_THREADS (2 * BR_THREADS)                 /* compute warpgroup + producer warpgroup (one warp of it works) */
 #define B3_REGS_PRODUCER 40                         /* setmaxnreg: 2 CTAs x (128 x 216 + 128 x 40) = 64 K registers  */
 #define B3_REGS_COMPUTE 216
@@ -64,9 +66,11 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar) {
 // barrier of the four compute warps only (the producer warp runs ahead on its own)
 __device__ __forceinline__ void sync_compute() { asm volatile("bar.sync 1, %0;" ::"n"(BR_THREADS) : "memory"); }
 // bounded: a transfer that never completes raises the device error flag instead of hanging the GPU
+template <bool BACKOFF>
 __device__ __forceinline__ bool mbar_wait(unsigned bar, unsigned parity, unsigned int* error_flag) {
   unsigned done = 0, spins = 0;
   do {
+    if (BACKOFF && spins) __nanosleep(256);  // the producer waits most of the time: keep it off the issue ports
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -84,6 +88,21 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// store v at p + OFF bytes unless v is the sentinel (all-ones high word, which no finite value has); one
+// address register pair serves every store of a run (the compiler re-derived it per predicated store)
+template <int OFF>
+__device__ __forceinline__ void st_unless_sentinel(const double* p, double v) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 lo, hi;\n"
+      "mov.b64 {lo, hi}, %1;\n"
+      "setp.ne.s32 p, hi, -1;\n"
+      "@p st.global.f64 [%0 + %2], %1;\n"
+      "}\n" ::"l"(p),
+      "d"(v), "n"(OFF)
+      : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -140,6 +159,7 @@ struct B3Geo {
   int nx, ny, nz, L, xrow;
   int nbx, nby, nsx, nsy, bk_begin, bk_end;
   int total;  // linear brick indices (super-tile order), some of them outside the mesh
+  unsigned ticket_base;  // value of the ticket counter when this launch starts
 };
 
 __device__ __forceinline__ bool b3_decode(const B3Geo& g, int b, int& bi, int& bj, int& bk) {
@@ -226,34 +246,52 @@ k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
   const int nx = g.nx, ny = g.ny, nz = g.nz, L = g.L, xrow = g.xrow;
   const bool k_unity = flags & 1;
 
-  int b = blockIdx.x, bi, bj, bk;
-  while (b < g.total && !b3_decode(g, b, bi, bj, bk)) b += gridDim.x;
+  int2* s_ids = reinterpret_cast<int2*>(sm + B3_OFF_IDS);
   if (t == 0) {
     mbar_init(bar_full, 1);            // the producer's arrive.expect_tx
     mbar_init(bar_empty, BR_THREADS / 32);  // one arrival per compute warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (b >= g.total) return;
 
   if (warp >= BR_THREADS / 32) {
     // ---- producer warpgroup: gives its registers to the compute warpgroup; one warp runs one brick
-    // ahead of the compute warps ----
+    // ahead of the compute warps.  Bricks are handed out by an atomic ticket in super-tile order, so the
+    // bricks in flight on the whole GPU stay a compact window however the CTAs drift apart: the two
+    // halves of a surface row (and the shared face records) meet in L2. ----
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B3_REGS_PRODUCER));
     if (warp != BR_THREADS / 32) return;
+    int bi = 0, bj = 0, bk = 0;
+    auto next_brick = [&]() {  // next valid brick of the global order, or g.total
+      int b;
+      do {
+        unsigned tk = 0;
+        if (lane == 0) tk = atomicAdd(a.ticket, 1u) - g.ticket_base;
+        tk = __shfl_sync(0xffffffffu, tk, 0);
+        b = tk < (unsigned)g.total ? (int)tk : g.total;
+      } while (b < g.total && !b3_decode(g, b, bi, bj, bk));
+      return b;
+    };
+    int b = next_brick();
     unsigned it = 0;
-    while (b < g.total) {
+    while (true) {
+      const int cbi = bi, cbj = bj, cbk = bk;
+      const int bn = b < g.total ? next_brick() : g.total;  // (overwrites bi, bj, bk)
       if (it > 0) {
         // the operands of the previous brick are in registers
-        if (!mbar_wait(bar_empty, (it - 1) & 1u, a.error_flag)) return;
+        if (!mbar_wait<true>(bar_empty, (it - 1) & 1u, a.error_flag)) return;
         fence_proxy_async();
       }
-      b3_issue(m, g, k_unity, bi, bj, bk, in_base, bar_full, lane);
+      if (lane == 0) s_ids[it & 1u] = make_int2(b, bn);
+      __syncwarp();
+      if (b >= g.total) {  // tell the compute warps that the work is done
+        if (lane == 0) mbar_arrive_expect_tx(bar_full, 0);
+        return;
+      }
+      b3_issue(m, g, k_unity, cbi, cbj, cbk, in_base, bar_full, lane);
       ++it;
-      b += gridDim.x;
-      while (b < g.total && !b3_decode(g, b, bi, bj, bk)) b += gridDim.x;
+      b = bn;
     }
-    return;
   }
 
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(B3_REGS_COMPUTE));
@@ -274,13 +312,11 @@ k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
       if (a.c_diag) pcdiag = __ldg(a.c_diag + cell);
     }
   };
-  prefetch(bi, bj, bk, crow, mult, cdiag);
   unsigned phase = 0;
+  bool first_brick = true;
+  double* const out_t = a.vals + t;
 
   while (true) {
-    int bn = b + gridDim.x, nbi = 0, nbj = 0, nbk = 0;
-    while (bn < g.total && !b3_decode(g, bn, nbi, nbj, nbk)) bn += gridDim.x;
-
     // sentinel-fill the output image (free since the barrier that ended the previous brick): a slot
     // nobody in this brick writes is not stored
     {
@@ -289,6 +325,18 @@ k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
 #pragma unroll 4
       for (int e = t; e < B2_OUT_SLOTS / 2; e += BR_THREADS) r2[e] = s2;
       if (t < B2_EXTRA_ROWS) s_extra_rs[t] = 0;
+    }
+    if (!mbar_wait<false>(bar_full, phase, a.error_flag)) return;  // (uniform: every compute thread waits on the same phase)
+    const int2 ids = s_ids[phase];
+    phase ^= 1u;
+    if (ids.x >= g.total) return;
+    int bi, bj, bk, nbi = 0, nbj = 0, nbk = 0;
+    b3_decode(g, ids.x, bi, bj, bk);
+    const int bn = ids.y;
+    if (bn < g.total) b3_decode(g, bn, nbi, nbj, nbk);
+    if (first_brick) {
+      prefetch(bi, bj, bk, crow, mult, cdiag);
+      first_brick = false;
     }
     const int ci0 = bi * BX, cj0 = bj * BY, ck0 = bk * BZ;
     const int ci = ci0 + li, cj = cj0 + lj, ck = ck0 + lk;
@@ -299,9 +347,6 @@ k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
                          cj + 1 < ny ? cbase + xrow + 1 : ck * L + ny * xrow + ci,
                          ck + 1 < nz ? cbase + L : nz * L + cj * nx + ci};
     const bool in_brick[NF] = {lk > 0, lj > 0, li > 0, li < BX - 1, lj < BY - 1, lk < BZ - 1};
-
-    if (!mbar_wait(bar_full, phase, a.error_flag)) return;  // (uniform: every compute thread waits on the same phase)
-    phase ^= 1u;
 
     // ---- pull: operands into registers ----
     CellOps<NF> o;
@@ -398,21 +443,29 @@ k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
         s_extra_rs[B2_RUNS + BX * BZ + lj * BX + li] = rs[5];
       }
       const int cb = B2_CELL0 + run * B2_CELL_SLOTS + (crow - s_cellbase[run]);
+      // Straight-line code from here to the end of cell_core: a store that must not happen (Neumann row or
+      // column) goes to the trash word in front of the image (slot index -2 + ... = `dead`) instead of
+      // being branched around, so the 36 entry chains of cell_core form ONE basic block and the
+      // scheduler can interleave them (with a branch per entry each DMUL-DFMA-DFMA-DADD-DFMA chain ran
+      // alone, exposed: 34 % of all stall samples were fixed-latency waits).
+      constexpr int dead = -(B3_OFF_OUT / 8);                      // row[dead] = the trash word
+      auto slot = [&](int i, int j, unsigned pos) {                 // image slot of entry (i, j), dead if dropped
+        const unsigned need = (1u << i) | (1u << j);                // faces i and j are flux DOFs (rs[i] >= 0)
+        return ((me & need) == need) ? sb[i] + (int)pos : dead;
+      };
 #pragma unroll
       for (int i = 0; i < NF; ++i) {
-        if (rs[i] >= 0) {
-          // -DIV^T: behind the M entries of the row, the lower-index cell first   mfd.py:240-243
-          row[sb[i] + __popc(mp[i]) + ((i < 3 && ((other_mask >> i) & 1u)) ? 1 : 0)] = -sa[i];
-          row[cb + __popc(me & ((1u << i) - 1u))] = sa[i];          // DIV      mfd.py:232-238
-        }
+        // -DIV^T: behind the M entries of the row, the lower-index cell first   mfd.py:240-243
+        row[slot(i, i, __popc(mp[i]) + ((i < 3 && ((other_mask >> i) & 1u)) ? 1u : 0u))] = -sa[i];
+        const int dslot = cb + __popc(me & ((1u << i) - 1u));       // DIV      mfd.py:232-238
+        row[((me >> i) & 1u) ? dslot : dead] = sa[i];
       }
       row[cb + __popc(me)] = a.c_diag ? cdiag : a.alpha * vol;      // mfd.py:766-772
       cell_core<NF, METHOD>(o, trk, vol, mult, [&](int i, int j, double v) {
-        if (i == j) {
+        if (i == j)
           diag[i] = v;
-        } else if (rs[i] >= 0 && ((me >> j) & 1u)) {
-          row[sb[i] + __popc(mp[i] & ((1u << merged_index(i, j)) - 1u))] = v;
-        }
+        else
+          row[slot(i, j, __popc(mp[i] & ((1u << merged_index(i, j)) - 1u)))] = v;
       });
       // diagonals, step 1: single-cell faces and the LOWER cell of faces inside the brick go to the
       // image.  A face shared with ANOTHER brick: both cells swap their half into diag_pub[f]
@@ -446,17 +499,17 @@ k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
     {  // face rows of the runs: 312 slots = 128 + 128 + 56 per run, addresses fixed per thread
       static_assert(B2_RUN_SLOTS > 2 * BR_THREADS && B2_RUN_SLOTS <= 3 * BR_THREADS, "three passes per run");
       const double* q = row + t;
-      double* out = a.vals + t;
+      const bool third = t < B2_RUN_SLOTS - 2 * BR_THREADS;
 #pragma unroll 4
       for (int r = 0; r < B2_RUNS; ++r, q += B2_RUN_SLOTS) {
         const int base = s_runbase[r];
         if (base == 0x7fffffff) continue;
         const double v0 = q[0], v1 = q[BR_THREADS];
-        const double v2 = t < B2_RUN_SLOTS - 2 * BR_THREADS ? q[2 * BR_THREADS] : __longlong_as_double(-1ll);
-        double* op = out + base;
-        if (__double2hiint(v0) != -1) op[0] = v0;
-        if (__double2hiint(v1) != -1) op[BR_THREADS] = v1;
-        if (__double2hiint(v2) != -1) op[2 * BR_THREADS] = v2;
+        const double v2 = third ? q[2 * BR_THREADS] : __longlong_as_double(-1ll);
+        const double* op = out_t + base;
+        st_unless_sentinel<0>(op, v0);
+        st_unless_sentinel<BR_THREADS * 8>(op, v1);
+        st_unless_sentinel<2 * BR_THREADS * 8>(op, v2);
       }
     }
     {  // cell rows: two runs per pass, 56 of 64 lanes each
@@ -465,7 +518,7 @@ k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
 #pragma unroll
         for (int r = half; r < B2_RUNS; r += 2) {
           const double v = row[B2_CELL0 + r * B2_CELL_SLOTS + l];
-          if (__double2hiint(v) != -1) a.vals[s_cellbase[r] + l] = v;
+          st_unless_sentinel<0>(a.vals + s_cellbase[r] + l, v);
         }
       }
     }
@@ -474,7 +527,7 @@ k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
 #pragma unroll
       for (int e = r0; e < B2_EXTRA_ROWS; e += 8) {
         const double v = row[B2_EXTRA0 + e * BR_RW + pos];
-        if (__double2hiint(v) != -1) a.vals[s_extra_rs[e] + pos] = v;
+        st_unless_sentinel<0>(a.vals + s_extra_rs[e] + pos, v);
       }
     }
     // diagonals, step 3: second arrivals at a face shared with another brick finish the slot
@@ -489,10 +542,6 @@ k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
     }
     if (bn >= g.total) break;
     sync_compute();  // every read of the image is done before the next brick refills it
-    b = bn;
-    bi = nbi;
-    bj = nbj;
-    bk = nbk;
     crow = crow_n;
     mult = mult_n;
     cdiag = cdiag_n;
@@ -524,16 +573,20 @@ static int bind_plan(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_sy
   return MIMPY_OK;
 }
 
-template <int METHOD>
-static int launch_brick3(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int flags, const UniArgs& a, const B3Geo& g) {
-  CUDA_TRY(cudaFuncSetAttribute(k_numeric_brick3<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B3_SMEM));
+static int b3_ctas_per_sm() {
   static int per_sm = 0;
   if (per_sm == 0) {
     const char* e = getenv("MIMPY_B200_B3_CTAS");
     per_sm = e ? atoi(e) : B3_MINB;
     if (per_sm < 1) per_sm = 1;
   }
-  long long grid = (long long)ctx->sm_count * per_sm;
+  return per_sm;
+}
+
+template <int METHOD>
+static int launch_brick3(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int flags, const UniArgs& a, const B3Geo& g) {
+  CUDA_TRY(cudaFuncSetAttribute(k_numeric_brick3<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B3_SMEM));
+  long long grid = (long long)ctx->sm_count * b3_ctas_per_sm();
   if (grid > g.total) grid = g.total;
   k_numeric_brick3<METHOD><<<(unsigned)grid, B3_THREADS, B3_SMEM, ctx->stream>>>(*mesh, flags, a, g);
   KERNEL_CHECK();
@@ -561,6 +614,11 @@ int mimpy_numeric_brick3(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimp
   if (super_tiles <= 0) return MIMPY_OK;
   if (super_tiles * 64 > 0x7fffffffLL) return MIMPY_E_UNSUPPORTED;
   g.total = (int)(super_tiles * 64);
+  // every CTA's producer draws tickets until it gets one past the end: total + grid draws per launch
+  long long grid = (long long)ctx->sm_count * b3_ctas_per_sm();
+  if (grid > g.total) grid = g.total;
+  g.ticket_base = ctx->b3_ticket;
+  ctx->b3_ticket += (unsigned)g.total + (unsigned)grid;
   if (method == 0) return launch_brick3<0>(ctx, mesh, flags, a, g);
   if (method == 1) return launch_brick3<1>(ctx, mesh, flags, a, g);
   return launch_brick3<6>(ctx, mesh, flags, a, g);

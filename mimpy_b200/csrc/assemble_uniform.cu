@@ -822,6 +822,7 @@ int mimpy_numeric_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mim
   a.ticket = ctx->counters + 8;
   a.error_flag = ctx->counters + 9;
   a.flux_dof = sym->flux_dof;
+  if (pipelined) a.ticket = ctx->counters + 12;  // monotonic across launches (no memset): see B3Geo::ticket_base
   if (pipelined) return mimpy_numeric_brick3(ctx, mesh, sym, method, flags, a, bk_begin, bk_end);
   if (method == 0) return launch_uniform<0>(ctx, mesh, flags, a, bk_begin, bk_end, staged);
   if (method == 1) return launch_uniform<1>(ctx, mesh, flags, a, bk_begin, bk_end, staged);

@@ -105,9 +105,11 @@ __device__ __forceinline__ void cell_core(CellOps<NF>& o, double trk, double vol
     const double coef = (METHOD == 6) ? mult * o.dcoef[i] : u;
 #pragma unroll
     for (int j = 0; j < NF; ++j) {
-      const double m0 = z[0] * rt[j][0] + z[1] * rt[j][1] + z[2] * rt[j][2];
-      const double qq = kn[i][0] * kn[j][0] + kn[i][1] * kn[j][1] + kn[i][2] * kn[j][2];
-      sink(i, j, m0 + coef * (((i == j) ? 1. : 0.) - qq));
+      // explicit fma chains: every kernel that instantiates this core rounds identically whatever its
+      // sink looks like (the contraction of a*b+c otherwise depends on the surrounding control flow)
+      const double m0 = fma(z[2], rt[j][2], fma(z[1], rt[j][1], z[0] * rt[j][0]));
+      const double qq = fma(kn[i][2], kn[j][2], fma(kn[i][1], kn[j][1], kn[i][0] * kn[j][0]));
+      sink(i, j, fma(coef, ((i == j) ? 1. : 0.) - qq, m0));
     }
   }
 }

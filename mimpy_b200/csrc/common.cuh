@@ -45,6 +45,7 @@ struct mimpy_ctx {
   // plan binding of the face records (assemble_brick3.cu): record array and symbolic serial last bound
   const void* bound_geom;
   long long bound_serial;
+  unsigned b3_ticket;    // value of the brick ticket counter (counters[12]) before the next launch
   double* partials;      // reduction partials (device)
   unsigned int* counters;  // last-block counters (device)
   double* scalars;       // device scalars for PCG (alpha, beta, rz, ...)

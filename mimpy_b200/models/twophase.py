@@ -8,6 +8,9 @@ Per time step (twophase.py:703-742):
     find_upwinding_direction (step 1 and every 10th)  -> mimpy_b200_twophase_upwind
     update_saturation -> mimpy_b200_twophase_saturation_step
 State arrays current_p_o / current_u_t / current_s_w are NumPy views refreshed after every step.
+Relative permeabilities: Corey curves are evaluated inside the kernels; user callables given to
+set_kro / set_krw (twophase.py:292-300) are evaluated on the host with NumPy, exactly as the reference
+does, and the resulting per-cell mobilities are handed to the kernels.
 Not covered: the PETSc solver branch, pointer couplings.
 """
 import ctypes as C
@@ -67,6 +70,8 @@ class TwoPhase(object):
         self.pcg_rtol = 1.e-12
         self.newton_history = []
         self.write_well_logs = False
+        self.pressure_files = []      # <well>.inj, one per rate well      (twophase.py:419)
+        self.production_files = []    # <well>.prod, one per pressure well (twophase.py:444)
 
     # ---- setters (twophase.py:198-474) -------------------------------------------------------
     def set_model_name(self, name):
@@ -118,10 +123,15 @@ class TwoPhase(object):
         self.kro = lambda se: (1.0 - np.clip(se, 0., 1.)) ** n_o
 
     def set_kro(self, kro):
-        raise NotImplementedError("user relperm callbacks are not supported on the device path; use set_corey_relperm")
+        """Oil relative permeability as a callable of the scaled saturation array (twophase.py:292-295).
+        The callable runs on the host (NumPy) once per Newton iteration / saturation sub-step."""
+        self.kro = kro
+        self._corey = None
 
     def set_krw(self, krw):
-        raise NotImplementedError("user relperm callbacks are not supported on the device path; use set_corey_relperm")
+        """Water relative permeability callable (twophase.py:297-300); see set_kro."""
+        self.krw = krw
+        self._corey = None
 
     def set_residual_saturation_water(self, v):
         self.residual_saturation_water = v
@@ -175,6 +185,7 @@ class TwoPhase(object):
         self.rate_wells_rate_water.append(injection_rate_water)
         self.rate_wells_rate_oil.append(injection_rate_oil)
         self.rate_wells_name.append(well_name)
+        self.pressure_files.append(open(well_name + ".inj", "w") if self.write_well_logs else None)
         return len(self.rate_wells) - 1
 
     def add_pressure_well(self, bhp, PI, cell_index, well_name):
@@ -182,6 +193,7 @@ class TwoPhase(object):
         self.pressure_wells_bhp.append(bhp)
         self.pressure_wells_pi.append(PI)
         self.pressure_wells_name.append(well_name)
+        self.production_files.append(open(well_name + ".prod", "w") if self.write_well_logs else None)
         return len(self.pressure_wells) - 1
 
     def reset_wells(self):
@@ -210,9 +222,9 @@ class TwoPhase(object):
 
     # ---- device helpers -------------------------------------------------------------------------
     def _fluid(self):
-        if self._corey is None:
-            raise Exception("relative permeabilities not set (set_corey_relperm)")
-        n_o, n_w, k0 = self._corey
+        if self._corey is None and (self.krw is None or self.kro is None):
+            raise Exception("relative permeabilities not set (set_corey_relperm, or set_krw and set_kro)")
+        n_o, n_w, k0 = self._corey if self._corey is not None else (1., 1., 1.)   # unused with callables
         return device.make_fluid(self.viscosity_water, self.viscosity_oil, self.ref_density_water,
                                  self.ref_density_oil, self.compressibility_water, self.compressibility_oil,
                                  self.residual_saturation_water, self.residual_saturation_oil, n_w, n_o, k0)
@@ -221,6 +233,14 @@ class TwoPhase(object):
         import torch
 
         return torch.as_tensor(np.ascontiguousarray(a, dtype=dtype), device=self.ctx.device)
+
+    def _host_mobilities(self, d_s, d_p):
+        """User relperm callables: (water, oil) mobilities per cell as device tensors, evaluated with
+        NumPy from host copies of s_w and p (twophase.py:326-344)."""
+        s = device.to_host(self.ctx, d_s)
+        p = device.to_host(self.ctx, d_p)
+        wm, om = self.water_mobility(s, p), self.oil_mobility(s, p)
+        return self._t(wm), self._t(om)
 
     def _sync_host(self):
         H = lambda t: device.to_host(self.ctx, t)
@@ -305,8 +325,12 @@ class TwoPhase(object):
             newton_residual = 100.
             newton_step = 0
             while abs(newton_residual > self.newton_threshold):
-                ctx.call("mimpy_b200_twophase_mobility", nc, C.byref(fl), _lib.ptr(self._d_s), _lib.ptr(po_k),
-                         _lib.ptr(self._d_invmob), None, None)
+                if self._corey is not None:
+                    ctx.call("mimpy_b200_twophase_mobility", nc, C.byref(fl), _lib.ptr(self._d_s), _lib.ptr(po_k),
+                             _lib.ptr(self._d_invmob), None, None)
+                else:
+                    wm, om = self._host_mobilities(self._d_s, po_k)
+                    torch.reciprocal(wm + om, out=self._d_invmob)
                 x = torch.cat([ut_k, po_k])
                 rhs = torch.empty(plan.ndof, dtype=torch.float64, device=ctx.device)
                 # accumulation diagonal (c_diag) first; rhs terms after the matvec
@@ -360,24 +384,46 @@ class TwoPhase(object):
         sat_delta_t = self.delta_t / float(self.saturation_time_steps)
         mv = dm.view()
         with ctx.on_stream():
+            wm = om = None
+            if self._corey is None:
+                wm, om = self._host_mobilities(self._d_s, self._d_p)
+            well = None
+            if self.pressure_wells:
+                # the well terms use the mobilities of the saturation BEFORE the update (twophase.py:965, 1059-1076)
+                idx = self._t(self.pressure_wells, np.int64)
+                well = (device.to_host(ctx, self._d_s[idx]), device.to_host(ctx, self._d_p[idx]), idx)
             ctx.call("mimpy_b200_twophase_saturation_step", C.byref(mv), C.byref(plan.s), C.byref(self._fl),
                      float(sat_delta_t), _lib.ptr(self._d_upw), _lib.ptr(self._d_u), _lib.ptr(self._d_p),
                      _lib.ptr(self._d_p_prev), _lib.ptr(self._d_phi), self._n_bnd, _lib.ptr(self._d_bf),
                      _lib.ptr(self._d_bs), _lib.ptr(self._d_bw), len(self.rate_wells), _lib.ptr(self._d_wc),
-                     _lib.ptr(self._d_wr), _lib.ptr(self._d_fw), _lib.ptr(self._d_s))
-            if self.pressure_wells:
-                self._pressure_well_saturation(sat_delta_t)
+                     _lib.ptr(self._d_wr), _lib.ptr(self._d_fw), _lib.ptr(self._d_s), _lib.ptr(wm), _lib.ptr(om))
+            if well is not None:
+                self._pressure_well_saturation(sat_delta_t, time_step, *well)
 
-    def _pressure_well_saturation(self, dt):
-        """twophase.py:1053-1090, a handful of cells: evaluated with host scalars."""
-        s = device.to_host(self.ctx, self._d_s)
-        p = device.to_host(self.ctx, self._d_p)
-        wm = self.water_mobility(s, p)
+    def _pressure_well_saturation(self, dt, time_step, s_old, p, idx):
+        """twophase.py:1053-1090, a handful of cells: evaluated with host scalars from the state before
+        the saturation update; production logs as the reference writes them."""
+        import torch
+
+        wm = self.water_mobility(s_old, p)
+        om = self.oil_mobility(s_old, p)
+        add = np.zeros(len(self.pressure_wells))
         for w, cell in enumerate(self.pressure_wells):
-            v = self.pressure_wells_pi[w] * (self.pressure_wells_bhp[w] - p[cell]) * dt * wm[cell]
-            v = v / self.porosities[cell] / self.ref_density_water / (1. + self.compressibility_water * p[cell])
-            v /= self.mesh.get_cell_volume(cell)
-            self._d_s[cell] += float(v)
+            pi, bhp = self.pressure_wells_pi[w], self.pressure_wells_bhp[w]
+            vol = self.mesh.get_cell_volume(cell)
+            wp = pi * (bhp - p[w]) * dt * wm[w]
+            wp = wp / self.porosities[cell] / self.ref_density_water / (1. + self.compressibility_water * p[w])
+            wp /= vol
+            op = pi * (bhp - p[w]) * dt * om[w]
+            op = op / self.porosities[cell] / self.ref_density_oil / (1. + self.compressibility_oil * p[w])
+            op /= vol
+            out = self.production_files[w] if w < len(self.production_files) else None
+            if out is not None and time_step % self.prod_output_frequency == 0:
+                print(time_step, op * (-1), end=' ', file=out)
+                print(wp * (-1), file=out)
+            add[w] = wp
+        # wells listed twice on a cell add twice (next_s_w[cell] += ..., twophase.py:1090)
+        self._d_s.index_add_(0, idx, torch.as_tensor(add, device=self.ctx.device))
 
     def start_solving(self):
         """IMPES driver (twophase.py:703-742).  No VTK output (SURVEY 2 #14)."""
@@ -389,6 +435,11 @@ class TwoPhase(object):
             for _ in range(self.saturation_time_steps):
                 self.update_saturation(time_step)
             self._sync_host()
+            if time_step % self.prod_output_frequency == 0:       # twophase.py:726-730
+                for cell, out in zip(self.rate_wells, self.pressure_files):
+                    if out is not None:
+                        print(time_step, self.current_p_o[cell], end=' ', file=out)
+                        print(self.current_s_w[cell], file=out)
             if time_step % self.output_frequency == 0:
                 self.time_step_output(self.current_time, time_step)
             self.current_time = time_step * self.delta_t
