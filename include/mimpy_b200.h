@@ -384,7 +384,12 @@ int mimpy_b200_twophase_saturation_step(mimpy_ctx* ctx, const mimpy_mesh_view* m
                                         const int32_t* bnd_faces, const int8_t* bnd_sigma,
                                         const double* bnd_fw, int32_t n_rate_wells,
                                         const int32_t* well_cells, const double* well_rate_water,
-                                        double* f_w /*flux_dof, in/out*/, double* s_w /*nc, in/out*/);
+                                        double* f_w /*flux_dof, in/out*/, double* s_w /*nc, in/out*/,
+                                        const double* water_mob /*nc or NULL*/,
+                                        const double* oil_mob /*nc or NULL*/);
+/* water_mob / oil_mob: per-cell phase mobilities evaluated by the caller from the saturation BEFORE this
+ * step -- the path of user relative-permeability callables (TwoPhase.set_krw / set_kro,
+ * twophase.py:292-300); NULL = Corey curves of `fluid_host` evaluated in the kernel. */
 
 /* -- (10) multi-GPU: z-slab partition of the cell set (host side in
  * mimpy_b200/partition.py) ----------------------------------------------------------------------

@@ -88,7 +88,7 @@ SIGNATURES = {
     "mimpy_b200_twophase_upwind": [_vp, _PM, _PS, _vp, _vp],
     "mimpy_b200_twophase_newton_terms": [_vp, _i32, _i32, C.POINTER(Fluid), _f64, _vp, _vp, _vp, _vp, _vp, _vp],
     "mimpy_b200_twophase_saturation_step": [_vp, _PM, _PS, C.POINTER(Fluid), _f64, _vp, _vp, _vp,
-                                            _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
+                                            _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
     "mimpy_b200_set_comm": [_vp, _vp, _i32, _i32],
     "mimpy_b200_nccl_load": [C.c_char_p],
     "mimpy_b200_nccl_unique_id": [_vp],

@@ -26,6 +26,8 @@
 // SURVEY 8d as the roofline numerator.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "cell_core.cuh"
 #include "assemble_args.cuh"
@@ -45,8 +47,8 @@
 #define B3_IN_BYTES (B3_IN_VOL + BR_THREADS * 8)
 #define B3_OFF_SMALL (B3_OFF_IN + B3_IN_BYTES)      /* int run_base[16], cell_base[16], extra_rowstart[80]  */
 #define B3_OFF_BAR (B3_OFF_SMALL + (2 * B2_RUNS + B2_EXTRA_ROWS) * 4)
-#define B3_OFF_IDS (B3_OFF_BAR + 16)                /* int2 {this brick, next brick} per parity              */
-#define B3_SMEM (B3_OFF_IDS + 16)                   /* full, empty                                           */
+#define B3_OFF_IDS (B3_OFF_BAR + 16)                /* int4 {brick, its (bi,bj,bk) packed, next brick, packed} per parity */
+#define B3_SMEM (B3_OFF_IDS + 32)
 #define B3_THREADS (2 * BR_THREADS)                 /* compute warpgroup + producer warpgroup (one warp of it works) */
 #define B3_REGS_PRODUCER 40                         /* setmaxnreg: 2 CTAs x (128 x 216 + 128 x 40) = 64 K registers  */
 #define B3_REGS_COMPUTE 216
@@ -65,6 +67,21 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar) {
 }
 // barrier of the four compute warps only (the producer warp runs ahead on its own)
 __device__ __forceinline__ void sync_compute() { asm volatile("bar.sync 1, %0;" ::"n"(BR_THREADS) : "memory"); }
+// the same barrier with an AND-reduction of a predicate over the compute threads
+__device__ __forceinline__ bool sync_compute_and(bool v) {
+  unsigned r;
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.u32 q, %1, 0;\n"
+      "bar.red.and.pred p, 1, %2, q;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(r)
+      : "r"((unsigned)v), "n"(BR_THREADS)
+      : "memory");
+  return r != 0;
+}
 // bounded: a transfer that never completes raises the device error flag instead of hanging the GPU
 template <bool BACKOFF>
 __device__ __forceinline__ bool mbar_wait(unsigned bar, unsigned parity, unsigned int* error_flag) {
@@ -246,7 +263,7 @@ k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
   const int nx = g.nx, ny = g.ny, nz = g.nz, L = g.L, xrow = g.xrow;
   const bool k_unity = flags & 1;
 
-  int2* s_ids = reinterpret_cast<int2*>(sm + B3_OFF_IDS);
+  int4* s_ids = reinterpret_cast<int4*>(sm + B3_OFF_IDS);
   if (t == 0) {
     mbar_init(bar_full, 1);            // the producer's arrive.expect_tx
     mbar_init(bar_empty, BR_THREADS / 32);  // one arrival per compute warp
@@ -277,12 +294,14 @@ k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
     while (true) {
       const int cbi = bi, cbj = bj, cbk = bk;
       const int bn = b < g.total ? next_brick() : g.total;  // (overwrites bi, bj, bk)
+      // the compute warps get the brick coordinates ready-made: the decode (integer divisions) stays here
+      const int4 ids = make_int4(b, cbi | (cbj << 10) | (cbk << 20), bn, bi | (bj << 10) | (bk << 20));
       if (it > 0) {
         // the operands of the previous brick are in registers
         if (!mbar_wait<true>(bar_empty, (it - 1) & 1u, a.error_flag)) return;
         fence_proxy_async();
       }
-      if (lane == 0) s_ids[it & 1u] = make_int2(b, bn);
+      if (lane == 0) s_ids[it & 1u] = ids;
       __syncwarp();
       if (b >= g.total) {  // tell the compute warps that the work is done
         if (lane == 0) mbar_arrive_expect_tx(bar_full, 0);
@@ -314,26 +333,16 @@ k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
   };
   unsigned phase = 0;
   bool first_brick = true;
+  bool image_regular = false;  // every slot of the image that a regular brick does not write holds the sentinel
   double* const out_t = a.vals + t;
 
   while (true) {
-    // sentinel-fill the output image (free since the barrier that ended the previous brick): a slot
-    // nobody in this brick writes is not stored
-    {
-      const ulonglong2 s2 = make_ulonglong2(AU_SENTINEL, AU_SENTINEL);
-      ulonglong2* r2 = reinterpret_cast<ulonglong2*>(sm + B3_OFF_OUT);
-#pragma unroll 4
-      for (int e = t; e < B2_OUT_SLOTS / 2; e += BR_THREADS) r2[e] = s2;
-      if (t < B2_EXTRA_ROWS) s_extra_rs[t] = 0;
-    }
     if (!mbar_wait<false>(bar_full, phase, a.error_flag)) return;  // (uniform: every compute thread waits on the same phase)
-    const int2 ids = s_ids[phase];
+    const int4 ids = s_ids[phase];
     phase ^= 1u;
     if (ids.x >= g.total) return;
-    int bi, bj, bk, nbi = 0, nbj = 0, nbk = 0;
-    b3_decode(g, ids.x, bi, bj, bk);
-    const int bn = ids.y;
-    if (bn < g.total) b3_decode(g, bn, nbi, nbj, nbk);
+    const int bi = ids.y & 1023, bj = (ids.y >> 10) & 1023, bk = ids.y >> 20;
+    const int bn = ids.z, nbi = ids.w & 1023, nbj = (ids.w >> 10) & 1023, nbk = ids.w >> 20;
     if (first_brick) {
       prefetch(bi, bj, bk, crow, mult, cdiag);
       first_brick = false;
@@ -353,6 +362,7 @@ k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
     int rs[NF];
     unsigned mp[NF], me = 0, other_mask = 0;  // other_mask bit i: face i has a second cell
     double sa[NF], vol = 0., trk = 1.;
+    bool mine_regular = ok;
     if (ok) {
       double K[9], xc[3], sgn[NF];
       double2 rec[NF][4];
@@ -388,6 +398,7 @@ k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
         const unsigned hi = (unsigned)(w >> 32);
         const unsigned p1 = hi & 63u, p2 = (hi >> 8) & 63u;  // lower cell, upper cell of the face
         mp[i] = merged_present(i, p1, p2);
+        mine_regular = mine_regular && mp[i] == 0x7FFu;
         if (i == 0) me = p2;
         if ((i < 3 ? p1 : p2) != 0u) other_mask |= 1u << i;
         sgn[i] = i < 3 ? -1. : 1.;  // hexmesh.py:329-342
@@ -410,7 +421,21 @@ k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
     // during everything below
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty);
-    sync_compute();  // the image is filled, run bases are visible
+    // A REGULAR brick: 128 cells whose six faces are all shared with a cell whose six faces are all flux
+    // DOFs (no boundary, no Neumann face in reach).  Every regular brick writes the same set of image
+    // slots, at positions known at compile time.
+    const bool regular = sync_compute_and(mine_regular);  // (barrier: run bases are visible)
+    if (!(regular && image_regular)) {
+      // sentinel-fill the output image: a slot nobody in this brick writes is not stored.  Skipped from
+      // one regular brick to the next: what the last one wrote is overwritten, the rest still is sentinel.
+      const ulonglong2 s2 = make_ulonglong2(AU_SENTINEL, AU_SENTINEL);
+      ulonglong2* r2 = reinterpret_cast<ulonglong2*>(sm + B3_OFF_OUT);
+#pragma unroll 4
+      for (int e = t; e < B2_OUT_SLOTS / 2; e += BR_THREADS) r2[e] = s2;
+      if (t < B2_EXTRA_ROWS) s_extra_rs[t] = 0;
+      sync_compute();
+    }
+    image_regular = regular;
 
     int crow_n = 0;
     double mult_n = 1., cdiag_n = 0.;
@@ -419,7 +444,8 @@ k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
     double diag[NF];
     unsigned long long other[NF];
     int sb[NF];  // where slot 0 of the face's row lives in the output image
-    if (ok) {
+    auto emit = [&](auto tag) {
+      constexpr bool REG = decltype(tag)::value;
       const int rb = s_runbase[run];
       sb[0] = run * B2_RUN_SLOTS + rs[0] - rb;
       sb[1] = run * B2_RUN_SLOTS + rs[1] - rb;
@@ -443,6 +469,32 @@ k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
         s_extra_rs[B2_RUNS + BX * BZ + lj * BX + li] = rs[5];
       }
       const int cb = B2_CELL0 + run * B2_CELL_SLOTS + (crow - s_cellbase[run]);
+      if (REG) {
+        // regular brick: every position is its index in the merged list; no Neumann test, no popcount
+#pragma unroll
+        for (int i = 0; i < NF; ++i) {
+          row[sb[i] + 11 + (i < 3 ? 1 : 0)] = -sa[i];              // -DIV^T   mfd.py:240-243
+          row[cb + i] = sa[i];                                      // DIV      mfd.py:232-238
+        }
+        row[cb + 6] = a.c_diag ? cdiag : a.alpha * vol;             // mfd.py:766-772
+        cell_core<NF, METHOD>(o, trk, vol, mult, [&](int i, int j, double v) {
+          if (i == j)
+            diag[i] = v;
+          else
+            row[sb[i] + merged_index(i, j)] = v;
+        });
+#pragma unroll
+        for (int i = 0; i < NF; ++i) {  // diagonals, step 1 (see below): every face is shared
+          other[i] = AU_SENTINEL;
+          if (in_brick[i]) {
+            if (i >= 3) row[sb[i] + 5] = diag[i];
+          } else {
+            other[i] = atomicExch(reinterpret_cast<unsigned long long*>(a.diag_pub) + fid[i],
+                                  (unsigned long long)__double_as_longlong(diag[i]));
+          }
+        }
+        return;
+      }
       // Straight-line code from here to the end of cell_core: a store that must not happen (Neumann row or
       // column) goes to the trash word in front of the image (slot index -2 + ... = `dead`) instead of
       // being branched around, so the 36 entry chains of cell_core form ONE basic block and the
@@ -482,7 +534,11 @@ k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
           other[i] = atomicExch(reinterpret_cast<unsigned long long*>(a.diag_pub) + fid[i],
                                 (unsigned long long)__double_as_longlong(diag[i]));
       }
-    }
+    };
+    if (regular)
+      emit(std::true_type{});
+    else if (ok)
+      emit(std::false_type{});
     sync_compute();
     if (ok) {  // diagonals, step 2: the UPPER cell adds its half (lower + upper, fixed order)
 #pragma unroll
@@ -552,6 +608,8 @@ bool mimpy_brick3_applies(const mimpy_mesh_view* mesh, const mimpy_symbolic* sym
   const bool structured = mesh->hex_nx > 0 && mesh->hex_ny > 0 && mesh->hex_nz > 0 &&
                           (long long)mesh->hex_nx * mesh->hex_ny * mesh->hex_nz == mesh->nc;
   if (!structured || mesh->uniform_faces != 6 || mesh->hex_nx % 2 != 0) return false;
+  // the producer hands the brick coordinates to the compute warps packed 10 + 10 + 11 bits
+  if ((mesh->hex_nx + BX - 1) / BX > 1023 || (mesh->hex_ny + BY - 1) / BY > 1023 || (mesh->hex_nz + BZ - 1) / BZ > 2047) return false;
   if (method != 0 && method != 1 && method != 6) return false;
   if (flags & (MIMPY_FLAG_DIRECT_KERNEL | MIMPY_FLAG_GENERIC_KERNEL)) return false;
   if (!sym->face_cell || !sym->face_to_flux || !sym->indptr || sym->serial == 0) return false;
@@ -612,7 +670,7 @@ int mimpy_numeric_brick3(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimp
   g.bk_end = bk_end < nbz ? bk_end : nbz;
   const long long super_tiles = (long long)g.nsx * g.nsy * ((g.bk_end - g.bk_begin + 3) / 4);
   if (super_tiles <= 0) return MIMPY_OK;
-  if (super_tiles * 64 > 0x7fffffffLL) return MIMPY_E_UNSUPPORTED;
+  if (super_tiles * 64 > 0x7fffffffLL || g.nbx > 1023 || g.nby > 1023 || nbz > 2047) return MIMPY_E_UNSUPPORTED;
   g.total = (int)(super_tiles * 64);
   // every CTA's producer draws tickets until it gets one past the end: total + grid draws per launch
   long long grid = (long long)ctx->sm_count * b3_ctas_per_sm();

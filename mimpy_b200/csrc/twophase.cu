@@ -66,15 +66,23 @@ __global__ void k_upwind_last(int F, const long long* __restrict__ last_key, int
   if (*last_key >= 0) upwind[F - 1] = (int)(*last_key >> 6);
 }
 
+// wm / om: per-cell mobilities evaluated by the caller (user relperm callables, twophase.py:292-300);
+// NULL: Corey curves evaluated here
 __global__ void k_frac_flow(int F, mimpy_fluid fl, const int* __restrict__ upwind,
                             const double* __restrict__ sw, const double* __restrict__ p,
+                            const double* __restrict__ wm, const double* __restrict__ om,
                             double* __restrict__ f_w) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= F) return;
   const int c = upwind[g];
   if (c < 0) return;
   double mw, mo;
-  mobilities(fl, sw[c], p[c], mw, mo);
+  if (wm) {
+    mw = wm[c];
+    mo = om[c];
+  } else {
+    mobilities(fl, sw[c], p[c], mw, mo);
+  }
   f_w[g] = mw / (mw + mo);
 }
 
@@ -176,14 +184,16 @@ int mimpy_b200_twophase_saturation_step(mimpy_ctx* ctx, const mimpy_mesh_view* m
                                         const int32_t* bnd_faces, const int8_t* bnd_sigma,
                                         const double* bnd_fw, int32_t n_rate_wells,
                                         const int32_t* well_cells, const double* well_rate_water,
-                                        double* f_w, double* s_w) {
+                                        double* f_w, double* s_w, const double* water_mob,
+                                        const double* oil_mob) {
   REQUIRE(ctx && mesh && sym && fluid_host && upwind_cell && u_t && p && p_prev && porosity && f_w && s_w,
           "NULL argument");
   const int F = sym->flux_dof, nc = mesh->nc;
   if (nc <= 0) return MIMPY_OK;
   cudaStream_t st = ctx->stream;
   const mimpy_fluid fl = *fluid_host;
-  if (F > 0) k_frac_flow<<<(F + 255) / 256, 256, 0, st>>>(F, fl, upwind_cell, s_w, p, f_w);
+  REQUIRE((water_mob == nullptr) == (oil_mob == nullptr), "water_mob and oil_mob must be given together");
+  if (F > 0) k_frac_flow<<<(F + 255) / 256, 256, 0, st>>>(F, fl, upwind_cell, s_w, p, water_mob, oil_mob, f_w);
   if (n_bnd > 0) {
     REQUIRE(bnd_faces && bnd_sigma && bnd_fw, "boundary inflow arrays are NULL");
     k_bnd_inflow<<<(n_bnd + 255) / 256, 256, 0, st>>>(n_bnd, bnd_faces, bnd_sigma, bnd_fw,

@@ -232,6 +232,45 @@ def test_twophase_model_matches_reference_history(golden, variant):
         assert np.linalg.norm(tp.current_u_t - g["u_t"][step - 1]) <= 1e-8 * np.linalg.norm(g["u_t"][step - 1]), step
 
 
+@pytest.mark.parametrize("name", ["pwell", "c4_1233"])
+def test_twophase_round2_cases_match_reference_history(golden, name, tmp_path, monkeypatch):
+    """Two more reference histories (tests/golden/gen_golden_r2.py): `pwell` -- pressure (BHP) wells whose
+    saturation term uses the mobilities of the state BEFORE the update (twophase.py:965, 1053-1090), user
+    relperm callables (set_krw / set_kro, twophase.py:292-300) and compressible fluids, production logs
+    compared with the reference's <well>.prod files; `c4_1233` -- BASELINE config 4 shape at 12x3x3."""
+    import mimpy_b200.mesh.hexmesh as hexmesh
+    import mimpy_b200.models.twophase as twophase
+    import twophase_cases as cases
+
+    g = golden("twophase_" + name)
+    nx, ny, nz, dims, dt, steps = cases.CASES[name]
+    mesh = hexmesh.HexMesh()
+    mesh.build_mesh(nx, ny, nz, dims[0], dims[1], dims[2], cases.permeability(name))
+    tp = twophase.TwoPhase()
+    tp.set_mesh(mesh)
+    tp.write_well_logs = True
+    monkeypatch.chdir(tmp_path)
+    assert cases.configure(tp, mesh, name, "t_") == int(g["steps"])
+    tp.initialize_system()
+    for step in range(1, steps + 1):
+        tp.update_pressure(step)
+        if step == 1 or step % 10 == 0:
+            tp.find_upwinding_direction()
+        tp.update_saturation(step)
+        tp._sync_host()
+        assert abs(tp.current_s_w - g["s_w"][step - 1]).max() < 1e-10, step
+        assert np.linalg.norm(tp.current_p_o - g["p_o"][step - 1]) <= 1e-8 * np.linalg.norm(g["p_o"][step - 1]), step
+        assert np.linalg.norm(tp.current_u_t - g["u_t"][step - 1]) <= 1e-8 * np.linalg.norm(g["u_t"][step - 1]), step
+    if name == "pwell":
+        for f in tp.production_files:
+            f.close()
+        for w, nme in enumerate(tp.pressure_wells_name):
+            log = np.loadtxt(nme + ".prod").reshape(-1, 3)
+            ref = g["prod_log"][w]
+            assert log.shape == ref.shape and np.array_equal(log[:, 0], ref[:, 0])
+            assert np.allclose(log[:, 1:], ref[:, 1:], rtol=1e-7, atol=1e-12 * abs(ref[:, 1:]).max())
+
+
 def test_singlephase_model_matches_reference_history(golden):
     """SinglePhase (implicit compressible stepping, singlephase.py:244-299): 6 steps vs the reference."""
     import mimpy_b200.mesh.hexmesh as hexmesh

@@ -727,7 +727,7 @@ def test_twophase_kernels_vs_reference_history(ctx, golden):
                     f_w.zero_()
                 ctx.call("mimpy_b200_twophase_saturation_step", C.byref(mv), C.byref(plan.s), C.byref(fl), dt,
                          ptr(upw), ptr(u), ptr(p), ptr(p_prev), ptr(poro), nb, ptr(bf), ptr(bs), ptr(bw),
-                         len(wc), ptr(twc), ptr(twr), ptr(f_w), ptr(s_w))
+                         len(wc), ptr(twc), ptr(twr), ptr(f_w), ptr(s_w), None, None)
                 got = s_w.cpu().numpy()
                 assert abs(got - g["s_w"][step - 1]).max() < 1e-10, (variant, step)
                 p_prev = p
