@@ -65,7 +65,7 @@ def test_bench_path_vs_spsolve(ctx, n):
         assert np.array_equal(b, f.rhs)
     ref = spsolve(a.tocsc(), b)
     hyb = device.HybridSystem(dm, plan, None, precond="auxmg", method=1)
-    sol, info = hyb.solve(rhs, rtol=BENCH_RTOL, maxit=2000, check_every=5, norm="saddle")
+    sol, info = hyb.solve(rhs, rtol=BENCH_RTOL, maxit=2000, check_every=5, norm="saddle", saddle_vals=vals)
     x = H(ctx, sol)
     err = np.linalg.norm(x - ref) / np.linalg.norm(ref)
     F = plan.flux_dof
@@ -116,9 +116,10 @@ def test_bench_path_c2_shape_vs_spsolve(ctx):
     assert abs(a - ref_a).max() <= 1e-12 * abs(ref_a).max()
     ref = spsolve(a.tocsc(), b)
     hyb = device.HybridSystem(dm, plan, None, precond="auxmg", method=1)
-    sol, info = hyb.solve(rhs, rtol=BENCH_RTOL, maxit=5000, check_every=5, norm="saddle")
+    sol, info = hyb.solve(rhs, rtol=BENCH_RTOL, maxit=5000, check_every=5, norm="saddle", saddle_vals=vals)
     x = H(ctx, sol)
     F = plan.flux_dof
+    assert np.linalg.norm(a @ x - b) <= 1.05 * BENCH_RTOL * np.linalg.norm(b)     # the verified stopping rule
     err = np.linalg.norm(x - ref) / np.linalg.norm(ref)
     err_p = np.linalg.norm(x[F:] - ref[F:]) / np.linalg.norm(ref[F:])
     assert err <= 1e-8 and err_p <= 1e-8, (err, err_p, info.iterations)
