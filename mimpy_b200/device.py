@@ -463,7 +463,7 @@ class HybridSystem(object):
         norm: what rtol is measured in --
           "face":   ||r||_2 / ||h||_2 of the condensed face system (or / ref_norm when given);
           "saddle": the residual of the ORIGINAL saddle system, ||b - A [v;p]||_2 <= rtol ||b||_2 -- what a user
-                    of the reference's spsolve expects.  The PCG runs on the face residual against
+                    of the reference's sparse direct solve expects.  The PCG runs on the face residual against
                     rtol * ||b||; with `saddle_vals` (the assembled CSR values of `numeric`) the recovered
                     [v;p] is then checked in the saddle matrix itself and, where the two residuals scale
                     differently (anisotropic cells, strong contrast), the PCG continues from where it stopped

@@ -514,6 +514,16 @@ class Mesh(object):
     def get_gravity_acceleration(self):
         return self.gravity_acceleration
 
+    def set_fluid_density(self, density):
+        """MFD.add_gravity reads mesh.get_fluid_density() (mfd.py:1008); the reference's Mesh never defines it.
+        Supplied here so that add_gravity is usable."""
+        self.fluid_density = density
+
+    def get_fluid_density(self):
+        if getattr(self, "fluid_density", None) is None:
+            raise AttributeError("fluid density not set (Mesh.set_fluid_density)")
+        return self.fluid_density
+
     # ---- planar polygon geometry, host side (mesh.py:1575-1756): used when cells are cut --------
     def find_basis_for_face(self, face_index):
         face = self.get_face(face_index)

@@ -13,8 +13,13 @@ Boundary/source callbacks keep the reference's signature (a Python callable of o
 array-valued fast path exists for meshes where nc Python calls are not an option.  Documented
 deviations from the reference: the M block keeps its full STRUCTURAL pattern (the
 reference drops exact zeros, mfd.py:582); get_velocity_solution returns the actual face fluxes
-(the reference returns a constant, mfd.py:1477-1478).  Pointer couplings (build_coupling_terms,
-mfd.py:776-849) are a "next" component: a mesh that defines them raises NotImplementedError.
+(the reference returns a constant, mfd.py:1477-1478).
+
+Pointer couplings (build_coupling_terms, mfd.py:776-849): the coupling entries L, L^T are
+added to the GPU-assembled saddle CSR, and the coupled system K = K0 + E is solved ON THE GPU by flexible GMRES
+preconditioned with the hybridised PCG solve of the uncoupled system K0 (E has one entry pair per pointer,
+so the Krylov space closes after about rank(E) + 1 steps).  Lagrange-multiplier / periodic pointers are
+assembled too, but their multiplier rows are empty in K0, so `solve` refuses them.
 """
 import ctypes as C
 
@@ -182,8 +187,6 @@ class MFD(object):
         key = (id(dm), tuple(sorted(self.neumann_boundary_values.keys())) if len(self.neumann_boundary_values) < 4096
                else hash(self._neumann_mask().tobytes()))
         if self._plan is None or self._plan_key != key or self.neumann_needs_updating:
-            if self.mesh.has_pointer_couplings():
-                raise NotImplementedError("pointer couplings (mfd.py:776-849) are not part of this build")
             self._plan = device.symbolic(dm, self._neumann_mask())
             self._plan_key = key
             self._hybrid = None
@@ -286,10 +289,37 @@ class MFD(object):
         return [np.asarray(data, dtype=float), idx, idx.copy()]
 
     def build_coupling_terms(self):
-        """Empty for meshes without pointer couplings (mfd.py:776-849)."""
-        if self.mesh.has_pointer_couplings():
-            raise NotImplementedError("pointer couplings (mfd.py:776-849) are not part of this build")
-        return [np.zeros(0), np.zeros(0, dtype=np.dtype("i")), np.zeros(0, dtype=np.dtype("i"))]
+        """COO triples [data, row, col] of the matrices L and L^T that couple cells and faces through the
+        mesh's forcing / Dirichlet / Lagrange pointers and periodic boundaries (mfd.py:776-849)."""
+        self._ensure_plan()
+        m, F = self.mesh, self.flux_dof
+        g = self.face_to_flux[:, 0]
+        data, row, col = [], [], []
+        for cell in m.get_forcing_pointer_cells():
+            for (f, orient) in m.get_forcing_pointers_for_cell(cell):
+                data.append(-m.get_face_area(f) * orient)
+                row.append(cell + F)
+                col.append(int(g[f]))
+        for f in m.get_dirichlet_pointer_faces():
+            (cell, orient) = m.get_dirichlet_pointer(f)
+            data.append(m.get_face_area(f) * orient)
+            row.append(int(g[f]))
+            col.append(cell + F)
+        for f in m.get_all_face_to_lagrange_pointers():
+            (lag, orient) = m.get_face_to_lagrange_pointer(f)
+            data.append(m.get_face_area(f) * orient)
+            row.append(int(g[f]))
+            col.append(int(g[lag]))
+        for lag in m.get_all_lagrange_to_face_pointers():
+            for (f, orient) in m.get_lagrange_to_face_pointers(lag):
+                data.append(-m.get_face_area(f) * orient)
+                row.append(int(g[lag]))
+                col.append(int(g[f]))
+        for (f1, o1, f2, o2, lag) in m.periodic_boundaries:
+            data += [m.get_face_area(f1) * o1, m.get_face_area(f2) * o2, o1, o2]     # L^T, L^T, L, L
+            row += [int(g[f1]), int(g[f2]), int(g[lag]), int(g[lag])]
+            col += [int(g[lag]), int(g[lag]), int(g[f1]), int(g[f2])]
+        return [np.asarray(data, dtype=float), np.asarray(row, dtype=np.dtype("i")), np.asarray(col, dtype=np.dtype("i"))]
 
     def build_lhs(self, alpha=0, beta=None):
         """The saddle-point matrix [M -DIV^T; DIV C] (mfd.py:851-914).  Assembled on the GPU straight
@@ -311,6 +341,18 @@ class MFD(object):
         n = plan.ndof
         H = lambda t: device.to_host(self.ctx, t)
         self.lhs = sparse.csr_matrix((H(vals)[:plan.nnz], H(plan.indices)[:plan.nnz], H(plan.indptr)[:n + 1]), shape=(n, n))
+        self._coupled = None
+        if self.mesh.has_pointer_couplings():
+            # the coupling entries sit off the mesh pattern: merged into the assembled CSR (the uncoupled matrix
+            # stays on the device as the preconditioner of the coupled solve)
+            import torch
+            cd, cr, cc = self.build_coupling_terms()
+            self.lhs = (self.lhs + sparse.coo_matrix((cd, (cr, cc)), shape=(n, n))).tocsr()
+            self.lhs.sort_indices()
+            dev = self.ctx.device
+            self._coupled = (torch.as_tensor(self.lhs.indptr.astype(np.int32), device=dev),
+                             torch.as_tensor(self.lhs.indices.astype(np.int32), device=dev),
+                             torch.as_tensor(self.lhs.data, device=dev))
         return self.lhs
 
     def get_number_of_dof(self):
@@ -326,6 +368,30 @@ class MFD(object):
                                            self.cell_forcing_function)
         self.rhs = device.to_host(self.ctx, self.device_rhs)
         return self.rhs
+
+    def add_gravity(self):
+        """rhs[f] += (M_{K=I} g)_f with g_f = rho * |g| * (e_g . n_f) (mfd.py:1001-1025), computed on the device:
+        the k_unity saddle matrix applied to [g; 0].  Like the reference, which indexes the right-hand side by
+        FACE and multiplies a flux_dof-sized matrix with a face-sized vector, this needs a problem without
+        Neumann faces (flux_dof == number of faces)."""
+        import torch
+        dm, plan = self._ensure_plan()
+        m = self.mesh
+        nf = m.get_number_of_faces()
+        if plan.flux_dof != nf:
+            raise ValueError("dimension mismatch: add_gravity needs flux_dof == number of faces (mfd.py:1015-1024)")
+        if self.rhs is None:
+            self.build_rhs()
+        scale = m.get_fluid_density() * m.get_gravity_acceleration()
+        gvec = np.asarray(m.get_gravity_vector(), dtype=float)
+        with self.ctx.on_stream():
+            force = torch.zeros(plan.ndof, dtype=torch.float64, device=self.ctx.device)
+            force[:nf] = scale * (dm.face_normals @ torch.as_tensor(gvec, device=self.ctx.device))
+            vals = device.numeric(dm, plan, self.m_e_construction_method, k_unity=True)
+            mg = device.spmv(self.ctx, plan.indptr, plan.indices, vals, force, n=plan.ndof)
+            self.device_rhs = self.device_rhs.clone()
+            self.device_rhs[:nf] += mg[:nf]
+        self.rhs = device.to_host(self.ctx, self.device_rhs)
 
     def update_m(self, m_coo, multipliers):
         """m_coo[k] = m_data_for_update[k] * multipliers[cell of k] (mfd.py:729-743,
@@ -355,12 +421,70 @@ class MFD(object):
             self._hybrid = device.HybridSystem(dm, plan, self._blocks(), alpha=getattr(self, "_alpha", 0.),
                                                c_diag=getattr(self, "_c_diag", None))
             self._hybrid_key = (self._m_e_key, getattr(self, "_alpha", 0.))
-        sol, info = self._hybrid.solve(rhs, rtol=rtol or self.pcg_rtol, maxit=maxit or self.pcg_maxit)
+        if getattr(self, "_coupled", None) is not None:
+            sol, info = self._solve_coupled(rhs, rtol or self.pcg_rtol, maxit or self.pcg_maxit)
+        else:
+            sol, info = self._hybrid.solve(rhs, rtol=rtol or self.pcg_rtol, maxit=maxit or self.pcg_maxit)
         self.solver_info = {"iterations": int(info.iterations), "residual": float(info.residual),
                             "rhs_norm": float(info.rhs_norm), "ms": float(info.ms_total)}
         self.device_solution = sol
         self.solution = device.to_host(self.ctx, sol)
         return self.solution
+
+    def _solve_coupled(self, rhs, rtol, maxit, restart=200):
+        """Flexible GMRES on the coupled saddle CSR (device SpMV, device vectors), preconditioned by the
+        hybridised PCG solve of the uncoupled system."""
+        import torch
+        m = self.mesh
+        if m.get_all_face_to_lagrange_pointers() or m.get_all_lagrange_to_face_pointers() or m.periodic_boundaries:
+            raise NotImplementedError("solve with Lagrange-multiplier / periodic pointers: their rows are empty in the "
+                                      "uncoupled system that preconditions the coupled solve")
+        ctx, plan = self.ctx, self._plan
+        ip, ix, vv = self._coupled
+        K = lambda v: device.spmv(ctx, ip, ix, vv, v, n=plan.ndof)
+        total_it, total_ms, info = 0, 0., None
+
+        def Pinv(v):
+            nonlocal total_it, total_ms, info
+            z, info = self._hybrid.solve(v, rtol=min(rtol, 1e-12), maxit=maxit)
+            total_it += int(info.iterations)
+            total_ms += float(info.ms_total)
+            return z
+
+        with ctx.on_stream():
+            b = rhs
+            bnorm = float(torch.linalg.norm(b))
+            x = torch.zeros_like(b)
+            r = b.clone()
+            tol = max(rtol, 1e-13) * max(bnorm, 1e-300)
+            for _cycle in range(10):
+                beta = float(torch.linalg.norm(r))
+                if beta <= tol:
+                    break
+                V, Z = [r / beta], []
+                Hm = np.zeros((restart + 1, restart))
+                y = None
+                for j in range(restart):
+                    Z.append(Pinv(V[j]))
+                    w = K(Z[j])
+                    for i in range(j + 1):            # modified Gram-Schmidt
+                        Hm[i, j] = float(torch.dot(w, V[i]))
+                        w = w - Hm[i, j] * V[i]
+                    Hm[j + 1, j] = float(torch.linalg.norm(w))
+                    e1 = np.zeros(j + 2)
+                    e1[0] = beta
+                    y, res, _, _ = np.linalg.lstsq(Hm[:j + 2, :j + 1], e1, rcond=None)
+                    resid = float(np.linalg.norm(Hm[:j + 2, :j + 1] @ y - e1))
+                    if resid <= tol or Hm[j + 1, j] <= 1e-300:
+                        break
+                    V.append(w / Hm[j + 1, j])
+                for c, z in zip(y, Z):
+                    x = x + float(c) * z
+                r = b - K(x)
+        info.iterations, info.ms_total = total_it, total_ms
+        info.residual = float(torch.linalg.norm(r))
+        info.rhs_norm = bnorm
+        return x, info
 
     def get_pressure_solution(self):
         return self.solution[self.flux_dof:]

@@ -57,10 +57,86 @@ def twophase_history(ref, name):
     return d
 
 
+class _ScalarIndexed(np.ndarray):
+    """face_to_flux is an (nf, 1) array and mfd.py:796-846 appends face_to_flux[f] -- a 1-element array -- to an
+    array.array('i'): accepted by the NumPy the reference was written for, a TypeError since NumPy 2.  Runtime
+    compatibility shim (like oracle/ref_shim.py): integer indexing yields the scalar; no source is edited."""
+
+    def __getitem__(self, idx):
+        if isinstance(idx, (int, np.integer)):
+            return int(np.ndarray.__getitem__(self, (idx, 0)))
+        return np.ndarray.__getitem__(self, idx)
+
+
+def _patch_coupling(ref):
+    orig = ref.mfd.MFD.build_coupling_terms
+    if getattr(orig, "_shimmed", False):
+        return
+
+    def build_coupling_terms(self):
+        keep = self.face_to_flux
+        self.face_to_flux = np.asarray(keep).view(_ScalarIndexed)
+        try:
+            return orig(self)
+        finally:
+            self.face_to_flux = keep
+
+    build_coupling_terms._shimmed = True
+    ref.mfd.MFD.build_coupling_terms = build_coupling_terms
+
+
+def coupling_system(ref):
+    """MFD with pointer couplings (mfd.py:776-849): the coupling COO, the full saddle matrix, rhs, spsolve."""
+    import coupling_cases as cc
+
+    _patch_coupling(ref)
+
+    mesh = g1.ref_hex(ref, cc.NX, cc.NY, cc.NZ, cc.DIMS, cc.permeability())
+    faces = cc.add_pointers(mesh)
+    f = ref.mfd.MFD()
+    cc.configure(f, mesh)
+    lhs = g1.quiet(f.build_lhs)
+    rhs = f.build_rhs()
+    cpl = f.build_coupling_terms()
+    d = orc.omesh_to_dict(orc.OMesh.from_mesh(mesh))
+    d["pointer_faces"] = np.array(faces)
+    d["coupling_data"], d["coupling_row"], d["coupling_col"] = np.array(cpl[0]), np.array(cpl[1]), np.array(cpl[2])
+    csr = lhs.tocsr()
+    csr.sort_indices()
+    d["csr_indptr"], d["csr_indices"], d["csr_data"] = csr.indptr.copy(), csr.indices.copy(), csr.data.copy()
+    d["rhs"] = rhs.copy()
+    d["solution"] = np.array(f.solve())
+    return d
+
+
+def gravity_rhs(ref):
+    """MFD.add_gravity (mfd.py:1001-1025) on a full-tensor 4x3x2 box, Dirichlet everywhere (the reference's
+    indexing needs flux_dof == number of faces).  Mesh.get_fluid_density does not exist in the reference
+    (mfd.py:1008 would raise AttributeError): the getter is supplied on the instance, nothing else changes."""
+    ktab = g1.spd_tensors(24, 3, full=True)
+    mesh = g1.ref_hex(ref, 4, 3, 2, (2., 1.5, 1.), ktab)
+    mesh.set_gravity_vector(np.array([0.1, -0.2, -1.]) / np.linalg.norm([0.1, -0.2, -1.]))
+    mesh.get_fluid_density = lambda: 850.
+    f = ref.mfd.MFD()
+    f.set_m_e_construction_method(1)
+    f.set_mesh(mesh)
+    for b in range(6):
+        f.apply_dirichlet_from_function(b, lambda p: 1. + p[0] - 2. * p[2])
+    g1.quiet(f.build_lhs)
+    rhs0 = f.build_rhs().copy()
+    g1.quiet(f.add_gravity)
+    d = orc.omesh_to_dict(orc.OMesh.from_mesh(mesh))
+    d["rhs_before"], d["rhs_after"] = rhs0, f.rhs.copy()
+    d["solution"] = np.array(f.solve())
+    return d
+
+
 def main():
     ref = ref_shim.load_reference()
     for name in cases.CASES:
         g1.save("twophase_" + name, twophase_history(ref, name))
+    g1.save("coupling_433", coupling_system(ref))
+    g1.save("gravity_432", gravity_rhs(ref))
 
 
 if __name__ == "__main__":

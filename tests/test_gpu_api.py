@@ -271,6 +271,78 @@ def test_twophase_round2_cases_match_reference_history(golden, name, tmp_path, m
             assert np.allclose(log[:, 1:], ref[:, 1:], rtol=1e-7, atol=1e-12 * abs(ref[:, 1:]).max())
 
 
+def test_pointer_couplings_match_reference(golden):
+    """Dirichlet / forcing pointers (mesh.py:1397-1525) -> MFD.build_coupling_terms
+    (mfd.py:776-849).  Coupling COO bit-exact, full saddle matrix 1e-12, rhs exact, and the coupled solve
+    (GPU flexible GMRES preconditioned by the hybridised uncoupled solve) within 1e-8 of the reference's spsolve."""
+    import mimpy_b200.mesh.hexmesh as hexmesh
+    import mimpy_b200.mfd.mfd as mfd
+    import coupling_cases as cc
+
+    g = golden("coupling_433")
+    mesh = hexmesh.HexMesh()
+    mesh.build_mesh(cc.NX, cc.NY, cc.NZ, cc.DIMS[0], cc.DIMS[1], cc.DIMS[2], cc.permeability())
+    faces = cc.add_pointers(mesh)
+    assert np.array_equal(faces, g["pointer_faces"])
+    f = mfd.MFD()
+    cc.configure(f, mesh)
+    lhs = f.build_lhs()
+    rhs = f.build_rhs()
+    cd, cr, ccol = f.build_coupling_terms()
+    assert np.array_equal(cr, g["coupling_row"]) and np.array_equal(ccol, g["coupling_col"])
+    assert np.array_equal(cd, g["coupling_data"])
+    n = f.get_number_of_dof()
+    ref = sparse.csr_matrix((g["csr_data"], g["csr_indices"], g["csr_indptr"]), shape=(n, n))
+    assert abs(lhs - ref).max() <= 1e-12 * abs(ref).max()
+    assert np.array_equal(rhs, g["rhs"])
+    sol = f.solve()
+    err = np.linalg.norm(sol - g["solution"]) / np.linalg.norm(g["solution"])
+    assert err <= 1e-8, (err, f.solver_info)
+    assert np.linalg.norm(ref @ sol - rhs) <= 1e-9 * np.linalg.norm(rhs)
+    # a Lagrange pointer assembles, but its solve is refused (loudly)
+    mesh.set_face_to_lagrange_pointer(int(faces[0]), 1, int(faces[1]))
+    f.build_lhs()
+    with pytest.raises(NotImplementedError):
+        f.solve()
+
+
+def test_add_gravity_matches_reference(golden):
+    """MFD.add_gravity (mfd.py:1001-1025): rhs += M_{K=I} (rho g e_g.n) on the device vs the reference."""
+    import mimpy_b200.mesh.hexmesh as hexmesh
+    import mimpy_b200.mfd.mfd as mfd
+
+    g = golden("gravity_432")
+    ref = orc.omesh_from_dict(g)
+    mesh = hexmesh.HexMesh()
+    mesh.build_mesh(4, 3, 2, 2., 1.5, 1., ref.cell_k.reshape(-1, 3, 3))
+    mesh.set_gravity_vector(np.array([0.1, -0.2, -1.]) / np.linalg.norm([0.1, -0.2, -1.]))
+    f = mfd.MFD()
+    f.set_m_e_construction_method(1)
+    f.set_mesh(mesh)
+    for b in range(6):
+        f.apply_dirichlet_from_function(b, lambda p: 1. + p[0] - 2. * p[2])
+    f.build_lhs()
+    assert np.array_equal(f.build_rhs(), g["rhs_before"])
+    with pytest.raises(AttributeError):
+        f.add_gravity()                      # the reference fails the same way: no fluid density on the mesh
+    mesh.set_fluid_density(850.)
+    f.add_gravity()
+    assert abs(f.rhs - g["rhs_after"]).max() <= 1e-12 * abs(g["rhs_after"]).max()
+    sol = f.solve()
+    assert np.linalg.norm(sol - g["solution"]) <= 1e-8 * np.linalg.norm(g["solution"])
+    # with Neumann faces the reference's face-indexed update does not fit the flux numbering
+    f2 = mfd.MFD()
+    f2.set_m_e_construction_method(1)
+    f2.set_mesh(mesh)
+    f2.apply_neumann_from_function(5, zero_flux)
+    for b in range(5):
+        f2.apply_dirichlet_from_function(b, lambda p: 1.)
+    f2.build_lhs()
+    f2.build_rhs()
+    with pytest.raises(ValueError):
+        f2.add_gravity()
+
+
 def test_singlephase_model_matches_reference_history(golden):
     """SinglePhase (implicit compressible stepping, singlephase.py:244-299): 6 steps vs the reference."""
     import mimpy_b200.mesh.hexmesh as hexmesh
