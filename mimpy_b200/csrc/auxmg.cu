@@ -28,17 +28,19 @@
 // straddle a rank; every level exchanges one ghost layer of x (before the residual) and of the coarse
 // correction (before the prolongation) with its z-neighbours (mimpy_layer_exchange, comm.cu); the
 // couplings through the interfaces (tzi / bzi, Galerkin sums of the interface t_f) are applied to
-// the ghost values; the ranks keep coarsening until world x (cells per rank) <= 128, all-gather the
-// coarse right-hand sides and every rank applies the dense inverse of the GLOBAL coarsest operator.
-// The cycle is then the single-GPU cycle (45 iterations at 256^3 on 1, 2 and 8 GPUs; a rank-local
-// block-Jacobi version needed 85 / 145).  tau sums and the prolongated correction of interface rows
-// are completed with the same exchange-add as the SpMV.  Uneven slabs: rank-local cycle.
+// the ghost values.  Below AUX_AGG cells per rank (default 32768) a level is AGGLOMERATED: its right-hand
+// side is all-gathered once (one peer-memory kernel) and every rank runs the rest of the V-cycle
+// redundantly on the GLOBAL coarse grid (nx x ny x world*nz), down to a dense inverse of <= 64 cells -- no
+// ghost exchange and no waiting on neighbours on those levels, whose kernels are pure launch latency.
+// The cycle is the single-GPU cycle up to where the smoothers of the agglomerated levels sit (same
+// iteration counts on 1, 2 and 8 GPUs; a rank-local block-Jacobi version needed 85 / 145 instead of 45).
+// tau sums and the prolongated correction of interface rows are completed with the same exchange-add as
+// the SpMV.  Uneven slabs: rank-local cycle.
 #include "reduce.cuh"
 
 #define AUX_MAX_LEVELS 24
 #define AUX_COARSEST 64
-#define AUX_GLOBAL_MAX 128   /* rows of the shared coarsest operator (world x cells per rank) */
-#define AUX_SLOT (5 * AUX_COARSEST)  /* per-rank record of the shared level: tx, ty, tz, dg, tzi */
+#define AUX_AGG_DEFAULT 32768 /* a level with at most this many cells per rank is agglomerated (8 GPUs, 256^3: 0.805 / 0.756 / 0.721 ms per iteration with 64 / 4096 / 32768) */
 #define AUX_T 256
 
 struct AuxLevel {
@@ -62,11 +64,10 @@ struct mimpy_auxmg {
   double* tsum;  // [flux_dof] sum of the half transmissibilities of a face
   double* cinv;  // dense inverse of the coarsest operator
   double* slab;  // the one stream-ordered allocation all arrays above are carved from
-  int global;    // 1: the coarsest level is shared between the ranks
-  int gn;        // rows of the shared operator = world * cells of the coarsest level
-  double* gset;  // [world * AUX_SLOT] gathered coarsest stencils
-  double* gbuf;  // [gn] gathered coarse right-hand side
-  double* ginv;  // [gn * gn] dense inverse of the shared operator
+  int global;    // 1: slab partition with the hierarchy shared between the ranks
+  int nglob;     // levels of the agglomerated (global, redundantly computed) part of the hierarchy
+  AuxLevel glev[AUX_MAX_LEVELS];  // glev[0] = the last distributed level, gathered: nx x ny x (world * nz)
+  double* gpack; // [world * 6 * n_last] set-up gather of the last distributed level's stencil
   double omega, scale;
   const int* cell_faces;
   const int* face_to_flux;
@@ -190,87 +191,58 @@ __global__ void __launch_bounds__(AUX_T) k_aux_coarsen(AuxLevel F, AuxLevel C) {
   }
 }
 
-// ---- shared coarsest level of a slab partition ----------------------------------------------
-// own record into slot `rank` of the (zeroed) gather buffer; an all-reduce completes the gather
-__global__ void k_aux_global_pack(AuxLevel L, int rank, double* __restrict__ gset) {
-  double* slot = gset + (size_t)rank * AUX_SLOT;
-  for (int c = threadIdx.x; c < L.n; c += blockDim.x) {
-    slot[c] = L.tx[c];
-    slot[AUX_COARSEST + c] = L.ty[c];
-    slot[2 * AUX_COARSEST + c] = L.tz[c];
-    slot[3 * AUX_COARSEST + c] = L.dg[c];
-    if (c < L.nx * L.ny) slot[4 * AUX_COARSEST + c] = L.tzi[c];
+// ---- agglomerated levels of a slab partition ---------------------------------------------------
+// own stencil of the last distributed level into slot `rank` of the (zeroed) gather buffer; an all-reduce
+// completes the gather.  Slot: tx, ty, tz, dd [n each], tzi, bzi [nx*ny each]
+__global__ void __launch_bounds__(AUX_T) k_aux_global_pack(AuxLevel L, int rank, double* __restrict__ gpack) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= L.n) return;
+  double* slot = gpack + (size_t)rank * 6 * L.n;
+  slot[c] = L.tx[c];
+  slot[L.n + c] = L.ty[c];
+  slot[2 * L.n + c] = L.tz[c];
+  slot[3 * L.n + c] = L.dd[c];
+  if (c < L.nx * L.ny) {
+    slot[4 * L.n + c] = L.tzi[c];
+    slot[5 * L.n + c] = L.bzi[c];
   }
 }
 
-// dense inverse of the global coarsest operator: rank r's cells are rows r*n .. r*n+n-1, stacked in z
-__global__ void __launch_bounds__(1024)
-k_aux_global_inverse(int world, int nx, int ny, int nz, const double* __restrict__ gset,
-                     double* __restrict__ ginv) {
-  extern __shared__ double A[];  // N x (N + 1)
-  __shared__ double piv_row[AUX_GLOBAL_MAX], piv_col[AUX_GLOBAL_MAX];
-  const int n = nx * ny * nz, N = world * n, ld = N + 1, t = threadIdx.x, T = blockDim.x;
-  for (int e = t; e < N * ld; e += T) A[e] = 0.;
-  __syncthreads();
-  double dmax = 0.;
-  for (int g = 0; g < N; ++g) dmax = fmax(dmax, gset[(size_t)(g / n) * AUX_SLOT + 3 * AUX_COARSEST + g % n]);
-  for (int g = t; g < N; g += T) {
-    const int r = g / n, c = g % n;
-    const double* slot = gset + (size_t)r * AUX_SLOT;
-    const int i = c % nx, j = (c / nx) % ny, k = c / (nx * ny);
-    A[g * ld + g] = slot[3 * AUX_COARSEST + c] + 1e-13 * dmax;
-    if (i + 1 < nx) { A[g * ld + g + 1] = -slot[c]; A[(g + 1) * ld + g] = -slot[c]; }
-    if (j + 1 < ny) { A[g * ld + g + nx] = -slot[AUX_COARSEST + c]; A[(g + nx) * ld + g] = -slot[AUX_COARSEST + c]; }
-    if (k + 1 < nz) {
-      A[g * ld + g + nx * ny] = -slot[2 * AUX_COARSEST + c];
-      A[(g + nx * ny) * ld + g] = -slot[2 * AUX_COARSEST + c];
-    } else if (r + 1 < world) {  // top layer: the cell above is the bottom-layer cell (i, j) of rank r + 1
-      const int g2 = (r + 1) * n + i + nx * j;
-      const double tu = slot[4 * AUX_COARSEST + i + nx * j];
-      A[g * ld + g2] = -tu;
-      A[g2 * ld + g] = -tu;
-    }
+// global level 0: rank r's cells are the z-layers [r*nz, (r+1)*nz).  The coupling through a rank interface
+// becomes an ordinary tz; the distributed levels keep it in their extra diagonal dd, so it is taken out.
+__global__ void __launch_bounds__(AUX_T)
+k_aux_global_unpack(int n, int nxy, int world, const double* __restrict__ gpack, AuxLevel G) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G.n) return;
+  const int r = g / n, c = g - r * n;
+  const double* slot = gpack + (size_t)r * 6 * n;
+  double tz = slot[2 * n + c], dd = slot[3 * n + c];
+  if (c >= n - nxy) {  // top layer of rank r
+    const double tu = slot[4 * n + (c - (n - nxy))];
+    dd -= tu;
+    if (r + 1 < world) tz = tu;
   }
-  __syncthreads();
-  for (int p = 0; p < N; ++p) {  // in-place Gauss-Jordan, no pivoting (SPD)
-    const double piv = 1.0 / A[p * ld + p];
-    for (int e = t; e < N; e += T) {
-      piv_row[e] = A[p * ld + e] * piv;
-      piv_col[e] = A[e * ld + p];
-    }
-    __syncthreads();
-    for (int e = t; e < N * N; e += T) {
-      const int r = e / N, c = e - r * N;
-      double v;
-      if (r == p) v = (c == p) ? piv : piv_row[c];
-      else if (c == p) v = -piv_col[r] * piv;
-      else v = A[r * ld + c] - piv_col[r] * piv_row[c];
-      A[r * ld + c] = v;
-    }
-    __syncthreads();
+  if (c < nxy) dd -= slot[5 * n + c];  // bottom layer: coupling with the rank below (its tz carries it)
+  G.tx[g] = slot[c];
+  G.ty[g] = slot[n + c];
+  G.tz[g] = tz;
+  G.dd[g] = dd;
+  if (g < G.nx * G.ny) {
+    G.tzi[g] = 0.;
+    G.bzi[g] = 0.;
   }
-  for (int e = t; e < N * N; e += T) ginv[e] = A[(e / N) * ld + e % N];
 }
 
-// x2 = rows of ginv times the gathered right-hand side: the rank's own n cells, then its two ghost
-// layers (top layer of the rank below, bottom layer of the rank above); one warp per row
-__global__ void __launch_bounds__(256)
-k_aux_global_solve(int N, int n, int nxy, int rank, int world, const double* __restrict__ ginv,
-                   const double* __restrict__ gbuf, double* __restrict__ x2) {
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  for (int r = w; r < n + 2 * nxy; r += 8) {
-    int g;
-    if (r < n) g = rank * n + r;
-    else if (r < n + nxy) g = rank > 0 ? (rank - 1) * n + (n - nxy) + (r - n) : -1;
-    else g = rank + 1 < world ? (rank + 1) * n + (r - n - nxy) : -1;
-    if (g < 0) continue;
-    const double* row = ginv + (size_t)g * N;
-    double s = 0.;
-    for (int c = l; c < N; c += 32) s += row[c] * gbuf[c];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (l == 0) x2[r] = s;
-  }
+// result of the global level 0 back into the last distributed level: own cells, then the two ghost layers
+__global__ void __launch_bounds__(AUX_T)
+k_aux_global_extract(int n, int nxy, int rank, int world, const double* __restrict__ gx, double* __restrict__ x2) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n + 2 * nxy) return;
+  long long g;
+  if (t < n) g = (long long)rank * n + t;
+  else if (t < n + nxy) g = rank > 0 ? (long long)rank * n - nxy + (t - n) : -1;
+  else g = rank + 1 < world ? (long long)(rank + 1) * n + (t - n - nxy) : -1;
+  if (g >= 0) x2[t] = gx[g];
 }
 
 // dense inverse of the coarsest operator (n <= AUX_COARSEST), Gauss-Jordan without pivoting (SPD)
@@ -496,10 +468,21 @@ int mimpy_auxmg_apply(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, const 
     k_aux_restrict<<<aux_blocks(L[l + 1].n), AUX_T, 0, st>>>(L[l], L[l + 1]);
   }
   if (h->global) {
-    rc = mimpy_allgather_f64(ctx, L[last].b, L[last].n, h->gbuf);
+    // agglomerated levels: every rank holds the whole coarse grid and cycles on it without communication
+    AuxLevel* G = h->glev;
+    rc = mimpy_allgather_f64(ctx, L[last].b, L[last].n, G[0].b);
     if (rc) return rc;
-    k_aux_global_solve<<<1, 256, 0, st>>>(h->gn, L[last].n, L[last].nx * L[last].ny, ctx->rank, ctx->world, h->ginv,
-                                          h->gbuf, L[last].x2);
+    const int glast = h->nglob - 1;
+    for (int l = 0; l < glast; ++l) {
+      k_aux_presmooth<<<aux_blocks(G[l].n), AUX_T, 0, st>>>(G[l], h->omega);
+      k_aux_restrict<<<aux_blocks(G[l + 1].n), AUX_T, 0, st>>>(G[l], G[l + 1]);
+    }
+    k_aux_coarse_solve<<<1, AUX_COARSEST, 0, st>>>(G[glast], h->cinv);
+    for (int l = glast - 1; l >= 0; --l)
+      k_aux_prolong_smooth<<<aux_blocks(G[l].n), AUX_T, 0, st>>>(G[l], G[l + 1], h->omega, h->scale);
+    const int nxy = L[last].nx * L[last].ny;
+    k_aux_global_extract<<<aux_blocks(L[last].n + 2 * nxy), AUX_T, 0, st>>>(L[last].n, nxy, ctx->rank, ctx->world, G[0].x2,
+                                                                        L[last].x2);
   } else {
     k_aux_coarse_solve<<<1, AUX_COARSEST, 0, st>>>(L[last], h->cinv);
   }
@@ -536,7 +519,7 @@ int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
   int nx = mesh->hex_nx, ny = mesh->hex_ny, nz = mesh->hex_nz;
   size_t total = 0;
   auto pad = [](size_t n) { return (n + 31) & ~(size_t)31; };  // keep every array 256-byte aligned
-  // slab partition with identical slabs on every rank: share the coarsest level (see the header)
+  // slab partition with identical slabs on every rank: share the hierarchy (see the header)
   int coarsest = AUX_COARSEST;
   h->global = 0;
   if (ctx->world > 1 && ctx->world <= 16 && ctx->nccl_comm != nullptr) {
@@ -556,24 +539,41 @@ int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
         same = same && mine[r * 3] == nx && mine[r * 3 + 1] == ny && mine[r * 3 + 2] == nz;
       if (same) {
         h->global = 1;
-        coarsest = AUX_GLOBAL_MAX / ctx->world;
-        if (coarsest > AUX_COARSEST) coarsest = AUX_COARSEST;
+        const char* agg = getenv("MIMPY_B200_AUX_AGG");
+        coarsest = agg ? atoi(agg) : AUX_AGG_DEFAULT;
         if (coarsest < 1) coarsest = 1;
       }
     }
   }
+  auto level_doubles = [&](int lx, int ly, int lz) {
+    const size_t n = (size_t)lx * ly * lz;
+    return 6 * pad(n) + 2 * pad(n + 2 * (size_t)lx * ly) + 2 * pad((size_t)lx * ly);
+  };
   for (;;) {
     if (h->nlev >= AUX_MAX_LEVELS) break;
     AuxLevel& L = h->lev[h->nlev++];
     L.nx = nx; L.ny = ny; L.nz = nz; L.n = nx * ny * nz;
-    total += 6 * pad((size_t)L.n) + 2 * pad((size_t)L.n + 2 * (size_t)nx * ny) + 2 * pad((size_t)nx * ny);
+    total += level_doubles(nx, ny, nz);
     if (L.n <= coarsest) break;
     nx = (nx + 1) / 2; ny = (ny + 1) / 2; nz = (nz + 1) / 2;
   }
-  h->gn = h->global ? ctx->world * h->lev[h->nlev - 1].n : 0;
   if (h->global && (h->lev[h->nlev - 1].n > coarsest || h->nlev < 2)) h->global = 0;
-  total += pad((size_t)AUX_GLOBAL_MAX * AUX_SLOT) + pad(AUX_GLOBAL_MAX) + pad((size_t)AUX_GLOBAL_MAX * AUX_GLOBAL_MAX);
-  if (h->lev[h->nlev - 1].n > AUX_COARSEST) {
+  h->nglob = 0;
+  if (h->global) {  // the agglomerated levels: the last distributed level stacked over the ranks, then coarsened
+    const AuxLevel& last = h->lev[h->nlev - 1];
+    int gx = last.nx, gy = last.ny, gz = last.nz * ctx->world;
+    for (;;) {
+      if (h->nglob >= AUX_MAX_LEVELS) break;
+      AuxLevel& G = h->glev[h->nglob++];
+      G.nx = gx; G.ny = gy; G.nz = gz; G.n = gx * gy * gz;
+      total += level_doubles(gx, gy, gz);
+      if (G.n <= AUX_COARSEST) break;
+      gx = (gx + 1) / 2; gy = (gy + 1) / 2; gz = (gz + 1) / 2;
+    }
+    total += pad((size_t)ctx->world * 6 * last.n);
+  }
+  const int coarse_n = h->global ? h->glev[h->nglob - 1].n : h->lev[h->nlev - 1].n;
+  if (coarse_n > AUX_COARSEST) {
     delete h;
     mimpy_set_error("auxmg_create: too many levels");
     return MIMPY_E_INVALID;
@@ -611,9 +611,17 @@ int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
     L.has_lo = (h->global && ctx->rank > 0) ? 1 : 0;
     L.has_hi = (h->global && ctx->rank < ctx->world - 1) ? 1 : 0;
   }
-  h->gset = take((size_t)AUX_GLOBAL_MAX * AUX_SLOT);
-  h->gbuf = take(AUX_GLOBAL_MAX);
-  h->ginv = take((size_t)AUX_GLOBAL_MAX * AUX_GLOBAL_MAX);
+  for (int l = 0; l < h->nglob; ++l) {
+    AuxLevel& G = h->glev[l];
+    G.tx = take(G.n); G.ty = take(G.n); G.tz = take(G.n); G.dd = take(G.n); G.dg = take(G.n);
+    G.b = take(G.n);
+    G.x = take((size_t)G.n + 2 * (size_t)G.nx * G.ny);
+    G.x2 = take((size_t)G.n + 2 * (size_t)G.nx * G.ny);
+    G.tzi = take((size_t)G.nx * G.ny);
+    G.bzi = take((size_t)G.nx * G.ny);
+    G.has_lo = G.has_hi = 0;
+  }
+  h->gpack = h->global ? take((size_t)ctx->world * 6 * h->lev[h->nlev - 1].n) : nullptr;
   h->wc = take((size_t)h->nc * 6);
   h->fw = take((size_t)h->nf);
   h->tsum = take((size_t)h->flux_dof);
@@ -655,14 +663,17 @@ int mimpy_b200_auxmg_setup(mimpy_ctx* ctx, void* handle, const mimpy_mesh_view* 
   }
   const AuxLevel& last = h->lev[h->nlev - 1];
   if (h->global) {
-    CUDA_TRY(cudaMemsetAsync(h->gset, 0, sizeof(double) * (size_t)ctx->world * AUX_SLOT, st));
-    k_aux_global_pack<<<1, AUX_COARSEST, 0, st>>>(last, ctx->rank, h->gset);
-    rc = mimpy_allreduce_f64(ctx, h->gset, ctx->world * AUX_SLOT);
+    const size_t pack = (size_t)ctx->world * 6 * last.n;
+    CUDA_TRY(cudaMemsetAsync(h->gpack, 0, sizeof(double) * pack, st));
+    k_aux_global_pack<<<aux_blocks(last.n), AUX_T, 0, st>>>(last, ctx->rank, h->gpack);
+    rc = mimpy_allreduce_f64(ctx, h->gpack, (int)pack);
     if (rc) return rc;
-    const size_t smem = sizeof(double) * (size_t)h->gn * (h->gn + 1);
-    CUDA_TRY(cudaFuncSetAttribute(k_aux_global_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize,  // per device
-                                  (int)(sizeof(double) * AUX_GLOBAL_MAX * (AUX_GLOBAL_MAX + 1))));
-    k_aux_global_inverse<<<1, 1024, smem, st>>>(ctx->world, last.nx, last.ny, last.nz, h->gset, h->ginv);
+    k_aux_global_unpack<<<aux_blocks(h->glev[0].n), AUX_T, 0, st>>>(last.n, last.nx * last.ny, ctx->world, h->gpack, h->glev[0]);
+    for (int l = 0; l < h->nglob; ++l) {
+      if (l > 0) k_aux_coarsen<<<aux_blocks(h->glev[l].n), AUX_T, 0, st>>>(h->glev[l - 1], h->glev[l]);
+      k_aux_diag<<<aux_blocks(h->glev[l].n), AUX_T, 0, st>>>(h->glev[l]);
+    }
+    k_aux_dense_inverse<<<1, AUX_T, 0, st>>>(h->glev[h->nglob - 1], h->cinv);
   } else {
     k_aux_dense_inverse<<<1, AUX_T, 0, st>>>(last, h->cinv);
   }

@@ -87,6 +87,12 @@ static int nccl_load(const char* path) {
 #define PEER_GATHER_MAX 64   /* doubles per rank */
 #define PEER_DATA_OFF 16384
 #define PEER_SPIN_MAX (1u << 24)
+// large all-gather (agglomerated multigrid levels, auxmg.cu): behind the halo data,
+//   [parity][source rank] x PEER_BIGG_CAP doubles; flags [parity][source rank] x u64 at PEER_BIGG_FLAG_OFF
+#define PEER_BIGG_CAP 32768
+#define PEER_BIGG_FLAG_OFF 2048
+#define PEER_BIGG_BYTES (sizeof(double) * 2 * 8 * (size_t)PEER_BIGG_CAP)
+__device__ __host__ __forceinline__ size_t peer_bigg_off(size_t halo_cap) { return PEER_DATA_OFF + sizeof(double) * 4 * halo_cap; }
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
   unsigned long long v;
@@ -294,6 +300,42 @@ k_peer_allgather(mimpy_peer pr, const double* __restrict__ mine, int n, double* 
   if (t == 0) pr.epoch[2] = e;
 }
 
+// all-gather of up to PEER_BIGG_CAP doubles per rank: block b pushes this rank's values into rank b's slot
+// [parity][this rank] over NVLink and raises its flag there, then waits for rank b's values in the local slot
+// [parity][b] and copies them out -- one kernel, no block depends on another.  Double-buffered by epoch
+// parity like the other peer collectives (a rank can be at most one gather ahead of its peers).
+__global__ void __launch_bounds__(1024)
+k_peer_allgather_big(mimpy_peer pr, const double* __restrict__ mine, int n, double* __restrict__ out,
+                     unsigned int* counter, unsigned int* error_flag) {
+  const unsigned long long e = pr.epoch[3] + 1;
+  const int par = (int)(e & 1), b = blockIdx.x, t = threadIdx.x;
+  const size_t off = peer_bigg_off(pr.halo_cap);
+  double* dst = reinterpret_cast<double*>(pr.peers[b] + off) + (size_t)(par * 8 + pr.rank) * PEER_BIGG_CAP;
+  for (int i = t; i < n; i += blockDim.x) dst[i] = mine[i];
+  __threadfence_system();
+  __syncthreads();
+  if (t == 0) {
+    st_volatile_u64(reinterpret_cast<unsigned long long*>(pr.peers[b] + PEER_BIGG_FLAG_OFF) + par * 8 + pr.rank, e);
+    const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(pr.local + PEER_BIGG_FLAG_OFF) + par * 8 + b;
+    unsigned int spins = 0;
+    while (ld_volatile_u64(flag) != e && ++spins < PEER_SPIN_MAX) {
+    }
+    if (spins >= PEER_SPIN_MAX) atomicExch(error_flag, 1u);
+    __threadfence_system();
+  }
+  __syncthreads();
+  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(pr.local + off) + (size_t)(par * 8 + b) * PEER_BIGG_CAP;
+  for (int i = t; i < n; i += blockDim.x) out[(size_t)b * n + i] = __longlong_as_double((long long)ld_volatile_u64(src + i));
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    if (atomicAdd(counter, 1u) == gridDim.x - 1) {  // the last block closes the epoch
+      pr.epoch[3] = e;
+      *counter = 0u;
+    }
+  }
+}
+
 __global__ void k_gather_pad(int N, int n, int rank, const double* __restrict__ mine, double* __restrict__ out) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g < N) out[g] = (g / n == rank) ? mine[g - rank * n] : 0.;
@@ -308,6 +350,11 @@ int mimpy_allgather_f64(mimpy_ctx* ctx, const double* mine, int n, double* out) 
   }
   if (ctx->peer.enabled && n <= PEER_GATHER_MAX && ctx->world * n <= 512) {
     k_peer_allgather<<<1, 512, 0, ctx->stream>>>(ctx->peer, mine, n, out, ctx->counters + 9);
+    KERNEL_CHECK();
+    return MIMPY_OK;
+  }
+  if (ctx->peer.enabled && ctx->peer.bigg && n <= PEER_BIGG_CAP) {
+    k_peer_allgather_big<<<ctx->world, 1024, 0, ctx->stream>>>(ctx->peer, mine, n, out, ctx->counters + 13, ctx->counters + 9);
     KERNEL_CHECK();
     return MIMPY_OK;
   }
@@ -474,7 +521,7 @@ int mimpy_b200_set_halo(mimpy_ctx* ctx, int32_t n_owned, int32_t n_lo, const int
 int mimpy_b200_peer_alloc(mimpy_ctx* ctx, int64_t halo_cap_doubles, void* handle64_host) {
   REQUIRE(ctx && handle64_host && halo_cap_doubles >= 0, "bad argument");
   CUDA_TRY(cudaSetDevice(ctx->device));
-  const size_t bytes = PEER_DATA_OFF + sizeof(double) * 4 * (size_t)halo_cap_doubles;
+  const size_t bytes = peer_bigg_off((size_t)halo_cap_doubles) + PEER_BIGG_BYTES;
   char* p = nullptr;
   CUDA_TRY(cudaMalloc(&p, bytes));
   CUDA_TRY(cudaMemset(p, 0, bytes));
@@ -484,6 +531,7 @@ int mimpy_b200_peer_alloc(mimpy_ctx* ctx, int64_t halo_cap_doubles, void* handle
   memcpy(handle64_host, &h, 64);
   ctx->peer.local = p;
   ctx->peer.halo_cap = (size_t)halo_cap_doubles;
+  ctx->peer.bigg = 1;
   return MIMPY_OK;
 }
 

@@ -23,8 +23,9 @@ struct mimpy_peer {
   int enabled, rank, world;
   char* local;
   char** peers;                 // device array of `world` pointers (peers[rank] == local)
-  unsigned long long* epoch;    // device: [0] all-reduce epoch, [1] halo epoch
+  unsigned long long* epoch;    // device: [0] all-reduce, [1] halo, [2] small all-gather, [3] large all-gather
   size_t halo_cap;              // doubles per halo buffer
+  int bigg;                     // 1: the buffer has the large all-gather region behind the halo data
 };
 
 struct mimpy_ctx {
