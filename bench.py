@@ -60,7 +60,7 @@ def launches_per_step(precond, n, nz_local, iters):
 
 
 def pcg_bytes_per_row(nnz_per_row):
-    return 12.0 * nnz_per_row + 108.0
+    return 12.0 * nnz_per_row + 108.0  # SURVEY.md 8d (indexed SpMV: the roofline numerator stays the survey's count)
 
 
 def measured_peak():
@@ -509,8 +509,12 @@ def run_cuda(args):
         for i in range(reps + 3):
             if i == 3:
                 e0.record(ctx.stream)
-            ctx.call("mimpy_b200_spmv_sell", F, _lib.ptr(hyb.sell_ptr), _lib.ptr(hyb.sell_cols), _lib.ptr(hyb.a_vals),
-                     _lib.ptr(xs), _lib.ptr(ys))
+            if getattr(plan, "sell_npat", 0) > 0:   # the SpMV the PCG runs: column patterns, no index array
+                ctx.call("mimpy_b200_spmv_sell_pat", F, _lib.ptr(hyb.sell_ptr), _lib.ptr(hyb.sell_cols), _lib.ptr(plan.sell_pat_id),
+                         _lib.ptr(plan.sell_pat_table), plan.sell_npat, _lib.ptr(hyb.a_vals), _lib.ptr(xs), _lib.ptr(ys))
+            else:
+                ctx.call("mimpy_b200_spmv_sell", F, _lib.ptr(hyb.sell_ptr), _lib.ptr(hyb.sell_cols), _lib.ptr(hyb.a_vals),
+                         _lib.ptr(xs), _lib.ptr(ys))
         e1.record(ctx.stream)
     ctx.sync()
     tj = torch.tensor([float(jinfo.ms_total) / max(int(jinfo.iterations), 1), e0.elapsed_time(e1) / reps],
@@ -651,7 +655,8 @@ def run_cuda(args):
                          "peak_source": peak_src, "frac_of_8TBs_spec": asm_gbs / 8000.,
                          "algorithmic_bytes_per_cell": ASM_BYTES_PER_CELL},
             "roofline_spmv": {"bound": "hbm", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak,
-                              "kernel": "k_spmv_sell (face system, SELL-32), per GPU, timed alone",
+                              "kernel": "k_spmv_sell_pat (face system, SELL-32, %d column patterns: 1 B/row instead of 4 B/entry; numerator = "
+                                        "the indexed count 12 nnz + 20 n), per GPU, timed alone" % getattr(plan, "sell_npat", 0),
                               "ms": spmv_ms, "algorithmic_bytes_per_row": 12.0 * nnz_row + 20.0},
             "roofline_pcg": {"bound": "hbm", "achieved": pcg_gbs, "peak": peak, "unit": "GB/s", "frac": pcg_gbs / peak,
                              "what": "one Jacobi-PCG iteration (3 kernels), 100-iteration run",

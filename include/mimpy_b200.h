@@ -308,6 +308,11 @@ typedef struct {
                            right-hand side the face system was condensed from                   */
   /* outputs */
   double rz0, rz;       /* r.Br of the initial guess and at the end                            */
+  /* inputs, SELL layout only (NULL / 0 = columns are read from sell_cols): the column patterns of
+     mimpy_b200_sell_patterns -- the SpMV then reads one byte per ROW instead of four per entry      */
+  const uint8_t* sell_pat_id;
+  const int32_t* sell_pat_table;
+  int32_t sell_npat;
 } mimpy_pcg_info;
 
 /* work: 4*n doubles (r, p, Ap, spare) */
@@ -323,6 +328,16 @@ int mimpy_b200_pcg(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, const int32
  * pcg_sell / spmv_sell are pcg / spmv on that layout. */
 int mimpy_b200_sell_sizes(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, int32_t* sell_ptr,
                           int64_t* total_host);
+/* Column patterns of a SELL-32 matrix: pat_id[32 * slices] (one byte per row), pat_table[255 *
+ * MIMPY_SELL_PAT_W] offset vectors (column = row + offset) of the 254 most frequent patterns; id 255 =
+ * escape, the row reads sell_cols.  *count_host = number of table patterns, 0 when more than a quarter of
+ * the rows would escape.  Every row is verified against its pattern on the device.  Synchronises. */
+#define MIMPY_SELL_PAT_W 12
+int mimpy_b200_sell_patterns(mimpy_ctx* ctx, int32_t n, const int32_t* sell_ptr, const int32_t* sell_cols,
+                             uint8_t* pat_id, int32_t* pat_table, int32_t* count_host);
+int mimpy_b200_spmv_sell_pat(mimpy_ctx* ctx, int32_t n, const int32_t* sell_ptr, const int32_t* sell_cols,
+                             const uint8_t* pat_id, const int32_t* pat_table, int32_t npat, const double* sell_vals,
+                             const double* x, double* y);
 int mimpy_b200_sell_fill(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, const int32_t* indices,
                          const int32_t* sell_ptr, int32_t* sell_cols);
 int mimpy_b200_pcg_sell(mimpy_ctx* ctx, int32_t n, const int32_t* sell_ptr, const int32_t* sell_cols,

@@ -37,7 +37,7 @@ class PcgInfo(C.Structure):
     _fields_ = [("rtol", _f64), ("atol", _f64), ("maxit", _i32), ("check_every", _i32),
                 ("use_graph", _i32), ("iterations", _i32), ("residual", _f64), ("rhs_norm", _f64),
                 ("ms_total", C.c_float), ("norm_kind", _i32), ("ref_norm", _f64), ("rz0", _f64),
-                ("rz", _f64)]
+                ("rz", _f64), ("sell_pat_id", _vp), ("sell_pat_table", _vp), ("sell_npat", _i32)]
 
 
 class Fluid(C.Structure):
@@ -89,6 +89,8 @@ SIGNATURES = {
     "mimpy_b200_twophase_newton_terms": [_vp, _i32, _i32, C.POINTER(Fluid), _f64, _vp, _vp, _vp, _vp, _vp, _vp],
     "mimpy_b200_twophase_saturation_step": [_vp, _PM, _PS, C.POINTER(Fluid), _f64, _vp, _vp, _vp,
                                             _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mimpy_b200_sell_patterns": [_vp, _i32, _vp, _vp, _vp, _vp, C.POINTER(_i32)],
+    "mimpy_b200_spmv_sell_pat": [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
     "mimpy_b200_set_comm": [_vp, _vp, _i32, _i32],
     "mimpy_b200_nccl_load": [C.c_char_p],
     "mimpy_b200_nccl_unique_id": [_vp],

@@ -205,18 +205,89 @@ k_spmv_sell(int n, const int* __restrict__ sell_ptr, const int* __restrict__ col
   }
 }
 
+// SELL-32 with column patterns (sell.cu): column = row + table[pattern of the row][k]; the table sits in
+// shared memory with an odd pitch (rows of a warp mix a few patterns: no bank conflict between them)
+#define PAT_PITCH (MIMPY_SELL_PAT_W + 1)
+template <bool DOT>
+__global__ void __launch_bounds__(RED_THREADS)
+k_spmv_sell_pat(int n, const int* __restrict__ sell_ptr, const uint8_t* __restrict__ pat_id,
+                const int* __restrict__ pat_table, int npat, const int* __restrict__ cols,
+                const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+                double* partials, unsigned int* counter, double* scal) {
+  __shared__ double sh[32];
+  __shared__ int tab[255 * PAT_PITCH];
+  for (int e = threadIdx.x; e < npat * MIMPY_SELL_PAT_W; e += RED_THREADS)
+    tab[(e / MIMPY_SELL_PAT_W) * PAT_PITCH + e % MIMPY_SELL_PAT_W] = pat_table[e];
+  __syncthreads();
+  const long long n_pad = ((long long)n + 31) & ~31LL;
+  double acc_dot = 0.;
+  for (long long row = (long long)blockIdx.x * RED_THREADS + threadIdx.x; row < n_pad;
+       row += (long long)gridDim.x * RED_THREADS) {
+    const int s = (int)(row >> 5);
+    const int base = __ldg(sell_ptr + s);
+    const int w = (__ldg(sell_ptr + s + 1) - base) >> 5;
+    const double* v = vals + base + (row & 31);
+    const int pid = (int)__ldg(pat_id + row);
+    double a0 = 0., a1 = 0.;
+    int k = 0;
+    if (pid != 255) {
+      const int* off = tab + pid * PAT_PITCH;
+      const double* xr = x + row;
+      for (; k + 3 < w; k += 4) {  // 4 independent value / x chains in flight
+        const double v0 = __ldg(v + 32 * k), v1 = __ldg(v + 32 * (k + 1));
+        const double v2 = __ldg(v + 32 * (k + 2)), v3 = __ldg(v + 32 * (k + 3));
+        a0 += v0 * __ldg(xr + off[k]);
+        a1 += v1 * __ldg(xr + off[k + 1]);
+        a0 += v2 * __ldg(xr + off[k + 2]);
+        a1 += v3 * __ldg(xr + off[k + 3]);
+      }
+      for (; k < w; ++k) a0 += __ldg(v + 32 * k) * __ldg(xr + off[k]);
+    } else {  // escape: a row whose offsets are not in the table reads its columns (same summation order)
+      const int* c = cols + base + (row & 31);
+      for (; k + 3 < w; k += 4) {
+        const double v0 = __ldg(v + 32 * k), v1 = __ldg(v + 32 * (k + 1));
+        const double v2 = __ldg(v + 32 * (k + 2)), v3 = __ldg(v + 32 * (k + 3));
+        a0 += v0 * __ldg(x + __ldg(c + 32 * k));
+        a1 += v1 * __ldg(x + __ldg(c + 32 * (k + 1)));
+        a0 += v2 * __ldg(x + __ldg(c + 32 * (k + 2)));
+        a1 += v3 * __ldg(x + __ldg(c + 32 * (k + 3)));
+      }
+      for (; k < w; ++k) a0 += __ldg(v + 32 * k) * __ldg(x + __ldg(c + 32 * k));
+    }
+    const double acc = a0 + a1;
+    if (row < n) {
+      y[row] = acc;
+      if (DOT) acc_dot += acc * __ldg(x + row);
+    }
+  }
+  if (DOT) {
+    const double vv[1] = {acc_dot};
+    finish_reduction<1>(vv, partials, counter, scal + S_PAP, sh);
+  }
+}
+
 // the face system in either layout
 struct SpmvMat {
   int sell;          // 0: CSR (ptr = indptr), 1: SELL-32 (ptr = sell_ptr)
   const int* ptr;
   const int* idx;
   const double* vals;
+  const uint8_t* pat_id;   // SELL only, nullable: column patterns instead of idx
+  const int* pat_table;
+  int npat;
 };
 
 static void launch_spmv(mimpy_ctx* ctx, int grid, int n, const SpmvMat& A, const double* x, double* y,
                         bool dot) {
   cudaStream_t st = ctx->stream;
-  if (A.sell) {
+  if (A.sell && A.pat_id && A.npat > 0) {
+    if (dot)
+      k_spmv_sell_pat<true><<<grid, RED_THREADS, 0, st>>>(n, A.ptr, A.pat_id, A.pat_table, A.npat, A.idx, A.vals, x, y,
+                                                          ctx->partials, ctx->counters + 0, ctx->scalars);
+    else
+      k_spmv_sell_pat<false><<<grid, RED_THREADS, 0, st>>>(n, A.ptr, A.pat_id, A.pat_table, A.npat, A.idx, A.vals, x, y,
+                                                           nullptr, nullptr, nullptr);
+  } else if (A.sell) {
     if (dot)
       k_spmv_sell<true><<<grid, RED_THREADS, 0, st>>>(n, A.ptr, A.idx, A.vals, x, y, ctx->partials,
                                                       ctx->counters + 0, ctx->scalars);
@@ -299,7 +370,21 @@ int mimpy_b200_spmv_sell(mimpy_ctx* ctx, int32_t n, const int32_t* sell_ptr, con
   if (n <= 0) return MIMPY_OK;
   long long want = ((long long)n + RED_THREADS - 1) / RED_THREADS;
   const int grid = (int)(want < (long long)ctx->sm_count * 8 ? want : (long long)ctx->sm_count * 8);
-  SpmvMat A = {1, sell_ptr, sell_cols, sell_vals};
+  SpmvMat A = {1, sell_ptr, sell_cols, sell_vals, nullptr, nullptr, 0};
+  launch_spmv(ctx, grid, n, A, x, y, false);
+  KERNEL_CHECK();
+  return MIMPY_OK;
+}
+
+int mimpy_b200_spmv_sell_pat(mimpy_ctx* ctx, int32_t n, const int32_t* sell_ptr, const int32_t* sell_cols,
+                             const uint8_t* pat_id, const int32_t* pat_table, int32_t npat, const double* sell_vals,
+                             const double* x, double* y) {
+  REQUIRE(ctx && sell_ptr && sell_cols && pat_id && pat_table && sell_vals && x && y, "NULL argument");
+  REQUIRE(npat > 0 && npat <= 254, "pattern count out of range");
+  if (n <= 0) return MIMPY_OK;
+  long long want = ((long long)n + RED_THREADS - 1) / RED_THREADS;
+  const int grid = (int)(want < (long long)ctx->sm_count * 8 ? want : (long long)ctx->sm_count * 8);
+  SpmvMat A = {1, sell_ptr, sell_cols, sell_vals, pat_id, pat_table, npat};
   launch_spmv(ctx, grid, n, A, x, y, false);
   KERNEL_CHECK();
   return MIMPY_OK;
@@ -430,14 +515,15 @@ extern "C" {
 int mimpy_b200_pcg(mimpy_ctx* ctx, int32_t n, const int32_t* indptr, const int32_t* indices,
                    const double* vals, const double* diag_inv, const double* b, double* x,
                    double* work, mimpy_pcg_info* info) {
-  SpmvMat A = {0, indptr, indices, vals};
+  SpmvMat A = {0, indptr, indices, vals, nullptr, nullptr, 0};
   return pcg_core(ctx, n, A, diag_inv, b, x, work, info);
 }
 
 int mimpy_b200_pcg_sell(mimpy_ctx* ctx, int32_t n, const int32_t* sell_ptr, const int32_t* sell_cols,
                         const double* sell_vals, const double* diag_inv, const double* b, double* x,
                         double* work, mimpy_pcg_info* info) {
-  SpmvMat A = {1, sell_ptr, sell_cols, sell_vals};
+  REQUIRE(info, "NULL argument");
+  SpmvMat A = {1, sell_ptr, sell_cols, sell_vals, info->sell_pat_id, info->sell_pat_table, info->sell_npat};
   return pcg_core(ctx, n, A, diag_inv, b, x, work, info);
 }
 
@@ -445,7 +531,9 @@ int mimpy_b200_pcg_aux(mimpy_ctx* ctx, int32_t n, const int32_t* ptr, const int3
                        const double* vals, int32_t sell, const double* diag_inv, void* auxmg,
                        const double* b, double* x, double* work, mimpy_pcg_info* info) {
   REQUIRE(auxmg, "NULL preconditioner handle");
-  SpmvMat A = {sell ? 1 : 0, ptr, idx, vals};
+  REQUIRE(info, "NULL argument");
+  SpmvMat A = {sell ? 1 : 0, ptr, idx, vals, sell ? info->sell_pat_id : nullptr, sell ? info->sell_pat_table : nullptr,
+               sell ? info->sell_npat : 0};
   return pcg_core(ctx, n, A, diag_inv, b, x, work, info, static_cast<mimpy_auxmg*>(auxmg));
 }
 

@@ -395,6 +395,7 @@ class HybridSystem(object):
         if precond not in ("auxmg", "jacobi"):
             raise ValueError("unknown preconditioner %r" % (precond,))
         self.precond = precond
+        self.use_patterns = True   # SELL SpMV with column patterns where the plan has them
         self.aux = None
         if m_e is None and method is None:
             raise ValueError("HybridSystem needs the M_E blocks or the construction method")
@@ -415,6 +416,13 @@ class HybridSystem(object):
                     ctx.call("mimpy_b200_sell_fill", F, ptr(plan.m_indptr), ptr(plan.m_indices), ptr(sp), ptr(sc))
                     plan.t["sell_ptr"], plan.t["sell_cols"] = sp, sc
                     plan.sell_total = int(total.value)
+                    # column patterns (one byte per row instead of four per entry) where the matrix has few of them
+                    pid = torch.zeros((F + 31) // 32 * 32, dtype=torch.uint8, device=dev)
+                    ptab = torch.zeros(255 * 12, dtype=torch.int32, device=dev)
+                    npat = C.c_int32(0)
+                    ctx.call("mimpy_b200_sell_patterns", F, ptr(sp), ptr(sc), ptr(pid), ptr(ptab), C.byref(npat))
+                    plan.sell_npat = int(npat.value)
+                    plan.t["sell_pat_id"], plan.t["sell_pat_table"] = (pid, ptab) if plan.sell_npat > 0 else (None, None)
                 self.sell_ptr, self.sell_cols = plan.t["sell_ptr"], plan.t["sell_cols"]
                 self.a_vals = torch.zeros(max(plan.sell_total, 1), dtype=torch.float64, device=dev)  # padding stays 0
             else:
@@ -498,6 +506,10 @@ class HybridSystem(object):
                 info.check_every, info.use_graph = check_every, 1 if use_graph else 0
                 info.norm_kind = 1 if norm == "energy" else 0
                 info.ref_norm = float(ref_norm) if ref_norm else 0.
+                if self.layout == "sell" and getattr(plan, "sell_npat", 0) > 0 and self.use_patterns:
+                    info.sell_pat_id = plan.t["sell_pat_id"].data_ptr()
+                    info.sell_pat_table = plan.t["sell_pat_table"].data_ptr()
+                    info.sell_npat = plan.sell_npat
                 allow = () if raise_on_noconv else (_lib.MIMPY_E_NOCONV,)
                 if self.aux is not None:
                     sell = self.layout == "sell"

@@ -572,6 +572,48 @@ def test_sell_layout_equals_csr_layout(ctx, golden):
         assert np.linalg.norm(H(ctx, s1) - H(ctx, s2)) <= 1e-11 * np.linalg.norm(H(ctx, s2))
 
 
+@pytest.mark.parametrize("dims", [(16, 12, 10), (7, 5, 3), (40, 36, 34)])
+def test_sell_column_patterns_equal_indexed_spmv(ctx, dims):
+    """SELL-32 SpMV with column patterns (one byte per row + <= 255 offset vectors, sell.cu) is the indexed
+    SpMV bit for bit, and so is the PCG built on it; a matrix with too many patterns keeps the indexed path."""
+    import ctypes as C
+    import torch
+    from mimpy_b200 import device
+    from mimpy_b200._lib import ptr
+
+    nx, ny, nz = dims
+    nc = nx * ny * nz
+    rng = np.random.default_rng(4)
+    g = np.exp(rng.standard_normal((nc, 3)))
+    k = np.zeros((nc, 9))
+    k[:, 0], k[:, 4], k[:, 8] = g[:, 0], g[:, 1], g[:, 2]
+    d = device.DeviceMesh.hex(ctx, nx, ny, nz, 1., 1., 1., cell_k=k)
+    hx = HexIndexHost(nx, ny, nz)
+    mask = np.zeros(d.nf, dtype=np.uint8)
+    for b in (2, 3, 4):
+        mask[hx.boundary(b)] = 1
+    mask[hx.boundary(5)[::3]] = 1              # an irregular Neumann set: more patterns
+    plan = device.symbolic(d, mask)
+    hyb = device.HybridSystem(d, plan, None, method=1, precond="jacobi")
+    F = plan.flux_dof
+    assert 0 < plan.sell_npat <= 254
+    with ctx.on_stream():
+        x = torch.as_tensor(rng.standard_normal(F), device=ctx.device)
+        y1 = torch.empty(F, dtype=torch.float64, device=ctx.device)
+        y2 = torch.empty(F, dtype=torch.float64, device=ctx.device)
+        ctx.call("mimpy_b200_spmv_sell", F, ptr(hyb.sell_ptr), ptr(hyb.sell_cols), ptr(hyb.a_vals), ptr(x), ptr(y1))
+        ctx.call("mimpy_b200_spmv_sell_pat", F, ptr(hyb.sell_ptr), ptr(hyb.sell_cols), ptr(plan.sell_pat_id), ptr(plan.sell_pat_table),
+                 plan.sell_npat, ptr(hyb.a_vals), ptr(x), ptr(y2))
+    assert np.array_equal(H(ctx, y1), H(ctx, y2))
+    xm = hx.boundary(0)
+    areas = H(ctx, d.face_areas)
+    rhs = device.build_rhs(d, plan, xm.astype(np.int32), -areas[xm], True, 0., None)
+    s1, i1 = hyb.solve(rhs, rtol=1e-12, maxit=5000, check_every=10)
+    hyb.use_patterns = False
+    s2, i2 = hyb.solve(rhs, rtol=1e-12, maxit=5000, check_every=10)
+    assert i1.iterations == i2.iterations and np.array_equal(H(ctx, s1), H(ctx, s2))
+
+
 @pytest.mark.parametrize("dims,alpha", [((12, 10, 9), 0.), ((16, 16, 16), 0.), ((21, 6, 14), 0.7), ((5, 4, 3), 0.)])
 def test_auxmg_preconditioner_vs_spsolve_and_jacobi(ctx, dims, alpha):
     """PCG with the auxiliary-space multigrid preconditioner (csrc/auxmg.cu) on structured hexes:
