@@ -35,28 +35,58 @@ ASM_BYTES_PER_CELL = 700.0     # 332 B read + 368 B written per he
 # upwind cell 16 + f_w 8 = 28 B) and k_saturation per cell (cell_faces 24 + sigma 6 + per face f2f 4 + area record sector
 # 32 + f_w 8 + u_t 8 (x6 gathers, each face read by two cells) + p, p_prev, phi, vol, s_w 40 + s_w written 8)
 SAT_BYTES_PER_CELL = 3 * 28.0 + (24 + 6 + 6 * (4 + 8 + 8) + 3 * 32 + 48)
-# dram__bytes_read.sum + dram__bytes_write.sum of k_numeric_brick2<1> at 256^3, one `ncu --set full`
-# capture (profiles/r1_ncu_full_summary.txt): 7.12 GB + 6.46 GB
-ASM_TRAFFIC_256 = 13.59e9
 
 
-def aux_levels(nx, ny, nz):
-    """Levels of the auxiliary-space multigrid (csrc/auxmg.cu: halve until <= 64 cells)."""
+def measured_traffic(n, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the assembly kernel, from the committed
+    `ncu --set full` capture (profiles/asm_traffic.json, written by scripts/ncu_traffic.py from the .ncu-rep).
+    The record carries the MD5 of the kernel sources it was captured with: if they changed since, the number
+    is stale and None is reported instead."""
+    import hashlib
+    p = os.path.join(ROOT, "profiles", "asm_traffic.json")
+    if world != 1 or not os.path.exists(p):
+        return None, "no capture for this configuration"
+    try:
+        rec = json.load(open(p))
+        h = hashlib.md5()
+        for f in rec["sources"]:
+            h.update(open(os.path.join(ROOT, f), "rb").read())
+        if h.hexdigest() != rec["sources_md5"]:
+            return None, "kernel sources changed since the capture %s" % rec.get("capture")
+        if int(rec["n"]) != int(n):
+            return None, "capture is for n = %s" % rec["n"]
+        return float(rec["dram_bytes_read"]) + float(rec["dram_bytes_write"]), rec.get("capture")
+    except Exception as e:
+        return None, "unreadable capture record: %s" % e
+
+
+def aux_levels(nx, ny, nz, coarsest=64):
+    """Levels of the auxiliary-space multigrid (csrc/auxmg.cu: halve until <= coarsest cells)."""
     lv = 1
-    while nx * ny * nz > 64:
+    while nx * ny * nz > coarsest:
         nx, ny, nz = (nx + 1) // 2, (ny + 1) // 2, (nz + 1) // 2
         lv += 1
-    return lv
+    return lv, (nx, ny, nz)
 
 
-def launches_per_step(precond, n, nz_local, iters):
-    """Kernels of OUR library launched by one bench step (assembly, set-up, solve)."""
-    setup = 1 + 4 + 1 + 1              # assembly; fused hybrid set-up (zero, set-up, diag, invert); rhs; recover
+def launches_per_step(precond, n, nz_local, iters, world=1, rounds=1):
+    """Kernels of OUR library launched by one bench step (assembly, set-up, solve): a count from the launch
+    sites of csrc/ (pcg.cu:launch_iteration, auxmg.cu:mimpy_auxmg_apply, comm.cu), not a measurement."""
+    comm = world > 1
+    halo = 2 if comm else 0            # k_peer_halo_push + k_peer_halo_add
+    red = 1 if comm else 0             # k_peer_allreduce
+    setup = 1 + 4 + 1                  # assembly; fused hybrid set-up (zero, set-up, diag, invert); face rhs
     if precond != "auxmg":
-        return setup + 3 + 3 * iters   # PCG init + 3 kernels per iteration
-    lv = aux_levels(n, n, nz_local)
-    cycle = 2 + 3 * (lv - 1) + 1       # face restrict/prolong, (pre-smooth, restrict, prolong) per level, coarse solve
-    return setup + (2 + 2 * lv) + (3 + cycle + 1) + (3 + cycle) * iters
+        return setup + 3 + (3 + halo + 2 * red) * iters + rounds * 2
+    if not comm:
+        lv, _ = aux_levels(n, n, nz_local)
+        cycle = 2 + 3 * (lv - 1) + 1   # face restrict / prolong, (pre-smooth, restrict, prolong) per level, coarse solve
+    else:
+        lv, (cx, cy, cz) = aux_levels(n, n, nz_local, 32768)   # distributed levels, then the agglomerated ones
+        glv, _ = aux_levels(cx, cy, cz * world)
+        cycle = 2 + 3 * (lv - 1) + 2 * (2 * (lv - 1) - 1) + 2 + 3 * (glv - 1) + 1   # + ghost-layer copies, gather, extract
+    per_iter = 3 + cycle + halo * 2 + red * 2    # SpMV, two vector updates; halo on Ap and z; two scalar all-reduces
+    return setup + (2 + 2 * lv) + (3 + cycle + 1) + per_iter * iters + rounds * 2   # + recover and saddle check per round
 
 
 def pcg_bytes_per_row(nnz_per_row):
@@ -538,7 +568,13 @@ def run_cuda(args):
     # per-GPU achieved bandwidth of the dominant kernels (algorithmic bytes of the local slab)
     asm_gbs = ASM_BYTES_PER_CELL * (nc_total / world) / (asm_ms / 1e3) / 1e9
     pcg_gbs = pcg_bytes_per_row(nnz_row) * (rows_total / world) / (jacobi_ms_iter / 1e3) / 1e9
-    spmv_gbs = (12.0 * nnz_row + 20.0) * (rows_total / world) / (spmv_ms / 1e3) / 1e9
+    # bytes the SpMV kernel that runs really has to move: with column patterns 8 B per entry + 1 B per row
+    # for the pattern id instead of 12 B per entry (the survey's indexed count)
+    pat = getattr(plan, "sell_npat", 0) > 0
+    spmv_row_bytes = (8.0 * nnz_row + 21.0) if pat else (12.0 * nnz_row + 20.0)
+    pcg_row_bytes = spmv_row_bytes + 88.0
+    pcg_gbs = pcg_row_bytes * (rows_total / world) / (jacobi_ms_iter / 1e3) / 1e9
+    spmv_gbs = spmv_row_bytes * (rows_total / world) / (spmv_ms / 1e3) / 1e9
 
     sol = res[-1]["sol"]
     with ctx.on_stream():
@@ -563,47 +599,28 @@ def run_cuda(args):
     sol_v_l2 = owned_norm(zc)
     del zc, res_vec
 
-    # ---- e2e: pinned host buffers in and out (H2D of K, D2H of the CSR values), every rank its slab.
-    # The assembly runs slab by slab (cell layers), so the download of one slab's finished rows
-    # overlaps the upload of K for the next: PCIe is full duplex and the transfers, not the 3 ms
-    # kernel, are what this number is made of.
+    # ---- e2e: pinned host buffers in and out through the library's host entry points (mimpy_b200/hostpipe.py),
+    # every rank its slab.  (a) the headline metric end to end: cell_k (host) -> assembly -> CSR values (host);
+    # the assembly runs slab by slab so that the download of one slab's finished rows overlaps the upload
+    # of K for the next (PCIe is full duplex; the transfers, not the 2.5 ms kernel, are what this number
+    # is made of).  (b) the solve end to end: cell_k (host) -> set-up -> PCG -> [v; p] (host).
+    # Each rank times itself (CUDA-synchronised wall clock); the slowest rank counts.  No collective and no
+    # barrier inside the timed regions.
     e2e = None
+    e2e_solve = None
     if not args.no_e2e:
+        from mimpy_b200 import hostpipe
         nc_loc = dm.nc
         k_pin = torch.from_numpy(pb["k_host"]).pin_memory().reshape(nc_loc, 9)
         vals_host = torch.empty(plan.nnz, dtype=torch.float64).pin_memory()
-        nzl, layer = pb["slab"].nzl, n * n
-        n_slabs = max(1, min(8, nzl // 16))
-        per = ((nzl + n_slabs - 1) // n_slabs + 3) // 4 * 4
-        bounds = list(range(0, nzl, per)) + [nzl]
-        ranges = device.layer_value_ranges(dm, plan, bounds)
-        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        piped = device.numeric_layers(dm, plan, method, vals, bounds[0], bounds[1])  # supported on this mesh?
+        pipe = hostpipe.AssemblyPipeline(dm, plan, method, n_slabs=8)
         times = []
-        for s in range(3):
+        for s in range(4):
             barrier()
             t0 = time.perf_counter()
-            if piped:
-                for (k0, k1), ((f0, f1), (c0, c1)) in zip(zip(bounds[:-1], bounds[1:]), ranges):
-                    with torch.cuda.stream(s_in):
-                        dm.cell_k[k0 * layer:k1 * layer].copy_(k_pin[k0 * layer:k1 * layer], non_blocking=True)
-                        ev_in = s_in.record_event()
-                    ctx.stream.wait_event(ev_in)
-                    device.numeric_layers(dm, plan, method, vals, k0, k1)
-                    ev_k = ctx.stream.record_event()
-                    s_out.wait_event(ev_k)
-                    with torch.cuda.stream(s_out):
-                        vals_host[f0:f1].copy_(vals[f0:f1], non_blocking=True)
-                        vals_host[c0:c1].copy_(vals[c0:c1], non_blocking=True)
-                s_out.synchronize()
-            else:
-                with ctx.on_stream():
-                    dm.cell_k.copy_(k_pin, non_blocking=True)
-                    device.numeric(dm, plan, method, vals=vals)
-                    vals_host.copy_(vals, non_blocking=True)
-            ctx.sync()
-            barrier()
+            pipe.run(k_pin, vals_host)
             times.append(time.perf_counter() - t0)
+        barrier()
         # what arrived on the host is the matrix of a plain full assembly
         device.numeric(dm, plan, method, vals=vals)
         ctx.sync()
@@ -613,11 +630,30 @@ def run_cuda(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": nc_total / float(tt) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": int(k_pin.numel() * 8 * world), "d2h_bytes_per_step": int(vals_host.numel() * 8 * world),
-               "what": "per rank: cell_k from pinned host -> numeric assembly -> CSR values to pinned host (wall clock, max "
-                       "over ranks)" + ("; %d layer slabs, upload / kernel / download pipelined on three streams" % (len(bounds) - 1)
-                                        if piped else ""),
+               "what": "mimpy_b200.hostpipe.AssemblyPipeline.run, per rank: cell_k from pinned host -> numeric assembly -> CSR "
+                       "values to pinned host (wall clock of the slowest rank)" +
+                       ("; %d layer slabs, upload / kernel / download pipelined on three streams" % (len(pipe.bounds) - 1)
+                        if pipe.piped else ""),
                "host_result_equals_full_assembly": e2e_ok}
-        del k_pin, vals_host
+        del vals_host, pipe
+        if world == 1:
+            sol_host = torch.empty(plan.ndof, dtype=torch.float64).pin_memory()
+            ts = []
+            for s in range(2):
+                barrier()
+                t0 = time.perf_counter()
+                sinfo = hostpipe.solve_to_host(dm, plan, method, k_pin, rhs, sol_host, rtol=args.rtol, precond=args.precond,
+                                               saddle_vals=vals, maxit=args.maxit, check_every=check_every,
+                                               raise_on_noconv=False)
+                ts.append(time.perf_counter() - t0)
+            e2e_solve = {"value": nc_total / min(ts) / 1e6, "unit": "Mcells/s (assembled into the face system and solved)",
+                         "seconds": min(ts), "pcg_iters": int(sinfo.iterations),
+                         "h2d_bytes_per_step": int(k_pin.numel() * 8), "d2h_bytes_per_step": int(sol_host.numel() * 8),
+                         "what": "mimpy_b200.hostpipe.solve_to_host: cell_k from pinned host -> fused hybrid set-up -> PCG "
+                                 "(residual of the saddle system <= rtol ||b||, verified) -> [v; p] to pinned host",
+                         "host_result_equals_device_solve": bool(torch.allclose(sol_host, sol.cpu(), rtol=0, atol=1e-9 * float(sol.abs().max())))}
+            del sol_host
+        del k_pin
 
     extra = None
     if not args.no_extras and rank == 0 and world == 1:
@@ -630,6 +666,7 @@ def run_cuda(args):
                "host_cores_available": os.cpu_count(),
                "sample": "%d^3 cells of the same workload (build_lhs+build_rhs, %.1f s); O(cells)" % (args.cpu_n, dt)}
 
+    traffic, traffic_src = measured_traffic(n, world)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -650,20 +687,22 @@ def run_cuda(args):
             "solution_norms": {"p_l2": sol_p_l2, "v_l2": sol_v_l2,
                                "note": "compare across N: the partitioned solves agree with the 1-GPU solve to the PCG tolerance"},
             "roofline": {"bound": "hbm", "achieved": asm_gbs, "peak": peak, "unit": "GB/s", "frac": asm_gbs / peak,
-                         "traffic": ASM_TRAFFIC_256 if (n == 256 and world == 1) else None,
-                         "kernel": "k_numeric_brick2<1> (fused M_E + CSR assembly), per GPU",
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "k_numeric_brick3<1> (pipelined brick: fused M_E + CSR assembly, bulk-copy staging), per GPU",
                          "peak_source": peak_src, "frac_of_8TBs_spec": asm_gbs / 8000.,
                          "algorithmic_bytes_per_cell": ASM_BYTES_PER_CELL},
             "roofline_spmv": {"bound": "hbm", "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak,
-                              "kernel": "k_spmv_sell_pat (face system, SELL-32, %d column patterns: 1 B/row instead of 4 B/entry; numerator = "
-                                        "the indexed count 12 nnz + 20 n), per GPU, timed alone" % getattr(plan, "sell_npat", 0),
-                              "ms": spmv_ms, "algorithmic_bytes_per_row": 12.0 * nnz_row + 20.0},
+                              "kernel": "k_spmv_sell_pat (face system, SELL-32, %d column patterns: 1 B/row instead of 4 B/entry; the "
+                                        "numerator counts what this kernel moves, 8 nnz + 21 n), per GPU, timed alone" % getattr(plan, "sell_npat", 0),
+                              "ms": spmv_ms, "algorithmic_bytes_per_row": spmv_row_bytes,
+                              "survey_indexed_bytes_per_row": 12.0 * nnz_row + 20.0},
             "roofline_pcg": {"bound": "hbm", "achieved": pcg_gbs, "peak": peak, "unit": "GB/s", "frac": pcg_gbs / peak,
                              "what": "one Jacobi-PCG iteration (3 kernels), 100-iteration run",
                              "s_per_iter": jacobi_ms_iter / 1e3,
-                             "algorithmic_bytes_per_row": pcg_bytes_per_row(nnz_row), "rows": int(rows_total)},
-            "configs": extra, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(args.steps * launches_per_step(args.precond, n, slab_nz, iters)),
+                             "algorithmic_bytes_per_row": pcg_row_bytes, "survey_indexed_bytes_per_row": pcg_bytes_per_row(nnz_row),
+                             "rows": int(rows_total)},
+            "configs": extra, "cpu_baseline": cpu, "e2e": e2e, "e2e_solve": e2e_solve,
+            "gpu_launches": int(args.steps * launches_per_step(args.precond, n, slab_nz, iters, world)),
             "clocks": sampler.summary(), "setup_s": t_setup, "wall_s_timed": wall,
         }
         print(json.dumps(line))
