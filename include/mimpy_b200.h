@@ -274,11 +274,16 @@ int mimpy_b200_hybrid_setup(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
 /* Same as mimpy_b200_mfd_local_matrices + mimpy_b200_hybrid_setup in one pass for hexahedral cells
  * (uniform_faces == 6, methods 0/1/6): M_E is built and inverted per cell without ever being stored
  * (mfd.py:357-483 feeding the elimination above).  Returns MIMPY_E_UNSUPPORTED otherwise -- callers
- * then use the two-step path.  flags: MIMPY_FLAG_K_UNITY. */
+ * then use the two-step path.  flags: MIMPY_FLAG_K_UNITY.
+ * face_rowbase_work (nf ints, nullable): scratch that enables the pipelined brick kernel on structured hex
+ * meshes with even nx (bulk-copy staging, closed-form row positions; csrc/assemble_brick3.cu).  That kernel
+ * also writes tau_out[nc*6] (nullable) = a_f^2 W_E[f,f], the half transmissibilities mimpy_b200_auxmg_setup
+ * needs, and sets *tau_written_host (nullable) to 1 when it did. */
 int mimpy_b200_hybrid_setup_fused(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
                                   int32_t method, int32_t flags, const double* multipliers, double alpha,
                                   const double* c_diag, double* w_e, double* a_vals, double* a_diag_inv,
-                                  const int32_t* sell_ptr);
+                                  const int32_t* sell_ptr, int32_t* face_rowbase_work, double* tau_out,
+                                  int32_t* tau_written_host);
 int mimpy_b200_hybrid_rhs(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
                           const double* w_e, double alpha, const double* c_diag,
                           const double* rhs /*flux_dof+nc*/, double* cell_tmp /*cell_ptr[nc]*/,
@@ -354,7 +359,8 @@ int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
                             void** handle);
 int mimpy_b200_auxmg_setup(mimpy_ctx* ctx, void* handle, const mimpy_mesh_view* mesh,
                            const mimpy_symbolic* sym, const double* w_e, double alpha,
-                           const double* c_diag);
+                           const double* c_diag, const double* tau /* nc*6 from hybrid_setup_fused, or NULL:
+                           read from the diagonals of w_e */);
 int mimpy_b200_auxmg_destroy(mimpy_ctx* ctx, void* handle);
 /* PCG with that preconditioner.  (ptr, idx, vals): the face system in CSR (sell = 0) or SELL-32
  * (sell = 1) layout; work: 4 n doubles.  Same info / error behaviour as mimpy_b200_pcg. */

@@ -71,13 +71,13 @@ SIGNATURES = {
     "mimpy_b200_singlephase_terms": [_vp, _i32, _i32, _f64, _f64, _f64, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp],
     "mimpy_b200_transport_step": [_vp, _PM, _PS, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _f64, _f64, _vp],
     "mimpy_b200_hybrid_setup": [_vp, _PM, _PS, _vp, _vp, _f64, _vp, _vp, _vp, _vp, _vp],
-    "mimpy_b200_hybrid_setup_fused": [_vp, _PM, _PS, _i32, _i32, _vp, _f64, _vp, _vp, _vp, _vp, _vp],
+    "mimpy_b200_hybrid_setup_fused": [_vp, _PM, _PS, _i32, _i32, _vp, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i32)],
     "mimpy_b200_sell_sizes": [_vp, _i32, _vp, _vp, C.POINTER(_i64)],
     "mimpy_b200_sell_fill": [_vp, _i32, _vp, _vp, _vp, _vp],
     "mimpy_b200_pcg_sell": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(PcgInfo)],
     "mimpy_b200_spmv_sell": [_vp, _i32, _vp, _vp, _vp, _vp, _vp],
     "mimpy_b200_auxmg_create": [_vp, _PM, _PS, C.POINTER(_vp)],
-    "mimpy_b200_auxmg_setup": [_vp, _vp, _PM, _PS, _vp, _f64, _vp],
+    "mimpy_b200_auxmg_setup": [_vp, _vp, _PM, _PS, _vp, _f64, _vp, _vp],
     "mimpy_b200_auxmg_destroy": [_vp, _vp],
     "mimpy_b200_pcg_aux": [_vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, C.POINTER(PcgInfo)],
     "mimpy_b200_hybrid_rhs": [_vp, _PM, _PS, _vp, _f64, _vp, _vp, _vp, _vp],

@@ -247,6 +247,51 @@ __device__ __forceinline__ void b3_issue(const mimpy_mesh_view& m, const B3Geo& 
 #define B3_MINB 2
 #endif
 
+// ---- producer warpgroup: gives its registers to the compute warpgroup; one warp runs one brick ahead of
+// the compute warps.  Bricks are handed out by an atomic ticket in super-tile order, so the bricks in
+// flight on the whole GPU stay a compact window however the CTAs drift apart: the two halves of a surface
+// row (and the shared face records) meet in L2.
+__device__ __forceinline__ void b3_producer(const mimpy_mesh_view& m, const B3Geo& g, bool k_unity, unsigned int* ticket,
+                                            unsigned int* error_flag, int4* s_ids, unsigned in_base, unsigned bar_full,
+                                            unsigned bar_empty, int warp, int lane) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B3_REGS_PRODUCER));
+  if (warp != BR_THREADS / 32) return;
+  int bi = 0, bj = 0, bk = 0;
+  auto next_brick = [&]() {  // next valid brick of the global order, or g.total
+    int b;
+    do {
+      unsigned tk = 0;
+      if (lane == 0) tk = atomicAdd(ticket, 1u) - g.ticket_base;
+      tk = __shfl_sync(0xffffffffu, tk, 0);
+      b = tk < (unsigned)g.total ? (int)tk : g.total;
+    } while (b < g.total && !b3_decode(g, b, bi, bj, bk));
+    return b;
+  };
+  int b = next_brick();
+  unsigned it = 0;
+  while (true) {
+    const int cbi = bi, cbj = bj, cbk = bk;
+    const int bn = b < g.total ? next_brick() : g.total;  // (overwrites bi, bj, bk)
+    // the compute warps get the brick coordinates ready-made: the decode (integer divisions) stays here
+    const int4 ids = make_int4(b, cbi | (cbj << 10) | (cbk << 20), bn, bi | (bj << 10) | (bk << 20));
+    if (it > 0) {
+      // the operands of the previous brick are in registers
+      if (!mbar_wait<true>(bar_empty, (it - 1) & 1u, error_flag)) return;
+      fence_proxy_async();
+    }
+    if (lane == 0) s_ids[it & 1u] = ids;
+    __syncwarp();
+    if (b >= g.total) {  // tell the compute warps that the work is done
+      if (lane == 0) mbar_arrive_expect_tx(bar_full, 0);
+      return;
+    }
+    b3_issue(m, g, k_unity, cbi, cbj, cbk, in_base, bar_full, lane);
+    ++it;
+    b = bn;
+  }
+}
+
+
 template <int METHOD>
 __global__ void __launch_bounds__(B3_THREADS, B3_MINB)
 k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
@@ -272,45 +317,8 @@ k_numeric_brick3(mimpy_mesh_view m, int flags, UniArgs a, B3Geo g) {
   __syncthreads();
 
   if (warp >= BR_THREADS / 32) {
-    // ---- producer warpgroup: gives its registers to the compute warpgroup; one warp runs one brick
-    // ahead of the compute warps.  Bricks are handed out by an atomic ticket in super-tile order, so the
-    // bricks in flight on the whole GPU stay a compact window however the CTAs drift apart: the two
-    // halves of a surface row (and the shared face records) meet in L2. ----
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B3_REGS_PRODUCER));
-    if (warp != BR_THREADS / 32) return;
-    int bi = 0, bj = 0, bk = 0;
-    auto next_brick = [&]() {  // next valid brick of the global order, or g.total
-      int b;
-      do {
-        unsigned tk = 0;
-        if (lane == 0) tk = atomicAdd(a.ticket, 1u) - g.ticket_base;
-        tk = __shfl_sync(0xffffffffu, tk, 0);
-        b = tk < (unsigned)g.total ? (int)tk : g.total;
-      } while (b < g.total && !b3_decode(g, b, bi, bj, bk));
-      return b;
-    };
-    int b = next_brick();
-    unsigned it = 0;
-    while (true) {
-      const int cbi = bi, cbj = bj, cbk = bk;
-      const int bn = b < g.total ? next_brick() : g.total;  // (overwrites bi, bj, bk)
-      // the compute warps get the brick coordinates ready-made: the decode (integer divisions) stays here
-      const int4 ids = make_int4(b, cbi | (cbj << 10) | (cbk << 20), bn, bi | (bj << 10) | (bk << 20));
-      if (it > 0) {
-        // the operands of the previous brick are in registers
-        if (!mbar_wait<true>(bar_empty, (it - 1) & 1u, a.error_flag)) return;
-        fence_proxy_async();
-      }
-      if (lane == 0) s_ids[it & 1u] = ids;
-      __syncwarp();
-      if (b >= g.total) {  // tell the compute warps that the work is done
-        if (lane == 0) mbar_arrive_expect_tx(bar_full, 0);
-        return;
-      }
-      b3_issue(m, g, k_unity, cbi, cbj, cbk, in_base, bar_full, lane);
-      ++it;
-      b = bn;
-    }
+    b3_producer(m, g, k_unity, a.ticket, a.error_flag, s_ids, in_base, bar_full, bar_empty, warp, lane);
+    return;
   }
 
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(B3_REGS_COMPUTE));
@@ -631,6 +639,318 @@ static int bind_plan(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_sy
   return MIMPY_OK;
 }
 
+static int b3_ctas_per_sm();
+
+// ---------------------------------------------------------------------------------------------
+// Set-up of the hybridised face system on the same pipeline (replaces k_hybrid_setup_hex of hybrid.cu on
+// structured hex meshes): inputs by bulk copy, M_E in registers, its inverse W_E in a private column of a
+// shared-memory tile (same elimination order as hybrid.cu), then
+//   * W_E leaves as contiguous 2304-byte pieces per x-run (36 doubles per cell),
+//   * tau_{E,f} = a_f^2 W_E[f,f] (the half transmissibilities the multigrid preconditioner is built from)
+//     leave with it, so auxmg.cu does not read W_E again,
+//   * the face-system entries a W a - r c^T / S go straight to their SELL-32 slots: the position inside the
+//     row is the same closed form as in the assembly kernel, the row's base comes from a per-face array.
+// ---------------------------------------------------------------------------------------------
+#define HS_LD (BR_THREADS + 1)
+struct SetupArgs {
+  const int* sell_rowbase;  // per face: sell_ptr[g >> 5] + (g & 31), -1 on faces that are no flux DOF
+  int row_stride;           // 32 (SELL) or 1 (CSR: sell_rowbase then holds m_indptr[g])
+  const uint8_t* face_flag; // nullable: slab partition, bit0 top / bit1 bottom interface layer
+  int nf;
+  double* w_e;
+  double* tau;              // nullable: nc * 6
+  double* a_vals;
+};
+static_assert(36 * HS_LD * 8 + B3_OFF_OUT <= B3_OFF_IN, "the inversion tile fits in the image region");
+
+template <int METHOD>
+__global__ void __launch_bounds__(B3_THREADS, B3_MINB)
+k_hybrid_setup_brick(mimpy_mesh_view m, int flags, UniArgs a, SetupArgs sa_, B3Geo g) {
+  constexpr int NF = 6;
+  extern __shared__ __align__(128) unsigned char sm[];
+  double* tile = reinterpret_cast<double*>(sm + B3_OFF_OUT);  // entry e of the cell of thread t at tile[e * HS_LD + t]
+  const unsigned char* in = sm + B3_OFF_IN;
+  long long* s_cell0 = reinterpret_cast<long long*>(sm + B3_OFF_SMALL);  // first cell of each x-run (-1: no run)
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm);
+  const unsigned bar_full = sbase + B3_OFF_BAR, bar_empty = bar_full + 8, in_base = sbase + B3_OFF_IN;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int nx = g.nx, ny = g.ny, nz = g.nz, L = g.L, xrow = g.xrow;
+  const bool k_unity = flags & 1;
+  int4* s_ids = reinterpret_cast<int4*>(sm + B3_OFF_IDS);
+  if (t == 0) {
+    mbar_init(bar_full, 1);
+    mbar_init(bar_empty, BR_THREADS / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp >= BR_THREADS / 32) {
+    b3_producer(m, g, k_unity, a.ticket, a.error_flag, s_ids, in_base, bar_full, bar_empty, warp, lane);
+    return;
+  }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(B3_REGS_COMPUTE));
+  const int li = t % BX, lj = (t / BX) % BY, lk = t / (BX * BY);
+  const int run = t >> 3;
+  // interface layers of a slab partition are interior faces of the global problem, not boundary faces
+  const bool has_lo = sa_.face_flag && (__ldg(sa_.face_flag) & 2);
+  const bool has_hi = sa_.face_flag && (__ldg(sa_.face_flag + sa_.nf - 1) & 1);
+  double* A = tile + t;
+  unsigned phase = 0;
+  bool first_brick = true;
+  double mult = 1., cdiag = 0.;
+  int rowb[NF];
+  auto prefetch = [&](int pbi, int pbj, int pbk, double& pmult, double& pcdiag, int (&prow)[NF]) {
+    const int ci = pbi * BX + li, cj = pbj * BY + lj, ck = pbk * BZ + lk;
+    pmult = 1.;
+    pcdiag = 0.;
+#pragma unroll
+    for (int i = 0; i < NF; ++i) prow[i] = -1;
+    if (ci < nx && cj < ny && ck < nz) {
+      const size_t cell = (size_t)ci + (size_t)nx * ((size_t)cj + (size_t)ny * ck);
+      if (a.multipliers) pmult = __ldg(a.multipliers + cell);
+      if (a.c_diag) pcdiag = __ldg(a.c_diag + cell);
+      const int cb = ck * L + cj * xrow + 3 * ci;
+      prow[0] = __ldg(sa_.sell_rowbase + cb);
+      prow[1] = __ldg(sa_.sell_rowbase + cb + 1);
+      prow[2] = __ldg(sa_.sell_rowbase + cb + 2);
+      prow[3] = __ldg(sa_.sell_rowbase + (ci + 1 < nx ? cb + 5 : ck * L + cj * xrow + 3 * nx));
+      prow[4] = __ldg(sa_.sell_rowbase + (cj + 1 < ny ? cb + xrow + 1 : ck * L + ny * xrow + ci));
+      prow[5] = __ldg(sa_.sell_rowbase + (ck + 1 < nz ? cb + L : nz * L + cj * nx + ci));
+    }
+  };
+
+  while (true) {
+    if (!mbar_wait<false>(bar_full, phase, a.error_flag)) return;
+    const int4 ids = s_ids[phase];
+    phase ^= 1u;
+    if (ids.x >= g.total) return;
+    const int bi = ids.y & 1023, bj = (ids.y >> 10) & 1023, bk = ids.y >> 20;
+    const int bn = ids.z, nbi = ids.w & 1023, nbj = (ids.w >> 10) & 1023, nbk = ids.w >> 20;
+    if (first_brick) {
+      prefetch(bi, bj, bk, mult, cdiag, rowb);
+      first_brick = false;
+    }
+    const int ci0 = bi * BX, cj0 = bj * BY, ck0 = bk * BZ;
+    const int ci = ci0 + li, cj = cj0 + lj, ck = ck0 + lk;
+    const bool ok = ci < nx && cj < ny && ck < nz;
+    const long long cell = (long long)ci + (long long)nx * ((long long)cj + (long long)ny * ck);
+    const int cbase = ck * L + cj * xrow + 3 * ci;
+    const int fid[NF] = {cbase, cbase + 1, cbase + 2,
+                         ci + 1 < nx ? cbase + 5 : ck * L + cj * xrow + 3 * nx,
+                         cj + 1 < ny ? cbase + xrow + 1 : ck * L + ny * xrow + ci,
+                         ck + 1 < nz ? cbase + L : nz * L + cj * nx + ci};
+    if (li == 0) s_cell0[run] = (cj < ny && ck < nz) ? cell : -1;
+
+    // ---- pull ----
+    CellOps<NF> o;
+    unsigned mp[NF], me = 0, other_mask = 0;
+    double area[NF], vol = 0., trk = 1.;
+    if (ok) {
+      double K[9], xc[3], sgn[NF];
+      double2 rec[NF][4];
+      int off[NF];
+      off[0] = B3_IN_REC + run * B3_REC_RUN + (3 * li) * 64;
+      off[1] = off[0] + 64;
+      off[2] = off[0] + 128;
+      off[3] = off[0] + (ci + 1 < nx ? 5 : 3) * 64;
+      off[4] = (lj < BY - 1 && cj + 1 < ny) ? B3_IN_REC + (run + 1) * B3_REC_RUN + (3 * li + 1) * 64
+                                            : B3_IN_YP + lk * B3_SURF_RUN + (cj + 1 < ny ? 3 * li : li) * 64;
+      off[5] = (lk < BZ - 1 && ck + 1 < nz) ? B3_IN_REC + (run + BY) * B3_REC_RUN + (3 * li) * 64
+                                            : B3_IN_ZP + lj * B3_SURF_RUN + (ck + 1 < nz ? 3 * li : li) * 64;
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        const int key = (fid[i] >> 1) & 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rec[i][q] = *reinterpret_cast<const double2*>(in + off[i] + ((q ^ key) << 4));
+      }
+      if (k_unity) {
+#pragma unroll
+        for (int q = 0; q < 9; ++q) K[q] = (q % 4 == 0) ? 1. : 0.;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 9; ++q) K[q] = *reinterpret_cast<const double*>(in + B3_IN_K + t * 72 + q * 8);
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) xc[q] = *reinterpret_cast<const double*>(in + B3_IN_XC + t * 24 + q * 8);
+      vol = *reinterpret_cast<const double*>(in + B3_IN_VOL + t * 8);
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        const unsigned hi = (unsigned)((unsigned long long)__double_as_longlong(rec[i][3].y) >> 32);
+        const unsigned p1 = hi & 63u, p2 = (hi >> 8) & 63u;
+        mp[i] = merged_present(i, p1, p2);
+        if (i == 0) me = p2;
+        if ((i < 3 ? p1 : p2) != 0u) other_mask |= 1u << i;
+        sgn[i] = i < 3 ? -1. : 1.;
+        area[i] = rec[i][0].x;
+      }
+      trk = K[0] + K[4] + K[8];
+      cell_prep<NF, METHOD>(K, xc, rec, sgn, o);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty);  // the input stage goes back to the producer
+
+    double mult_n = 1., cdiag_n = 0.;
+    int rowb_n[NF];
+    if (bn < g.total) prefetch(nbi, nbj, nbk, mult_n, cdiag_n, rowb_n);
+
+    if (ok) {
+      // faces that are no flux DOF (Neumann), and boundary faces (one cell, prescribed multiplier)
+      const unsigned dropbits = ~me & 63u;
+      unsigned bndbits = ~other_mask & 63u;
+      if (has_lo && ck == 0) bndbits &= ~1u;
+      if (has_hi && ck == nz - 1) bndbits &= ~32u;
+      // mult * M_E acting on the outward fluxes u = sigma o v (cell_core folds sigma_i sigma_j in: folded back)
+      cell_core<NF, METHOD>(o, trk, vol, mult, [&](int i, int j, double v) {
+        const bool drop = ((dropbits >> i) | (dropbits >> j)) & 1u;
+        const double s = ((i < 3) == (j < 3)) ? 1. : -1.;
+        A[(i * NF + j) * HS_LD] = drop ? (i == j ? 1. : 0.) : s * v;
+      });
+      // Gauss-Jordan without pivoting in REGISTERS (the operands of cell_core are dead by now; the tile only
+      // carried the 36 entries across), same elimination order as group_invert (common.cuh); fully unrolled
+      double R[NF * NF];
+#pragma unroll
+      for (int e = 0; e < NF * NF; ++e) R[e] = A[e * HS_LD];
+#pragma unroll
+      for (int k = 0; k < NF; ++k) {
+        const double pinv = 1.0 / R[k * NF + k];
+#pragma unroll
+        for (int j = 0; j < NF; ++j) {
+          if (j == k) continue;
+          const double akj = R[k * NF + j] * pinv;
+#pragma unroll
+          for (int i = 0; i < NF; ++i) {
+            if (i == k) continue;
+            R[i * NF + j] -= R[i * NF + k] * akj;
+          }
+          R[k * NF + j] = akj;
+        }
+#pragma unroll
+        for (int i = 0; i < NF; ++i) {
+          if (i == k) continue;
+          R[i * NF + k] = -R[i * NF + k] * pinv;
+        }
+        R[k * NF + k] = pinv;
+      }
+      double rsum[NF], csum[NF];
+#pragma unroll
+      for (int i = 0; i < NF; ++i) rsum[i] = csum[i] = 0.;
+#pragma unroll
+      for (int i = 0; i < NF; ++i)
+#pragma unroll
+        for (int j = 0; j < NF; ++j) {
+          const bool drop = ((dropbits >> i) | (dropbits >> j)) & 1u;
+          const double w = drop ? 0. : R[i * NF + j];
+          R[i * NF + j] = w;
+          A[(i * NF + j) * HS_LD] = w;   // W leaves through the tile (coalesced copy-out below)
+          const double awa = area[i] * w * area[j];
+          rsum[i] += awa;
+          csum[j] += awa;
+        }
+      const double cd = a.c_diag ? cdiag : a.alpha * vol;
+      double S = cd;
+#pragma unroll
+      for (int j = 0; j < NF; ++j) S += csum[j];
+      const double inv_s = 1.0 / S;
+      if (sa_.tau) {
+#pragma unroll
+        for (int i = 0; i < NF; ++i)
+          sa_.tau[cell * NF + i] = ((me >> i) & 1u) ? area[i] * area[i] * R[i * NF + i] : 0.;
+      }
+      const int stride = sa_.row_stride;
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        if (rowb[i] < 0) continue;
+#pragma unroll
+        for (int j = 0; j < NF; ++j) {
+          if (!((me >> j) & 1u)) continue;
+          const bool bnd = ((bndbits >> i) | (bndbits >> j)) & 1u;
+          double v = area[i] * R[i * NF + j] * area[j] - rsum[i] * csum[j] * inv_s;
+          if (bnd) v = (i == j) ? 1. : 0.;
+          const int pos = __popc(mp[i] & ((1u << merged_index(i, j)) - 1u));
+          if (i == j) atomicAdd(sa_.a_vals + rowb[i] + pos * stride, v);
+          else sa_.a_vals[rowb[i] + pos * stride] = v;
+        }
+      }
+    }
+    sync_compute();
+    // copy-out of W: an x-run of cells is one contiguous piece of w_e (36 doubles per cell)
+    {
+      const int runlen = min(BX, nx - ci0);
+      for (int q = t; q < B2_RUNS * BX * NF * NF; q += BR_THREADS) {
+        const int r = q / (BX * NF * NF), e = q - r * (BX * NF * NF);
+        const long long c0 = s_cell0[r];
+        if (c0 < 0 || e >= runlen * NF * NF) continue;
+        const int c8 = e / (NF * NF), entry = e - c8 * (NF * NF);
+        sa_.w_e[c0 * (NF * NF) + e] = tile[entry * HS_LD + r * BX + c8];
+      }
+    }
+    if (bn >= g.total) break;
+    sync_compute();  // the tile is free for the next brick
+    mult = mult_n;
+    cdiag = cdiag_n;
+#pragma unroll
+    for (int i = 0; i < NF; ++i) rowb[i] = rowb_n[i];
+  }
+}
+
+// per-face base of the face-system row: SELL-32 slot of entry 0, or the CSR offset
+__global__ void __launch_bounds__(256)
+k_face_rowbase(int nf, const int* __restrict__ f2f, const int* __restrict__ sell_ptr, const int* __restrict__ m_indptr,
+               int* __restrict__ out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  const int g = f2f[f];
+  out[f] = g < 0 ? -1 : (sell_ptr ? sell_ptr[g >> 5] + (g & 31) : m_indptr[g]);
+}
+
+int mimpy_face_rowbase(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym, const int* sell_ptr, int* out) {
+  k_face_rowbase<<<(mesh->nf + 255) / 256, 256, 0, ctx->stream>>>(mesh->nf, sym->face_to_flux, sell_ptr, sym->m_indptr, out);
+  KERNEL_CHECK();
+  return MIMPY_OK;
+}
+
+template <int METHOD>
+static int launch_setup_brick(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int flags, const UniArgs& a, const SetupArgs& sa,
+                              const B3Geo& g, long long grid) {
+  CUDA_TRY(cudaFuncSetAttribute(k_hybrid_setup_brick<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B3_SMEM));
+  k_hybrid_setup_brick<METHOD><<<(unsigned)grid, B3_THREADS, B3_SMEM, ctx->stream>>>(*mesh, flags, a, sa, g);
+  KERNEL_CHECK();
+  return MIMPY_OK;
+}
+
+static int b3_geometry(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int bk_begin, int bk_end, B3Geo& g, long long& grid);
+
+// Face-system set-up on the pipelined brick kernel; MIMPY_E_UNSUPPORTED when it does not apply.
+int mimpy_hybrid_setup_brick(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym, int method, int flags,
+                             const double* multipliers, double alpha, const double* c_diag, const int* face_rowbase,
+                             int row_stride, double* w_e, double* tau, double* a_vals) {
+  if (!mimpy_brick3_applies(mesh, sym, method, flags) || !face_rowbase) return MIMPY_E_UNSUPPORTED;
+  int rc = bind_plan(ctx, mesh, sym);
+  if (rc) return rc;
+  B3Geo g;
+  long long grid = 0;
+  rc = b3_geometry(ctx, mesh, 0, 0x3fffffff, g, grid);
+  if (rc) return rc;
+  if (grid == 0) return MIMPY_OK;
+  UniArgs a = {};
+  a.multipliers = multipliers;
+  a.c_diag = c_diag;
+  a.alpha = alpha;
+  a.ticket = ctx->counters + 12;
+  a.error_flag = ctx->counters + 9;
+  a.flux_dof = sym->flux_dof;
+  SetupArgs sa;
+  sa.sell_rowbase = face_rowbase;
+  sa.row_stride = row_stride;
+  sa.face_flag = sym->face_flag;
+  sa.nf = mesh->nf;
+  sa.w_e = w_e;
+  sa.tau = tau;
+  sa.a_vals = a_vals;
+  if (method == 0) return launch_setup_brick<0>(ctx, mesh, flags, a, sa, g, grid);
+  if (method == 1) return launch_setup_brick<1>(ctx, mesh, flags, a, sa, g, grid);
+  return launch_setup_brick<6>(ctx, mesh, flags, a, sa, g, grid);
+}
+
 static int b3_ctas_per_sm() {
   static int per_sm = 0;
   if (per_sm == 0) {
@@ -651,11 +971,7 @@ static int launch_brick3(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int flags,
   return MIMPY_OK;
 }
 
-int mimpy_numeric_brick3(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym, int method,
-                         int flags, const UniArgs& a, int bk_begin, int bk_end) {
-  int rc = bind_plan(ctx, mesh, sym);
-  if (rc) return rc;
-  B3Geo g;
+static int b3_geometry(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int bk_begin, int bk_end, B3Geo& g, long long& grid) {
   g.nx = mesh->hex_nx;
   g.ny = mesh->hex_ny;
   g.nz = mesh->hex_nz;
@@ -669,14 +985,28 @@ int mimpy_numeric_brick3(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimp
   g.bk_begin = bk_begin;
   g.bk_end = bk_end < nbz ? bk_end : nbz;
   const long long super_tiles = (long long)g.nsx * g.nsy * ((g.bk_end - g.bk_begin + 3) / 4);
+  grid = 0;
+  g.total = 0;
   if (super_tiles <= 0) return MIMPY_OK;
-  if (super_tiles * 64 > 0x7fffffffLL || g.nbx > 1023 || g.nby > 1023 || nbz > 2047) return MIMPY_E_UNSUPPORTED;
+  if (super_tiles * 64 > 0x7fffffffLL) return MIMPY_E_UNSUPPORTED;
   g.total = (int)(super_tiles * 64);
   // every CTA's producer draws tickets until it gets one past the end: total + grid draws per launch
-  long long grid = (long long)ctx->sm_count * b3_ctas_per_sm();
+  grid = (long long)ctx->sm_count * b3_ctas_per_sm();
   if (grid > g.total) grid = g.total;
   g.ticket_base = ctx->b3_ticket;
   ctx->b3_ticket += (unsigned)g.total + (unsigned)grid;
+  return MIMPY_OK;
+}
+
+int mimpy_numeric_brick3(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym, int method,
+                         int flags, const UniArgs& a, int bk_begin, int bk_end) {
+  int rc = bind_plan(ctx, mesh, sym);
+  if (rc) return rc;
+  B3Geo g;
+  long long grid = 0;
+  rc = b3_geometry(ctx, mesh, bk_begin, bk_end, g, grid);
+  if (rc) return rc;
+  if (grid == 0) return MIMPY_OK;
   if (method == 0) return launch_brick3<0>(ctx, mesh, flags, a, g);
   if (method == 1) return launch_brick3<1>(ctx, mesh, flags, a, g);
   return launch_brick3<6>(ctx, mesh, flags, a, g);

@@ -99,6 +99,20 @@ k_aux_tau(int nc, const int* __restrict__ cell_faces, const int* __restrict__ f2
   }
 }
 
+// the same with the half transmissibilities already at hand (written by the set-up kernel)
+__global__ void __launch_bounds__(AUX_T)
+k_aux_tau_given(int nc, const int* __restrict__ cell_faces, const int* __restrict__ f2f,
+                const double* __restrict__ tau_in, double* __restrict__ wc, double* __restrict__ tsum) {
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= (long long)nc * 6) return;
+  const double tau = tau_in[e];
+  wc[e] = tau;
+  if (tau != 0.) {
+    const int g = f2f[cell_faces[e]];
+    if (g >= 0) atomicAdd(tsum + g, tau);
+  }
+}
+
 __global__ void __launch_bounds__(AUX_T)
 k_aux_level0(int nc, const int* __restrict__ cell_faces, const int* __restrict__ f2f,
              const int* __restrict__ face_cell, const uint8_t* __restrict__ face_flag,
@@ -638,7 +652,7 @@ int mimpy_b200_auxmg_destroy(mimpy_ctx* ctx, void* handle) {
 
 int mimpy_b200_auxmg_setup(mimpy_ctx* ctx, void* handle, const mimpy_mesh_view* mesh,
                            const mimpy_symbolic* sym, const double* w_e, double alpha,
-                           const double* c_diag) {
+                           const double* c_diag, const double* tau) {
   REQUIRE(ctx && handle && mesh && sym && w_e, "NULL argument");
   mimpy_auxmg* h = static_cast<mimpy_auxmg*>(handle);
   REQUIRE(h->nc == mesh->nc && h->nf == mesh->nf && h->flux_dof == sym->flux_dof, "handle/mesh mismatch");
@@ -649,8 +663,12 @@ int mimpy_b200_auxmg_setup(mimpy_ctx* ctx, void* handle, const mimpy_mesh_view* 
   h->face_flag = sym->face_flag;
   CUDA_TRY(cudaMemsetAsync(h->tsum, 0, sizeof(double) * (size_t)(h->flux_dof ? h->flux_dof : 1), st));
   CUDA_TRY(cudaMemsetAsync(h->fw, 0, sizeof(double) * (size_t)h->nf, st));
-  k_aux_tau<<<aux_blocks(h->nc), AUX_T, 0, st>>>(h->nc, mesh->cell_faces, sym->face_to_flux, sym->m_ptr,
-                                                mesh->face_geom, w_e, h->wc, h->tsum);
+  if (tau)
+    k_aux_tau_given<<<(unsigned)(((long long)h->nc * 6 + AUX_T - 1) / AUX_T), AUX_T, 0, st>>>(h->nc, mesh->cell_faces, sym->face_to_flux,
+                                                                                            tau, h->wc, h->tsum);
+  else
+    k_aux_tau<<<aux_blocks(h->nc), AUX_T, 0, st>>>(h->nc, mesh->cell_faces, sym->face_to_flux, sym->m_ptr,
+                                                  mesh->face_geom, w_e, h->wc, h->tsum);
   KERNEL_CHECK();
   int rc = mimpy_halo_exchange_add(ctx, h->tsum);  // interface faces: tau of the cell on the other rank
   if (rc) return rc;

@@ -61,6 +61,11 @@ void mimpy_set_error(const char* fmt, ...);
 int mimpy_numeric_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
                           int method, int flags, const double* multipliers, double alpha,
                           const double* c_diag, double* vals, int layer_begin = 0, int layer_end = -1);
+// assemble_brick3.cu: face-system set-up on the pipelined brick kernel (structured hex meshes)
+int mimpy_face_rowbase(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym, const int* sell_ptr, int* out);
+int mimpy_hybrid_setup_brick(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym, int method, int flags,
+                             const double* multipliers, double alpha, const double* c_diag, const int* face_rowbase,
+                             int row_stride, double* w_e, double* tau, double* a_vals);
 int mimpy_scratch(mimpy_ctx* ctx, size_t bytes, void** out);
 int mimpy_check_device_flag(mimpy_ctx* ctx);  // stream sync + error if a bounded device wait ran out
 // auxmg.cu: z = B r (auxiliary-space multigrid + Jacobi), this rank's share of r.z -> *rz_dst

@@ -11,6 +11,8 @@
 // whose pattern is the pattern of M (m_indptr / m_indices).  Boundary flux DOFs (one cell) have
 // lambda prescribed: lambda_f = -sigma b_v / a_f (= the Dirichlet pressure), identity rows in A.
 // The recovered [v ; p] is the solution of the original system (up to the CG tolerance).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "cell_core.cuh"
 
@@ -387,8 +389,10 @@ int mimpy_b200_hybrid_setup(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
 int mimpy_b200_hybrid_setup_fused(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
                                   int32_t method, int32_t flags, const double* multipliers, double alpha,
                                   const double* c_diag, double* w_e, double* a_vals, double* a_diag_inv,
-                                  const int32_t* sell_ptr) {
+                                  const int32_t* sell_ptr, int32_t* face_rowbase_work, double* tau_out,
+                                  int32_t* tau_written_host) {
   REQUIRE(ctx && mesh && sym && w_e && a_vals && a_diag_inv, "NULL argument");
+  if (tau_written_host) *tau_written_host = 0;
   if (mesh->uniform_faces != 6 || (method != 0 && method != 1 && method != 6)) return MIMPY_E_UNSUPPORTED;
   if (mesh->nc <= 0) return MIMPY_OK;
   const int F = sym->flux_dof;
@@ -398,6 +402,28 @@ int mimpy_b200_hybrid_setup_fused(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, c
   if (F > 0) {
     k_zero_diag_m<<<(F + 255) / 256, 256, 0, st>>>(F, h, sym->diag_pos, a_vals);
     KERNEL_CHECK();
+  }
+  // structured hex meshes: the pipelined brick kernel (bulk-copy staging, closed-form positions)
+  bool done = false;
+  if (face_rowbase_work && !getenv("MIMPY_B200_SETUP_OLD")) {
+    int rc = mimpy_face_rowbase(ctx, mesh, sym, sell_ptr, face_rowbase_work);
+    if (rc) return rc;
+    rc = mimpy_hybrid_setup_brick(ctx, mesh, sym, method, flags, multipliers, alpha, c_diag, face_rowbase_work,
+                                  sell_ptr ? 32 : 1, w_e, tau_out, a_vals);
+    if (rc == MIMPY_OK) done = true;
+    else if (rc != MIMPY_E_UNSUPPORTED) return rc;
+  }
+  if (done) {
+    if (F > 0) {
+      k_diag_inv<<<(F + 255) / 256, 256, 0, st>>>(F, h, sym->diag_pos, a_vals, a_diag_inv);
+      KERNEL_CHECK();
+      int rc = mimpy_halo_exchange_add(ctx, a_diag_inv);
+      if (rc) return rc;
+      k_invert<<<(F + 255) / 256, 256, 0, st>>>(F, a_diag_inv);
+      KERNEL_CHECK();
+    }
+    if (tau_written_host) *tau_written_host = tau_out ? 1 : 0;
+    return MIMPY_OK;
   }
   const size_t smem = sizeof(double) * 36 * HX_LD;
   const int blocks = (mesh->nc + HX_THREADS - 1) / HX_THREADS;

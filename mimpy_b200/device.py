@@ -406,6 +406,7 @@ class HybridSystem(object):
         with ctx.on_stream():
             self.w_e = torch.empty(max(plan.n_blocks, 1), dtype=torch.float64, device=dev)
             self.a_diag_inv = torch.empty(max(F, 1), dtype=torch.float64, device=dev)
+            self.tau = None
             self.work = None
             if layout == "sell":
                 if "sell_ptr" not in plan.t:  # pattern-only: built once per symbolic plan
@@ -424,7 +425,10 @@ class HybridSystem(object):
                     plan.sell_npat = int(npat.value)
                     plan.t["sell_pat_id"], plan.t["sell_pat_table"] = (pid, ptab) if plan.sell_npat > 0 else (None, None)
                 self.sell_ptr, self.sell_cols = plan.t["sell_ptr"], plan.t["sell_cols"]
-                self.a_vals = torch.zeros(max(plan.sell_total, 1), dtype=torch.float64, device=dev)  # padding stays 0
+                # padding entries stay 0 for ever, every real entry is rewritten by each set-up: a buffer of a
+                # released system is taken back instead of clearing 4.4 GB again (256^3)
+                pool = plan.t.setdefault("_a_vals_pool", [])
+                self.a_vals = pool.pop() if pool else torch.zeros(max(plan.sell_total, 1), dtype=torch.float64, device=dev)
             else:
                 self.sell_ptr = self.sell_cols = None
                 self.a_vals = torch.zeros(max(plan.nnz_m, 1), dtype=torch.float64, device=dev)
@@ -436,11 +440,24 @@ class HybridSystem(object):
         with ctx.on_stream():
             mv = self.dmesh.view()
             fused = False
+            tau_in = None
             if m_e is None:
+                structured = getattr(self.dmesh, "hex_dims", (0, 0, 0))[0] > 0
+                work = None
+                if structured:   # scratch of the pipelined brick kernel; tau only where the multigrid will want it
+                    if "face_rowbase" not in self.plan.t:
+                        self.plan.t["face_rowbase"] = torch.empty(self.dmesh.nf, dtype=torch.int32, device=ctx.device)
+                    work = self.plan.t["face_rowbase"]
+                    if self.precond == "auxmg" and self.tau is None:
+                        self.tau = torch.empty(self.dmesh.nc * 6, dtype=torch.float64, device=ctx.device)
+                written = C.c_int32(0)
                 rc = ctx.call("mimpy_b200_hybrid_setup_fused", C.byref(mv), C.byref(self.plan.s), int(self.method),
                               1 if self.k_unity else 0, ptr(multipliers), self.alpha, ptr(c_diag), ptr(self.w_e),
-                              ptr(self.a_vals), ptr(self.a_diag_inv), ptr(self.sell_ptr), allow=(_lib.MIMPY_E_UNSUPPORTED,))
+                              ptr(self.a_vals), ptr(self.a_diag_inv), ptr(self.sell_ptr), ptr(work), ptr(self.tau),
+                              C.byref(written), allow=(_lib.MIMPY_E_UNSUPPORTED,))
                 fused = rc == 0
+                if fused and written.value:
+                    tau_in = self.tau
                 if not fused:
                     m_e = local_matrices(self.dmesh, self.plan, self.method, k_unity=self.k_unity)[0]
             if not fused:
@@ -453,9 +470,21 @@ class HybridSystem(object):
                     ctx.call("mimpy_b200_auxmg_create", C.byref(mv), C.byref(self.plan.s), C.byref(h))
                     self.aux = h
                 ctx.call("mimpy_b200_auxmg_setup", self.aux, C.byref(mv), C.byref(self.plan.s), ptr(self.w_e),
-                         self.alpha, ptr(c_diag))
+                         self.alpha, ptr(c_diag), ptr(tau_in))
+
+    def release(self):
+        """Gives the SELL value buffer back to the plan (its padding is still zero) -- called by __del__."""
+        if getattr(self, "layout", None) == "sell" and getattr(self, "a_vals", None) is not None:
+            pool = self.plan.t.setdefault("_a_vals_pool", [])
+            if len(pool) < 2 and self.a_vals.numel() == max(self.plan.sell_total, 1):
+                pool.append(self.a_vals)
+            self.a_vals = None
 
     def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
         try:
             if getattr(self, "aux", None):
                 self.dmesh.ctx.call("mimpy_b200_auxmg_destroy", self.aux)

@@ -663,16 +663,19 @@ def test_auxmg_preconditioner_vs_spsolve_and_jacobi(ctx, dims, alpha):
         assert ia.iterations < ij.iterations
 
 
+@pytest.mark.parametrize("dims", [(11, 7, 5), (12, 6, 9), (18, 5, 4)])
 @pytest.mark.parametrize("method", [0, 1, 6])
 @pytest.mark.parametrize("layout", ["sell", "csr"])
-def test_fused_hex_setup_equals_two_step_setup(ctx, method, layout):
+def test_fused_hex_setup_equals_two_step_setup(ctx, method, layout, dims):
     """mimpy_b200_hybrid_setup_fused (M_E built and inverted inside the kernel) gives the same face
     system, W_E blocks and Jacobi diagonal as local_matrices + hybrid_setup: Neumann faces, per-cell
-    multipliers, an accumulation diagonal and k_unity included; other meshes fall back."""
+    multipliers, an accumulation diagonal and k_unity included; other meshes fall back.  Odd nx: the
+    thread-per-cell kernel of hybrid.cu; even nx: the pipelined brick kernel (assemble_brick3.cu), which also
+    hands the half transmissibilities to the multigrid set-up."""
     import torch
     from mimpy_b200 import device
 
-    nx, ny, nz = 11, 7, 5
+    nx, ny, nz = dims
     nc = nx * ny * nz
     rng = np.random.default_rng(21)
     k = np.zeros((nc, 3, 3))
@@ -695,6 +698,15 @@ def test_fused_hex_setup_equals_two_step_setup(ctx, method, layout):
         for name in ("a_vals", "w_e", "a_diag_inv"):
             a, b = H(ctx, getattr(one, name)), H(ctx, getattr(two, name))
             assert abs(a - b).max() <= 1e-12 * abs(b).max(), (name, k_unity)
+        if layout == "sell":   # with the multigrid: tau from the set-up kernel == tau read from W_E
+            ax = device.HybridSystem(d, plan, None, multipliers=mult, c_diag=cd, precond="auxmg", method=method, k_unity=k_unity)
+            bx = device.HybridSystem(d, plan, m_e, multipliers=mult, c_diag=cd, precond="auxmg")
+            rng2 = np.random.default_rng(1)
+            rhs = torch.as_tensor(rng2.standard_normal(plan.ndof), device=ctx.device)
+            sa, ia = ax.solve(rhs, rtol=1e-11, maxit=500, check_every=5)
+            sb, ib = bx.solve(rhs, rtol=1e-11, maxit=500, check_every=5)
+            assert ia.iterations == ib.iterations
+            assert np.linalg.norm(H(ctx, sa) - H(ctx, sb)) <= 1e-9 * np.linalg.norm(H(ctx, sb))
     # generic meshes: the same call falls back to the two-step path
     o = orc.hex_mesh(3, 3, 2, 1., 1., 1.)
     dg = device.DeviceMesh.from_oracle_mesh(ctx, o)
