@@ -391,9 +391,32 @@ def run_c5(ctx, peak, n=16):
             "pcg_iters": int(f.solver_info["iterations"]), "pcg_ms": float(f.solver_info["ms"]), "saddle_rel_residual": res}
 
 
+def run_generic_path(ctx, peak, n=128):
+    """The kernel every polyhedral mesh goes through (k_local_matrices<G,SCATTER>: lane group per cell, any n_E <= 32,
+    all eight methods), timed on a mesh large enough to say something about it: the C3 workload at n^3 with the
+    fast paths switched off.  Algorithmic bytes: the generic count of DESIGN 3 with n_E = 6."""
+    import torch
+    from mimpy_b200 import device
+
+    nc = n ** 3
+    dm = device.DeviceMesh.hex(ctx, n, n, n, 1., 1., 1., cell_k=lognormal_k(nc, 256))
+    plan = device.symbolic(dm, np.zeros(dm.nf, dtype=np.uint8))
+    with ctx.on_stream():
+        vals = torch.empty(plan.nnz, dtype=torch.float64, device=ctx.device)
+    device.numeric(dm, plan, 1, vals=vals, generic_kernel=True)
+    t_asm, _ = _timed(ctx, lambda: device.numeric(dm, plan, 1, vals=vals, generic_kernel=True))
+    bytes_cell = 24. * 6 + 112. + 60. * dm.nf / nc + 8. * plan.nnz_m / nc
+    return {"workload": "generic warp-group kernel on %d^3 hexes (the path of cut / polyhedral meshes), method 1" % n, "cells": nc,
+            "asm_ms": t_asm, "asm_mcells_per_s": nc / t_asm / 1e3,
+            "asm_roofline": {"bound": "hbm", "achieved": bytes_cell * nc / (t_asm / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": bytes_cell * nc / (t_asm / 1e3) / 1e9 / peak, "algorithmic_bytes_per_cell": bytes_cell,
+                             "kernel": "k_local_matrices<8,SCATTER>"}}
+
+
 def run_extra_configs(ctx, peak, rtol):
     out = {}
-    for name, fn in (("c2", lambda: run_c2(ctx, peak, rtol)), ("c4", lambda: run_c4(ctx, peak)), ("c5", lambda: run_c5(ctx, peak))):
+    for name, fn in (("c2", lambda: run_c2(ctx, peak, rtol)), ("c4", lambda: run_c4(ctx, peak)), ("c5", lambda: run_c5(ctx, peak)),
+                     ("generic_path", lambda: run_generic_path(ctx, peak))):
         try:
             out[name] = fn()
         except Exception as e:  # a failing side config must not take the headline line down
@@ -723,7 +746,7 @@ def main():
     ap.add_argument("--maxit", type=int, default=20000)
     ap.add_argument("--check-every", type=int, default=0, help="PCG convergence check interval (0: 5 with auxmg, 50 with jacobi)")
     ap.add_argument("--precond", default="auxmg", choices=["auxmg", "jacobi"])
-    ap.add_argument("--cpu-n", type=int, default=40)
+    ap.add_argument("--cpu-n", type=int, default=32, help="n^3 sample of the cpu_baseline leg (the same sample as --ref-n)")
     ap.add_argument("--ref-n", type=int, default=32)
     ap.add_argument("--ref-solve-n", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")

@@ -245,6 +245,11 @@ int mimpy_halo_exchange_add(mimpy_ctx* ctx, double* v) {
     KERNEL_CHECK();
     return MIMPY_OK;
   }
+  if (!ctx->nccl_comm || !g_nccl.handle) {
+    mimpy_set_error("halo exchange: world size %d, the interface (%d / %d rows) does not fit the peer buffers (%zu) and no "
+                    "NCCL communicator is attached", ctx->world, h.n_lo, h.n_hi, ctx->peer.halo_cap);
+    return MIMPY_E_NCCL;
+  }
   double* send_lo = h.buf;
   double* recv_lo = h.buf + h.n_lo;
   double* send_hi = h.buf + 2 * (size_t)h.n_lo;

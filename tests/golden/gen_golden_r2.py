@@ -131,8 +131,32 @@ def gravity_rhs(ref):
     return d
 
 
+def cut_checker(ref, n):
+    """BASELINE config 5 shape at n^3 (6^3): every other cell cut by a plane through its centroid,
+    full-tensor K, the C2 boundary conditions (Dirichlet x-/x+, no-flow elsewhere), method 1."""
+    ktab = g1.spd_tensors(n ** 3, 17, full=True)
+    mesh = g1.ref_hex(ref, n, n, n, (1., 1., 1.), ktab)
+    # the reference's variable_array reallocates under live views while cells are divided: pre-size (as gen_golden.py does)
+    nrm = np.array([1.2, .2, 1.3])
+    nrm /= np.linalg.norm(nrm)
+    for va in (mesh.faces, mesh.cells, mesh.cell_normal_orientation):
+        va.set_data_capacity(40 * len(va.data) + 1000)
+        va.set_pointer_capacity(8 * len(va.pointers) + 1000)
+    for c in range(n ** 3):
+        i, j, k = c % n, (c // n) % n, c // (n * n)
+        if (i + j + k) % 2 == 0:
+            mesh.divide_cell_by_plane(c, np.array(mesh.get_cell_real_centroid(c)), nrm)
+    d = orc.omesh_to_dict(orc.OMesh.from_mesh(mesh))
+    bc = [("d", 0, lambda p: 1.), ("d", 1, lambda p: 0.)] + [("n", b, cases.zero_flux) for b in (2, 3, 4, 5)]
+    r = g1.dump_system(ref, mesh, 1, bc, None, with_blocks=False)
+    for k_, v in r.items():
+        d["m1n_%s" % k_] = v
+    return d
+
+
 def main():
     ref = ref_shim.load_reference()
+    g1.save("cut_checker_6", cut_checker(ref, 6))
     for name in cases.CASES:
         g1.save("twophase_" + name, twophase_history(ref, name))
     g1.save("coupling_433", coupling_system(ref))

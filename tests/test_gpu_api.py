@@ -175,6 +175,42 @@ def test_cut_mesh_generator_and_solve_match_reference(golden):
     assert np.linalg.norm(sol - g["m1_solution"]) <= 1e-8 * np.linalg.norm(g["m1_solution"])
 
 
+def test_cut_mesh_6cubed_c2_boundary_conditions(golden):
+    """BASELINE config 5 at the parity size BASELINE.md names (6^3 checkerboard-cut polyhedral mesh) with the C2
+    boundary conditions (Dirichlet x-/x+, no-flow elsewhere): mesh, saddle matrix and solution vs the reference."""
+    import mimpy_b200.mesh.hexmesh as hexmesh
+    import mimpy_b200.mfd.mfd as mfd
+
+    g = golden("cut_checker_6")
+    ref = orc.omesh_from_dict(g)
+    n = 6
+    mesh = hexmesh.HexMesh()
+    mesh.build_mesh(n, n, n, 1., 1., 1., spd_tensors(n ** 3, 17, full=True))
+    nrm = np.array([1.2, .2, 1.3])
+    nrm /= np.linalg.norm(nrm)
+    for c in range(n ** 3):
+        i, j, k = c % n, (c // n) % n, c // (n * n)
+        if (i + j + k) % 2 == 0:
+            mesh.divide_cell_by_plane(c, np.array(mesh.get_cell_real_centroid(c)), nrm)
+    assert_mesh_equals_reference(mesh, ref, geometry_exact=False)
+    f = mfd.MFD()
+    f.set_m_e_construction_method(1)
+    f.set_mesh(mesh)
+    f.apply_dirichlet_from_function(0, lambda p: 1.)
+    f.apply_dirichlet_from_function(1, lambda p: 0.)
+    for b in (2, 3, 4, 5):
+        f.apply_neumann_from_function(b, zero_flux)
+    lhs = f.build_lhs()
+    rhs = f.build_rhs()
+    assert np.array_equal(f.face_to_flux[:, 0], g["m1n_face_to_flux"])
+    nd = f.get_number_of_dof()
+    ref_a = sparse.csr_matrix((g["m1n_csr_data"], g["m1n_csr_indices"], g["m1n_csr_indptr"]), shape=(nd, nd))
+    assert abs(lhs - ref_a).max() <= 1e-12 * abs(ref_a).max()
+    assert np.array_equal(rhs, g["m1n_rhs"])
+    sol = f.solve()
+    assert np.linalg.norm(sol - g["m1n_solution"]) <= 1e-8 * np.linalg.norm(g["m1n_solution"])
+
+
 @pytest.mark.parametrize("variant", ["wells", "inflow"])
 def test_twophase_model_matches_reference_history(golden, variant):
     """BASELINE config 4 shape at 6x3x3: 12 IMPES steps; s_w within 1e-10 per step, p/u within 1e-8."""
