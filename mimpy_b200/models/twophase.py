@@ -255,6 +255,10 @@ class TwoPhase(object):
 
         mfd = self.mfd
         mfd.set_mesh(self.mesh, self.ctx) if mfd.mesh is None else None
+        if self.mesh.has_pointer_couplings():
+            raise NotImplementedError("TwoPhase on a mesh with pointer couplings (twophase.py:950-955, 1039-1051): the IMPES "
+                                      "pressure solve here is the hybridised PCG of the uncoupled saddle system; "
+                                      "MFD.solve handles couplings (mfd.py), the time loop does not yet")
         dm, plan = mfd._ensure_plan()
         self._dm, self._plan = dm, plan
         ctx = self.ctx
