@@ -336,7 +336,9 @@ def run_c4(ctx, peak, n=128, steps=6):
             "pcg_iters_per_step": iters, "sat_step_us": sat_us,
             "sat_roofline": {"bound": "hbm", "achieved": sat_bytes / (sat_us / 1e6) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": sat_bytes / (sat_us / 1e6) / 1e9 / peak, "algorithmic_bytes_per_cell": SAT_BYTES_PER_CELL,
-                             "kernels": "k_frac_flow + k_saturation + k_rate_wells (twophase.cu)"},
+                             "kernels": "k_frac_flow + k_saturation + k_rate_wells (twophase.cu); the fused single-pass form "
+                                        "(MIMPY_B200_SAT_FUSED, 278 B/cell) is division-bound and slower: 313 us",
+                             "survey_fused_bytes_per_cell": 80.0},
             "water_mass_balance_rel_err": abs(float(sw.mean()) - injected) / injected,
             "s_w_max": float(sw.max())}
 

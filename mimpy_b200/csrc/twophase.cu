@@ -1,5 +1,7 @@
 // Two-phase (IMPES) transport kernels: Corey mobilities (twophase.py:268-344), upwind direction
 // (twophase.py:928-958) and the explicit saturation update (twophase.py:960-1092).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 __device__ __forceinline__ double powd(double x, double e) {
@@ -130,6 +132,77 @@ __global__ void k_saturation(int nc, mimpy_fluid fl, double dt, const int* __res
   s_w[c] = a + b;
 }
 
+// Fused form of k_frac_flow + k_saturation: the fractional flow of a face is evaluated from its upwind cell
+// on the fly (no pass over the faces, no f_w read for upwinded faces); the upwind cell records it in f_w,
+// which stays the STATE the reference keeps between steps (a face that is in no upwind pair -- inflow
+// boundary, zero flux -- uses the value it had, twophase.py:968-994).  Reads the saturation of the
+// previous sub-step (s_old), writes s_new.  The last flux DOF (the u_t[-1] quirk) is prepared separately.
+__global__ void __launch_bounds__(256)
+k_saturation_fused(int nc, int F, mimpy_fluid fl, double dt, const int* __restrict__ cell_ptr,
+                   const int* __restrict__ cell_faces, const int8_t* __restrict__ sigma,
+                   const double* __restrict__ face_geom, const int* __restrict__ f2f,
+                   const int* __restrict__ upwind, const double* __restrict__ u_t, const double* __restrict__ p,
+                   const double* __restrict__ p_prev, const double* __restrict__ porosity,
+                   const double* __restrict__ vol, const double* __restrict__ wm, const double* __restrict__ om,
+                   const double* __restrict__ s_old, double* __restrict__ s_new, double* __restrict__ f_w) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int base = cell_ptr[c];
+  const int n = cell_ptr[c + 1] - base;
+  double div = 0.;
+  for (int j = 0; j < n; ++j) {
+    const int f = cell_faces[base + j];
+    const int g = f2f[f];
+    if (g < 0) continue;
+    const int up = upwind[g];
+    double fw;
+    if (up < 0 || g == F - 1) {
+      fw = f_w[g];
+    } else {
+      double mw, mo;
+      if (wm) {
+        mw = wm[up];
+        mo = om[up];
+      } else {
+        mobilities(fl, s_old[up], p[up], mw, mo);
+      }
+      fw = mw / (mw + mo);
+      if (up == c) f_w[g] = fw;
+    }
+    const double e = (double)sigma[base + j] * rec_area(face_geom, (size_t)f);
+    div += e * (fw * u_t[g]);
+  }
+  // twophase.py:1007-1022
+  double a = p_prev[c] * fl.c_w + 1.;
+  a *= fl.rho_w;
+  a *= s_old[c];
+  a /= fl.rho_w;
+  a /= 1. + fl.c_w * p[c];
+  double b = 1. / porosity[c];
+  b /= fl.rho_w;
+  b /= (1. + fl.c_w * p[c]);
+  b /= vol[c];
+  b *= div;
+  b *= -dt;
+  s_new[c] = a + b;
+}
+
+// the last flux DOF: f_w of its upwind cell, before the boundary loop may override it (twophase.py:968-994)
+__global__ void k_frac_flow_last(int F, mimpy_fluid fl, const int* __restrict__ upwind, const double* __restrict__ sw,
+                                 const double* __restrict__ p, const double* __restrict__ wm,
+                                 const double* __restrict__ om, double* __restrict__ f_w) {
+  const int c = upwind[F - 1];
+  if (c < 0) return;
+  double mw, mo;
+  if (wm) {
+    mw = wm[c];
+    mo = om[c];
+  } else {
+    mobilities(fl, sw[c], p[c], mw, mo);
+  }
+  f_w[F - 1] = mw / (mw + mo);
+}
+
 __global__ void k_rate_wells(int nw, mimpy_fluid fl, double dt, const int* __restrict__ cells,
                              const double* __restrict__ rate_w, const double* __restrict__ p,
                              const double* __restrict__ porosity, const double* __restrict__ vol,
@@ -193,16 +266,38 @@ int mimpy_b200_twophase_saturation_step(mimpy_ctx* ctx, const mimpy_mesh_view* m
   cudaStream_t st = ctx->stream;
   const mimpy_fluid fl = *fluid_host;
   REQUIRE((water_mob == nullptr) == (oil_mob == nullptr), "water_mob and oil_mob must be given together");
-  if (F > 0) k_frac_flow<<<(F + 255) / 256, 256, 0, st>>>(F, fl, upwind_cell, s_w, p, water_mob, oil_mob, f_w);
-  if (n_bnd > 0) {
-    REQUIRE(bnd_faces && bnd_sigma && bnd_fw, "boundary inflow arrays are NULL");
-    k_bnd_inflow<<<(n_bnd + 255) / 256, 256, 0, st>>>(n_bnd, bnd_faces, bnd_sigma, bnd_fw,
-                                                      sym->face_to_flux, u_t, f_w);
+  // The fused form (k_saturation_fused: no pass over the faces, f_w not read back) moves 278 instead of
+  // 378 B/cell but evaluates the mobilities and an FP64 division per (cell, upwinded face) instead of per
+  // face: measured 313 us against 227 us at 128^3 -- it is bound by the divisions, not by HBM.  Kept
+  // behind MIMPY_B200_SAT_FUSED; the default stays the per-face pass.
+  static const bool unfused = getenv("MIMPY_B200_SAT_FUSED") == nullptr;
+  if (unfused) {
+    if (F > 0) k_frac_flow<<<(F + 255) / 256, 256, 0, st>>>(F, fl, upwind_cell, s_w, p, water_mob, oil_mob, f_w);
+    if (n_bnd > 0) {
+      REQUIRE(bnd_faces && bnd_sigma && bnd_fw, "boundary inflow arrays are NULL");
+      k_bnd_inflow<<<(n_bnd + 255) / 256, 256, 0, st>>>(n_bnd, bnd_faces, bnd_sigma, bnd_fw,
+                                                        sym->face_to_flux, u_t, f_w);
+    }
+    k_saturation<<<(nc + 255) / 256, 256, 0, st>>>(nc, fl, dt, mesh->cell_ptr, mesh->cell_faces,
+                                                   mesh->cell_sigma, mesh->face_geom,
+                                                   sym->face_to_flux, u_t, f_w, p, p_prev, porosity,
+                                                   mesh->cell_volume, s_w);
+  } else {
+    if (F > 0) k_frac_flow_last<<<1, 1, 0, st>>>(F, fl, upwind_cell, s_w, p, water_mob, oil_mob, f_w);
+    if (n_bnd > 0) {
+      REQUIRE(bnd_faces && bnd_sigma && bnd_fw, "boundary inflow arrays are NULL");
+      k_bnd_inflow<<<(n_bnd + 255) / 256, 256, 0, st>>>(n_bnd, bnd_faces, bnd_sigma, bnd_fw,
+                                                        sym->face_to_flux, u_t, f_w);
+    }
+    void* scratch = nullptr;
+    int rc = mimpy_scratch(ctx, sizeof(double) * (size_t)nc, &scratch);
+    if (rc) return rc;
+    double* s_new = static_cast<double*>(scratch);
+    k_saturation_fused<<<(nc + 255) / 256, 256, 0, st>>>(nc, F, fl, dt, mesh->cell_ptr, mesh->cell_faces, mesh->cell_sigma,
+                                                         mesh->face_geom, sym->face_to_flux, upwind_cell, u_t, p, p_prev,
+                                                         porosity, mesh->cell_volume, water_mob, oil_mob, s_w, s_new, f_w);
+    CUDA_TRY(cudaMemcpyAsync(s_w, s_new, sizeof(double) * (size_t)nc, cudaMemcpyDeviceToDevice, st));
   }
-  k_saturation<<<(nc + 255) / 256, 256, 0, st>>>(nc, fl, dt, mesh->cell_ptr, mesh->cell_faces,
-                                                 mesh->cell_sigma, mesh->face_geom,
-                                                 sym->face_to_flux, u_t, f_w, p, p_prev, porosity,
-                                                 mesh->cell_volume, s_w);
   if (n_rate_wells > 0) {
     REQUIRE(well_cells && well_rate_water, "well arrays are NULL");
     k_rate_wells<<<(n_rate_wells + 255) / 256, 256, 0, st>>>(n_rate_wells, fl, dt, well_cells,

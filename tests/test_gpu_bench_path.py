@@ -1,4 +1,4 @@
-"""The EXACT code path bench.py times (DeviceMesh.hex with even nx -> staged brick assembly,
+"""The EXACT code path bench.py times (DeviceMesh.hex with even nx -> pipelined brick assembly,
 HybridSystem(dm, plan, None, precond="auxmg", method=1) = fused hex set-up, PCG with check_every=5 and
 the bench's stopping test) against SciPy's SuperLU on the assembled saddle matrix and against the
 oracle's assembly (reference algorithm, mfd.py:545-599), at the BASELINE shapes C2 and C3 scaled to
@@ -123,3 +123,33 @@ def test_bench_path_c2_shape_vs_spsolve(ctx):
     err = np.linalg.norm(x - ref) / np.linalg.norm(ref)
     err_p = np.linalg.norm(x[F:] - ref[F:]) / np.linalg.norm(ref[F:])
     assert err <= 1e-8 and err_p <= 1e-8, (err, err_p, info.iterations)
+
+
+def test_host_pipeline_entry_points(ctx):
+    """mimpy_b200/hostpipe.py (what bench.py's e2e figures time): slab-pipelined assembly host -> host equals a
+    plain device assembly bit for bit, twice in a row; solve_to_host equals the device solve."""
+    import torch
+    import bench
+    from mimpy_b200 import device, hostpipe
+
+    n = 32
+    pb = bench.build_problem(ctx, n, 0, 1)
+    dm, plan, rhs = pb["dm"], pb["plan"], pb["rhs"]
+    ref_vals = H(ctx, device.numeric(dm, plan, 1))
+    k_pin = torch.from_numpy(pb["k_host"]).pin_memory().reshape(dm.nc, 9)
+    vals_pin = torch.empty(plan.nnz, dtype=torch.float64).pin_memory()
+    pipe = hostpipe.AssemblyPipeline(dm, plan, 1, n_slabs=4)
+    assert pipe.piped and len(pipe.bounds) - 1 == 4
+    for _ in range(2):
+        vals_pin.fill_(float("nan"))
+        with ctx.on_stream():
+            dm.cell_k.zero_()                      # the pipeline must bring K itself
+        pipe.run(k_pin, vals_pin)
+        assert np.array_equal(vals_pin.numpy(), ref_vals)
+    sol_pin = torch.empty(plan.ndof, dtype=torch.float64).pin_memory()
+    info = hostpipe.solve_to_host(dm, plan, 1, k_pin, rhs, sol_pin, rtol=BENCH_RTOL, saddle_vals=device.numeric(dm, plan, 1),
+                                  maxit=2000, check_every=5)
+    hyb = device.HybridSystem(dm, plan, None, precond="auxmg", method=1)
+    sol, info2 = hyb.solve(rhs, rtol=BENCH_RTOL, maxit=2000, check_every=5, norm="saddle", saddle_vals=device.numeric(dm, plan, 1))
+    assert info.iterations == info2.iterations
+    assert np.array_equal(sol_pin.numpy(), H(ctx, sol))
