@@ -16,7 +16,8 @@
 //   V     one V(1,1) cycle of geometric multigrid on the 7-point operator: 2x2x2 aggregation with
 //         piecewise-constant transfer (the Galerkin coarse operators stay 7-point: coarse couplings
 //         are sums of the fine couplings through the coarse face), damped Jacobi smoothing, coarse
-//         correction scaled by 2 (the usual cure for unsmoothed aggregation), dense inverse on the
+//         correction scaled by 1.5 (over-correction, the usual cure for unsmoothed aggregation; 2 is worse
+//         here), dense inverse on the
 //         coarsest (<= 64 cells) level.  Every operation is linear and symmetric, so B is a fixed SPD
 //         operator and plain CG applies.
 //
@@ -69,6 +70,7 @@ struct mimpy_auxmg {
   AuxLevel glev[AUX_MAX_LEVELS];  // glev[0] = the last distributed level, gathered: nx x ny x (world * nz)
   double* gpack; // [world * 6 * n_last] set-up gather of the last distributed level's stencil
   double omega, scale;
+  double wj;     // weight of the Jacobi term D^-1 against the auxiliary-space term
   const int* cell_faces;
   const int* face_to_flux;
   const int* face_cell;
@@ -411,7 +413,7 @@ k_aux_face_restrict(AuxHex hx, const int* __restrict__ f2f, const double* __rest
 // face is written by exactly one cell: its second cell (the cell whose z-/y-/x- face it is), or its
 // only cell -- three consecutive rows per cell.
 __global__ void __launch_bounds__(RED_THREADS)
-k_aux_face_prolong(AuxHex hx, int n_owned, const int* __restrict__ f2f, const double* __restrict__ fw,
+k_aux_face_prolong(AuxHex hx, int n_owned, double wj, const int* __restrict__ f2f, const double* __restrict__ fw,
                    const double* __restrict__ e, const double* __restrict__ dinv,
                    const double* __restrict__ r, double* __restrict__ z, double* partials,
                    unsigned int* counter, double* dst) {
@@ -426,7 +428,7 @@ k_aux_face_prolong(AuxHex hx, int n_owned, const int* __restrict__ f2f, const do
       const int g = f2f[f];
       if (g < 0) return;
       const double rg = r[g], w1 = fw[f];
-      double zz = (g < n_owned) ? dinv[g] * rg : 0.;
+      double zz = (g < n_owned) ? wj * dinv[g] * rg : 0.;
       if (other >= 0) {
         if (w1 > 0.) zz += w1 * e[other] + (1. - w1) * ec;
       } else {
@@ -505,7 +507,7 @@ int mimpy_auxmg_apply(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, const 
     if (h->global && l > 0 && (rc = ghosts(L[l].x2, L[l]))) return rc;
   }
   const int grid = ctx->sm_count * 8;
-  k_aux_face_prolong<<<grid, RED_THREADS, 0, st>>>(hx, n_owned, h->face_to_flux, h->fw, L[0].x2, dinv, r, z,
+  k_aux_face_prolong<<<grid, RED_THREADS, 0, st>>>(hx, n_owned, h->wj, h->face_to_flux, h->fw, L[0].x2, dinv, r, z,
                                                    ctx->partials, ctx->counters + 4, rz_dst);
   KERNEL_CHECK();
   return MIMPY_OK;
@@ -524,8 +526,15 @@ int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
   h->nc = mesh->nc;
   h->nf = mesh->nf;
   h->flux_dof = sym->flux_dof;
-  h->omega = 0.8;
-  h->scale = 2.0;
+  // damping of the Jacobi smoother and over-correction of the piecewise-constant coarse space, measured
+  // (scripts/exp_iters.py, rtol 1e-8 on the saddle residual): (0.8, 2.0) 110 iterations at 256^3 and 1600 on C2,
+  // (0.9, 1.5) 95 and 1085, (1.0, 1.3) 105 and 960, (0.9, 1.7) 95 and 1255, scale 1.0: 135 at 128^3, 3.0: 180
+  h->omega = 0.9;
+  h->scale = 1.5;
+  h->wj = 1.0;
+  if (const char* e = getenv("MIMPY_B200_AUX_WJ")) h->wj = atof(e);
+  if (const char* e = getenv("MIMPY_B200_AUX_OMEGA")) h->omega = atof(e);
+  if (const char* e = getenv("MIMPY_B200_AUX_SCALE")) h->scale = atof(e);
   h->cell_faces = mesh->cell_faces;
   h->face_to_flux = sym->face_to_flux;
   h->face_cell = sym->face_cell;

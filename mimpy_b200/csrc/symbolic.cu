@@ -55,8 +55,8 @@ __global__ void k_flux_fix(int nf, const uint8_t* __restrict__ neumann, int* __r
 // sorted unique flux DOFs of the cells adjacent to face f; returns count
 __device__ int row_columns(int f, const int* __restrict__ cell_ptr,
                            const int* __restrict__ cell_faces, const int* __restrict__ f2f,
-                           const int* __restrict__ face_cell, int* cols) {
-  int n = 0;
+                           const int* __restrict__ face_cell, int* cols, int* n_dup = nullptr) {
+  int n = 0, dups = 0;
   for (int s = 0; s < 2; ++s) {
     const int c = face_cell[2 * (size_t)f + s];
     if (c < 0) continue;
@@ -73,12 +73,16 @@ __device__ int row_columns(int f, const int* __restrict__ cell_ptr,
         }
         --k;
       }
-      if (dup) continue;
+      if (dup) {
+        ++dups;
+        continue;
+      }
       for (int m = n; m > k; --m) cols[m] = cols[m - 1];
       cols[k] = g;
       ++n;
     }
   }
+  if (n_dup) *n_dup = dups;
   return n;
 }
 
@@ -87,13 +91,17 @@ __device__ int row_columns(int f, const int* __restrict__ cell_ptr,
 __global__ void k_row_len_faces(int nf, const int* __restrict__ cell_ptr,
                                 const int* __restrict__ cell_faces, const int* __restrict__ f2f,
                                 const int* __restrict__ face_cell, int* __restrict__ len,
-                                int* __restrict__ len_m) {
+                                int* __restrict__ len_m, int* __restrict__ multi_shared) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= nf) return;
   const int g = f2f[f];
   if (g < 0) return;
   int cols[MAXC];
-  const int n = row_columns(f, cell_ptr, cell_faces, f2f, face_cell, cols);
+  int dups = 0;
+  const int n = row_columns(f, cell_ptr, cell_faces, f2f, face_cell, cols, &dups);
+  // the two cells of f share f itself; any further common flux face means an entry M[g(f), g(f')] with two
+  // contributors, which the numeric kernels (one writer per off-diagonal slot) do not sum
+  if (dups > 1) *multi_shared = 1;
   const int ncell = (face_cell[2 * (size_t)f] >= 0) + (face_cell[2 * (size_t)f + 1] >= 0);
   len_m[g] = n;
   len[g] = n + ncell;
@@ -242,13 +250,14 @@ int mimpy_b200_mfd_symbolic_sizes(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,
     if (cudaStreamSynchronize(st) != cudaSuccess) { rc = MIMPY_E_CUDA; break; }
     k_flux_fix<<<(nf + T - 1) / T, T, 0, st>>>(nf, neumann_mask, sym->face_to_flux);
     k_row_len_faces<<<(nf + T - 1) / T, T, 0, st>>>(nf, mesh->cell_ptr, mesh->cell_faces,
-                                                    sym->face_to_flux, sym->face_cell, len, len_m);
+                                                    sym->face_to_flux, sym->face_cell, len, len_m, flag + nf);
     k_row_len_cells<<<(nc + T - 1) / T, T, 0, st>>>(nc, F, mesh->cell_ptr, mesh->cell_faces,
                                                     sym->face_to_flux, len, blk);
     if ((rc = scan_i32(ctx, len, sym->indptr, F + nc + 1))) break;
     if ((rc = scan_i32(ctx, len_m, sym->m_indptr, F + 1))) break;
     if ((rc = scan_i32(ctx, blk, sym->m_ptr, nc + 1))) break;
-    int nnz = 0, nnz_m = 0, nb = 0;
+    int nnz = 0, nnz_m = 0, nb = 0, multi = 0;
+    cudaMemcpyAsync(&multi, flag + nf, sizeof(int), cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(&nnz, sym->indptr + F + nc, sizeof(int), cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(&nnz_m, sym->m_indptr + F, sizeof(int), cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(&nb, sym->m_ptr + nc, sizeof(int), cudaMemcpyDeviceToHost, st);
@@ -260,6 +269,10 @@ int mimpy_b200_mfd_symbolic_sizes(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,
     sym->n_blocks = nb;
     if (nnz < 0 || nb < 0) {
       mimpy_set_error("saddle matrix exceeds int32 indexing (nnz >= 2^31)");
+      rc = MIMPY_E_UNSUPPORTED;
+    } else if (multi) {
+      mimpy_set_error("two cells of the mesh share more than one face: an off-diagonal entry of M would have two "
+                      "contributors, which the assembly kernels do not sum");
       rc = MIMPY_E_UNSUPPORTED;
     }
   } while (0);

@@ -458,6 +458,27 @@ def test_numeric_layers_repeated_and_out_of_order(ctx):
     assert np.array_equal(H(ctx, vals), full)
 
 
+def test_symbolic_rejects_cells_sharing_two_faces(ctx):
+    """Two cells with more than one common face would give an off-diagonal entry of M two contributors (the
+    reference sums COO duplicates); the assembly kernels have one writer per such slot, so the symbolic pass
+    refuses the mesh loudly instead of dropping a contribution."""
+    from mimpy_b200 import _lib, device
+
+    rng = np.random.default_rng(0)
+    nf = 6
+    cell_ptr = np.array([0, 4, 8])
+    cell_faces = np.array([0, 1, 2, 3, 2, 3, 4, 5])          # faces 2 and 3 belong to both cells
+    sigma = np.array([1, 1, 1, 1, -1, -1, 1, 1])
+    nrm = rng.standard_normal((nf, 3))
+    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    d = device.DeviceMesh.from_arrays(ctx, cell_ptr, cell_faces, sigma, rng.uniform(.5, 1., nf), nrm,
+                                      rng.standard_normal((nf, 3)), np.tile(np.eye(3).ravel(), (2, 1)),
+                                      rng.standard_normal((2, 3)), np.ones(2))
+    with pytest.raises(_lib.MimpyB200Error) as err:
+        device.symbolic(d, np.zeros(nf, dtype=np.uint8))
+    assert "share more than one face" in str(err.value)
+
+
 class HexIndexHost(object):
     """Closed-form HexMesh face numbering (hexmesh.py:161-234) for picking boundary faces by index."""
 
