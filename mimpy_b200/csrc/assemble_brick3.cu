@@ -121,6 +121,16 @@ __device__ __forceinline__ void st_unless_sentinel(const double* p, double v) {
       "d"(v), "n"(OFF)
       : "memory");
 }
+// 1 / x without the slow path of the IEEE division: MUFU seed (~20 bits) and two Newton steps (<= 1 ulp);
+// x is a pivot or a sum of an SPD block here, far from the denormal range
+__device__ __forceinline__ double rcp_nr(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- plan binding of the face records ---------------------------------------------------------------
@@ -663,7 +673,7 @@ struct SetupArgs {
 };
 static_assert(36 * HS_LD * 8 + B3_OFF_OUT <= B3_OFF_IN, "the inversion tile fits in the image region");
 
-template <int METHOD>
+template <int METHOD, int STRIDE>
 __global__ void __launch_bounds__(B3_THREADS, B3_MINB)
 k_hybrid_setup_brick(mimpy_mesh_view m, int flags, UniArgs a, SetupArgs sa_, B3Geo g) {
   constexpr int NF = 6;
@@ -779,8 +789,13 @@ k_hybrid_setup_brick(mimpy_mesh_view m, int flags, UniArgs a, SetupArgs sa_, B3G
         mp[i] = merged_present(i, p1, p2);
         if (i == 0) me = p2;
         if ((i < 3 ? p1 : p2) != 0u) other_mask |= 1u << i;
-        sgn[i] = i < 3 ? -1. : 1.;
+        sgn[i] = 1.;
         area[i] = rec[i][0].x;
+        if (i < 3) {  // outward normal sigma n_f of the z-, y-, x- faces (hexmesh.py:329-342)
+          rec[i][0].y = -rec[i][0].y;
+          rec[i][1].x = -rec[i][1].x;
+          rec[i][1].y = -rec[i][1].y;
+        }
       }
       trk = K[0] + K[4] + K[8];
       cell_prep<NF, METHOD>(K, xc, rec, sgn, o);
@@ -792,26 +807,40 @@ k_hybrid_setup_brick(mimpy_mesh_view m, int flags, UniArgs a, SetupArgs sa_, B3G
     int rowb_n[NF];
     if (bn < g.total) prefetch(nbi, nbj, nbk, mult_n, cdiag_n, rowb_n);
 
-    if (ok) {
-      // faces that are no flux DOF (Neumann), and boundary faces (one cell, prescribed multiplier)
-      const unsigned dropbits = ~me & 63u;
-      unsigned bndbits = ~other_mask & 63u;
-      if (has_lo && ck == 0) bndbits &= ~1u;
-      if (has_hi && ck == nz - 1) bndbits &= ~32u;
-      // mult * M_E acting on the outward fluxes u = sigma o v (cell_core folds sigma_i sigma_j in: folded back)
-      cell_core<NF, METHOD>(o, trk, vol, mult, [&](int i, int j, double v) {
-        const bool drop = ((dropbits >> i) | (dropbits >> j)) & 1u;
-        const double s = ((i < 3) == (j < 3)) ? 1. : -1.;
-        A[(i * NF + j) * HS_LD] = drop ? (i == j ? 1. : 0.) : s * v;
-      });
-      // Gauss-Jordan without pivoting in REGISTERS (the operands of cell_core are dead by now; the tile only
-      // carried the 36 entries across), same elimination order as group_invert (common.cuh); fully unrolled
-      double R[NF * NF];
+    // A REGULAR cell: its six faces are flux DOFs shared with a cell whose six faces are flux DOFs as well (no
+    // boundary, no Neumann face in reach).  A warp of regular cells takes the instantiation without masks,
+    // selects and popcounts: every row position is its index in the merged list (88 % of the cells at 256^3).
+    bool mine_regular = ok;
+    unsigned long long other[NF];
+    double diag_half[NF];
+    int diag_at[NF];
 #pragma unroll
-      for (int e = 0; e < NF * NF; ++e) R[e] = A[e * HS_LD];
+    for (int i = 0; i < NF; ++i) {
+      mine_regular = mine_regular && mp[i] == 0x7FFu;
+      other[i] = AU_SENTINEL;
+      diag_half[i] = 0.;
+      diag_at[i] = 0;
+    }
+    auto body = [&](auto tag) {
+      constexpr bool REG = decltype(tag)::value;
+      // faces that are no flux DOF (Neumann), and boundary faces (one cell, prescribed multiplier)
+      const unsigned dropbits = REG ? 0u : (~me & 63u);
+      unsigned bndbits = REG ? 0u : (~other_mask & 63u);
+      if (!REG) {
+        if (has_lo && ck == 0) bndbits &= ~1u;
+        if (has_hi && ck == nz - 1) bndbits &= ~32u;
+      }
+      // mult * M_E acting on the outward fluxes u = sigma o v: the orientations were folded into the normals
+      // (cell_prep got sigma n_f and R_f itself), so cell_core delivers M_E and not sigma_i sigma_j M_E
+      double R[NF * NF];
+      cell_core<NF, METHOD>(o, trk, vol, mult, [&](int i, int j, double v) {
+        const bool drop = !REG && (((dropbits >> i) | (dropbits >> j)) & 1u);
+        R[i * NF + j] = drop ? (i == j ? 1. : 0.) : v;
+      });
+      // Gauss-Jordan without pivoting in registers, same elimination order as group_invert (common.cuh)
 #pragma unroll
       for (int k = 0; k < NF; ++k) {
-        const double pinv = 1.0 / R[k * NF + k];
+        const double pinv = rcp_nr(R[k * NF + k]);
 #pragma unroll
         for (int j = 0; j < NF; ++j) {
           if (j == k) continue;
@@ -837,11 +866,11 @@ k_hybrid_setup_brick(mimpy_mesh_view m, int flags, UniArgs a, SetupArgs sa_, B3G
       for (int i = 0; i < NF; ++i)
 #pragma unroll
         for (int j = 0; j < NF; ++j) {
-          const bool drop = ((dropbits >> i) | (dropbits >> j)) & 1u;
+          const bool drop = !REG && (((dropbits >> i) | (dropbits >> j)) & 1u);
           const double w = drop ? 0. : R[i * NF + j];
-          R[i * NF + j] = w;
           A[(i * NF + j) * HS_LD] = w;   // W leaves through the tile (coalesced copy-out below)
           const double awa = area[i] * w * area[j];
+          R[i * NF + j] = awa;
           rsum[i] += awa;
           csum[j] += awa;
         }
@@ -849,38 +878,76 @@ k_hybrid_setup_brick(mimpy_mesh_view m, int flags, UniArgs a, SetupArgs sa_, B3G
       double S = cd;
 #pragma unroll
       for (int j = 0; j < NF; ++j) S += csum[j];
-      const double inv_s = 1.0 / S;
-      if (sa_.tau) {
+      const double inv_s = rcp_nr(S);
+      if (sa_.tau) {  // tau_{E,f} = a_f^2 W_E[f,f]: 48 contiguous bytes per cell
+        double2* tp = reinterpret_cast<double2*>(sa_.tau + cell * NF);
 #pragma unroll
-        for (int i = 0; i < NF; ++i)
-          sa_.tau[cell * NF + i] = ((me >> i) & 1u) ? area[i] * area[i] * R[i * NF + i] : 0.;
+        for (int i = 0; i < NF; i += 2)
+          tp[i >> 1] = make_double2((REG || ((me >> i) & 1u)) ? R[i * NF + i] : 0.,
+                                    (REG || ((me >> (i + 1)) & 1u)) ? R[(i + 1) * NF + i + 1] : 0.);
       }
-      const int stride = sa_.row_stride;
+#pragma unroll
+      for (int j = 0; j < NF; ++j) csum[j] *= inv_s;  // entry (i, j) = aWa[i,j] - rsum[i] csum[j] / S
 #pragma unroll
       for (int i = 0; i < NF; ++i) {
-        if (rowb[i] < 0) continue;
+        if (!REG && rowb[i] < 0) continue;
+        double* const rowp = sa_.a_vals + rowb[i];
 #pragma unroll
         for (int j = 0; j < NF; ++j) {
-          if (!((me >> j) & 1u)) continue;
-          const bool bnd = ((bndbits >> i) | (bndbits >> j)) & 1u;
-          double v = area[i] * R[i * NF + j] * area[j] - rsum[i] * csum[j] * inv_s;
-          if (bnd) v = (i == j) ? 1. : 0.;
-          const int pos = __popc(mp[i] & ((1u << merged_index(i, j)) - 1u));
-          if (i == j) atomicAdd(sa_.a_vals + rowb[i] + pos * stride, v);
-          else sa_.a_vals[rowb[i] + pos * stride] = v;
+          if (!REG && !((me >> j) & 1u)) continue;
+          double v = fma(-rsum[i], csum[j], R[i * NF + j]);
+          if (!REG && (((bndbits >> i) | (bndbits >> j)) & 1u)) v = (i == j) ? 1. : 0.;
+          const int pos = REG ? merged_index(i, j) : __popc(mp[i] & ((1u << merged_index(i, j)) - 1u));
+          if (i != j) {
+            rowp[pos * STRIDE] = v;
+          } else if (!REG && !((other_mask >> i) & 1u)) {
+            rowp[pos * STRIDE] = v;  // the only local cell of the face
+          } else {
+            // the two cells of a face swap their halves of the diagonal through the face's exchange slot
+            // (all-sentinel between launches): the second to arrive writes half + half and restores the
+            // sentinel -- commutative, so the value does not depend on the arrival order; nobody waits
+            // (the answers are collected after the copy-out of W: six round trips to L2 in flight at once)
+            diag_half[i] = v;
+            diag_at[i] = rowb[i] + pos * STRIDE;
+            other[i] = atomicExch(reinterpret_cast<unsigned long long*>(a.diag_pub) + fid[i],
+                                  (unsigned long long)__double_as_longlong(v));
+          }
         }
       }
-    }
+    };
+    if (__all_sync(0xffffffffu, mine_regular))
+      body(std::true_type{});
+    else if (ok)
+      body(std::false_type{});
     sync_compute();
-    // copy-out of W: an x-run of cells is one contiguous piece of w_e (36 doubles per cell)
+    // copy-out of W: an x-run of 8 cells is one contiguous piece of w_e (288 doubles): warp w streams the runs
+    // 4w .. 4w+3, nine coalesced passes each; element e = lane + 32 p of a run is entry e % 36 of cell e / 36
     {
       const int runlen = min(BX, nx - ci0);
-      for (int q = t; q < B2_RUNS * BX * NF * NF; q += BR_THREADS) {
-        const int r = q / (BX * NF * NF), e = q - r * (BX * NF * NF);
+      int wo[9];
+#pragma unroll
+      for (int p = 0; p < 9; ++p) {
+        const int e = lane + 32 * p, c8 = (e * 57) >> 11;  // e / 36 for e < 288
+        wo[p] = (c8 < runlen) ? (e - 36 * c8) * HS_LD + c8 : -1;
+      }
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int r = warp * 4 + rr;
         const long long c0 = s_cell0[r];
-        if (c0 < 0 || e >= runlen * NF * NF) continue;
-        const int c8 = e / (NF * NF), entry = e - c8 * (NF * NF);
-        sa_.w_e[c0 * (NF * NF) + e] = tile[entry * HS_LD + r * BX + c8];
+        if (c0 < 0) continue;
+        double* dst = sa_.w_e + c0 * (NF * NF) + lane;
+        const double* src = tile + r * BX;
+#pragma unroll
+        for (int p = 0; p < 9; ++p)
+          if (wo[p] >= 0) dst[32 * p] = src[wo[p]];
+      }
+    }
+    // diagonals: the second cell to arrive at a face finds the other's half, writes the sum and leaves the slot clean
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+      if (other[i] != AU_SENTINEL) {
+        sa_.a_vals[diag_at[i]] = __longlong_as_double((long long)other[i]) + diag_half[i];
+        reinterpret_cast<unsigned long long*>(a.diag_pub)[fid[i]] = AU_SENTINEL;
       }
     }
     if (bn >= g.total) break;
@@ -903,16 +970,24 @@ k_face_rowbase(int nf, const int* __restrict__ f2f, const int* __restrict__ sell
 }
 
 int mimpy_face_rowbase(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym, const int* sell_ptr, int* out) {
+  // pattern-only: the same (plan, layout, buffer) as last time needs no second pass
+  if (sym->serial != 0 && ctx->rowbase_serial == (long long)sym->serial && ctx->rowbase_sell == (const void*)sell_ptr &&
+      ctx->rowbase_out == (const void*)out && ctx->rowbase_nf == mesh->nf)
+    return MIMPY_OK;
+  ctx->rowbase_serial = (long long)sym->serial;
+  ctx->rowbase_sell = sell_ptr;
+  ctx->rowbase_out = out;
+  ctx->rowbase_nf = mesh->nf;
   k_face_rowbase<<<(mesh->nf + 255) / 256, 256, 0, ctx->stream>>>(mesh->nf, sym->face_to_flux, sell_ptr, sym->m_indptr, out);
   KERNEL_CHECK();
   return MIMPY_OK;
 }
 
-template <int METHOD>
+template <int METHOD, int STRIDE>
 static int launch_setup_brick(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int flags, const UniArgs& a, const SetupArgs& sa,
                               const B3Geo& g, long long grid) {
-  CUDA_TRY(cudaFuncSetAttribute(k_hybrid_setup_brick<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B3_SMEM));
-  k_hybrid_setup_brick<METHOD><<<(unsigned)grid, B3_THREADS, B3_SMEM, ctx->stream>>>(*mesh, flags, a, sa, g);
+  CUDA_TRY(cudaFuncSetAttribute(k_hybrid_setup_brick<METHOD, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B3_SMEM));
+  k_hybrid_setup_brick<METHOD, STRIDE><<<(unsigned)grid, B3_THREADS, B3_SMEM, ctx->stream>>>(*mesh, flags, a, sa, g);
   KERNEL_CHECK();
   return MIMPY_OK;
 }
@@ -931,10 +1006,15 @@ int mimpy_hybrid_setup_brick(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const 
   rc = b3_geometry(ctx, mesh, 0, 0x3fffffff, g, grid);
   if (rc) return rc;
   if (grid == 0) return MIMPY_OK;
+  if (row_stride != 32 && row_stride != 1) return MIMPY_E_UNSUPPORTED;
+  // exchange slots of the two-contributor diagonals (shared with the assembly kernels; all-sentinel between launches)
+  rc = mimpy_swap_prepare(ctx, mesh, false, 0, 0);
+  if (rc) return rc;
   UniArgs a = {};
   a.multipliers = multipliers;
   a.c_diag = c_diag;
   a.alpha = alpha;
+  a.diag_pub = ctx->diag_swap;
   a.ticket = ctx->counters + 12;
   a.error_flag = ctx->counters + 9;
   a.flux_dof = sym->flux_dof;
@@ -946,9 +1026,13 @@ int mimpy_hybrid_setup_brick(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const 
   sa.w_e = w_e;
   sa.tau = tau;
   sa.a_vals = a_vals;
-  if (method == 0) return launch_setup_brick<0>(ctx, mesh, flags, a, sa, g, grid);
-  if (method == 1) return launch_setup_brick<1>(ctx, mesh, flags, a, sa, g, grid);
-  return launch_setup_brick<6>(ctx, mesh, flags, a, sa, g, grid);
+#define SETUP_LAUNCH(M)                                                                        \
+  (row_stride == 32 ? launch_setup_brick<M, 32>(ctx, mesh, flags, a, sa, g, grid)               \
+                    : launch_setup_brick<M, 1>(ctx, mesh, flags, a, sa, g, grid))
+  if (method == 0) return SETUP_LAUNCH(0);
+  if (method == 1) return SETUP_LAUNCH(1);
+  return SETUP_LAUNCH(6);
+#undef SETUP_LAUNCH
 }
 
 static int b3_ctas_per_sm() {

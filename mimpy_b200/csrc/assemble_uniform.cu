@@ -327,7 +327,7 @@ static int launch_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int flags
 // slots until the neighbouring range is assembled.  Left there they would be taken for the partner's
 // half by a REPEATED or out-of-order launch, so the layers a launch is about to write from the same side
 // again are re-sentinelled first (1 = left by the cells below the layer, 2 = by the cells above).
-static int swap_prepare(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, bool ranged, int layer_begin, int layer_end) {
+int mimpy_swap_prepare(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, bool ranged, int layer_begin, int layer_end) {
   const int nx = mesh->hex_nx, ny = mesh->hex_ny, nz = mesh->hex_nz;
   const int L = nx * ny + nx * (ny + 1) + (nx + 1) * ny;
   if (ctx->diag_swap_len < (size_t)mesh->nf) {
@@ -418,7 +418,7 @@ int mimpy_numeric_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mim
   const int bk_end = ranged ? (layer_end + BZ - 1) / BZ : 0x3fffffff;
   double* exchange = nullptr;
   if (staged || pipelined) {
-    int rc = swap_prepare(ctx, mesh, ranged && !(layer_begin == 0 && layer_end >= mesh->hex_nz), layer_begin, layer_end);
+    int rc = mimpy_swap_prepare(ctx, mesh, ranged && !(layer_begin == 0 && layer_end >= mesh->hex_nz), layer_begin, layer_end);
     if (rc) return rc;
     exchange = ctx->diag_swap;
   } else {

@@ -385,6 +385,57 @@ struct AuxHex {
   __device__ __forceinline__ int zp(int i, int j, int k) const { return k + 1 < nz ? cbase(i, j, k) + L : nz * L + j * nx + i; }
 };
 
+// Level 0 of a single-rank structured hex mesh from the half transmissibilities the set-up kernel wrote
+// (tau[c*6 + q]): the partner of face q of cell c is local face 5 - q of the neighbouring cell, so neither the
+// per-face sums (tsum: 100 M atomics at 256^3), nor a copy of tau, nor an index array is needed.  Same
+// arithmetic as k_aux_tau_given + k_aux_level0 (the sum of two addends does not depend on their order).
+__global__ void __launch_bounds__(AUX_T)
+k_aux_level0_hex(AuxHex hx, const int* __restrict__ f2f, const double* __restrict__ tau,
+                 const double* __restrict__ cell_volume, double alpha, const double* __restrict__ c_diag,
+                 double* __restrict__ fw, AuxLevel L) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= L.n) return;
+  const int sy = hx.nx, sz = hx.nx * hx.ny;
+  const int i = c % hx.nx, j = (c / hx.nx) % hx.ny, k = c / sz;
+  const int cb = hx.cbase(i, j, k);
+  const int f[6] = {cb, cb + 1, cb + 2, hx.xp(i, j, k), hx.yp(i, j, k), hx.zp(i, j, k)};
+  const bool partner[6] = {k > 0, j > 0, i > 0, i + 1 < hx.nx, j + 1 < hx.ny, k + 1 < hx.nz};
+  const int other[6] = {c - sz, c - sy, c - 1, c + 1, c + sy, c + sz};
+  double own[6];
+  {
+    const double2* t2 = reinterpret_cast<const double2*>(tau + (size_t)c * 6);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const double2 v = t2[q];
+      own[2 * q] = v.x;
+      own[2 * q + 1] = v.y;
+    }
+  }
+  double dd = c_diag ? c_diag[c] : alpha * cell_volume[c];
+  double tp[3] = {0., 0., 0.};
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    const int g = f2f[f[q]];
+    double w = 0.;
+    if (g >= 0 && own[q] > 0.) {
+      if (!partner[q]) {
+        dd += own[q];  // boundary face with a prescribed multiplier
+      } else {
+        const double S = own[q] + tau[(size_t)other[q] * 6 + (5 - q)];
+        w = own[q] / S;
+        if (q >= 3) tp[q - 3] = own[q] * (S - own[q]) / S;
+      }
+    }
+    if (q >= 3 || !partner[q]) fw[f[q]] = w;  // the first (or only) cell of the face
+  }
+  L.tx[c] = tp[0];
+  L.ty[c] = tp[1];
+  L.tz[c] = tp[2];
+  L.dd[c] = dd;
+  if (c >= L.n - sz) L.tzi[c - (L.n - sz)] = 0.;
+  if (c < sz) L.bzi[c] = 0.;
+}
+
 // b = Pi^T r on the cells.  A cell is the SECOND cell of its z-/y-/x- face when that neighbour exists
 // (weight 1 - fw), the first cell of every other face (weight fw); no index array is read.
 __global__ void __launch_bounds__(AUX_T)
@@ -670,20 +721,32 @@ int mimpy_b200_auxmg_setup(mimpy_ctx* ctx, void* handle, const mimpy_mesh_view* 
   h->face_to_flux = sym->face_to_flux;
   h->face_cell = sym->face_cell;
   h->face_flag = sym->face_flag;
-  CUDA_TRY(cudaMemsetAsync(h->tsum, 0, sizeof(double) * (size_t)(h->flux_dof ? h->flux_dof : 1), st));
-  CUDA_TRY(cudaMemsetAsync(h->fw, 0, sizeof(double) * (size_t)h->nf, st));
-  if (tau)
-    k_aux_tau_given<<<(unsigned)(((long long)h->nc * 6 + AUX_T - 1) / AUX_T), AUX_T, 0, st>>>(h->nc, mesh->cell_faces, sym->face_to_flux,
-                                                                                            tau, h->wc, h->tsum);
-  else
-    k_aux_tau<<<aux_blocks(h->nc), AUX_T, 0, st>>>(h->nc, mesh->cell_faces, sym->face_to_flux, sym->m_ptr,
-                                                  mesh->face_geom, w_e, h->wc, h->tsum);
-  KERNEL_CHECK();
-  int rc = mimpy_halo_exchange_add(ctx, h->tsum);  // interface faces: tau of the cell on the other rank
-  if (rc) return rc;
-  k_aux_level0<<<aux_blocks(h->nc), AUX_T, 0, st>>>(h->nc, mesh->cell_faces, sym->face_to_flux, sym->face_cell,
-                                                   sym->face_flag, h->tsum, mesh->cell_volume, alpha, c_diag,
-                                                   h->wc, h->fw, h->lev[0]);
+  int rc = MIMPY_OK;
+  if (tau && ctx->world == 1 && !sym->face_flag && ((uintptr_t)tau & 15u) == 0) {
+    // one rank, half transmissibilities at hand: closed-form partners, no sums over faces, no copy
+    AuxHex hx;
+    hx.nx = mesh->hex_nx; hx.ny = mesh->hex_ny; hx.nz = mesh->hex_nz;
+    hx.L = hx.nx * hx.ny + hx.nx * (hx.ny + 1) + (hx.nx + 1) * hx.ny;
+    hx.xrow = 3 * hx.nx + 1;
+    k_aux_level0_hex<<<aux_blocks(h->nc), AUX_T, 0, st>>>(hx, sym->face_to_flux, tau, mesh->cell_volume, alpha, c_diag,
+                                                         h->fw, h->lev[0]);
+    KERNEL_CHECK();
+  } else {
+    CUDA_TRY(cudaMemsetAsync(h->tsum, 0, sizeof(double) * (size_t)(h->flux_dof ? h->flux_dof : 1), st));
+    CUDA_TRY(cudaMemsetAsync(h->fw, 0, sizeof(double) * (size_t)h->nf, st));
+    if (tau)
+      k_aux_tau_given<<<(unsigned)(((long long)h->nc * 6 + AUX_T - 1) / AUX_T), AUX_T, 0, st>>>(h->nc, mesh->cell_faces, sym->face_to_flux,
+                                                                                              tau, h->wc, h->tsum);
+    else
+      k_aux_tau<<<aux_blocks(h->nc), AUX_T, 0, st>>>(h->nc, mesh->cell_faces, sym->face_to_flux, sym->m_ptr,
+                                                    mesh->face_geom, w_e, h->wc, h->tsum);
+    KERNEL_CHECK();
+    rc = mimpy_halo_exchange_add(ctx, h->tsum);  // interface faces: tau of the cell on the other rank
+    if (rc) return rc;
+    k_aux_level0<<<aux_blocks(h->nc), AUX_T, 0, st>>>(h->nc, mesh->cell_faces, sym->face_to_flux, sym->face_cell,
+                                                     sym->face_flag, h->tsum, mesh->cell_volume, alpha, c_diag,
+                                                     h->wc, h->fw, h->lev[0]);
+  }
   for (int l = 0; l < h->nlev; ++l) {
     if (l > 0) k_aux_coarsen<<<aux_blocks(h->lev[l].n), AUX_T, 0, st>>>(h->lev[l - 1], h->lev[l]);
     k_aux_diag<<<aux_blocks(h->lev[l].n), AUX_T, 0, st>>>(h->lev[l]);

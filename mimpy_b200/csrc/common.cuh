@@ -47,6 +47,11 @@ struct mimpy_ctx {
   const void* bound_geom;
   long long bound_serial;
   unsigned b3_ticket;    // value of the brick ticket counter (counters[12]) before the next launch
+  // per-face row bases of the face system last written by mimpy_face_rowbase (plan serial, layout, buffer)
+  long long rowbase_serial;
+  const void* rowbase_sell;
+  const void* rowbase_out;
+  int rowbase_nf;
   double* partials;      // reduction partials (device)
   unsigned int* counters;  // last-block counters (device)
   double* scalars;       // device scalars for PCG (alpha, beta, rz, ...)
@@ -66,6 +71,8 @@ int mimpy_face_rowbase(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_
 int mimpy_hybrid_setup_brick(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym, int method, int flags,
                              const double* multipliers, double alpha, const double* c_diag, const int* face_rowbase,
                              int row_stride, double* w_e, double* tau, double* a_vals);
+// assemble_uniform.cu: exchange slots of the two-contributor diagonals, clean (all-sentinel) for the launch to come
+int mimpy_swap_prepare(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, bool ranged, int layer_begin, int layer_end);
 int mimpy_scratch(mimpy_ctx* ctx, size_t bytes, void** out);
 int mimpy_check_device_flag(mimpy_ctx* ctx);  // stream sync + error if a bounded device wait ran out
 // auxmg.cu: z = B r (auxiliary-space multigrid + Jacobi), this rank's share of r.z -> *rz_dst

@@ -234,11 +234,14 @@ k_hybrid_setup_hex(mimpy_mesh_view m, HybArgs h, int k_unity, const double* __re
   }
 }
 
+// INVERT = false: the diagonal itself (inverted by k_invert after the interface exchange of a slab partition)
+template <bool INVERT>
 __global__ void k_diag_inv(int F, HybArgs h, const uint8_t* __restrict__ diag_pos,
                            const double* __restrict__ a_vals, double* __restrict__ dinv) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= F) return;
-  dinv[g] = a_vals[h.row_base(g) + (int)diag_pos[g] * h.row_stride()];  // inverted after the interface exchange
+  const double d = a_vals[h.row_base(g) + (int)diag_pos[g] * h.row_stride()];
+  dinv[g] = INVERT ? 1.0 / d : d;
 }
 
 __global__ void k_invert(int F, double* __restrict__ d) {
@@ -375,7 +378,7 @@ int mimpy_b200_hybrid_setup(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
              (k_hybrid_setup<32><<<blocks, 128, 0, st>>>(*mesh, h, m_e, multipliers, w_e, a_vals)));
   KERNEL_CHECK();
   if (F > 0) {
-    k_diag_inv<<<(F + 255) / 256, 256, 0, st>>>(F, h, sym->diag_pos, a_vals, a_diag_inv);
+    k_diag_inv<false><<<(F + 255) / 256, 256, 0, st>>>(F, h, sym->diag_pos, a_vals, a_diag_inv);
     KERNEL_CHECK();
     // slab partition: the diagonal of an interface row is the sum of both ranks' halves
     int rc = mimpy_halo_exchange_add(ctx, a_diag_inv);
@@ -399,11 +402,8 @@ int mimpy_b200_hybrid_setup_fused(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, c
   cudaStream_t st = ctx->stream;
   HybArgs h = make_hyb(sym, alpha, c_diag);
   h.sell_ptr = sell_ptr;
-  if (F > 0) {
-    k_zero_diag_m<<<(F + 255) / 256, 256, 0, st>>>(F, h, sym->diag_pos, a_vals);
-    KERNEL_CHECK();
-  }
-  // structured hex meshes: the pipelined brick kernel (bulk-copy staging, closed-form positions)
+  // structured hex meshes: the pipelined brick kernel (bulk-copy staging, closed-form positions; the two halves
+  // of a diagonal entry meet in an exchange slot, so no slot is zeroed first and nothing is added atomically)
   bool done = false;
   if (face_rowbase_work && !getenv("MIMPY_B200_SETUP_OLD")) {
     int rc = mimpy_face_rowbase(ctx, mesh, sym, sell_ptr, face_rowbase_work);
@@ -415,15 +415,23 @@ int mimpy_b200_hybrid_setup_fused(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, c
   }
   if (done) {
     if (F > 0) {
-      k_diag_inv<<<(F + 255) / 256, 256, 0, st>>>(F, h, sym->diag_pos, a_vals, a_diag_inv);
-      KERNEL_CHECK();
-      int rc = mimpy_halo_exchange_add(ctx, a_diag_inv);
-      if (rc) return rc;
-      k_invert<<<(F + 255) / 256, 256, 0, st>>>(F, a_diag_inv);
+      if (ctx->world > 1) {  // slab partition: the diagonal of an interface row is the sum of both ranks' halves
+        k_diag_inv<false><<<(F + 255) / 256, 256, 0, st>>>(F, h, sym->diag_pos, a_vals, a_diag_inv);
+        KERNEL_CHECK();
+        int rc = mimpy_halo_exchange_add(ctx, a_diag_inv);
+        if (rc) return rc;
+        k_invert<<<(F + 255) / 256, 256, 0, st>>>(F, a_diag_inv);
+      } else {
+        k_diag_inv<true><<<(F + 255) / 256, 256, 0, st>>>(F, h, sym->diag_pos, a_vals, a_diag_inv);
+      }
       KERNEL_CHECK();
     }
     if (tau_written_host) *tau_written_host = tau_out ? 1 : 0;
     return MIMPY_OK;
+  }
+  if (F > 0) {
+    k_zero_diag_m<<<(F + 255) / 256, 256, 0, st>>>(F, h, sym->diag_pos, a_vals);
+    KERNEL_CHECK();
   }
   const size_t smem = sizeof(double) * 36 * HX_LD;
   const int blocks = (mesh->nc + HX_THREADS - 1) / HX_THREADS;
@@ -439,7 +447,7 @@ int mimpy_b200_hybrid_setup_fused(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, c
 #undef HX_LAUNCH
   KERNEL_CHECK();
   if (F > 0) {
-    k_diag_inv<<<(F + 255) / 256, 256, 0, st>>>(F, h, sym->diag_pos, a_vals, a_diag_inv);
+    k_diag_inv<false><<<(F + 255) / 256, 256, 0, st>>>(F, h, sym->diag_pos, a_vals, a_diag_inv);
     KERNEL_CHECK();
     int rc = mimpy_halo_exchange_add(ctx, a_diag_inv);
     if (rc) return rc;
