@@ -670,8 +670,24 @@ struct SetupArgs {
   double* w_e;
   double* tau;              // nullable: nc * 6
   double* a_vals;
+  double* dhalf;            // [nf] half of the diagonal entry that the upper cell of a two-cell face contributes
 };
-static_assert(36 * HS_LD * 8 + B3_OFF_OUT <= B3_OFF_IN, "the inversion tile fits in the image region");
+// image of a regular brick: [16 runs][12 = 11 entries + the diagonal halves][32: 24 rows + 8 idle], pitch 392 per
+// run (bank-conflict free for the stores of a half-warp: 3 li + 8 lj mod 16 are distinct)
+#define HS_IMG_K 32
+#define HS_IMG_RUN (12 * HS_IMG_K + 8)
+#define HS_OFF_WO ((B3_OFF_OUT + B2_RUNS * HS_IMG_RUN * 8 + 15) / 16 * 16)  /* int wo[9][32]: tile offsets of the W copy-out */
+static_assert(36 * HS_LD <= B2_RUNS * HS_IMG_RUN, "the image overlays the inversion tile");
+static_assert(HS_OFF_WO + 9 * 32 * 4 <= B3_OFF_IN, "image and copy-out table fit in the image region");
+static_assert(B2_RUNS * 8 + 3 * B2_RUNS * 4 <= (2 * B2_RUNS + B2_EXTRA_ROWS) * 4, "small arrays of the set-up kernel fit");
+#define HS_OFF_ROWB B3_SMEM                       /* int rowb[2][6][128]: behind everything the assembly kernel has */
+#define HS_SMEM (HS_OFF_ROWB + 2 * 6 * BR_THREADS * 4)
+static_assert(2 * (HS_SMEM + 1024) <= 232448, "two CTAs per SM");
+__device__ __forceinline__ void cp_async4(unsigned dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int METHOD, int STRIDE>
 __global__ void __launch_bounds__(B3_THREADS, B3_MINB)
@@ -681,6 +697,9 @@ k_hybrid_setup_brick(mimpy_mesh_view m, int flags, UniArgs a, SetupArgs sa_, B3G
   double* tile = reinterpret_cast<double*>(sm + B3_OFF_OUT);  // entry e of the cell of thread t at tile[e * HS_LD + t]
   const unsigned char* in = sm + B3_OFF_IN;
   long long* s_cell0 = reinterpret_cast<long long*>(sm + B3_OFF_SMALL);  // first cell of each x-run (-1: no run)
+  int* s_rb0 = reinterpret_cast<int*>(s_cell0 + B2_RUNS);  // per run of a regular brick: row base of its first row,
+  int* s_rbl = s_rb0 + B2_RUNS;                            //   of its last row - 23 (the run may straddle a slice),
+  int* s_cb0 = s_rbl + B2_RUNS;                            //   id of its first face
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm);
   const unsigned bar_full = sbase + B3_OFF_BAR, bar_empty = bar_full + 8, in_base = sbase + B3_OFF_IN;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -700,6 +719,10 @@ k_hybrid_setup_brick(mimpy_mesh_view m, int flags, UniArgs a, SetupArgs sa_, B3G
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(B3_REGS_COMPUTE));
   const int li = t % BX, lj = (t / BX) % BY, lk = t / (BX * BY);
   const int run = t >> 3;
+  // W copy-out of a full x-run (288 doubles, nine passes of a warp): element e = lane + 32 p is entry e % 36 of
+  // cell e / 36 -- its offset in the tile, tabulated once
+  int* s_wo = reinterpret_cast<int*>(sm + HS_OFF_WO);
+  for (int e = t; e < 9 * 32; e += BR_THREADS) s_wo[e] = (e % 36) * HS_LD + e / 36;
   // interface layers of a slab partition are interior faces of the global problem, not boundary faces
   const bool has_lo = sa_.face_flag && (__ldg(sa_.face_flag) & 2);
   const bool has_hi = sa_.face_flag && (__ldg(sa_.face_flag + sa_.nf - 1) & 1);
@@ -707,26 +730,31 @@ k_hybrid_setup_brick(mimpy_mesh_view m, int flags, UniArgs a, SetupArgs sa_, B3G
   unsigned phase = 0;
   bool first_brick = true;
   double mult = 1., cdiag = 0.;
-  int rowb[NF];
-  auto prefetch = [&](int pbi, int pbj, int pbk, double& pmult, double& pcdiag, int (&prow)[NF]) {
+  // per-cell scalars that no bulk copy brings.  The six row bases travel by cp.async straight into shared memory
+  // (double-buffered by brick parity): held in registers across the elimination they were spilled right behind
+  // their loads, and the spill store waited for the data.
+  const int* s_rowb = reinterpret_cast<const int*>(sm + HS_OFF_ROWB);
+  const unsigned rowb_base = sbase + HS_OFF_ROWB + t * 4;
+  auto prefetch = [&](int pbi, int pbj, int pbk, double& pmult, double& pcdiag, unsigned par) {
     const int ci = pbi * BX + li, cj = pbj * BY + lj, ck = pbk * BZ + lk;
     pmult = 1.;
     pcdiag = 0.;
-#pragma unroll
-    for (int i = 0; i < NF; ++i) prow[i] = -1;
     if (ci < nx && cj < ny && ck < nz) {
       const size_t cell = (size_t)ci + (size_t)nx * ((size_t)cj + (size_t)ny * ck);
       if (a.multipliers) pmult = __ldg(a.multipliers + cell);
       if (a.c_diag) pcdiag = __ldg(a.c_diag + cell);
       const int cb = ck * L + cj * xrow + 3 * ci;
-      prow[0] = __ldg(sa_.sell_rowbase + cb);
-      prow[1] = __ldg(sa_.sell_rowbase + cb + 1);
-      prow[2] = __ldg(sa_.sell_rowbase + cb + 2);
-      prow[3] = __ldg(sa_.sell_rowbase + (ci + 1 < nx ? cb + 5 : ck * L + cj * xrow + 3 * nx));
-      prow[4] = __ldg(sa_.sell_rowbase + (cj + 1 < ny ? cb + xrow + 1 : ck * L + ny * xrow + ci));
-      prow[5] = __ldg(sa_.sell_rowbase + (ck + 1 < nz ? cb + L : nz * L + cj * nx + ci));
+      const unsigned dst = rowb_base + par * (NF * BR_THREADS * 4);
+      cp_async4(dst, sa_.sell_rowbase + cb);
+      cp_async4(dst + BR_THREADS * 4, sa_.sell_rowbase + cb + 1);
+      cp_async4(dst + 2 * BR_THREADS * 4, sa_.sell_rowbase + cb + 2);
+      cp_async4(dst + 3 * BR_THREADS * 4, sa_.sell_rowbase + (ci + 1 < nx ? cb + 5 : ck * L + cj * xrow + 3 * nx));
+      cp_async4(dst + 4 * BR_THREADS * 4, sa_.sell_rowbase + (cj + 1 < ny ? cb + xrow + 1 : ck * L + ny * xrow + ci));
+      cp_async4(dst + 5 * BR_THREADS * 4, sa_.sell_rowbase + (ck + 1 < nz ? cb + L : nz * L + cj * nx + ci));
     }
+    cp_async_commit();
   };
+  unsigned par = 0;  // parity of the brick in this CTA's sequence: which row-base buffer is its own
 
   while (true) {
     if (!mbar_wait<false>(bar_full, phase, a.error_flag)) return;
@@ -736,7 +764,7 @@ k_hybrid_setup_brick(mimpy_mesh_view m, int flags, UniArgs a, SetupArgs sa_, B3G
     const int bi = ids.y & 1023, bj = (ids.y >> 10) & 1023, bk = ids.y >> 20;
     const int bn = ids.z, nbi = ids.w & 1023, nbj = (ids.w >> 10) & 1023, nbk = ids.w >> 20;
     if (first_brick) {
-      prefetch(bi, bj, bk, mult, cdiag, rowb);
+      prefetch(bi, bj, bk, mult, cdiag, par);
       first_brick = false;
     }
     const int ci0 = bi * BX, cj0 = bj * BY, ck0 = bk * BZ;
@@ -803,26 +831,26 @@ k_hybrid_setup_brick(mimpy_mesh_view m, int flags, UniArgs a, SetupArgs sa_, B3G
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty);  // the input stage goes back to the producer
 
+    // this brick's row bases have landed (their copies were issued a whole brick ago); then the next brick's
+    cp_async_wait_all();
     double mult_n = 1., cdiag_n = 0.;
-    int rowb_n[NF];
-    if (bn < g.total) prefetch(nbi, nbj, nbk, mult_n, cdiag_n, rowb_n);
+    if (bn < g.total) prefetch(nbi, nbj, nbk, mult_n, cdiag_n, par ^ 1u);
 
     // A REGULAR cell: its six faces are flux DOFs shared with a cell whose six faces are flux DOFs as well (no
     // boundary, no Neumann face in reach).  A warp of regular cells takes the instantiation without masks,
     // selects and popcounts: every row position is its index in the merged list (88 % of the cells at 256^3).
+    // A brick of 128 regular cells (SELL layout) sends its face-system entries through an IMAGE in shared memory.
     bool mine_regular = ok;
-    unsigned long long other[NF];
-    double diag_half[NF];
-    int diag_at[NF];
 #pragma unroll
-    for (int i = 0; i < NF; ++i) {
-      mine_regular = mine_regular && mp[i] == 0x7FFu;
-      other[i] = AU_SENTINEL;
-      diag_half[i] = 0.;
-      diag_at[i] = 0;
-    }
-    auto body = [&](auto tag) {
+    for (int i = 0; i < NF; ++i) mine_regular = mine_regular && mp[i] == 0x7FFu;
+    // (barrier: every read of the tile / image by the previous brick is done)
+    const bool brick_regular = sync_compute_and(mine_regular) && STRIDE == 32;
+    const bool warp_regular = __all_sync(0xffffffffu, mine_regular);
+    double R[NF * NF];
+    // ---- part 1: M_E, its inverse W (to the tile), aWa, the half transmissibilities ----
+    auto invert = [&](auto tag) {
       constexpr bool REG = decltype(tag)::value;
+      double rsum[NF], csum[NF];
       // faces that are no flux DOF (Neumann), and boundary faces (one cell, prescribed multiplier)
       const unsigned dropbits = REG ? 0u : (~me & 63u);
       unsigned bndbits = REG ? 0u : (~other_mask & 63u);
@@ -832,7 +860,6 @@ k_hybrid_setup_brick(mimpy_mesh_view m, int flags, UniArgs a, SetupArgs sa_, B3G
       }
       // mult * M_E acting on the outward fluxes u = sigma o v: the orientations were folded into the normals
       // (cell_prep got sigma n_f and R_f itself), so cell_core delivers M_E and not sigma_i sigma_j M_E
-      double R[NF * NF];
       cell_core<NF, METHOD>(o, trk, vol, mult, [&](int i, int j, double v) {
         const bool drop = !REG && (((dropbits >> i) | (dropbits >> j)) & 1u);
         R[i * NF + j] = drop ? (i == j ? 1. : 0.) : v;
@@ -859,7 +886,6 @@ k_hybrid_setup_brick(mimpy_mesh_view m, int flags, UniArgs a, SetupArgs sa_, B3G
         }
         R[k * NF + k] = pinv;
       }
-      double rsum[NF], csum[NF];
 #pragma unroll
       for (int i = 0; i < NF; ++i) rsum[i] = csum[i] = 0.;
 #pragma unroll
@@ -886,77 +912,155 @@ k_hybrid_setup_brick(mimpy_mesh_view m, int flags, UniArgs a, SetupArgs sa_, B3G
           tp[i >> 1] = make_double2((REG || ((me >> i) & 1u)) ? R[i * NF + i] : 0.,
                                     (REG || ((me >> (i + 1)) & 1u)) ? R[(i + 1) * NF + i + 1] : 0.);
       }
+      // entry (i, j) of the cell's contribution to the face system: aWa[i,j] - rsum[i] csum[j] / S (identity rows
+      // and columns for boundary faces, whose multiplier is prescribed)
 #pragma unroll
-      for (int j = 0; j < NF; ++j) csum[j] *= inv_s;  // entry (i, j) = aWa[i,j] - rsum[i] csum[j] / S
+      for (int j = 0; j < NF; ++j) csum[j] *= inv_s;
 #pragma unroll
-      for (int i = 0; i < NF; ++i) {
-        if (!REG && rowb[i] < 0) continue;
-        double* const rowp = sa_.a_vals + rowb[i];
+      for (int i = 0; i < NF; ++i)
 #pragma unroll
         for (int j = 0; j < NF; ++j) {
-          if (!REG && !((me >> j) & 1u)) continue;
           double v = fma(-rsum[i], csum[j], R[i * NF + j]);
           if (!REG && (((bndbits >> i) | (bndbits >> j)) & 1u)) v = (i == j) ? 1. : 0.;
-          const int pos = REG ? merged_index(i, j) : __popc(mp[i] & ((1u << merged_index(i, j)) - 1u));
-          if (i != j) {
-            rowp[pos * STRIDE] = v;
-          } else if (!REG && !((other_mask >> i) & 1u)) {
-            rowp[pos * STRIDE] = v;  // the only local cell of the face
-          } else {
-            // the two cells of a face swap their halves of the diagonal through the face's exchange slot
-            // (all-sentinel between launches): the second to arrive writes half + half and restores the
-            // sentinel -- commutative, so the value does not depend on the arrival order; nobody waits
-            // (the answers are collected after the copy-out of W: six round trips to L2 in flight at once)
-            diag_half[i] = v;
-            diag_at[i] = rowb[i] + pos * STRIDE;
-            other[i] = atomicExch(reinterpret_cast<unsigned long long*>(a.diag_pub) + fid[i],
-                                  (unsigned long long)__double_as_longlong(v));
-          }
+          R[i * NF + j] = v;
         }
-      }
     };
-    if (__all_sync(0xffffffffu, mine_regular))
-      body(std::true_type{});
+    if (warp_regular)
+      invert(std::true_type{});
     else if (ok)
-      body(std::false_type{});
+      invert(std::false_type{});
     sync_compute();
     // copy-out of W: an x-run of 8 cells is one contiguous piece of w_e (288 doubles): warp w streams the runs
     // 4w .. 4w+3, nine coalesced passes each; element e = lane + 32 p of a run is entry e % 36 of cell e / 36
     {
       const int runlen = min(BX, nx - ci0);
-      int wo[9];
-#pragma unroll
-      for (int p = 0; p < 9; ++p) {
-        const int e = lane + 32 * p, c8 = (e * 57) >> 11;  // e / 36 for e < 288
-        wo[p] = (c8 < runlen) ? (e - 36 * c8) * HS_LD + c8 : -1;
-      }
-#pragma unroll
+#pragma unroll 1
       for (int rr = 0; rr < 4; ++rr) {
         const int r = warp * 4 + rr;
         const long long c0 = s_cell0[r];
         if (c0 < 0) continue;
         double* dst = sa_.w_e + c0 * (NF * NF) + lane;
         const double* src = tile + r * BX;
+        if (runlen == BX) {
 #pragma unroll
-        for (int p = 0; p < 9; ++p)
-          if (wo[p] >= 0) dst[32 * p] = src[wo[p]];
+          for (int p = 0; p < 9; ++p) dst[32 * p] = src[s_wo[32 * p + lane]];
+        } else {
+          for (int e = lane; e < runlen * NF * NF; e += 32) dst[e - lane] = src[s_wo[e]];
+        }
       }
     }
-    // diagonals: the second cell to arrive at a face finds the other's half, writes the sum and leaves the slot clean
+    // ---- part 2: the face-system entries a W a - r c^T / S ----
+    int rowb[NF];  // (read here, not before the elimination: six registers less across it)
 #pragma unroll
-    for (int i = 0; i < NF; ++i) {
-      if (other[i] != AU_SENTINEL) {
-        sa_.a_vals[diag_at[i]] = __longlong_as_double((long long)other[i]) + diag_half[i];
-        reinterpret_cast<unsigned long long*>(a.diag_pub)[fid[i]] = AU_SENTINEL;
+    for (int i = 0; i < NF; ++i) rowb[i] = s_rowb[(par * NF + i) * BR_THREADS + t];
+    auto face_id = [&](int i) {  // global id of face i of the cell (HexMesh numbering, hexmesh.py:161-234)
+      return i < 3 ? cbase + i
+                   : i == 3 ? (ci + 1 < nx ? cbase + 5 : ck * L + cj * xrow + 3 * nx)
+                            : i == 4 ? (cj + 1 < ny ? cbase + xrow + 1 : ck * L + ny * xrow + ci)
+                                     : (ck + 1 < nz ? cbase + L : nz * L + cj * nx + ci);
+    };
+    if (!brick_regular) {
+      // straight to memory, row by row: position by popcount over the merged face list (constant for a regular cell)
+      auto scatter = [&](auto tag) {
+        constexpr bool REG = decltype(tag)::value;
+#pragma unroll
+        for (int i = 0; i < NF; ++i) {
+          if (!REG && rowb[i] < 0) continue;
+          double* const rowp = sa_.a_vals + rowb[i];
+#pragma unroll
+          for (int j = 0; j < NF; ++j) {
+            if (!REG && !((me >> j) & 1u)) continue;
+            const double v = R[i * NF + j];
+            const int pos = REG ? merged_index(i, j) : __popc(mp[i] & ((1u << merged_index(i, j)) - 1u));
+            if (i != j) {
+              rowp[pos * STRIDE] = v;
+            } else if (!REG && !((other_mask >> i) & 1u)) {
+              rowp[pos * STRIDE] = v;  // the only local cell of the face
+              sa_.dhalf[face_id(i)] = 0.;
+            } else if (i >= 3) {
+              rowp[pos * STRIDE] = v;  // a face with two cells: the half of the lower cell goes to the slot,
+            } else {
+              sa_.dhalf[face_id(i)] = v;   // the half of the upper cell to a per-face array; k_diag_finish adds them
+            }
+          }
+        }
+      };
+      if (warp_regular)
+        scatter(std::true_type{});
+      else if (ok)
+        scatter(std::false_type{});
+    } else {
+      // Regular brick, SELL-32: entry k of the 24 consecutive face rows of an x-run is ONE contiguous piece of the
+      // value array (two where the run straddles a slice), but the 8-byte stores of the scatter above reach it from
+      // 36 different instructions: 16 sectors per request, every sector written four times (1.9 of the kernel's
+      // 4.3 ms at 256^3).  The entries are laid out in shared memory as the array has them -- image[run][k][row],
+      // k = 11: the upper cells' halves of the diagonals, bound for dhalf -- and streamed out with consecutive lanes
+      // on consecutive values.  Rows on the brick's upper surfaces belong to other runs / bricks: stored directly.
+      sync_compute();  // the copy-out has read the tile, which the image overlays
+      double* img = tile;
+      const int ib = run * HS_IMG_RUN + 3 * li;
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        const bool inside = i < 3 || (i == 3 ? li < BX - 1 : i == 4 ? lj < BY - 1 : lk < BZ - 1);
+        const int tb = i < 3 ? ib + i : i == 3 ? ib + 5 : i == 4 ? ib + HS_IMG_RUN + 1 : ib + BY * HS_IMG_RUN;
+        if (inside) {
+#pragma unroll
+          for (int j = 0; j < NF; ++j) {
+            const int k = (i == j && i < 3) ? 11 : merged_index(i, j);
+            img[tb + k * HS_IMG_K] = R[i * NF + j];
+          }
+        } else {
+          double* const rowp = sa_.a_vals + rowb[i];
+#pragma unroll
+          for (int j = 0; j < NF; ++j) rowp[merged_index(i, j) * 32] = R[i * NF + j];
+        }
+      }
+      if (li == 0) {
+        s_rb0[run] = rowb[0];
+        s_cb0[run] = cbase;
+      }
+      if (li == BX - 1) s_rbl[run] = rowb[2] - 23;
+      sync_compute();
+      // stream-out: lane = row of the run, one pass per entry k (lanes 24-31 idle).  A slot whose entry comes from the
+      // LOWER cell of its face is only there when that cell belongs to the brick (z-: lk > 0, y-: lj > 0, x-: not the
+      // first cell of the run); the merged positions of those entries (and 5, the diagonal) per face type:
+      const int q = (lane * 11) >> 5, d = lane - 3 * q;  // row = 3 q + d for lane < 24
+      const unsigned lower = d == 0 ? 0x03Fu : d == 1 ? 0x22Fu : 0x2A7u;
+#pragma unroll 1
+      for (int rr = 0; rr < 4; ++rr) {
+        const int r = warp * 4 + rr;
+        const bool lower_absent = d == 0 ? (r >> 2) == 0 : d == 1 ? (r & 3) == 0 : q == 0;
+        const unsigned there = lane < 24 ? (lower_absent ? ~lower & 0x7FFu : 0x7FFu) : 0u;
+        const int rb0 = s_rb0[r];
+        double* const dst = sa_.a_vals + ((lane < 32 - (rb0 & 31)) ? rb0 : s_rbl[r]) + lane;
+        const double* src = img + r * HS_IMG_RUN + lane;
+#pragma unroll
+        for (int k = 0; k < 11; ++k)
+          if ((there >> k) & 1u) dst[32 * k] = src[HS_IMG_K * k];
+        if (lane < 24) sa_.dhalf[s_cb0[r] + lane] = src[HS_IMG_K * 11];
       }
     }
     if (bn >= g.total) break;
-    sync_compute();  // the tile is free for the next brick
     mult = mult_n;
     cdiag = cdiag_n;
-#pragma unroll
-    for (int i = 0; i < NF; ++i) rowb[i] = rowb_n[i];
+    par ^= 1u;
   }
+}
+
+// the diagonal of the face system: half of the lower cell (already in its slot) + half of the upper cell; the Jacobi
+// diagonal with it (INVERT = false: not inverted yet -- the interface rows of a slab partition are completed first)
+template <bool INVERT>
+__global__ void __launch_bounds__(256)
+k_diag_finish(int nf, const int* __restrict__ f2f, const int* __restrict__ rowbase, const uint8_t* __restrict__ diag_pos,
+              int stride, const double* __restrict__ dhalf, double* __restrict__ a_vals, double* __restrict__ dinv) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  const int g = f2f[f];
+  if (g < 0) return;
+  double* slot = a_vals + rowbase[f] + (int)diag_pos[g] * stride;
+  const double d = *slot + dhalf[f];
+  *slot = d;
+  dinv[g] = INVERT ? 1.0 / d : d;
 }
 
 // per-face base of the face-system row: SELL-32 slot of entry 0, or the CSR offset
@@ -986,8 +1090,8 @@ int mimpy_face_rowbase(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_
 template <int METHOD, int STRIDE>
 static int launch_setup_brick(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int flags, const UniArgs& a, const SetupArgs& sa,
                               const B3Geo& g, long long grid) {
-  CUDA_TRY(cudaFuncSetAttribute(k_hybrid_setup_brick<METHOD, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B3_SMEM));
-  k_hybrid_setup_brick<METHOD, STRIDE><<<(unsigned)grid, B3_THREADS, B3_SMEM, ctx->stream>>>(*mesh, flags, a, sa, g);
+  CUDA_TRY(cudaFuncSetAttribute(k_hybrid_setup_brick<METHOD, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HS_SMEM));
+  k_hybrid_setup_brick<METHOD, STRIDE><<<(unsigned)grid, B3_THREADS, HS_SMEM, ctx->stream>>>(*mesh, flags, a, sa, g);
   KERNEL_CHECK();
   return MIMPY_OK;
 }
@@ -997,8 +1101,8 @@ static int b3_geometry(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, int bk_begin
 // Face-system set-up on the pipelined brick kernel; MIMPY_E_UNSUPPORTED when it does not apply.
 int mimpy_hybrid_setup_brick(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym, int method, int flags,
                              const double* multipliers, double alpha, const double* c_diag, const int* face_rowbase,
-                             int row_stride, double* w_e, double* tau, double* a_vals) {
-  if (!mimpy_brick3_applies(mesh, sym, method, flags) || !face_rowbase) return MIMPY_E_UNSUPPORTED;
+                             int row_stride, double* w_e, double* tau, double* a_vals, double* a_diag, int invert_diag) {
+  if (!mimpy_brick3_applies(mesh, sym, method, flags) || !face_rowbase || !a_diag || !sym->diag_pos) return MIMPY_E_UNSUPPORTED;
   int rc = bind_plan(ctx, mesh, sym);
   if (rc) return rc;
   B3Geo g;
@@ -1007,14 +1111,13 @@ int mimpy_hybrid_setup_brick(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const 
   if (rc) return rc;
   if (grid == 0) return MIMPY_OK;
   if (row_stride != 32 && row_stride != 1) return MIMPY_E_UNSUPPORTED;
-  // exchange slots of the two-contributor diagonals (shared with the assembly kernels; all-sentinel between launches)
-  rc = mimpy_swap_prepare(ctx, mesh, false, 0, 0);
+  void* dhalf = nullptr;  // per-face scratch of the two-contributor diagonals (every slot is written by the kernel)
+  rc = mimpy_scratch(ctx, sizeof(double) * (size_t)mesh->nf, &dhalf);
   if (rc) return rc;
   UniArgs a = {};
   a.multipliers = multipliers;
   a.c_diag = c_diag;
   a.alpha = alpha;
-  a.diag_pub = ctx->diag_swap;
   a.ticket = ctx->counters + 12;
   a.error_flag = ctx->counters + 9;
   a.flux_dof = sym->flux_dof;
@@ -1026,13 +1129,22 @@ int mimpy_hybrid_setup_brick(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const 
   sa.w_e = w_e;
   sa.tau = tau;
   sa.a_vals = a_vals;
+  sa.dhalf = static_cast<double*>(dhalf);
 #define SETUP_LAUNCH(M)                                                                        \
   (row_stride == 32 ? launch_setup_brick<M, 32>(ctx, mesh, flags, a, sa, g, grid)               \
                     : launch_setup_brick<M, 1>(ctx, mesh, flags, a, sa, g, grid))
-  if (method == 0) return SETUP_LAUNCH(0);
-  if (method == 1) return SETUP_LAUNCH(1);
-  return SETUP_LAUNCH(6);
+  rc = method == 0 ? SETUP_LAUNCH(0) : method == 1 ? SETUP_LAUNCH(1) : SETUP_LAUNCH(6);
 #undef SETUP_LAUNCH
+  if (rc) return rc;
+  const int blocks = (mesh->nf + 255) / 256;
+  if (invert_diag)
+    k_diag_finish<true><<<blocks, 256, 0, ctx->stream>>>(mesh->nf, sym->face_to_flux, face_rowbase, sym->diag_pos, row_stride,
+                                                        sa.dhalf, a_vals, a_diag);
+  else
+    k_diag_finish<false><<<blocks, 256, 0, ctx->stream>>>(mesh->nf, sym->face_to_flux, face_rowbase, sym->diag_pos, row_stride,
+                                                         sa.dhalf, a_vals, a_diag);
+  KERNEL_CHECK();
+  return MIMPY_OK;
 }
 
 static int b3_ctas_per_sm() {

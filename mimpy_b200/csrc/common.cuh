@@ -70,7 +70,7 @@ int mimpy_numeric_uniform(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mim
 int mimpy_face_rowbase(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym, const int* sell_ptr, int* out);
 int mimpy_hybrid_setup_brick(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym, int method, int flags,
                              const double* multipliers, double alpha, const double* c_diag, const int* face_rowbase,
-                             int row_stride, double* w_e, double* tau, double* a_vals);
+                             int row_stride, double* w_e, double* tau, double* a_vals, double* a_diag, int invert_diag);
 // assemble_uniform.cu: exchange slots of the two-contributor diagonals, clean (all-sentinel) for the launch to come
 int mimpy_swap_prepare(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, bool ranged, int layer_begin, int layer_end);
 int mimpy_scratch(mimpy_ctx* ctx, size_t bytes, void** out);

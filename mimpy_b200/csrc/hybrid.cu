@@ -403,28 +403,25 @@ int mimpy_b200_hybrid_setup_fused(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, c
   HybArgs h = make_hyb(sym, alpha, c_diag);
   h.sell_ptr = sell_ptr;
   // structured hex meshes: the pipelined brick kernel (bulk-copy staging, closed-form positions; the two halves
-  // of a diagonal entry meet in an exchange slot, so no slot is zeroed first and nothing is added atomically)
+  // of a diagonal entry are added by a finishing pass that also writes the Jacobi diagonal: no slot is zeroed
+  // first and nothing is added atomically)
   bool done = false;
   if (face_rowbase_work && !getenv("MIMPY_B200_SETUP_OLD")) {
     int rc = mimpy_face_rowbase(ctx, mesh, sym, sell_ptr, face_rowbase_work);
     if (rc) return rc;
     rc = mimpy_hybrid_setup_brick(ctx, mesh, sym, method, flags, multipliers, alpha, c_diag, face_rowbase_work,
-                                  sell_ptr ? 32 : 1, w_e, tau_out, a_vals);
+                                  sell_ptr ? 32 : 1, w_e, tau_out, a_vals, a_diag_inv, ctx->world > 1 ? 0 : 1);
     if (rc == MIMPY_OK) done = true;
     else if (rc != MIMPY_E_UNSUPPORTED) return rc;
   }
   if (done) {
     if (F > 0) {
       if (ctx->world > 1) {  // slab partition: the diagonal of an interface row is the sum of both ranks' halves
-        k_diag_inv<false><<<(F + 255) / 256, 256, 0, st>>>(F, h, sym->diag_pos, a_vals, a_diag_inv);
-        KERNEL_CHECK();
         int rc = mimpy_halo_exchange_add(ctx, a_diag_inv);
         if (rc) return rc;
         k_invert<<<(F + 255) / 256, 256, 0, st>>>(F, a_diag_inv);
-      } else {
-        k_diag_inv<true><<<(F + 255) / 256, 256, 0, st>>>(F, h, sym->diag_pos, a_vals, a_diag_inv);
+        KERNEL_CHECK();
       }
-      KERNEL_CHECK();
     }
     if (tau_written_host) *tau_written_host = tau_out ? 1 : 0;
     return MIMPY_OK;

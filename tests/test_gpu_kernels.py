@@ -684,7 +684,7 @@ def test_auxmg_preconditioner_vs_spsolve_and_jacobi(ctx, dims, alpha):
         assert ia.iterations < ij.iterations
 
 
-@pytest.mark.parametrize("dims", [(11, 7, 5), (12, 6, 9), (18, 5, 4)])
+@pytest.mark.parametrize("dims", [(11, 7, 5), (12, 6, 9), (18, 5, 4), (32, 16, 12), (26, 14, 13)])
 @pytest.mark.parametrize("method", [0, 1, 6])
 @pytest.mark.parametrize("layout", ["sell", "csr"])
 def test_fused_hex_setup_equals_two_step_setup(ctx, method, layout, dims):
@@ -692,7 +692,8 @@ def test_fused_hex_setup_equals_two_step_setup(ctx, method, layout, dims):
     system, W_E blocks and Jacobi diagonal as local_matrices + hybrid_setup: Neumann faces, per-cell
     multipliers, an accumulation diagonal and k_unity included; other meshes fall back.  Odd nx: the
     thread-per-cell kernel of hybrid.cu; even nx: the pipelined brick kernel (assemble_brick3.cu), which also
-    hands the half transmissibilities to the multigrid set-up."""
+    hands the half transmissibilities to the multigrid set-up.  The two largest meshes hold REGULAR bricks (128
+    cells away from every boundary), whose entries leave through the shared-memory image, next to partial ones."""
     import torch
     from mimpy_b200 import device
 
