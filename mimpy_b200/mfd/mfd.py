@@ -142,6 +142,19 @@ class MFD(object):
             out[c] = forcing_function(cen[c]) * vol[c]
         self.cell_forcing_function = out
 
+    def apply_forcing_from_grad(self, grad_p):
+        """Source term of a cell from the exact flux through its faces (mfd.py:1178-1192), vectorised over the
+        faces: F_c += sum_f sigma_f a_f grad_p(x_f) . n_f"""
+        m = self.mesh
+        nf = m.get_number_of_faces()
+        flux = np.array([np.dot(grad_p(m.get_face_real_centroid(f)), m.get_face_normal(f)) for f in range(nf)])
+        flux *= np.asarray(m.face_areas[:nf])
+        ptr, data = m.cells.compact()
+        sigma = np.asarray(m.cell_normal_orientation.compact()[1], dtype=float)
+        contrib = flux[np.asarray(data)] * sigma
+        cells = np.repeat(np.arange(m.get_number_of_cells()), np.diff(ptr))
+        np.add.at(self.cell_forcing_function, cells, contrib)
+
     def apply_forcing_from_array(self, values):
         """Extension: f sampled at the cell centroids, as an array (no Python callback per cell)."""
         nc = self.mesh.get_number_of_cells()
@@ -235,6 +248,39 @@ class MFD(object):
         if not k_unity:
             n = n @ m.get_cell_k(cell_index).T
         return n * s[:, None]
+
+    def build_c_e(self, n_e):
+        """Orthonormal basis of null(N_E^T) from the SVD (mfd.py:314-322); the device kernels only ever need
+        C_E C_E^T = I - Q Q^T and build Q by CholeskyQR2 instead."""
+        _, _, v = np.linalg.svd(np.transpose(n_e))
+        return np.transpose(v)[:, 3:]
+
+    def build_d_e(self, n_e):
+        """mfd.py:324-336 (the same null-space basis; two-dimensional meshes keep one more column)."""
+        _, _, v = np.linalg.svd(np.transpose(n_e))
+        return np.transpose(v)[:, (3 if self.mesh.dim == 3 else 2):]
+
+    def build_w_e(self, cell_index):
+        """W_E of Brezzi et al. (mfd.py:338-355); method 4 inverts it (on the device for whole meshes)."""
+        r_e = self.build_r_e(cell_index)
+        n_e = self.build_n_e(cell_index)
+        d_e = self.build_d_e(r_e)
+        current_k = self.mesh.get_cell_k(cell_index)
+        w_e = n_e.dot(np.linalg.inv(n_e.T.dot(r_e)).dot(n_e.T))
+        w_e += d_e.dot(d_e.T)
+        w_e *= np.trace(current_k)
+        w_e /= self.mesh.get_cell_volume(cell_index)
+        return w_e
+
+    def proj_vector(self, vector_f):
+        """Per cell, the normal components sigma n_f . F(x_f) of a vector field at the face centroids
+        (mfd.py:601-616)."""
+        m = self.mesh
+        out = []
+        for cell_index in range(m.get_number_of_cells()):
+            out.append([vector_f(m.get_face_real_centroid(f)).dot(m.get_face_normal(f) * o)
+                        for f, o in zip(m.get_cell(cell_index), m.get_cell_normal_orientation(cell_index))])
+        return out
 
     def build_m_e(self, cell_index, k_unity=False):
         """The n_E x n_E block of one cell (computed for all cells on the GPU, then sliced)."""
@@ -368,6 +414,20 @@ class MFD(object):
                                            self.cell_forcing_function)
         self.rhs = device.to_host(self.ctx, self.device_rhs)
         return self.rhs
+
+    # the three parts of build_rhs (mfd.py:1027-1041, 1209-1215) on the host vector self.rhs, for callers that
+    # compose a right-hand side themselves; build_rhs itself runs them fused on the device
+    def build_rhs_forcing(self):
+        self.rhs[self.flux_dof:self.flux_dof + self.mesh.get_number_of_cells()] += \
+            np.asarray(self.cell_forcing_function)[:self.mesh.get_number_of_cells()]
+
+    def build_rhs_neumann(self):
+        for boundary_index, boundary_value in self.get_neumann_boundary_values():
+            self.rhs[self.face_to_flux[boundary_index, 0]] = boundary_value   # (g = -1: the last entry, like the reference)
+
+    def build_rhs_dirichlet(self):
+        for boundary_index, boundary_value in self.get_dirichlet_boundary_values():
+            self.rhs[self.face_to_flux[boundary_index, 0]] = -boundary_value
 
     def add_gravity(self):
         """rhs[f] += (M_{K=I} g)_f with g_f = rho * |g| * (e_g . n_f) (mfd.py:1001-1025), computed on the device:
@@ -520,6 +580,32 @@ class MFD(object):
         p = self.solution[m.get_number_of_faces():m.get_number_of_faces() + nc] if self.flux_dof == m.get_number_of_faces() \
             else self.get_pressure_solution()
         return np.sqrt(np.sum(m.cell_volume[:nc] * (p - exact) ** 2))
+
+    def l2_error_velocity_per_cell(self, grad_p):
+        """Relative velocity error per cell (mfd.py:1245-1271; the reference's last line takes the square root of
+        the whole vector inside the loop -- the per-cell value is what it means)."""
+        m = self.mesh
+        out = np.zeros(m.get_number_of_cells())
+        for c in range(m.get_number_of_cells()):
+            num = den = 0.
+            for f in m.get_cell(c):
+                exact = np.dot(grad_p(m.get_face_real_centroid(f)), m.get_face_normal(f))
+                num += m.get_cell_volume(c) * (self.get_velocity_solution_by_index(f) - exact) ** 2
+                den += m.get_cell_volume(c) * exact ** 2
+            out[c] = np.sqrt(num / den) if den > 0. else 0.
+        return out
+
+    def compute_x_error_velocity(self, grad_p):
+        """||| grad_p^I - v_h |||_X with the assembled M block (mfd.py:1301-1319); like the reference it addresses
+        the solution by face index, i.e. it is meant for systems without Neumann faces."""
+        m = self.mesh
+        nf = m.get_number_of_faces()
+        diff = np.zeros(nf + m.get_number_of_cells())
+        for f in range(nf):
+            diff[f] = np.dot(grad_p(m.get_face_real_centroid(f)), m.get_face_normal(f)) - self.solution[f]
+        lhs = self.lhs.tocsr() if hasattr(self.lhs, "tocsr") else self.lhs
+        err = lhs.dot(diff)[:nf].dot(diff[:nf])
+        return np.sqrt(err)
 
     def compute_l2_error_velocity(self, grad_p, quadrature_method=0):
         m = self.mesh

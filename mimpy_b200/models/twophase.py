@@ -155,6 +155,9 @@ class TwoPhase(object):
         self.initial_p_o = p_o
         self.current_p_o = p_o
 
+    def set_initial_u_t(self, u_t):
+        raise Exception("deprecated use of intialize u_t")   # twophase.py:353-357: the reference refuses it as well
+
     def set_initial_s_w(self, s_w):
         self.initial_s_w = s_w
         self.current_s_w = s_w

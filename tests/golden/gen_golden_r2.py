@@ -154,8 +154,84 @@ def cut_checker(ref, n):
     return d
 
 
+def mfd_helpers(ref):
+    """The small MFD helpers a script may call directly (mfd.py:314-355 build_c_e / build_d_e / build_w_e, 601-616
+    proj_vector, 1027-1041 + 1209-1215 the three parts of build_rhs, 1178-1192 apply_forcing_from_grad, 1301-1319
+    compute_x_error_velocity) on a full-tensor 4x3x2 box, Dirichlet everywhere."""
+    ktab = g1.spd_tensors(24, 9, full=True)
+    mesh = g1.ref_hex(ref, 4, 3, 2, (2., 1.5, 1.), ktab)
+    grad = lambda p: np.array([2. * p[0] + .3, -1. + p[2], .5 * p[1]])
+    f = ref.mfd.MFD()
+    f.set_m_e_construction_method(1)
+    f.set_mesh(mesh)
+    for b in range(6):
+        f.apply_dirichlet_from_function(b, lambda p: 1. + p[0] - 2. * p[2] + p[0] * p[1])
+    f.apply_forcing_from_function(lambda p: p[0] - p[1])
+    forcing0 = np.array(f.cell_forcing_function).copy()
+    f.get_face_area = mesh.get_face_area   # mfd.py:1190 calls a getter MFD never defines (it is the mesh's)
+    f.apply_forcing_from_grad(grad)
+    d = orc.omesh_to_dict(orc.OMesh.from_mesh(mesh))
+    d["forcing_before"], d["forcing_after"] = forcing0, np.array(f.cell_forcing_function).copy()
+    d["w_e"] = np.array([f.build_w_e(c) for c in (0, 7, 23)])
+    n_e = f.build_n_e(5)
+    c_e = f.build_c_e(n_e)
+    d["n_e_5"], d["c_e_5_projector"] = n_e, c_e.dot(c_e.T)
+    d["proj"] = np.array(f.proj_vector(grad))
+    g1.quiet(f.build_lhs)
+    d["rhs"] = f.build_rhs().copy()
+    f.solve()
+    d["solution"] = np.array(f.solution)
+    d["x_error"] = np.float64(f.compute_x_error_velocity(grad))
+    d["l2_error_velocity"] = np.float64(f.compute_l2_error_velocity(grad))
+    return d
+
+
+VORO_BOX = [(0., 2.), (0., 1.5), (0., 1.)]
+
+
+def voro_k(p):
+    """Permeability of the Voronoi fixture as a function of the cell centroid (shared with the tests)."""
+    return np.diag([1. + p[0], 2. - p[1], 1. + .5 * p[2]])
+
+
+def voro_mesh(ref):
+    """VoroMesh.build_mesh (voromesh.py:19-201) on a bounded Voronoi tessellation of 48 jittered lattice points
+    (cells of 6..16 faces), written in voro++'s text format by tests/voro_util.py; the file is committed as
+    tests/golden/voro_48.vol.gz.  Dirichlet p on x-/x+, no-flow elsewhere, a source term; method 1 and the
+    shifted centroids VoroMesh switches on."""
+    import gzip
+    import voro_util
+    from mimpy.mesh import voromesh
+    path = os.path.join(g1.OUT, "voro_48.vol.gz")
+    if not os.path.exists(path):
+        txt = voro_util.voronoi_vol_text(voro_util.jittered_points(4, 4, 3, VORO_BOX, 7), VORO_BOX)
+        with gzip.GzipFile(path, "wb", mtime=0) as fh:
+            fh.write(txt.encode())
+    cwd = os.getcwd()
+    os.chdir("/tmp")   # the reference opens 'shifted_out' and 'ortho_line' for writing in the cwd
+    try:
+        with open("/tmp/voro_48.vol", "w") as fh:
+            fh.write(gzip.open(path, "rt").read())
+        mesh = voromesh.VoroMesh()
+        g1.quiet(mesh.build_mesh, "/tmp/voro_48.vol", voro_k)
+    finally:
+        os.chdir(cwd)
+    d = orc.omesh_to_dict(orc.OMesh.from_mesh(mesh))
+    d["face_shifted_centroids"] = np.array(mesh.face_shifted_centroids[:mesh.get_number_of_faces()])
+    d["cell_shifted_centroids"] = np.array(mesh.cell_shifted_centroid[:mesh.get_number_of_cells()])
+    bc = [("d", 0, lambda p: 1. + p[1]), ("d", 1, lambda p: 0.)] + [("n", b, cases.zero_flux) for b in (2, 3, 4, 5)]
+    r = g1.dump_system(ref, mesh, 1, bc, lambda p: p[0] * p[2], with_blocks=True)
+    for k_, v in r.items():
+        d["m1_%s" % k_] = v
+    return d
+
+
 def main():
     ref = ref_shim.load_reference()
+    g1.save("voro_48", voro_mesh(ref))
+    g1.save("mfd_helpers_432", mfd_helpers(ref))
+    if "--helpers-only" in sys.argv:
+        return
     g1.save("cut_checker_6", cut_checker(ref, 6))
     for name in cases.CASES:
         g1.save("twophase_" + name, twophase_history(ref, name))

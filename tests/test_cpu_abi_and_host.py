@@ -280,3 +280,26 @@ def test_vtk_writers(golden, tmp_path):
     assert t2[i] == "CELLS 3 %d" % sum(len(o.face(f)) + 1 for f in faces)
     assert t2[i + 1].split() == [str(len(o.face(0)))] + [str(int(q)) for q in o.face(0)]
     assert t2[i + 4:i + 8] == ["CELL_TYPES 3", "7", "7", "7"]
+
+
+def test_voromesh_reads_voro_file_like_reference(golden):
+    """VoroMesh.build_mesh is host code: the mesh read from the voro++-format fixture equals the reference's
+    (voromesh.py:19-201) point by point, face by face, cell by cell -- no GPU involved."""
+    import os
+    from oracle import mimpy_oracle as orc
+    import mimpy_b200.mesh.voromesh as voromesh
+
+    g = golden("voro_48")
+    ref = orc.omesh_from_dict(g)
+    mesh = voromesh.VoroMesh()
+    mesh.build_mesh(os.path.join(os.path.dirname(__file__), "golden", "voro_48.vol.gz"),
+                    lambda p: np.diag([1. + p[0], 2. - p[1], 1. + .5 * p[2]]))
+    o = orc.OMesh.from_mesh(mesh)
+    for k in ("points", "face_ptr", "face_points", "cell_ptr", "cell_faces", "cell_sigma", "face_normals", "face_areas",
+              "face_to_cell", "cell_volume", "cell_centroid", "cell_k"):
+        assert np.array_equal(getattr(o, k), getattr(ref, k)), k
+    assert np.allclose(o.face_centroids, ref.face_centroids, rtol=0, atol=1e-14)
+    assert np.allclose(o.face_shifted_centroids, g["face_shifted_centroids"], rtol=0, atol=1e-14)   # (boundary faces: find_face_centroid)
+    assert np.array_equal(o.cell_shifted_centroids, g["cell_shifted_centroids"])
+    assert {m: [(int(a), int(b)) for a, b in v] for m, v in o.boundary_faces.items()} == ref.boundary_faces
+    assert abs(o.cell_volume.sum() - 3.0) < 1e-12

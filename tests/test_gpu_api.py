@@ -379,6 +379,99 @@ def test_add_gravity_matches_reference(golden):
         f2.add_gravity()
 
 
+def test_voromesh_matches_reference(golden):
+    """VoroMesh.build_mesh (voromesh.py:19-201) on a voro++-format file of 48 Voronoi cells with 6..16 faces: the mesh
+    equals the reference's array by array (shifted centroids included), and the generic lane-group kernels
+    (16 lanes per cell here) reproduce its M_E blocks, saddle matrix, right-hand side and solution."""
+    import os
+    import mimpy_b200.mesh.voromesh as voromesh
+    import mimpy_b200.mfd.mfd as mfd
+
+    g = golden("voro_48")
+    ref = orc.omesh_from_dict(g)
+    mesh = voromesh.VoroMesh()
+    mesh.build_mesh(os.path.join(os.path.dirname(__file__), "golden", "voro_48.vol.gz"),
+                    lambda p: np.diag([1. + p[0], 2. - p[1], 1. + .5 * p[2]]))
+    assert_mesh_equals_reference(mesh, ref, geometry_exact=False)
+    nf, nc = mesh.get_number_of_faces(), mesh.get_number_of_cells()
+    assert mesh.is_using_face_shifted_centroid() and mesh.is_using_cell_shifted_centroid()
+    assert np.allclose(mesh.face_shifted_centroids[:nf], g["face_shifted_centroids"], rtol=0, atol=1e-14)
+    assert np.array_equal(mesh.cell_shifted_centroid[:nc], g["cell_shifted_centroids"])
+    n_e = np.diff(ref.cell_ptr)
+    assert n_e.min() == 6 and n_e.max() == 16
+    f = mfd.MFD()
+    f.set_m_e_construction_method(1)
+    f.set_mesh(mesh)
+    f.apply_dirichlet_from_function(0, lambda p: 1. + p[1])
+    f.apply_dirichlet_from_function(1, lambda p: 0.)
+    for b in (2, 3, 4, 5):
+        f.apply_neumann_from_function(b, zero_flux)
+    f.apply_forcing_from_function(lambda p: p[0] * p[2])
+    blocks = np.concatenate([f.build_m_e(c).ravel() for c in range(nc)])
+    assert abs(blocks - g["m1_m_e_flat"]).max() <= 1e-11 * abs(g["m1_m_e_flat"]).max()
+    f.build_lhs()
+    assert np.array_equal(f.face_to_flux[:, 0], g["m1_face_to_flux"]) and f.flux_dof == int(g["m1_flux_dof"])
+    n = f.flux_dof + nc
+    ours = f.lhs.tocsr()
+    theirs = sparse.csr_matrix((g["m1_csr_data"], g["m1_csr_indices"], g["m1_csr_indptr"]), shape=(n, n))
+    assert abs(ours - theirs).max() <= 1e-11 * abs(theirs).max()
+    assert np.allclose(f.build_rhs(), g["m1_rhs"], rtol=1e-12, atol=1e-15)
+    sol = f.solve()
+    assert np.linalg.norm(sol - g["m1_solution"]) <= 1e-8 * np.linalg.norm(g["m1_solution"])
+
+
+def test_mfd_helper_methods_match_reference(golden):
+    """The small MFD helpers a script may call directly -- build_c_e / build_d_e / build_w_e (mfd.py:314-355),
+    proj_vector (:601-616), the three parts of build_rhs (:1027-1041, 1209-1215), apply_forcing_from_grad
+    (:1178-1192), compute_x_error_velocity (:1301-1319) -- against the unmodified reference."""
+    import mimpy_b200.mesh.hexmesh as hexmesh
+    import mimpy_b200.mfd.mfd as mfd
+
+    g = golden("mfd_helpers_432")
+    ref = orc.omesh_from_dict(g)
+    mesh = hexmesh.HexMesh()
+    mesh.build_mesh(4, 3, 2, 2., 1.5, 1., ref.cell_k.reshape(-1, 3, 3))
+    grad = lambda p: np.array([2. * p[0] + .3, -1. + p[2], .5 * p[1]])
+    f = mfd.MFD()
+    f.set_m_e_construction_method(1)
+    f.set_mesh(mesh)
+    for b in range(6):
+        f.apply_dirichlet_from_function(b, lambda p: 1. + p[0] - 2. * p[2] + p[0] * p[1])
+    f.apply_forcing_from_function(lambda p: p[0] - p[1])
+    assert np.allclose(f.cell_forcing_function, g["forcing_before"], rtol=1e-13, atol=0)
+    f.apply_forcing_from_grad(grad)
+    assert np.allclose(f.cell_forcing_function, g["forcing_after"], rtol=1e-12, atol=1e-15)
+    for q, c in enumerate((0, 7, 23)):
+        w = f.build_w_e(c)
+        assert abs(w - g["w_e"][q]).max() <= 1e-12 * abs(g["w_e"][q]).max()
+    # method 4 is M_E = W_E^-1 (mfd.py:420-421): the device blocks invert the host W_E
+    f4 = mfd.MFD()
+    f4.set_m_e_construction_method(4)
+    f4.set_mesh(mesh)
+    assert abs(f4.build_m_e(7) @ f.build_w_e(7) - np.eye(6)).max() <= 1e-10
+    n_e = f.build_n_e(5)
+    assert abs(n_e - g["n_e_5"]).max() <= 1e-13 * abs(g["n_e_5"]).max()
+    c_e = f.build_c_e(n_e)
+    assert c_e.shape == (6, 3) and abs(n_e.T @ c_e).max() <= 1e-12
+    assert abs(c_e @ c_e.T - g["c_e_5_projector"]).max() <= 1e-12
+    assert f.build_d_e(n_e).shape == (6, 3)
+    assert np.allclose(np.array(f.proj_vector(grad)), g["proj"], rtol=1e-12, atol=1e-14)
+    f.build_lhs()
+    rhs = f.build_rhs().copy()
+    assert np.allclose(rhs, g["rhs"], rtol=1e-12, atol=1e-15)
+    f.rhs = np.zeros_like(rhs)   # the same vector from its three parts
+    f.build_rhs_neumann()
+    f.build_rhs_dirichlet()
+    f.build_rhs_forcing()
+    assert np.array_equal(f.rhs, rhs)
+    sol = f.solve()
+    assert np.linalg.norm(sol - g["solution"]) <= 1e-8 * np.linalg.norm(g["solution"])
+    assert abs(f.compute_x_error_velocity(grad) - float(g["x_error"])) <= 1e-7 * float(g["x_error"])
+    assert abs(f.compute_l2_error_velocity(grad) - float(g["l2_error_velocity"])) <= 1e-7 * float(g["l2_error_velocity"])
+    per_cell = f.l2_error_velocity_per_cell(grad)
+    assert per_cell.shape == (24,) and np.all(np.isfinite(per_cell)) and np.all(per_cell >= 0.)
+
+
 def test_singlephase_model_matches_reference_history(golden):
     """SinglePhase (implicit compressible stepping, singlephase.py:244-299): 6 steps vs the reference."""
     import mimpy_b200.mesh.hexmesh as hexmesh
