@@ -623,15 +623,26 @@ int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
     const size_t n = (size_t)lx * ly * lz;
     return 6 * pad(n) + 2 * pad(n + 2 * (size_t)lx * ly) + 2 * pad((size_t)lx * ly);
   };
-  for (;;) {
-    if (h->nlev >= AUX_MAX_LEVELS) break;
-    AuxLevel& L = h->lev[h->nlev++];
-    L.nx = nx; L.ny = ny; L.nz = nz; L.n = nx * ny * nz;
-    total += level_doubles(nx, ny, nz);
-    if (L.n <= coarsest) break;
-    nx = (nx + 1) / 2; ny = (ny + 1) / 2; nz = (nz + 1) / 2;
+  auto build_levels = [&](int stop_at) {
+    int lx = mesh->hex_nx, ly = mesh->hex_ny, lz = mesh->hex_nz;
+    h->nlev = 0;
+    total = 0;
+    for (;;) {
+      if (h->nlev >= AUX_MAX_LEVELS) break;
+      AuxLevel& L = h->lev[h->nlev++];
+      L.nx = lx; L.ny = ly; L.nz = lz; L.n = lx * ly * lz;
+      total += level_doubles(lx, ly, lz);
+      if (L.n <= stop_at) break;
+      lx = (lx + 1) / 2; ly = (ly + 1) / 2; lz = (lz + 1) / 2;
+    }
+  };
+  build_levels(coarsest);
+  if (h->global && (h->lev[h->nlev - 1].n > coarsest || h->nlev < 2)) {
+    // a slab that is below the agglomeration threshold already (or a hierarchy that does not get there): the
+    // rank-local cycle with its own coarsest level
+    h->global = 0;
+    build_levels(AUX_COARSEST);
   }
-  if (h->global && (h->lev[h->nlev - 1].n > coarsest || h->nlev < 2)) h->global = 0;
   h->nglob = 0;
   if (h->global) {  // the agglomerated levels: the last distributed level stacked over the ranks, then coarsened
     const AuxLevel& last = h->lev[h->nlev - 1];
