@@ -82,6 +82,7 @@ struct mimpy_auxmg {
   AuxLevel32 lev32[AUX_MAX_LEVELS];
   double* sdev;  // device: [0] = s_A (power of two ~ 1 / tau of the first cells)
   float* fw32;   // FP32 copy of fw for the transfers of the FP32 cycle
+  float* dinv32; // FP32 copy of the Jacobi diagonal (fused update of p), made per solve
   double omega, scale;
   double wj;     // weight of the Jacobi term D^-1 against the auxiliary-space term
   const int* cell_faces;
@@ -327,25 +328,32 @@ __global__ void __launch_bounds__(AUX_T) k_aux_dense_inverse(AuxLevel L, double*
 // ---------------------------------------------------------------------------------------------
 // V-cycle
 // ---------------------------------------------------------------------------------------------
+// The cycle computes in the storage type of the levels: FP32 arithmetic on the FP32 mirrors (conversions to FP64 run at
+// a sixteenth of the FP32 rate and had made the level-0 kernels compute-bound: 0.31 ms for 0.5 GB), FP64 on FP64 levels.
+template <typename T>
+__device__ __forceinline__ T aux_rcp(T d) { return (T)1 / d; }
+template <>
+__device__ __forceinline__ float aux_rcp<float>(float d) { return __frcp_rn(d); }
+
 template <typename T>
 __global__ void __launch_bounds__(AUX_T) k_aux_presmooth(AuxLevelT<T> L, double omega) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < L.n) L.x[c] = (T)(omega * (double)L.b[c] / (double)L.dg[c]);
+  if (c < L.n) L.x[c] = (T)omega * L.b[c] * aux_rcp<T>(L.dg[c]);
 }
 
 template <typename T>
-__device__ __forceinline__ double aux_apply(const AuxLevelT<T>& L, const T* __restrict__ x, int c,
-                                            int i, int j, int k, double xc) {
-  double s = (double)L.dg[c] * xc;
+__device__ __forceinline__ T aux_apply(const AuxLevelT<T>& L, const T* __restrict__ x, int c,
+                                       int i, int j, int k, T xc) {
+  T s = L.dg[c] * xc;
   const int sx = 1, sy = L.nx, sz = L.nx * L.ny;
-  if (i + 1 < L.nx) s -= (double)L.tx[c] * (double)x[c + sx];
-  if (i > 0) s -= (double)L.tx[c - sx] * (double)x[c - sx];
-  if (j + 1 < L.ny) s -= (double)L.ty[c] * (double)x[c + sy];
-  if (j > 0) s -= (double)L.ty[c - sy] * (double)x[c - sy];
-  if (k + 1 < L.nz) s -= (double)L.tz[c] * (double)x[c + sz];
-  else if (L.has_hi) s -= (double)L.tzi[i + sy * j] * (double)x[L.n + sz + i + sy * j];  // cell of the rank above
-  if (k > 0) s -= (double)L.tz[c - sz] * (double)x[c - sz];
-  else if (L.has_lo) s -= (double)L.bzi[i + sy * j] * (double)x[L.n + i + sy * j];       // cell of the rank below
+  if (i + 1 < L.nx) s -= L.tx[c] * x[c + sx];
+  if (i > 0) s -= L.tx[c - sx] * x[c - sx];
+  if (j + 1 < L.ny) s -= L.ty[c] * x[c + sy];
+  if (j > 0) s -= L.ty[c - sy] * x[c - sy];
+  if (k + 1 < L.nz) s -= L.tz[c] * x[c + sz];
+  else if (L.has_hi) s -= L.tzi[i + sy * j] * x[L.n + sz + i + sy * j];  // cell of the rank above
+  if (k > 0) s -= L.tz[c - sz] * x[c - sz];
+  else if (L.has_lo) s -= L.bzi[i + sy * j] * x[L.n + i + sy * j];       // cell of the rank below
   return s;
 }
 
@@ -357,42 +365,53 @@ __global__ void __launch_bounds__(AUX_T) k_aux_restrict(AuxLevelT<T> F, AuxLevel
   const int I = c % C.nx, J = (c / C.nx) % C.ny, K = c / (C.nx * C.ny);
   const int i0 = 2 * I, j0 = 2 * J, k0 = 2 * K;
   const int i1 = min(i0 + 1, F.nx - 1), j1 = min(j0 + 1, F.ny - 1), k1 = min(k0 + 1, F.nz - 1);
-  double s = 0.;
+  T s = 0;
   for (int k = k0; k <= k1; ++k)
     for (int j = j0; j <= j1; ++j)
       for (int i = i0; i <= i1; ++i) {
         const int f = i + F.nx * (j + F.ny * k);
-        s += (double)F.b[f] - aux_apply(F, F.x, f, i, j, k, (double)F.x[f]);
+        s += F.b[f] - aux_apply(F, F.x, f, i, j, k, F.x[f]);
       }
-  C.b[c] = (T)s;
+  C.b[c] = s;
 }
 
-// x2 = xp + omega D^-1 (b - A xp),  xp = x + scale * P e_coarse   (prolongation fused into the smoother)
-template <typename T>
+// x2 = xp + omega D^-1 (b - A xp),  xp = x + scale * P e_coarse   (prolongation fused into the smoother).
+// DOT (level 0 of the fused update of p): b . x2 summed on the way (in FP64) -- the cell-space half of r . z.
+template <typename T, bool DOT>
 __global__ void __launch_bounds__(AUX_T)
-k_aux_prolong_smooth(AuxLevelT<T> F, AuxLevelT<T> C, double omega, double scale) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= F.n) return;
-  const int i = c % F.nx, j = (c / F.nx) % F.ny, k = c / (F.nx * F.ny);
+k_aux_prolong_smooth(AuxLevelT<T> F, AuxLevelT<T> C, double omega_, double scale_, double* partials, unsigned int* counter,
+                     double* dst) {
+  __shared__ double sh[32];
   const T* __restrict__ e = C.x2;
   const T* __restrict__ x = F.x;
+  const T omega = (T)omega_, scale = (T)scale_;
   const int cs_y = C.nx, cs_z = C.nx * C.ny;
-  auto xp = [&](int ii, int jj, int kk) {
-    return (double)x[ii + F.nx * (jj + F.ny * kk)] + scale * (double)e[(ii >> 1) + cs_y * (jj >> 1) + cs_z * (kk >> 1)];
-  };
-  const double xc = xp(i, j, k);
-  double s = (double)F.dg[c] * xc;
   const int sx = 1, sy = F.nx, sz = F.nx * F.ny;
-  if (i + 1 < F.nx) s -= (double)F.tx[c] * xp(i + 1, j, k);
-  if (i > 0) s -= (double)F.tx[c - sx] * xp(i - 1, j, k);
-  if (j + 1 < F.ny) s -= (double)F.ty[c] * xp(i, j + 1, k);
-  if (j > 0) s -= (double)F.ty[c - sy] * xp(i, j - 1, k);
-  const int ij = i + sy * j, cij = (i >> 1) + cs_y * (j >> 1);
-  if (k + 1 < F.nz) s -= (double)F.tz[c] * xp(i, j, k + 1);
-  else if (F.has_hi) s -= (double)F.tzi[ij] * ((double)x[F.n + sz + ij] + scale * (double)e[C.n + C.nx * C.ny + cij]);
-  if (k > 0) s -= (double)F.tz[c - sz] * xp(i, j, k - 1);
-  else if (F.has_lo) s -= (double)F.bzi[ij] * ((double)x[F.n + ij] + scale * (double)e[C.n + cij]);
-  F.x2[c] = (T)(xc + omega * ((double)F.b[c] - s) / (double)F.dg[c]);
+  double acc = 0.;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < F.n; c += gridDim.x * blockDim.x) {
+    const int i = c % F.nx, j = (c / F.nx) % F.ny, k = c / (F.nx * F.ny);
+    // the coarse cell of a neighbour is the own one, or the next one across the parity boundary
+    const int ce = (i >> 1) + cs_y * (j >> 1) + cs_z * (k >> 1);
+    const T xc = x[c] + scale * e[ce];
+    T s = F.dg[c] * xc;
+    if (i + 1 < F.nx) s -= F.tx[c] * (x[c + sx] + scale * e[ce + (i & 1)]);
+    if (i > 0) s -= F.tx[c - sx] * (x[c - sx] + scale * e[ce - ((i & 1) ^ 1)]);
+    if (j + 1 < F.ny) s -= F.ty[c] * (x[c + sy] + scale * e[ce + (j & 1) * cs_y]);
+    if (j > 0) s -= F.ty[c - sy] * (x[c - sy] + scale * e[ce - ((j & 1) ^ 1) * cs_y]);
+    const int ij = i + sy * j, cij = (i >> 1) + cs_y * (j >> 1);
+    if (k + 1 < F.nz) s -= F.tz[c] * (x[c + sz] + scale * e[ce + (k & 1) * cs_z]);
+    else if (F.has_hi) s -= F.tzi[ij] * (x[F.n + sz + ij] + scale * e[C.n + C.nx * C.ny + cij]);
+    if (k > 0) s -= F.tz[c - sz] * (x[c - sz] + scale * e[ce - ((k & 1) ^ 1) * cs_z]);
+    else if (F.has_lo) s -= F.bzi[ij] * (x[F.n + ij] + scale * e[C.n + cij]);
+    const T bc = F.b[c];
+    const T out = xc + omega * (bc - s) * aux_rcp<T>(F.dg[c]);
+    F.x2[c] = out;
+    if (DOT) acc += (double)bc * (double)out;  // (the stored, rounded value: what the prolongation will read)
+  }
+  if (DOT) {
+    const double v[1] = {acc};
+    finish_reduction<1>(v, partials, counter, dst, sh);
+  }
 }
 
 // x2 = inv_scale * cinv b  (cinv: FP64 inverse of the unscaled coarsest operator; inv_scale = 1 / s_A for the FP32 levels)
@@ -479,6 +498,15 @@ k_aux_level0_hex(AuxHex hx, const int* __restrict__ f2f, const double* __restric
   L.dd[c] = dd;
   if (c >= L.n - sz) L.tzi[c - (L.n - sz)] = 0.;
   if (c < sz) L.bzi[c] = 0.;
+}
+
+// b . x of a level of at most AUX_COARSEST cells (a mesh whose only level is the coarsest one)
+__global__ void __launch_bounds__(AUX_T) k_aux_dot32(int n, const float* __restrict__ b, const float* __restrict__ x, double* dst) {
+  __shared__ double sh[32];
+  double a = 0.;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) a += (double)b[c] * (double)x[c];
+  a = block_sum(a, sh);
+  if (threadIdx.x == 0) dst[0] = a;
 }
 
 // power of two ~ 1 / rms(r), from the device scalar ||r||^2 of the PCG (FP32 levels: the restricted residual is O(1))
@@ -578,10 +606,119 @@ static int aux_apply32(mimpy_ctx* ctx, mimpy_auxmg* h, const AuxHex& hx, const d
   }
   k_aux_coarse_solve<float><<<1, AUX_COARSEST, 0, st>>>(L[last], h->cinv, h->sdev);
   for (int l = last - 1; l >= 0; --l)
-    k_aux_prolong_smooth<float><<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], L[l + 1], h->omega, h->scale);
+    k_aux_prolong_smooth<float, false><<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], L[l + 1], h->omega, h->scale, nullptr, nullptr, nullptr);
   const int grid = ctx->sm_count * 8;
   k_aux_face_prolong<float><<<grid, RED_THREADS, 0, st>>>(hx, n_owned, h->wj, h->face_to_flux, h->fw32, L[0].x2, dinv, r, z,
                                                           ctx->partials, ctx->counters + 4, rz_dst, rr, nrows, h->sdev);
+  KERNEL_CHECK();
+  return MIMPY_OK;
+}
+
+// p = z + beta p with z = w_J D^-1 r + Pi e formed on the fly (never stored).  r . z = S_RDR + (s_A / s_b^2) S_BE is
+// complete before this kernel starts, so beta = r.z / (r.z of the previous iteration) is known to every thread; the last
+// block rotates the scalars (every block has read S_RZ by then).
+__global__ void __launch_bounds__(RED_THREADS)
+k_aux_face_prolong_p(AuxHex hx, int nf, double wj, const int* __restrict__ f2f, const float* __restrict__ fw,
+                     const float* __restrict__ e, const float* __restrict__ dinv32, const double* __restrict__ r,
+                     double* __restrict__ p, double* scal, unsigned int* counter, double nrows,
+                     const double* __restrict__ s_a, int first) {
+  const int sy = hx.nx, sz = hx.nx * hx.ny;
+  const double sb = residual_scale(scal + S_RR, nrows), sa = s_a[0];
+  const double back = sa / sb;
+  const double rz_new = scal[S_RDR] + scal[S_BE] * (sa / (sb * sb));
+  const double rz_old = scal[S_RZ];
+  const double beta = (first || rz_old == 0.) ? 0. : rz_new / rz_old;
+  // one thread per FACE (rows of p, r, D^-1 and the weights are then read and written as consecutive runs; a thread per
+  // cell touched them with a stride of three rows): the face's cell(s) from the closed-form HexMesh numbering
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
+    const int g = f2f[f];
+    if (g < 0) continue;
+    const int k = f / hx.L, rem = f - k * hx.L;
+    int c, other = -1;  // c: the cell whose z-/y-/x- face f is, or the only cell of a face on the upper boundaries
+    if (k == hx.nz) {                       // top z level: face of cell (i, j, nz-1)
+      c = rem + (hx.nz - 1) * sz;
+    } else {
+      const int j = rem / hx.xrow, r2 = rem - j * hx.xrow;
+      if (j == hx.ny) {                     // last y row of the layer: face of cell (i, ny-1, k)
+        c = r2 + (hx.ny - 1) * sy + k * sz;
+      } else if (r2 == 3 * hx.nx) {         // x+ boundary face of cell (nx-1, j, k)
+        c = hx.nx - 1 + j * sy + k * sz;
+      } else {
+        const int i = r2 / 3, d = r2 - 3 * i;
+        c = i + j * sy + k * sz;
+        if (d == 0) other = k > 0 ? c - sz : -1;
+        else if (d == 1) other = j > 0 ? c - sy : -1;
+        else other = i > 0 ? c - 1 : -1;
+      }
+    }
+    const double w1 = (double)fw[f];
+    const double ec = back * (double)e[c];
+    double zz = wj * (double)dinv32[g] * r[g];
+    if (other >= 0) {
+      if (w1 > 0.) zz += w1 * (back * (double)e[other]) + (1. - w1) * ec;
+    } else {
+      zz += w1 * ec;
+    }
+    p[g] = first ? zz : zz + beta * p[g];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(counter, 1u);
+    if (t == gridDim.x - 1) {
+      scal[S_RZNEW] = rz_new;
+      scal[S_RZ] = rz_new;
+      *counter = 0u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_aux_dinv32(int n, const double* __restrict__ dinv, float* __restrict__ out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) out[g] = (float)dinv[g];
+}
+
+int mimpy_auxmg_fused(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, int n, mimpy_aux_fused* out) {
+  // opt-in (MIMPY_B200_AUX_FUSED_P): measured 2.82 ms against 2.79 ms per iteration at 256^3 -- the 0.8 GB of z it saves
+  // are paid back by the face-indexed gather of e and the second pass over D^-1; kept for smaller caches / other meshes
+  if (!h->use32 || ctx->world != 1 || n != h->flux_dof || !getenv("MIMPY_B200_AUX_FUSED_P")) return 0;
+  k_aux_dinv32<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, dinv, h->dinv32);
+  if (cudaGetLastError() != cudaSuccess) return 0;
+  out->dinv32 = h->dinv32;
+  out->wj = h->wj;
+  return 1;
+}
+
+// p = B r + beta p on the FP32 levels of a single rank (see k_aux_face_prolong_p); S_RR and S_RDR are current
+int mimpy_auxmg_apply_p(mimpy_ctx* ctx, mimpy_auxmg* h, const double* r, double* p, int first) {
+  cudaStream_t st = ctx->stream;
+  AuxLevel32* L = h->lev32;
+  AuxHex hx;
+  hx.nx = L[0].nx; hx.ny = L[0].ny; hx.nz = L[0].nz;
+  hx.L = hx.nx * hx.ny + hx.nx * (hx.ny + 1) + (hx.nx + 1) * hx.ny;
+  hx.xrow = 3 * hx.nx + 1;
+  const double* rr = ctx->scalars + S_RR;
+  const double nrows = (double)(h->flux_dof > 0 ? h->flux_dof : 1);
+  const int grid = ctx->sm_count * 8;
+  k_aux_face_restrict<float><<<aux_blocks(h->nc), AUX_T, 0, st>>>(hx, h->face_to_flux, h->fw32, r, L[0].b, rr, nrows);
+  const int last = h->nlev - 1;
+  for (int l = 0; l < last; ++l) {
+    k_aux_presmooth<float><<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], h->omega);
+    k_aux_restrict<float><<<aux_blocks(L[l + 1].n), AUX_T, 0, st>>>(L[l], L[l + 1]);
+  }
+  k_aux_coarse_solve<float><<<1, AUX_COARSEST, 0, st>>>(L[last], h->cinv, h->sdev);
+  for (int l = last - 1; l >= 1; --l)
+    k_aux_prolong_smooth<float, false><<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], L[l + 1], h->omega, h->scale, nullptr, nullptr, nullptr);
+  if (last >= 1) {
+    // (as many blocks as the reduction has partial slots for: neighbouring cells stay neighbours in time)
+    const int dot_grid = aux_blocks(L[0].n) < 8192 ? aux_blocks(L[0].n) : 8192;
+    k_aux_prolong_smooth<float, true><<<dot_grid, AUX_T, 0, st>>>(L[0], L[1], h->omega, h->scale, ctx->partials, ctx->counters + 4,
+                                                               ctx->scalars + S_BE);
+  } else {  // a mesh of one level: the coarse solve is the whole cycle
+    k_aux_dot32<<<1, AUX_T, 0, st>>>(L[0].n, L[0].b, L[0].x2, ctx->scalars + S_BE);
+  }
+  k_aux_face_prolong_p<<<grid, RED_THREADS, 0, st>>>(hx, h->nf, h->wj, h->face_to_flux, h->fw32, L[0].x2, h->dinv32, r, p, ctx->scalars,
+                                                    ctx->counters + 2, nrows, h->sdev, first);
   KERNEL_CHECK();
   return MIMPY_OK;
 }
@@ -625,7 +762,7 @@ int mimpy_auxmg_apply(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, const 
     }
     k_aux_coarse_solve<double><<<1, AUX_COARSEST, 0, st>>>(G[glast], h->cinv, nullptr);
     for (int l = glast - 1; l >= 0; --l)
-      k_aux_prolong_smooth<double><<<aux_blocks(G[l].n), AUX_T, 0, st>>>(G[l], G[l + 1], h->omega, h->scale);
+      k_aux_prolong_smooth<double, false><<<aux_blocks(G[l].n), AUX_T, 0, st>>>(G[l], G[l + 1], h->omega, h->scale, nullptr, nullptr, nullptr);
     const int nxy = L[last].nx * L[last].ny;
     k_aux_global_extract<<<aux_blocks(L[last].n + 2 * nxy), AUX_T, 0, st>>>(L[last].n, nxy, ctx->rank, ctx->world, G[0].x2,
                                                                         L[last].x2);
@@ -633,7 +770,7 @@ int mimpy_auxmg_apply(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, const 
     k_aux_coarse_solve<double><<<1, AUX_COARSEST, 0, st>>>(L[last], h->cinv, nullptr);
   }
   for (int l = last - 1; l >= 0; --l) {
-    k_aux_prolong_smooth<double><<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], L[l + 1], h->omega, h->scale);
+    k_aux_prolong_smooth<double, false><<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], L[l + 1], h->omega, h->scale, nullptr, nullptr, nullptr);
     if (h->global && l > 0 && (rc = ghosts(L[l].x2, L[l]))) return rc;
   }
   const int grid = ctx->sm_count * 8;
@@ -753,7 +890,7 @@ int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
   size_t total32 = 0;  // in doubles
   if (h->use32)
     for (int l = 0; l < h->nlev; ++l) total32 += 7 * pad(((size_t)h->lev[l].n + 1) / 2);
-  if (h->use32) total32 += pad(((size_t)h->nf + 1) / 2);
+  if (h->use32) total32 += pad(((size_t)h->nf + 1) / 2) + pad(((size_t)h->flux_dof + 1) / 2);
   total += total32 + pad(8);
   static bool pool_configured[64] = {false};  // per device
   bool& pool_done = pool_configured[ctx->device & 63];
@@ -803,8 +940,10 @@ int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
   h->cinv = take((size_t)AUX_COARSEST * AUX_COARSEST);
   h->sdev = take(8);
   h->fw32 = nullptr;
+  h->dinv32 = nullptr;
   if (h->use32) {
     h->fw32 = reinterpret_cast<float*>(take(((size_t)h->nf + 1) / 2));
+    h->dinv32 = reinterpret_cast<float*>(take(((size_t)h->flux_dof + 1) / 2));
     for (int l = 0; l < h->nlev; ++l) {
       const AuxLevel& L = h->lev[l];
       AuxLevel32& M = h->lev32[l];

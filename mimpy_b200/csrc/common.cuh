@@ -79,6 +79,15 @@ int mimpy_check_device_flag(mimpy_ctx* ctx);  // stream sync + error if a bounde
 struct mimpy_auxmg;
 int mimpy_auxmg_apply(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, const double* r, double* z,
                       double* rz_dst, int n_owned);
+// single rank, FP32 levels: the preconditioner application fused with the update of the search direction,
+// p = B r + beta p, z never stored (r . z = S_RDR + b . e is known before the prolongation).  mimpy_auxmg_fused
+// returns 1 when the handle supports it and prepares the FP32 copy of the Jacobi diagonal.
+struct mimpy_aux_fused {
+  const float* dinv32;
+  double wj;
+};
+int mimpy_auxmg_fused(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, int n, mimpy_aux_fused* out);
+int mimpy_auxmg_apply_p(mimpy_ctx* ctx, mimpy_auxmg* h, const double* r, double* p, int first);
 // comm.cu
 int mimpy_allreduce_f64(mimpy_ctx* ctx, double* buf, int count);
 int mimpy_halo_exchange_add(mimpy_ctx* ctx, double* v);

@@ -112,6 +112,42 @@ k_update_xr_gen(int n, int n_owned, const double* __restrict__ p, const double* 
   finish_reduction<1>(v, partials, counter, scal + S_RR, sh);
 }
 
+// the same for the fused update of p (mimpy_auxmg_apply_p): also S_RDR = r . (w_J D^-1 r) with the FP32 copy of the
+// Jacobi diagonal that the prolongation will use
+__global__ void __launch_bounds__(RED_THREADS)
+k_update_xr_aux(int n, const double* __restrict__ p, const double* __restrict__ ap, const float* __restrict__ dinv32,
+                double wj, double* __restrict__ x, double* __restrict__ r, double* partials, unsigned int* counter,
+                double* scal) {
+  __shared__ double sh[32];
+  const double pap = scal[S_PAP];
+  const double alpha = (pap != 0.) ? scal[S_RZ] / pap : 0.;
+  double rr = 0., rdr = 0.;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    x[i] += alpha * p[i];
+    const double ri = r[i] - alpha * ap[i];
+    r[i] = ri;
+    rr += ri * ri;
+    rdr += ri * (wj * (double)__ldg(dinv32 + i) * ri);
+  }
+  const double v[2] = {rr, rdr};
+  finish_reduction<2>(v, partials, counter, scal + S_RR, sh);  // S_RR, S_RDR are neighbours
+}
+
+// S_RDR of the initial residual
+__global__ void __launch_bounds__(RED_THREADS)
+k_rdr(int n, const double* __restrict__ r, const float* __restrict__ dinv32, double wj, double* partials,
+      unsigned int* counter, double* scal) {
+  __shared__ double sh[32];
+  double rdr = 0.;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double ri = r[i];
+    rdr += ri * (wj * (double)__ldg(dinv32 + i) * ri);
+  }
+  const double v[1] = {rdr};
+  finish_reduction<1>(v, partials, counter, scal + S_RDR, sh);
+}
+
 // p = z + b p (b = S_RZNEW / S_RZ, or 0 when `first`), then S_RZ <- S_RZNEW
 __global__ void __launch_bounds__(RED_THREADS)
 k_update_p_gen(int n, const double* __restrict__ z, double* __restrict__ p, unsigned int* counter,
@@ -317,8 +353,14 @@ static int apply_aux(mimpy_ctx* ctx, mimpy_auxmg* aux, int n, const double* dinv
 
 static int launch_iteration(mimpy_ctx* ctx, int grid, int n, const SpmvMat& A, const double* dinv,
                             double* x, double* r, double* p, double* ap, mimpy_auxmg* aux = nullptr,
-                            double* z = nullptr) {
+                            double* z = nullptr, const mimpy_aux_fused* fz = nullptr) {
   cudaStream_t st = ctx->stream;
+  if (aux && fz) {  // single rank: three kernels around the V-cycle, z never stored
+    launch_spmv(ctx, grid, n, A, p, ap, true);
+    k_update_xr_aux<<<grid, RED_THREADS, 0, st>>>(n, p, ap, fz->dinv32, fz->wj, x, r, ctx->partials, ctx->counters + 1,
+                                                  ctx->scalars);
+    return mimpy_auxmg_apply_p(ctx, aux, r, p, 0);
+  }
   if (aux) {
     launch_spmv(ctx, grid, n, A, p, ap, true);
     int rc = allreduce(ctx, ctx->scalars + S_PAP, 1);
@@ -418,7 +460,13 @@ static int pcg_core(mimpy_ctx* ctx, int32_t n, const SpmvMat& A, const double* d
   if (rc) return rc;
   k_init_scalars<<<1, 1, 0, st>>>(ctx->scalars);
   KERNEL_CHECK();
-  if (aux) {  // replace the Jacobi start by z0 = B r0, p0 = z0
+  mimpy_aux_fused fz_store;
+  const mimpy_aux_fused* fz = (aux && mimpy_auxmg_fused(ctx, aux, diag_inv, n, &fz_store)) ? &fz_store : nullptr;
+  if (aux && fz) {  // p0 = B r0 with the fused update
+    k_rdr<<<grid, RED_THREADS, 0, st>>>(n, r, fz->dinv32, fz->wj, ctx->partials, ctx->counters + 3, ctx->scalars);
+    rc = mimpy_auxmg_apply_p(ctx, aux, r, p, 1);
+    if (rc) return rc;
+  } else if (aux) {  // replace the Jacobi start by z0 = B r0, p0 = z0
     rc = apply_aux(ctx, aux, n, diag_inv, r, z, 1);
     if (rc) return rc;
     k_update_p_gen<<<grid, RED_THREADS, 0, st>>>(n, z, p, ctx->counters + 2, ctx->scalars, 1);
@@ -448,7 +496,7 @@ static int pcg_core(mimpy_ctx* ctx, int32_t n, const SpmvMat& A, const double* d
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
       int crc = MIMPY_OK;
       for (int k = 0; k < check && crc == MIMPY_OK; ++k)
-        crc = launch_iteration(ctx, grid, n, A, diag_inv, x, r, p, ap, aux, z);
+        crc = launch_iteration(ctx, grid, n, A, diag_inv, x, r, p, ap, aux, z, fz);
       cudaError_t e = cudaStreamEndCapture(st, &graph);
       if (crc != MIMPY_OK || e != cudaSuccess || graph == nullptr ||
           cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) {
@@ -469,7 +517,7 @@ static int pcg_core(mimpy_ctx* ctx, int32_t n, const SpmvMat& A, const double* d
       CUDA_TRY(cudaGraphLaunch(gexec, st));
     } else {
       for (int k = 0; k < check; ++k) {
-        rc = launch_iteration(ctx, grid, n, A, diag_inv, x, r, p, ap, aux, z);
+        rc = launch_iteration(ctx, grid, n, A, diag_inv, x, r, p, ap, aux, z, fz);
         if (rc) return rc;
       }
       KERNEL_CHECK();

@@ -2,7 +2,9 @@
 #pragma once
 #include "common.cuh"
 
-enum { S_RZ = 0, S_PAP = 1, S_RZNEW = 2, S_RR = 3, S_BNORM = 4, S_TMP = 8 };
+// S_RDR = r . (w_J D^-1 r) and S_BE = b~ . e~ (cell space): the two parts of r . z of the auxiliary-space preconditioner,
+// known before z itself is formed (pcg.cu, fused update of p)
+enum { S_RZ = 0, S_PAP = 1, S_RZNEW = 2, S_RR = 3, S_RDR = 4, S_BNORM = 5, S_BE = 6, S_TMP = 8 };
 
 #define RED_THREADS 256
 
