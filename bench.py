@@ -265,10 +265,9 @@ def run_c2(ctx, peak, rtol):
             "solve_s": wall, "saddle_rel_residual": res, "rtol": rtol}
 
 
-def run_c4(ctx, peak, n=128, steps=6):
-    """BASELINE configs[3]: two-phase IMPES on n^3 hexes through the drop-in TwoPhase API (method 6, n^2 rate
-    wells on x-, Dirichlet outflow on x+): ms per IMPES step and the device time of the saturation update."""
-    import torch
+def build_c4(ctx, n):
+    """The TwoPhase model of BASELINE configs[3] on n^3 hexes (method 6, n^2 rate wells on x-, Dirichlet outflow on x+),
+    before initialize_system; returns (model, seconds spent in HexMesh.build_mesh, time step size)."""
     import mimpy_b200.mesh.hexmesh as hexmesh
     import mimpy_b200.models.twophase as twophase
 
@@ -305,6 +304,16 @@ def run_c4(ctx, peak, n=128, steps=6):
     tp.set_time_step_size(dt)
     for c in range(0, nc, n):
         tp.add_rate_well(10. / (n * n), 0., c, "w%d" % c)
+    return tp, t_mesh, dt
+
+
+def run_c4(ctx, peak, n=128, steps=6):
+    """BASELINE configs[3]: two-phase IMPES on n^3 hexes through the drop-in TwoPhase API (method 6, n^2 rate
+    wells on x-, Dirichlet outflow on x+): ms per IMPES step and the device time of the saturation update."""
+    import torch
+
+    nc = n ** 3
+    tp, t_mesh, dt = build_c4(ctx, n)
     t0 = time.perf_counter()
     tp.initialize_system()
     ctx.sync()

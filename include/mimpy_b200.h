@@ -411,6 +411,20 @@ int mimpy_b200_twophase_saturation_step(mimpy_ctx* ctx, const mimpy_mesh_view* m
 /* water_mob / oil_mob: per-cell phase mobilities evaluated by the caller from the saturation BEFORE this
  * step -- the path of user relative-permeability callables (TwoPhase.set_krw / set_kro,
  * twophase.py:292-300); NULL = Corey curves of `fluid_host` evaluated in the kernel. */
+/* The same step with flux_area[g] = area of the face of flux DOF g (8 B per face instead of the 32-B sector of
+ * the packed record; filled once per (mesh, plan) by mimpy_b200_flux_areas; NULL = read the records). */
+int mimpy_b200_twophase_saturation_step2(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,
+                                         const mimpy_symbolic* sym, const mimpy_fluid* fluid_host,
+                                         double dt, const int32_t* upwind_cell, const double* u_t,
+                                         const double* p, const double* p_prev,
+                                         const double* porosity, int32_t n_bnd,
+                                         const int32_t* bnd_faces, const int8_t* bnd_sigma,
+                                         const double* bnd_fw, int32_t n_rate_wells,
+                                         const int32_t* well_cells, const double* well_rate_water,
+                                         double* f_w, double* s_w, const double* water_mob,
+                                         const double* oil_mob, const double* flux_area /*flux_dof or NULL*/);
+int mimpy_b200_flux_areas(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
+                          double* flux_area /*flux_dof*/);
 
 /* -- (10) multi-GPU: z-slab partition of the cell set (host side in
  * mimpy_b200/partition.py) ----------------------------------------------------------------------

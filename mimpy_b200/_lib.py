@@ -89,6 +89,9 @@ SIGNATURES = {
     "mimpy_b200_twophase_newton_terms": [_vp, _i32, _i32, C.POINTER(Fluid), _f64, _vp, _vp, _vp, _vp, _vp, _vp],
     "mimpy_b200_twophase_saturation_step": [_vp, _PM, _PS, C.POINTER(Fluid), _f64, _vp, _vp, _vp,
                                             _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mimpy_b200_twophase_saturation_step2": [_vp, _PM, _PS, C.POINTER(Fluid), _f64, _vp, _vp, _vp,
+                                             _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mimpy_b200_flux_areas": [_vp, _PM, _PS, _vp],
     "mimpy_b200_sell_patterns": [_vp, _i32, _vp, _vp, _vp, _vp, C.POINTER(_i32)],
     "mimpy_b200_spmv_sell_pat": [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
     "mimpy_b200_set_comm": [_vp, _vp, _i32, _i32],

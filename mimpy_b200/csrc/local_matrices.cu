@@ -13,6 +13,7 @@
 //            Q from CholeskyQR2 so the projector is accurate to O(eps) for anisotropic K)
 //   method 0..7: stabilisation                                 mfd.py:379-468
 #include "common.cuh"
+#include "cell_core.cuh"
 
 #define SM_PAD 1
 
@@ -45,11 +46,20 @@ struct ScatterArgs {
   int flux_dof;
 };
 
-template <int G, bool SCATTER>
-__global__ void __launch_bounds__(128, 4)  // <= 128 registers: 4 CTAs per SM
-k_local_matrices(mimpy_mesh_view m, int method, int flags, const int* __restrict__ m_ptr,
+// MT: the construction method at compile time (0, 1, 6: the methods of the BASELINE configs), or -1 = the run-time
+// argument (all eight methods in one body: more registers, dead branches)
+template <int G, bool SCATTER, int MT>
+// Resident CTAs per SM: the kernel waits on its gather chains (cell_ptr -> cell_faces -> record / face_to_flux -> indptr), so
+// occupancy pays -- measured on 128^3 hexes, method 1: 4 CTAs (126 registers) 1.85 ms, 5 (94) 1.55 ms, 6 (80) 1.32 ms, 8 (64,
+// spills) 1.26 ms.  Methods 0 and 1 fit 80 registers without spilling; the others get 5 CTAs.
+#ifndef LM_MINB
+#define LM_MINB(MT) (((MT) == 0 || (MT) == 1) ? 6 : 5)
+#endif
+__global__ void __launch_bounds__(128, LM_MINB(MT))
+k_local_matrices(mimpy_mesh_view m, int method_rt, int flags, const int* __restrict__ m_ptr,
                  double* __restrict__ m_e, double* __restrict__ diagonality,
                  double* __restrict__ consistency, ScatterArgs sc) {
+  const int method = MT >= 0 ? MT : method_rt;
   constexpr int CPB = 128 / G;
   __shared__ CellSmem<G> sm[CPB];
   const int slot = threadIdx.x / G;
@@ -141,7 +151,7 @@ k_local_matrices(mimpy_mesh_view m, int method, int flags, const int* __restrict
       g00 = rr0[0]; g10 = rr0[1]; g11 = rr11; g20 = rr0[2]; g21 = rr21; g22 = rr22;
     }
     if (n > 0) {
-      Chol3 c1 = chol3(g00, g10, g11, g20, g21, g22);
+      Chol3 c1 = chol3r(g00, g10, g11, g20, g21, g22);
       chol3_fwd(c1, q[0], q[1], q[2]);
     }
 #pragma unroll
@@ -155,7 +165,7 @@ k_local_matrices(mimpy_mesh_view m, int method, int flags, const int* __restrict
     }
     __syncwarp();
     if (n > 0) {
-      Chol3 c2 = chol3(h00, h10, h11, h20, h21, h22);
+      Chol3 c2 = chol3r(h00, h10, h11, h20, h21, h22);
       chol3_fwd(c2, q[0], q[1], q[2]);
     }
 #pragma unroll
@@ -444,13 +454,21 @@ int mimpy_b200_mfd_local_matrices(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, i
   const int blocks = (mesh->nc + cpb - 1) / cpb;
   ScatterArgs sc = {};
   const size_t dyn = (method == 4) ? sizeof(double) * (size_t)cpb * G * (G + 1) : 0;
-#define LAUNCH(GG)                                                                     \
-  k_local_matrices<GG, false><<<blocks, 128, dyn, ctx->stream>>>(*mesh, method, flags, m_ptr, m_e, \
-                                                                 diagonality, consistency, sc)
+#define LAUNCH_M(GG, MM)                                                                   \
+  k_local_matrices<GG, false, MM><<<blocks, 128, dyn, ctx->stream>>>(*mesh, method, flags, m_ptr, m_e, \
+                                                                     diagonality, consistency, sc)
+#define LAUNCH(GG)                       \
+  do {                                   \
+    if (method == 0) LAUNCH_M(GG, 0);    \
+    else if (method == 1) LAUNCH_M(GG, 1); \
+    else if (method == 6) LAUNCH_M(GG, 6); \
+    else LAUNCH_M(GG, -1);               \
+  } while (0)
   if (G == 8) LAUNCH(8);
   else if (G == 16) LAUNCH(16);
   else LAUNCH(32);
 #undef LAUNCH
+#undef LAUNCH_M
   KERNEL_CHECK();
   return MIMPY_OK;
 }
@@ -479,13 +497,21 @@ int mimpy_b200_mfd_numeric(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mi
   const int blocks = (mesh->nc + cpb - 1) / cpb;
   ScatterArgs sc = make_scatter(sym, multipliers, alpha, c_diag, vals);
   const size_t dyn = (method == 4) ? sizeof(double) * (size_t)cpb * G * (G + 1) : 0;
-#define LAUNCH(GG)                                                                                \
-  k_local_matrices<GG, true><<<blocks, 128, dyn, ctx->stream>>>(*mesh, method, flags, sym->m_ptr, \
-                                                                m_e_out, nullptr, nullptr, sc)
+#define LAUNCH_M(GG, MM)                                                                              \
+  k_local_matrices<GG, true, MM><<<blocks, 128, dyn, ctx->stream>>>(*mesh, method, flags, sym->m_ptr, \
+                                                                    m_e_out, nullptr, nullptr, sc)
+#define LAUNCH(GG)                       \
+  do {                                   \
+    if (method == 0) LAUNCH_M(GG, 0);    \
+    else if (method == 1) LAUNCH_M(GG, 1); \
+    else if (method == 6) LAUNCH_M(GG, 6); \
+    else LAUNCH_M(GG, -1);               \
+  } while (0)
   if (G == 8) LAUNCH(8);
   else if (G == 16) LAUNCH(16);
   else LAUNCH(32);
 #undef LAUNCH
+#undef LAUNCH_M
   KERNEL_CHECK();
   return MIMPY_OK;
 }

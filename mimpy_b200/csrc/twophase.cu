@@ -132,8 +132,25 @@ __global__ void k_saturation(int nc, mimpy_fluid fl, double dt, const int* __res
   s_w[c] = a + b;
 }
 
+// Fractional flow of every CELL (twophase.py:968-971 evaluates it per upwinded face from the face's upwind cell: the
+// same arithmetic on the same operands, once per cell instead of once per face)
+__global__ void __launch_bounds__(256)
+k_cell_frac_flow(int nc, mimpy_fluid fl, const double* __restrict__ sw, const double* __restrict__ p,
+                 const double* __restrict__ wm, const double* __restrict__ om, double* __restrict__ fwc) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  double mw, mo;
+  if (wm) {
+    mw = wm[c];
+    mo = om[c];
+  } else {
+    mobilities(fl, sw[c], p[c], mw, mo);
+  }
+  fwc[c] = mw / (mw + mo);
+}
+
 // Fused form of k_frac_flow + k_saturation: the fractional flow of a face is evaluated from its upwind cell
-// on the fly (no pass over the faces, no f_w read for upwinded faces); the upwind cell records it in f_w,
+// on the fly (or, two-pass form, taken from the per-cell array fwc; s_new may then be s_old) (no pass over the faces, no f_w read for upwinded faces); the upwind cell records it in f_w,
 // which stays the STATE the reference keeps between steps (a face that is in no upwind pair -- inflow
 // boundary, zero flux -- uses the value it had, twophase.py:968-994).  Reads the saturation of the
 // previous sub-step (s_old), writes s_new.  The last flux DOF (the u_t[-1] quirk) is prepared separately.
@@ -144,7 +161,7 @@ k_saturation_fused(int nc, int F, mimpy_fluid fl, double dt, const int* __restri
                    const int* __restrict__ upwind, const double* __restrict__ u_t, const double* __restrict__ p,
                    const double* __restrict__ p_prev, const double* __restrict__ porosity,
                    const double* __restrict__ vol, const double* __restrict__ wm, const double* __restrict__ om,
-                   const double* __restrict__ s_old, double* __restrict__ s_new, double* __restrict__ f_w) {
+                   const double* __restrict__ fwc, const double* s_old, double* s_new, double* __restrict__ f_w) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
   const int base = cell_ptr[c];
@@ -159,14 +176,18 @@ k_saturation_fused(int nc, int F, mimpy_fluid fl, double dt, const int* __restri
     if (up < 0 || g == F - 1) {
       fw = f_w[g];
     } else {
-      double mw, mo;
-      if (wm) {
-        mw = wm[up];
-        mo = om[up];
+      if (fwc) {  // two-pass form: the fractional flow of every cell was evaluated once (k_cell_frac_flow)
+        fw = fwc[up];
       } else {
-        mobilities(fl, s_old[up], p[up], mw, mo);
+        double mw, mo;
+        if (wm) {
+          mw = wm[up];
+          mo = om[up];
+        } else {
+          mobilities(fl, s_old[up], p[up], mw, mo);
+        }
+        fw = mw / (mw + mo);
       }
-      fw = mw / (mw + mo);
       if (up == c) f_w[g] = fw;
     }
     const double e = (double)sigma[base + j] * rec_area(face_geom, (size_t)f);
@@ -185,6 +206,88 @@ k_saturation_fused(int nc, int F, mimpy_fluid fl, double dt, const int* __restri
   b *= div;
   b *= -dt;
   s_new[c] = a + b;
+}
+
+// Default form: the update over the cells with the fractional flow of every cell evaluated once before (k_cell_frac_flow).
+// Same arithmetic as k_saturation_fused; what changes is how the gathers are issued.  The face loop of the kernels above
+// walks a dependent chain per face (cell_faces -> face_to_flux -> upwind -> f_w of the upwind cell), one face after the
+// other: 4 x n_E exposed latencies per thread, 20 % issue utilisation, 45 % of the DRAM peak (ncu, 128^3).  Here the
+// faces go through the chain B at a time, stage by stage, so B loads of a stage are in flight together; s_w is updated in
+// place (only the own saturation is read).  flux_area: area of the face of every flux DOF (mimpy_b200_flux_areas), 8 B
+// instead of the 32-B sector of the packed record; NULL = read the record.
+template <int B>
+__global__ void __launch_bounds__(256)
+k_saturation_cells(int nc, int F, mimpy_fluid fl, double dt, const int* __restrict__ cell_ptr,
+                   const int* __restrict__ cell_faces, const int8_t* __restrict__ sigma,
+                   const double* __restrict__ face_geom, const double* __restrict__ flux_area,
+                   const int* __restrict__ f2f, const int* __restrict__ upwind, const double* __restrict__ u_t,
+                   const double* __restrict__ p, const double* __restrict__ p_prev,
+                   const double* __restrict__ porosity, const double* __restrict__ vol,
+                   const double* __restrict__ fwc, double* __restrict__ s_w, double* f_w) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int base = __ldg(cell_ptr + c);
+  const int n = __ldg(cell_ptr + c + 1) - base;
+  const double pc = __ldg(p + c), pp = __ldg(p_prev + c), phi = __ldg(porosity + c), v = __ldg(vol + c);
+  const double s_old = s_w[c];
+  double div = 0.;
+  for (int j0 = 0; j0 < n; j0 += B) {
+    int f[B], g[B], up[B];
+    double sg[B], a[B], u[B], fw[B];
+#pragma unroll
+    for (int q = 0; q < B; ++q) {
+      const bool in = j0 + q < n;
+      f[q] = in ? __ldg(cell_faces + base + j0 + q) : -1;
+      sg[q] = in ? (double)sigma[base + j0 + q] : 0.;
+    }
+#pragma unroll
+    for (int q = 0; q < B; ++q) g[q] = f[q] >= 0 ? __ldg(f2f + f[q]) : -1;
+#pragma unroll
+    for (int q = 0; q < B; ++q) {
+      up[q] = -1;
+      u[q] = a[q] = 0.;
+      if (g[q] >= 0) {
+        up[q] = __ldg(upwind + g[q]);
+        u[q] = __ldg(u_t + g[q]);
+        a[q] = flux_area ? __ldg(flux_area + g[q]) : rec_area(face_geom, (size_t)f[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < B; ++q) {
+      fw[q] = 0.;
+      if (g[q] >= 0) {
+        const bool state = up[q] < 0 || g[q] == F - 1;  // no upwind pair / the u_t[-1] quirk: the value f_w holds
+        fw[q] = state ? f_w[g[q]] : __ldg(fwc + up[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < B; ++q) {
+      if (g[q] < 0) continue;
+      if (up[q] == c && g[q] != F - 1) f_w[g[q]] = fw[q];  // the upwind cell records the state (twophase.py:968-971)
+      div += (sg[q] * a[q]) * (fw[q] * u[q]);
+    }
+  }
+  // twophase.py:1007-1022
+  double x = pp * fl.c_w + 1.;
+  x *= fl.rho_w;
+  x *= s_old;
+  x /= fl.rho_w;
+  x /= 1. + fl.c_w * pc;
+  double y = 1. / phi;
+  y /= fl.rho_w;
+  y /= (1. + fl.c_w * pc);
+  y /= v;
+  y *= div;
+  y *= -dt;
+  s_w[c] = x + y;
+}
+
+__global__ void k_flux_areas(int nf, const int* __restrict__ f2f, const double* __restrict__ face_geom,
+                             double* __restrict__ out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  const int g = f2f[f];
+  if (g >= 0) out[g] = rec_area(face_geom, (size_t)f);
 }
 
 // the last flux DOF: f_w of its upwind cell, before the boundary loop may override it (twophase.py:968-994)
@@ -249,6 +352,14 @@ int mimpy_b200_twophase_upwind(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,
   return MIMPY_OK;
 }
 
+int mimpy_b200_flux_areas(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym, double* flux_area) {
+  REQUIRE(ctx && mesh && sym && flux_area && mesh->face_geom && sym->face_to_flux, "NULL argument");
+  if (mesh->nf <= 0) return MIMPY_OK;
+  k_flux_areas<<<(mesh->nf + 255) / 256, 256, 0, ctx->stream>>>(mesh->nf, sym->face_to_flux, mesh->face_geom, flux_area);
+  KERNEL_CHECK();
+  return MIMPY_OK;
+}
+
 int mimpy_b200_twophase_saturation_step(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,
                                         const mimpy_symbolic* sym, const mimpy_fluid* fluid_host,
                                         double dt, const int32_t* upwind_cell, const double* u_t,
@@ -259,6 +370,21 @@ int mimpy_b200_twophase_saturation_step(mimpy_ctx* ctx, const mimpy_mesh_view* m
                                         const int32_t* well_cells, const double* well_rate_water,
                                         double* f_w, double* s_w, const double* water_mob,
                                         const double* oil_mob) {
+  return mimpy_b200_twophase_saturation_step2(ctx, mesh, sym, fluid_host, dt, upwind_cell, u_t, p, p_prev, porosity, n_bnd,
+                                              bnd_faces, bnd_sigma, bnd_fw, n_rate_wells, well_cells, well_rate_water, f_w,
+                                              s_w, water_mob, oil_mob, nullptr);
+}
+
+int mimpy_b200_twophase_saturation_step2(mimpy_ctx* ctx, const mimpy_mesh_view* mesh,
+                                         const mimpy_symbolic* sym, const mimpy_fluid* fluid_host,
+                                         double dt, const int32_t* upwind_cell, const double* u_t,
+                                         const double* p, const double* p_prev,
+                                         const double* porosity, int32_t n_bnd,
+                                         const int32_t* bnd_faces, const int8_t* bnd_sigma,
+                                         const double* bnd_fw, int32_t n_rate_wells,
+                                         const int32_t* well_cells, const double* well_rate_water,
+                                         double* f_w, double* s_w, const double* water_mob,
+                                         const double* oil_mob, const double* flux_area) {
   REQUIRE(ctx && mesh && sym && fluid_host && upwind_cell && u_t && p && p_prev && porosity && f_w && s_w,
           "NULL argument");
   const int F = sym->flux_dof, nc = mesh->nc;
@@ -266,12 +392,16 @@ int mimpy_b200_twophase_saturation_step(mimpy_ctx* ctx, const mimpy_mesh_view* m
   cudaStream_t st = ctx->stream;
   const mimpy_fluid fl = *fluid_host;
   REQUIRE((water_mob == nullptr) == (oil_mob == nullptr), "water_mob and oil_mob must be given together");
-  // The fused form (k_saturation_fused: no pass over the faces, f_w not read back) moves 278 instead of
-  // 378 B/cell but evaluates the mobilities and an FP64 division per (cell, upwinded face) instead of per
-  // face: measured 313 us against 227 us at 128^3 -- it is bound by the divisions, not by HBM.  Kept
-  // behind MIMPY_B200_SAT_FUSED; the default stays the per-face pass.
-  static const bool unfused = getenv("MIMPY_B200_SAT_FUSED") == nullptr;
-  if (unfused) {
+  // Three forms of the same update (identical arithmetic per face):
+  //  * default, two passes: the fractional flow of every cell once (k_cell_frac_flow, 24 B/cell), then one pass over the
+  //    cells that takes f_w of a face from its upwind cell's entry and updates s_w in place -- no pass over the faces,
+  //    one division per cell;
+  //  * MIMPY_B200_SAT_PERFACE: the reference's formulation, a pass over the faces (k_frac_flow) and one over the cells
+  //    (k_saturation), 378 B/cell: 227 us at 128^3;
+  //  * MIMPY_B200_SAT_FUSED: single pass, mobilities and a division per (cell, upwinded face): 313 us, division-bound.
+  // f_w stays the STATE the reference keeps between steps in all three.
+  const int form = getenv("MIMPY_B200_SAT_PERFACE") ? 1 : getenv("MIMPY_B200_SAT_FUSED") ? 2 : 0;
+  if (form == 1) {
     if (F > 0) k_frac_flow<<<(F + 255) / 256, 256, 0, st>>>(F, fl, upwind_cell, s_w, p, water_mob, oil_mob, f_w);
     if (n_bnd > 0) {
       REQUIRE(bnd_faces && bnd_sigma && bnd_fw, "boundary inflow arrays are NULL");
@@ -283,20 +413,28 @@ int mimpy_b200_twophase_saturation_step(mimpy_ctx* ctx, const mimpy_mesh_view* m
                                                    sym->face_to_flux, u_t, f_w, p, p_prev, porosity,
                                                    mesh->cell_volume, s_w);
   } else {
+    void* scratch = nullptr;
+    int rc = mimpy_scratch(ctx, sizeof(double) * (size_t)nc, &scratch);
+    if (rc) return rc;
+    double* buf = static_cast<double*>(scratch);  // form 0: per-cell fractional flow; form 2: the new saturation
+    if (form == 0) k_cell_frac_flow<<<(nc + 255) / 256, 256, 0, st>>>(nc, fl, s_w, p, water_mob, oil_mob, buf);
     if (F > 0) k_frac_flow_last<<<1, 1, 0, st>>>(F, fl, upwind_cell, s_w, p, water_mob, oil_mob, f_w);
     if (n_bnd > 0) {
       REQUIRE(bnd_faces && bnd_sigma && bnd_fw, "boundary inflow arrays are NULL");
       k_bnd_inflow<<<(n_bnd + 255) / 256, 256, 0, st>>>(n_bnd, bnd_faces, bnd_sigma, bnd_fw,
                                                         sym->face_to_flux, u_t, f_w);
     }
-    void* scratch = nullptr;
-    int rc = mimpy_scratch(ctx, sizeof(double) * (size_t)nc, &scratch);
-    if (rc) return rc;
-    double* s_new = static_cast<double*>(scratch);
-    k_saturation_fused<<<(nc + 255) / 256, 256, 0, st>>>(nc, F, fl, dt, mesh->cell_ptr, mesh->cell_faces, mesh->cell_sigma,
-                                                         mesh->face_geom, sym->face_to_flux, upwind_cell, u_t, p, p_prev,
-                                                         porosity, mesh->cell_volume, water_mob, oil_mob, s_w, s_new, f_w);
-    CUDA_TRY(cudaMemcpyAsync(s_w, s_new, sizeof(double) * (size_t)nc, cudaMemcpyDeviceToDevice, st));
+    if (form == 0) {
+      k_saturation_cells<6><<<(nc + 255) / 256, 256, 0, st>>>(nc, F, fl, dt, mesh->cell_ptr, mesh->cell_faces, mesh->cell_sigma,
+                                                              mesh->face_geom, flux_area, sym->face_to_flux, upwind_cell, u_t,
+                                                              p, p_prev, porosity, mesh->cell_volume, buf, s_w, f_w);
+    } else {
+      k_saturation_fused<<<(nc + 255) / 256, 256, 0, st>>>(nc, F, fl, dt, mesh->cell_ptr, mesh->cell_faces, mesh->cell_sigma,
+                                                           mesh->face_geom, sym->face_to_flux, upwind_cell, u_t, p, p_prev,
+                                                           porosity, mesh->cell_volume, water_mob, oil_mob, nullptr, s_w, buf,
+                                                           f_w);
+      CUDA_TRY(cudaMemcpyAsync(s_w, buf, sizeof(double) * (size_t)nc, cudaMemcpyDeviceToDevice, st));
+    }
   }
   if (n_rate_wells > 0) {
     REQUIRE(well_cells && well_rate_water, "well arrays are NULL");

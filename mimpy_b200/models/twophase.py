@@ -6,7 +6,7 @@ Per time step (twophase.py:703-742):
                       mfd_cython.update_m_fast) inside the fused numeric assembly, the diagonal block
                       is the accumulation term, the linear solve is the hybridised PCG
     find_upwinding_direction (step 1 and every 10th)  -> mimpy_b200_twophase_upwind
-    update_saturation -> mimpy_b200_twophase_saturation_step
+    update_saturation -> mimpy_b200_twophase_saturation_step2
 State arrays current_p_o / current_u_t / current_s_w are NumPy views refreshed after every step.
 Relative permeabilities: Corey curves are evaluated inside the kernels; user callables given to
 set_kro / set_krw (twophase.py:292-300) are evaluated on the host with NumPy, exactly as the reference
@@ -278,6 +278,10 @@ class TwoPhase(object):
             self._d_phi = self._t(self.porosities)
             self._d_fw = torch.zeros(F, dtype=torch.float64, device=ctx.device)
             self._d_upw = torch.full((F,), -1, dtype=torch.int32, device=ctx.device)
+            # area of the face of every flux DOF: 8 B per face for the saturation update instead of a record sector
+            self._d_flux_area = torch.empty(max(F, 1), dtype=torch.float64, device=ctx.device)
+            mv0 = dm.view()
+            ctx.call("mimpy_b200_flux_areas", C.byref(mv0), C.byref(plan.s), _lib.ptr(self._d_flux_area))
             self._d_vals = torch.empty(plan.nnz, dtype=torch.float64, device=ctx.device)
             self._d_invmob = torch.empty(nc, dtype=torch.float64, device=ctx.device)
             self._d_cdiag = torch.empty(nc, dtype=torch.float64, device=ctx.device)
@@ -399,11 +403,12 @@ class TwoPhase(object):
                 # the well terms use the mobilities of the saturation BEFORE the update (twophase.py:965, 1059-1076)
                 idx = self._t(self.pressure_wells, np.int64)
                 well = (device.to_host(ctx, self._d_s[idx]), device.to_host(ctx, self._d_p[idx]), idx)
-            ctx.call("mimpy_b200_twophase_saturation_step", C.byref(mv), C.byref(plan.s), C.byref(self._fl),
+            ctx.call("mimpy_b200_twophase_saturation_step2", C.byref(mv), C.byref(plan.s), C.byref(self._fl),
                      float(sat_delta_t), _lib.ptr(self._d_upw), _lib.ptr(self._d_u), _lib.ptr(self._d_p),
                      _lib.ptr(self._d_p_prev), _lib.ptr(self._d_phi), self._n_bnd, _lib.ptr(self._d_bf),
                      _lib.ptr(self._d_bs), _lib.ptr(self._d_bw), len(self.rate_wells), _lib.ptr(self._d_wc),
-                     _lib.ptr(self._d_wr), _lib.ptr(self._d_fw), _lib.ptr(self._d_s), _lib.ptr(wm), _lib.ptr(om))
+                     _lib.ptr(self._d_wr), _lib.ptr(self._d_fw), _lib.ptr(self._d_s), _lib.ptr(wm), _lib.ptr(om),
+                     _lib.ptr(self._d_flux_area))
             if well is not None:
                 self._pressure_well_saturation(sat_delta_t, time_step, *well)
 

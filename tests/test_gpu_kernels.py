@@ -753,10 +753,16 @@ def test_auxmg_rejected_on_unstructured_mesh(ctx, golden):
 
 
 # ---- two-phase kernels ---------------------------------------------------------------------------------
-def test_twophase_kernels_vs_reference_history(ctx, golden):
+@pytest.mark.parametrize("form", ["", "MIMPY_B200_SAT_PERFACE", "MIMPY_B200_SAT_FUSED"])
+def test_twophase_kernels_vs_reference_history(ctx, golden, form, monkeypatch):
     """Upwind flags + saturation step reproduce the reference's s_w to 1e-10 per step when driven
-    by the reference's own p/u_t history (isolates T2/T4/T5 from the linear solver)."""
+    by the reference's own p/u_t history (isolates T2/T4/T5 from the linear solver).  The three forms of the
+    update (two-pass default, the reference's per-face pass, single pass) give the same saturations."""
     import ctypes as C
+    for k in ("MIMPY_B200_SAT_PERFACE", "MIMPY_B200_SAT_FUSED"):
+        monkeypatch.delenv(k, raising=False)
+    if form:
+        monkeypatch.setenv(form, "1")
     import torch
     from mimpy_b200 import device
     from mimpy_b200._lib import ptr
