@@ -31,10 +31,10 @@ sys.path.insert(0, ROOT)
 METRIC = "mfd_assembly_mcells_per_s"
 UNIT = "Mcells/s"
 ASM_BYTES_PER_CELL = 700.0     # 332 B read + 368 B written per hex cell
-# saturation step as built (twophase.cu), hex cells, r = 3 faces per cell: k_frac_flow per face (upwind 4 + s, p of the
-# upwind cell 16 + f_w 8 = 28 B) and k_saturation per cell (cell_faces 24 + sigma 6 + per face f2f 4 + area record sector
-# 32 + f_w 8 + u_t 8 (x6 gathers, each face read by two cells) + p, p_prev, phi, vol, s_w 40 + s_w written 8)
-SAT_BYTES_PER_CELL = 3 * 28.0 + (24 + 6 + 6 * (4 + 8 + 8) + 3 * 32 + 48)
+# saturation step as built (twophase.cu), structured hex cells, r = 3 faces per cell: k_cell_frac_flow (s, p read, f_w of the
+# cell written: 24 B) and k_saturation_cells<HEX> (per face: face_to_flux 4 + upwind 4 + u_t 8 + area 8; f_w of the cell's
+# upwinded faces written 24; f_w of the neighbours 8; p, p_prev, phi, vol, s_w 40 + s_w written 8); every face counted once
+SAT_BYTES_PER_CELL = 24.0 + 3 * 24.0 + 24 + 8 + 48
 
 
 def measured_traffic(n, world):
@@ -345,8 +345,10 @@ def run_c4(ctx, peak, n=128, steps=6):
             "pcg_iters_per_step": iters, "sat_step_us": sat_us,
             "sat_roofline": {"bound": "hbm", "achieved": sat_bytes / (sat_us / 1e6) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": sat_bytes / (sat_us / 1e6) / 1e9 / peak, "algorithmic_bytes_per_cell": SAT_BYTES_PER_CELL,
-                             "kernels": "k_frac_flow + k_saturation + k_rate_wells (twophase.cu); the fused single-pass form "
-                                        "(MIMPY_B200_SAT_FUSED, 278 B/cell) is division-bound and slower: 313 us",
+                             "kernels": "k_cell_frac_flow + k_saturation_cells<HEX> + k_rate_wells (twophase.cu): fractional flow once per cell, "
+                                        "closed-form face ids, the six faces of a cell through the gather chain together; the "
+                                        "reference's per-face formulation (MIMPY_B200_SAT_PERFACE, 378 B/cell) takes 219 us, a "
+                                        "single pass with the mobilities per (cell, face) (MIMPY_B200_SAT_FUSED) 309 us",
                              "survey_fused_bytes_per_cell": 80.0},
             "water_mass_balance_rel_err": abs(float(sw.mean()) - injected) / injected,
             "s_w_max": float(sw.max())}

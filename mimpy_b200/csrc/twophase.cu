@@ -136,7 +136,8 @@ __global__ void k_saturation(int nc, mimpy_fluid fl, double dt, const int* __res
 // same arithmetic on the same operands, once per cell instead of once per face)
 __global__ void __launch_bounds__(256)
 k_cell_frac_flow(int nc, mimpy_fluid fl, const double* __restrict__ sw, const double* __restrict__ p,
-                 const double* __restrict__ wm, const double* __restrict__ om, double* __restrict__ fwc) {
+                 const double* __restrict__ wm, const double* __restrict__ om, double* __restrict__ fwc, int F,
+                 const int* __restrict__ upwind, double* __restrict__ f_w) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
   double mw, mo;
@@ -146,7 +147,10 @@ k_cell_frac_flow(int nc, mimpy_fluid fl, const double* __restrict__ sw, const do
   } else {
     mobilities(fl, sw[c], p[c], mw, mo);
   }
-  fwc[c] = mw / (mw + mo);
+  const double fw = mw / (mw + mo);
+  fwc[c] = fw;
+  // the last flux DOF takes f_w of its upwind cell before the boundary loop may override it (twophase.py:968-994)
+  if (F > 0 && upwind[F - 1] == c) f_w[F - 1] = fw;
 }
 
 // Fused form of k_frac_flow + k_saturation: the fractional flow of a face is evaluated from its upwind cell
@@ -215,9 +219,14 @@ k_saturation_fused(int nc, int F, mimpy_fluid fl, double dt, const int* __restri
 // faces go through the chain B at a time, stage by stage, so B loads of a stage are in flight together; s_w is updated in
 // place (only the own saturation is read).  flux_area: area of the face of every flux DOF (mimpy_b200_flux_areas), 8 B
 // instead of the 32-B sector of the packed record; NULL = read the record.
-template <int B>
-__global__ void __launch_bounds__(256)
-k_saturation_cells(int nc, int F, mimpy_fluid fl, double dt, const int* __restrict__ cell_ptr,
+// HEX: structured hex mesh with HexMesh's numbering (hexmesh.py:172-243): the face ids and orientations of a cell are
+// closed-form, two levels of the chain (cell_ptr, cell_faces) and 34 B/cell disappear.
+struct HexDims {
+  int nx, ny, nz;
+};
+template <int B, int MINB, bool HEX>
+__global__ void __launch_bounds__(256, MINB)
+k_saturation_cells(int nc, int F, mimpy_fluid fl, double dt, HexDims hd, const int* __restrict__ cell_ptr,
                    const int* __restrict__ cell_faces, const int8_t* __restrict__ sigma,
                    const double* __restrict__ face_geom, const double* __restrict__ flux_area,
                    const int* __restrict__ f2f, const int* __restrict__ upwind, const double* __restrict__ u_t,
@@ -226,19 +235,35 @@ k_saturation_cells(int nc, int F, mimpy_fluid fl, double dt, const int* __restri
                    const double* __restrict__ fwc, double* __restrict__ s_w, double* f_w) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
-  const int base = __ldg(cell_ptr + c);
-  const int n = __ldg(cell_ptr + c + 1) - base;
+  static_assert(!HEX || B == 6, "a hex cell is one batch");
+  const int base = HEX ? 0 : __ldg(cell_ptr + c);
+  const int n = HEX ? 6 : __ldg(cell_ptr + c + 1) - base;
   const double pc = __ldg(p + c), pp = __ldg(p_prev + c), phi = __ldg(porosity + c), v = __ldg(vol + c);
   const double s_old = s_w[c];
   double div = 0.;
   for (int j0 = 0; j0 < n; j0 += B) {
     int f[B], g[B], up[B];
     double sg[B], a[B], u[B], fw[B];
+    if (HEX) {  // cells list [z-, y-, x-, x+, y+, z+] with orientations [-1, -1, -1, 1, 1, 1]   hexmesh.py:329-342
+      const int nx = hd.nx, ny = hd.ny, nz = hd.nz;
+      const int ci = c % nx, cj = (c / nx) % ny, ck = c / (nx * ny);
+      const int xrow = 3 * nx + 1, L = nx * ny + nx * (ny + 1) + (nx + 1) * ny;
+      const int cbase = ck * L + cj * xrow + 3 * ci;
+      f[0] = cbase;
+      f[1] = cbase + 1;
+      f[2] = cbase + 2;
+      f[3 % B] = ci + 1 < nx ? cbase + 5 : ck * L + cj * xrow + 3 * nx;
+      f[4 % B] = cj + 1 < ny ? cbase + xrow + 1 : ck * L + ny * xrow + ci;
+      f[5 % B] = ck + 1 < nz ? cbase + L : nz * L + cj * nx + ci;
 #pragma unroll
-    for (int q = 0; q < B; ++q) {
-      const bool in = j0 + q < n;
-      f[q] = in ? __ldg(cell_faces + base + j0 + q) : -1;
-      sg[q] = in ? (double)sigma[base + j0 + q] : 0.;
+      for (int q = 0; q < B; ++q) sg[q] = q < 3 ? -1. : 1.;
+    } else {
+#pragma unroll
+      for (int q = 0; q < B; ++q) {
+        const bool in = j0 + q < n;
+        f[q] = in ? __ldg(cell_faces + base + j0 + q) : -1;
+        sg[q] = in ? (double)sigma[base + j0 + q] : 0.;
+      }
     }
 #pragma unroll
     for (int q = 0; q < B; ++q) g[q] = f[q] >= 0 ? __ldg(f2f + f[q]) : -1;
@@ -417,17 +442,27 @@ int mimpy_b200_twophase_saturation_step2(mimpy_ctx* ctx, const mimpy_mesh_view* 
     int rc = mimpy_scratch(ctx, sizeof(double) * (size_t)nc, &scratch);
     if (rc) return rc;
     double* buf = static_cast<double*>(scratch);  // form 0: per-cell fractional flow; form 2: the new saturation
-    if (form == 0) k_cell_frac_flow<<<(nc + 255) / 256, 256, 0, st>>>(nc, fl, s_w, p, water_mob, oil_mob, buf);
-    if (F > 0) k_frac_flow_last<<<1, 1, 0, st>>>(F, fl, upwind_cell, s_w, p, water_mob, oil_mob, f_w);
+    if (form == 0)
+      k_cell_frac_flow<<<(nc + 255) / 256, 256, 0, st>>>(nc, fl, s_w, p, water_mob, oil_mob, buf, F, upwind_cell, f_w);
+    else if (F > 0)
+      k_frac_flow_last<<<1, 1, 0, st>>>(F, fl, upwind_cell, s_w, p, water_mob, oil_mob, f_w);
     if (n_bnd > 0) {
       REQUIRE(bnd_faces && bnd_sigma && bnd_fw, "boundary inflow arrays are NULL");
       k_bnd_inflow<<<(n_bnd + 255) / 256, 256, 0, st>>>(n_bnd, bnd_faces, bnd_sigma, bnd_fw,
                                                         sym->face_to_flux, u_t, f_w);
     }
     if (form == 0) {
-      k_saturation_cells<6><<<(nc + 255) / 256, 256, 0, st>>>(nc, F, fl, dt, mesh->cell_ptr, mesh->cell_faces, mesh->cell_sigma,
-                                                              mesh->face_geom, flux_area, sym->face_to_flux, upwind_cell, u_t,
-                                                              p, p_prev, porosity, mesh->cell_volume, buf, s_w, f_w);
+      const HexDims hd = {mesh->hex_nx, mesh->hex_ny, mesh->hex_nz};
+      const bool hex = hd.nx > 0 && hd.ny > 0 && hd.nz > 0 && mesh->uniform_faces == 6 &&
+                       (long long)hd.nx * hd.ny * hd.nz == nc && !getenv("MIMPY_B200_SAT_NOHEX");
+#define SAT_LAUNCH(HX)                                                                                                         \
+  k_saturation_cells<6, 3, HX><<<(nc + 255) / 256, 256, 0, st>>>(nc, F, fl, dt, hd, mesh->cell_ptr, mesh->cell_faces,          \
+                                                                 mesh->cell_sigma, mesh->face_geom, flux_area,                  \
+                                                                 sym->face_to_flux, upwind_cell, u_t, p, p_prev, porosity,     \
+                                                                 mesh->cell_volume, buf, s_w, f_w)
+      if (hex) SAT_LAUNCH(true);
+      else SAT_LAUNCH(false);
+#undef SAT_LAUNCH
     } else {
       k_saturation_fused<<<(nc + 255) / 256, 256, 0, st>>>(nc, F, fl, dt, mesh->cell_ptr, mesh->cell_faces, mesh->cell_sigma,
                                                            mesh->face_geom, sym->face_to_flux, upwind_cell, u_t, p, p_prev,

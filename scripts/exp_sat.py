@@ -20,11 +20,11 @@ for step in (1, 2):
         tp.find_upwinding_direction()
     tp.update_saturation(step)
 ctx.sync()
-for form in ("", "MIMPY_B200_SAT_PERFACE", "MIMPY_B200_SAT_FUSED"):
-    for k in ("MIMPY_B200_SAT_PERFACE", "MIMPY_B200_SAT_FUSED"):
+for form in ("", "MIMPY_B200_SAT_NOHEX", "MIMPY_B200_SAT_PERFACE", "MIMPY_B200_SAT_FUSED"):
+    for k in ("MIMPY_B200_SAT_PERFACE", "MIMPY_B200_SAT_FUSED", "MIMPY_B200_SAT_NOHEX"):
         os.environ.pop(k, None)
     if form:
-        os.environ[form] = "1"
+        os.environ[form.split("=")[0]] = form.split("=")[1] if "=" in form else "1"
     ts = []
     for r in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
