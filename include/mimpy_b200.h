@@ -362,6 +362,14 @@ int mimpy_b200_auxmg_setup(mimpy_ctx* ctx, void* handle, const mimpy_mesh_view* 
                            const double* c_diag, const double* tau /* nc*6 from hybrid_setup_fused, or NULL:
                            read from the diagonals of w_e */);
 int mimpy_b200_auxmg_destroy(mimpy_ctx* ctx, void* handle);
+/* Cell-block smoother of that preconditioner: after auxmg_setup, hand the assembled face system (CSR: ptr = row
+ * offsets, sell = 0; SELL-32: ptr = slice offsets, sell = 1) and its inverted (complete) diagonal; the face-space
+ * term D^-1 of B becomes the weighted additive Schwarz sum over the cells of the inverses of the 6 x 6 blocks of A
+ * on the faces of each cell (stored as 21 floats per cell).  No reference counterpart.  MIMPY_B200_AUX_BLOCKS=0 in
+ * the environment of auxmg_create keeps the Jacobi term (the call is then a no-op). */
+int mimpy_b200_auxmg_cellblocks(mimpy_ctx* ctx, void* auxmg, const mimpy_mesh_view* mesh,
+                                const mimpy_symbolic* sym, const int32_t* ptr, const int32_t* idx,
+                                const double* vals, int32_t sell, const double* diag_inv);
 /* PCG with that preconditioner.  (ptr, idx, vals): the face system in CSR (sell = 0) or SELL-32
  * (sell = 1) layout; work: 4 n doubles.  Same info / error behaviour as mimpy_b200_pcg. */
 int mimpy_b200_pcg_aux(mimpy_ctx* ctx, int32_t n, const int32_t* ptr, const int32_t* idx,

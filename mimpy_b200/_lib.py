@@ -79,6 +79,7 @@ SIGNATURES = {
     "mimpy_b200_auxmg_create": [_vp, _PM, _PS, C.POINTER(_vp)],
     "mimpy_b200_auxmg_setup": [_vp, _vp, _PM, _PS, _vp, _f64, _vp, _vp],
     "mimpy_b200_auxmg_destroy": [_vp, _vp],
+    "mimpy_b200_auxmg_cellblocks": [_vp, _vp, _PM, _PS, _vp, _vp, _vp, _i32, _vp],
     "mimpy_b200_pcg_aux": [_vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, C.POINTER(PcgInfo)],
     "mimpy_b200_hybrid_rhs": [_vp, _PM, _PS, _vp, _f64, _vp, _vp, _vp, _vp],
     "mimpy_b200_hybrid_recover": [_vp, _PM, _PS, _vp, _f64, _vp, _vp, _vp, _vp],

@@ -83,6 +83,13 @@ struct mimpy_auxmg {
   double* sdev;  // device: [0] = s_A (power of two ~ 1 / tau of the first cells)
   float* fw32;   // FP32 copy of fw for the transfers of the FP32 cycle
   float* dinv32; // FP32 copy of the Jacobi diagonal (fused update of p), made per solve
+  // cell-block smoother (mimpy_b200_auxmg_cellblocks): instead of D^-1 the face-space term of B is the weighted
+  // additive Schwarz sum over the cells, sum_E P_E^T S_E (A_EE)^-1 S_E P_E (A_EE: the block of the face system on
+  // the faces of cell E; S_E = diag(sqrt(1/2)) on faces with two cells, 1 on the others)
+  float* binv;   // [21 * cpad] upper triangles of s_A^-1 x the weighted block inverses, entry-major (SoA)
+  void* ycell;   // [6 * cpad] float (FP32 levels) or double: the block solutions of the current residual
+  size_t cpad;
+  int blocks;    // 0: not allocated, 1: allocated, 2: set up for the current matrix
   double omega, scale;
   double wj;     // weight of the Jacobi term D^-1 against the auxiliary-space term
   const int* cell_faces;
@@ -517,26 +524,137 @@ __device__ __forceinline__ double residual_scale(const double* __restrict__ rr, 
 
 // b = Pi^T r on the cells.  A cell is the SECOND cell of its z-/y-/x- face when that neighbour exists
 // (weight 1 - fw), the first cell of every other face (weight fw); no index array is read.
-template <typename T>
+// BLOCKS: also y_E = S_E (A_EE)^-1 S_E r_E, the cell's term of the block smoother (the six residuals are in registers
+// anyway); stored per (local face, cell), scaled like b, and summed over the two cells of a face by k_aux_face_prolong.
+template <typename T, bool BLOCKS>
 __global__ void __launch_bounds__(AUX_T)
 k_aux_face_restrict(AuxHex hx, const int* __restrict__ f2f, const T* __restrict__ fw,
-                    const double* __restrict__ r, T* __restrict__ b, const double* __restrict__ rr, double nrows) {
+                    const double* __restrict__ r, T* __restrict__ b, const double* __restrict__ rr, double nrows,
+                    const float* __restrict__ binv, T* __restrict__ y, size_t cpad) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= hx.nx * hx.ny * hx.nz) return;
   const int i = c % hx.nx, j = (c / hx.nx) % hx.ny, k = c / (hx.nx * hx.ny);
   const int cb = hx.cbase(i, j, k);
   const int f[6] = {cb, cb + 1, cb + 2, hx.xp(i, j, k), hx.yp(i, j, k), hx.zp(i, j, k)};
   const bool second[6] = {k > 0, j > 0, i > 0, false, false, false};
+  const double sc = rr ? residual_scale(rr, nrows) : 1.;
   double s = 0.;
+  T rq[6];
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
+    rq[q] = 0;
     const int g = f2f[f[q]];
     if (g < 0) continue;
     const double w1 = (double)fw[f[q]];
     const double w = second[q] ? (w1 > 0. ? 1. - w1 : 0.) : w1;
-    if (w != 0.) s += w * r[g];
+    if (BLOCKS) {
+      const double rg = r[g];
+      rq[q] = (T)(rg * sc);
+      s += w * rg;
+    } else if (w != 0.) {
+      s += w * r[g];
+    }
   }
-  b[c] = (T)(rr ? s * residual_scale(rr, nrows) : s);
+  b[c] = (T)(s * sc);
+  if (BLOCKS) {
+    T m[21];
+#pragma unroll
+    for (int e = 0; e < 21; ++e) m[e] = (T)binv[e * cpad + c];
+    T yq[6] = {0, 0, 0, 0, 0, 0};
+    int e = 0;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+#pragma unroll
+      for (int p2 = q; p2 < 6; ++p2, ++e) {
+        yq[q] += m[e] * rq[p2];
+        if (p2 != q) yq[p2] += m[e] * rq[q];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) y[q * cpad + c] = yq[q];
+  }
+}
+
+// Weighted inverses of the cell blocks of the face system (see mimpy_auxmg::binv).  Off-diagonal entries of a block
+// belong to the cell alone (two faces of a hex mesh share at most one cell) and are looked up in the rows of the
+// assembled matrix; the diagonal is the ASSEMBLED one (1 / dinv: complete also on the interface rows of a slab
+// partition, where the matrix rows hold this rank's half).  A face that is not a flux DOF leaves an identity row.
+// Gauss-Jordan without pivoting in registers: the block is a principal submatrix of an SPD matrix.
+template <bool SELL>
+__global__ void __launch_bounds__(128)
+k_aux_cellblocks(AuxHex hx, const int* __restrict__ f2f, const uint8_t* __restrict__ face_flag,
+                 const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ vals,
+                 const double* __restrict__ dinv, const double* __restrict__ s_a, float* __restrict__ binv, size_t cpad) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= hx.nx * hx.ny * hx.nz) return;
+  const int i = c % hx.nx, j = (c / hx.nx) % hx.ny, k = c / (hx.nx * hx.ny);
+  const int cb = hx.cbase(i, j, k);
+  const int f[6] = {cb, cb + 1, cb + 2, hx.xp(i, j, k), hx.yp(i, j, k), hx.zp(i, j, k)};
+  const bool inner[6] = {k > 0, j > 0, i > 0, i + 1 < hx.nx, j + 1 < hx.ny, k + 1 < hx.nz};
+  int g[6];
+  double wt[6];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    g[q] = f2f[f[q]];
+    const bool two = inner[q] || (face_flag && (face_flag[f[q]] & 3));
+    wt[q] = two ? 0.70710678118654752440 : 1.;
+  }
+  double B[6][6];
+#pragma unroll
+  for (int q = 0; q < 6; ++q)
+#pragma unroll
+    for (int p2 = 0; p2 < 6; ++p2) B[q][p2] = (q == p2) ? 1. : 0.;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    if (g[q] < 0) continue;
+    B[q][q] = 1. / dinv[g[q]];
+    int base, stride, len;
+    if (SELL) {
+      const int s0 = ptr[g[q] >> 5];
+      base = s0 + (g[q] & 31);
+      stride = 32;
+      len = (ptr[(g[q] >> 5) + 1] - s0) >> 5;
+    } else {
+      base = ptr[g[q]];
+      stride = 1;
+      len = ptr[g[q] + 1] - base;
+    }
+    for (int e = 0; e < len; ++e) {
+      const int col = idx[base + e * stride];
+      const double v = vals[base + e * stride];
+#pragma unroll
+      for (int p2 = q + 1; p2 < 6; ++p2)
+        if (col == g[p2]) B[q][p2] = v;   // (a padding entry names its own row: never a partner)
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q)
+#pragma unroll
+    for (int p2 = q + 1; p2 < 6; ++p2) B[p2][q] = B[q][p2];
+#pragma unroll
+  for (int kk = 0; kk < 6; ++kk) {
+    const double pinv = 1. / B[kk][kk];
+#pragma unroll
+    for (int p2 = 0; p2 < 6; ++p2)
+      if (p2 != kk) B[kk][p2] *= pinv;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      if (q == kk) continue;
+      const double fqk = B[q][kk];
+#pragma unroll
+      for (int p2 = 0; p2 < 6; ++p2)
+        if (p2 != kk) B[q][p2] -= fqk * B[kk][p2];
+      B[q][kk] = -fqk * pinv;
+    }
+    B[kk][kk] = pinv;
+  }
+  const double inv_sa = 1. / s_a[0];
+  int e = 0;
+#pragma unroll
+  for (int q = 0; q < 6; ++q)
+#pragma unroll
+    for (int p2 = q; p2 < 6; ++p2, ++e)  // symmetrised: rounding leaves the two triangles a few ulps apart
+      binv[e * cpad + c] = (float)(0.5 * (B[q][p2] + B[p2][q]) * wt[q] * wt[p2] * inv_sa);
 }
 
 // z = [owned rows] D^-1 r + Pi e ; partial sums of r.z over ALL local rows (interface rows hold this
@@ -549,20 +667,30 @@ k_aux_face_prolong(AuxHex hx, int n_owned, double wj, const int* __restrict__ f2
                    const T* __restrict__ e, const double* __restrict__ dinv,
                    const double* __restrict__ r, double* __restrict__ z, double* partials,
                    unsigned int* counter, double* dst, const double* __restrict__ rr, double nrows,
-                   const double* __restrict__ s_a) {
+                   const double* __restrict__ s_a, const T* __restrict__ y, size_t cpad, const double* __restrict__ s_y) {
   __shared__ double sh[32];
   const int nc = hx.nx * hx.ny * hx.nz, sy = hx.nx, sz = hx.nx * hx.ny;
   const double back = rr ? s_a[0] / residual_scale(rr, nrows) : 1.;
+  // block smoother: y holds (s_b / s_A) x the block solutions of both cells of a face (every rank adds its own cells'
+  // on interface rows; the exchange-add of z completes them like the prolongated correction)
+  const double yback = y ? wj * s_y[0] / (rr ? residual_scale(rr, nrows) : 1.) : 0.;
   double acc = 0.;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
     const int i = c % hx.nx, j = (c / hx.nx) % hx.ny, k = c / sz;
     const int cb = hx.cbase(i, j, k);
     const double ec = back * (double)e[c];
-    auto face = [&](int f, int other) {  // other: the first cell of the face, or -1 when this cell is
+    auto face = [&](int f, int other, int q) {  // other: the first cell of the face, or -1 when this cell is
       const int g = f2f[f];
       if (g < 0) return;
       const double rg = r[g], w1 = (double)fw[f];
-      double zz = (g < n_owned) ? wj * dinv[g] * rg : 0.;
+      double zz;
+      if (y) {
+        double ys = (double)y[q * cpad + c];
+        if (other >= 0) ys += (double)y[(5 - q) * cpad + other];
+        zz = yback * ys;
+      } else {
+        zz = (g < n_owned) ? wj * dinv[g] * rg : 0.;
+      }
       if (other >= 0) {
         if (w1 > 0.) zz += w1 * (back * (double)e[other]) + (1. - w1) * ec;
       } else {
@@ -571,12 +699,12 @@ k_aux_face_prolong(AuxHex hx, int n_owned, double wj, const int* __restrict__ f2
       z[g] = zz;
       acc += rg * zz;
     };
-    face(cb, k > 0 ? c - sz : -1);
-    face(cb + 1, j > 0 ? c - sy : -1);
-    face(cb + 2, i > 0 ? c - 1 : -1);
-    if (i + 1 == hx.nx) face(hx.xp(i, j, k), -1);
-    if (j + 1 == hx.ny) face(hx.yp(i, j, k), -1);
-    if (k + 1 == hx.nz) face(hx.zp(i, j, k), -1);
+    face(cb, k > 0 ? c - sz : -1, 0);
+    face(cb + 1, j > 0 ? c - sy : -1, 1);
+    face(cb + 2, i > 0 ? c - 1 : -1, 2);
+    if (i + 1 == hx.nx) face(hx.xp(i, j, k), -1, 3);
+    if (j + 1 == hx.ny) face(hx.yp(i, j, k), -1, 4);
+    if (k + 1 == hx.nz) face(hx.zp(i, j, k), -1, 5);
   }
   const double v[1] = {acc};
   finish_reduction<1>(v, partials, counter, dst, sh);
@@ -598,7 +726,14 @@ static int aux_apply32(mimpy_ctx* ctx, mimpy_auxmg* h, const AuxHex& hx, const d
   AuxLevel32* L = h->lev32;
   const double* rr = ctx->scalars + S_RR;  // ||r||^2 of the PCG: current when this runs (k_init / k_update_xr_gen)
   const double nrows = (double)(h->flux_dof > 0 ? h->flux_dof : 1);
-  k_aux_face_restrict<float><<<aux_blocks(h->nc), AUX_T, 0, st>>>(hx, h->face_to_flux, h->fw32, r, L[0].b, rr, nrows);
+  const bool blocks = h->blocks == 2;
+  float* y = blocks ? static_cast<float*>(h->ycell) : nullptr;
+  if (blocks)
+    k_aux_face_restrict<float, true><<<aux_blocks(h->nc), AUX_T, 0, st>>>(hx, h->face_to_flux, h->fw32, r, L[0].b, rr, nrows,
+                                                                         h->binv, y, h->cpad);
+  else
+    k_aux_face_restrict<float, false><<<aux_blocks(h->nc), AUX_T, 0, st>>>(hx, h->face_to_flux, h->fw32, r, L[0].b, rr, nrows,
+                                                                          nullptr, nullptr, 0);
   const int last = h->nlev - 1;
   for (int l = 0; l < last; ++l) {
     k_aux_presmooth<float><<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], h->omega);
@@ -609,7 +744,8 @@ static int aux_apply32(mimpy_ctx* ctx, mimpy_auxmg* h, const AuxHex& hx, const d
     k_aux_prolong_smooth<float, false><<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], L[l + 1], h->omega, h->scale, nullptr, nullptr, nullptr);
   const int grid = ctx->sm_count * 8;
   k_aux_face_prolong<float><<<grid, RED_THREADS, 0, st>>>(hx, n_owned, h->wj, h->face_to_flux, h->fw32, L[0].x2, dinv, r, z,
-                                                          ctx->partials, ctx->counters + 4, rz_dst, rr, nrows, h->sdev);
+                                                          ctx->partials, ctx->counters + 4, rz_dst, rr, nrows, h->sdev, y,
+                                                          h->cpad, h->sdev);
   KERNEL_CHECK();
   return MIMPY_OK;
 }
@@ -681,7 +817,7 @@ __global__ void __launch_bounds__(256) k_aux_dinv32(int n, const double* __restr
 int mimpy_auxmg_fused(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, int n, mimpy_aux_fused* out) {
   // opt-in (MIMPY_B200_AUX_FUSED_P): measured 2.82 ms against 2.79 ms per iteration at 256^3 -- the 0.8 GB of z it saves
   // are paid back by the face-indexed gather of e and the second pass over D^-1; kept for smaller caches / other meshes
-  if (!h->use32 || ctx->world != 1 || n != h->flux_dof || !getenv("MIMPY_B200_AUX_FUSED_P")) return 0;
+  if (!h->use32 || ctx->world != 1 || n != h->flux_dof || h->blocks == 2 || !getenv("MIMPY_B200_AUX_FUSED_P")) return 0;
   k_aux_dinv32<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, dinv, h->dinv32);
   if (cudaGetLastError() != cudaSuccess) return 0;
   out->dinv32 = h->dinv32;
@@ -700,7 +836,8 @@ int mimpy_auxmg_apply_p(mimpy_ctx* ctx, mimpy_auxmg* h, const double* r, double*
   const double* rr = ctx->scalars + S_RR;
   const double nrows = (double)(h->flux_dof > 0 ? h->flux_dof : 1);
   const int grid = ctx->sm_count * 8;
-  k_aux_face_restrict<float><<<aux_blocks(h->nc), AUX_T, 0, st>>>(hx, h->face_to_flux, h->fw32, r, L[0].b, rr, nrows);
+  k_aux_face_restrict<float, false><<<aux_blocks(h->nc), AUX_T, 0, st>>>(hx, h->face_to_flux, h->fw32, r, L[0].b, rr, nrows,
+                                                                        nullptr, nullptr, 0);
   const int last = h->nlev - 1;
   for (int l = 0; l < last; ++l) {
     k_aux_presmooth<float><<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], h->omega);
@@ -733,7 +870,14 @@ int mimpy_auxmg_apply(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, const 
   hx.L = hx.nx * hx.ny + hx.nx * (hx.ny + 1) + (hx.nx + 1) * hx.ny;
   hx.xrow = 3 * hx.nx + 1;
   if (h->use32) return aux_apply32(ctx, h, hx, dinv, r, z, rz_dst, n_owned);
-  k_aux_face_restrict<double><<<aux_blocks(h->nc), AUX_T, 0, st>>>(hx, h->face_to_flux, h->fw, r, L[0].b, nullptr, 1.);
+  const bool blocks = h->blocks == 2;
+  double* y = blocks ? static_cast<double*>(h->ycell) : nullptr;
+  if (blocks)
+    k_aux_face_restrict<double, true><<<aux_blocks(h->nc), AUX_T, 0, st>>>(hx, h->face_to_flux, h->fw, r, L[0].b, nullptr, 1.,
+                                                                          h->binv, y, h->cpad);
+  else
+    k_aux_face_restrict<double, false><<<aux_blocks(h->nc), AUX_T, 0, st>>>(hx, h->face_to_flux, h->fw, r, L[0].b, nullptr, 1.,
+                                                                           nullptr, nullptr, 0);
   const int last = h->nlev - 1;
   auto ghosts = [&](double* v, const AuxLevel& lv) {  // both ghost layers of a level vector
     mimpy_xchg x;
@@ -775,7 +919,8 @@ int mimpy_auxmg_apply(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, const 
   }
   const int grid = ctx->sm_count * 8;
   k_aux_face_prolong<double><<<grid, RED_THREADS, 0, st>>>(hx, n_owned, h->wj, h->face_to_flux, h->fw, L[0].x2, dinv, r, z,
-                                                           ctx->partials, ctx->counters + 4, rz_dst, nullptr, 1., nullptr);
+                                                           ctx->partials, ctx->counters + 4, rz_dst, nullptr, 1., nullptr, y,
+                                                           h->cpad, h->sdev);
   KERNEL_CHECK();
   return MIMPY_OK;
 }
@@ -892,6 +1037,14 @@ int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
     for (int l = 0; l < h->nlev; ++l) total32 += 7 * pad(((size_t)h->lev[l].n + 1) / 2);
   if (h->use32) total32 += pad(((size_t)h->nf + 1) / 2) + pad(((size_t)h->flux_dof + 1) / 2);
   total += total32 + pad(8);
+  // cell-block smoother: 21 floats per cell + the block solutions (6 per cell, in the type of the levels)
+  h->blocks = 0;
+  h->cpad = pad((size_t)h->nc);
+  {
+    const char* env = getenv("MIMPY_B200_AUX_BLOCKS");
+    if (!(env && env[0] == '0')) h->blocks = 1;
+  }
+  if (h->blocks) total += pad((21 * h->cpad + 1) / 2) + (h->use32 ? pad((6 * h->cpad + 1) / 2) : 6 * h->cpad);
   static bool pool_configured[64] = {false};  // per device
   bool& pool_done = pool_configured[ctx->device & 63];
   if (!pool_done) {  // keep freed blocks in the pool: set-up is repeated every Newton step
@@ -955,7 +1108,36 @@ int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
       M.has_lo = M.has_hi = 0;
     }
   }
+  h->binv = nullptr;
+  h->ycell = nullptr;
+  if (h->blocks) {
+    h->binv = reinterpret_cast<float*>(take((21 * h->cpad + 1) / 2));
+    h->ycell = take(h->use32 ? (6 * h->cpad + 1) / 2 : 6 * h->cpad);
+  }
   *handle = h;
+  return MIMPY_OK;
+}
+
+int mimpy_b200_auxmg_cellblocks(mimpy_ctx* ctx, void* handle, const mimpy_mesh_view* mesh, const mimpy_symbolic* sym,
+                                const int32_t* ptr, const int32_t* idx, const double* vals, int32_t sell,
+                                const double* diag_inv) {
+  REQUIRE(ctx && handle && mesh && sym && ptr && idx && vals && diag_inv, "NULL argument");
+  mimpy_auxmg* h = static_cast<mimpy_auxmg*>(handle);
+  REQUIRE(h->nc == mesh->nc && h->nf == mesh->nf && h->flux_dof == sym->flux_dof, "handle/mesh mismatch");
+  if (!h->blocks) return MIMPY_OK;  // switched off (MIMPY_B200_AUX_BLOCKS=0): the Jacobi term stays
+  AuxHex hx;
+  hx.nx = mesh->hex_nx; hx.ny = mesh->hex_ny; hx.nz = mesh->hex_nz;
+  hx.L = hx.nx * hx.ny + hx.nx * (hx.ny + 1) + (hx.nx + 1) * hx.ny;
+  hx.xrow = 3 * hx.nx + 1;
+  const int grid = (h->nc + 127) / 128;
+  if (sell)
+    k_aux_cellblocks<true><<<grid, 128, 0, ctx->stream>>>(hx, sym->face_to_flux, sym->face_flag, ptr, idx, vals, diag_inv,
+                                                          h->sdev, h->binv, h->cpad);
+  else
+    k_aux_cellblocks<false><<<grid, 128, 0, ctx->stream>>>(hx, sym->face_to_flux, sym->face_flag, ptr, idx, vals, diag_inv,
+                                                           h->sdev, h->binv, h->cpad);
+  KERNEL_CHECK();
+  h->blocks = 2;
   return MIMPY_OK;
 }
 
@@ -1002,7 +1184,8 @@ int mimpy_b200_auxmg_setup(mimpy_ctx* ctx, void* handle, const mimpy_mesh_view* 
                                                      sym->face_flag, h->tsum, mesh->cell_volume, alpha, c_diag,
                                                      h->wc, h->fw, h->use32 ? h->fw32 : nullptr, h->lev[0]);
   }
-  if (h->use32) k_aux_scale<<<1, 32, 0, st>>>(tau ? tau : h->wc, h->nc * 6 < 256 ? h->nc * 6 : 256, h->sdev);
+  k_aux_scale<<<1, 32, 0, st>>>(tau ? tau : h->wc, h->nc * 6 < 256 ? h->nc * 6 : 256, h->sdev);
+  if (h->blocks == 2) h->blocks = 1;  // the blocks of the previous matrix are stale until auxmg_cellblocks runs again
   for (int l = 0; l < h->nlev; ++l) {
     if (l > 0) k_aux_coarsen<<<aux_blocks(h->lev[l].n), AUX_T, 0, st>>>(h->lev[l - 1], h->lev[l]);
     k_aux_diag<<<aux_blocks(h->lev[l].n), AUX_T, 0, st>>>(h->lev[l], h->lev32[l], h->use32 ? h->sdev : nullptr);

@@ -471,6 +471,12 @@ class HybridSystem(object):
                     self.aux = h
                 ctx.call("mimpy_b200_auxmg_setup", self.aux, C.byref(mv), C.byref(self.plan.s), ptr(self.w_e),
                          self.alpha, ptr(c_diag), ptr(tau_in))
+                # cell-block smoother: inverses of the 6 x 6 blocks of the assembled face system (csrc/auxmg.cu)
+                sell = self.layout == "sell"
+                ctx.call("mimpy_b200_auxmg_cellblocks", self.aux, C.byref(mv), C.byref(self.plan.s),
+                         ptr(self.sell_ptr if sell else self.plan.m_indptr),
+                         ptr(self.sell_cols if sell else self.plan.m_indices), ptr(self.a_vals), 1 if sell else 0,
+                         ptr(self.a_diag_inv))
 
     def release(self):
         """Gives the SELL value buffer back to the plan (its padding is still zero) -- called by __del__."""
