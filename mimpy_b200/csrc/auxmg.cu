@@ -386,12 +386,12 @@ __global__ void __launch_bounds__(AUX_T) k_aux_restrict(AuxLevelT<T> F, AuxLevel
 // DOT (level 0 of the fused update of p): b . x2 summed on the way (in FP64) -- the cell-space half of r . z.
 template <typename T, bool DOT>
 __global__ void __launch_bounds__(AUX_T)
-k_aux_prolong_smooth(AuxLevelT<T> F, AuxLevelT<T> C, double omega_, double scale_, double* partials, unsigned int* counter,
-                     double* dst) {
+k_aux_prolong_smooth(AuxLevelT<T> F, AuxLevelT<T> C, double omega_, const double* __restrict__ scale_dev, double* partials,
+                     unsigned int* counter, double* dst) {
   __shared__ double sh[32];
   const T* __restrict__ e = C.x2;
   const T* __restrict__ x = F.x;
-  const T omega = (T)omega_, scale = (T)scale_;
+  const T omega = (T)omega_, scale = (T)scale_dev[0];
   const int cs_y = C.nx, cs_z = C.nx * C.ny;
   const int sx = 1, sy = F.nx, sz = F.nx * F.ny;
   double acc = 0.;
@@ -430,6 +430,42 @@ k_aux_coarse_solve(AuxLevelT<T> L, const double* __restrict__ cinv, const double
   double s = 0.;
   for (int c = 0; c < L.n; ++c) s += cinv[r * L.n + c] * (double)L.b[c];
   L.x2[r] = (T)(s_a ? s / s_a[0] : s);
+}
+
+// Over-correction of the piecewise-constant coarse space, chosen from the anisotropy of the cell operator: sums of the
+// couplings of level 0 per direction (deterministic two-stage reduction; all-reduced over the ranks of a partition), then
+//   scale = 1.8 - 0.5 log(ratio) / log(30), clamped to [1.3, 1.8],  ratio = largest / smallest directional sum.
+// Measured with the cell-block smoother (iterations to a saddle residual of 1e-8): 256^3 with statistically isotropic
+// couplings 60 / 50 / 45 at 1.5 / 1.65 / 1.8; C2 (flat cells, k_v = 0.1 k_h: ratio ~60) 245 / 265 / 310 / 350 at 1.3 / 1.5 /
+// 1.65 / 1.8.  A prototype over six coefficient fields shows the same trend (isotropic: the larger the better up to 2,
+// ratio >= 60: 1.3).
+__global__ void __launch_bounds__(RED_THREADS)
+k_aux_aniso_sums(AuxLevel L, double* partials, unsigned int* counter, double* dst) {
+  __shared__ double sh[32];
+  double v[3] = {0., 0., 0.};
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < L.n; c += gridDim.x * blockDim.x) {
+    v[0] += L.tx[c];
+    v[1] += L.ty[c];
+    v[2] += L.tz[c];
+  }
+  finish_reduction<3>(v, partials, counter, dst, sh);
+}
+__global__ void k_aux_pick_scale(const double* __restrict__ sums, double fixed, double* __restrict__ scale_out) {
+  if (fixed > 0.) {
+    scale_out[0] = fixed;
+    return;
+  }
+  double hi = 0., lo = 1e300;
+  for (int d = 0; d < 3; ++d) {
+    if (sums[d] > 0.) {
+      hi = fmax(hi, sums[d]);
+      lo = fmin(lo, sums[d]);
+    }
+  }
+  double sc = 1.8;
+  if (hi > 0. && lo < 1e300 && hi > lo) sc = 1.8 - 0.5 * log(hi / lo) / log(30.);
+  sc = fmin(1.8, fmax(1.3, sc));
+  scale_out[0] = floor(sc * 64. + 0.5) / 64.;  // (a few bits only: nothing hangs on the last digits of the sums)
 }
 
 // s_A = 2^-e with 2^e ~ the largest of the first half transmissibilities (any representative magnitude will do)
@@ -584,7 +620,8 @@ template <bool SELL>
 __global__ void __launch_bounds__(128)
 k_aux_cellblocks(AuxHex hx, const int* __restrict__ f2f, const uint8_t* __restrict__ face_flag,
                  const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ vals,
-                 const double* __restrict__ dinv, const double* __restrict__ s_a, float* __restrict__ binv, size_t cpad) {
+                 const double* __restrict__ dinv, const double* __restrict__ s_a, float* __restrict__ binv, size_t cpad,
+                 double w_two) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= hx.nx * hx.ny * hx.nz) return;
   const int i = c % hx.nx, j = (c / hx.nx) % hx.ny, k = c / (hx.nx * hx.ny);
@@ -597,7 +634,7 @@ k_aux_cellblocks(AuxHex hx, const int* __restrict__ f2f, const uint8_t* __restri
   for (int q = 0; q < 6; ++q) {
     g[q] = f2f[f[q]];
     const bool two = inner[q] || (face_flag && (face_flag[f[q]] & 3));
-    wt[q] = two ? 0.70710678118654752440 : 1.;
+    wt[q] = two ? w_two : 1.;
   }
   double B[6][6];
 #pragma unroll
@@ -713,6 +750,7 @@ k_aux_face_prolong(AuxHex hx, int n_owned, double wj, const int* __restrict__ f2
 static int aux_free(mimpy_ctx* ctx, mimpy_auxmg* h) {
   if (!h) return MIMPY_OK;
   if (h->slab) cudaFreeAsync(h->slab, ctx->stream);  // stream-ordered: no device synchronisation
+  if (h->binv) cudaFreeAsync(h->binv, ctx->stream);
   delete h;
   return MIMPY_OK;
 }
@@ -741,7 +779,7 @@ static int aux_apply32(mimpy_ctx* ctx, mimpy_auxmg* h, const AuxHex& hx, const d
   }
   k_aux_coarse_solve<float><<<1, AUX_COARSEST, 0, st>>>(L[last], h->cinv, h->sdev);
   for (int l = last - 1; l >= 0; --l)
-    k_aux_prolong_smooth<float, false><<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], L[l + 1], h->omega, h->scale, nullptr, nullptr, nullptr);
+    k_aux_prolong_smooth<float, false><<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], L[l + 1], h->omega, h->sdev + 1, nullptr, nullptr, nullptr);
   const int grid = ctx->sm_count * 8;
   k_aux_face_prolong<float><<<grid, RED_THREADS, 0, st>>>(hx, n_owned, h->wj, h->face_to_flux, h->fw32, L[0].x2, dinv, r, z,
                                                           ctx->partials, ctx->counters + 4, rz_dst, rr, nrows, h->sdev, y,
@@ -845,11 +883,11 @@ int mimpy_auxmg_apply_p(mimpy_ctx* ctx, mimpy_auxmg* h, const double* r, double*
   }
   k_aux_coarse_solve<float><<<1, AUX_COARSEST, 0, st>>>(L[last], h->cinv, h->sdev);
   for (int l = last - 1; l >= 1; --l)
-    k_aux_prolong_smooth<float, false><<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], L[l + 1], h->omega, h->scale, nullptr, nullptr, nullptr);
+    k_aux_prolong_smooth<float, false><<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], L[l + 1], h->omega, h->sdev + 1, nullptr, nullptr, nullptr);
   if (last >= 1) {
     // (as many blocks as the reduction has partial slots for: neighbouring cells stay neighbours in time)
     const int dot_grid = aux_blocks(L[0].n) < 8192 ? aux_blocks(L[0].n) : 8192;
-    k_aux_prolong_smooth<float, true><<<dot_grid, AUX_T, 0, st>>>(L[0], L[1], h->omega, h->scale, ctx->partials, ctx->counters + 4,
+    k_aux_prolong_smooth<float, true><<<dot_grid, AUX_T, 0, st>>>(L[0], L[1], h->omega, h->sdev + 1, ctx->partials, ctx->counters + 4,
                                                                ctx->scalars + S_BE);
   } else {  // a mesh of one level: the coarse solve is the whole cycle
     k_aux_dot32<<<1, AUX_T, 0, st>>>(L[0].n, L[0].b, L[0].x2, ctx->scalars + S_BE);
@@ -906,7 +944,7 @@ int mimpy_auxmg_apply(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, const 
     }
     k_aux_coarse_solve<double><<<1, AUX_COARSEST, 0, st>>>(G[glast], h->cinv, nullptr);
     for (int l = glast - 1; l >= 0; --l)
-      k_aux_prolong_smooth<double, false><<<aux_blocks(G[l].n), AUX_T, 0, st>>>(G[l], G[l + 1], h->omega, h->scale, nullptr, nullptr, nullptr);
+      k_aux_prolong_smooth<double, false><<<aux_blocks(G[l].n), AUX_T, 0, st>>>(G[l], G[l + 1], h->omega, h->sdev + 1, nullptr, nullptr, nullptr);
     const int nxy = L[last].nx * L[last].ny;
     k_aux_global_extract<<<aux_blocks(L[last].n + 2 * nxy), AUX_T, 0, st>>>(L[last].n, nxy, ctx->rank, ctx->world, G[0].x2,
                                                                         L[last].x2);
@@ -914,7 +952,7 @@ int mimpy_auxmg_apply(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, const 
     k_aux_coarse_solve<double><<<1, AUX_COARSEST, 0, st>>>(L[last], h->cinv, nullptr);
   }
   for (int l = last - 1; l >= 0; --l) {
-    k_aux_prolong_smooth<double, false><<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], L[l + 1], h->omega, h->scale, nullptr, nullptr, nullptr);
+    k_aux_prolong_smooth<double, false><<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], L[l + 1], h->omega, h->sdev + 1, nullptr, nullptr, nullptr);
     if (h->global && l > 0 && (rc = ghosts(L[l].x2, L[l]))) return rc;
   }
   const int grid = ctx->sm_count * 8;
@@ -942,7 +980,7 @@ int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
   // (scripts/exp_iters.py, rtol 1e-8 on the saddle residual): (0.8, 2.0) 110 iterations at 256^3 and 1600 on C2,
   // (0.9, 1.5) 95 and 1085, (1.0, 1.3) 105 and 960, (0.9, 1.7) 95 and 1255, scale 1.0: 135 at 128^3, 3.0: 180
   h->omega = 0.9;
-  h->scale = 1.5;
+  h->scale = 0.;  // 0: chosen at set-up from the anisotropy of the cell operator (k_aux_pick_scale)
   h->wj = 1.0;
   if (const char* e = getenv("MIMPY_B200_AUX_WJ")) h->wj = atof(e);
   if (const char* e = getenv("MIMPY_B200_AUX_OMEGA")) h->omega = atof(e);
@@ -1037,14 +1075,9 @@ int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
     for (int l = 0; l < h->nlev; ++l) total32 += 7 * pad(((size_t)h->lev[l].n + 1) / 2);
   if (h->use32) total32 += pad(((size_t)h->nf + 1) / 2) + pad(((size_t)h->flux_dof + 1) / 2);
   total += total32 + pad(8);
-  // cell-block smoother: 21 floats per cell + the block solutions (6 per cell, in the type of the levels)
+  // cell-block smoother: storage comes with the first mimpy_b200_auxmg_cellblocks call
   h->blocks = 0;
   h->cpad = pad((size_t)h->nc);
-  {
-    const char* env = getenv("MIMPY_B200_AUX_BLOCKS");
-    if (!(env && env[0] == '0')) h->blocks = 1;
-  }
-  if (h->blocks) total += pad((21 * h->cpad + 1) / 2) + (h->use32 ? pad((6 * h->cpad + 1) / 2) : 6 * h->cpad);
   static bool pool_configured[64] = {false};  // per device
   bool& pool_done = pool_configured[ctx->device & 63];
   if (!pool_done) {  // keep freed blocks in the pool: set-up is repeated every Newton step
@@ -1110,10 +1143,6 @@ int mimpy_b200_auxmg_create(mimpy_ctx* ctx, const mimpy_mesh_view* mesh, const m
   }
   h->binv = nullptr;
   h->ycell = nullptr;
-  if (h->blocks) {
-    h->binv = reinterpret_cast<float*>(take((21 * h->cpad + 1) / 2));
-    h->ycell = take(h->use32 ? (6 * h->cpad + 1) / 2 : 6 * h->cpad);
-  }
   *handle = h;
   return MIMPY_OK;
 }
@@ -1124,18 +1153,38 @@ int mimpy_b200_auxmg_cellblocks(mimpy_ctx* ctx, void* handle, const mimpy_mesh_v
   REQUIRE(ctx && handle && mesh && sym && ptr && idx && vals && diag_inv, "NULL argument");
   mimpy_auxmg* h = static_cast<mimpy_auxmg*>(handle);
   REQUIRE(h->nc == mesh->nc && h->nf == mesh->nf && h->flux_dof == sym->flux_dof, "handle/mesh mismatch");
-  if (!h->blocks) return MIMPY_OK;  // switched off (MIMPY_B200_AUX_BLOCKS=0): the Jacobi term stays
+  {
+    const char* env = getenv("MIMPY_B200_AUX_BLOCKS");
+    if (env && env[0] == '0') return MIMPY_OK;  // switched off: the Jacobi term stays
+  }
+  if (!h->binv) {  // 21 floats per cell + the block solutions (6 per cell, in the type of the levels)
+    const size_t bytes = sizeof(float) * 21 * h->cpad + (h->use32 ? sizeof(float) : sizeof(double)) * 6 * h->cpad;
+    void* blk = nullptr;
+    cudaError_t e = cudaMallocAsync(&blk, bytes, ctx->stream);
+    if (e != cudaSuccess) {
+      mimpy_set_error("auxmg_cellblocks: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      return MIMPY_E_CUDA;
+    }
+    h->binv = static_cast<float*>(blk);
+    h->ycell = h->binv + 21 * h->cpad;
+    h->blocks = 1;
+  }
   AuxHex hx;
   hx.nx = mesh->hex_nx; hx.ny = mesh->hex_ny; hx.nz = mesh->hex_nz;
   hx.L = hx.nx * hx.ny + hx.nx * (hx.ny + 1) + (hx.nx + 1) * hx.ny;
   hx.xrow = 3 * hx.nx + 1;
   const int grid = (h->nc + 127) / 128;
+  // weight of a block on a face with two cells (the two blocks of a face add up): 1/2 measured best (prototype, 24^3 and
+  // the C2 shape: 0.5 -> 28 / 90 iterations, 0.75 -> 32 / 92, 1.0 -> 36 / 97)
+  double w_two = sqrt(0.5);
+  if (const char* e = getenv("MIMPY_B200_AUX_BW")) w_two = sqrt(atof(e));
   if (sell)
     k_aux_cellblocks<true><<<grid, 128, 0, ctx->stream>>>(hx, sym->face_to_flux, sym->face_flag, ptr, idx, vals, diag_inv,
-                                                          h->sdev, h->binv, h->cpad);
+                                                          h->sdev, h->binv, h->cpad, w_two);
   else
     k_aux_cellblocks<false><<<grid, 128, 0, ctx->stream>>>(hx, sym->face_to_flux, sym->face_flag, ptr, idx, vals, diag_inv,
-                                                           h->sdev, h->binv, h->cpad);
+                                                           h->sdev, h->binv, h->cpad, w_two);
   KERNEL_CHECK();
   h->blocks = 2;
   return MIMPY_OK;
@@ -1189,6 +1238,19 @@ int mimpy_b200_auxmg_setup(mimpy_ctx* ctx, void* handle, const mimpy_mesh_view* 
   for (int l = 0; l < h->nlev; ++l) {
     if (l > 0) k_aux_coarsen<<<aux_blocks(h->lev[l].n), AUX_T, 0, st>>>(h->lev[l - 1], h->lev[l]);
     k_aux_diag<<<aux_blocks(h->lev[l].n), AUX_T, 0, st>>>(h->lev[l], h->lev32[l], h->use32 ? h->sdev : nullptr);
+  }
+  {  // over-correction factor -> sdev[1]
+    const int n0 = h->lev[0].n;
+    const int grid = aux_blocks(n0) < ctx->sm_count * 4 ? aux_blocks(n0) : ctx->sm_count * 4;
+    if (h->scale <= 0.) {
+      k_aux_aniso_sums<<<grid, RED_THREADS, 0, st>>>(h->lev[0], ctx->partials, ctx->counters + 6, h->sdev + 2);
+      KERNEL_CHECK();
+      if (ctx->world > 1) {
+        rc = mimpy_allreduce_f64(ctx, h->sdev + 2, 3);
+        if (rc) return rc;
+      }
+    }
+    k_aux_pick_scale<<<1, 1, 0, st>>>(h->sdev + 2, h->scale, h->sdev + 1);
   }
   const AuxLevel& last = h->lev[h->nlev - 1];
   if (h->global) {
