@@ -87,7 +87,7 @@ struct mimpy_auxmg {
   // additive Schwarz sum over the cells, sum_E P_E^T S_E (A_EE)^-1 S_E P_E (A_EE: the block of the face system on
   // the faces of cell E; S_E = diag(sqrt(1/2)) on faces with two cells, 1 on the others)
   float* binv;   // [21 * cpad] upper triangles of s_A^-1 x the weighted block inverses, entry-major (SoA)
-  void* ycell;   // [6 * cpad] float (FP32 levels) or double: the block solutions of the current residual
+  void* ycell;   // [6 * cpad] float: the block solutions of the current residual
   size_t cpad;
   int blocks;    // 0: not allocated, 1: allocated, 2: set up for the current matrix
   double omega, scale;
@@ -566,7 +566,7 @@ template <typename T, bool BLOCKS>
 __global__ void __launch_bounds__(AUX_T)
 k_aux_face_restrict(AuxHex hx, const int* __restrict__ f2f, const T* __restrict__ fw,
                     const double* __restrict__ r, T* __restrict__ b, const double* __restrict__ rr, double nrows,
-                    const float* __restrict__ binv, T* __restrict__ y, size_t cpad) {
+                    const float* __restrict__ binv, float* __restrict__ y, size_t cpad, const double* __restrict__ ry) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= hx.nx * hx.ny * hx.nz) return;
   const int i = c % hx.nx, j = (c / hx.nx) % hx.ny, k = c / (hx.nx * hx.ny);
@@ -574,8 +574,10 @@ k_aux_face_restrict(AuxHex hx, const int* __restrict__ f2f, const T* __restrict_
   const int f[6] = {cb, cb + 1, cb + 2, hx.xp(i, j, k), hx.yp(i, j, k), hx.zp(i, j, k)};
   const bool second[6] = {k > 0, j > 0, i > 0, false, false, false};
   const double sc = rr ? residual_scale(rr, nrows) : 1.;
+  // the block solves run in FP32 whatever the type of the levels (scaled by a power of two ~ 1 / rms(r) of this rank)
+  const double scy = (BLOCKS && ry) ? residual_scale(ry, nrows) : 1.;
   double s = 0.;
-  T rq[6];
+  float rq[6];
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
     rq[q] = 0;
@@ -585,7 +587,7 @@ k_aux_face_restrict(AuxHex hx, const int* __restrict__ f2f, const T* __restrict_
     const double w = second[q] ? (w1 > 0. ? 1. - w1 : 0.) : w1;
     if (BLOCKS) {
       const double rg = r[g];
-      rq[q] = (T)(rg * sc);
+      rq[q] = (float)(rg * scy);
       s += w * rg;
     } else if (w != 0.) {
       s += w * r[g];
@@ -593,10 +595,10 @@ k_aux_face_restrict(AuxHex hx, const int* __restrict__ f2f, const T* __restrict_
   }
   b[c] = (T)(s * sc);
   if (BLOCKS) {
-    T m[21];
+    float m[21];
 #pragma unroll
-    for (int e = 0; e < 21; ++e) m[e] = (T)binv[e * cpad + c];
-    T yq[6] = {0, 0, 0, 0, 0, 0};
+    for (int e = 0; e < 21; ++e) m[e] = binv[e * cpad + c];
+    float yq[6] = {0, 0, 0, 0, 0, 0};
     int e = 0;
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
@@ -704,13 +706,14 @@ k_aux_face_prolong(AuxHex hx, int n_owned, double wj, const int* __restrict__ f2
                    const T* __restrict__ e, const double* __restrict__ dinv,
                    const double* __restrict__ r, double* __restrict__ z, double* partials,
                    unsigned int* counter, double* dst, const double* __restrict__ rr, double nrows,
-                   const double* __restrict__ s_a, const T* __restrict__ y, size_t cpad, const double* __restrict__ s_y) {
+                   const double* __restrict__ s_a, const float* __restrict__ y, size_t cpad, const double* __restrict__ s_y,
+                   const double* __restrict__ ry) {
   __shared__ double sh[32];
   const int nc = hx.nx * hx.ny * hx.nz, sy = hx.nx, sz = hx.nx * hx.ny;
   const double back = rr ? s_a[0] / residual_scale(rr, nrows) : 1.;
   // block smoother: y holds (s_b / s_A) x the block solutions of both cells of a face (every rank adds its own cells'
   // on interface rows; the exchange-add of z completes them like the prolongated correction)
-  const double yback = y ? wj * s_y[0] / (rr ? residual_scale(rr, nrows) : 1.) : 0.;
+  const double yback = y ? wj * s_y[0] / (ry ? residual_scale(ry, nrows) : 1.) : 0.;
   double acc = 0.;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
     const int i = c % hx.nx, j = (c / hx.nx) % hx.ny, k = c / sz;
@@ -768,10 +771,10 @@ static int aux_apply32(mimpy_ctx* ctx, mimpy_auxmg* h, const AuxHex& hx, const d
   float* y = blocks ? static_cast<float*>(h->ycell) : nullptr;
   if (blocks)
     k_aux_face_restrict<float, true><<<aux_blocks(h->nc), AUX_T, 0, st>>>(hx, h->face_to_flux, h->fw32, r, L[0].b, rr, nrows,
-                                                                         h->binv, y, h->cpad);
+                                                                         h->binv, y, h->cpad, rr);
   else
     k_aux_face_restrict<float, false><<<aux_blocks(h->nc), AUX_T, 0, st>>>(hx, h->face_to_flux, h->fw32, r, L[0].b, rr, nrows,
-                                                                          nullptr, nullptr, 0);
+                                                                          nullptr, nullptr, 0, nullptr);
   const int last = h->nlev - 1;
   for (int l = 0; l < last; ++l) {
     k_aux_presmooth<float><<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], h->omega);
@@ -783,7 +786,7 @@ static int aux_apply32(mimpy_ctx* ctx, mimpy_auxmg* h, const AuxHex& hx, const d
   const int grid = ctx->sm_count * 8;
   k_aux_face_prolong<float><<<grid, RED_THREADS, 0, st>>>(hx, n_owned, h->wj, h->face_to_flux, h->fw32, L[0].x2, dinv, r, z,
                                                           ctx->partials, ctx->counters + 4, rz_dst, rr, nrows, h->sdev, y,
-                                                          h->cpad, h->sdev);
+                                                          h->cpad, h->sdev, rr);
   KERNEL_CHECK();
   return MIMPY_OK;
 }
@@ -875,7 +878,7 @@ int mimpy_auxmg_apply_p(mimpy_ctx* ctx, mimpy_auxmg* h, const double* r, double*
   const double nrows = (double)(h->flux_dof > 0 ? h->flux_dof : 1);
   const int grid = ctx->sm_count * 8;
   k_aux_face_restrict<float, false><<<aux_blocks(h->nc), AUX_T, 0, st>>>(hx, h->face_to_flux, h->fw32, r, L[0].b, rr, nrows,
-                                                                        nullptr, nullptr, 0);
+                                                                        nullptr, nullptr, 0, nullptr);
   const int last = h->nlev - 1;
   for (int l = 0; l < last; ++l) {
     k_aux_presmooth<float><<<aux_blocks(L[l].n), AUX_T, 0, st>>>(L[l], h->omega);
@@ -909,13 +912,17 @@ int mimpy_auxmg_apply(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, const 
   hx.xrow = 3 * hx.nx + 1;
   if (h->use32) return aux_apply32(ctx, h, hx, dinv, r, z, rz_dst, n_owned);
   const bool blocks = h->blocks == 2;
-  double* y = blocks ? static_cast<double*>(h->ycell) : nullptr;
+  float* y = blocks ? static_cast<float*>(h->ycell) : nullptr;
+  // scale of the FP32 block solves: this rank's ||r||^2 (k_update_xr_gen's partial sum until apply_aux all-reduces it
+  // AFTER this application: the same value in the restriction and in the prolongation)
+  const double* ry = ctx->scalars + S_RR;
+  const double nrows_y = (double)(h->flux_dof > 0 ? h->flux_dof : 1);
   if (blocks)
-    k_aux_face_restrict<double, true><<<aux_blocks(h->nc), AUX_T, 0, st>>>(hx, h->face_to_flux, h->fw, r, L[0].b, nullptr, 1.,
-                                                                          h->binv, y, h->cpad);
+    k_aux_face_restrict<double, true><<<aux_blocks(h->nc), AUX_T, 0, st>>>(hx, h->face_to_flux, h->fw, r, L[0].b, nullptr,
+                                                                          nrows_y, h->binv, y, h->cpad, ry);
   else
     k_aux_face_restrict<double, false><<<aux_blocks(h->nc), AUX_T, 0, st>>>(hx, h->face_to_flux, h->fw, r, L[0].b, nullptr, 1.,
-                                                                           nullptr, nullptr, 0);
+                                                                           nullptr, nullptr, 0, nullptr);
   const int last = h->nlev - 1;
   auto ghosts = [&](double* v, const AuxLevel& lv) {  // both ghost layers of a level vector
     mimpy_xchg x;
@@ -957,8 +964,8 @@ int mimpy_auxmg_apply(mimpy_ctx* ctx, mimpy_auxmg* h, const double* dinv, const 
   }
   const int grid = ctx->sm_count * 8;
   k_aux_face_prolong<double><<<grid, RED_THREADS, 0, st>>>(hx, n_owned, h->wj, h->face_to_flux, h->fw, L[0].x2, dinv, r, z,
-                                                           ctx->partials, ctx->counters + 4, rz_dst, nullptr, 1., nullptr, y,
-                                                           h->cpad, h->sdev);
+                                                           ctx->partials, ctx->counters + 4, rz_dst, nullptr, nrows_y, nullptr,
+                                                           y, h->cpad, h->sdev, ry);
   KERNEL_CHECK();
   return MIMPY_OK;
 }
@@ -1157,8 +1164,8 @@ int mimpy_b200_auxmg_cellblocks(mimpy_ctx* ctx, void* handle, const mimpy_mesh_v
     const char* env = getenv("MIMPY_B200_AUX_BLOCKS");
     if (env && env[0] == '0') return MIMPY_OK;  // switched off: the Jacobi term stays
   }
-  if (!h->binv) {  // 21 floats per cell + the block solutions (6 per cell, in the type of the levels)
-    const size_t bytes = sizeof(float) * 21 * h->cpad + (h->use32 ? sizeof(float) : sizeof(double)) * 6 * h->cpad;
+  if (!h->binv) {  // 21 floats per cell + the block solutions (6 floats per cell)
+    const size_t bytes = sizeof(float) * (21 + 6) * h->cpad;
     void* blk = nullptr;
     cudaError_t e = cudaMallocAsync(&blk, bytes, ctx->stream);
     if (e != cudaSuccess) {
