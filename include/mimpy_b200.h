@@ -367,6 +367,10 @@ int mimpy_b200_auxmg_destroy(mimpy_ctx* ctx, void* handle);
  * term D^-1 of B becomes the weighted additive Schwarz sum over the cells of the inverses of the 6 x 6 blocks of A
  * on the faces of each cell (stored as 21 floats per cell).  No reference counterpart.  MIMPY_B200_AUX_BLOCKS=0 in
  * the environment of auxmg_create keeps the Jacobi term (the call is then a no-op). */
+/* Number of cells (summed over the ranks of a partition) with tr(K)^3 / (27 det K) > threshold: how anisotropic the
+ * permeability field is; decides between the two smoothers (host side: device.HybridSystem(smoother="auto")). */
+int mimpy_b200_k_anisotropy(mimpy_ctx* ctx, int32_t nc, const double* cell_k /*nc*9*/, double threshold,
+                            double* count_out /*host*/);
 int mimpy_b200_auxmg_cellblocks(mimpy_ctx* ctx, void* auxmg, const mimpy_mesh_view* mesh,
                                 const mimpy_symbolic* sym, const int32_t* ptr, const int32_t* idx,
                                 const double* vals, int32_t sell, const double* diag_inv);

@@ -80,6 +80,7 @@ SIGNATURES = {
     "mimpy_b200_auxmg_setup": [_vp, _vp, _PM, _PS, _vp, _f64, _vp, _vp],
     "mimpy_b200_auxmg_destroy": [_vp, _vp],
     "mimpy_b200_auxmg_cellblocks": [_vp, _vp, _PM, _PS, _vp, _vp, _vp, _i32, _vp],
+    "mimpy_b200_k_anisotropy": [_vp, _i32, _vp, _f64, C.POINTER(C.c_double)],
     "mimpy_b200_pcg_aux": [_vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, C.POINTER(PcgInfo)],
     "mimpy_b200_hybrid_rhs": [_vp, _PM, _PS, _vp, _f64, _vp, _vp, _vp, _vp],
     "mimpy_b200_hybrid_recover": [_vp, _PM, _PS, _vp, _f64, _vp, _vp, _vp, _vp],

@@ -1197,6 +1197,44 @@ int mimpy_b200_auxmg_cellblocks(mimpy_ctx* ctx, void* handle, const mimpy_mesh_v
   return MIMPY_OK;
 }
 
+// number of cells whose permeability tensor is clearly anisotropic: tr(K)^3 / (27 det K) > threshold (1 for an isotropic
+// tensor by the AM-GM inequality, 1.54 for eigenvalues 3:1:1); deterministic two-stage sum
+__global__ void __launch_bounds__(RED_THREADS)
+k_aniso_count(int nc, const double* __restrict__ k, double threshold, double* partials, unsigned int* counter, double* dst) {
+  __shared__ double sh[32];
+  double v[1] = {0.};
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+    const double* a = k + 9 * (size_t)c;
+    const double tr = a[0] + a[4] + a[8];
+    const double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) +
+                       a[2] * (a[3] * a[7] - a[4] * a[6]);
+    const double t = tr * tr * tr / (27. * det);
+    if (!(t <= threshold)) v[0] += 1.;  // (NaN / inf count as anisotropic)
+  }
+  finish_reduction<1>(v, partials, counter, dst, sh);
+}
+
+int mimpy_b200_k_anisotropy(mimpy_ctx* ctx, int32_t nc, const double* cell_k, double threshold, double* count_out) {
+  REQUIRE(ctx && cell_k && count_out, "NULL argument");
+  if (nc <= 0) {
+    *count_out = 0.;
+    return MIMPY_OK;
+  }
+  int grid = (nc + RED_THREADS - 1) / RED_THREADS;
+  if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+  k_aniso_count<<<grid, RED_THREADS, 0, ctx->stream>>>(nc, cell_k, threshold, ctx->partials, ctx->counters + 6,
+                                                       ctx->scalars + 40);
+  KERNEL_CHECK();
+  if (ctx->world > 1) {  // every rank of a partition must take the same decision
+    int rc = mimpy_allreduce_f64(ctx, ctx->scalars + 40, 1);
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaMemcpyAsync(ctx->host_scalars + 40, ctx->scalars + 40, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  *count_out = ctx->host_scalars[40];
+  return MIMPY_OK;
+}
+
 int mimpy_b200_auxmg_destroy(mimpy_ctx* ctx, void* handle) {
   REQUIRE(ctx, "NULL context");
   if (!handle) return MIMPY_OK;

@@ -16,6 +16,9 @@
 #include "common.cuh"
 
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "reduce.cuh"
 
 // ---- SpMV: LPR lanes per row (rows of the face system have ~11 entries) --------------------
@@ -512,8 +515,49 @@ static int pcg_core(mimpy_ctx* ctx, int32_t n, const SpmvMat& A, const double* d
     }
   }
 
+  // Between two checks `check` iterations run as one graph.  Near the end that granularity is wasted work (up to
+  // check - 1 iterations of ~3 ms each at 256^3 against ~30 us for a check): from the contraction observed over the last
+  // interval the number of iterations still needed is estimated, and when it is below `check` exactly that many
+  // single-iteration graphs are launched before the next check.  Deterministic (a function of the all-reduced residuals).
+  cudaGraph_t graph1 = nullptr;
+  cudaGraphExec_t gexec1 = nullptr;
+  bool single_ok = use_graph && gexec != nullptr && check > 1 && !getenv("MIMPY_B200_PCG_FIXED_CHECKS");
+  const bool trace = getenv("MIMPY_B200_PCG_TRACE") != nullptr;
+  double prev_measure = -1.;
+  int prev_it = 0;
+  auto measure = [&]() { return energy ? sqrt(fabs(rz)) : rnorm; };
+  auto goal = [&]() { return energy ? sqrt(target_rz) : target; };
   while (running() && it < info->maxit) {
-    if (use_graph && gexec) {
+    int todo = check;
+    if (single_ok && prev_measure > 0. && measure() > 0. && measure() < prev_measure && it > prev_it) {
+      const double rate = log(measure() / prev_measure) / (double)(it - prev_it);  // < 0
+      const double need = ceil(log(goal() / measure()) / rate);
+      if (need >= 1. && need < (double)check) todo = (int)need;
+    }
+    prev_measure = measure();
+    prev_it = it;
+    if (todo < check && !gexec1) {
+      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const int crc = launch_iteration(ctx, grid, n, A, diag_inv, x, r, p, ap, aux, z, fz);
+        const cudaError_t e = cudaStreamEndCapture(st, &graph1);
+        if (crc != MIMPY_OK || e != cudaSuccess || graph1 == nullptr ||
+            cudaGraphInstantiate(&gexec1, graph1, 0) != cudaSuccess) {
+          if (graph1) cudaGraphDestroy(graph1);
+          graph1 = nullptr;
+          gexec1 = nullptr;
+          cudaGetLastError();
+        }
+      } else {
+        cudaGetLastError();
+      }
+      if (!gexec1) {
+        single_ok = false;
+        todo = check;
+      }
+    }
+    if (todo < check && gexec1) {
+      for (int k = 0; k < todo; ++k) CUDA_TRY(cudaGraphLaunch(gexec1, st));
+    } else if (use_graph && gexec) {
       CUDA_TRY(cudaGraphLaunch(gexec, st));
     } else {
       for (int k = 0; k < check; ++k) {
@@ -522,7 +566,8 @@ static int pcg_core(mimpy_ctx* ctx, int32_t n, const SpmvMat& A, const double* d
       }
       KERNEL_CHECK();
     }
-    it += check;
+    it += todo;
+    if (trace) fprintf(stderr, "pcg: it %d (+%d) residual before %.3e target %.3e\n", it, todo, prev_measure, goal());
     CUDA_TRY(cudaMemcpyAsync(ctx->host_scalars, ctx->scalars, sizeof(double) * 8,
                              cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -530,6 +575,8 @@ static int pcg_core(mimpy_ctx* ctx, int32_t n, const SpmvMat& A, const double* d
     rz = ctx->host_scalars[S_RZ];
     if (!(rnorm == rnorm)) break;  // NaN: matrix not SPD
   }
+  if (gexec1) cudaGraphExecDestroy(gexec1);
+  if (graph1) cudaGraphDestroy(graph1);
   CUDA_TRY(cudaEventRecord(ctx->ev1, st));
   CUDA_TRY(cudaEventSynchronize(ctx->ev1));
   CUDA_TRY(cudaEventElapsedTime(&info->ms_total, ctx->ev0, ctx->ev1));

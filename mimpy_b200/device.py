@@ -374,23 +374,28 @@ def build_rhs(dmesh, plan, dirichlet_faces, dirichlet_values, has_neumann, last_
 
 
 def _k_is_anisotropic(dmesh, threshold=1.5, fraction=0.01):
-    """True when more than `fraction` of the cells have tr(K)^3 / (27 det K) > threshold (1 for an isotropic tensor,
-    1.54 for eigenvalues 3:1:1) -- decides the smoother of the auxiliary-space preconditioner."""
+    """True when more than `fraction` of the cells (of all ranks) have tr(K)^3 / (27 det K) > threshold (1 for an
+    isotropic tensor, 1.54 for eigenvalues 3:1:1) -- decides the smoother of the auxiliary-space preconditioner.
+    One pass over cell_k (mimpy_b200_k_anisotropy), remembered per tensor version."""
     k = getattr(dmesh, "cell_k", None)
     if k is None or k.numel() < 9:
         return False
+    key = (k.data_ptr(), k._version, k.numel(), getattr(dmesh.ctx, "world", 1))
+    cached = getattr(dmesh, "_k_aniso", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    cnt = C.c_double(0.)
     with dmesh.ctx.on_stream():
-        k = k.reshape(-1, 9)
-        tr = k[:, 0] + k[:, 4] + k[:, 8]
-        det = (k[:, 0] * (k[:, 4] * k[:, 8] - k[:, 5] * k[:, 7]) - k[:, 1] * (k[:, 3] * k[:, 8] - k[:, 5] * k[:, 6])
-               + k[:, 2] * (k[:, 3] * k[:, 7] - k[:, 4] * k[:, 6]))
-        t = tr * tr * tr / (27. * det)
-        cnt = torch.stack([((t > threshold) | ~torch.isfinite(t)).double().sum(),
-                           torch.tensor(float(t.numel()), dtype=torch.float64, device=t.device)])
-        if getattr(dmesh.ctx, "world", 1) > 1:   # every rank of a partition must take the same decision
-            dmesh.ctx.call("mimpy_b200_allreduce_sum", ptr(cnt), 2)
-        cnt = cnt.cpu()
-        return bool(cnt[0].item() > fraction * cnt[1].item())
+        dmesh.ctx.call("mimpy_b200_k_anisotropy", k.numel() // 9, ptr(k), float(threshold), C.byref(cnt))
+    total = k.numel() // 9
+    if getattr(dmesh.ctx, "world", 1) > 1:   # the count is summed over the ranks; so must the cells be
+        t = torch.tensor([float(total)], dtype=torch.float64, device=k.device)
+        with dmesh.ctx.on_stream():
+            dmesh.ctx.call("mimpy_b200_allreduce_sum", ptr(t), 1)
+            total = float(t.cpu().item())
+    res = bool(cnt.value > fraction * total)
+    dmesh._k_aniso = (key, res)
+    return res
 
 
 class HybridSystem(object):

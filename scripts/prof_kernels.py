@@ -1,5 +1,6 @@
 """Small driver for ncu: runs the numeric assembly / hybrid set-up / PCG kernels a few times.
-usage: python scripts/prof_kernels.py [n] [what]   what in {asm, pcg, all}"""
+usage: python scripts/prof_kernels.py [n] [what]   what in {asm, pcg, all, bench}
+bench = the path bench.py times: brick assembly, fused set-up, auxmg PCG (10 iterations, no graph replay)"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -32,5 +33,11 @@ for it in range(3):
         m_e, _, _ = device.local_matrices(dm, plan, 1)
         hyb = device.HybridSystem(dm, plan, m_e)
         sol, info = hyb.solve(rhs, rtol=1e-30, maxit=20, check_every=10, raise_on_noconv=False, use_graph=False)
+if what == "bench":
+    for it in range(2):
+        vals = device.numeric(dm, plan, 1, vals=vals)
+        hyb = device.HybridSystem(dm, plan, None, precond="auxmg", method=1)
+        sol, info = hyb.solve(rhs, rtol=1e-30, maxit=10, check_every=10, raise_on_noconv=False, use_graph=False)
+        del hyb
 ctx.sync()
 print("done", n, what)

@@ -727,7 +727,9 @@ def test_fused_hex_setup_equals_two_step_setup(ctx, method, layout, dims):
             rhs = torch.as_tensor(rng2.standard_normal(plan.ndof), device=ctx.device)
             sa, ia = ax.solve(rhs, rtol=1e-11, maxit=500, check_every=5)
             sb, ib = bx.solve(rhs, rtol=1e-11, maxit=500, check_every=5)
-            assert ia.iterations == ib.iterations
+            # (the last checks of a solve are placed by the observed contraction: two operators that differ in the
+            # last bits may stop up to one check interval apart)
+            assert abs(ia.iterations - ib.iterations) < 5, (ia.iterations, ib.iterations)
             assert np.linalg.norm(H(ctx, sa) - H(ctx, sb)) <= 1e-9 * np.linalg.norm(H(ctx, sb))
     # generic meshes: the same call falls back to the two-step path
     o = orc.hex_mesh(3, 3, 2, 1., 1., 1.)
