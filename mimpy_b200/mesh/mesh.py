@@ -765,6 +765,185 @@ class Mesh(object):
         self.set_cell_k(new_cell, self.get_cell_k(cell_index))
         return new_cell
 
+    # ---- many cells, one plane ----------------------------------------------------
+    def divide_cells_by_plane(self, cell_indices, point_on_plane, plane_normal, tol=1.e-8):
+        """Splits every cell of `cell_indices` (None: all cells) that the plane really crosses; returns
+        {cell_index: new_cell_index}.  Cells that the plane only touches are left alone.
+
+        `divide_cell_by_plane` (mesh.py:2227-2419) cannot be applied to two face-adjacent cells: the second call
+        meets the already-split shared face, whose new vertices lie ON the plane, and splits it again into
+        degenerate pieces (the reference raises; HexMeshWMSFracs.add_fractures works around it with its
+        `done_faces` list, hexmeshwmsfracs.py:725-737).  Here the cut is done mesh-wide and conforming:
+          * every vertex is classified once by its signed distance (|s| <= tol: ON the plane, it becomes a
+            vertex of the cut polygon and no point is created next to it);
+          * every crossed EDGE gets one new point, shared by all faces and cells around it (the reference
+            creates one per face and matches them by position afterwards);
+          * every crossed FACE is split once, into its part below (keeps the face index) and above the plane
+            (new index, same normal, same boundary marker); both cells of the face receive the new part;
+          * every cell then sorts its faces by side, chains the in-plane edges of its faces into the cut
+            polygon (by point id) and is divided like the reference does: `cell_index` keeps the part
+            below the plane (`(point_on_plane - x) . plane_normal > 0`), the new cell gets the part above
+            and the same K and domain.
+        Faces are assumed convex (two crossings per face), as in the reference."""
+        p0 = np.asarray(point_on_plane, dtype=float)
+        nrm = np.asarray(plane_normal, dtype=float)
+        nrm = nrm / np.linalg.norm(nrm)
+        if cell_indices is None:
+            cell_indices = range(self.get_number_of_cells())
+        cell_indices = [int(c) for c in cell_indices]
+        if len(set(cell_indices)) != len(cell_indices):
+            raise ValueError("divide_cells_by_plane: a cell is listed twice")
+
+        sign = {}      # point -> -1 / 0 / +1
+
+        def side_of_point(p):
+            s = sign.get(p)
+            if s is None:
+                d = float((self.get_point(p) - p0).dot(nrm))
+                s = 0 if abs(d) <= tol else (1 if d > 0. else -1)
+                sign[p] = s
+            return s
+
+        edge_point = {}  # (low point, high point) -> the point where the plane crosses the edge
+
+        def crossing(a, b):
+            key = (a, b) if a < b else (b, a)
+            p = edge_point.get(key)
+            if p is None:
+                pa, pb = self.get_point(key[0]), self.get_point(key[1])
+                da, db = float((pa - p0).dot(nrm)), float((pb - p0).dot(nrm))
+                p = self.add_point(pa + (da / (da - db)) * (pb - pa))
+                sign[p] = 0
+                edge_point[key] = p
+            return p
+
+        boundary_of = {}
+        for marker in self.get_boundary_markers():
+            for face_index, orientation in self.boundary_faces[marker]:
+                boundary_of[int(face_index)] = marker
+
+        # 1. split the crossed faces, once each
+        face_side = {}  # face -> -1 below, +1 above, 0 in the plane
+        for c in cell_indices:
+            for f in [int(x) for x in self.get_cell(c)]:
+                if f in face_side:
+                    continue
+                loop = [int(p) for p in self.get_face(f)]
+                full = []
+                for a, b in zip(loop, loop[1:] + loop[:1]):
+                    full.append(a)
+                    if side_of_point(a) * side_of_point(b) < 0:
+                        full.append(crossing(a, b))
+                signs = [sign[p] for p in full]
+                below, above = -1 in signs, 1 in signs
+                if not (below and above):
+                    face_side[f] = -1 if below else (1 if above else 0)
+                    if len(full) != len(loop):
+                        raise AssertionError("a face without vertices on both sides has no crossed edge")
+                    continue
+                on = [i for i, s in enumerate(signs) if s == 0]
+                if len(on) != 2:
+                    raise Exception("divide_cells_by_plane: face %d meets the plane in %d points (not convex, "
+                                    "or it carries collinear vertices in the plane)" % (f, len(on)))
+                i0, i1 = on
+                part_a = full[i0:i1 + 1]
+                part_b = full[i1:] + full[:i0 + 1]
+                if len(part_a) < 3 or len(part_b) < 3:
+                    raise Exception("divide_cells_by_plane: degenerate split of face %d" % f)
+                if signs[i0 + 1] > 0:
+                    part_a, part_b = part_b, part_a   # part_a: below the plane, keeps the index
+                self.set_face(f, part_a)
+                new_face = self.add_face(part_b)
+                self.set_face_normal(new_face, self.get_face_normal(f))
+                for g in (f, new_face):
+                    area, centroid = self.find_face_centroid(g)
+                    self.set_face_area(g, area)
+                    self.set_face_real_centroid(g, centroid)
+                    if self.has_face_shifted_centroid:
+                        self.set_face_shifted_centroid(g, centroid)
+                face_side[f], face_side[new_face] = -1, 1
+                for cell in self.get_face_to_cell(f):
+                    cf = list(self.get_cell(cell))
+                    co = list(self.get_cell_normal_orientation(cell))
+                    local = cf.index(f)
+                    self.set_cell_faces(cell, cf + [new_face])
+                    self.set_cell_orientation(cell, np.array(co + [co[local]]))
+                    if f in boundary_of:
+                        self.add_boundary_face(boundary_of[f], new_face, co[local])
+                        boundary_of[new_face] = boundary_of[f]
+
+        # 2. divide the cells
+        new_cells = {}
+        for c in cell_indices:
+            cf = [int(x) for x in self.get_cell(c)]
+            co = [int(x) for x in self.get_cell_normal_orientation(c)]
+            sides = [face_side[f] for f in cf]
+            if not (-1 in sides and 1 in sides):
+                continue   # the plane touches the cell at most in a face, an edge or a vertex
+            if 0 in sides:
+                raise Exception("divide_cells_by_plane: cell %d has a face in the plane and faces on both sides" % c)
+            segments = set()
+            for f in cf:
+                loop = [int(p) for p in self.get_face(f)]
+                for a, b in zip(loop, loop[1:] + loop[:1]):
+                    if sign.get(a, 1) == 0 and sign.get(b, 1) == 0:
+                        segments.add((a, b) if a < b else (b, a))
+            polygon = self._chain_segments(segments, c)
+            cut_face = self.add_face(polygon)
+            area, centroid = self.find_face_centroid(cut_face)
+            self.set_face_area(cut_face, area)
+            self.set_face_real_centroid(cut_face, centroid)
+            if self.has_face_shifted_centroid:
+                self.set_face_shifted_centroid(cut_face, centroid)
+            cut_normal = self.find_face_normal(cut_face)
+            self.set_face_normal(cut_face, cut_normal)
+            face_side[cut_face] = 0
+            same = cut_normal.dot(nrm) > 0.
+            faces_1 = [f for f, s in zip(cf, sides) if s < 0] + [cut_face]
+            orient_1 = [o for o, s in zip(co, sides) if s < 0] + [1 if same else -1]
+            faces_2 = [f for f, s in zip(cf, sides) if s > 0] + [cut_face]
+            orient_2 = [o for o, s in zip(co, sides) if s > 0] + [-1 if same else 1]
+            for f in faces_2[:-1]:
+                self.remove_from_face_to_cell(f, c)
+            self.set_cell_faces(c, faces_1)
+            self.set_cell_orientation(c, orient_1)
+            new_cell = self.add_cell(faces_2, orient_2)
+            self.set_cell_k(new_cell, self.get_cell_k(c))
+            self.cell_domain[new_cell] = self.cell_domain[c]
+            for cell in (c, new_cell):
+                volume, centroid = self.find_volume_centroid(cell)
+                self.set_cell_volume(cell, volume)
+                self.set_cell_real_centroid(cell, centroid)
+                if self.has_cell_shifted_centroid:
+                    self.set_cell_shifted_centroid(cell, centroid)
+            new_cells[c] = new_cell
+        return new_cells
+
+    @staticmethod
+    def _chain_segments(segments, cell_index):
+        """Closed polygon (point ids) from the in-plane edges of one cell: every point must end two edges."""
+        ends = {}
+        for a, b in segments:
+            ends.setdefault(a, []).append(b)
+            ends.setdefault(b, []).append(a)
+        if len(segments) < 3 or any(len(v) != 2 for v in ends.values()):
+            raise Exception("divide_cells_by_plane: the plane does not cut cell %d in one simple polygon "
+                            "(%d in-plane edges)" % (cell_index, len(segments)))
+        start = min(ends)
+        polygon, previous, here = [start], None, start
+        while True:
+            a, b = ends[here]
+            nxt = b if a == previous else a
+            if nxt == start:
+                break
+            polygon.append(nxt)
+            previous, here = here, nxt
+            if len(polygon) > len(ends):
+                raise Exception("divide_cells_by_plane: open chain of in-plane edges in cell %d" % cell_index)
+        if len(polygon) != len(ends):
+            raise Exception("divide_cells_by_plane: the in-plane edges of cell %d form more than one loop" % cell_index)
+        return polygon
+
     # ---- SoA export ---------------------------------------------------------------------------------
     # ---- on-disk formats (mesh.py:584-949, 1985-2087) -> meshio.py --------------------------------
     def load_mesh(self, input_file):
