@@ -151,6 +151,9 @@ def lognormal_k(nc, seed, sigma=1.0):
 # ------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference algorithm on host cores
 # ------------------------------------------------------------------------------------------
+WORKLOAD = "C3: %d^3 hex, log-normal diag K (seed 256), method 1, Dirichlet x-/x+, no-flow else"
+
+
 def cpu_assembly_sample(n, seed=256):
     """build_lhs + build_rhs of the reference algorithm (oracle port, per-cell Python/NumPy loop
     exactly like mfd.py:545-599) on an n^3 sample of the workload. Returns (seconds, cells, mfd)."""
@@ -193,8 +196,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C3 hex n^3 log-normal diag K, method 1 (sampled at n=%d)" % n,
-                   "n": n, "cells": cells},
+        # the product arm's workload (same string, same cell count); each step is a bounded sample of it
+        "config": {"workload": WORKLOAD % args.n, "cells": args.n ** 3,
+                   "sample": "each step assembles a %d^3 block of it (%d cells), throughput is per cell" % (n, cells)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                          "host_cores_available": os.cpu_count(),
                          "note": "the reference is single-threaded Python (per-cell NumPy/LAPACK calls); 1 core is all it can use",
@@ -708,7 +712,7 @@ def run_cuda(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C3: %d^3 hex, log-normal diag K (seed 256), method 1, Dirichlet x-/x+, no-flow else" % n,
+            "config": {"workload": WORKLOAD % n,
                        "cells": nc_total, "face_rows": int(rows_total), "face_system_nnz": int(nnz_total),
                        "partition": "z-slabs x%d" % world, "pcg_collectives": comm,
                        "l2": "inputs larger than L2 (>= %.1f GB touched per step per GPU)" % (ASM_BYTES_PER_CELL * nc_total / world / 1e9),
