@@ -9,7 +9,7 @@ GPU through libmimpy_b200:
     find_volume_centroid_all   -> mimpy_b200_geom_cells        (mesh_cython.pyx:5-207)
     HexMesh face geometry      -> mimpy_b200_geom_hex_faces    (hexmesh_cython.pyx:30-118)
 
-Out of scope here: .mms I/O, VTK writers, fracture extrusion, VoroMesh.
+.mms I/O and VTK writers: meshio.py; VoroMesh: voromesh.py.  Out of scope: fracture extrusion.
 """
 import numpy as np
 
@@ -491,6 +491,13 @@ class Mesh(object):
     def get_lagrange_to_face_pointers(self, lagrange_index):
         return self.lagrange_to_face_pointers[lagrange_index]
 
+    def set_periodic_boundary(self, face_index_1, face_orientation_1, face_index_2, face_orientation_2):
+        """Ties two boundary faces through one shared multiplier face, a duplicate of the first (mesh.py:1476-1492):
+        MFD imposes continuity of pressure and flux across the pair."""
+        lagrange_index_1 = self.duplicate_face(face_index_1)
+        self.periodic_boundaries.append((face_index_1, face_orientation_1, face_index_2, face_orientation_2,
+                                         lagrange_index_1))
+
     def set_forcing_pointer(self, cell_index, face_indices, face_orientations):
         self.forcing_function_pointers[cell_index] = list(zip(face_indices, face_orientations))
 
@@ -794,15 +801,13 @@ class Mesh(object):
         if len(set(cell_indices)) != len(cell_indices):
             raise ValueError("divide_cells_by_plane: a cell is listed twice")
 
-        sign = {}      # point -> -1 / 0 / +1
+        # every existing vertex is classified once (-1 below / 0 on / +1 above); points created here lie on the plane
+        n_old = self.get_number_of_points()
+        distance = (self.points[:n_old] - p0).dot(nrm)
+        sign_old = np.where(np.abs(distance) <= tol, 0, np.where(distance > 0., 1, -1))
 
         def side_of_point(p):
-            s = sign.get(p)
-            if s is None:
-                d = float((self.get_point(p) - p0).dot(nrm))
-                s = 0 if abs(d) <= tol else (1 if d > 0. else -1)
-                sign[p] = s
-            return s
+            return int(sign_old[p]) if p < n_old else 0
 
         edge_point = {}  # (low point, high point) -> the point where the plane crosses the edge
 
@@ -810,10 +815,9 @@ class Mesh(object):
             key = (a, b) if a < b else (b, a)
             p = edge_point.get(key)
             if p is None:
+                da, db = distance[key[0]], distance[key[1]]
                 pa, pb = self.get_point(key[0]), self.get_point(key[1])
-                da, db = float((pa - p0).dot(nrm)), float((pb - p0).dot(nrm))
                 p = self.add_point(pa + (da / (da - db)) * (pb - pa))
-                sign[p] = 0
                 edge_point[key] = p
             return p
 
@@ -834,7 +838,7 @@ class Mesh(object):
                     full.append(a)
                     if side_of_point(a) * side_of_point(b) < 0:
                         full.append(crossing(a, b))
-                signs = [sign[p] for p in full]
+                signs = [side_of_point(p) for p in full]
                 below, above = -1 in signs, 1 in signs
                 if not (below and above):
                     face_side[f] = -1 if below else (1 if above else 0)
@@ -886,7 +890,7 @@ class Mesh(object):
             for f in cf:
                 loop = [int(p) for p in self.get_face(f)]
                 for a, b in zip(loop, loop[1:] + loop[:1]):
-                    if sign.get(a, 1) == 0 and sign.get(b, 1) == 0:
+                    if side_of_point(a) == 0 and side_of_point(b) == 0:
                         segments.add((a, b) if a < b else (b, a))
             polygon = self._chain_segments(segments, c)
             cut_face = self.add_face(polygon)

@@ -18,8 +18,10 @@ reference drops exact zeros, mfd.py:582); get_velocity_solution returns the actu
 Pointer couplings (build_coupling_terms, mfd.py:776-849): the coupling entries L, L^T are
 added to the GPU-assembled saddle CSR, and the coupled system K = K0 + E is solved ON THE GPU by flexible GMRES
 preconditioned with the hybridised PCG solve of the uncoupled system K0 (E has one entry pair per pointer,
-so the Krylov space closes after about rank(E) + 1 steps).  Lagrange-multiplier / periodic pointers are
-assembled too, but their multiplier rows are empty in K0, so `solve` refuses them.
+so the Krylov space closes after about rank(E) + 1 steps).  Lagrange-multiplier / periodic pointers add
+MULTIPLIER FACES (faces of no cell, Mesh.duplicate_face): the reference numbers them among the flux DOFs, the device
+system leaves them out (their rows would be empty), the host renames device rows to reference rows (monotone, so the
+CSR order survives) and the preconditioner of the GMRES solve is blockdiag(K0, I on the multipliers).
 """
 import ctypes as C
 
@@ -32,6 +34,32 @@ from .. import _lib, device
 def sign(x):
     """Returns the sign of float x (mfd.py:25-31)."""
     return 1. if abs(x) == x else -1.
+
+
+def reference_numbering(face_to_flux_dev, multiplier_faces, nc):
+    """The reference's flux numbering (mfd.py:141-159: every non-Neumann face in face order, multiplier faces
+    included) from the device plan's numbering, which leaves the multiplier faces out.
+    Returns (face_to_flux of the reference, its flux_dof, device index -> reference index over [flux ; cells])."""
+    f2f = np.asarray(face_to_flux_dev)
+    is_flux = f2f >= 0
+    f_dev = int(is_flux.sum())
+    real = is_flux.copy()
+    is_flux[np.asarray(multiplier_faces, dtype=np.int64)] = True
+    g_ref = np.where(is_flux, np.cumsum(is_flux) - 1, -1)
+    f_ref = int(is_flux.sum())
+    dev2ref = np.empty(f_dev + nc, dtype=np.int64)
+    dev2ref[f2f[real]] = g_ref[real]
+    dev2ref[f_dev:] = f_ref + np.arange(nc)
+    return g_ref, f_ref, dev2ref
+
+
+def rename_csr(a, dev2ref, n):
+    """Rows and columns of the CSR matrix `a` renamed by the monotone map dev2ref into an n x n matrix (the
+    entries keep their order; rows / columns that nothing maps to stay empty)."""
+    lens = np.zeros(n, dtype=np.int64)
+    lens[dev2ref] = np.diff(a.indptr)
+    indptr = np.concatenate([[0], np.cumsum(lens)])
+    return sparse.csr_matrix((a.data, dev2ref[a.indices].astype(np.int32), indptr.astype(np.int32)), shape=(n, n))
 
 
 class MFD(object):
@@ -66,6 +94,7 @@ class MFD(object):
         self._m_e = None        # device blocks of the current (mesh, method)
         self._m_e_key = None
         self._hybrid = None
+        self._mult = None       # (device index -> reference index, reference dofs, rows of the multiplier faces)
         self.device_lhs = None  # (indptr, indices, vals) tensors of the saddle CSR
         self.device_rhs = None
         self.solver_info = None
@@ -189,10 +218,25 @@ class MFD(object):
     def _dmesh(self):
         return self.mesh.to_device(self.ctx)
 
+    def _multiplier_faces(self):
+        """Faces that belong to no cell: the multipliers of periodic boundaries and of Lagrange pointers
+        (Mesh.duplicate_face, mesh.py:1476-1492, 2106-2150).  They are flux DOFs of the reference's numbering whose
+        rows hold coupling terms only."""
+        m = self.mesh
+        if not (m.periodic_boundaries or m.face_to_lagrange_pointers or m.lagrange_to_face_pointers) or len(m.cells) == 0:
+            return np.empty(0, dtype=np.int64)
+        nf = m.get_number_of_faces()
+        used = np.zeros(nf, dtype=bool)
+        used[self.mesh.cells.compact()[1]] = True
+        return np.nonzero(~used)[0]
+
     def _neumann_mask(self):
+        """Faces that are no flux DOF of the DEVICE plan: Neumann faces, and multiplier faces (no cell assembles
+        into their rows; the host keeps them in the reference's numbering, see _ensure_plan)."""
         mask = np.zeros(self.mesh.get_number_of_faces(), dtype=np.uint8)
         if self.neumann_boundary_values:
             mask[np.fromiter(self.neumann_boundary_values.keys(), dtype=np.int64)] = 1
+        mask[self._multiplier_faces()] = 1
         return mask
 
     def _ensure_plan(self):
@@ -204,8 +248,17 @@ class MFD(object):
             self._plan_key = key
             self._hybrid = None
             f2f = device.to_host(self.ctx, self._plan.face_to_flux)[:dm.nf]
-            self.face_to_flux = f2f.reshape(-1, 1).astype(np.dtype("i"))
             self.flux_dof = self._plan.flux_dof
+            self._mult = None
+            mult = self._multiplier_faces()
+            if len(mult):
+                # the reference numbers the multiplier faces among the flux DOFs, in face order (mfd.py:141-159); the
+                # device system leaves them out.  Both numberings run in face order, so device index -> reference
+                # index is monotone: rows and columns of the device CSR keep their order when they are renamed.
+                g_ref, f_ref, dev2ref = reference_numbering(f2f, mult, dm.nc)
+                self._mult = (dev2ref, f_ref + dm.nc, g_ref[mult])
+                f2f, self.flux_dof = g_ref, f_ref
+            self.face_to_flux = f2f.reshape(-1, 1).astype(np.dtype("i"))
             self.pressure_dof = dm.nc
             self.total_dof = self.flux_dof + dm.nc
             self.neumann_needs_updating = False
@@ -300,6 +353,8 @@ class MFD(object):
         loc, rows, cols, vals = device.coo_view(dm, plan, blocks)
         H = lambda t: device.to_host(self.ctx, t)
         data, row, col = H(vals), H(rows), H(cols)
+        if self._mult is not None:
+            row, col = self._mult[0][row].astype(row.dtype), self._mult[0][col].astype(col.dtype)
         if save_update_info:
             self.m_data_for_update = data.copy()
             self.m_e_locations = H(loc)
@@ -387,6 +442,10 @@ class MFD(object):
         n = plan.ndof
         H = lambda t: device.to_host(self.ctx, t)
         self.lhs = sparse.csr_matrix((H(vals)[:plan.nnz], H(plan.indices)[:plan.nnz], H(plan.indptr)[:n + 1]), shape=(n, n))
+        if self._mult is not None:
+            # rename to the reference's numbering: empty rows / columns appear where the multiplier faces sit
+            dev2ref, n, _ = self._mult
+            self.lhs = rename_csr(self.lhs, dev2ref, n)
         self._coupled = None
         if self.mesh.has_pointer_couplings():
             # the coupling entries sit off the mesh pattern: merged into the assembled CSR (the uncoupled matrix
@@ -412,6 +471,13 @@ class MFD(object):
         nvals = list(self.neumann_boundary_values.values())
         self.device_rhs = device.build_rhs(dm, plan, dfaces, dvals, len(nvals) > 0, nvals[-1] if nvals else 0.,
                                            self.cell_forcing_function)
+        if self._mult is not None:
+            import torch
+            dev2ref, n, _ = self._mult
+            with self.ctx.on_stream():
+                full = torch.zeros(n, dtype=torch.float64, device=self.ctx.device)
+                full[torch.as_tensor(dev2ref, device=self.ctx.device)] = self.device_rhs
+            self.device_rhs = full
         self.rhs = device.to_host(self.ctx, self.device_rhs)
         return self.rhs
 
@@ -438,7 +504,7 @@ class MFD(object):
         dm, plan = self._ensure_plan()
         m = self.mesh
         nf = m.get_number_of_faces()
-        if plan.flux_dof != nf:
+        if plan.flux_dof != nf or self._mult is not None:
             raise ValueError("dimension mismatch: add_gravity needs flux_dof == number of faces (mfd.py:1015-1024)")
         if self.rhs is None:
             self.build_rhs()
@@ -483,6 +549,8 @@ class MFD(object):
             self._hybrid_key = (self._m_e_key, getattr(self, "_alpha", 0.))
         if getattr(self, "_coupled", None) is not None:
             sol, info = self._solve_coupled(rhs, rtol or self.pcg_rtol, maxit or self.pcg_maxit)
+        elif self._mult is not None:
+            raise ValueError("the mesh has multiplier faces (faces of no cell) but no pointer couples them: singular system")
         else:
             sol, info = self._hybrid.solve(rhs, rtol=rtol or self.pcg_rtol, maxit=maxit or self.pcg_maxit)
         self.solver_info = {"iterations": int(info.iterations), "residual": float(info.residual),
@@ -495,18 +563,31 @@ class MFD(object):
         """Flexible GMRES on the coupled saddle CSR (device SpMV, device vectors), preconditioned by the
         hybridised PCG solve of the uncoupled system."""
         import torch
-        m = self.mesh
-        if m.get_all_face_to_lagrange_pointers() or m.get_all_lagrange_to_face_pointers() or m.periodic_boundaries:
-            raise NotImplementedError("solve with Lagrange-multiplier / periodic pointers: their rows are empty in the "
-                                      "uncoupled system that preconditions the coupled solve")
-        ctx, plan = self.ctx, self._plan
+        ctx = self.ctx
         ip, ix, vv = self._coupled
-        K = lambda v: device.spmv(ctx, ip, ix, vv, v, n=plan.ndof)
+        n_full = int(ip.numel() - 1)
+        K = lambda v: device.spmv(ctx, ip, ix, vv, v, n=n_full)
         total_it, total_ms, info = 0, 0., None
+        if self._mult is not None:
+            # multiplier faces (Lagrange / periodic pointers): their rows are empty in the uncoupled system, so the
+            # preconditioner is blockdiag(uncoupled saddle matrix on the mesh DOFs, identity on the multipliers) --
+            # still the coupled matrix up to a low-rank term
+            with ctx.on_stream():
+                mesh_rows = torch.as_tensor(self._mult[0], device=ctx.device)
+                mult_rows = torch.as_tensor(np.asarray(self._mult[2], dtype=np.int64), device=ctx.device)
 
         def Pinv(v):
             nonlocal total_it, total_ms, info
-            z, info = self._hybrid.solve(v, rtol=min(rtol, 1e-12), maxit=maxit)
+            if self._mult is None:
+                z, info = self._hybrid.solve(v, rtol=min(rtol, 1e-12), maxit=maxit)
+            else:
+                v_mesh = v[mesh_rows].contiguous()
+                z = torch.zeros_like(v)
+                z[mult_rows] = v[mult_rows]
+                if float(torch.linalg.norm(v_mesh)) == 0.:   # a Krylov vector that lives on the multipliers only
+                    return z
+                z_mesh, info = self._hybrid.solve(v_mesh, rtol=min(rtol, 1e-12), maxit=maxit)
+                z[mesh_rows] = z_mesh
             total_it += int(info.iterations)
             total_ms += float(info.ms_total)
             return z

@@ -104,6 +104,10 @@ class SinglePhase(object):
         import torch
 
         mfd = self.mfd
+        if self.mesh.has_pointer_couplings():
+            raise NotImplementedError("SinglePhase / Transport on a mesh with pointer couplings (singlephase.py:199-223, "
+                                      "transport.py:209-239): the time loop solves the uncoupled saddle system; "
+                                      "MFD.solve handles couplings (mfd.py), the time loops do not yet")
         dm, plan = mfd._ensure_plan()
         self._dm, self._plan = dm, plan
         self._m_e = mfd._blocks()

@@ -39,3 +39,51 @@ def configure(mfd_obj, mesh):
     for b in (2, 3, 4, 5):
         mfd_obj.apply_neumann_from_function(b, zero_flux)
     mfd_obj.apply_forcing_from_function(lambda x: 0.3 * x[2])
+
+
+# ---- multiplier faces: periodic boundaries and Lagrange pointers (mesh.py:1420-1492, mfd.py:806-848) ----------------
+def add_multipliers(mesh):
+    """The same box, (i) periodic in z: every z- face is tied to the z+ face above it (set_periodic_boundary creates
+    the shared multiplier face), (ii) cut into two sub-domains between i = 1 and i = 2: the interior x-face of every
+    (j, k) row is doubled -- one copy per side -- and a third copy is the Lagrange multiplier that glues them
+    (pressure continuity through face_to_lagrange, flux continuity through lagrange_to_face).  Works on the reference's
+    Mesh and on ours (public API only).  Returns (periodic pairs, [(face, new_face, lagrange face)])."""
+    lo = {}
+    for (f, orient) in mesh.get_boundary_faces_by_marker(4):
+        cell = int([c for c in mesh.face_to_cell[f] if c >= 0][0])
+        lo[cell % (NX * NY)] = (f, orient)
+    pairs = []
+    for (f, orient) in mesh.get_boundary_faces_by_marker(5):
+        cell = int([c for c in mesh.face_to_cell[f] if c >= 0][0])
+        f_lo, o_lo = lo[cell % (NX * NY)]
+        mesh.set_periodic_boundary(f_lo, o_lo, f, orient)
+        pairs.append((f_lo, f))
+    glue = []
+    for k in range(NZ):
+        for j in range(NY):
+            c1, c2 = 1 + NX * j + NX * NY * k, 2 + NX * j + NX * NY * k
+            f = [int(x) for x in mesh.get_cell(c1) if x in set(int(y) for y in mesh.get_cell(c2))][0]
+            o1 = int(mesh.get_cell_normal_orientation(c1)[list(mesh.get_cell(c1)).index(f)])
+            new_face, lag = mesh.duplicate_face(f), mesh.duplicate_face(f)
+            for g in (new_face, lag):
+                mesh.set_face_normal(g, mesh.get_face_normal(f))
+                mesh.set_face_real_centroid(g, mesh.get_face_real_centroid(f))
+            faces2 = [int(x) for x in mesh.get_cell(c2)]
+            faces2[faces2.index(f)] = new_face
+            mesh.remove_from_face_to_cell(f, c2)
+            mesh.set_cell_faces(c2, faces2)
+            mesh.set_face_to_lagrange_pointer(f, o1, lag)
+            mesh.set_face_to_lagrange_pointer(new_face, -o1, lag)
+            mesh.set_lagrange_to_face_pointers(lag, [f, new_face], [o1, -o1])
+            glue.append((f, new_face, lag))
+    return pairs, glue
+
+
+def configure_multipliers(mfd_obj, mesh):
+    mfd_obj.set_m_e_construction_method(1)
+    mfd_obj.set_mesh(mesh)
+    mfd_obj.apply_dirichlet_from_function(0, lambda p: 1. + p[1])
+    mfd_obj.apply_dirichlet_from_function(1, lambda p: 0.25 * p[2])
+    for b in (2, 3):
+        mfd_obj.apply_neumann_from_function(b, zero_flux)
+    mfd_obj.apply_forcing_from_function(lambda x: 0.3 * x[2])

@@ -226,8 +226,43 @@ def voro_mesh(ref):
     return d
 
 
+def multiplier_system(ref):
+    """MFD with multiplier faces (faces of no cell): periodic boundaries + Lagrange pointers between two sub-domains
+    (mesh.py:1420-1492, mfd.py:806-848): coupling COO, the full saddle matrix, rhs, spsolve."""
+    import coupling_cases as cc
+
+    _patch_coupling(ref)
+    mesh = g1.ref_hex(ref, cc.NX, cc.NY, cc.NZ, cc.DIMS, cc.permeability())
+    pairs, glue = cc.add_multipliers(mesh)
+    # the reference stores zip(...) objects (mesh.py:1454), exhausted after one pass in Python 3: make them lists
+    for lag in list(mesh.lagrange_to_face_pointers):
+        mesh.lagrange_to_face_pointers[lag] = list(mesh.lagrange_to_face_pointers[lag])
+    f = ref.mfd.MFD()
+    cc.configure_multipliers(f, mesh)
+    lhs = g1.quiet(f.build_lhs)
+    rhs = f.build_rhs()
+    cpl = f.build_coupling_terms()
+    d = orc.omesh_to_dict(orc.OMesh.from_mesh(mesh))
+    d["periodic_pairs"], d["glue"] = np.array(pairs), np.array(glue)
+    d["periodic_boundaries"] = np.array(mesh.periodic_boundaries)
+    d["face_to_lagrange"] = np.array([[f] + list(mesh.get_face_to_lagrange_pointer(f))
+                                      for f in mesh.get_all_face_to_lagrange_pointers()])
+    d["flux_dof"] = np.array([f.flux_dof])
+    d["face_to_flux"] = np.asarray(f.face_to_flux).reshape(-1).copy()
+    d["coupling_data"], d["coupling_row"], d["coupling_col"] = np.array(cpl[0]), np.array(cpl[1]), np.array(cpl[2])
+    csr = lhs.tocsr()
+    csr.sort_indices()
+    d["csr_indptr"], d["csr_indices"], d["csr_data"] = csr.indptr.copy(), csr.indices.copy(), csr.data.copy()
+    d["rhs"] = rhs.copy()
+    d["solution"] = np.array(f.solve())
+    return d
+
+
 def main():
     ref = ref_shim.load_reference()
+    if "--multipliers-only" in sys.argv:
+        g1.save("multipliers_433", multiplier_system(ref))
+        return
     g1.save("voro_48", voro_mesh(ref))
     g1.save("mfd_helpers_432", mfd_helpers(ref))
     if "--helpers-only" in sys.argv:
@@ -237,6 +272,7 @@ def main():
         g1.save("twophase_" + name, twophase_history(ref, name))
     g1.save("coupling_433", coupling_system(ref))
     g1.save("gravity_432", gravity_rhs(ref))
+    g1.save("multipliers_433", multiplier_system(ref))
 
 
 if __name__ == "__main__":

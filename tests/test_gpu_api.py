@@ -335,11 +335,6 @@ def test_pointer_couplings_match_reference(golden):
     err = np.linalg.norm(sol - g["solution"]) / np.linalg.norm(g["solution"])
     assert err <= 1e-8, (err, f.solver_info)
     assert np.linalg.norm(ref @ sol - rhs) <= 1e-9 * np.linalg.norm(rhs)
-    # a Lagrange pointer assembles, but its solve is refused (loudly)
-    mesh.set_face_to_lagrange_pointer(int(faces[0]), 1, int(faces[1]))
-    f.build_lhs()
-    with pytest.raises(NotImplementedError):
-        f.solve()
 
 
 def test_add_gravity_matches_reference(golden):

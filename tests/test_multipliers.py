@@ -1,0 +1,76 @@
+"""Host side of the multiplier faces (periodic boundaries / Lagrange pointers; mesh.py:1420-1492, mfd.py:806-848):
+the pointer API of our Mesh reproduces the reference's mesh, the reference's flux numbering is recovered from the
+device plan's (which leaves the multiplier faces out), the coupling COO is the reference's bit for bit, the CSR
+renaming is exact, and the preconditioner of the coupled solve -- blockdiag(uncoupled matrix, identity on the
+multipliers) -- closes the Krylov space after rank + 1 steps.  CPU only; golden from the unmodified reference."""
+import numpy as np
+from scipy import sparse
+from scipy.sparse.linalg import LinearOperator, gmres, splu
+
+import coupling_cases as cc
+from oracle import mimpy_oracle as orc
+from test_cpu_abi_and_host import mesh_from_omesh
+
+
+def test_multiplier_numbering_coupling_terms_and_solve_strategy(golden):
+    import mimpy_b200.mfd.mfd as mfd
+
+    g = golden("multipliers_433")
+    ref = orc.omesh_from_dict(g)
+    m = mesh_from_omesh(orc.hex_mesh(cc.NX, cc.NY, cc.NZ, *cc.DIMS, k_array=cc.permeability()))
+    pairs, glue = cc.add_multipliers(m)
+    o = orc.OMesh.from_mesh(m)
+    for key in ("face_ptr", "face_points", "cell_ptr", "cell_faces", "cell_sigma"):
+        assert np.array_equal(getattr(o, key), getattr(ref, key)), key
+    assert np.array_equal(np.array(pairs), g["periodic_pairs"]) and np.array_equal(np.array(glue), g["glue"])
+    assert np.array_equal(np.array(m.periodic_boundaries), g["periodic_boundaries"])
+    assert np.array_equal(np.array([[f] + list(m.get_face_to_lagrange_pointer(f)) for f in m.get_all_face_to_lagrange_pointers()]),
+                          g["face_to_lagrange"])
+    assert m.has_pointer_couplings()
+
+    f = mfd.MFD()
+    f.mesh = m
+    mult = f._multiplier_faces()
+    assert sorted(mult) == sorted([p[4] for p in m.periodic_boundaries] + [t[2] for t in glue])
+    nf, nc = m.get_number_of_faces(), m.get_number_of_cells()
+    masked = np.zeros(nf, dtype=bool)
+    for b in (2, 3):
+        masked[[face for face, s in m.get_boundary_faces_by_marker(b)]] = True
+    f.neumann_boundary_values = {int(x): 0. for x in np.nonzero(masked)[0]}
+    assert np.array_equal(f._neumann_mask().astype(bool), masked | np.isin(np.arange(nf), mult))
+    # what the device plan computes (A1, bit-exact on the GPU): unmasked faces in face order
+    masked[mult] = True
+    f2f_dev = np.where(~masked, np.cumsum(~masked) - 1, -1)
+    g_ref, f_ref, dev2ref = mfd.reference_numbering(f2f_dev, mult, nc)
+    assert f_ref == int(g["flux_dof"][0]) and np.array_equal(g_ref, g["face_to_flux"])
+    assert np.all(np.diff(dev2ref) > 0) and len(dev2ref) == f_ref - len(mult) + nc
+
+    f.face_to_flux, f.flux_dof = g_ref.reshape(-1, 1), f_ref
+    f._ensure_plan = lambda: None
+    cd, cr, ccol = f.build_coupling_terms()
+    assert np.array_equal(cd, g["coupling_data"]) and np.array_equal(cr, g["coupling_row"])
+    assert np.array_equal(ccol, g["coupling_col"])
+
+    n = f_ref + nc
+    k = sparse.csr_matrix((g["csr_data"], g["csr_indices"], g["csr_indptr"]), shape=(n, n))
+    k0 = (k - sparse.coo_matrix((cd, (cr, ccol)), shape=(n, n)).tocsr()).tocsr()
+    k0.eliminate_zeros()
+    rows = g_ref[mult]
+    assert abs(k0[rows]).sum() == 0 and abs(k0[:, rows]).sum() == 0   # multiplier rows hold coupling terms only
+    a_dev = k0[dev2ref][:, dev2ref].tocsr()
+    a_dev.sort_indices()
+    assert abs(mfd.rename_csr(a_dev, dev2ref, n) - k0).max() == 0
+
+    lu = splu(a_dev.tocsc())
+    applications = [0]
+
+    def pinv(v):
+        applications[0] += 1
+        z = np.zeros_like(v)
+        z[dev2ref] = lu.solve(v[dev2ref])
+        z[rows] = v[rows]
+        return z
+
+    x, info = gmres(k, g["rhs"], M=LinearOperator((n, n), matvec=pinv), rtol=1e-13, restart=200, maxiter=3)
+    assert info == 0 and applications[0] <= 2 * len(cd) // 4 + 8
+    assert np.linalg.norm(x - g["solution"]) <= 1e-12 * np.linalg.norm(g["solution"])
