@@ -62,6 +62,75 @@ def rename_csr(a, dev2ref, n):
     return sparse.csr_matrix((a.data, dev2ref[a.indices].astype(np.int32), indptr.astype(np.int32)), shape=(n, n))
 
 
+def coupled_gmres(ctx, apply_k, hybrid, rhs, rtol, maxit, mult=None, x0=None, restart=200):
+    """Flexible GMRES for the pointer-coupled saddle system K = K0 + E (device vectors; `apply_k(v)` = K v),
+    preconditioned by the hybridised PCG solve of the uncoupled system K0 (`hybrid`, a device.HybridSystem).
+    mult: the multiplier faces of Lagrange / periodic pointers (MFD._mult) -- their rows are empty in K0, so the
+    preconditioner is blockdiag(K0 on the mesh DOFs, identity on the multipliers): still K up to a low-rank term,
+    and the Krylov space closes after about rank + 1 steps.  Returns (x, info of the last inner solve with the
+    totals of all of them)."""
+    import torch
+    total_it, total_ms, info = 0, 0., None
+    if mult is not None:
+        with ctx.on_stream():
+            mesh_rows = torch.as_tensor(mult[0], device=ctx.device)
+            mult_rows = torch.as_tensor(np.asarray(mult[2], dtype=np.int64), device=ctx.device)
+
+    def Pinv(v):
+        nonlocal total_it, total_ms, info
+        if mult is None:
+            z, info = hybrid.solve(v, rtol=min(rtol, 1e-12), maxit=maxit)
+        else:
+            v_mesh = v[mesh_rows].contiguous()
+            z = torch.zeros_like(v)
+            z[mult_rows] = v[mult_rows]
+            if float(torch.linalg.norm(v_mesh)) == 0.:   # a Krylov vector that lives on the multipliers only
+                return z
+            z_mesh, info = hybrid.solve(v_mesh, rtol=min(rtol, 1e-12), maxit=maxit)
+            z[mesh_rows] = z_mesh
+        total_it += int(info.iterations)
+        total_ms += float(info.ms_total)
+        return z
+
+    with ctx.on_stream():
+        b = rhs
+        bnorm = float(torch.linalg.norm(b))
+        x = torch.zeros_like(b) if x0 is None else x0.clone()
+        r = b.clone() if x0 is None else b - apply_k(x)
+        tol = max(rtol, 1e-13) * max(bnorm, 1e-300)
+        for _cycle in range(10):
+            beta = float(torch.linalg.norm(r))
+            if beta <= tol:
+                break
+            V, Z = [r / beta], []
+            Hm = np.zeros((restart + 1, restart))
+            y = None
+            for j in range(restart):
+                Z.append(Pinv(V[j]))
+                w = apply_k(Z[j])
+                for i in range(j + 1):            # modified Gram-Schmidt
+                    Hm[i, j] = float(torch.dot(w, V[i]))
+                    w = w - Hm[i, j] * V[i]
+                Hm[j + 1, j] = float(torch.linalg.norm(w))
+                e1 = np.zeros(j + 2)
+                e1[0] = beta
+                y, res, _, _ = np.linalg.lstsq(Hm[:j + 2, :j + 1], e1, rcond=None)
+                resid = float(np.linalg.norm(Hm[:j + 2, :j + 1] @ y - e1))
+                if resid <= tol or Hm[j + 1, j] <= 1e-300:
+                    break
+                V.append(w / Hm[j + 1, j])
+            for c, z in zip(y, Z):
+                x = x + float(c) * z
+            r = b - apply_k(x)
+    if info is None:   # the right-hand side was met by the initial guess
+        import types
+        info = types.SimpleNamespace(iterations=0, ms_total=0., residual=0., rhs_norm=bnorm)
+    info.iterations, info.ms_total = total_it, total_ms
+    info.residual = float(torch.linalg.norm(r))
+    info.rhs_norm = bnorm
+    return x, info
+
+
 class MFD(object):
     def __init__(self):
         self.mesh = None
@@ -559,73 +628,12 @@ class MFD(object):
         self.solution = device.to_host(self.ctx, sol)
         return self.solution
 
-    def _solve_coupled(self, rhs, rtol, maxit, restart=200):
-        """Flexible GMRES on the coupled saddle CSR (device SpMV, device vectors), preconditioned by the
-        hybridised PCG solve of the uncoupled system."""
-        import torch
-        ctx = self.ctx
+    def _solve_coupled(self, rhs, rtol, maxit):
+        """The coupled saddle CSR (device SpMV) solved by `coupled_gmres` around the hybridised uncoupled solve."""
         ip, ix, vv = self._coupled
         n_full = int(ip.numel() - 1)
-        K = lambda v: device.spmv(ctx, ip, ix, vv, v, n=n_full)
-        total_it, total_ms, info = 0, 0., None
-        if self._mult is not None:
-            # multiplier faces (Lagrange / periodic pointers): their rows are empty in the uncoupled system, so the
-            # preconditioner is blockdiag(uncoupled saddle matrix on the mesh DOFs, identity on the multipliers) --
-            # still the coupled matrix up to a low-rank term
-            with ctx.on_stream():
-                mesh_rows = torch.as_tensor(self._mult[0], device=ctx.device)
-                mult_rows = torch.as_tensor(np.asarray(self._mult[2], dtype=np.int64), device=ctx.device)
-
-        def Pinv(v):
-            nonlocal total_it, total_ms, info
-            if self._mult is None:
-                z, info = self._hybrid.solve(v, rtol=min(rtol, 1e-12), maxit=maxit)
-            else:
-                v_mesh = v[mesh_rows].contiguous()
-                z = torch.zeros_like(v)
-                z[mult_rows] = v[mult_rows]
-                if float(torch.linalg.norm(v_mesh)) == 0.:   # a Krylov vector that lives on the multipliers only
-                    return z
-                z_mesh, info = self._hybrid.solve(v_mesh, rtol=min(rtol, 1e-12), maxit=maxit)
-                z[mesh_rows] = z_mesh
-            total_it += int(info.iterations)
-            total_ms += float(info.ms_total)
-            return z
-
-        with ctx.on_stream():
-            b = rhs
-            bnorm = float(torch.linalg.norm(b))
-            x = torch.zeros_like(b)
-            r = b.clone()
-            tol = max(rtol, 1e-13) * max(bnorm, 1e-300)
-            for _cycle in range(10):
-                beta = float(torch.linalg.norm(r))
-                if beta <= tol:
-                    break
-                V, Z = [r / beta], []
-                Hm = np.zeros((restart + 1, restart))
-                y = None
-                for j in range(restart):
-                    Z.append(Pinv(V[j]))
-                    w = K(Z[j])
-                    for i in range(j + 1):            # modified Gram-Schmidt
-                        Hm[i, j] = float(torch.dot(w, V[i]))
-                        w = w - Hm[i, j] * V[i]
-                    Hm[j + 1, j] = float(torch.linalg.norm(w))
-                    e1 = np.zeros(j + 2)
-                    e1[0] = beta
-                    y, res, _, _ = np.linalg.lstsq(Hm[:j + 2, :j + 1], e1, rcond=None)
-                    resid = float(np.linalg.norm(Hm[:j + 2, :j + 1] @ y - e1))
-                    if resid <= tol or Hm[j + 1, j] <= 1e-300:
-                        break
-                    V.append(w / Hm[j + 1, j])
-                for c, z in zip(y, Z):
-                    x = x + float(c) * z
-                r = b - K(x)
-        info.iterations, info.ms_total = total_it, total_ms
-        info.residual = float(torch.linalg.norm(r))
-        info.rhs_norm = bnorm
-        return x, info
+        apply_k = lambda v: device.spmv(self.ctx, ip, ix, vv, v, n=n_full)
+        return coupled_gmres(self.ctx, apply_k, self._hybrid, rhs, rtol, maxit, mult=self._mult)
 
     def get_pressure_solution(self):
         return self.solution[self.flux_dof:]

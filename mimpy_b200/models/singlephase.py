@@ -17,6 +17,8 @@ from ..mfd import mfd as _mfd
 
 
 class SinglePhase(object):
+    _couplings_supported = True   # pointer couplings in the time loop (singlephase.py:199-223)
+
     def __init__(self):
         self.mesh = None
         self.mfd = None
@@ -104,10 +106,9 @@ class SinglePhase(object):
         import torch
 
         mfd = self.mfd
-        if self.mesh.has_pointer_couplings():
-            raise NotImplementedError("SinglePhase / Transport on a mesh with pointer couplings (singlephase.py:199-223, "
-                                      "transport.py:209-239): the time loop solves the uncoupled saddle system; "
-                                      "MFD.solve handles couplings (mfd.py), the time loops do not yet")
+        if self.mesh.has_pointer_couplings() and not self._couplings_supported:
+            raise NotImplementedError("Transport on a mesh with pointer couplings (transport.py:209-239): its time loop "
+                                      "solves the uncoupled saddle system; MFD.solve and SinglePhase handle couplings")
         dm, plan = mfd._ensure_plan()
         self._dm, self._plan = dm, plan
         self._m_e = mfd._blocks()
@@ -117,11 +118,57 @@ class SinglePhase(object):
         self.c_end = dm.nc
         self.rhs_mfd = mfd.build_rhs()
         self._d_rhs_mfd = mfd.device_rhs
+        self._coupling = None
+        if self.mesh.has_pointer_couplings():
+            # singlephase.py:199-223: the coupling terms L, L^T sit off the mesh pattern; they are kept as a CSR of their
+            # own (reference numbering) next to the saddle matrix of the mesh, which is re-assembled every time step
+            from scipy import sparse
+            n = mfd.get_number_of_dof()
+            cd, cr, cc = mfd.build_coupling_terms()
+            e = sparse.coo_matrix((cd, (cr, cc)), shape=(n, n)).tocsr()
+            e.sort_indices()
+            dev = self.ctx.device
+            with self.ctx.on_stream():
+                self._coupling = (torch.as_tensor(e.indptr.astype(np.int32), device=dev),
+                                  torch.as_tensor(e.indices.astype(np.int32), device=dev),
+                                  torch.as_tensor(e.data, device=dev))
+                self._mesh_rows = None
+                if mfd._mult is not None:   # multiplier faces: device rows -> reference rows (mfd.reference_numbering)
+                    self._mesh_rows = torch.as_tensor(mfd._mult[0], device=dev)
+                    self._d_rhs_mfd = self._d_rhs_mfd[self._mesh_rows].contiguous()
         ctx = self.ctx
         with ctx.on_stream():
             self._d_mult = torch.empty(dm.nc, dtype=torch.float64, device=ctx.device)
             self._d_cdiag = torch.empty(dm.nc, dtype=torch.float64, device=ctx.device)
         self._hyb = None
+
+    def _solve_coupled_step(self, rhs_mesh):
+        """One time step on a mesh with pointer couplings: K = K0(multipliers, accumulation diagonal) + E, solved by
+        mfd.coupled_gmres around the hybridised solve of K0 (self._hyb, just set up for this step)."""
+        import torch
+        from ..mfd.mfd import coupled_gmres
+
+        ctx, dm, plan, mfd = self.ctx, self._dm, self._plan, self.mfd
+        vals = device.numeric_from_blocks(dm, plan, self._m_e, multipliers=self._d_mult, c_diag=self._d_cdiag)
+        ip, ix, ev = self._coupling
+        n = int(ip.numel() - 1)
+        rows = self._mesh_rows
+
+        def apply_k(v):
+            if rows is None:
+                y = device.spmv(ctx, plan.indptr, plan.indices, vals, v, n=plan.ndof)
+            else:
+                y = torch.zeros_like(v)
+                y[rows] = device.spmv(ctx, plan.indptr, plan.indices, vals, v[rows].contiguous(), n=plan.ndof)
+            return y + device.spmv(ctx, ip, ix, ev, v, n=n)
+
+        with ctx.on_stream():
+            if rows is None:
+                rhs = rhs_mesh
+            else:
+                rhs = torch.zeros(n, dtype=torch.float64, device=ctx.device)
+                rhs[rows] = rhs_mesh
+        return coupled_gmres(ctx, apply_k, self._hyb, rhs, self.pcg_rtol, 50000, mult=mfd._mult)
 
     def time_step_output(self, current_time, time_step):
         pass
@@ -154,6 +201,16 @@ class SinglePhase(object):
                     self._hyb = device.HybridSystem(dm, plan, self._m_e, multipliers=self._d_mult, c_diag=self._d_cdiag)
                 else:
                     self._hyb.setup(self._m_e, self._d_mult, self._d_cdiag)
+                if self._coupling is not None:
+                    sol, info = self._solve_coupled_step(rhs)
+                    F_ref = self.mfd.flux_dof
+                    self.last_solver_info = info
+                    d_p = sol[F_ref:].clone()
+                    self.current_pressure = device.to_host(ctx, d_p)
+                    self.current_velocity = device.to_host(ctx, sol[:F_ref])
+                    if time_step % self.output_frequency == 0:
+                        self.time_step_output(time_step * self.delta_t, time_step)
+                    continue
                 # warm start: the face multipliers of the previous time step
                 sol, info = self._hyb.solve(rhs, rtol=self.pcg_rtol, maxit=50000,
                                             x0=getattr(self._hyb, "last_lambda", None))

@@ -87,3 +87,24 @@ def configure_multipliers(mfd_obj, mesh):
     for b in (2, 3):
         mfd_obj.apply_neumann_from_function(b, zero_flux)
     mfd_obj.apply_forcing_from_function(lambda x: 0.3 * x[2])
+
+
+# ---- SinglePhase time loop on a mesh with every kind of pointer (singlephase.py:199-223) ----------------------------
+def configure_singlephase(sp, mesh):
+    """x+ faces are Dirichlet pointers feeding forcing pointers (add_pointers), z is periodic and the box is glued
+    from two sub-domains (add_multipliers); pressure 2 on x-, no-flow on y; slightly compressible fluid, one well."""
+    sp.set_mesh(mesh)
+    nc = mesh.get_number_of_cells()
+    add_pointers(mesh)
+    add_multipliers(mesh)
+    for b in (2, 3):
+        sp.apply_flux_boundary_from_function(b, zero_flux)
+    sp.apply_pressure_boundary_from_function(0, lambda p: 2.)
+    sp.set_compressibility(1.e-2)
+    sp.set_ref_density(1.3)
+    sp.set_ref_pressure(1.)
+    sp.set_viscosity(0.7)
+    sp.set_porosities(np.linspace(.1, .3, nc))
+    sp.set_time_step_size(0.5)
+    sp.set_number_of_time_steps(1)
+    sp.add_point_rate_well(0.4, 17, "w")

@@ -258,10 +258,33 @@ def multiplier_system(ref):
     return d
 
 
+def singlephase_coupled(ref):
+    """SinglePhase time loop (singlephase.py:182-299) on a mesh with Dirichlet / forcing pointers, periodic boundaries
+    and Lagrange pointers: 5 steps of the unmodified reference."""
+    import coupling_cases as cc
+
+    _patch_coupling(ref)
+    mesh = g1.ref_hex(ref, cc.NX, cc.NY, cc.NZ, cc.DIMS, cc.permeability())
+    sp = ref.singlephase.SinglePhase()
+    cc.configure_singlephase(sp, mesh)
+    for lag in list(mesh.lagrange_to_face_pointers):   # zip objects (mesh.py:1454) are exhausted after one pass
+        mesh.lagrange_to_face_pointers[lag] = list(mesh.lagrange_to_face_pointers[lag])
+    g1.quiet(sp.initialize_system)
+    nc = mesh.get_number_of_cells()
+    sp.set_initial_pressure(np.full(nc, 1.5))
+    p_hist, v_hist = [], []
+    for step in range(5):
+        g1.quiet(sp.start_solving)
+        p_hist.append(np.array(sp.current_pressure))
+        v_hist.append(np.array(sp.current_velocity))
+    return {"p": np.array(p_hist), "v": np.array(v_hist), "flux_dof": np.array([sp.mfd.flux_dof])}
+
+
 def main():
     ref = ref_shim.load_reference()
     if "--multipliers-only" in sys.argv:
         g1.save("multipliers_433", multiplier_system(ref))
+        g1.save("singlephase_coupled_433", singlephase_coupled(ref))
         return
     g1.save("voro_48", voro_mesh(ref))
     g1.save("mfd_helpers_432", mfd_helpers(ref))
@@ -273,6 +296,7 @@ def main():
     g1.save("coupling_433", coupling_system(ref))
     g1.save("gravity_432", gravity_rhs(ref))
     g1.save("multipliers_433", multiplier_system(ref))
+    g1.save("singlephase_coupled_433", singlephase_coupled(ref))
 
 
 if __name__ == "__main__":

@@ -43,3 +43,30 @@ def test_periodic_and_lagrange_multipliers_match_reference(golden):
     err = np.linalg.norm(sol - g["solution"]) / np.linalg.norm(g["solution"])
     assert err <= 1e-8, (err, f.solver_info)
     assert np.linalg.norm(ref @ sol - rhs) <= 1e-9 * np.linalg.norm(rhs)
+
+
+def test_singlephase_time_loop_with_pointer_couplings(golden):
+    """SinglePhase.start_solving on a mesh with Dirichlet / forcing pointers, periodic boundaries and Lagrange pointers
+    (singlephase.py:199-223 adds L, L^T to the step matrix): 5 steps against the unmodified reference."""
+    import mimpy_b200.mesh.hexmesh as hexmesh
+    import mimpy_b200.models.singlephase as singlephase
+    import mimpy_b200.models.transport as transport
+    import coupling_cases as cc
+
+    g = golden("singlephase_coupled_433")
+    mesh = hexmesh.HexMesh()
+    mesh.build_mesh(cc.NX, cc.NY, cc.NZ, cc.DIMS[0], cc.DIMS[1], cc.DIMS[2], cc.permeability())
+    sp = singlephase.SinglePhase()
+    cc.configure_singlephase(sp, mesh)
+    sp.initialize_system()
+    assert sp.mfd.flux_dof == int(g["flux_dof"][0])
+    sp.set_initial_pressure(np.full(mesh.get_number_of_cells(), 1.5))
+    for step in range(len(g["p"])):
+        sp.start_solving()
+        assert np.linalg.norm(sp.current_pressure - g["p"][step]) <= 1e-8 * np.linalg.norm(g["p"][step]), step
+        assert np.linalg.norm(sp.current_velocity - g["v"][step]) <= 1e-8 * np.linalg.norm(g["v"][step]), step
+    # Transport's loop does not carry the couplings: refused loudly, not ignored
+    tr = transport.Transport()
+    tr.set_mesh(mesh)
+    with pytest.raises(NotImplementedError):
+        tr.initialize_system()
