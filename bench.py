@@ -358,9 +358,11 @@ def run_c4(ctx, peak, n=128, steps=6):
             "s_w_max": float(sw.max())}
 
 
-def run_c5(ctx, peak, n=16):
-    """BASELINE configs[4]: n^3 hexes with every other cell cut by a plane (cells of 7..12 faces), full-tensor K,
-    Dirichlet everywhere, through the drop-in MFD API (generic warp-group kernels, Jacobi-PCG)."""
+def run_c5(ctx, peak, n=32):
+    """BASELINE configs[4] at its timing size (32^3): n^3 hexes with every other cell cut by a plane through its
+    centroid (cells of 7..12 faces), full-tensor K, Dirichlet everywhere, through the drop-in MFD API (generic
+    warp-group kernels, Jacobi-PCG).  The cuts are host code (Mesh.divide_cells_by_plane with one plane per cell: the
+    same halves as the reference's divide_cell_by_plane, tests/test_cutting.py)."""
     import torch
     import mimpy_b200.mesh.hexmesh as hexmesh
     import mimpy_b200.mfd.mfd as mfd
@@ -377,10 +379,8 @@ def run_c5(ctx, peak, n=16):
     mesh.build_mesh(n, n, n, 1., 1., 1., k)
     nrm = np.array([1.2, .2, 1.3])
     nrm /= np.linalg.norm(nrm)
-    for c in range(nc0):
-        i, j, kk = c % n, (c // n) % n, c // (n * n)
-        if (i + j + kk) % 2 == 0:
-            mesh.divide_cell_by_plane(c, np.array(mesh.get_cell_real_centroid(c)), nrm)
+    cut = [c for c in range(nc0) if (c % n + (c // n) % n + c // (n * n)) % 2 == 0]
+    mesh.divide_cells_by_plane(cut, np.array([mesh.get_cell_real_centroid(c) for c in cut]), nrm)
     t_mesh = time.perf_counter() - t0
     nc, nf = mesh.get_number_of_cells(), mesh.get_number_of_faces()
     lin = lambda p: 1. + 2. * p[0] - p[1] + .5 * p[2]

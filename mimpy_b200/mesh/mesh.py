@@ -124,6 +124,11 @@ class variable_array(object):
         return ptr, self.data[idx]
 
 
+def _cross3(a, b):
+    """np.cross for two 3-vectors without its axis bookkeeping (same products, same order: bit-identical)."""
+    return np.array([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]])
+
+
 def _grow(arr, n, fill=None):
     """Grow the first axis geometrically until index n-1 exists (the reference's _memory_extension)."""
     if len(arr) >= n:
@@ -134,6 +139,139 @@ def _grow(arr, n, fill=None):
         new[...] = fill
     new[:len(arr)] = arr
     return new
+
+
+class _PlaneCut(object):
+    """State of one plane cut (Mesh.divide_cells_by_plane): vertex classification, the new point of every crossed
+    edge, the side of every face met so far."""
+
+    def __init__(self, mesh, point, normal, tol, boundary_of, local):
+        self.mesh, self.p0, self.nrm, self.tol, self.boundary_of = mesh, point, normal, tol, boundary_of
+        self.edge_point = {}   # (low point, high point) -> the point where the plane crosses the edge
+        self.face_side = {}    # face -> -1 below, +1 above, 0 in the plane
+        if local:              # a cut of one cell: distances on demand (the mesh may have millions of points)
+            self.distance = {}
+        else:                  # mesh-wide: every existing vertex classified at once; points created here lie on the plane
+            n_old = mesh.get_number_of_points()
+            self.distance = (mesh.points[:n_old] - point).dot(normal)
+        self.n_old = mesh.get_number_of_points()
+        self.local = local
+
+    def dist(self, p):
+        if not self.local:
+            return float(self.distance[p]) if p < self.n_old else 0.
+        d = self.distance.get(p)
+        if d is None:
+            d = self.distance[p] = float((self.mesh.get_point(p) - self.p0).dot(self.nrm))
+        return d
+
+    def side(self, p):
+        d = self.dist(p)
+        return 0 if abs(d) <= self.tol else (1 if d > 0. else -1)
+
+    def crossing(self, a, b):
+        key = (a, b) if a < b else (b, a)
+        p = self.edge_point.get(key)
+        if p is None:
+            da, db = self.dist(key[0]), self.dist(key[1])
+            pa, pb = self.mesh.get_point(key[0]), self.mesh.get_point(key[1])
+            p = self.mesh.add_point(pa + (da / (da - db)) * (pb - pa))
+            if self.local:
+                self.distance[p] = 0.
+            self.edge_point[key] = p
+        return p
+
+    def split_faces_of(self, c):
+        m = self.mesh
+        for f in [int(x) for x in m.get_cell(c)]:
+            if f in self.face_side:
+                continue
+            loop = [int(p) for p in m.get_face(f)]
+            full = []
+            for a, b in zip(loop, loop[1:] + loop[:1]):
+                full.append(a)
+                if self.side(a) * self.side(b) < 0:
+                    full.append(self.crossing(a, b))
+            signs = [self.side(p) for p in full]
+            below, above = -1 in signs, 1 in signs
+            if not (below and above):
+                self.face_side[f] = -1 if below else (1 if above else 0)
+                continue
+            on = [i for i, s in enumerate(signs) if s == 0]
+            if len(on) != 2:
+                raise Exception("divide_cells_by_plane: face %d meets the plane in %d points (not convex, "
+                                "or it carries collinear vertices in the plane)" % (f, len(on)))
+            i0, i1 = on
+            part_a = full[i0:i1 + 1]
+            part_b = full[i1:] + full[:i0 + 1]
+            if len(part_a) < 3 or len(part_b) < 3:
+                raise Exception("divide_cells_by_plane: degenerate split of face %d" % f)
+            if signs[i0 + 1] > 0:
+                part_a, part_b = part_b, part_a   # part_a: below the plane, keeps the index
+            m.set_face(f, part_a)
+            new_face = m.add_face(part_b)
+            m.set_face_normal(new_face, m.get_face_normal(f))
+            for g in (f, new_face):
+                area, centroid = m.find_face_centroid(g)
+                m.set_face_area(g, area)
+                m.set_face_real_centroid(g, centroid)
+                if m.has_face_shifted_centroid:
+                    m.set_face_shifted_centroid(g, centroid)
+            self.face_side[f], self.face_side[new_face] = -1, 1
+            for cell in m.get_face_to_cell(f):
+                cf = list(m.get_cell(cell))
+                co = list(m.get_cell_normal_orientation(cell))
+                local = cf.index(f)
+                m.set_cell_faces(cell, cf + [new_face])
+                m.set_cell_orientation(cell, np.array(co + [co[local]]))
+                if f in self.boundary_of:
+                    m.add_boundary_face(self.boundary_of[f], new_face, co[local])
+                    self.boundary_of[new_face] = self.boundary_of[f]
+
+    def divide(self, c, new_cells):
+        m = self.mesh
+        cf = [int(x) for x in m.get_cell(c)]
+        co = [int(x) for x in m.get_cell_normal_orientation(c)]
+        sides = [self.face_side[f] for f in cf]
+        if not (-1 in sides and 1 in sides):
+            return   # the plane touches the cell at most in a face, an edge or a vertex
+        if 0 in sides:
+            raise Exception("divide_cells_by_plane: cell %d has a face in the plane and faces on both sides" % c)
+        segments = set()
+        for f in cf:
+            loop = [int(p) for p in m.get_face(f)]
+            for a, b in zip(loop, loop[1:] + loop[:1]):
+                if self.side(a) == 0 and self.side(b) == 0:
+                    segments.add((a, b) if a < b else (b, a))
+        polygon = m._chain_segments(segments, c)
+        cut_face = m.add_face(polygon)
+        area, centroid = m.find_face_centroid(cut_face)
+        m.set_face_area(cut_face, area)
+        m.set_face_real_centroid(cut_face, centroid)
+        if m.has_face_shifted_centroid:
+            m.set_face_shifted_centroid(cut_face, centroid)
+        cut_normal = m.find_face_normal(cut_face)
+        m.set_face_normal(cut_face, cut_normal)
+        self.face_side[cut_face] = 0
+        same = cut_normal.dot(self.nrm) > 0.
+        faces_1 = [f for f, s in zip(cf, sides) if s < 0] + [cut_face]
+        orient_1 = [o for o, s in zip(co, sides) if s < 0] + [1 if same else -1]
+        faces_2 = [f for f, s in zip(cf, sides) if s > 0] + [cut_face]
+        orient_2 = [o for o, s in zip(co, sides) if s > 0] + [-1 if same else 1]
+        for f in faces_2[:-1]:
+            m.remove_from_face_to_cell(f, c)
+        m.set_cell_faces(c, faces_1)
+        m.set_cell_orientation(c, orient_1)
+        new_cell = m.add_cell(faces_2, orient_2)
+        m.set_cell_k(new_cell, m.get_cell_k(c))
+        m.cell_domain[new_cell] = m.cell_domain[c]
+        for cell in (c, new_cell):
+            volume, centroid = m.find_volume_centroid(cell)
+            m.set_cell_volume(cell, volume)
+            m.set_cell_real_centroid(cell, centroid)
+            if m.has_cell_shifted_centroid:
+                m.set_cell_shifted_centroid(cell, centroid)
+        new_cells[c] = new_cell
 
 
 class Mesh(object):
@@ -551,7 +689,7 @@ class Mesh(object):
         for i in range(n):
             v1 = self.get_point(face[(i + 1) % n]) - self.get_point(face[i])
             v2 = self.get_point(face[i]) - self.get_point(face[i - 1])
-            nrm = np.cross(v2, v1)
+            nrm = _cross3(v2, v1)
             length = np.linalg.norm(nrm)
             if length > 1.e-10:
                 return nrm / length
@@ -568,9 +706,9 @@ class Mesh(object):
         v1, v2, origin_index = self.find_basis_for_face(face_index)
         polygon = np.array([self.get_point(x) for x in self.get_face(face_index)], dtype=float)
         v1 = v1 / np.linalg.norm(v1)
-        v2 = np.cross(np.cross(v1, v2), v1)
+        v2 = _cross3(_cross3(v1, v2), v1)
         if np.linalg.norm(v2) < 1.e-10:
-            v2 = np.cross(np.cross(v1, polygon[-2] - polygon[-1]), v1)
+            v2 = _cross3(_cross3(v1, polygon[-2] - polygon[-1]), v1)
         v2 = v2 / np.linalg.norm(v2)
         rel = polygon - self.get_point(origin_index)
         a, b = rel.dot(v1), rel.dot(v2)
@@ -791,6 +929,9 @@ class Mesh(object):
             polygon (by point id) and is divided like the reference does: `cell_index` keeps the part
             below the plane (`(point_on_plane - x) . plane_normal > 0`), the new cell gets the part above
             and the same K and domain.
+        `point_on_plane` may also hold ONE POINT PER CELL (shape (len(cell_indices), 3)): parallel planes, each cell
+        cut by its own -- the checkerboard generator of BASELINE config 5 in one call.  The listed cells must then
+        not share faces (a shared face cannot be split by two planes).
         Faces are assumed convex (two crossings per face), as in the reference."""
         p0 = np.asarray(point_on_plane, dtype=float)
         nrm = np.asarray(plane_normal, dtype=float)
@@ -800,127 +941,33 @@ class Mesh(object):
         cell_indices = [int(c) for c in cell_indices]
         if len(set(cell_indices)) != len(cell_indices):
             raise ValueError("divide_cells_by_plane: a cell is listed twice")
-
-        # every existing vertex is classified once (-1 below / 0 on / +1 above); points created here lie on the plane
-        n_old = self.get_number_of_points()
-        distance = (self.points[:n_old] - p0).dot(nrm)
-        sign_old = np.where(np.abs(distance) <= tol, 0, np.where(distance > 0., 1, -1))
-
-        def side_of_point(p):
-            return int(sign_old[p]) if p < n_old else 0
-
-        edge_point = {}  # (low point, high point) -> the point where the plane crosses the edge
-
-        def crossing(a, b):
-            key = (a, b) if a < b else (b, a)
-            p = edge_point.get(key)
-            if p is None:
-                da, db = distance[key[0]], distance[key[1]]
-                pa, pb = self.get_point(key[0]), self.get_point(key[1])
-                p = self.add_point(pa + (da / (da - db)) * (pb - pa))
-                edge_point[key] = p
-            return p
-
         boundary_of = {}
         for marker in self.get_boundary_markers():
             for face_index, orientation in self.boundary_faces[marker]:
                 boundary_of[int(face_index)] = marker
 
-        # 1. split the crossed faces, once each
-        face_side = {}  # face -> -1 below, +1 above, 0 in the plane
-        for c in cell_indices:
-            for f in [int(x) for x in self.get_cell(c)]:
-                if f in face_side:
-                    continue
-                loop = [int(p) for p in self.get_face(f)]
-                full = []
-                for a, b in zip(loop, loop[1:] + loop[:1]):
-                    full.append(a)
-                    if side_of_point(a) * side_of_point(b) < 0:
-                        full.append(crossing(a, b))
-                signs = [side_of_point(p) for p in full]
-                below, above = -1 in signs, 1 in signs
-                if not (below and above):
-                    face_side[f] = -1 if below else (1 if above else 0)
-                    if len(full) != len(loop):
-                        raise AssertionError("a face without vertices on both sides has no crossed edge")
-                    continue
-                on = [i for i, s in enumerate(signs) if s == 0]
-                if len(on) != 2:
-                    raise Exception("divide_cells_by_plane: face %d meets the plane in %d points (not convex, "
-                                    "or it carries collinear vertices in the plane)" % (f, len(on)))
-                i0, i1 = on
-                part_a = full[i0:i1 + 1]
-                part_b = full[i1:] + full[:i0 + 1]
-                if len(part_a) < 3 or len(part_b) < 3:
-                    raise Exception("divide_cells_by_plane: degenerate split of face %d" % f)
-                if signs[i0 + 1] > 0:
-                    part_a, part_b = part_b, part_a   # part_a: below the plane, keeps the index
-                self.set_face(f, part_a)
-                new_face = self.add_face(part_b)
-                self.set_face_normal(new_face, self.get_face_normal(f))
-                for g in (f, new_face):
-                    area, centroid = self.find_face_centroid(g)
-                    self.set_face_area(g, area)
-                    self.set_face_real_centroid(g, centroid)
-                    if self.has_face_shifted_centroid:
-                        self.set_face_shifted_centroid(g, centroid)
-                face_side[f], face_side[new_face] = -1, 1
-                for cell in self.get_face_to_cell(f):
-                    cf = list(self.get_cell(cell))
-                    co = list(self.get_cell_normal_orientation(cell))
-                    local = cf.index(f)
-                    self.set_cell_faces(cell, cf + [new_face])
-                    self.set_cell_orientation(cell, np.array(co + [co[local]]))
-                    if f in boundary_of:
-                        self.add_boundary_face(boundary_of[f], new_face, co[local])
-                        boundary_of[new_face] = boundary_of[f]
+        if p0.ndim == 2:
+            if p0.shape != (len(cell_indices), 3):
+                raise ValueError("divide_cells_by_plane: one point per listed cell expected")
+            seen = set()
+            for c in cell_indices:
+                faces = set(int(f) for f in self.get_cell(c))
+                if seen & faces:
+                    raise ValueError("divide_cells_by_plane: cells that share a face cannot be cut by different planes")
+                seen |= faces
+            new_cells = {}
+            for c, point in zip(cell_indices, p0):
+                cut = _PlaneCut(self, point, nrm, tol, boundary_of, local=True)
+                cut.split_faces_of(c)
+                cut.divide(c, new_cells)
+            return new_cells
 
-        # 2. divide the cells
+        cut = _PlaneCut(self, p0, nrm, tol, boundary_of, local=False)
+        for c in cell_indices:      # 1. split the crossed faces, once each
+            cut.split_faces_of(c)
         new_cells = {}
-        for c in cell_indices:
-            cf = [int(x) for x in self.get_cell(c)]
-            co = [int(x) for x in self.get_cell_normal_orientation(c)]
-            sides = [face_side[f] for f in cf]
-            if not (-1 in sides and 1 in sides):
-                continue   # the plane touches the cell at most in a face, an edge or a vertex
-            if 0 in sides:
-                raise Exception("divide_cells_by_plane: cell %d has a face in the plane and faces on both sides" % c)
-            segments = set()
-            for f in cf:
-                loop = [int(p) for p in self.get_face(f)]
-                for a, b in zip(loop, loop[1:] + loop[:1]):
-                    if side_of_point(a) == 0 and side_of_point(b) == 0:
-                        segments.add((a, b) if a < b else (b, a))
-            polygon = self._chain_segments(segments, c)
-            cut_face = self.add_face(polygon)
-            area, centroid = self.find_face_centroid(cut_face)
-            self.set_face_area(cut_face, area)
-            self.set_face_real_centroid(cut_face, centroid)
-            if self.has_face_shifted_centroid:
-                self.set_face_shifted_centroid(cut_face, centroid)
-            cut_normal = self.find_face_normal(cut_face)
-            self.set_face_normal(cut_face, cut_normal)
-            face_side[cut_face] = 0
-            same = cut_normal.dot(nrm) > 0.
-            faces_1 = [f for f, s in zip(cf, sides) if s < 0] + [cut_face]
-            orient_1 = [o for o, s in zip(co, sides) if s < 0] + [1 if same else -1]
-            faces_2 = [f for f, s in zip(cf, sides) if s > 0] + [cut_face]
-            orient_2 = [o for o, s in zip(co, sides) if s > 0] + [-1 if same else 1]
-            for f in faces_2[:-1]:
-                self.remove_from_face_to_cell(f, c)
-            self.set_cell_faces(c, faces_1)
-            self.set_cell_orientation(c, orient_1)
-            new_cell = self.add_cell(faces_2, orient_2)
-            self.set_cell_k(new_cell, self.get_cell_k(c))
-            self.cell_domain[new_cell] = self.cell_domain[c]
-            for cell in (c, new_cell):
-                volume, centroid = self.find_volume_centroid(cell)
-                self.set_cell_volume(cell, volume)
-                self.set_cell_real_centroid(cell, centroid)
-                if self.has_cell_shifted_centroid:
-                    self.set_cell_shifted_centroid(cell, centroid)
-            new_cells[c] = new_cell
+        for c in cell_indices:      # 2. divide the cells
+            cut.divide(c, new_cells)
         return new_cells
 
     @staticmethod

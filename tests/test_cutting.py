@@ -158,3 +158,28 @@ def test_reference_routine_fails_on_adjacent_cells():
     m = mesh_from_omesh(orc.hex_mesh(2, 1, 1, 2., 1., 1.))
     assert m.divide_cells_by_plane([0, 1], *plane) == {0: 2, 1: 3}
     conforming(m, 2., {0: 1., 1: 1., 2: 2., 3: 2., 4: 2., 5: 2.})
+
+
+def test_one_plane_per_cell_is_the_checkerboard_generator(golden):
+    """point_on_plane with one row per cell: parallel planes, every listed cell cut through its own point -- BASELINE
+    config 5's generator in one call (bench.py:run_c5).  Same halves as the reference's mesh; face-sharing cells refused."""
+    g = golden("cut_checker_4")
+    ref = orc.omesh_from_dict(g)
+    n = 4
+    m = mesh_from_omesh(orc.hex_mesh(n, n, n, 1., 1., 1.))
+    nrm = np.array([1.2, .2, 1.3])
+    cells = [c for c in range(n ** 3) if (c % n + (c // n) % n + c // (n * n)) % 2 == 0]
+    points = np.array([m.get_cell_real_centroid(c) for c in cells])
+    new = m.divide_cells_by_plane(cells, points, nrm)
+    assert list(new) == cells and list(new.values()) == list(range(64, 64 + len(cells)))
+    o = conforming(m, 1., UNIT)
+    assert o.nc == ref.nc and o.nf == ref.nf
+    assert np.allclose(o.cell_volume, ref.cell_volume, rtol=1e-12, atol=0)
+    assert np.allclose(o.cell_centroid, ref.cell_centroid, rtol=1e-11, atol=1e-14)
+    assert np.array_equal(np.diff(o.cell_ptr), np.diff(ref.cell_ptr))
+    patch_test(o, methods=(1,))
+    m = mesh_from_omesh(orc.hex_mesh(2, 1, 1, 2., 1., 1.))
+    with pytest.raises(ValueError):
+        m.divide_cells_by_plane([0, 1], np.array([[.5, .5, .5], [1.5, .5, .4]]), nrm)
+    with pytest.raises(ValueError):
+        m.divide_cells_by_plane([0], np.array([[.5, .5, .5], [1.5, .5, .4]]), nrm)
