@@ -408,6 +408,73 @@ class Mesh(object):
     def get_face_shifted_centroid(self, face_index):
         return self.face_shifted_centroids[face_index]
 
+    def set_face_shifted_to_tpfa_all(self):
+        """Shifted centroid of every interior face = the point where the line between the centroids of its two
+        cells pierces the face's plane (boundary faces keep their real centroid): with these points the MFD
+        inner product of a K-orthogonal cell is the two-point flux one (mesh.py:510-527).  All faces at once."""
+        nf = self.get_number_of_faces()
+        if not self.has_face_shifted_centroid:
+            self.use_face_shifted_centroid()
+        self.face_shifted_centroids = _grow(self.face_shifted_centroids, nf)
+        f2c = self.face_to_cell[:nf]
+        shifted = self.face_real_centroids[:nf].copy()
+        two = np.nonzero((f2c >= 0).all(axis=1))[0]
+        if len(two):
+            c1 = self.cell_real_centroid[f2c[two, 0]]
+            direction = self.cell_real_centroid[f2c[two, 1]] - c1
+            direction = direction / np.linalg.norm(direction, axis=1)[:, None]
+            normal = self.face_normals[two]
+            d = ((self.face_real_centroids[two] - c1) * normal).sum(axis=1) / (direction * normal).sum(axis=1)
+            shifted[two] = d[:, None] * direction + c1
+        self.face_shifted_centroids[:nf] = shifted
+        self._touch()
+
+    def is_line_seg_intersect_face(self, face_index, p1, p2):
+        """True when the segment p1-p2 pierces the (convex, planar) face: the point where it meets the face's plane
+        lies on the same side of every edge (mesh.py:529-576)."""
+        p1, p2 = np.asarray(p1, dtype=float), np.asarray(p2, dtype=float)
+        length = np.linalg.norm(p2 - p1)
+        vector = (p2 - p1) / length
+        normal = self.get_face_normal(face_index)
+        denom = vector.dot(normal)
+        if abs(denom) < 1e-10:
+            return None   # parallel to the face: the reference falls through without a verdict
+        d = (self.get_face_real_centroid(face_index) - p1).dot(normal) / denom
+        if not (1.e-8 < d <= length + 1.e-8):
+            return None
+        hit = d * vector + p1
+        pts = self.points[np.asarray(self.get_face(face_index))]
+        previous = np.roll(pts, 1, axis=0)
+        direction = np.cross(pts - previous, previous - hit).dot(normal)
+        return bool((direction > 0.).all() or (direction < 0.).all())
+
+    def find_centroid_for_coordinates(self, face_index, coordinates):
+        """(signed area, centroid coordinate 1, centroid coordinate 2) of the face projected on the two chosen
+        coordinate axes (mesh.py:1604-1637)."""
+        pts = self.points[np.asarray(self.get_face(face_index))]
+        a, b = pts[:, coordinates[0]], pts[:, coordinates[1]]
+        an, bn = np.roll(a, -1), np.roll(b, -1)
+        cross = a * bn - an * b
+        area = .5 * cross.sum()
+        return (area, ((a + an) * cross).sum() / (6. * area), ((b + bn) * cross).sum() / (6. * area))
+
+    def find_domain_faces(self, domain):
+        """(faces, orientations) of the hull of `domain`, seen from its cells, in cell order: every face whose other
+        side is not a cell of the domain -- another domain's cell or, like in the reference, nothing at all (a face
+        on the mesh boundary has -1 there, which is in no domain; mesh.py:2152-2184)."""
+        nc = self.get_number_of_cells()
+        inside = np.zeros(nc, dtype=bool)
+        inside[self.get_cells_in_domain(domain)] = True
+        faces, orientations = [], []
+        for c in np.nonzero(inside)[0]:
+            for f, s in zip(self.get_cell(c), self.get_cell_normal_orientation(c)):
+                row = self.face_to_cell[f]
+                other = row[1] if row[0] == c else row[0]
+                if other < 0 or not inside[other]:
+                    faces.append(int(f))
+                    orientations.append(int(s))
+        return (faces, orientations)
+
     def set_face_area(self, face_index, area):
         self.face_areas[face_index] = area
         self._touch()

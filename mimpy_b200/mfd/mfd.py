@@ -635,6 +635,27 @@ class MFD(object):
         apply_k = lambda v: device.spmv(self.ctx, ip, ix, vv, v, n=n_full)
         return coupled_gmres(self.ctx, apply_k, self._hybrid, rhs, rtol, maxit, mult=self._mult)
 
+    # ---- diagnostics of the assembled saddle matrix (mfd.py:1481-1529; small systems only: dense) -----------------
+    def lhs_svd(self):
+        return np.linalg.svd(self.lhs.toarray())[1]
+
+    def lhs_rank(self):
+        return int((np.abs(self.lhs_svd()) > 1.e-9).sum())
+
+    def print_lhs_to_file(self, filename):
+        """The whole matrix in dense text form, `value , value , ...` per row."""
+        with open(filename + ".dat", "w") as out:
+            for row in self.lhs.toarray():
+                out.write(" ".join("%s ," % v for v in row) + " \n")
+
+    def print_lhs_to_ppm(self, filename):
+        """The sparsity pattern (|entry| > 1e-10) as a plain-text bitmap."""
+        dense = np.abs(self.lhs.toarray()) > 1.e-10
+        with open(filename + ".ppm", "w") as out:
+            out.write("P1\n%d %d\n" % dense.shape)
+            for row in dense:
+                out.write(" ".join("1" if x else "0" for x in row) + " \n")
+
     def get_pressure_solution(self):
         return self.solution[self.flux_dof:]
 

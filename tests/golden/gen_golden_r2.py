@@ -258,6 +258,45 @@ def multiplier_system(ref):
     return d
 
 
+def mesh_helpers(ref):
+    """Host-side Mesh helpers next to the path (mesh.py:510-576 TPFA face shift, segment/face intersection; 1604-1637
+    projected centroid; 2152-2184 domain hull) and the dense diagnostics of MFD (mfd.py:1481-1508), on a distorted
+    4x3x2 box."""
+    ktab = g1.spd_tensors(24, 9, full=True)
+    mod = lambda p, i, j, k: p + 0.06 * np.array([np.sin(3. * p[1] + k), np.cos(2. * p[0] + i), np.sin(p[0] + 2. * p[1])])
+    mesh = g1.ref_hex(ref, 4, 3, 2, (2., 1.5, 1.), ktab, mod)
+    nf, nc = mesh.get_number_of_faces(), mesh.get_number_of_cells()
+    d = orc.omesh_to_dict(orc.OMesh.from_mesh(mesh))
+    mesh.use_face_shifted_centroid()
+    mesh.face_shifted_centroids = np.zeros((nf, 3))
+    mesh.set_face_shifted_to_tpfa_all()
+    d["tpfa_shifted"] = np.array(mesh.face_shifted_centroids[:nf])
+    segs = [(np.array([.1, .2, -.5]), np.array([.3, .4, 1.5])), (np.array([-1., .7, .3]), np.array([3., .8, .35])),
+            (np.array([.9, -1., .7]), np.array([1.1, 2.5, .2])), (np.array([.2, .2, .2]), np.array([.25, .22, .21]))]
+    hit = np.zeros((len(segs), nf), dtype=np.int8)
+    for a, (p1, p2) in enumerate(segs):
+        for f in range(nf):
+            r = mesh.is_line_seg_intersect_face(f, p1.copy(), p2.copy())
+            hit[a, f] = -1 if r is None else int(bool(r))
+    d["segments"], d["segment_hits"] = np.array(segs), hit
+    d["projected"] = np.array([[mesh.find_centroid_for_coordinates(f, co) for co in ((0, 1), (1, 2), (0, 2))] for f in (0, 5, 17, 40)])
+    for c in (5, 6, 9, 10, 21):
+        mesh.set_cell_domain(c, 1)
+    faces, orients = mesh.find_domain_faces(1)
+    d["domain_faces"], d["domain_orientations"] = np.array(faces), np.array(orients)
+    mesh.has_face_shifted_centroid = False
+    f = ref.mfd.MFD()
+    f.set_m_e_construction_method(1)
+    f.set_mesh(mesh)
+    for b in (0, 1):
+        f.apply_dirichlet_from_function(b, lambda p: 1. + p[0])
+    g1.quiet(f.build_lhs)
+    f.lhs = f.lhs.tocsr()
+    d["lhs_svd"] = np.array(f.lhs_svd())
+    d["lhs_rank"] = np.array([f.lhs_rank()])
+    return d
+
+
 def singlephase_coupled(ref):
     """SinglePhase time loop (singlephase.py:182-299) on a mesh with Dirichlet / forcing pointers, periodic boundaries
     and Lagrange pointers: 5 steps of the unmodified reference."""
@@ -286,6 +325,9 @@ def main():
         g1.save("multipliers_433", multiplier_system(ref))
         g1.save("singlephase_coupled_433", singlephase_coupled(ref))
         return
+    if "--mesh-helpers-only" in sys.argv:
+        g1.save("mesh_helpers_432", mesh_helpers(ref))
+        return
     g1.save("voro_48", voro_mesh(ref))
     g1.save("mfd_helpers_432", mfd_helpers(ref))
     if "--helpers-only" in sys.argv:
@@ -297,6 +339,7 @@ def main():
     g1.save("gravity_432", gravity_rhs(ref))
     g1.save("multipliers_433", multiplier_system(ref))
     g1.save("singlephase_coupled_433", singlephase_coupled(ref))
+    g1.save("mesh_helpers_432", mesh_helpers(ref))
 
 
 if __name__ == "__main__":

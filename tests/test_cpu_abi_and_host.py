@@ -303,3 +303,46 @@ def test_voromesh_reads_voro_file_like_reference(golden):
     assert np.array_equal(o.cell_shifted_centroids, g["cell_shifted_centroids"])
     assert {m: [(int(a), int(b)) for a, b in v] for m, v in o.boundary_faces.items()} == ref.boundary_faces
     assert abs(o.cell_volume.sum() - 3.0) < 1e-12
+
+
+def test_mesh_helpers_and_mfd_diagnostics_match_reference(golden, tmp_path):
+    """Host-side helpers next to the path -- TPFA face shift (mesh.py:510-527), segment / face intersection
+    (:529-576), projected centroid (:1604-1637), domain hull (:2152-2184) -- against the unmodified reference on a
+    distorted 4x3x2 box; the dense diagnostics of MFD (mfd.py:1481-1529) on a matrix taken from the golden mesh."""
+    import mimpy_b200.mfd.mfd as mfd
+    from scipy import sparse
+
+    g = golden("mesh_helpers_432")
+    o = orc.omesh_from_dict(g)
+    m = mesh_from_omesh(o)
+    nf = m.get_number_of_faces()
+    m.set_face_shifted_to_tpfa_all()
+    assert m.is_using_face_shifted_centroid()
+    assert np.allclose(m.face_shifted_centroids[:nf], g["tpfa_shifted"], rtol=1e-13, atol=1e-15)
+    interior = (m.face_to_cell[:nf] >= 0).all(axis=1)
+    assert np.array_equal(m.face_shifted_centroids[:nf][~interior], m.face_real_centroids[:nf][~interior])
+    for a, (p1, p2) in enumerate(g["segments"]):
+        for f in range(nf):
+            r = m.is_line_seg_intersect_face(f, p1, p2)
+            assert (-1 if r is None else int(r)) == g["segment_hits"][a, f], (a, f)
+    assert (g["segment_hits"] == 1).sum() >= 4 and (g["segment_hits"] == 0).sum() >= 4
+    for row, f in zip(g["projected"], (0, 5, 17, 40)):
+        for ref3, co in zip(row, ((0, 1), (1, 2), (0, 2))):
+            assert np.allclose(m.find_centroid_for_coordinates(f, co), ref3, rtol=1e-12, atol=1e-15)
+    for c in (5, 6, 9, 10, 21):
+        m.set_cell_domain(c, 1)
+    faces, orients = m.find_domain_faces(1)
+    assert np.array_equal(faces, g["domain_faces"]) and np.array_equal(orients, g["domain_orientations"])
+    # MFD diagnostics: any small matrix will do -- the oracle's saddle matrix of the same problem
+    r = orc.OracleMFD(o, 1)
+    for b in (0, 1):
+        r.apply_dirichlet_from_function(b, lambda p: 1. + p[0])
+    r.build_lhs()
+    f = mfd.MFD()
+    f.lhs = r.lhs.tocsr()
+    assert np.allclose(f.lhs_svd(), g["lhs_svd"], rtol=1e-9, atol=1e-12) and f.lhs_rank() == int(g["lhs_rank"][0])
+    f.lhs = sparse.csr_matrix(np.array([[1.5, 0.], [1e-12, -2.]]))
+    f.print_lhs_to_file(str(tmp_path / "a"))
+    f.print_lhs_to_ppm(str(tmp_path / "a"))
+    assert open(str(tmp_path / "a.dat")).read().split() == ["1.5", ",", "0.0", ",", "1e-12", ",", "-2.0", ","]
+    assert open(str(tmp_path / "a.ppm")).read().split() == ["P1", "2", "2", "1", "0", "0", "1"]
