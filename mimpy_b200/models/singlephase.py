@@ -142,6 +142,30 @@ class SinglePhase(object):
             self._d_cdiag = torch.empty(dm.nc, dtype=torch.float64, device=ctx.device)
         self._hyb = None
 
+    def start_solving_newton(self, inner_iterations=100):
+        """singlephase.py:300-356: every time step repeats the implicit step 100 times, each pass starting from the
+        pressure the previous pass returned (a fixed-point sweep towards the state where the accumulation term
+        vanishes); output after the last pass of a step.  The same device loop as start_solving, 100 passes per step."""
+        outer, frequency, user_output = self.number_of_time_steps, self.output_frequency, self.time_step_output
+        assigned = "time_step_output" in self.__dict__   # set on the instance by the user (else: a method)
+
+        def output_of_pass(current_time, k):
+            if k == 0:
+                user_output(0., 0)
+            elif k % inner_iterations == 0 and (k // inner_iterations) % frequency == 0:
+                user_output((k // inner_iterations) * self.delta_t, k // inner_iterations)
+
+        self.number_of_time_steps, self.output_frequency = outer * inner_iterations, 1
+        self.time_step_output = output_of_pass
+        try:
+            self.start_solving()
+        finally:
+            self.number_of_time_steps, self.output_frequency = outer, frequency
+            if assigned:
+                self.time_step_output = user_output
+            else:
+                del self.__dict__["time_step_output"]
+
     def _solve_coupled_step(self, rhs_mesh):
         """One time step on a mesh with pointer couplings: K = K0(multipliers, accumulation diagonal) + E, solved by
         mfd.coupled_gmres around the hybridised solve of K0 (self._hyb, just set up for this step)."""

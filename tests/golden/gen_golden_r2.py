@@ -297,6 +297,37 @@ def mesh_helpers(ref):
     return d
 
 
+def singlephase_newton(ref):
+    """SinglePhase.start_solving_newton (singlephase.py:300-356) on the set-up of fixture singlephase_543: two time
+    steps of 100 passes each."""
+    nx, ny, nz = 5, 4, 3
+    ktab = g1.spd_tensors(nx * ny * nz, 11, full=False)
+    mesh = g1.ref_hex(ref, nx, ny, nz, (5., 4., 3.), ktab)
+    sp = ref.singlephase.SinglePhase()
+    sp.set_mesh(mesh)
+    nc = mesh.get_number_of_cells()
+    for b in (2, 3, 4, 5):
+        sp.apply_flux_boundary_from_function(b, lambda p: np.array([0., 0., 0.]))
+    sp.apply_pressure_boundary_from_function(0, lambda p: 2.)
+    sp.apply_pressure_boundary_from_function(1, lambda p: 1.)
+    sp.set_compressibility(1.e-2)
+    sp.set_ref_density(1.3)
+    sp.set_ref_pressure(1.)
+    sp.set_viscosity(0.7)
+    sp.set_porosities(np.linspace(.1, .3, nc))
+    sp.set_time_step_size(0.5)
+    sp.set_number_of_time_steps(2)
+    sp.add_point_rate_well(0.4, 27, "w")
+    g1.quiet(sp.initialize_system)
+    sp.set_initial_pressure(np.full(nc, 1.5))
+    calls = []
+    sp.time_step_output = lambda t, k: calls.append((t, k, np.array(sp.current_pressure).copy()))
+    g1.quiet(sp.start_solving_newton)
+    return {"p": np.array(sp.current_pressure), "v": np.array(sp.current_velocity),
+            "output_times": np.array([c[0] for c in calls]), "output_steps": np.array([c[1] for c in calls]),
+            "output_p": np.array([c[2] for c in calls])}
+
+
 def singlephase_coupled(ref):
     """SinglePhase time loop (singlephase.py:182-299) on a mesh with Dirichlet / forcing pointers, periodic boundaries
     and Lagrange pointers: 5 steps of the unmodified reference."""
@@ -328,6 +359,9 @@ def main():
     if "--mesh-helpers-only" in sys.argv:
         g1.save("mesh_helpers_432", mesh_helpers(ref))
         return
+    if "--newton-only" in sys.argv:
+        g1.save("singlephase_newton_543", singlephase_newton(ref))
+        return
     g1.save("voro_48", voro_mesh(ref))
     g1.save("mfd_helpers_432", mfd_helpers(ref))
     if "--helpers-only" in sys.argv:
@@ -340,6 +374,7 @@ def main():
     g1.save("multipliers_433", multiplier_system(ref))
     g1.save("singlephase_coupled_433", singlephase_coupled(ref))
     g1.save("mesh_helpers_432", mesh_helpers(ref))
+    g1.save("singlephase_newton_543", singlephase_newton(ref))
 
 
 if __name__ == "__main__":
