@@ -1076,6 +1076,14 @@ class Mesh(object):
         from . import meshio
         meshio.output_vtk_mesh(self, file_name, cell_values, cell_value_labels)
 
+    def output_vector_field(self, file_name, vector_magnitudes=[], vector_labels=[]):
+        from . import meshio
+        meshio.output_vector_field(self, file_name, vector_magnitudes, vector_labels)
+
+    def output_cell_normals(self, file_name, cell_index):
+        from . import meshio
+        meshio.output_cell_normals(self, file_name, cell_index)
+
     def output_vtk_faces(self, file_name, face_indices, face_values=[], face_value_labels=[]):
         from . import meshio
         meshio.output_vtk_faces(self, file_name, face_indices, face_values, face_value_labels)

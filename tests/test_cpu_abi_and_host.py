@@ -280,6 +280,23 @@ def test_vtk_writers(golden, tmp_path):
     assert t2[i] == "CELLS 3 %d" % sum(len(o.face(f)) + 1 for f in faces)
     assert t2[i + 1].split() == [str(len(o.face(0)))] + [str(int(q)) for q in o.face(0)]
     assert t2[i + 4:i + 8] == ["CELL_TYPES 3", "7", "7", "7"]
+    # glyph fields (mesh.py:1892-1983): face fluxes as magnitude x normal at the face centroids; a cell's outward normals
+    flux = np.linspace(-1., 2., o.nf)
+    m.output_vector_field(base + "_v", [flux], ["flux"])
+    t3 = open(base + "_v.vtk").read().split("\n")
+    assert t3[4] == "POINTS %d float" % o.nf and [float(x) for x in t3[5 + 7].split()] == list(o.face_centroids[7])
+    assert t3[5 + o.nf] == "CELLS %d %d" % (o.nf, 2 * o.nf) and t3[6 + o.nf] == "1 0"
+    j = t3.index("VECTORS flux double")
+    assert t3[j - 1] == "POINT_DATA %d" % o.nf
+    assert np.allclose([float(x) for x in t3[j + 1 + 11].split()], flux[11] * o.face_normals[11], rtol=0, atol=0)
+    m.output_cell_normals(base + "_n", 3)
+    t4 = open(base + "_n.vtk").read().split("\n")
+    n3 = len(o.cell(3))
+    j = t4.index("VECTORS OUT_NORMAL double")
+    got = np.array([[float(x) for x in l.split()] for l in t4[j + 1:j + 1 + n3]])
+    assert np.array_equal(got, o.sigma(3)[:, None] * o.face_normals[o.cell(3)])
+    area_vec = (got * o.face_areas[o.cell(3)][:, None]).sum(axis=0)
+    assert abs(area_vec).max() < 1e-14   # outward area vectors of a closed cell cancel
 
 
 def test_voromesh_reads_voro_file_like_reference(golden):
