@@ -45,6 +45,12 @@ class OMesh(object):
         self.cell_k = None
         self.boundary_faces = {}
         self.internal_no_flow = []
+        # pointer couplings (mesh.py:1397-1525)
+        self.dirichlet_pointers = {}   # face -> (cell, orientation)
+        self.forcing_pointers = {}     # cell -> [(face, orientation), ...]
+        self.face_to_lagrange = {}     # face -> (multiplier face, orientation)
+        self.lagrange_to_face = {}     # multiplier face -> [(face, orientation), ...]
+        self.periodic = []             # (face 1, orientation 1, face 2, orientation 2, multiplier face)
 
     @property
     def nc(self):
@@ -95,6 +101,14 @@ class OMesh(object):
         o.boundary_faces = {m: [(int(a), int(b)) for a, b in mesh.get_boundary_faces_by_marker(m)]
                             for m in mesh.get_boundary_markers()}
         o.internal_no_flow = [(int(a), int(b)) for a, b in mesh.get_internal_no_flow()]
+        # pointer dictionaries carry the reference's attribute names (mesh.py:271-292)
+        o.dirichlet_pointers = {int(f): (int(v[0]), int(v[1])) for f, v in getattr(mesh, "dirichlet_boundary_pointers", {}).items()}
+        o.forcing_pointers = {int(c): [(int(f), int(s)) for f, s in v]
+                              for c, v in getattr(mesh, "forcing_function_pointers", {}).items()}
+        o.face_to_lagrange = {int(f): (int(v[0]), int(v[1])) for f, v in getattr(mesh, "face_to_lagrange_pointers", {}).items()}
+        o.lagrange_to_face = {int(l): [(int(f), int(s)) for f, s in v]
+                              for l, v in getattr(mesh, "lagrange_to_face_pointers", {}).items()}
+        o.periodic = [tuple(int(x) for x in p) for p in getattr(mesh, "periodic_boundaries", [])]
         return o
 
 
@@ -631,14 +645,45 @@ class OracleMFD(object):
         idx = (np.arange(o.nc) + shift * self.flux_dof).astype(np.int32)
         return [alpha * o.cell_volume, idx, idx.copy()]
 
+    def build_coupling_terms(self):
+        """COO triples of the pointer couplings L, L^T in the reference's order: forcing pointers, Dirichlet
+        pointers, face -> multiplier, multiplier -> faces, periodic pairs (mfd.py:776-849)."""
+        o, F = self.o, self.flux_dof
+        g = self.face_to_flux[:, 0]
+        data, row, col = [], [], []
+        for cell, pointers in o.forcing_pointers.items():          # the cell's source = flux through the faces
+            for f, orient in pointers:
+                data.append(-o.face_areas[f] * orient)
+                row.append(cell + F)
+                col.append(g[f])
+        for f, (cell, orient) in o.dirichlet_pointers.items():      # the face's pressure = the cell's
+            data.append(o.face_areas[f] * orient)
+            row.append(g[f])
+            col.append(cell + F)
+        for f, (lag, orient) in o.face_to_lagrange.items():         # the face's pressure = the multiplier
+            data.append(o.face_areas[f] * orient)
+            row.append(g[f])
+            col.append(g[lag])
+        for lag, pointers in o.lagrange_to_face.items():            # the multiplier's equation: fluxes balance
+            for f, orient in pointers:
+                data.append(-o.face_areas[f] * orient)
+                row.append(g[lag])
+                col.append(g[f])
+        for f1, o1, f2, o2, lag in o.periodic:
+            data += [o.face_areas[f1] * o1, o.face_areas[f2] * o2, o1, o2]
+            row += [g[f1], g[f2], g[lag], g[lag]]
+            col += [g[lag], g[lag], g[f1], g[f2]]
+        return [np.asarray(data, dtype=np.float64), np.asarray(row, dtype=np.int32), np.asarray(col, dtype=np.int32)]
+
     def build_lhs(self, alpha=0., m_e_list=None):
-        """M | DIV | -DIV^T | C concatenated into one COO matrix (mfd.py:851-914)."""
+        """M | DIV | -DIV^T | C | couplings concatenated into one COO matrix (mfd.py:851-914)."""
         m = self.build_m(m_e_list=m_e_list)
         dv, dvt = self.build_div()
         c = self.build_bottom_right(alpha)
-        data = np.concatenate([m[0], dv[0], dvt[0], c[0]])
-        row = np.concatenate([m[1], dv[1], dvt[1], c[1]])
-        col = np.concatenate([m[2], dv[2], dvt[2], c[2]])
+        cpl = self.build_coupling_terms()
+        data = np.concatenate([m[0], dv[0], dvt[0], c[0], cpl[0]])
+        row = np.concatenate([m[1], dv[1], dvt[1], c[1], cpl[1]])
+        col = np.concatenate([m[2], dv[2], dvt[2], c[2], cpl[2]])
         self.lhs = sparse.coo_matrix((data, (row, col)))
         return self.lhs
 
@@ -874,9 +919,10 @@ class OracleSinglePhase(object):
         c = mfd.build_bottom_right()
         data = np.concatenate([m[0], dv[0], dvt[0]])
         self.c_start = len(data)
-        data = np.concatenate([data, c[0]])
-        row = np.concatenate([m[1], dv[1], dvt[1], c[1]])
-        col = np.concatenate([m[2], dv[2], dvt[2], c[2]])
+        cpl = mfd.build_coupling_terms()   # singlephase.py:199-223: appended after the C block
+        data = np.concatenate([data, c[0], cpl[0]])
+        row = np.concatenate([m[1], dv[1], dvt[1], c[1], cpl[1]])
+        col = np.concatenate([m[2], dv[2], dvt[2], c[2], cpl[2]])
         self.lhs_coo = sparse.coo_matrix((data, (row, col)))
         self.rhs_mfd = mfd.build_rhs()
 

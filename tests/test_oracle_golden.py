@@ -318,3 +318,62 @@ def test_transport_history(golden):
         assert np.linalg.norm(t.current_pressure - g["p"][step]) <= 1e-10 * np.linalg.norm(g["p"][step])
         assert np.linalg.norm(t.current_velocity - g["v"][step]) <= 1e-9 * np.linalg.norm(g["v"][step])
         assert abs(t.current_concentration - g["c"][step]).max() <= 1e-12, step
+
+
+# ---- pointer couplings (mfd.py:776-849, singlephase.py:199-223): the oracle's restatement against the reference -----
+def _coupled_mesh(multipliers, pointers):
+    import coupling_cases as cc
+    from test_cpu_abi_and_host import mesh_from_omesh
+
+    m = mesh_from_omesh(orc.hex_mesh(cc.NX, cc.NY, cc.NZ, *cc.DIMS, k_array=cc.permeability()))
+    if pointers:
+        cc.add_pointers(m)
+    if multipliers:
+        cc.add_multipliers(m)
+    return orc.OMesh.from_mesh(m)
+
+
+def _assert_coupled_system(f, g):
+    cd, cr, ccol = f.build_coupling_terms()
+    assert np.array_equal(cd, g["coupling_data"]) and np.array_equal(cr, g["coupling_row"])
+    assert np.array_equal(ccol, g["coupling_col"])
+    assert_csr_matches(f.lhs, g, "")
+    assert np.array_equal(f.rhs, g["rhs"])
+    sol = f.solve()
+    assert np.linalg.norm(sol - g["solution"]) <= 1e-9 * np.linalg.norm(g["solution"])
+
+
+def test_dirichlet_and_forcing_pointers(golden):
+    g = golden("coupling_433")
+    o = _coupled_mesh(multipliers=False, pointers=True)
+    bc = [("d", 0, lambda p: 1. + p[1])] + [("n", b, zero_flux) for b in (2, 3, 4, 5)]
+    _assert_coupled_system(_system(o, 1, bc, lambda x: 0.3 * x[2]), g)
+
+
+def test_periodic_boundaries_and_lagrange_pointers(golden):
+    g = golden("multipliers_433")
+    o = _coupled_mesh(multipliers=True, pointers=False)
+    bc = [("d", 0, lambda p: 1. + p[1]), ("d", 1, lambda p: 0.25 * p[2])] + [("n", b, zero_flux) for b in (2, 3)]
+    f = _system(o, 1, bc, lambda x: 0.3 * x[2])
+    assert f.flux_dof == int(g["flux_dof"][0]) and np.array_equal(f.face_to_flux[:, 0], g["face_to_flux"])
+    _assert_coupled_system(f, g)
+
+
+def test_singlephase_history_with_all_pointer_kinds(golden):
+    g = golden("singlephase_coupled_433")
+    o = _coupled_mesh(multipliers=True, pointers=True)
+    sp = orc.OracleSinglePhase(o)
+    for b in (2, 3):
+        sp.mfd.apply_neumann_from_function(b, zero_flux)
+    sp.mfd.apply_dirichlet_from_function(0, lambda p: 2.)
+    sp.compressibility, sp.ref_density, sp.ref_pressure, sp.viscosity = 1.e-2, 1.3, 1., 0.7
+    sp.porosities = np.linspace(.1, .3, o.nc)
+    sp.delta_t = 0.5
+    sp.add_point_rate_well(0.4, 17)
+    sp.initialize_system()
+    assert sp.mfd.flux_dof == int(g["flux_dof"][0])
+    sp.current_pressure = np.full(o.nc, 1.5)
+    for step in range(len(g["p"])):
+        sp.step()
+        assert np.linalg.norm(sp.current_pressure - g["p"][step]) <= 1e-9 * np.linalg.norm(g["p"][step]), step
+        assert np.linalg.norm(sp.current_velocity - g["v"][step]) <= 1e-9 * np.linalg.norm(g["v"][step]), step
