@@ -363,3 +363,23 @@ def test_mesh_helpers_and_mfd_diagnostics_match_reference(golden, tmp_path):
     f.print_lhs_to_ppm(str(tmp_path / "a"))
     assert open(str(tmp_path / "a.dat")).read().split() == ["1.5", ",", "0.0", ",", "1e-12", ",", "-2.0", ","]
     assert open(str(tmp_path / "a.ppm")).read().split() == ["P1", "2", "2", "1", "0", "0", "1"]
+
+
+def test_brick_kernels_stage_with_bulk_copies(lib_path):
+    """SASS census of the built library (scripts/sass_census.py, profiles/r2_sass_bulk_copy.txt): the headline assembly
+    kernel and the fused set-up kernel move their inputs with cp.async.bulk (UBLKCP) through mbarriers (SYNCS) and use
+    setmaxnreg (USETMAXREG); the assembly kernel has no Ampere-style cp.async (LDGSTS) left."""
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import sass_census
+
+    counts = sass_census.census(lib_path)
+    brick3 = [k for k in counts if "k_numeric_brick3" in k]
+    setup = [k for k in counts if "k_hybrid_setup_brick" in k]
+    assert len(brick3) == 3 and len(setup) == 6      # methods 0 / 1 / 6 (x CSR / SELL row stride for the set-up)
+    for k in brick3 + setup:
+        assert counts[k]["UBLKCP"] >= 6 and counts[k]["SYNCS"] >= 6 and counts[k]["USETMAXREG"] == 2, (k, counts[k])
+    assert all(counts[k]["LDGSTS"] == 0 for k in brick3)
