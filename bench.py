@@ -60,6 +60,20 @@ def measured_traffic(n, world):
         return None, "unreadable capture record: %s" % e
 
 
+def auxmg_iteration_bytes(rows, nnz, nc, nf, patterns=True, blocks=True, fp32_cycle=True):
+    """Bytes ONE iteration of the benched PCG (auxiliary-space multigrid preconditioner) has to move, per GPU -- the
+    counts of DESIGN 3 / 4, each array touched once:
+      SpMV of the face system      8 nnz + 21 rows with column patterns (12 nnz + 20 rows indexed)
+      two vector kernels           88 rows (x, r, p updated; A p, z read; dots fused)
+      face -> cell restriction     116 nc (r of the six faces, weights, right-hand side of level 0 written)
+        + cell-block smoother      84 nc (21 floats per cell; the six residuals are in registers already)
+      cell -> face prolongation    55 nf (correction of the two cells, weights, D^-1 r or the block sums, z written, r.z)
+      V(1,1) cycle                 64 nc on FP32 mirrors / 136 nc on FP64 levels at level 0, x 8/7 for the coarser levels."""
+    spmv = (8. * nnz + 21. * rows) if patterns else (12. * nnz + 20. * rows)
+    cycle = (64. if fp32_cycle else 136.) * nc * 8. / 7.
+    return spmv + 88. * rows + (116. + (84. if blocks else 0.)) * nc + 55. * nf + cycle
+
+
 def aux_levels(nx, ny, nz, coarsest=64):
     """Levels of the auxiliary-space multigrid (csrc/auxmg.cu: halve until <= coarsest cells)."""
     lv = 1
@@ -548,6 +562,7 @@ def run_cuda(args):
         t = t.tolist()
         out = {"asm_ms": t[0], "setup_ms": t[1], "solve_ms": t[2], "pcg_ms": t[3], "step_ms": t[4],
                "iters": int(info.iterations), "residual": float(info.residual), "rhs_norm": float(info.rhs_norm)}
+        out["smoother"] = getattr(hyb, "smoother", None)
         if collect:
             out["sol"] = sol
         del hyb
@@ -615,6 +630,22 @@ def run_cuda(args):
     pcg_row_bytes = spmv_row_bytes + 88.0
     pcg_gbs = pcg_row_bytes * (rows_total / world) / (jacobi_ms_iter / 1e3) / 1e9
     spmv_gbs = spmv_row_bytes * (rows_total / world) / (spmv_ms / 1e3) / 1e9
+
+    aux_roofline = None
+    if args.precond == "auxmg":
+        try:   # the benched iteration itself (the Jacobi figure above is the survey's 3-kernel iteration)
+            blocks = res[-1].get("smoother") == "blocks"
+            aux_bytes = auxmg_iteration_bytes(rows_total / world, nnz_total / world, nc_total / world, float(dm.nf),
+                                              patterns=pat, blocks=blocks, fp32_cycle=(world == 1))
+            aux_gbs = aux_bytes / s_per_iter / 1e9
+            aux_roofline = {"bound": "hbm", "achieved": aux_gbs, "peak": peak, "unit": "GB/s", "frac": aux_gbs / peak,
+                            "what": "one iteration of the benched PCG (SpMV + 2 vector kernels + restriction%s + V(1,1) cycle on %s "
+                                    "levels + prolongation), mean over the solve incl. its convergence checks"
+                                    % (" with cell-block solves" if blocks else "", "FP32" if world == 1 else "FP64"),
+                            "s_per_iter": s_per_iter, "bytes_per_iteration": aux_bytes,
+                            "formula": "8 nnz + 109 rows + (116 + 84 blocks) nc + 55 nf + (64 | 136) nc 8/7 (bench.py:auxmg_iteration_bytes)"}
+        except Exception as e:   # a side figure must not take the headline line down
+            aux_roofline = {"error": "%s: %s" % (type(e).__name__, e)}
 
     sol = res[-1]["sol"]
     with ctx.on_stream():
@@ -741,6 +772,7 @@ def run_cuda(args):
                              "s_per_iter": jacobi_ms_iter / 1e3,
                              "algorithmic_bytes_per_row": pcg_row_bytes, "survey_indexed_bytes_per_row": pcg_bytes_per_row(nnz_row),
                              "rows": int(rows_total)},
+            "roofline_pcg_auxmg": aux_roofline,
             "configs": extra, "cpu_baseline": cpu, "e2e": e2e, "e2e_solve": e2e_solve,
             "gpu_launches": int(args.steps * launches_per_step(args.precond, n, slab_nz, iters, world)),
             "clocks": sampler.summary(), "setup_s": t_setup, "wall_s_timed": wall,

@@ -43,3 +43,22 @@ def test_traffic_record_matches_the_kernel_sources():
     algorithmic = bench.ASM_BYTES_PER_CELL * 256 ** 3
     assert 1.0 <= traffic / algorithmic <= 1.10   # 1.04 x at the capture
     assert bench.measured_traffic(256, 8)[0] is None and bench.measured_traffic(128, 1)[0] is None
+
+
+def test_bytes_of_the_benched_pcg_iteration():
+    """roofline_pcg_auxmg's numerator (bench.py:auxmg_iteration_bytes) at the 256^3 sizes of the committed bench line:
+    17.25 GB per iteration -> 82.5 % of the measured copy peak at the measured 3.19 ms."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    line = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_default.json")))
+    rows, nnz, nc = line["config"]["face_rows"], line["config"]["face_system_nnz"], line["config"]["cells"]
+    nf = 3 * 256 * 256 * 257
+    b = bench.auxmg_iteration_bytes(rows, nnz, nc, nf)
+    assert abs(b - (8 * nnz + 109 * rows + 200 * nc + 55 * nf + 64 * nc * 8 / 7)) < 1.
+    assert 17.2e9 < b < 17.3e9
+    frac = b / line["pcg_s_per_iter"] / 1e9 / line["roofline"]["peak"]
+    assert 0.80 < frac < 0.85
+    # the Jacobi-term / FP64-level variants move less / more
+    assert bench.auxmg_iteration_bytes(rows, nnz, nc, nf, blocks=False) == b - 84 * nc
+    assert bench.auxmg_iteration_bytes(rows, nnz, nc, nf, fp32_cycle=False) == b + 72 * nc * 8 / 7
