@@ -183,3 +183,25 @@ def test_one_plane_per_cell_is_the_checkerboard_generator(golden):
         m.divide_cells_by_plane([0, 1], np.array([[.5, .5, .5], [1.5, .5, .4]]), nrm)
     with pytest.raises(ValueError):
         m.divide_cells_by_plane([0], np.array([[.5, .5, .5], [1.5, .5, .4]]), nrm)
+
+
+def test_random_and_degenerate_planes_keep_the_mesh_conforming():
+    """Seeded stress: up to three successive cuts of a 3^3 box by planes in general position, through grid vertices,
+    along grid planes and through grid edges -- every result is a conforming mesh of unchanged volume."""
+    rng = np.random.default_rng(1)
+    o0 = orc.hex_mesh(3, 3, 3, 1., 1., 1.)
+    for trial in range(60):
+        m = mesh_from_omesh(o0)
+        for _ in range(int(rng.integers(1, 4))):
+            kind = int(rng.integers(0, 4))
+            if kind == 0:
+                p, n = rng.random(3), rng.standard_normal(3)
+            elif kind == 1:
+                p, n = rng.integers(0, 4, 3) / 3., rng.standard_normal(3)
+            elif kind == 2:
+                p, n = rng.integers(0, 7, 3) / 6., np.eye(3)[int(rng.integers(0, 3))]
+            else:
+                p, n = rng.integers(0, 4, 3) / 3., rng.standard_normal(3)
+                n[int(rng.integers(0, 3))] = 0.
+            m.divide_cells_by_plane(None, p, n)
+        conforming(m, 1., UNIT)
