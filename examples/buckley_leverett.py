@@ -1,6 +1,7 @@
-"""Two-phase Buckley-Leverett displacement -- the reference's examples/twophase/buckleyleverett/buckleyleverett.py
-with the two import lines changed (mimpy -> mimpy_b200) and the run shortened; the IMPES loop (Newton pressure solve,
-upwind saturation update) runs on the GPU through libmimpy_b200.so.  Needs a CUDA device.
+"""Two-phase Buckley-Leverett displacement: the problem of the reference's examples/twophase/buckleyleverett (300 x 1 x 1
+cells, 80 m, Corey(2, 2), mu_o = 2 mu_w, S_or = 0.2, one water injector) through the same TwoPhase API -- only the two
+import lines differ from a mimpy script -- with a shorter run; the IMPES loop (Newton pressure solve, upwind saturation
+update) runs on the GPU through libmimpy_b200.so.  Needs a CUDA device.
 
 At the end the computed water front is compared with the analytic Buckley-Leverett solution (Welge tangent) and the
 injected water with the water in place.
@@ -19,49 +20,38 @@ import mimpy_b200.models.twophase as twophase    # import mimpy.models.twophase 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 nx, length = 300, 80.
 
+no_flow = lambda p: np.zeros(3)
+cells = nx
+
 mesh = hexmesh.HexMesh()
+mesh.build_mesh(nx, 1, 1, length, 1., 1., lambda point, i, j, k: 1.e-15 * np.eye(3))
 
+model = twophase.TwoPhase()
+model.set_mesh(mesh)
+for marker in (0, 2, 3, 4, 5):                       # injection end and the four sides: no flow
+    model.apply_flux_boundary_from_function(marker, no_flow)
+model.apply_pressure_boundary_from_function(1, lambda p: 0.)   # outlet
 
-def res_k(point, i, j, k):
-    return 1.e-12 * np.eye(3) * 1.e-3
-
-
-mesh.build_mesh(nx, 1, 1, length, 1., 1., res_k)
-
-res_twophase = twophase.TwoPhase()
-res_twophase.set_mesh(mesh)
-
-res_twophase.apply_flux_boundary_from_function(0, lambda p: np.array([0., 0., 0.]))
-res_twophase.apply_pressure_boundary_from_function(1, lambda p: 0.)
-for marker in (2, 3, 4, 5):
-    res_twophase.apply_flux_boundary_from_function(marker, lambda p: np.array([0., 0., 0.]))
-
-res_twophase.set_initial_p_o(np.array([100.] * mesh.get_number_of_cells()))
-res_twophase.set_initial_s_w(np.array([0.] * mesh.get_number_of_cells()))
-res_twophase.set_porosities(np.array([.2] * mesh.get_number_of_cells()))
-
-res_twophase.set_viscosity_water(8.90e-4)
-res_twophase.set_viscosity_oil(8.90e-4 * 2.)
-res_twophase.set_compressibility_water(0.)
-res_twophase.set_compressibility_oil(0.)
-res_twophase.set_ref_density_water(1000.)
-res_twophase.set_ref_density_oil(1000.)
-res_twophase.set_ref_pressure_oil(0.)
-res_twophase.set_ref_pressure_water(0.)
-res_twophase.set_residual_saturation_water(.0)
-res_twophase.set_residual_saturation_oil(.2)
-res_twophase.set_corey_relperm(2., 2.)
+model.set_initial_p_o(np.full(cells, 100.))
+model.set_initial_s_w(np.zeros(cells))
+model.set_porosities(np.full(cells, .2))
+for setter, value in ((model.set_viscosity_water, 8.90e-4), (model.set_viscosity_oil, 2. * 8.90e-4),
+                      (model.set_compressibility_water, 0.), (model.set_compressibility_oil, 0.),
+                      (model.set_ref_density_water, 1000.), (model.set_ref_density_oil, 1000.),
+                      (model.set_ref_pressure_oil, 0.), (model.set_ref_pressure_water, 0.),
+                      (model.set_residual_saturation_water, 0.), (model.set_residual_saturation_oil, .2)):
+    setter(value)
+model.set_corey_relperm(2., 2.)
 
 delta_t, rate = 200000., 3. / (60. * 60. * 24)
-res_twophase.set_time_step_size(delta_t)
-res_twophase.add_rate_well(rate, 0., 0, "WELL1")
-res_twophase.set_output_frequency(10 ** 9)      # no VTK files from an example
-res_twophase.set_number_of_time_steps(steps)
+model.set_time_step_size(delta_t)
+model.add_rate_well(rate, 0., 0, "WELL1")            # water injector in the first cell
+model.set_output_frequency(10 ** 9)                  # no VTK files from an example
+model.set_number_of_time_steps(steps)
+model.initialize_system()
+model.start_solving()
 
-res_twophase.initialize_system()
-res_twophase.start_solving()
-
-s_w = np.asarray(res_twophase.current_s_w)
+s_w = np.asarray(model.current_s_w)
 x = (np.arange(nx) + .5) * length / nx
 
 # analytic solution: f(S) with Corey(2, 2), S_or = 0.2, mu_o = 2 mu_w; the front saturation is Welge's tangent point
