@@ -1072,6 +1072,10 @@ class Mesh(object):
         from . import meshio
         meshio.save_mesh(self, output_file)
 
+    def save_cell(self, cell_index, output_file):
+        from . import meshio
+        meshio.save_cell(self, cell_index, output_file)
+
     def output_vtk_mesh(self, file_name, cell_values=[], cell_value_labels=[]):
         from . import meshio
         meshio.output_vtk_mesh(self, file_name, cell_values, cell_value_labels)

@@ -311,3 +311,28 @@ def output_cell_normals(mesh, file_name, cell_index):
     with open(file_name + ".vtk", "w") as out:
         _vtk_vertices(out, mesh.face_real_centroids[faces])
         _vtk_vectors(out, "OUT_NORMAL", orientation[:, None] * mesh.face_normals[faces])
+
+
+def save_cell(mesh, cell_index, output_file):
+    """One cell as a mesh of its own in the .mms format (mesh.py:766-809): its faces in cell order, its points
+    renumbered in order of first use, geometry and K carried over."""
+    single = mesh.__class__()
+    local = {}
+    faces = []
+    for f in mesh.get_cell(cell_index):
+        points = []
+        for p in mesh.get_face(f):
+            p = int(p)
+            if p not in local:
+                local[p] = single.add_point(mesh.get_point(p))
+            points.append(local[p])
+        g = single.add_face(points)
+        single.set_face_area(g, mesh.get_face_area(f))
+        single.set_face_normal(g, mesh.get_face_normal(f))
+        single.set_face_real_centroid(g, mesh.get_face_real_centroid(f))
+        faces.append(g)
+    single.add_cell(faces, [int(o) for o in mesh.get_cell_normal_orientation(cell_index)])
+    single.set_cell_k(0, mesh.get_cell_k(cell_index))
+    single.set_cell_volume(0, mesh.get_cell_volume(cell_index))
+    single.set_cell_real_centroid(0, mesh.get_cell_real_centroid(cell_index))
+    save_mesh(single, output_file)

@@ -383,3 +383,47 @@ def test_brick_kernels_stage_with_bulk_copies(lib_path):
     for k in brick3 + setup:
         assert counts[k]["UBLKCP"] >= 6 and counts[k]["SYNCS"] >= 6 and counts[k]["USETMAXREG"] == 2, (k, counts[k])
     assert all(counts[k]["LDGSTS"] == 0 for k in brick3)
+
+
+def test_save_cell_round_trip_and_reference_interchange(golden, tmp_path):
+    """Mesh.save_cell (mesh.py:766-809): one cut cell written as a mesh of its own and read back -- faces in cell
+    order, points renumbered by first use, geometry and K carried over; with the reference tree present, the same
+    cell saved by the UNMODIFIED reference loads into the same arrays."""
+    from mimpy_b200.mesh.mesh import Mesh
+
+    o = orc.omesh_from_dict(golden("cut_checker_4"))
+    m = mesh_from_omesh(o)
+    c = int(np.argmax(np.diff(o.cell_ptr)))          # a cell with the most faces
+    path = str(tmp_path / "cell.mms")
+    m.save_cell(c, open(path, "w"))
+    one = Mesh()
+    one.load_mesh(open(path))
+    faces = o.cell(c)
+    assert one.get_number_of_cells() == 1 and one.get_number_of_faces() == len(faces)
+    assert one.get_number_of_points() == len(np.unique(np.concatenate([o.face(f) for f in faces])))
+    assert list(one.get_cell(0)) == list(range(len(faces)))
+    assert np.array_equal(one.get_cell_normal_orientation(0), o.sigma(c))
+    for g, f in enumerate(faces):
+        assert np.array_equal(one.points[one.get_face(g)], o.points[o.face(f)])
+        assert one.get_face_area(g) == o.face_areas[f] and np.array_equal(one.get_face_normal(g), o.face_normals[f])
+    assert one.get_cell_volume(0) == o.cell_volume[c] and np.array_equal(one.get_cell_k(0).ravel(), o.cell_k[c])
+    volume, centroid = one.find_volume_centroid(0)
+    assert abs(volume - o.cell_volume[c]) <= 1e-14 and np.allclose(centroid, o.cell_centroid[c], rtol=0, atol=1e-13)
+    if os.path.isdir("/root/reference/mimpy"):
+        from oracle import ref_shim
+
+        ref = ref_shim.load_reference()
+        r = ref.mesh.Mesh()
+        r.load_mesh(open(str(_save_full(m, tmp_path))))
+        ref_path = str(tmp_path / "cell_ref.mms")
+        r.save_cell(c, open(ref_path, "wb"))
+        theirs = Mesh()
+        theirs.load_mesh(open(ref_path))
+        theirs.number_of_points = one.get_number_of_points()   # the reference writes its over-allocated point table
+        _assert_same_mesh(orc.OMesh.from_mesh(theirs), orc.OMesh.from_mesh(one), exact=True)
+
+
+def _save_full(m, tmp_path):
+    path = tmp_path / "full.mms"
+    m.save_mesh(open(str(path), "w"))
+    return path
