@@ -204,9 +204,14 @@ def load_mesh(mesh, input_file):
                 face_index, lagrange_index, orientation = [int(x) for x in next(lines).split()[:3]]
                 mesh.set_face_to_lagrange_pointer(face_index, orientation, lagrange_index)
         elif key == "LAGRANGE_TO_FACE_POINTERS":
+            # one (face, orientation) per line; a multiplier that balances several faces has several lines (the
+            # reference's loader passes the two integers to a setter that zips them, mesh.py:759-764, 1447-1455)
+            pairs = {}
             for _ in range(n):
                 lagrange_index, face_index, orientation = [int(x) for x in next(lines).split()[:3]]
-                mesh.set_lagrange_to_face_pointers(lagrange_index, face_index, orientation)
+                pairs.setdefault(lagrange_index, []).append((face_index, orientation))
+            for lagrange_index, entries in pairs.items():
+                mesh.set_lagrange_to_face_pointers(lagrange_index, [e[0] for e in entries], [e[1] for e in entries])
     nc = mesh.get_number_of_cells()
     if len(mesh.cell_domain) < nc:
         mesh.cell_domain = np.zeros(nc, dtype=int)

@@ -74,3 +74,22 @@ def test_multiplier_numbering_coupling_terms_and_solve_strategy(golden):
     x, info = gmres(k, g["rhs"], M=LinearOperator((n, n), matvec=pinv), rtol=1e-13, restart=200, maxiter=3)
     assert info == 0 and applications[0] <= 2 * len(cd) // 4 + 8
     assert np.linalg.norm(x - g["solution"]) <= 1e-12 * np.linalg.norm(g["solution"])
+
+
+def test_multiplier_mesh_survives_the_mms_round_trip(tmp_path):
+    """save_mesh / load_mesh with multiplier faces: faces of no cell, face -> multiplier pointers and multipliers that
+    balance TWO faces each (one LAGRANGE_TO_FACE_POINTERS line per pair)."""
+    from mimpy_b200.mesh.mesh import Mesh
+
+    m = mesh_from_omesh(orc.hex_mesh(cc.NX, cc.NY, cc.NZ, *cc.DIMS, k_array=cc.permeability()))
+    pairs, glue = cc.add_multipliers(m)
+    path = str(tmp_path / "glued.mms")
+    m.save_mesh(open(path, "w"))
+    m2 = Mesh()
+    m2.load_mesh(open(path))
+    a, b = orc.OMesh.from_mesh(m), orc.OMesh.from_mesh(m2)
+    for key in ("face_ptr", "face_points", "cell_ptr", "cell_faces", "cell_sigma", "face_areas", "face_to_cell"):
+        assert np.array_equal(getattr(a, key), getattr(b, key)), key
+    assert b.face_to_lagrange == a.face_to_lagrange and len(b.face_to_lagrange) == 2 * len(glue)
+    assert b.lagrange_to_face == a.lagrange_to_face and all(len(v) == 2 for v in b.lagrange_to_face.values())
+    assert m2.has_pointer_couplings()
