@@ -978,6 +978,35 @@ class Mesh(object):
         return new_cell
 
     # ---- many cells, one plane ----------------------------------------------------
+    def find_cells_crossed_by_plane(self, point_on_plane, plane_normal, inside=None, tol=1.e-8):
+        """Cells with at least one edge that crosses the plane -- at a point x with inside(x) true, when a bounded
+        piece of the plane is meant: `inside` maps an (m, 3) array of points in the plane to m booleans (a disc, an
+        ellipse, a polygon: what Fracture.is_point_on_frac decides in the reference's selection loop,
+        hexmeshwmsfracs.py:683-713).  All edges of the mesh at once; the result is what divide_cells_by_plane takes."""
+        p0 = np.asarray(point_on_plane, dtype=float)
+        nrm = np.asarray(plane_normal, dtype=float)
+        nrm = nrm / np.linalg.norm(nrm)
+        nf, nc = self.get_number_of_faces(), self.get_number_of_cells()
+        fptr, fdata = self.faces.compact()
+        fdata = np.asarray(fdata, dtype=np.int64)
+        lens = np.diff(fptr)
+        successor = np.arange(len(fdata)) + 1
+        successor[fptr[1:][lens > 0] - 1] = fptr[:-1][lens > 0]      # the loop of a face closes on its first point
+        a, b = fdata, fdata[successor]
+        distance = (self.points[:self.get_number_of_points()] - p0).dot(nrm)
+        da, db = distance[a], distance[b]
+        crossed = (da * db < 0.) & (np.abs(da) > tol) & (np.abs(db) > tol)
+        if inside is not None and crossed.any():
+            pa, pb = self.points[a[crossed]], self.points[b[crossed]]
+            x = pa + (da[crossed] / (da[crossed] - db[crossed]))[:, None] * (pb - pa)
+            keep = np.asarray(inside(x), dtype=bool)
+            crossed[np.nonzero(crossed)[0][~keep]] = False
+        face_hit = np.zeros(nf, dtype=bool)
+        face_hit[np.repeat(np.arange(nf), lens)[crossed]] = True
+        cptr, cdata = self.cells.compact()
+        cell_of_entry = np.repeat(np.arange(nc), np.diff(cptr))
+        return [int(c) for c in np.unique(cell_of_entry[face_hit[np.asarray(cdata, dtype=np.int64)]])]
+
     def divide_cells_by_plane(self, cell_indices, point_on_plane, plane_normal, tol=1.e-8):
         """Splits every cell of `cell_indices` (None: all cells) that the plane really crosses; returns
         {cell_index: new_cell_index}.  Cells that the plane only touches are left alone.

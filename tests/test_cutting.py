@@ -205,3 +205,32 @@ def test_random_and_degenerate_planes_keep_the_mesh_conforming():
                 n[int(rng.integers(0, 3))] = 0.
             m.divide_cells_by_plane(None, p, n)
         conforming(m, 1., UNIT)
+
+
+def test_cells_crossed_by_a_bounded_piece_of_the_plane():
+    """find_cells_crossed_by_plane with an `inside` predicate (a disc-shaped fracture): the same cells as the
+    reference's edge-by-edge selection loop (hexmeshwmsfracs.py:683-713) restated per cell, and cutting exactly those
+    cells leaves a conforming mesh whose uncut neighbours carry the split faces."""
+    n = 5
+    m = mesh_from_omesh(orc.hex_mesh(n, n, n, 1., 1., 1.))
+    p0, nrm = np.array([.5, .5, .45]), np.array([.3, .2, 1.])
+    nrm /= np.linalg.norm(nrm)
+    disc = lambda x: np.linalg.norm(x - p0, axis=1) < .3
+    cells = m.find_cells_crossed_by_plane(p0, nrm, inside=disc)
+    expected = []
+    for c in range(n ** 3):
+        hit = False
+        for f in m.get_cell(c):
+            loop = [int(q) for q in m.get_face(f)]
+            for a, b in zip(loop, loop[1:] + loop[:1]):
+                da, db = (m.get_point(a) - p0).dot(nrm), (m.get_point(b) - p0).dot(nrm)
+                if da * db < 0. and min(abs(da), abs(db)) > 1e-8:
+                    x = m.get_point(a) + da / (da - db) * (m.get_point(b) - m.get_point(a))
+                    hit = hit or bool(disc(x[None, :])[0])
+        if hit:
+            expected.append(c)
+    assert cells == expected and 0 < len(cells) < len(m.find_cells_crossed_by_plane(p0, nrm)) <= n * n * 2
+    new = m.divide_cells_by_plane(cells, p0, nrm)
+    assert sorted(new) == cells
+    conforming(m, 1., UNIT)
+    assert m.find_cells_crossed_by_plane(p0, nrm, inside=disc) == []      # nothing left to cut inside the disc
