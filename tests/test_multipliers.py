@@ -93,3 +93,47 @@ def test_multiplier_mesh_survives_the_mms_round_trip(tmp_path):
     assert b.face_to_lagrange == a.face_to_lagrange and len(b.face_to_lagrange) == 2 * len(glue)
     assert b.lagrange_to_face == a.lagrange_to_face and all(len(v) == 2 for v in b.lagrange_to_face.values())
     assert m2.has_pointer_couplings()
+
+
+def test_coupled_gmres_on_the_cpu_with_a_direct_inner_solve(golden):
+    """The product's coupled solver (mfd.coupled_gmres: flexible GMRES, blockdiag(K0, I) preconditioner, warm start)
+    driven on CPU tensors with SuperLU standing in for the hybridised device solve: the reference's solution of the
+    periodic / Lagrange system in about rank + 1 preconditioner applications."""
+    import contextlib
+    import types
+
+    import torch
+    import mimpy_b200.mfd.mfd as mfd
+
+    g = golden("multipliers_433")
+    n = len(g["rhs"])
+    k = sparse.csr_matrix((g["csr_data"], g["csr_indices"], g["csr_indptr"]), shape=(n, n))
+    e = sparse.coo_matrix((g["coupling_data"], (g["coupling_row"], g["coupling_col"])), shape=(n, n)).tocsr()
+    k0 = (k - e).tocsr()
+    k0.eliminate_zeros()
+    mult_rows = np.nonzero(np.diff(k0.indptr) == 0)[0]          # rows that hold coupling terms only
+    assert len(mult_rows) == 21
+    dev2ref = np.setdiff1d(np.arange(n), mult_rows)
+    lu = splu(k0[dev2ref][:, dev2ref].tocsc())
+    calls = [0]
+
+    class Inner(object):
+        def solve(self, v, rtol, maxit):
+            calls[0] += 1
+            info = types.SimpleNamespace(iterations=1, ms_total=0., residual=0., rhs_norm=float(torch.linalg.norm(v)))
+            return torch.as_tensor(lu.solve(v.numpy())), info
+
+    ctx = types.SimpleNamespace(device=torch.device("cpu"), on_stream=contextlib.nullcontext)
+    apply_k = lambda v: torch.as_tensor(k @ v.numpy())
+    rhs = torch.as_tensor(g["rhs"])
+    x, info = mfd.coupled_gmres(ctx, apply_k, Inner(), rhs, 1e-13, 100, mult=(dev2ref, n, mult_rows))
+    assert np.linalg.norm(x.numpy() - g["solution"]) <= 1e-11 * np.linalg.norm(g["solution"])
+    assert info.iterations == calls[0] <= 50 and info.residual <= 1e-12 * info.rhs_norm
+    # warm start from a nearby state: fewer applications; from the solution itself: none
+    first = calls[0]
+    x2, _ = mfd.coupled_gmres(ctx, apply_k, Inner(), rhs, 1e-13, 100, mult=(dev2ref, n, mult_rows),
+                              x0=x + 1e-6 * torch.as_tensor(np.cos(np.arange(n, dtype=float))))
+    assert np.linalg.norm(x2.numpy() - g["solution"]) <= 1e-11 * np.linalg.norm(g["solution"]) and calls[0] - first <= first
+    before = calls[0]
+    x3, info3 = mfd.coupled_gmres(ctx, apply_k, Inner(), rhs, 1e-10, 100, mult=(dev2ref, n, mult_rows), x0=x)
+    assert calls[0] == before and info3.iterations == 0 and torch.equal(x3, x)
